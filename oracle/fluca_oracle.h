@@ -1,0 +1,106 @@
+/*
+ * oracle/fluca_oracle.h -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement (plain C + OpenMP, no PETSc) of the Navier-Stokes time step of
+ * thecasterian/fluca: NS type "cnlinear" + PC "abf" on a MeshCart mesh.  It follows
+ *   fluca/src/ns/utils/cartdiscret.c            (24 closed-form stencil formulas)
+ *   fluca/src/ns/impl/linearcn/cnlinearcart2d.c (operators, BC vectors, RHS, step; 2-D)
+ *   fluca/src/ns/impl/linearcn/cnlinearcart3d.c (same, 3-D)
+ *   fluca/src/ns/utils/abfpc/abfpc.c:48-182     (PCSetUp_ABF / PCApply_ABF = the fractional step)
+ *   fluca/src/ns/interface/nsbasic.c:215-251, nssol.c:13-30 (null space, zero guess, tolerances)
+ * of /root/reference.  The arithmetic the reference delegates to PETSc (>= 3.23, un-vendored,
+ * unpinned: fluca/CMakeLists.txt:9-11) -- MatMult, MatMatMult, GMRES(30), ILU(0)/block-Jacobi --
+ * is restated in oracle/src/sparse.c from the published algorithms.
+ *
+ * PARITY STATUS: *parity unpinned* for the NS step itself.  The reference registers no NS test
+ * and stores no NS golden output, and it cannot be built here (needs PETSc, MPI,
+ * HDF5, CGNS).  What IS pinned: the stencil coefficients, against the reference's own fd golden
+ * outputs (tests/golden/fd_coefficients.json, extracted from fluca/tests/fd/output/ *.out), and
+ * the Taylor-Green analytic solution of fluca/tests/taylor_green_vortex.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * use this library.  The product path (fluca_b200/) never links or loads it.
+ */
+#pragma once
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* same numeric values as NSBoundaryConditionType, fluca/include/flucansbc.h:5-11 */
+enum { ORC_BC_NONE = 0, ORC_BC_VELOCITY = 1, ORC_BC_PRESSURE_OUTLET = 2, ORC_BC_PERIODIC = 3, ORC_BC_SYMMETRY = 4 };
+
+/* same signature as NSBoundaryConditionFunction, flucansbc.h:14 (PetscErrorCode -> int) */
+typedef int (*OrcBCFn)(int dim, double t, const double x[], double val[], void *ctx);
+
+/* same fields as NSBoundaryCondition, flucansbc.h:16-22 */
+typedef struct {
+  int     type;
+  OrcBCFn velocity;
+  void   *ctx_velocity;
+  OrcBCFn pressure;
+  void   *ctx_pressure;
+} OrcBC;
+
+typedef struct Orc Orc;
+
+typedef struct {
+  int    mode;            /* 0 = Mode A: outer GMRES(30) on the coupled system, PC = ABF (reference default);
+                             1 = Mode B: one ABF application (-ns_ksp_type preonly) = classical fractional step */
+  double outer_rtol;      /* nssol.c:24: 1e-5 */
+  int    outer_maxit;     /* PETSc default 10000 */
+  double mom_rtol;        /* inner KSP "abf_momentum_": PETSc default 1e-5 */
+  double schur_rtol;      /* inner KSP "abf_schur_":    PETSc default 1e-5 */
+  int    inner_maxit;     /* PETSc default 10000 */
+  int    ilu_blocks;      /* 1 = serial ILU(0); P = bjacobi+ILU(0) of a P-rank run */
+  int    exact_schur;     /* 0: S by sparse products as abfpc.c:151-170; 1: S = -D*Gst assembled directly */
+  int    quirk_bcg_scale; /* 1 (default): 3-D RHS scales the outlet gradient BC vector by 1 like
+                             cnlinearcart3d.c:2977; 0: use dt/rho as the 2-D file does */
+} OrcOptions;
+
+typedef struct {
+  int    outer_its, mom_its, schur_its; /* totals over the step */
+  int    abf_applies;
+  int    converged;
+  double outer_rnorm0, outer_rnorm;
+  int    nhist;
+  double hist[512]; /* outer KSP true-residual history */
+} OrcStepInfo;
+
+void orc_default_options(OrcOptions *o);
+
+/* n[d] cells, periodic[d] flags, xf[d] = n[d]+1 face coordinates (centres are face midpoints,
+ * cart.c:497).  bcs ordered LEFT,RIGHT,DOWN,UP,BACK,FRONT (cart.c:564-591). */
+Orc *orc_create(int dim, const int n[3], const int periodic[3], const double *const xf[3], double rho, double mu, double dt, const OrcBC bcs[6]);
+void orc_destroy(Orc *o);
+
+/* sizes: ncell, nface[d] */
+void orc_sizes(const Orc *o, long *ncell, long nface[3]);
+
+/* state, SoA: v[c*ncell + cell]; U_d[face]; cell = i + nx*(j + ny*k);
+ * x-face = i + nfx*(j + ny*k), y-face = i + nx*(j + nfy*k), z-face = i + nx*(j + ny*k) */
+void orc_set_state(Orc *o, const double *v, const double *const U[3], const double *p, const double *phalf, int step, double t);
+void orc_get_state(const Orc *o, double *v, double *const U[3], double *p, double *phalf, int *step, double *t);
+
+/* one NSStep (nsbasic.c:276-299 + cnlinearcart{2,3}d.c NSStep_CNLinear_*_Internal) */
+int orc_step(Orc *o, const OrcOptions *opt, OrcStepInfo *info);
+
+/* ---- operator-level access, for tests ---- */
+/* names: "G" (scaled dt/rho), "L", "T", "B", "D", "Gst" (scaled dt/rho), "A", "C", "S", "negR".
+ * A, C, S refer to the operators of the most recent orc_prepare_step / orc_step. Returns 0 or -1. */
+int  orc_matrix(const Orc *o, const char *name, int *nrows, int *ncols, long *nnz, const int **ptr, const int **idx, const double **val);
+/* builds v0interp, A and the RHS b = (r_mom, r_int, r_con) for the current state (NSFormFunction +
+ * NSFormJacobian(UPDATE)); rhs has length dim*ncell + sum(nface) + ncell */
+void orc_prepare_step(Orc *o, const OrcOptions *opt, double *rhs);
+/* one PCApply_ABF (abfpc.c:48-111): x = ABF(b); sizes as rhs */
+void orc_abf_apply(Orc *o, const OrcOptions *opt, const double *b, double *x, OrcStepInfo *info);
+/* 1-D stencil formulas of cartdiscret.c, by name, on an explicit coordinate tuple; returns ncols */
+int orc_formula(const char *name, const double *xs, double h, double vf, double w[4], int off[4]);
+
+/* built-in BC callbacks for timing runs (ctx = double[3] constant value) */
+int orc_bc_constant(int dim, double t, const double x[], double val[], void *ctx);
+/* pressure flavour: ctx = double[1] */
+int orc_bc_constant_pressure(int dim, double t, const double x[], double val[], void *ctx);
+
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,1274 @@
+/*
+ * oracle/src/ns.c -- TEST INFRASTRUCTURE (CPU oracle), NOT PRODUCT CODE.  See ../fluca_oracle.h.
+ *
+ * Restates, with explicitly assembled sparse matrices exactly like the reference, the NS type
+ * "cnlinear" of thecasterian/fluca.  Citations are relative to /root/reference/fluca/src/ns/.
+ * The reference has one hand-unrolled copy of every loop per direction and per dimension
+ * (impl/linearcn/cnlinearcart2d.c, cnlinearcart3d.c); here each operator is written once,
+ * looped over the direction d and the (lower, upper) side, which is the same arithmetic.
+ *
+ * PARITY STATUS: parity unpinned for the NS step (no reference NS golden output exists; the
+ * reference cannot be built here).  Coefficients are pinned by tests/golden/fd_coefficients.json.
+ */
+#include "../fluca_oracle.h"
+#include "sparse.h"
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------ 1-D formulas
+ * utils/cartdiscret.c.  Each returns weights; the column offsets are fixed by the formula. */
+typedef struct {
+  int    n;
+  int    off[4];
+  double w[4];
+} St;
+
+static St st_none(void)
+{
+  St s;
+  memset(&s, 0, sizeof s);
+  return s;
+}
+
+/* cartdiscret.c:3-24  first derivative, forward, no condition: cells P, E, EE */
+static St d1_fwd_nocond(double xP, double xE, double xEE)
+{
+  St     s  = st_none();
+  double h1 = xE - xP, h2 = xEE - xP;
+  s.n      = 3;
+  s.off[0] = 0, s.off[1] = 1, s.off[2] = 2;
+  s.w[0] = -(h1 + h2) / (h1 * h2);
+  s.w[1] = -h2 / (h1 * (h1 - h2));
+  s.w[2] = h1 / (h2 * (h1 - h2));
+  return s;
+}
+/* cartdiscret.c:26-43  forward, Dirichlet value at wall w: cells P, E */
+static St d1_fwd_dirichlet(double xw, double xP, double xE)
+{
+  St     s  = st_none();
+  double h1 = xP - xw, h2 = xE - xP;
+  s.n      = 2;
+  s.off[0] = 0, s.off[1] = 1;
+  s.w[0] = (h2 - h1) / (h1 * h2);
+  s.w[1] = h1 / (h2 * (h1 + h2));
+  return s;
+}
+/* cartdiscret.c:45-62  forward, zero gradient at wall */
+static St d1_fwd_neumann(double xw, double xP, double xE)
+{
+  St     s  = st_none();
+  double h1 = xP - xw, h2 = xE - xP;
+  s.n      = 2;
+  s.off[0] = 0, s.off[1] = 1;
+  s.w[0] = -2. * h1 / (h2 * (2. * h1 + h2));
+  s.w[1] = 2. * h1 / (h2 * (2. * h1 + h2));
+  return s;
+}
+/* cartdiscret.c:64-77  central: cells W, E */
+static St d1_central(double xW, double xE)
+{
+  St s     = st_none();
+  s.n      = 2;
+  s.off[0] = -1, s.off[1] = 1;
+  s.w[0] = -1. / (xE - xW);
+  s.w[1] = 1. / (xE - xW);
+  return s;
+}
+/* cartdiscret.c:79-100  backward, no condition: cells WW, W, P */
+static St d1_bwd_nocond(double xWW, double xW, double xP)
+{
+  St     s  = st_none();
+  double h1 = xP - xW, h2 = xP - xWW;
+  s.n      = 3;
+  s.off[0] = -2, s.off[1] = -1, s.off[2] = 0;
+  s.w[0] = -h1 / (h2 * (h1 - h2));
+  s.w[1] = h2 / (h1 * (h1 - h2));
+  s.w[2] = (h1 + h2) / (h1 * h2);
+  return s;
+}
+/* cartdiscret.c:102-119 */
+static St d1_bwd_dirichlet(double xW, double xP, double xe)
+{
+  St     s  = st_none();
+  double h1 = xe - xP, h2 = xP - xW;
+  s.n      = 2;
+  s.off[0] = -1, s.off[1] = 0;
+  s.w[0] = -h1 / (h2 * (h1 + h2));
+  s.w[1] = (h1 - h2) / (h1 * h2);
+  return s;
+}
+/* cartdiscret.c:120-137 */
+static St d1_bwd_neumann(double xW, double xP, double xe)
+{
+  St     s  = st_none();
+  double h1 = xe - xP, h2 = xP - xW;
+  s.n      = 2;
+  s.off[0] = -1, s.off[1] = 0;
+  s.w[0] = -2. * h1 / (h2 * (2. * h1 + h2));
+  s.w[1] = 2. * h1 / (h2 * (2. * h1 + h2));
+  return s;
+}
+/* cartdiscret.c:139-165  second derivative, forward, no condition: P, E, EE, EEE (unused by NS) */
+static St d2_fwd_nocond(double xP, double xE, double xEE, double xEEE)
+{
+  St     s  = st_none();
+  double h1 = xE - xP, h2 = xEE - xP, h3 = xEEE - xP;
+  s.n = 4;
+  for (int q = 0; q < 4; ++q) s.off[q] = q;
+  s.w[0] = 2. * (h1 + h2 + h3) / (h1 * h2 * h3);
+  s.w[1] = -2. * (h2 + h3) / (h1 * (h1 - h2) * (h1 - h3));
+  s.w[2] = 2. * (h1 + h3) / (h2 * (h1 - h2) * (h2 - h3));
+  s.w[3] = -2. * (h1 + h2) / (h3 * (h1 - h3) * (h2 - h3));
+  return s;
+}
+/* cartdiscret.c:167-189  forward, Dirichlet at wall: P, E, EE */
+static St d2_fwd_dirichlet(double xw, double xP, double xE, double xEE)
+{
+  St     s  = st_none();
+  double h1 = xP - xw, h2 = xE - xP, h3 = xEE - xP;
+  s.n      = 3;
+  s.off[0] = 0, s.off[1] = 1, s.off[2] = 2;
+  s.w[0] = 2. * (h1 - h2 - h3) / (h1 * h2 * h3);
+  s.w[1] = 2. * (h1 - h3) / (h2 * (h1 + h2) * (h2 - h3));
+  s.w[2] = 2. * (h2 - h1) / (h3 * (h1 + h3) * (h2 - h3));
+  return s;
+}
+/* cartdiscret.c:191-208  forward, zero gradient at wall: P, E */
+static St d2_fwd_neumann(double xw, double xP, double xe, double xE)
+{
+  St     s  = st_none();
+  double h1 = xE - xP, h2 = xe - xw;
+  (void)xP;
+  s.n      = 2;
+  s.off[0] = 0, s.off[1] = 1;
+  s.w[0] = -1. / (h1 * h2);
+  s.w[1] = 1. / (h1 * h2);
+  return s;
+}
+/* cartdiscret.c:210-232  central: W, P, E with faces w, e */
+static St d2_central(double xW, double xw, double xP, double xe, double xE)
+{
+  St     s  = st_none();
+  double h1 = xP - xW, h2 = xE - xP, h3 = xe - xw;
+  s.n      = 3;
+  s.off[0] = -1, s.off[1] = 0, s.off[2] = 1;
+  s.w[0] = 1. / (h1 * h3);
+  s.w[1] = -(1. / (h1 * h3) + 1. / (h2 * h3));
+  s.w[2] = 1. / (h2 * h3);
+  return s;
+}
+/* cartdiscret.c:262-284  backward, Dirichlet at wall: WW, W, P */
+static St d2_bwd_dirichlet(double xWW, double xW, double xP, double xe)
+{
+  St     s  = st_none();
+  double h1 = xe - xP, h2 = xP - xW, h3 = xP - xWW;
+  s.n      = 3;
+  s.off[0] = -2, s.off[1] = -1, s.off[2] = 0;
+  s.w[0] = 2. * (h2 - h1) / (h3 * (h1 + h3) * (h2 - h3));
+  s.w[1] = 2. * (h1 - h3) / (h2 * (h1 + h2) * (h2 - h3));
+  s.w[2] = 2. * (h1 - h2 - h3) / (h1 * h2 * h3);
+  return s;
+}
+/* cartdiscret.c:286-303  backward, zero gradient at wall: W, P */
+static St d2_bwd_neumann(double xW, double xw, double xP, double xe)
+{
+  St     s  = st_none();
+  double h1 = xP - xW, h2 = xe - xw;
+  s.n      = 2;
+  s.off[0] = -1, s.off[1] = 0;
+  s.w[0] = 1. / (h1 * h2);
+  s.w[1] = -1. / (h1 * h2);
+  return s;
+}
+/* cartdiscret.c:305-318  convective flux through the lower face, linear interpolation W, P */
+static St conv_prev(double xW, double xw, double xP, double h, double vf)
+{
+  St s     = st_none();
+  s.n      = 2;
+  s.off[0] = -1, s.off[1] = 0;
+  s.w[0] = -0.5 * vf / h * (xP - xw) / (xP - xW);
+  s.w[1] = -0.5 * vf / h * (xw - xW) / (xP - xW);
+  return s;
+}
+/* cartdiscret.c:320-333  upper face, linear interpolation P, E */
+static St conv_next(double xP, double xe, double xE, double h, double vf)
+{
+  St s     = st_none();
+  s.n      = 2;
+  s.off[0] = 0, s.off[1] = 1;
+  s.w[0] = 0.5 * vf / h * (xE - xe) / (xE - xP);
+  s.w[1] = 0.5 * vf / h * (xe - xP) / (xE - xP);
+  return s;
+}
+/* cartdiscret.c:335-352  lower boundary face, zero-gradient extrapolation from P, E.
+ * NOTE (kept on purpose): the two weights sum to +0.5*vf/h, i.e. the flux through a LOWER face
+ * enters with the sign of an UPPER face.  Restated as the reference has it. */
+static St conv_fwd_extrap(double xw, double xP, double xE, double h, double vf)
+{
+  St     s  = st_none();
+  double h1 = xP - xw, h2 = xE - xw;
+  s.n      = 2;
+  s.off[0] = 0, s.off[1] = 1;
+  s.w[0] = -0.5 * vf / h * (h2 * h2) / ((h1 + h2) * (h1 - h2));
+  s.w[1] = 0.5 * vf / h * (h1 * h1) / ((h1 + h2) * (h1 - h2));
+  return s;
+}
+/* cartdiscret.c:354-371  upper boundary face, extrapolation from W, P */
+static St conv_bwd_extrap(double xW, double xP, double xe, double h, double vf)
+{
+  St     s  = st_none();
+  double h1 = xe - xP, h2 = xe - xW;
+  s.n      = 2;
+  s.off[0] = -1, s.off[1] = 0;
+  s.w[0] = 0.5 * vf / h * (h1 * h1) / ((h1 + h2) * (h1 - h2));
+  s.w[1] = -0.5 * vf / h * (h2 * h2) / ((h1 + h2) * (h1 - h2));
+  return s;
+}
+/* cartdiscret.c:373-386  linear interpolation to face w from W, P */
+static St lin_interp(double xW, double xw, double xP)
+{
+  St s     = st_none();
+  s.n      = 2;
+  s.off[0] = -1, s.off[1] = 0;
+  s.w[0] = (xP - xw) / (xP - xW);
+  s.w[1] = (xw - xW) / (xP - xW);
+  return s;
+}
+/* cartdiscret.c:388-405  value at lower wall by zero-gradient extrapolation from P, E */
+static St lin_fwd_extrap(double xw, double xP, double xE)
+{
+  St     s  = st_none();
+  double h1 = xP - xw, h2 = xE - xw;
+  s.n      = 2;
+  s.off[0] = 0, s.off[1] = 1;
+  s.w[0] = -(h2 * h2) / ((h1 + h2) * (h1 - h2));
+  s.w[1] = (h1 * h1) / ((h1 + h2) * (h1 - h2));
+  return s;
+}
+/* cartdiscret.c:406-423  value at upper wall from WW, W (row index is the face = cell index + 1) */
+static St lin_bwd_extrap(double xWW, double xW, double xw)
+{
+  St     s  = st_none();
+  double h1 = xw - xW, h2 = xw - xWW;
+  s.n      = 2;
+  s.off[0] = -2, s.off[1] = -1;
+  s.w[0] = (h1 * h1) / ((h1 + h2) * (h1 - h2));
+  s.w[1] = -(h2 * h2) / ((h1 + h2) * (h1 - h2));
+  return s;
+}
+/* cartdiscret.c:425-442  face-normal derivative at the lower wall, Dirichlet value at the wall */
+static St fn_fwd_dirichlet(double xw, double xP, double xE)
+{
+  St     s  = st_none();
+  double h1 = xP - xw, h2 = xE - xw;
+  s.n      = 2;
+  s.off[0] = 0, s.off[1] = 1;
+  s.w[0] = -h2 / (h1 * (h1 - h2));
+  s.w[1] = h1 / (h2 * (h1 - h2));
+  return s;
+}
+/* cartdiscret.c:444-457  face-normal derivative at an interior face: W, P */
+static St fn_central(double xW, double xP)
+{
+  St s     = st_none();
+  s.n      = 2;
+  s.off[0] = -1, s.off[1] = 0;
+  s.w[0] = -1. / (xP - xW);
+  s.w[1] = 1. / (xP - xW);
+  return s;
+}
+/* cartdiscret.c:459-476  face-normal derivative at the upper wall: WW, W */
+static St fn_bwd_dirichlet(double xWW, double xW, double xw)
+{
+  St     s  = st_none();
+  double h1 = xw - xW, h2 = xw - xWW;
+  s.n      = 2;
+  s.off[0] = -2, s.off[1] = -1;
+  s.w[0] = -h1 / (h2 * (h1 - h2));
+  s.w[1] = h2 / (h1 * (h1 - h2));
+  return s;
+}
+
+int orc_formula(const char *name, const double *x, double h, double vf, double w[4], int off[4])
+{
+  St s = st_none();
+  if (!strcmp(name, "d1_fwd_nocond")) s = d1_fwd_nocond(x[0], x[1], x[2]);
+  else if (!strcmp(name, "d1_fwd_dirichlet")) s = d1_fwd_dirichlet(x[0], x[1], x[2]);
+  else if (!strcmp(name, "d1_fwd_neumann")) s = d1_fwd_neumann(x[0], x[1], x[2]);
+  else if (!strcmp(name, "d1_central")) s = d1_central(x[0], x[1]);
+  else if (!strcmp(name, "d1_bwd_nocond")) s = d1_bwd_nocond(x[0], x[1], x[2]);
+  else if (!strcmp(name, "d1_bwd_dirichlet")) s = d1_bwd_dirichlet(x[0], x[1], x[2]);
+  else if (!strcmp(name, "d1_bwd_neumann")) s = d1_bwd_neumann(x[0], x[1], x[2]);
+  else if (!strcmp(name, "d2_fwd_nocond")) s = d2_fwd_nocond(x[0], x[1], x[2], x[3]);
+  else if (!strcmp(name, "d2_fwd_dirichlet")) s = d2_fwd_dirichlet(x[0], x[1], x[2], x[3]);
+  else if (!strcmp(name, "d2_fwd_neumann")) s = d2_fwd_neumann(x[0], x[1], x[2], x[3]);
+  else if (!strcmp(name, "d2_central")) s = d2_central(x[0], x[1], x[2], x[3], x[4]);
+  else if (!strcmp(name, "d2_bwd_dirichlet")) s = d2_bwd_dirichlet(x[0], x[1], x[2], x[3]);
+  else if (!strcmp(name, "d2_bwd_neumann")) s = d2_bwd_neumann(x[0], x[1], x[2], x[3]);
+  else if (!strcmp(name, "conv_prev")) s = conv_prev(x[0], x[1], x[2], h, vf);
+  else if (!strcmp(name, "conv_next")) s = conv_next(x[0], x[1], x[2], h, vf);
+  else if (!strcmp(name, "conv_fwd_extrap")) s = conv_fwd_extrap(x[0], x[1], x[2], h, vf);
+  else if (!strcmp(name, "conv_bwd_extrap")) s = conv_bwd_extrap(x[0], x[1], x[2], h, vf);
+  else if (!strcmp(name, "lin_interp")) s = lin_interp(x[0], x[1], x[2]);
+  else if (!strcmp(name, "lin_fwd_extrap")) s = lin_fwd_extrap(x[0], x[1], x[2]);
+  else if (!strcmp(name, "lin_bwd_extrap")) s = lin_bwd_extrap(x[0], x[1], x[2]);
+  else if (!strcmp(name, "fn_fwd_dirichlet")) s = fn_fwd_dirichlet(x[0], x[1], x[2]);
+  else if (!strcmp(name, "fn_central")) s = fn_central(x[0], x[1]);
+  else if (!strcmp(name, "fn_bwd_dirichlet")) s = fn_bwd_dirichlet(x[0], x[1], x[2]);
+  else return -1;
+  for (int q = 0; q < 4; ++q) {
+    w[q]   = s.w[q];
+    off[q] = s.off[q];
+  }
+  return s.n;
+}
+
+/* ------------------------------------------------------------------ grid and state */
+struct Orc {
+  int     dim, n[3], per[3], nf[3];
+  long    N, NF[3], foff[3], NFtot;
+  double *xf[3], *xc[3], len[3];
+  double  rho, mu, dt;
+  OrcBC   bcs[6];
+  int     has_outlet; /* nsbasic.c:215-244: no null space if any boundary is an outlet */
+
+  /* state */
+  double *v, *U, *p, *phalf;
+  int     step;
+  double  t;
+  /* time-n copies (ns->sol0, nsbasic.c:281-282) and v0interp (cnlinearcart2d.c:1947-1957) */
+  double *v0, *U0, *p0, *v0interp;
+
+  /* constant operators (NS_INIT_JACOBIAN branch, cnlinearcart2d.c:2010-2054) */
+  Csr *G, *negT, *L, *Gst, *negR, *D, *B;
+  /* per-step */
+  Csr    *C, *A, *S;
+  BJIlu0 *iluA, *iluS;
+  int     mom_its, schur_its, abf_applies;
+  const OrcOptions *opt;
+};
+
+static double XF(const Orc *g, int d, int i)
+{
+  int n = g->n[d];
+  if (i < 0) return g->xf[d][i + n] - g->len[d];
+  if (i > n) return g->xf[d][i - n] + g->len[d];
+  return g->xf[d][i];
+}
+static double XC(const Orc *g, int d, int i)
+{
+  int n = g->n[d];
+  if (i < 0) return g->xc[d][i + n] - g->len[d];
+  if (i >= n) return g->xc[d][i - n] + g->len[d];
+  return g->xc[d][i];
+}
+static int wrap(int i, int n)
+{
+  return ((i % n) + n) % n;
+}
+static long cell_at(const Orc *g, const int ijk[3])
+{
+  int q[3];
+  for (int d = 0; d < 3; ++d) {
+    q[d] = g->per[d] ? wrap(ijk[d], g->n[d]) : ijk[d];
+    if (q[d] < 0 || q[d] >= g->n[d]) {
+      fprintf(stderr, "oracle: cell index out of range\n");
+      abort();
+    }
+  }
+  return q[0] + (long)g->n[0] * (q[1] + (long)g->n[1] * q[2]);
+}
+/* face of direction d at lattice position ijk (ijk[d] is the face index) */
+static long face_at(const Orc *g, int d, const int ijk[3])
+{
+  int  q[3], ext[3];
+  for (int e = 0; e < 3; ++e) {
+    ext[e] = (e == d) ? g->nf[d] : g->n[e];
+    q[e]   = g->per[e] ? wrap(ijk[e], g->n[e]) : ijk[e];
+    if (q[e] < 0 || q[e] >= ext[e]) {
+      fprintf(stderr, "oracle: face index out of range\n");
+      abort();
+    }
+  }
+  return g->foff[d] + q[0] + (long)ext[0] * (q[1] + (long)ext[1] * q[2]);
+}
+static long vdof(const Orc *g, int c, const int ijk[3])
+{
+  return c * g->N + cell_at(g, ijk);
+}
+/* Vdm dof: component c interpolated to faces of direction d */
+static long vbar_at(const Orc *g, int c, int d, const int ijk[3])
+{
+  return (long)c * g->NFtot + face_at(g, d, ijk);
+}
+
+#define FOR_CELLS(g, ijk) \
+  for (ijk[2] = 0; ijk[2] < (g)->n[2]; ++ijk[2]) \
+    for (ijk[1] = 0; ijk[1] < (g)->n[1]; ++ijk[1]) \
+      for (ijk[0] = 0; ijk[0] < (g)->n[0]; ++ijk[0])
+
+#define FOR_FACES(g, d, ijk) \
+  for (ijk[2] = 0; ijk[2] < ((d) == 2 ? (g)->nf[2] : (g)->n[2]); ++ijk[2]) \
+    for (ijk[1] = 0; ijk[1] < ((d) == 1 ? (g)->nf[1] : (g)->n[1]); ++ijk[1]) \
+      for (ijk[0] = 0; ijk[0] < ((d) == 0 ? (g)->nf[0] : (g)->n[0]); ++ijk[0])
+
+static void add_cells(Coo *M, long row, long colbase_comp, const Orc *g, const St *s, int d, const int ijk[3])
+{
+  for (int q = 0; q < s->n; ++q) {
+    int c[3] = {ijk[0], ijk[1], ijk[2]};
+    c[d] += s->off[q];
+    coo_add(M, (int)row, (int)(colbase_comp + cell_at(g, c)), s->w[q]);
+  }
+}
+
+static void bc_point(const Orc *g, int b, const int ijk[3], double xb[3])
+{
+  int d = b / 2, hi = b % 2;
+  for (int e = 0; e < 3; ++e) xb[e] = (e < g->dim) ? XC(g, e, ijk[e]) : 0.;
+  xb[d] = hi ? XF(g, d, g->n[d]) : XF(g, d, 0);
+}
+static void bc_velocity(const Orc *g, int b, double t, const int ijk[3], double vb[3])
+{
+  double xb[3];
+  bc_point(g, b, ijk, xb);
+  vb[0] = vb[1] = vb[2] = 0.;
+  if (!g->bcs[b].velocity) {
+    fprintf(stderr, "oracle: velocity callback missing on boundary %d\n", b);
+    abort();
+  }
+  g->bcs[b].velocity(g->dim, t, xb, vb, g->bcs[b].ctx_velocity);
+}
+static double bc_pressure(const Orc *g, int b, double t, const int ijk[3])
+{
+  double xb[3], pb = 0.;
+  bc_point(g, b, ijk, xb);
+  if (!g->bcs[b].pressure) {
+    fprintf(stderr, "oracle: pressure callback missing on boundary %d\n", b);
+    abort();
+  }
+  g->bcs[b].pressure(g->dim, t, xb, &pb, g->bcs[b].ctx_pressure);
+  return pb;
+}
+
+/* loop over the cells adjacent to boundary b (the reference's "for (j...) row.i = 0" loops) */
+#define FOR_BOUNDARY_CELLS(g, b, ijk) \
+  for (ijk[2] = ((b) / 2 == 2 ? ((b) % 2 ? (g)->n[2] - 1 : 0) : 0); ijk[2] < ((b) / 2 == 2 ? ((b) % 2 ? (g)->n[2] : 1) : (g)->n[2]); ++ijk[2]) \
+    for (ijk[1] = ((b) / 2 == 1 ? ((b) % 2 ? (g)->n[1] - 1 : 0) : 0); ijk[1] < ((b) / 2 == 1 ? ((b) % 2 ? (g)->n[1] : 1) : (g)->n[1]); ++ijk[1]) \
+      for (ijk[0] = ((b) / 2 == 0 ? ((b) % 2 ? (g)->n[0] - 1 : 0) : 0); ijk[0] < ((b) / 2 == 0 ? ((b) % 2 ? (g)->n[0] : 1) : (g)->n[0]); ++ijk[0])
+
+static void bad_bc(int b)
+{
+  fprintf(stderr, "oracle: unsupported boundary condition type on boundary %d\n", b);
+  abort();
+}
+
+/* ------------------------------------------------------------------ operators */
+
+/* ComputePressureGradientOperator_Private, cnlinearcart2d.c:4-153 / cnlinearcart3d.c:4-217 */
+static Csr *build_G(const Orc *g)
+{
+  Coo *M = coo_new((int)(g->dim * g->N), (int)g->N);
+  int  ijk[3];
+  for (int d = 0; d < g->dim; ++d) FOR_CELLS(g, ijk)
+    {
+      int i = ijk[d], n = g->n[d];
+      St  s;
+      if (i == 0) {
+        switch (g->bcs[2 * d].type) {
+        case ORC_BC_VELOCITY: s = d1_fwd_nocond(XC(g, d, i), XC(g, d, i + 1), XC(g, d, i + 2)); break;
+        case ORC_BC_PRESSURE_OUTLET: s = d1_fwd_dirichlet(XF(g, d, i), XC(g, d, i), XC(g, d, i + 1)); break;
+        case ORC_BC_PERIODIC: s = d1_central(XC(g, d, i - 1), XC(g, d, i + 1)); break;
+        case ORC_BC_SYMMETRY: s = d1_fwd_neumann(XF(g, d, i), XC(g, d, i), XC(g, d, i + 1)); break;
+        default: bad_bc(2 * d); s = st_none();
+        }
+      } else if (i == n - 1) {
+        switch (g->bcs[2 * d + 1].type) {
+        case ORC_BC_VELOCITY: s = d1_bwd_nocond(XC(g, d, i - 2), XC(g, d, i - 1), XC(g, d, i)); break;
+        case ORC_BC_PRESSURE_OUTLET: s = d1_bwd_dirichlet(XC(g, d, i - 1), XC(g, d, i), XF(g, d, i + 1)); break;
+        case ORC_BC_PERIODIC: s = d1_central(XC(g, d, i - 1), XC(g, d, i + 1)); break;
+        case ORC_BC_SYMMETRY: s = d1_bwd_neumann(XC(g, d, i - 1), XC(g, d, i), XF(g, d, i + 1)); break;
+        default: bad_bc(2 * d + 1); s = st_none();
+        }
+      } else s = d1_central(XC(g, d, i - 1), XC(g, d, i + 1));
+      add_cells(M, vdof(g, d, ijk), 0, g, &s, d, ijk);
+    }
+  Csr *r = coo_to_csr(M);
+  coo_free(M);
+  return r;
+}
+
+/* ComputePressureGradientBoundaryConditionVector_Private, cnlinearcart2d.c:155-290 / 3d:219-423 */
+static void bcvec_G(const Orc *g, double t, double *vbc)
+{
+  int ijk[3];
+  memset(vbc, 0, sizeof(double) * (size_t)(g->dim * g->N));
+  for (int b = 0; b < 2 * g->dim; ++b) {
+    int d = b / 2, n = g->n[d];
+    if (g->bcs[b].type != ORC_BC_PRESSURE_OUTLET) continue;
+    FOR_BOUNDARY_CELLS(g, b, ijk)
+    {
+      double pb = bc_pressure(g, b, t, ijk), h1, h2, v;
+      if (b % 2 == 0) {
+        h1 = XC(g, d, 0) - XF(g, d, 0);
+        h2 = XC(g, d, 1) - XC(g, d, 0);
+        v  = -h2 / (h1 * (h1 + h2)) * pb;
+      } else {
+        h1 = XF(g, d, n) - XC(g, d, n - 1);
+        h2 = XC(g, d, n - 1) - XC(g, d, n - 2);
+        v  = h2 / (h1 * (h1 + h2)) * pb;
+      }
+      vbc[vdof(g, d, ijk)] += v;
+    }
+  }
+}
+
+/* the 1-D second-derivative row of component c in direction d at cell index i */
+static St lap_row(const Orc *g, int c, int d, int i)
+{
+  int n = g->n[d];
+  if (i == 0) {
+    switch (g->bcs[2 * d].type) {
+    case ORC_BC_VELOCITY: return d2_fwd_dirichlet(XF(g, d, i), XC(g, d, i), XC(g, d, i + 1), XC(g, d, i + 2));
+    case ORC_BC_PRESSURE_OUTLET: return d2_fwd_neumann(XF(g, d, i), XC(g, d, i), XF(g, d, i + 1), XC(g, d, i + 1));
+    case ORC_BC_PERIODIC: return d2_central(XC(g, d, i - 1), XF(g, d, i), XC(g, d, i), XF(g, d, i + 1), XC(g, d, i + 1));
+    case ORC_BC_SYMMETRY:
+      if (c == d) return d2_fwd_dirichlet(XF(g, d, i), XC(g, d, i), XC(g, d, i + 1), XC(g, d, i + 2));
+      return d2_fwd_neumann(XF(g, d, i), XC(g, d, i), XF(g, d, i + 1), XC(g, d, i + 1));
+    default: bad_bc(2 * d);
+    }
+  } else if (i == n - 1) {
+    switch (g->bcs[2 * d + 1].type) {
+    case ORC_BC_VELOCITY: return d2_bwd_dirichlet(XC(g, d, i - 2), XC(g, d, i - 1), XC(g, d, i), XF(g, d, i + 1));
+    case ORC_BC_PRESSURE_OUTLET: return d2_bwd_neumann(XC(g, d, i - 1), XF(g, d, i), XC(g, d, i), XF(g, d, i + 1));
+    case ORC_BC_PERIODIC: return d2_central(XC(g, d, i - 1), XF(g, d, i), XC(g, d, i), XF(g, d, i + 1), XC(g, d, i + 1));
+    case ORC_BC_SYMMETRY:
+      if (c == d) return d2_bwd_dirichlet(XC(g, d, i - 2), XC(g, d, i - 1), XC(g, d, i), XF(g, d, i + 1));
+      return d2_bwd_neumann(XC(g, d, i - 1), XF(g, d, i), XC(g, d, i), XF(g, d, i + 1));
+    default: bad_bc(2 * d + 1);
+    }
+  }
+  return d2_central(XC(g, d, i - 1), XF(g, d, i), XC(g, d, i), XF(g, d, i + 1), XC(g, d, i + 1));
+}
+
+/* ComputeVelocityLaplacianOperator_Private, cnlinearcart2d.c:292-448 / 3d:425-646 */
+static Csr *build_L(const Orc *g)
+{
+  Coo *M = coo_new((int)(g->dim * g->N), (int)(g->dim * g->N));
+  int  ijk[3];
+  for (int c = 0; c < g->dim; ++c) FOR_CELLS(g, ijk)
+      for (int d = 0; d < g->dim; ++d) {
+        St s = lap_row(g, c, d, ijk[d]);
+        add_cells(M, vdof(g, c, ijk), c * g->N, g, &s, d, ijk);
+      }
+  Csr *r = coo_to_csr(M);
+  coo_free(M);
+  return r;
+}
+
+/* ComputeVelocityLaplacianBoundaryConditionVector_Private, cnlinearcart2d.c:450-599 / 3d:648-871 */
+static void bcvec_L(const Orc *g, double t, double *vbc)
+{
+  int ijk[3];
+  memset(vbc, 0, sizeof(double) * (size_t)(g->dim * g->N));
+  for (int b = 0; b < 2 * g->dim; ++b) {
+    int d = b / 2, n = g->n[d];
+    if (g->bcs[b].type != ORC_BC_VELOCITY) continue;
+    FOR_BOUNDARY_CELLS(g, b, ijk)
+    {
+      double vb[3], h1, h2, h3;
+      bc_velocity(g, b, t, ijk, vb);
+      if (b % 2 == 0) {
+        h1 = XC(g, d, 0) - XF(g, d, 0);
+        h2 = XC(g, d, 1) - XC(g, d, 0);
+        h3 = XC(g, d, 2) - XC(g, d, 0);
+      } else {
+        h1 = XF(g, d, n) - XC(g, d, n - 1);
+        h2 = XC(g, d, n - 1) - XC(g, d, n - 2);
+        h3 = XC(g, d, n - 1) - XC(g, d, n - 3);
+      }
+      for (int c = 0; c < g->dim; ++c) vbc[vdof(g, c, ijk)] += 2. * (h2 + h3) / (h1 * (h1 + h2) * (h1 + h3)) * vb[c];
+    }
+  }
+}
+
+/* ComputeConvectionOperator_Private, cnlinearcart2d.c:601-897 / 3d:873-1294
+ * (C v)_c = 1/2 d/dx_d ( v_c * V0_d + v0interp_c * v_d ) */
+static Csr *build_C(const Orc *g, const double *U0, const double *v0interp)
+{
+  Coo *M = coo_new((int)(g->dim * g->N), (int)(g->dim * g->N));
+  int  ijk[3];
+  for (int c = 0; c < g->dim; ++c) FOR_CELLS(g, ijk)
+    {
+      long row = vdof(g, c, ijk);
+      for (int d = 0; d < g->dim; ++d) {
+        int    i = ijk[d], n = g->n[d];
+        double h = XF(g, d, i + 1) - XF(g, d, i);
+        int    fl[3] = {ijk[0], ijk[1], ijk[2]}, fu[3] = {ijk[0], ijk[1], ijk[2]};
+        fu[d] += 1;
+        double Ul = U0[face_at(g, d, fl)], Uu = U0[face_at(g, d, fu)];
+        double vl = v0interp[vbar_at(g, c, d, fl)], vu = v0interp[vbar_at(g, c, d, fu)];
+        St     s;
+        /* lower face, first term: columns of component c, advected by V0 */
+        s = st_none();
+        if (i == 0) {
+          switch (g->bcs[2 * d].type) {
+          case ORC_BC_VELOCITY: break;
+          case ORC_BC_PRESSURE_OUTLET: s = conv_fwd_extrap(XF(g, d, i), XC(g, d, i), XC(g, d, i + 1), h, Ul); break;
+          case ORC_BC_PERIODIC: s = conv_prev(XC(g, d, i - 1), XF(g, d, i), XC(g, d, i), h, Ul); break;
+          case ORC_BC_SYMMETRY:
+            if (c != d) s = conv_fwd_extrap(XF(g, d, i), XC(g, d, i), XC(g, d, i + 1), h, Ul);
+            break;
+          default: bad_bc(2 * d);
+          }
+        } else s = conv_prev(XC(g, d, i - 1), XF(g, d, i), XC(g, d, i), h, Ul);
+        add_cells(M, row, c * g->N, g, &s, d, ijk);
+        /* lower face, second term: columns of component d, weighted by v0interp_c */
+        s = st_none();
+        if (i == 0) {
+          switch (g->bcs[2 * d].type) {
+          case ORC_BC_VELOCITY: break;
+          case ORC_BC_PRESSURE_OUTLET: s = conv_fwd_extrap(XF(g, d, i), XC(g, d, i), XC(g, d, i + 1), h, vl); break;
+          case ORC_BC_PERIODIC: s = conv_prev(XC(g, d, i - 1), XF(g, d, i), XC(g, d, i), h, vl); break;
+          case ORC_BC_SYMMETRY: break;
+          default: bad_bc(2 * d);
+          }
+        } else s = conv_prev(XC(g, d, i - 1), XF(g, d, i), XC(g, d, i), h, vl);
+        add_cells(M, row, d * g->N, g, &s, d, ijk);
+        /* upper face, first term */
+        s = st_none();
+        if (i == n - 1) {
+          switch (g->bcs[2 * d + 1].type) {
+          case ORC_BC_VELOCITY: break;
+          case ORC_BC_PRESSURE_OUTLET: s = conv_bwd_extrap(XC(g, d, i - 1), XC(g, d, i), XF(g, d, i + 1), h, Uu); break;
+          case ORC_BC_PERIODIC: s = conv_next(XC(g, d, i), XF(g, d, i + 1), XC(g, d, i + 1), h, Uu); break;
+          case ORC_BC_SYMMETRY:
+            if (c != d) s = conv_bwd_extrap(XC(g, d, i - 1), XC(g, d, i), XF(g, d, i + 1), h, Uu);
+            break;
+          default: bad_bc(2 * d + 1);
+          }
+        } else s = conv_next(XC(g, d, i), XF(g, d, i + 1), XC(g, d, i + 1), h, Uu);
+        add_cells(M, row, c * g->N, g, &s, d, ijk);
+        /* upper face, second term */
+        s = st_none();
+        if (i == n - 1) {
+          switch (g->bcs[2 * d + 1].type) {
+          case ORC_BC_VELOCITY: break;
+          case ORC_BC_PRESSURE_OUTLET: s = conv_bwd_extrap(XC(g, d, i - 1), XC(g, d, i), XF(g, d, i + 1), h, vu); break;
+          case ORC_BC_PERIODIC: s = conv_next(XC(g, d, i), XF(g, d, i + 1), XC(g, d, i + 1), h, vu); break;
+          case ORC_BC_SYMMETRY: break;
+          default: bad_bc(2 * d + 1);
+          }
+        } else s = conv_next(XC(g, d, i), XF(g, d, i + 1), XC(g, d, i + 1), h, vu);
+        add_cells(M, row, d * g->N, g, &s, d, ijk);
+      }
+    }
+  Csr *r = coo_to_csr(M);
+  coo_free(M);
+  return r;
+}
+
+/* ComputeConvectionBoundaryConditionVector_Private, cnlinearcart2d.c:899-1042 / 3d:1296-1511 */
+static void bcvec_C(const Orc *g, double t0, double t, double *vbc)
+{
+  int ijk[3];
+  memset(vbc, 0, sizeof(double) * (size_t)(g->dim * g->N));
+  for (int b = 0; b < 2 * g->dim; ++b) {
+    int d = b / 2, n = g->n[d];
+    if (g->bcs[b].type != ORC_BC_VELOCITY) continue;
+    FOR_BOUNDARY_CELLS(g, b, ijk)
+    {
+      double vb0[3], vb[3], h, sgn;
+      bc_velocity(g, b, t0, ijk, vb0);
+      bc_velocity(g, b, t, ijk, vb);
+      if (b % 2 == 0) {
+        h   = XF(g, d, 1) - XF(g, d, 0);
+        sgn = -0.5;
+      } else {
+        h   = XF(g, d, n) - XF(g, d, n - 1);
+        sgn = 0.5;
+      }
+      for (int c = 0; c < g->dim; ++c) vbc[vdof(g, c, ijk)] += sgn * (vb[c] * vb0[d] + vb0[c] * vb[d]) / h;
+    }
+  }
+}
+
+/* one row of the linear face interpolation of component c to face f of direction d.
+ * full = 1: operator B (every component, cnlinearcart2d.c:1044-1207 / 3d:1513-1747);
+ * full = 0: operator T (normal component only, :1331-1474 / 3d:1934-2140): symmetry rows empty. */
+static St interp_row(const Orc *g, int c, int d, int f, int full)
+{
+  int n = g->n[d];
+  if (f == 0) {
+    switch (g->bcs[2 * d].type) {
+    case ORC_BC_VELOCITY: return st_none();
+    case ORC_BC_PRESSURE_OUTLET: return lin_fwd_extrap(XF(g, d, f), XC(g, d, f), XC(g, d, f + 1));
+    case ORC_BC_PERIODIC: return lin_interp(XC(g, d, f - 1), XF(g, d, f), XC(g, d, f));
+    case ORC_BC_SYMMETRY:
+      if (full && c != d) return lin_fwd_extrap(XF(g, d, f), XC(g, d, f), XC(g, d, f + 1));
+      return st_none();
+    default: bad_bc(2 * d);
+    }
+  } else if (f == n) {
+    switch (g->bcs[2 * d + 1].type) {
+    case ORC_BC_VELOCITY: return st_none();
+    case ORC_BC_PRESSURE_OUTLET: return lin_bwd_extrap(XC(g, d, f - 2), XC(g, d, f - 1), XF(g, d, f));
+    case ORC_BC_SYMMETRY:
+      if (full && c != d) return lin_bwd_extrap(XC(g, d, f - 2), XC(g, d, f - 1), XF(g, d, f));
+      return st_none();
+    default: bad_bc(2 * d + 1); /* periodic cannot happen: no face n */
+    }
+  }
+  return lin_interp(XC(g, d, f - 1), XF(g, d, f), XC(g, d, f));
+}
+
+static Csr *build_B(const Orc *g)
+{
+  Coo *M = coo_new((int)(g->dim * g->NFtot), (int)(g->dim * g->N));
+  int  ijk[3];
+  for (int c = 0; c < g->dim; ++c)
+    for (int d = 0; d < g->dim; ++d) FOR_FACES(g, d, ijk)
+      {
+        St s = interp_row(g, c, d, ijk[d], 1);
+        add_cells(M, vbar_at(g, c, d, ijk), c * g->N, g, &s, d, ijk);
+      }
+  Csr *r = coo_to_csr(M);
+  coo_free(M);
+  return r;
+}
+
+static Csr *build_T(const Orc *g)
+{
+  Coo *M = coo_new((int)g->NFtot, (int)(g->dim * g->N));
+  int  ijk[3];
+  for (int d = 0; d < g->dim; ++d) FOR_FACES(g, d, ijk)
+    {
+      St s = interp_row(g, d, d, ijk[d], 0);
+      add_cells(M, face_at(g, d, ijk), d * g->N, g, &s, d, ijk);
+    }
+  Csr *r = coo_to_csr(M);
+  coo_free(M);
+  return r;
+}
+
+/* loop over the boundary faces of boundary b */
+static void boundary_face_of_cell(const Orc *g, int b, const int ijk[3], int f[3])
+{
+  int d = b / 2;
+  f[0] = ijk[0], f[1] = ijk[1], f[2] = ijk[2];
+  f[d] = (b % 2) ? g->n[d] : 0;
+}
+
+/* ComputeFaceVelocityInterpolationBoundaryConditionVector_Private, 2d:1209-1329 / 3d:1749-1932 */
+static void bcvec_B(const Orc *g, double t, double *vbc)
+{
+  int ijk[3], f[3];
+  memset(vbc, 0, sizeof(double) * (size_t)(g->dim * g->NFtot));
+  for (int b = 0; b < 2 * g->dim; ++b) {
+    int d = b / 2;
+    if (g->bcs[b].type != ORC_BC_VELOCITY) continue;
+    FOR_BOUNDARY_CELLS(g, b, ijk)
+    {
+      double vb[3];
+      bc_velocity(g, b, t, ijk, vb);
+      boundary_face_of_cell(g, b, ijk, f);
+      for (int c = 0; c < g->dim; ++c) vbc[vbar_at(g, c, d, f)] = vb[c];
+    }
+  }
+}
+
+/* ComputeFaceNormalVelocityInterpolationBoundaryConditionVector_Private, 2d:1476-1587 / 3d:2142-2312 */
+static void bcvec_T(const Orc *g, double t, double *vbc)
+{
+  int ijk[3], f[3];
+  memset(vbc, 0, sizeof(double) * (size_t)g->NFtot);
+  for (int b = 0; b < 2 * g->dim; ++b) {
+    int d = b / 2;
+    if (g->bcs[b].type != ORC_BC_VELOCITY) continue;
+    FOR_BOUNDARY_CELLS(g, b, ijk)
+    {
+      double vb[3];
+      bc_velocity(g, b, t, ijk, vb);
+      boundary_face_of_cell(g, b, ijk, f);
+      vbc[face_at(g, d, f)] = vb[d];
+    }
+  }
+}
+
+/* ComputeStaggeredVelocityDivergenceOperator_Private, 2d:1589-1660 / 3d:2314-2408 */
+static Csr *build_D(const Orc *g)
+{
+  Coo *M = coo_new((int)g->N, (int)g->NFtot);
+  int  ijk[3];
+  FOR_CELLS(g, ijk)
+  {
+    long row = cell_at(g, ijk);
+    for (int d = 0; d < g->dim; ++d) {
+      double dx    = XF(g, d, ijk[d] + 1) - XF(g, d, ijk[d]);
+      int    fu[3] = {ijk[0], ijk[1], ijk[2]};
+      fu[d] += 1;
+      coo_add(M, (int)row, (int)face_at(g, d, ijk), -1. / dx);
+      coo_add(M, (int)row, (int)face_at(g, d, fu), 1. / dx);
+    }
+  }
+  Csr *r = coo_to_csr(M);
+  coo_free(M);
+  return r;
+}
+
+/* ComputeStaggeredPressureGradientOperator_Private, 2d:1662-1795 / 3d:2410-2600 */
+static Csr *build_Gst(const Orc *g)
+{
+  Coo *M = coo_new((int)g->NFtot, (int)g->N);
+  int  ijk[3];
+  for (int d = 0; d < g->dim; ++d) FOR_FACES(g, d, ijk)
+    {
+      int f = ijk[d], n = g->n[d];
+      St  s = st_none();
+      if (f == 0) {
+        switch (g->bcs[2 * d].type) {
+        case ORC_BC_VELOCITY:
+        case ORC_BC_SYMMETRY: break;
+        case ORC_BC_PRESSURE_OUTLET: s = fn_fwd_dirichlet(XF(g, d, f), XC(g, d, f), XC(g, d, f + 1)); break;
+        case ORC_BC_PERIODIC: s = fn_central(XC(g, d, f - 1), XC(g, d, f)); break;
+        default: bad_bc(2 * d);
+        }
+      } else if (f == n) {
+        switch (g->bcs[2 * d + 1].type) {
+        case ORC_BC_VELOCITY:
+        case ORC_BC_SYMMETRY: break;
+        case ORC_BC_PRESSURE_OUTLET: s = fn_bwd_dirichlet(XC(g, d, f - 2), XC(g, d, f - 1), XF(g, d, f)); break;
+        default: bad_bc(2 * d + 1);
+        }
+      } else s = fn_central(XC(g, d, f - 1), XC(g, d, f));
+      add_cells(M, face_at(g, d, ijk), 0, g, &s, d, ijk);
+    }
+  Csr *r = coo_to_csr(M);
+  coo_free(M);
+  return r;
+}
+
+/* ComputeStaggeredPressureGradientBoundaryConditionVector_Private, 2d:1797-1931 / 3d:2602-2805 */
+static void bcvec_Gst(const Orc *g, double t, double *vbc)
+{
+  int ijk[3], f[3];
+  memset(vbc, 0, sizeof(double) * (size_t)g->NFtot);
+  for (int b = 0; b < 2 * g->dim; ++b) {
+    int d = b / 2, n = g->n[d];
+    if (g->bcs[b].type != ORC_BC_PRESSURE_OUTLET) continue;
+    FOR_BOUNDARY_CELLS(g, b, ijk)
+    {
+      double pb = bc_pressure(g, b, t, ijk), h1, h2, v;
+      if (b % 2 == 0) {
+        h1 = XC(g, d, 0) - XF(g, d, 0);
+        h2 = XC(g, d, 1) - XF(g, d, 0);
+        v  = -(h1 + h2) / (h1 * h2) * pb;
+      } else {
+        h1 = XF(g, d, n) - XC(g, d, n - 1);
+        h2 = XF(g, d, n) - XC(g, d, n - 2);
+        v  = (h1 + h2) / (h1 * h2) * pb;
+      }
+      boundary_face_of_cell(g, b, ijk, f);
+      vbc[face_at(g, d, f)] = v;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ create / destroy */
+void orc_default_options(OrcOptions *o)
+{
+  o->mode            = 0;
+  o->outer_rtol      = 1e-5;
+  o->outer_maxit     = 10000;
+  o->mom_rtol        = 1e-5;
+  o->schur_rtol      = 1e-5;
+  o->inner_maxit     = 10000;
+  o->ilu_blocks      = 1;
+  o->exact_schur     = 0;
+  o->quirk_bcg_scale = 1;
+}
+
+Orc *orc_create(int dim, const int n[3], const int periodic[3], const double *const xf[3], double rho, double mu, double dt, const OrcBC bcs[6])
+{
+  Orc *g = (Orc *)calloc(1, sizeof(Orc));
+  g->dim = dim;
+  g->rho = rho, g->mu = mu, g->dt = dt;
+  for (int d = 0; d < 3; ++d) {
+    g->n[d]   = d < dim ? n[d] : 1;
+    g->per[d] = d < dim ? periodic[d] : 0;
+    g->nf[d]  = d < dim ? g->n[d] + (g->per[d] ? 0 : 1) : 0;
+  }
+  g->N = (long)g->n[0] * g->n[1] * g->n[2];
+  long off = 0;
+  for (int d = 0; d < 3; ++d) {
+    g->NF[d]   = d < dim ? g->N / g->n[d] * g->nf[d] : 0;
+    g->foff[d] = off;
+    off += g->NF[d];
+    if (d < dim) {
+      g->xf[d] = (double *)malloc(sizeof(double) * (size_t)(g->n[d] + 1));
+      g->xc[d] = (double *)malloc(sizeof(double) * (size_t)g->n[d]);
+      memcpy(g->xf[d], xf[d], sizeof(double) * (size_t)(g->n[d] + 1));
+      for (int i = 0; i < g->n[d]; ++i) g->xc[d][i] = (g->xf[d][i] + g->xf[d][i + 1]) / 2.0; /* cart.c:497 */
+      g->len[d] = g->xf[d][g->n[d]] - g->xf[d][0];
+    }
+  }
+  g->NFtot = off;
+  for (int b = 0; b < 6; ++b) g->bcs[b] = bcs[b];
+  for (int b = 0; b < 2 * dim; ++b)
+    if (g->bcs[b].type == ORC_BC_PRESSURE_OUTLET) g->has_outlet = 1;
+  for (int d = 0; d < dim; ++d)
+    if (g->per[d] != (g->bcs[2 * d].type == ORC_BC_PERIODIC) || g->per[d] != (g->bcs[2 * d + 1].type == ORC_BC_PERIODIC)) {
+      fprintf(stderr, "oracle: periodic mesh direction %d must carry ORC_BC_PERIODIC on both sides\n", d);
+      abort();
+    }
+
+  size_t nv = (size_t)(dim * g->N);
+  g->v = calloc(nv, sizeof(double)), g->v0 = calloc(nv, sizeof(double));
+  g->U = calloc((size_t)g->NFtot, sizeof(double)), g->U0 = calloc((size_t)g->NFtot, sizeof(double));
+  g->p = calloc((size_t)g->N, sizeof(double)), g->p0 = calloc((size_t)g->N, sizeof(double));
+  g->phalf    = calloc((size_t)g->N, sizeof(double));
+  g->v0interp = calloc((size_t)(dim * g->NFtot), sizeof(double));
+
+  /* NS_INIT_JACOBIAN, cnlinearcart2d.c:2010-2054: dt/rho is baked into G, Gst, negR */
+  g->G = build_G(g);
+  csr_scale(g->G, dt / rho);
+  g->negT = build_T(g);
+  csr_scale(g->negT, -1.);
+  g->L   = build_L(g);
+  g->Gst = build_Gst(g);
+  csr_scale(g->Gst, dt / rho);
+  {
+    Csr *tg = csr_matmat(g->negT, g->G);     /* MatMatMult(negT, G) :2035 */
+    g->negR = csr_axpy(tg, 1., g->Gst);      /* MatAXPY(negR, 1, Gst) :2036 */
+    csr_free(tg);
+  }
+  g->D = build_D(g);
+  g->B = build_B(g);
+  return g;
+}
+
+void orc_destroy(Orc *g)
+{
+  if (!g) return;
+  for (int d = 0; d < 3; ++d) free(g->xf[d]), free(g->xc[d]);
+  free(g->v), free(g->v0), free(g->U), free(g->U0), free(g->p), free(g->p0), free(g->phalf), free(g->v0interp);
+  csr_free(g->G), csr_free(g->negT), csr_free(g->L), csr_free(g->Gst), csr_free(g->negR), csr_free(g->D), csr_free(g->B);
+  csr_free(g->C), csr_free(g->A), csr_free(g->S);
+  bjilu0_free(g->iluA), bjilu0_free(g->iluS);
+  free(g);
+}
+
+void orc_sizes(const Orc *g, long *ncell, long nface[3])
+{
+  *ncell = g->N;
+  for (int d = 0; d < 3; ++d) nface[d] = g->NF[d];
+}
+
+void orc_set_state(Orc *g, const double *v, const double *const U[3], const double *p, const double *phalf, int step, double t)
+{
+  memcpy(g->v, v, sizeof(double) * (size_t)(g->dim * g->N));
+  for (int d = 0; d < g->dim; ++d) memcpy(g->U + g->foff[d], U[d], sizeof(double) * (size_t)g->NF[d]);
+  memcpy(g->p, p, sizeof(double) * (size_t)g->N);
+  if (phalf) memcpy(g->phalf, phalf, sizeof(double) * (size_t)g->N);
+  g->step = step;
+  g->t    = t;
+}
+
+void orc_get_state(const Orc *g, double *v, double *const U[3], double *p, double *phalf, int *step, double *t)
+{
+  if (v) memcpy(v, g->v, sizeof(double) * (size_t)(g->dim * g->N));
+  if (U)
+    for (int d = 0; d < g->dim; ++d)
+      if (U[d]) memcpy(U[d], g->U + g->foff[d], sizeof(double) * (size_t)g->NF[d]);
+  if (p) memcpy(p, g->p, sizeof(double) * (size_t)g->N);
+  if (phalf) memcpy(phalf, g->phalf, sizeof(double) * (size_t)g->N);
+  if (step) *step = g->step;
+  if (t) *t = g->t;
+}
+
+/* ------------------------------------------------------------------ RHS, Jacobian update */
+static long nsol(const Orc *g)
+{
+  return g->dim * g->N + g->NFtot + g->N;
+}
+
+/* NSFormFunction_CNLinear_Cart{2,3}d_Internal, cnlinearcart2d.c:2071-2171 / 3d:2945-3043 */
+static void form_function(Orc *g, const OrcOptions *opt, double *f)
+{
+  long    nv = g->dim * g->N;
+  double *momrhs = f, *interprhs = f + nv, *contrhs = f + nv + g->NFtot;
+  double *Gq = malloc(sizeof(double) * (size_t)nv), *Lv = malloc(sizeof(double) * (size_t)nv), *vbc = malloc(sizeof(double) * (size_t)nv);
+  double  tq   = (g->step == 0) ? g->t : g->t - 0.5 * g->dt;
+  const double *q = (g->step == 0) ? g->p0 : g->phalf;
+  double  nu2  = 0.5 * g->mu * g->dt / g->rho;
+  /* 2-D scales the outlet gradient BC vector by dt/rho (2d:2104,2109); 3-D by 1 (3d:2977,2981) */
+  double  sG   = (g->dim == 3 && opt->quirk_bcg_scale) ? 1. : g->dt / g->rho;
+  long    k;
+
+  csr_mult(g->G, q, Gq);
+  bcvec_G(g, tq, vbc);
+  for (k = 0; k < nv; ++k) Gq[k] += sG * vbc[k];
+  csr_mult(g->L, g->v0, Lv);
+  bcvec_L(g, g->t, vbc);
+  for (k = 0; k < nv; ++k) Lv[k] += vbc[k];
+  for (k = 0; k < nv; ++k) momrhs[k] = g->v0[k] + nu2 * Lv[k];
+  bcvec_C(g, g->t, g->t + g->dt, vbc);
+  for (k = 0; k < nv; ++k) momrhs[k] += -g->dt * vbc[k];
+  for (k = 0; k < nv; ++k) momrhs[k] += -Gq[k];
+  bcvec_L(g, g->t + g->dt, vbc);
+  for (k = 0; k < nv; ++k) momrhs[k] += nu2 * vbc[k];
+
+  bcvec_T(g, g->t + g->dt, interprhs);
+  {
+    /* boundary condition for the Rhie-Chow correction term, 2d:2130-2161 */
+    double *vbcGp = malloc(sizeof(double) * (size_t)nv), *vbcGq = malloc(sizeof(double) * (size_t)nv);
+    double *vbcGstp = malloc(sizeof(double) * (size_t)g->NFtot), *vbcGstq = malloc(sizeof(double) * (size_t)g->NFtot);
+    double *tmp = malloc(sizeof(double) * (size_t)g->NFtot);
+    bcvec_G(g, g->t + 0.5 * g->dt, vbcGp);
+    bcvec_Gst(g, g->t + 0.5 * g->dt, vbcGstp);
+    bcvec_G(g, tq, vbcGq);
+    bcvec_Gst(g, tq, vbcGstq);
+    for (k = 0; k < nv; ++k) vbcGq[k] = (vbcGq[k] - vbcGp[k]) * (g->dt / g->rho);
+    csr_mult_add(g->negT, vbcGq, interprhs, tmp);
+    for (k = 0; k < g->NFtot; ++k) interprhs[k] = tmp[k] + (g->dt / g->rho) * (vbcGstq[k] - vbcGstp[k]);
+    free(vbcGp), free(vbcGq), free(vbcGstp), free(vbcGstq), free(tmp);
+  }
+  for (k = 0; k < g->N; ++k) contrhs[k] = 0.;
+  free(Gq), free(Lv), free(vbc);
+}
+
+/* NSFormJacobian(UPDATE), cnlinearcart2d.c:2056-2067: A = I + dt*C - (nu*dt/2)*L */
+static void form_jacobian_update(Orc *g)
+{
+  csr_free(g->C), csr_free(g->A);
+  g->C = build_C(g, g->U0, g->v0interp);
+  Csr *dtC = csr_copy(g->C);
+  csr_scale(dtC, g->dt);
+  Csr *t1 = csr_axpy(dtC, -0.5 * g->mu * g->dt / g->rho, g->L);
+  g->A    = csr_shift_identity(t1, 1.);
+  csr_free(dtC), csr_free(t1);
+}
+
+/* PCSetUp_ABF, abfpc.c:113-182 (Ainv type ID) */
+static void abf_setup(Orc *g, const OrcOptions *opt)
+{
+  csr_free(g->S);
+  bjilu0_free(g->iluA), bjilu0_free(g->iluS);
+  if (opt->exact_schur) {
+    Csr *dg = csr_matmat(g->D, g->Gst);
+    csr_scale(dg, -1.);
+    g->S = dg;
+  } else {
+    Csr *tmp  = csr_matmat(g->negT, g->G);      /* :153 */
+    Csr *tmp2 = csr_axpy(tmp, -1., g->negR);    /* :169 */
+    g->S      = csr_matmat(g->D, tmp2);         /* :170 */
+    csr_free(tmp), csr_free(tmp2);
+  }
+  g->iluA = bjilu0_factor(g->A, opt->ilu_blocks);
+  g->iluS = bjilu0_factor(g->S, opt->ilu_blocks);
+}
+
+static void op_csr(void *ctx, const double *x, double *y)
+{
+  csr_mult((const Csr *)ctx, x, y);
+}
+static void op_ilu(void *ctx, const double *x, double *y)
+{
+  bjilu0_solve((const BJIlu0 *)ctx, x, y);
+}
+typedef struct {
+  long n;
+} MeanCtx;
+static void op_remove_mean(void *ctx, const double *x, double *y)
+{
+  long   n = ((MeanCtx *)ctx)->n, k;
+  double s = 0.;
+  for (k = 0; k < n; ++k) s += x[k];
+  s /= (double)n;
+  for (k = 0; k < n; ++k) y[k] = x[k] - s;
+}
+
+/* PCApply_ABF, abfpc.c:48-111 */
+static void abf_apply_internal(Orc *g, const OrcOptions *opt, const double *b, double *x)
+{
+  long          nv = g->dim * g->N, k;
+  const double *momrhs = b, *interprhs = b + nv, *contrhs = b + nv + g->NFtot;
+  double       *v = x, *V = x + nv, *p = x + nv + g->NFtot;
+  double       *vstar = calloc((size_t)nv, sizeof(double)), *Vstar = malloc(sizeof(double) * (size_t)g->NFtot);
+  double       *Srhs = malloc(sizeof(double) * (size_t)g->N), *gp = malloc(sizeof(double) * (size_t)nv);
+  double       *negRp = malloc(sizeof(double) * (size_t)g->NFtot);
+  KspInfo       ki;
+  MeanCtx       mc = {g->N};
+
+  /* stage 1 */
+  gmres((int)nv, op_csr, g->A, op_ilu, g->iluA, NULL, NULL, momrhs, vstar, 30, opt->mom_rtol, 1e-50, opt->inner_maxit, 0, &ki); /* :72 */
+  g->mom_its += ki.its;
+  csr_mult(g->negT, vstar, Vstar);                                     /* :73 */
+  for (k = 0; k < g->NFtot; ++k) Vstar[k] = interprhs[k] - Vstar[k];   /* :74 */
+  csr_mult(g->D, Vstar, Srhs);                                         /* :75 */
+  for (k = 0; k < g->N; ++k) Srhs[k] = contrhs[k] - Srhs[k];           /* :76 */
+  for (k = 0; k < g->N; ++k) p[k] = 0.;
+  gmres((int)g->N, op_csr, g->S, op_ilu, g->iluS, g->has_outlet ? NULL : op_remove_mean, &mc, Srhs, p, 30, opt->schur_rtol, 1e-50, opt->inner_maxit, 0, &ki); /* :77, null space :173-177 */
+  g->schur_its += ki.its;
+  /* stage 2 */
+  csr_mult(g->G, p, gp);                                               /* :80 */
+  for (k = 0; k < nv; ++k) v[k] = vstar[k] - gp[k];                    /* :95 */
+  csr_mult_add(g->negT, gp, Vstar, V);                                 /* :96 */
+  csr_mult(g->negR, p, negRp);                                         /* :99 */
+  for (k = 0; k < g->NFtot; ++k) V[k] -= negRp[k];                     /* :100 */
+  g->abf_applies++;
+  free(vstar), free(Vstar), free(Srhs), free(gp), free(negRp);
+}
+
+/* coupled operator M of THEORY_GUIDE.md / MatNest J (nsbasic.c:203-207) */
+static void op_coupled(void *ctx, const double *x, double *y)
+{
+  Orc          *g  = (Orc *)ctx;
+  long          nv = g->dim * g->N, k;
+  const double *v = x, *V = x + nv, *p = x + nv + g->NFtot;
+  double       *yv = y, *yV = y + nv, *yp = y + nv + g->NFtot;
+  double       *t1 = malloc(sizeof(double) * (size_t)nv), *t2 = malloc(sizeof(double) * (size_t)g->NFtot);
+  csr_mult(g->A, v, yv);
+  csr_mult(g->G, p, t1);
+  for (k = 0; k < nv; ++k) yv[k] += t1[k];
+  csr_mult(g->negT, v, yV);
+  csr_mult(g->negR, p, t2);
+  for (k = 0; k < g->NFtot; ++k) yV[k] += V[k] + t2[k];
+  csr_mult(g->D, V, yp);
+  free(t1), free(t2);
+}
+typedef struct {
+  Orc              *g;
+  const OrcOptions *opt;
+} AbfCtx;
+static void op_abf(void *ctx, const double *x, double *y)
+{
+  AbfCtx *a = (AbfCtx *)ctx;
+  abf_apply_internal(a->g, a->opt, x, y);
+}
+/* null space of J: constant pressure (nsbasic.c:229-243) */
+static void op_remove_pmean(void *ctx, const double *x, double *y)
+{
+  Orc   *g   = (Orc *)ctx;
+  long   off = g->dim * g->N + g->NFtot, k, n = nsol(g);
+  double s   = 0.;
+  if (y != x) memcpy(y, x, sizeof(double) * (size_t)n);
+  for (k = 0; k < g->N; ++k) s += x[off + k];
+  s /= (double)g->N;
+  for (k = 0; k < g->N; ++k) y[off + k] = x[off + k] - s;
+}
+
+void orc_prepare_step(Orc *g, const OrcOptions *opt, double *rhs)
+{
+  long nv = g->dim * g->N;
+  /* NSStep: sol0 = sol (nsbasic.c:281-282) */
+  memcpy(g->v0, g->v, sizeof(double) * (size_t)nv);
+  memcpy(g->U0, g->U, sizeof(double) * (size_t)g->NFtot);
+  memcpy(g->p0, g->p, sizeof(double) * (size_t)g->N);
+  /* v0interp = B v0 + bc(t), cnlinearcart2d.c:1951-1957 */
+  {
+    double *vbc = malloc(sizeof(double) * (size_t)(g->dim * g->NFtot));
+    bcvec_B(g, g->t, vbc);
+    csr_mult_add(g->B, g->v0, vbc, g->v0interp);
+    free(vbc);
+  }
+  form_jacobian_update(g);
+  abf_setup(g, opt);
+  if (rhs) form_function(g, opt, rhs);
+}
+
+void orc_abf_apply(Orc *g, const OrcOptions *opt, const double *b, double *x, OrcStepInfo *info)
+{
+  g->mom_its = g->schur_its = g->abf_applies = 0;
+  abf_apply_internal(g, opt, b, x);
+  if (info) {
+    memset(info, 0, sizeof *info);
+    info->mom_its = g->mom_its, info->schur_its = g->schur_its, info->abf_applies = g->abf_applies;
+  }
+}
+
+/* NSStep (nsbasic.c:276-299) -> NSStep_CNLinear_Cart{2,3}d_Internal (2d:1933-1989, 3d:2807-2863) */
+int orc_step(Orc *g, const OrcOptions *opt, OrcStepInfo *info)
+{
+  long    n = nsol(g), nv = g->dim * g->N, k;
+  double *b = malloc(sizeof(double) * (size_t)n), *x = calloc((size_t)n, sizeof(double));
+  AbfCtx  actx = {g, opt};
+  OrcStepInfo local;
+  if (!info) info = &local;
+  memset(info, 0, sizeof *info);
+  g->mom_its = g->schur_its = g->abf_applies = 0;
+
+  orc_prepare_step(g, opt, b);
+  /* F(0) = -b with the null space removed (nsbasic.c:133-144); zero initial guess (:146-151) */
+  if (!g->has_outlet) op_remove_pmean(g, b, b);
+
+  if (opt->mode == 1) {
+    abf_apply_internal(g, opt, b, x);
+    if (!g->has_outlet) op_remove_pmean(g, x, x);
+    info->converged = 1;
+  } else {
+    KspInfo ki;
+    gmres((int)n, op_coupled, g, op_abf, &actx, g->has_outlet ? NULL : op_remove_pmean, g, b, x, 30, opt->outer_rtol, 1e-50, opt->outer_maxit, 1, &ki);
+    info->outer_its    = ki.its;
+    info->converged    = ki.converged;
+    info->outer_rnorm0 = ki.rnorm0;
+    info->outer_rnorm  = ki.rnorm;
+    info->nhist        = ki.nhist;
+    memcpy(info->hist, ki.hist, sizeof(double) * (size_t)ki.nhist);
+  }
+  info->mom_its = g->mom_its, info->schur_its = g->schur_its, info->abf_applies = g->abf_applies;
+
+  {
+    const double *v = x, *V = x + nv, *dp = x + nv + g->NFtot;
+    memcpy(g->v, v, sizeof(double) * (size_t)nv);
+    memcpy(g->U, V, sizeof(double) * (size_t)g->NFtot);
+    if (g->step == 0) {
+      for (k = 0; k < g->N; ++k) g->p[k] = g->p0[k] + 2. * dp[k];
+      for (k = 0; k < g->N; ++k) g->phalf[k] = g->p0[k] + dp[k];
+    } else {
+      for (k = 0; k < g->N; ++k) g->p[k] = g->phalf[k] + 1.5 * dp[k];
+      for (k = 0; k < g->N; ++k) g->phalf[k] += dp[k];
+    }
+  }
+  g->step++;
+  g->t += g->dt;
+  free(b), free(x);
+  return info->converged ? 0 : 1;
+}
+
+int orc_matrix(const Orc *g, const char *name, int *nrows, int *ncols, long *nnz, const int **ptr, const int **idx, const double **val)
+{
+  const Csr *m = NULL;
+  if (!strcmp(name, "G")) m = g->G;
+  else if (!strcmp(name, "L")) m = g->L;
+  else if (!strcmp(name, "negT")) m = g->negT;
+  else if (!strcmp(name, "B")) m = g->B;
+  else if (!strcmp(name, "D")) m = g->D;
+  else if (!strcmp(name, "Gst")) m = g->Gst;
+  else if (!strcmp(name, "negR")) m = g->negR;
+  else if (!strcmp(name, "A")) m = g->A;
+  else if (!strcmp(name, "C")) m = g->C;
+  else if (!strcmp(name, "S")) m = g->S;
+  if (!m) return -1;
+  *nrows = m->nrows, *ncols = m->ncols, *nnz = m->nnz, *ptr = m->ptr, *idx = m->idx, *val = m->val;
+  return 0;
+}
+
+int orc_bc_constant(int dim, double t, const double x[], double val[], void *ctx)
+{
+  const double *c = (const double *)ctx;
+  (void)t, (void)x;
+  for (int d = 0; d < dim; ++d) val[d] = c[d];
+  return 0;
+}
+
+int orc_bc_constant_pressure(int dim, double t, const double x[], double val[], void *ctx)
+{
+  (void)dim, (void)t, (void)x;
+  val[0] = *(const double *)ctx;
+  return 0;
+}
