@@ -1,0 +1,485 @@
+// capi.cu -- extern "C" boundary (include/fluca_b200.h).  No torch types, no C++ types, no
+// exceptions cross this file: every entry point catches and converts to an error code.
+#include "../../include/fluca_b200.h"
+#include "solver.h"
+#include <string>
+
+using namespace fluca;
+
+struct fluca_b200_comm {
+  Comm *c;
+};
+
+struct fluca_b200_solver {
+  Solver s;
+  // snapshot of the state for device-resident benchmarking
+  bool    have_snap = false;
+  V3      sv, sU;
+  double *sp = nullptr, *sph = nullptr;
+  int     snap_step = 0;
+  // outputs of the operator-level test entry points
+  bool    have_api = false;
+  V3      av, aU;
+  double *ap = nullptr;
+};
+
+static thread_local std::string g_err;
+
+#define API_BEGIN try {
+#define API_END \
+  } \
+  catch (const fluca::Error &e) \
+  { \
+    g_err = e.what(); \
+    return e.code; \
+  } \
+  catch (const std::exception &e) \
+  { \
+    g_err = e.what(); \
+    return FLUCA_B200_ERR_INTERNAL; \
+  } \
+  return FLUCA_B200_OK;
+
+extern "C" const char *fluca_b200_last_error(void) { return g_err.c_str(); }
+
+extern "C" int fluca_b200_is_host_emulation(void)
+{
+#ifdef FLUCA_HOSTEMU
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+extern "C" int fluca_b200_comm_unique_id(void *out, int capacity, int *bytes)
+{
+  API_BEGIN
+#ifndef FLUCA_HOSTEMU
+  *bytes = nccl_unique_id(out, capacity);
+#else
+  (void)out, (void)capacity, (void)bytes;
+  throw Error(FL_ERR_NCCL, "NCCL is not part of the host-emulation test build");
+#endif
+  API_END
+}
+
+extern "C" int fluca_b200_comm_create_nccl(const void *unique_id, int bytes, int rank, int nranks, fluca_b200_comm **out)
+{
+  API_BEGIN
+#ifndef FLUCA_HOSTEMU
+  fluca_b200_comm *c = new fluca_b200_comm;
+  c->c               = make_nccl_comm(unique_id, bytes, rank, nranks);
+  *out               = c;
+#else
+  (void)unique_id, (void)bytes, (void)rank, (void)nranks, (void)out;
+  throw Error(FL_ERR_NCCL, "NCCL is not part of the host-emulation test build");
+#endif
+  API_END
+}
+
+extern "C" int fluca_b200_comm_create_callbacks(int rank, int nranks, fluca_b200_halo_fn h, fluca_b200_allsum_fn a, fluca_b200_allgather_fn g, void *ctx, fluca_b200_comm **out)
+{
+  API_BEGIN
+  if (!h || !a) throw Error(FL_ERR_ARG, "halo and allsum callbacks are required");
+  CallbackComm *cc = new CallbackComm;
+  cc->rank = rank, cc->nranks = nranks, cc->halo_cb = h, cc->allsum_cb = a, cc->allgather_cb = g, cc->ctx = ctx;
+  fluca_b200_comm *c = new fluca_b200_comm;
+  c->c               = cc;
+  *out               = c;
+  API_END
+}
+
+extern "C" int fluca_b200_create(const fluca_b200_desc *d, fluca_b200_comm *comm, fluca_b200_solver **out)
+{
+  API_BEGIN
+  if (!d || !out) throw Error(FL_ERR_ARG, "null argument");
+#ifndef FLUCA_HOSTEMU
+  {
+    int         ndev = 0;
+    cudaError_t e    = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1) throw Error(FL_ERR_NODEVICE, "fluca_b200 needs a CUDA device (sm_100a); there is no CPU fallback");
+  }
+#endif
+  Options o;
+  o.mode = d->mode;
+  if (d->outer_rtol > 0.) o.outer_rtol = d->outer_rtol;
+  if (d->outer_maxit > 0) o.outer_maxit = d->outer_maxit;
+  if (d->outer_restart > 0) o.outer_restart = d->outer_restart;
+  if (d->mom_rtol > 0.) o.mom_rtol = d->mom_rtol;
+  if (d->schur_rtol > 0.) o.schur_rtol = d->schur_rtol;
+  if (d->inner_maxit > 0) o.inner_maxit = d->inner_maxit;
+  if (d->mg_nu1 > 0) o.mg_nu1 = d->mg_nu1;
+  if (d->mg_nu2 > 0) o.mg_nu2 = d->mg_nu2;
+  if (d->mg_coarse_sweeps > 0) o.mg_coarse_sweeps = d->mg_coarse_sweeps;
+  o.quirk_bcg_scale = d->no_bcg_quirk ? 0 : 1;
+  if (o.mode != FLUCA_B200_MODE_COUPLED && o.mode != FLUCA_B200_MODE_FRACTIONAL) throw Error(FL_ERR_ARG, "unknown solve mode");
+  fluca_b200_solver *h = new fluca_b200_solver;
+  Comm              *c = comm ? comm->c : nullptr;
+  delete comm;
+  try {
+    solver_setup(h->s, d->dim, d->n, d->xf, d->bc_type, d->rho, d->mu, d->dt, o, c, d->k0, d->dim == 3 ? d->nzl : 1);
+  } catch (...) {
+    try {
+      solver_destroy(h->s);
+    } catch (...) {
+    }
+    delete h;
+    throw;
+  }
+  *out = h;
+  API_END
+}
+
+extern "C" int fluca_b200_destroy(fluca_b200_solver *h)
+{
+  API_BEGIN
+  if (!h) return FLUCA_B200_OK;
+  solver_destroy(h->s);
+  delete h;
+  API_END
+}
+
+// ------------------------------------------------------------------ compact <-> padded copies
+namespace {
+struct Ext {
+  int w, hgt, planes;
+};
+Ext cell_ext(const Geom &g) { return Ext{g.nx, g.ny, g.nzl}; }
+Ext face_ext(const Geom &g, int d)
+{
+  Ext e = cell_ext(g);
+  if (d == 0 && !g.t[0].per) e.w += 1;
+  if (d == 1 && !g.t[1].per) e.hgt += 1;
+  if (d == 2 && g.t[2].wall_hi) e.planes += 1;
+  return e;
+}
+void put(Solver &s, double *dev, const double *host, Ext e)
+{
+  const Geom &g = s.gh.g;
+  for (int k = 0; k < e.planes; ++k)
+    copy2d_h2d(s.ex, dev + g.idx(0, 0, k), sizeof(double) * g.px, host + (size_t)k * e.w * e.hgt, sizeof(double) * e.w, sizeof(double) * e.w, e.hgt);
+}
+void get(Solver &s, double *host, const double *dev, Ext e)
+{
+  const Geom &g = s.gh.g;
+  for (int k = 0; k < e.planes; ++k)
+    copy2d_d2h(s.ex, host + (size_t)k * e.w * e.hgt, sizeof(double) * e.w, dev + g.idx(0, 0, k), sizeof(double) * g.px, sizeof(double) * e.w, e.hgt);
+}
+size_t ext_count(Ext e) { return (size_t)e.w * e.hgt * e.planes; }
+
+void put_cells(Solver &s, const V3 &dst, const double *src)
+{
+  const Ext e = cell_ext(s.gh.g);
+  for (int c = 0; c < s.dim; ++c) put(s, dst.c[c], src + c * ext_count(e), e);
+}
+void get_cells(Solver &s, double *dst, const V3 &src)
+{
+  const Ext e = cell_ext(s.gh.g);
+  for (int c = 0; c < s.dim; ++c) get(s, dst + c * ext_count(e), src.c[c], e);
+}
+void fill_stats(const Solver &s, fluca_b200_stats *st)
+{
+  if (!st) return;
+  memset(st, 0, sizeof(*st));
+  st->outer_its = s.stats.outer_its, st->mom_its = s.stats.mom_its, st->schur_its = s.stats.schur_its;
+  st->abf_applies = s.stats.abf_applies, st->converged = s.stats.converged;
+  st->outer_rnorm0 = s.stats.outer_rnorm0, st->outer_rnorm = s.stats.outer_rnorm;
+  st->nhist = s.stats.nhist;
+  for (int i = 0; i < s.stats.nhist && i < 128; ++i) st->hist[i] = s.stats.hist[i];
+  st->launches     = s.stats.launches;
+  st->mom_last_rel = s.stats.mom_last_rel, st->schur_last_rel = s.stats.schur_last_rel;
+}
+} // namespace
+
+extern "C" int fluca_b200_set_state(fluca_b200_solver *h, const double *v, const double *const U[3], const double *p, const double *phalf)
+{
+  API_BEGIN
+  Solver &s = h->s;
+  if (v) put_cells(s, s.v, v);
+  if (U)
+    for (int d = 0; d < s.dim; ++d)
+      if (U[d]) put(s, s.U.c[d], U[d], face_ext(s.gh.g, d));
+  if (p) put(s, s.p, p, cell_ext(s.gh.g));
+  if (phalf) put(s, s.phalf, phalf, cell_ext(s.gh.g));
+  s.ex.sync();
+  API_END
+}
+
+extern "C" int fluca_b200_get_state(fluca_b200_solver *h, double *v, double *const U[3], double *p, double *phalf)
+{
+  API_BEGIN
+  Solver &s = h->s;
+  if (v) get_cells(s, v, s.v);
+  if (U)
+    for (int d = 0; d < s.dim; ++d)
+      if (U[d]) get(s, U[d], s.U.c[d], face_ext(s.gh.g, d));
+  if (p) get(s, p, s.p, cell_ext(s.gh.g));
+  if (phalf) get(s, phalf, s.phalf, cell_ext(s.gh.g));
+  s.ex.sync();
+  API_END
+}
+
+extern "C" int fluca_b200_set_boundary_velocity(fluca_b200_solver *h, int b, int slot, const double *values)
+{
+  API_BEGIN
+  Solver &s = h->s;
+  if (b < 0 || b >= 2 * s.dim || slot < 0 || slot > 1 || !values) throw Error(FL_ERR_ARG, "bad boundary / slot");
+  copy_h2d(s.ex, s.bc_store[b][0][slot], values, sizeof(double) * s.bc.npts[b] * s.dim);
+  s.ex.sync();
+  API_END
+}
+
+extern "C" int fluca_b200_set_boundary_pressure(fluca_b200_solver *h, int b, int slot, const double *values)
+{
+  API_BEGIN
+  Solver &s = h->s;
+  if (b < 0 || b >= 2 * s.dim || slot < 0 || slot > 1 || !values) throw Error(FL_ERR_ARG, "bad boundary / slot");
+  copy_h2d(s.ex, s.bc_store[b][1][slot], values, sizeof(double) * s.bc.npts[b]);
+  s.ex.sync();
+  API_END
+}
+
+extern "C" int fluca_b200_step(fluca_b200_solver *h, double t, int step_index, fluca_b200_stats *st)
+{
+  API_BEGIN
+  int rc = do_step(h->s, t, step_index);
+  fill_stats(h->s, st);
+  if (rc) throw Error(FL_ERR_DIVERGED, "the linear solve of the time step did not reach its tolerance within the iteration limit");
+  API_END
+}
+
+extern "C" int fluca_b200_prepare_step(fluca_b200_solver *h, double t, int step_index)
+{
+  API_BEGIN
+  prepare_step(h->s, t, step_index);
+  h->s.ex.sync();
+  API_END
+}
+
+extern "C" int fluca_b200_get_rhs(fluca_b200_solver *h, double *rmom, double *const rint[3], double *rcon)
+{
+  API_BEGIN
+  Solver &s = h->s;
+  if (!s.prepared) throw Error(FL_ERR_ARG, "call fluca_b200_prepare_step first");
+  if (rmom) get_cells(s, rmom, s.rm);
+  if (rint)
+    for (int d = 0; d < s.dim; ++d)
+      if (rint[d]) get(s, rint[d], s.ri.c[d], face_ext(s.gh.g, d));
+  if (rcon) get(s, rcon, s.rc, cell_ext(s.gh.g));
+  s.ex.sync();
+  API_END
+}
+
+extern "C" int fluca_b200_apply_momentum(fluca_b200_solver *h, const double *x, double *y)
+{
+  API_BEGIN
+  Solver &s = h->s;
+  if (!s.prepared) throw Error(FL_ERR_ARG, "call fluca_b200_prepare_step first");
+  put_cells(s, s.kp, x);
+  a_apply(s, s.kp, s.kv);
+  get_cells(s, y, s.kv);
+  s.ex.sync();
+  API_END
+}
+
+extern "C" int fluca_b200_apply_schur(fluca_b200_solver *h, const double *p, double *y)
+{
+  API_BEGIN
+  Solver &s = h->s;
+  put(s, s.pp, p, cell_ext(s.gh.g));
+  schur_apply_reference_scaling(s, s.pp, s.pq);
+  get(s, y, s.pq, cell_ext(s.gh.g));
+  s.ex.sync();
+  API_END
+}
+
+extern "C" int fluca_b200_apply_coupled(fluca_b200_solver *h, const double *xv, const double *const xU[3], const double *xp, double *yv, double *const yU[3], double *yp)
+{
+  API_BEGIN
+  Solver &s = h->s;
+  if (!s.prepared) throw Error(FL_ERR_ARG, "call fluca_b200_prepare_step first");
+  put_cells(s, s.vstar, xv);
+  for (int d = 0; d < s.dim; ++d) put(s, s.Ustar.c[d], xU[d], face_ext(s.gh.g, d));
+  put(s, s.srhs, xp, cell_ext(s.gh.g));
+  // outputs go to dedicated fields: a cell-located work vector must never receive face data (its padding
+  // entries have to stay zero for the flat vector kernels)
+  if (!h->have_api) {
+    h->av = s.alloc_v3(), h->aU = s.alloc_v3(), h->ap = s.alloc_field();
+    h->have_api = true;
+  }
+  coupled_apply(s, s.vstar, s.Ustar, s.srhs, h->av, h->aU, h->ap);
+  get_cells(s, yv, h->av);
+  for (int d = 0; d < s.dim; ++d) get(s, yU[d], h->aU.c[d], face_ext(s.gh.g, d));
+  get(s, yp, h->ap, cell_ext(s.gh.g));
+  s.ex.sync();
+  API_END
+}
+
+extern "C" int fluca_b200_apply_abf(fluca_b200_solver *h, const double *bv, const double *const bU[3], const double *bp, double *xv, double *const xU[3], double *xp, fluca_b200_stats *st)
+{
+  API_BEGIN
+  Solver &s = h->s;
+  if (!s.prepared) throw Error(FL_ERR_ARG, "call fluca_b200_prepare_step first");
+  s.stats = Stats();
+  // stage the input in the solve-vector slots, which abf_apply does not touch as inputs
+  put_cells(s, s.xv, bv);
+  for (int d = 0; d < s.dim; ++d) put(s, s.xU.c[d], bU[d], face_ext(s.gh.g, d));
+  put(s, s.xp, bp, cell_ext(s.gh.g));
+  if (!h->have_api) {
+    h->av = s.alloc_v3(), h->aU = s.alloc_v3(), h->ap = s.alloc_field();
+    h->have_api = true;
+  }
+  abf_apply(s, s.xv, s.xU, s.xp, h->av, h->aU, h->ap);
+  get_cells(s, xv, h->av);
+  for (int d = 0; d < s.dim; ++d) get(s, xU[d], h->aU.c[d], face_ext(s.gh.g, d));
+  get(s, xp, h->ap, cell_ext(s.gh.g));
+  s.ex.sync();
+  fill_stats(s, st);
+  API_END
+}
+
+// ------------------------------------------------------------------ device-resident helpers
+extern "C" int fluca_b200_snapshot_save(fluca_b200_solver *h)
+{
+  API_BEGIN
+  Solver &s = h->s;
+  if (!h->have_snap) {
+    h->sv = s.alloc_v3(), h->sU = s.alloc_v3(), h->sp = s.alloc_field(), h->sph = s.alloc_field();
+    h->have_snap = true;
+  }
+  const size_t nb = sizeof(double) * (size_t)s.gh.g.nalloc;
+  for (int c = 0; c < s.dim; ++c) copy_d2d(s.ex, h->sv.c[c], s.v.c[c], nb), copy_d2d(s.ex, h->sU.c[c], s.U.c[c], nb);
+  copy_d2d(s.ex, h->sp, s.p, nb), copy_d2d(s.ex, h->sph, s.phalf, nb);
+  s.ex.sync();
+  API_END
+}
+
+extern "C" int fluca_b200_snapshot_restore(fluca_b200_solver *h)
+{
+  API_BEGIN
+  Solver &s = h->s;
+  if (!h->have_snap) throw Error(FL_ERR_ARG, "no snapshot saved");
+  const size_t nb = sizeof(double) * (size_t)s.gh.g.nalloc;
+  for (int c = 0; c < s.dim; ++c) copy_d2d(s.ex, s.v.c[c], h->sv.c[c], nb), copy_d2d(s.ex, s.U.c[c], h->sU.c[c], nb);
+  copy_d2d(s.ex, s.p, h->sp, nb), copy_d2d(s.ex, s.phalf, h->sph, nb);
+  s.ex.sync();
+  API_END
+}
+
+extern "C" int fluca_b200_device_layout(fluca_b200_solver *h, int *px, int *py, long *plane, long *nalloc)
+{
+  API_BEGIN
+  const Geom &g = h->s.gh.g;
+  if (px) *px = g.px;
+  if (py) *py = g.py;
+  if (plane) *plane = g.plane;
+  if (nalloc) *nalloc = g.nalloc;
+  API_END
+}
+
+extern "C" int fluca_b200_device_field(fluca_b200_solver *h, const char *name, void **ptr)
+{
+  API_BEGIN
+  Solver     &s = h->s;
+  std::string n(name ? name : "");
+  double     *p = nullptr;
+  if (n == "p") p = s.p;
+  else if (n == "phalf") p = s.phalf;
+  else if (n.size() == 2 && (n[0] == 'v' || n[0] == 'U') && n[1] >= '0' && n[1] < '0' + s.dim) p = (n[0] == 'v' ? s.v : s.U).c[n[1] - '0'];
+  if (!p) throw Error(FL_ERR_ARG, "unknown field name");
+  *ptr = p;
+  API_END
+}
+
+extern "C" int fluca_b200_stream(fluca_b200_solver *h, void **stream)
+{
+  API_BEGIN
+  *stream = (void *)h->s.ex.stream;
+  API_END
+}
+
+extern "C" long fluca_b200_launch_count(fluca_b200_solver *h) { return h ? h->s.ex.stats.launches : 0; }
+
+extern "C" double fluca_b200_step_model_bytes(fluca_b200_solver *h, const fluca_b200_stats *st)
+{
+  // algorithmic bytes per cell (each distinct array element read once, written once
+  // per kernel), fp64.  3-D: rhs 56, BiCGStab iteration 552, poisson_rhs 32, PCG+V(2,2) iteration 227,
+  // project 104, coupled residual 176, orthogonalisation (2k+3)*56 at GMRES index k.
+  if (!h || !st) return 0.;
+  const Solver &s   = h->s;
+  const Geom   &g   = s.gh.g;
+  const double  N   = (double)g.nx * g.ny * g.nzl;
+  const bool    d3  = (s.dim == 3);
+  const double  rhs = d3 ? 56 : 40, bicg = d3 ? 552 : 368, prhs = d3 ? 32 : 24, pcg = d3 ? 227 : 251, proj = d3 ? 104 : 80;
+  const double  coup = d3 ? 176 : 128, vec7 = d3 ? 56 : 40;
+  // with a pressure outlet the pressure Krylov method is BiCGStab: two applies + two V-cycles per iteration
+  const double  piter = s.has_outlet ? 2. * pcg : pcg;
+  double        B = rhs + st->abf_applies * (prhs + proj) + st->mom_its * bicg + st->schur_its * piter;
+  if (s.opt.mode == 0)
+    for (int k = 0; k < st->outer_its; ++k) B += coup + (2. * (k % s.opt.outer_restart) + 3.) * vec7;
+  return B * N;
+}
+
+extern "C" int fluca_b200_kernel_timing(fluca_b200_solver *h, int enable)
+{
+  API_BEGIN
+  h->s.ex.sync();
+  h->s.ex.ktime_on = enable != 0;
+  API_END
+}
+
+extern "C" int fluca_b200_kernel_times(fluca_b200_solver *h, double ms[FLUCA_B200_KT_NCLASS], long counts[FLUCA_B200_KT_NCLASS], int reset)
+{
+  API_BEGIN
+  Exec &ex = h->s.ex;
+  ex.ktime_collect();
+  for (int c = 0; c < KT_NCLASS; ++c) {
+    if (ms) ms[c] = ex.kt_ms[c];
+    if (counts) counts[c] = ex.kt_count[c];
+    if (reset) ex.kt_ms[c] = 0., ex.kt_count[c] = 0;
+  }
+  API_END
+}
+
+extern "C" int fluca_b200_time_kernel(fluca_b200_solver *h, const char *name, int reps, double *ms, double *bytes)
+{
+  API_BEGIN
+#ifdef FLUCA_HOSTEMU
+  (void)h, (void)name, (void)reps, (void)ms, (void)bytes;
+  throw Error(FL_ERR_NODEVICE, "kernel timing needs the CUDA build");
+#else
+  Solver     &s = h->s;
+  const Geom &g = s.gh.g;
+  std::string n(name ? name : "");
+  const double N = (double)g.nx * g.ny * g.nzl;
+  if (reps < 1) reps = 1;
+  if (!s.prepared && n == "momentum_apply") throw Error(FL_ERR_ARG, "momentum_apply timing needs fluca_b200_prepare_step first");
+  cudaEvent_t e0, e1;
+  FL_CUDA(cudaEventCreate(&e0));
+  FL_CUDA(cudaEventCreate(&e1));
+  auto run = [&](int k) {
+    for (int r = 0; r < k; ++r) {
+      if (n == "momentum_apply") a_apply(s, s.kp, s.kv);
+      else if (n == "poisson_apply") poisson_apply(s, s.pp, s.pq);
+      else if (n == "mg_vcycle") (void)mg_vcycle(s, s.pr);
+      else throw Error(FL_ERR_ARG, "unknown kernel name");
+    }
+  };
+  run(2);
+  s.ex.sync();
+  FL_CUDA(cudaEventRecord(e0, s.ex.stream));
+  run(reps);
+  FL_CUDA(cudaEventRecord(e1, s.ex.stream));
+  FL_CUDA(cudaEventSynchronize(e1));
+  float t = 0.f;
+  FL_CUDA(cudaEventElapsedTime(&t, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms = (double)t / reps;
+  const bool d3 = (s.dim == 3);
+  if (n == "momentum_apply") *bytes = (d3 ? 96. : 64.) * N;
+  else if (n == "poisson_apply") *bytes = 16. * N;
+  else *bytes = (d3 ? 122. * 8. / 7. : 122. * 4. / 3.) * N;
+#endif
+  API_END
+}

@@ -1,0 +1,328 @@
+// krylov.cu -- inner Krylov solvers of the ABF application.
+//
+//   momentum_solve : A v* = r_mom  (KSPSolve(abf->kspA), abfpc.c:72).  A is non-symmetric and
+//                    strongly diagonally dominant (I + O(dt)): unpreconditioned BiCGStab with the
+//                    dot products fused into the matrix-free A apply and the vector updates.
+//   poisson_solve  : P p' = s      (KSPSolve(abf->kspS), abfpc.c:77).  P = vol * (-D Gst0) is
+//                    symmetric positive semi-definite unless a pressure outlet exists: CG
+//                    preconditioned by one geometric-multigrid V-cycle; with an outlet the one-sided
+//                    wall derivative makes the boundary rows non-symmetric and the same V-cycle
+//                    right-preconditions BiCGStab.
+// Convergence is tested on the true residual 2-norm relative to the right-hand side (the reference's
+// inner KSPs use PETSc's default preconditioned norm with ILU(0); inner histories cannot match
+// pointwise across preconditioners, SURVEY.md section 7 "hard parts").
+#include "solver.h"
+
+namespace fluca {
+
+static Box cell_box(const Solver &s)
+{
+  Box b = {s.gh.g.nx, s.gh.g.ny, s.gh.g.nzl};
+  return b;
+}
+
+// y = A x fused with acc[0] += <a, y>, acc[1] += <y, y>
+template <int DIM>
+struct AApplyDots {
+  Geom       g;
+  StepParams sp;
+  BcDev      bc;
+  CV3        x, v0, U0, a;
+  V3         y;
+  FL_HD void operator()(int i, int j, int kl, double acc[2]) const
+  {
+    double r[DIM];
+    a_apply_cell<DIM>(g, sp, bc, x, v0, U0, i, j, kl, r);
+    const long c = g.idx(i, j, kl);
+    double     d0 = 0., d1 = 0.;
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) {
+      y.c[q][c] = r[q];
+      d0 += a.c[q][c] * r[q];
+      d1 += r[q] * r[q];
+    }
+    acc[0] += d0;
+    acc[1] += d1;
+  }
+};
+
+static void a_apply_dots(Solver &s, const V3 &x, const V3 &y, const V3 &a, double out[2])
+{
+  halo_cells(s, x);
+  {
+    KTimer kt(s.ex, KT_MOMENTUM_APPLY);
+    if (s.dim == 2) {
+      AApplyDots<2> f;
+      f.g = s.gh.g, f.sp = s.sp, f.bc = s.bc, f.x = CV3(x), f.v0 = CV3(s.v0), f.U0 = CV3(s.U0), f.a = CV3(a), f.y = y;
+      for_box_reduce<2>(s.ex, cell_box(s), f);
+    } else {
+      AApplyDots<3> f;
+      f.g = s.gh.g, f.sp = s.sp, f.bc = s.bc, f.x = CV3(x), f.v0 = CV3(s.v0), f.U0 = CV3(s.U0), f.a = CV3(a), f.y = y;
+      for_box_reduce<2>(s.ex, cell_box(s), f);
+    }
+  }
+  reduce_finish(s, 2, out);
+}
+
+struct P3 { // three component pointers offset to the interior planes
+  double *c[3];
+};
+static P3 off3(const Solver &s, const V3 &v)
+{
+  P3 r;
+  for (int q = 0; q < 3; ++q) r.c[q] = v.c[q] ? v.c[q] + interior_off(s) : nullptr;
+  return r;
+}
+
+int momentum_solve(Solver &s, const V3 &b, const V3 &x)
+{
+  const int    nc  = s.dim;
+  const long   len = interior_len(s);
+  const P3     B = off3(s, b), X = off3(s, x), R = off3(s, s.kr), RH = off3(s, s.krh), PV = off3(s, s.kp), VV = off3(s, s.kv), SV = off3(s, s.ks), TV = off3(s, s.kt);
+  double       red[4];
+  // x = 0, r = rhat = p = b, rho = <b, b>
+  for_range_reduce<1>(s.ex, len, FL_LAMBDA(long i, double acc[1]) {
+    double t = 0.;
+    for (int q = 0; q < nc; ++q) {
+      const double bv = B.c[q][i];
+      X.c[q][i]  = 0.;
+      R.c[q][i]  = bv;
+      RH.c[q][i] = bv;
+      PV.c[q][i] = bv;
+      t += bv * bv;
+    }
+    acc[0] += t;
+  });
+  reduce_finish(s, 1, red);
+  const double bnorm = std::sqrt(red[0]);
+  s.stats.mom_last_rel = 0.;
+  if (bnorm == 0.) return 0;
+  if (!(bnorm == bnorm)) throw Error(FL_ERR_DIVERGED, "momentum right-hand side is NaN");
+  const double tol = s.opt.mom_rtol * bnorm;
+  double       rho = red[0], alpha = 1., omega = 1.;
+  int          it = 0;
+  for (; it < s.opt.inner_maxit;) {
+    // v = A p, <rhat, v>
+    a_apply_dots(s, s.kp, s.kv, s.krh, red);
+    const double rhv = red[0];
+    if (rhv == 0. || !(rhv == rhv)) throw Error(FL_ERR_DIVERGED, "BiCGStab breakdown in the momentum solve (<rhat, A p> = 0)");
+    alpha = rho / rhv;
+    // s = r - alpha v, |s|^2
+    for_range_reduce<1>(s.ex, len, FL_LAMBDA(long i, double acc[1]) {
+      double t = 0.;
+      for (int q = 0; q < nc; ++q) {
+        const double sv = R.c[q][i] - alpha * VV.c[q][i];
+        SV.c[q][i]      = sv;
+        t += sv * sv;
+      }
+      acc[0] += t;
+    });
+    reduce_finish(s, 1, red);
+    ++it;
+    if (std::sqrt(red[0]) <= tol) {
+      for_range(s.ex, len, FL_LAMBDA(long i) {
+        for (int q = 0; q < nc; ++q) X.c[q][i] += alpha * PV.c[q][i];
+      });
+      s.stats.mom_last_rel = std::sqrt(red[0]) / bnorm;
+      break;
+    }
+    // t = A s, <s, t>, <t, t>
+    a_apply_dots(s, s.ks, s.kt, s.ks, red);
+    if (red[1] == 0.) throw Error(FL_ERR_DIVERGED, "BiCGStab breakdown in the momentum solve (A s = 0)");
+    omega = red[0] / red[1];
+    // x += alpha p + omega s ; r = s - omega t ; |r|^2, <rhat, r>
+    for_range_reduce<2>(s.ex, len, FL_LAMBDA(long i, double acc[2]) {
+      double t0 = 0., t1 = 0.;
+      for (int q = 0; q < nc; ++q) {
+        const double sv = SV.c[q][i];
+        X.c[q][i] += alpha * PV.c[q][i] + omega * sv;
+        const double rv = sv - omega * TV.c[q][i];
+        R.c[q][i]       = rv;
+        t0 += rv * rv;
+        t1 += RH.c[q][i] * rv;
+      }
+      acc[0] += t0;
+      acc[1] += t1;
+    });
+    reduce_finish(s, 2, red);
+    s.stats.mom_last_rel = std::sqrt(red[0]) / bnorm;
+    if (std::sqrt(red[0]) <= tol) break;
+    if (!(red[0] == red[0])) throw Error(FL_ERR_DIVERGED, "momentum residual is NaN");
+    const double rho_new = red[1];
+    if (rho_new == 0. || omega == 0.) throw Error(FL_ERR_DIVERGED, "BiCGStab breakdown in the momentum solve (rho = 0)");
+    const double beta = (rho_new / rho) * (alpha / omega);
+    rho               = rho_new;
+    // p = r + beta (p - omega v)
+    for_range(s.ex, len, FL_LAMBDA(long i) {
+      for (int q = 0; q < nc; ++q) PV.c[q][i] = R.c[q][i] + beta * (PV.c[q][i] - omega * VV.c[q][i]);
+    });
+  }
+  s.stats.mom_its += it;
+  return (it >= s.opt.inner_maxit) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------ Poisson
+template <int DIM>
+struct PoissonApplyDot { // out = P p ; acc[0] += <a, out>
+  Geom          g;
+  const double *p, *a;
+  double       *out;
+  FL_HD void operator()(int i, int j, int kl, double acc[1]) const
+  {
+    Nbr<DIM> nb;
+    nbr<DIM>(g, i, j, kl, nb);
+    const double v = poisson_apply_cell<DIM>(g, p, nb);
+    out[nb.c]      = v;
+    acc[0] += a[nb.c] * v;
+  }
+};
+
+static double poisson_apply_dot(Solver &s, double *pin, double *out, const double *a)
+{
+  halo_scalar(s, pin);
+  {
+    KTimer kt(s.ex, KT_POISSON_APPLY);
+    if (s.dim == 2) {
+      PoissonApplyDot<2> f;
+      f.g = s.gh.g, f.p = pin, f.a = a, f.out = out;
+      for_box_reduce<1>(s.ex, cell_box(s), f);
+    } else {
+      PoissonApplyDot<3> f;
+      f.g = s.gh.g, f.p = pin, f.a = a, f.out = out;
+      for_box_reduce<1>(s.ex, cell_box(s), f);
+    }
+  }
+  double r;
+  reduce_finish(s, 1, &r);
+  return r;
+}
+
+void poisson_apply(Solver &s, double *pin, double *out)
+{
+  (void)poisson_apply_dot(s, pin, out, pin);
+}
+
+static int poisson_pcg(Solver &s, double *b, double *x)
+{
+  const long off = interior_off(s), len = interior_len(s);
+  double    *B = b + off, *X = x + off, *R = s.pr + off, *PP = s.pp + off, *Q = s.pq + off;
+  double     red[2];
+  for_range_reduce<1>(s.ex, len, FL_LAMBDA(long i, double acc[1]) {
+    const double bv = B[i];
+    X[i] = 0.;
+    R[i] = bv;
+    acc[0] += bv * bv;
+  });
+  reduce_finish(s, 1, red);
+  const double bnorm = std::sqrt(red[0]);
+  s.stats.schur_last_rel = 0.;
+  if (bnorm == 0.) return 0;
+  if (!(bnorm == bnorm)) throw Error(FL_ERR_DIVERGED, "Poisson right-hand side is NaN");
+  const double tol = s.opt.schur_rtol * bnorm;
+  double       rz = 0.;
+  int          it = 0;
+  for (; it < s.opt.inner_maxit;) {
+    const double *Z = mg_vcycle(s, s.pr) + off;
+    // rz_new = <r, z>
+    for_range_reduce<1>(s.ex, len, FL_LAMBDA(long i, double acc[1]) { acc[0] += R[i] * Z[i]; });
+    reduce_finish(s, 1, red);
+    const double rz_new = red[0];
+    if (it == 0) {
+      for_range(s.ex, len, FL_LAMBDA(long i) { PP[i] = Z[i]; });
+    } else {
+      const double beta = rz_new / rz;
+      for_range(s.ex, len, FL_LAMBDA(long i) { PP[i] = Z[i] + beta * PP[i]; });
+    }
+    rz = rz_new;
+    const double pq = poisson_apply_dot(s, s.pp, s.pq, s.pp);
+    if (!(pq > 0.)) {
+      if (pq == 0.) break;
+      throw Error(FL_ERR_DIVERGED, "CG breakdown in the pressure solve (<p, P p> <= 0 or NaN)");
+    }
+    const double alpha = rz / pq;
+    for_range_reduce<1>(s.ex, len, FL_LAMBDA(long i, double acc[1]) {
+      X[i] += alpha * PP[i];
+      const double rv = R[i] - alpha * Q[i];
+      R[i]            = rv;
+      acc[0] += rv * rv;
+    });
+    reduce_finish(s, 1, red);
+    ++it;
+    s.stats.schur_last_rel = std::sqrt(red[0]) / bnorm;
+    if (std::sqrt(red[0]) <= tol) break;
+  }
+  s.stats.schur_its += it;
+  return (it >= s.opt.inner_maxit) ? 1 : 0;
+}
+
+// right-preconditioned BiCGStab (pressure outlet present: boundary rows of P are not symmetric)
+static int poisson_bicgstab(Solver &s, double *b, double *x)
+{
+  const long off = interior_off(s), len = interior_len(s);
+  double    *B = b + off, *X = x + off, *R = s.pr + off, *RH = s.prh + off, *PP = s.pp + off, *V = s.pq + off, *S = s.ps + off, *T = s.pt + off;
+  double     red[2];
+  for_range_reduce<1>(s.ex, len, FL_LAMBDA(long i, double acc[1]) {
+    const double bv = B[i];
+    X[i]  = 0.;
+    R[i]  = bv;
+    RH[i] = bv;
+    PP[i] = bv;
+    acc[0] += bv * bv;
+  });
+  reduce_finish(s, 1, red);
+  const double bnorm = std::sqrt(red[0]);
+  s.stats.schur_last_rel = 0.;
+  if (bnorm == 0.) return 0;
+  if (!(bnorm == bnorm)) throw Error(FL_ERR_DIVERGED, "Poisson right-hand side is NaN");
+  const double tol = s.opt.schur_rtol * bnorm;
+  double       rho = red[0], alpha = 1., omega = 1.;
+  int          it = 0;
+  for (; it < s.opt.inner_maxit;) {
+    double       *yf = mg_vcycle(s, s.pp); // y = M^-1 p
+    const double *Y  = yf + off;
+    const double  rhv = poisson_apply_dot(s, yf, s.pq, s.prh);
+    if (rhv == 0. || !(rhv == rhv)) throw Error(FL_ERR_DIVERGED, "BiCGStab breakdown in the pressure solve");
+    alpha = rho / rhv;
+    for_range_reduce<1>(s.ex, len, FL_LAMBDA(long i, double acc[1]) {
+      const double sv = R[i] - alpha * V[i];
+      S[i]            = sv;
+      X[i] += alpha * Y[i];
+      acc[0] += sv * sv;
+    });
+    reduce_finish(s, 1, red);
+    ++it;
+    s.stats.schur_last_rel = std::sqrt(red[0]) / bnorm;
+    if (std::sqrt(red[0]) <= tol) break;
+    double       *zf = mg_vcycle(s, s.ps); // z = M^-1 s  (y is dead by now: x was updated above)
+    const double *Z  = zf + off;
+    const double  ts = poisson_apply_dot(s, zf, s.pt, s.ps);
+    for_range_reduce<1>(s.ex, len, FL_LAMBDA(long i, double acc[1]) { acc[0] += T[i] * T[i]; });
+    reduce_finish(s, 1, red);
+    if (red[0] == 0.) throw Error(FL_ERR_DIVERGED, "BiCGStab breakdown in the pressure solve (P z = 0)");
+    omega = ts / red[0];
+    for_range_reduce<2>(s.ex, len, FL_LAMBDA(long i, double acc[2]) {
+      X[i] += omega * Z[i];
+      const double rv = S[i] - omega * T[i];
+      R[i]            = rv;
+      acc[0] += rv * rv;
+      acc[1] += RH[i] * rv;
+    });
+    reduce_finish(s, 2, red);
+    s.stats.schur_last_rel = std::sqrt(red[0]) / bnorm;
+    if (std::sqrt(red[0]) <= tol) break;
+    if (!(red[0] == red[0])) throw Error(FL_ERR_DIVERGED, "pressure residual is NaN");
+    if (red[1] == 0. || omega == 0.) throw Error(FL_ERR_DIVERGED, "BiCGStab breakdown in the pressure solve (rho = 0)");
+    const double beta = (red[1] / rho) * (alpha / omega);
+    rho               = red[1];
+    for_range(s.ex, len, FL_LAMBDA(long i) { PP[i] = R[i] + beta * (PP[i] - omega * V[i]); });
+  }
+  s.stats.schur_its += it;
+  return (it >= s.opt.inner_maxit) ? 1 : 0;
+}
+
+int poisson_solve(Solver &s, double *b, double *x)
+{
+  return s.has_outlet ? poisson_bicgstab(s, b, x) : poisson_pcg(s, b, x);
+}
+
+} // namespace fluca

@@ -1,0 +1,334 @@
+// mg.cu -- matrix-free geometric multigrid V-cycle, the preconditioner of the pressure solve.
+//
+// Replaces the ILU(0) that PETSc applies to the explicitly formed Schur complement S
+// (abfpc.c:151-180; S = -(dt/rho) D Gst is a 5/7-point Laplacian with Neumann rows at walls).
+// Cell-centred, finite-volume (flux) form on the rectilinear product grid:
+//   (P x)_c = sum_d area_d [ k_d(lo) (x_c - x_lo) + k_d(hi) (x_c - x_hi) ],   k = 1 / centre distance
+// Components (chosen with tools/mg_prototype.py: 5 PCG iterations for 1e-5, 8 for 1e-8, mesh
+// independent): damped-Jacobi smoothing (order independent => identical on any slab partition),
+// residual fused with summation restriction (flux-form residuals are extensive), trilinear
+// prolongation fused with the correction, rediscretised coarse operators, coarsening by 2 per
+// direction while the (local) size stays even.  At pressure outlets the hierarchy uses a plain
+// first-order Dirichlet row; the Krylov method outside applies the exact one-sided operator.
+#include "solver.h"
+
+namespace fluca {
+
+namespace {
+
+template <int DIM>
+FL_HD void mg_row(const MGLevel &L, const double *__restrict__ x, int i, int j, int kl, double &Ax, double &diag)
+{
+  const long   c  = L.idx(i, j, kl);
+  const double xc = x[c];
+  const double hx = L.h[0][i], hy = L.h[1][j];
+  const double hz = (DIM == 3) ? L.h[2][L.k0 + kl] : 1.;
+  const double ax = hy * hz, ay = hx * hz, az = hx * hy;
+  double       s = 0., dg = 0.;
+  {
+    const int    n  = L.n[0];
+    const double kl_ = L.kf[0][i], ku = L.kf[0][i + 1];
+    const double xm = i > 0 ? x[c - 1] : (L.per[0] ? x[c + (n - 1)] : 0.);
+    const double xp = i < n - 1 ? x[c + 1] : (L.per[0] ? x[c - (n - 1)] : 0.);
+    s += ax * (kl_ * (xc - xm) + ku * (xc - xp));
+    dg += ax * (kl_ + ku);
+  }
+  {
+    const int    n  = L.n[1];
+    const double kl_ = L.kf[1][j], ku = L.kf[1][j + 1];
+    const double xm = j > 0 ? x[c - L.px] : (L.per[1] ? x[c + (long)(n - 1) * L.px] : 0.);
+    const double xp = j < n - 1 ? x[c + L.px] : (L.per[1] ? x[c - (long)(n - 1) * L.px] : 0.);
+    s += ay * (kl_ * (xc - xm) + ku * (xc - xp));
+    dg += ay * (kl_ + ku);
+  }
+  if (DIM == 3) {
+    const int    kg = L.k0 + kl;
+    const double kl_ = L.kf[2][kg], ku = L.kf[2][kg + 1];
+    // ghost planes: neighbour rank / periodic wrap, or zeros at a wall
+    const double xm = x[c - L.plane], xp = x[c + L.plane];
+    s += az * (kl_ * (xc - xm) + ku * (xc - xp));
+    dg += az * (kl_ + ku);
+  }
+  Ax   = s;
+  diag = dg;
+}
+
+template <int DIM>
+struct MGSmooth {
+  MGLevel       L;
+  double        omega;
+  int           zero_guess;
+  const double *xin, *b;
+  double       *xout;
+  FL_HD void operator()(int i, int j, int kl) const
+  {
+    const long c = L.idx(i, j, kl);
+    double     Ax, dg;
+    if (zero_guess) {
+      // diag only
+      const double hx = L.h[0][i], hy = L.h[1][j], hz = (DIM == 3) ? L.h[2][L.k0 + kl] : 1.;
+      dg = hy * hz * (L.kf[0][i] + L.kf[0][i + 1]) + hx * hz * (L.kf[1][j] + L.kf[1][j + 1]);
+      if (DIM == 3) dg += hx * hy * (L.kf[2][L.k0 + kl] + L.kf[2][L.k0 + kl + 1]);
+      xout[c] = dg > 0. ? omega * b[c] / dg : 0.;
+      return;
+    }
+    mg_row<DIM>(L, xin, i, j, kl, Ax, dg);
+    xout[c] = dg > 0. ? xin[c] + omega * (b[c] - Ax) / dg : xin[c];
+  }
+};
+
+// coarse b = sum over children of (b - P x)
+template <int DIM>
+struct MGResidRestrict {
+  MGLevel F, C;
+  FL_HD void operator()(int I, int J, int K) const
+  {
+    double    s   = 0.;
+    const int cfz = (DIM == 3) ? F.cf[2] : 1;
+    for (int dk = 0; dk < cfz; ++dk)
+      for (int dj = 0; dj < F.cf[1]; ++dj)
+        for (int di = 0; di < F.cf[0]; ++di) {
+          const int i = F.cf[0] * I + di, j = F.cf[1] * J + dj, kl = cfz * K + dk;
+          double    Ax, dg;
+          mg_row<DIM>(F, F.x, i, j, kl, Ax, dg);
+          s += F.b[F.idx(i, j, kl)] - Ax;
+        }
+    C.b[C.idx(I, J, K)] = s;
+  }
+};
+
+// 1-D cell-centred linear interpolation: fine index i -> coarse (I0, w0), (I1, w1)
+FL_HD void interp1(int i, int cf, int nc, int per, int &I0, int &I1, double &w1)
+{
+  if (cf == 1) {
+    I0 = I1 = i;
+    w1 = 0.;
+    return;
+  }
+  I0 = i >> 1;
+  I1 = (i & 1) ? I0 + 1 : I0 - 1;
+  w1 = 0.25;
+  if (I1 < 0) {
+    if (per) I1 = nc - 1;
+    else I1 = I0, w1 = 0.;
+  } else if (I1 >= nc) {
+    if (per) I1 = 0;
+    else I1 = I0, w1 = 0.;
+  }
+}
+
+template <int DIM>
+struct MGProlong {
+  MGLevel F, C;
+  FL_HD void operator()(int i, int j, int kl) const
+  {
+    int    I0, I1, J0, J1;
+    double wi, wj;
+    interp1(i, F.cf[0], C.n[0], C.per[0], I0, I1, wi);
+    interp1(j, F.cf[1], C.n[1], C.per[1], J0, J1, wj);
+    const double *e = C.x;
+    double        v;
+    if (DIM == 3) {
+      // z: local coarse index with ghost planes; clamp only at a physical wall
+      int    K0, K1;
+      double wk;
+      if (F.cf[2] == 1) K0 = K1 = kl, wk = 0.;
+      else {
+        K0 = kl >> 1;
+        K1 = (kl & 1) ? K0 + 1 : K0 - 1;
+        wk = 0.25;
+        if (K1 < 0 && C.wall_lo_z) K1 = K0, wk = 0.;
+        if (K1 >= C.nzl && C.wall_hi_z) K1 = K0, wk = 0.;
+      }
+      double a0 = (1. - wi) * ((1. - wj) * e[C.idx(I0, J0, K0)] + wj * e[C.idx(I0, J1, K0)]) + wi * ((1. - wj) * e[C.idx(I1, J0, K0)] + wj * e[C.idx(I1, J1, K0)]);
+      double a1 = (1. - wi) * ((1. - wj) * e[C.idx(I0, J0, K1)] + wj * e[C.idx(I0, J1, K1)]) + wi * ((1. - wj) * e[C.idx(I1, J0, K1)] + wj * e[C.idx(I1, J1, K1)]);
+      v         = (1. - wk) * a0 + wk * a1;
+    } else {
+      v = (1. - wi) * ((1. - wj) * e[C.idx(I0, J0, 0)] + wj * e[C.idx(I0, J1, 0)]) + wi * ((1. - wj) * e[C.idx(I1, J0, 0)] + wj * e[C.idx(I1, J1, 0)]);
+    }
+    F.x[F.idx(i, j, kl)] += v;
+  }
+};
+
+const double *upload_mg(Solver &s, const std::vector<double> &v)
+{
+  double *d = (double *)dev_alloc(sizeof(double) * v.size());
+  copy_h2d(s.ex, d, v.data(), sizeof(double) * v.size());
+  s.ex.sync();
+  s.mg_owned.push_back(d);
+  return d;
+}
+
+void level_tables(Solver &s, MGLevel &L, const std::vector<double> xf[3], const int bc[6])
+{
+  for (int d = 0; d < 3; ++d) {
+    const int           n = L.n[d];
+    std::vector<double> h(n), kf(n + 1, 0.), xc(n);
+    if (d >= s.dim) {
+      h.assign(1, 1.);
+      kf.assign(2, 0.);
+      L.h[d]  = upload_mg(s, h);
+      L.kf[d] = upload_mg(s, kf);
+      continue;
+    }
+    for (int i = 0; i < n; ++i) h[i] = xf[d][i + 1] - xf[d][i], xc[i] = 0.5 * (xf[d][i] + xf[d][i + 1]);
+    for (int f = 1; f < n; ++f) kf[f] = 1. / (xc[f] - xc[f - 1]);
+    if (L.per[d]) {
+      const double len = xf[d][n] - xf[d][0];
+      kf[0] = kf[n] = 1. / (xc[0] + len - xc[n - 1]);
+    } else {
+      if (bc[2 * d] == BC_PRESSURE_OUTLET) kf[0] = 1. / (xc[0] - xf[d][0]);
+      if (bc[2 * d + 1] == BC_PRESSURE_OUTLET) kf[n] = 1. / (xf[d][n] - xc[n - 1]);
+    }
+    L.h[d]  = upload_mg(s, h);
+    L.kf[d] = upload_mg(s, kf);
+  }
+}
+
+Box level_box(const MGLevel &L)
+{
+  Box b = {L.n[0], L.n[1], L.nzl};
+  return b;
+}
+
+void level_halo(Solver &s, MGLevel &L, double *x)
+{
+  if (s.dim != 3) return;
+  double *f[1] = {x};
+  s.comm->halo(s.ex, f, 1, L.plane, L.nzl, L.per[2] != 0);
+}
+
+template <int DIM>
+void smooth(Solver &s, MGLevel &L, bool zero_guess)
+{
+  const double omega = (DIM == 3) ? 6. / 7. : 0.8;
+  if (!zero_guess) level_halo(s, L, L.x);
+  KTimer        kt(s.ex, KT_MG_SMOOTH);
+  MGSmooth<DIM> f;
+  f.L = L, f.omega = omega, f.zero_guess = zero_guess ? 1 : 0, f.xin = L.x, f.b = L.b, f.xout = zero_guess ? L.x : L.t;
+  for_box(s.ex, level_box(L), f);
+  if (!zero_guess) {
+    double *tmp = L.x;
+    L.x         = L.t;
+    L.t         = tmp;
+  }
+}
+
+template <int DIM>
+void vcycle(Solver &s, size_t l)
+{
+  MGLevel &L = s.mg[l];
+  const bool coarsest = (l + 1 == s.mg.size());
+  if (coarsest) {
+    smooth<DIM>(s, L, true);
+    for (int k = 1; k < s.opt.mg_coarse_sweeps; ++k) smooth<DIM>(s, L, false);
+    return;
+  }
+  smooth<DIM>(s, L, true);
+  for (int k = 1; k < s.opt.mg_nu1; ++k) smooth<DIM>(s, L, false);
+  MGLevel &C = s.mg[l + 1];
+  level_halo(s, L, L.x);
+  {
+    KTimer               kt(s.ex, KT_MG_TRANSFER);
+    MGResidRestrict<DIM> rr;
+    rr.F = L, rr.C = C;
+    for_box(s.ex, level_box(C), rr);
+  }
+  vcycle<DIM>(s, l + 1);
+  level_halo(s, C, C.x);
+  {
+    KTimer         kt(s.ex, KT_MG_TRANSFER);
+    MGProlong<DIM> pr;
+    pr.F = L, pr.C = C;
+    for_box(s.ex, level_box(L), pr);
+  }
+  for (int k = 0; k < s.opt.mg_nu2; ++k) smooth<DIM>(s, L, false);
+}
+
+} // namespace
+
+void mg_setup(Solver &s)
+{
+  const Geom &g = s.gh.g;
+  int         bc[6];
+  for (int d = 0; d < 3; ++d) bc[2 * d] = g.t[d].bc_lo, bc[2 * d + 1] = g.t[d].bc_hi;
+  std::vector<double> xf[3];
+  for (int d = 0; d < s.dim; ++d) xf[d] = s.gh.xf[d];
+  const bool equal_slabs = (g.nzl * g.nranks == g.nzg);
+
+  MGLevel L;
+  memset(&L, 0, sizeof(L));
+  L.n[0] = g.nx, L.n[1] = g.ny, L.n[2] = g.nzg;
+  L.nzl = g.nzl, L.k0 = g.k0, L.px = g.px, L.py = g.py, L.plane = g.plane, L.nalloc = g.nalloc;
+  for (int d = 0; d < 3; ++d) L.per[d] = d < s.dim ? g.t[d].per : 0;
+  L.wall_lo_z = g.t[2].wall_lo, L.wall_hi_z = g.t[2].wall_hi;
+  for (int lev = 0; lev < 24; ++lev) {
+    level_tables(s, L, xf, bc);
+    // level 0 borrows b from the Krylov solver (mg_vcycle); x and the Jacobi scratch t are owned
+    L.own_x = true, L.own_b = (lev > 0);
+    L.b = nullptr;
+    L.x = (double *)dev_alloc(sizeof(double) * (size_t)L.nalloc);
+    s.mg_owned.push_back(L.x);
+    if (lev > 0) {
+      L.b = (double *)dev_alloc(sizeof(double) * (size_t)L.nalloc);
+      s.mg_owned.push_back(L.b);
+    }
+    L.t = (double *)dev_alloc(sizeof(double) * (size_t)L.nalloc);
+    s.mg_owned.push_back(L.t);
+    // coarsening decision (identical on every rank)
+    int  cf[3] = {1, 1, 1};
+    bool any   = false;
+    for (int d = 0; d < s.dim; ++d) {
+      bool ok = (L.n[d] % 2 == 0) && (L.n[d] >= 4);
+      if (d == 2) ok = (L.n[2] % 2 == 0) && equal_slabs && (L.nzl % 2 == 0) && (g.nranks > 1 ? L.nzl >= 2 : L.n[2] >= 4);
+      if (ok) cf[d] = 2, any = true;
+    }
+    if (!any) {
+      L.cf[0] = L.cf[1] = L.cf[2] = 0;
+      s.mg.push_back(L);
+      break;
+    }
+    for (int d = 0; d < 3; ++d) L.cf[d] = cf[d];
+    s.mg.push_back(L);
+    // next level
+    MGLevel Cn;
+    memset(&Cn, 0, sizeof(Cn));
+    for (int d = 0; d < 3; ++d) {
+      Cn.n[d]   = L.n[d] / cf[d];
+      Cn.per[d] = L.per[d];
+      if (d < s.dim) {
+        std::vector<double> c(Cn.n[d] + 1);
+        for (int i = 0; i <= Cn.n[d]; ++i) c[i] = xf[d][(size_t)i * cf[d]];
+        xf[d] = c;
+      }
+    }
+    Cn.nzl = L.nzl / cf[2], Cn.k0 = L.k0 / cf[2];
+    Cn.px     = ((Cn.n[0] + 7) / 8) * 8;
+    Cn.py     = Cn.n[1];
+    Cn.plane  = (long)Cn.px * Cn.py;
+    Cn.nalloc = Cn.plane * (Cn.nzl + 2);
+    Cn.wall_lo_z = L.wall_lo_z, Cn.wall_hi_z = L.wall_hi_z;
+    L = Cn;
+  }
+}
+
+void mg_destroy(Solver &s)
+{
+  for (void *p : s.mg_owned) dev_free(p);
+  s.mg_owned.clear();
+  s.mg.clear();
+}
+
+// returns z = V-cycle(r) with zero initial guess.  r is a fine-level field (Geom layout); the result
+// lives in a level-0 buffer (same layout, ghost planes included) that stays valid until the next call.
+double *mg_vcycle(Solver &s, double *r)
+{
+  MGLevel &L0 = s.mg[0];
+  L0.b        = r;
+  if (s.dim == 2) vcycle<2>(s, 0);
+  else vcycle<3>(s, 0);
+  L0.b = nullptr;
+  return L0.x;
+}
+
+} // namespace fluca

@@ -1,0 +1,170 @@
+// solver.h -- device-resident state of one rank's slab and the solver entry points.
+#pragma once
+#include "geom.h"
+#include "stencil.h"
+#include <memory>
+
+namespace fluca {
+
+// ------------------------------------------------------------------ communication (z-slab partition)
+// One process per GPU.  The data path needs exactly two collectives:
+//   halo   : ghost-plane exchange with the two z neighbours (ncclSend/ncclRecv, grouped)
+//   allsum : Krylov dot products / means (ncclAllReduce on a tiny device buffer)
+struct Comm {
+  int rank = 0, nranks = 1;
+  virtual ~Comm() { }
+  // fields[f] points at the start of an array laid out as (nzl + 2) planes of `plane` doubles.
+  // Sends plane 0 down / plane nzl-1 up, receives into plane nzl / plane -1.
+  virtual void halo(Exec &ex, double *const *fields, int nf, long plane, int nzl, bool periodic) = 0;
+  // in-place sum over ranks of n doubles in device memory
+  virtual void allsum(Exec &ex, double *dev, int n) = 0;
+  // gathers `count` doubles from every rank (device), rank-major
+  virtual void allgather(Exec &ex, const double *send, double *recv, long count) = 0;
+  virtual void barrier(Exec &ex) { (void)ex; }
+};
+
+struct LocalComm : public Comm {
+  void halo(Exec &ex, double *const *fields, int nf, long plane, int nzl, bool periodic) override;
+  void allsum(Exec &, double *, int) override { }
+  void allgather(Exec &ex, const double *send, double *recv, long count) override { copy_d2d(ex, recv, send, sizeof(double) * count); }
+};
+
+// host-callback communicator: used by the CPU (gloo) tests of the multi-rank logic, and available
+// to an MPI host (the PETSc glue) when NCCL is not bootstrapped.  Buffers are host pointers.
+typedef int (*fl_halo_cb)(void *ctx, const double *send_down, double *recv_down, const double *send_up, double *recv_up, long count, int periodic);
+typedef int (*fl_allsum_cb)(void *ctx, double *vals, int n);
+typedef int (*fl_allgather_cb)(void *ctx, const double *send, double *recv, long count);
+struct CallbackComm : public Comm {
+  fl_halo_cb      halo_cb      = nullptr;
+  fl_allsum_cb    allsum_cb    = nullptr;
+  fl_allgather_cb allgather_cb = nullptr;
+  void           *ctx          = nullptr;
+  std::vector<double> hs0, hs1, hr0, hr1; // host staging (CUDA build)
+  void halo(Exec &ex, double *const *fields, int nf, long plane, int nzl, bool periodic) override;
+  void allsum(Exec &ex, double *dev, int n) override;
+  void allgather(Exec &ex, const double *send, double *recv, long count) override;
+};
+
+#ifndef FLUCA_HOSTEMU
+Comm *make_nccl_comm(const void *unique_id, int id_bytes, int rank, int nranks);
+int   nccl_unique_id(void *out, int bytes); // returns bytes written
+#endif
+
+// ------------------------------------------------------------------ multigrid level (cell-centred, flux form)
+struct MGLevel {
+  int  n[3];          // global cells per direction at this level (n[2] = 1 in 2-D)
+  int  nzl, k0;       // local slab
+  int  px, py;
+  long plane, nalloc;
+  int  per[3];
+  int  cf[3];         // coarsening factor towards the next level (1 or 2); 0,0,0 on the coarsest
+  const double *h[3]; // [n[d]]     cell widths
+  const double *kf[3]; // [n[d]+1]  face conductance 1/dist, 0 at Neumann walls, 1/(xc-xw) at outlet walls
+  int  wall_lo_z, wall_hi_z;
+  double *x, *b, *t;  // solution, right-hand side, scratch (Jacobi double buffer)
+  bool own_x, own_b;
+  FL_HD long idx(int i, int j, int kl) const { return (long)i + (long)px * ((long)j + (long)py * (long)(kl + 1)); }
+};
+
+struct Options {
+  int    mode          = 0;     // 0: coupled solve (outer GMRES, PC = ABF)   1: one ABF application
+  double outer_rtol    = 1e-5;  // nssol.c:24
+  int    outer_maxit   = 100;
+  int    outer_restart = 30;
+  double mom_rtol      = 1e-5;
+  double schur_rtol    = 1e-5;
+  int    inner_maxit   = 500;
+  int    mg_nu1 = 2, mg_nu2 = 2, mg_coarse_sweeps = 40;
+  int    quirk_bcg_scale = 1;
+};
+
+struct Stats {
+  int    outer_its = 0, mom_its = 0, schur_its = 0, abf_applies = 0, converged = 0;
+  double outer_rnorm0 = 0., outer_rnorm = 0.;
+  int    nhist = 0;
+  double hist[128];
+  long   launches = 0;
+  double mom_last_rel = 0., schur_last_rel = 0.;
+};
+
+struct Field {
+  double *d = nullptr;
+};
+
+struct Solver {
+  Exec      ex;
+  GeomHost  gh;
+  Options   opt;
+  StepParams sp;
+  std::unique_ptr<Comm> comm;
+  bool      has_outlet = false;
+  int       dim = 3;
+  // boundary values (device) + descriptor
+  BcDev     bc;
+  double   *bc_store[6][2][2] = {}; // [b][kind 0 vel / 1 prs][slot]
+
+  std::vector<double *> pool; // every field allocation (freed in destroy)
+  // state
+  V3      v, U, v0, U0;
+  double *p = nullptr, *phalf = nullptr;
+  // right-hand side b = (rm, ri, rc) and solve vector x = (xv, xU, xp)
+  V3      rm, ri, xv, xU;
+  double *rc = nullptr, *xp = nullptr;
+  // ABF temporaries
+  V3      vstar, Ustar;
+  double *srhs = nullptr;
+  // momentum BiCGStab
+  V3      kr, krh, kp, kv, ks, kt;
+  // Poisson Krylov
+  double *pr = nullptr, *pp = nullptr, *pq = nullptr, *ps = nullptr, *pt = nullptr, *prh = nullptr;
+  std::vector<MGLevel> mg;
+  std::vector<void *>  mg_owned;
+  // outer GMRES basis: (restart + 1) vectors of 7 fields, plus work vectors
+  std::vector<std::vector<double *>> basis;
+  V3      wv, wU, zv, zU, tw;
+  double *wp = nullptr, *zp = nullptr;
+  int     basis_size = 0;
+
+  Stats  stats;
+  int    step_index = 0;
+  double t          = 0.;
+  bool   prepared   = false;
+
+  double *alloc_field();
+  V3      alloc_v3();
+};
+
+// construction
+void solver_setup(Solver &s, int dim, const int n[3], const double *const xf[3], const int bc[6], double rho, double mu, double dt, const Options &opt, Comm *comm, int k0, int nzl);
+void solver_destroy(Solver &s);
+
+// halo helpers
+void halo_cells(Solver &s, const V3 &v);
+void halo_scalar(Solver &s, double *f);
+void halo_faces(Solver &s, const V3 &U);
+
+// reductions: finish the NR sums left in ex.d_result (sum over ranks, copy to host)
+void reduce_finish(Solver &s, int n, double *out);
+
+// flat vector extents
+long interior_len(const Solver &s);                 // plane * nzl
+long interior_off(const Solver &s);                 // plane (skip the lower ghost plane)
+long face_len(const Solver &s, int d);              // interior_len (+ one plane for z faces on the last wall rank)
+
+// operators (step.cu)
+void prepare_step(Solver &s, double t, int step_index);
+void a_apply(Solver &s, const V3 &x, const V3 &y);
+void abf_apply(Solver &s, const V3 &bm, const V3 &bi, const double *bcn, const V3 &ov, const V3 &oU, double *op);
+void coupled_apply(Solver &s, const V3 &xv, const V3 &xU, double *xp, const V3 &yv, const V3 &yU, double *yp);
+void schur_apply_reference_scaling(Solver &s, double *pin, double *out);
+int  do_step(Solver &s, double t, int step_index);
+
+// Krylov / multigrid (krylov.cu, mg.cu)
+int  momentum_solve(Solver &s, const V3 &b, const V3 &x);
+int  poisson_solve(Solver &s, double *b, double *x);
+void mg_setup(Solver &s);
+void mg_destroy(Solver &s);
+double *mg_vcycle(Solver &s, double *r);
+void poisson_apply(Solver &s, double *pin, double *out);
+
+} // namespace fluca

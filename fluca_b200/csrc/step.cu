@@ -1,0 +1,637 @@
+// step.cu -- the NS time step: right-hand side, ABF (fractional-step) application, coupled operator,
+// outer GMRES and the step driver.
+//
+// Host-side control flow mirrors NSStep_CNLinear_Cart3d_Internal (cnlinearcart3d.c:2807-2863),
+// NSFormFunction (:2945-3043), PCApply_ABF (abfpc.c:48-111) and the outer KSP the base class sets
+// up (nssol.c:13-30: GMRES, right-preconditioned because the norm is unpreconditioned, zero guess).
+#include "solver.h"
+
+namespace fluca {
+
+double *Solver::alloc_field()
+{
+  double *d = (double *)dev_alloc(sizeof(double) * (size_t)gh.g.nalloc);
+  pool.push_back(d);
+  return d;
+}
+V3 Solver::alloc_v3()
+{
+  V3 r;
+  r.c[0] = alloc_field();
+  r.c[1] = alloc_field();
+  r.c[2] = (dim == 3) ? alloc_field() : nullptr;
+  return r;
+}
+
+long interior_len(const Solver &s) { return s.gh.g.plane * s.gh.g.nzl; }
+long interior_off(const Solver &s) { return s.gh.g.plane; }
+long face_len(const Solver &s, int d)
+{
+  const Geom &g = s.gh.g;
+  return g.plane * g.nzl + ((d == 2 && g.t[2].wall_hi) ? g.plane : 0);
+}
+
+// ------------------------------------------------------------------ halos
+void LocalComm::halo(Exec &ex, double *const *fields, int nf, long plane, int nzl, bool periodic)
+{
+  if (!periodic) return;
+  for (int f = 0; f < nf; ++f) {
+    double *a = fields[f];
+    copy_d2d(ex, a, a + plane * nzl, sizeof(double) * plane);             // ghost -1 <- plane nzl-1
+    copy_d2d(ex, a + plane * (nzl + 1), a + plane, sizeof(double) * plane); // ghost nzl <- plane 0
+  }
+  ex.stats.launches += 2 * nf;
+}
+
+void CallbackComm::halo(Exec &ex, double *const *fields, int nf, long plane, int nzl, bool periodic)
+{
+  if (nranks == 1 && !periodic) return;
+  for (int f = 0; f < nf; ++f) {
+    double *a = fields[f];
+#ifdef FLUCA_HOSTEMU
+    int rc = halo_cb(ctx, a + plane, a, a + plane * nzl, a + plane * (nzl + 1), plane, periodic ? 1 : 0);
+#else
+    hs0.resize(plane), hs1.resize(plane), hr0.resize(plane), hr1.resize(plane);
+    copy_d2h(ex, hs0.data(), a + plane, sizeof(double) * plane);
+    copy_d2h(ex, hs1.data(), a + plane * nzl, sizeof(double) * plane);
+    copy_d2h(ex, hr0.data(), a, sizeof(double) * plane);
+    copy_d2h(ex, hr1.data(), a + plane * (nzl + 1), sizeof(double) * plane);
+    ex.sync();
+    int rc = halo_cb(ctx, hs0.data(), hr0.data(), hs1.data(), hr1.data(), plane, periodic ? 1 : 0);
+    copy_h2d(ex, a, hr0.data(), sizeof(double) * plane);
+    copy_h2d(ex, a + plane * (nzl + 1), hr1.data(), sizeof(double) * plane);
+    ex.sync();
+#endif
+    if (rc) throw Error(FL_ERR_INTERNAL, "halo callback failed");
+  }
+}
+void CallbackComm::allsum(Exec &ex, double *dev, int n)
+{
+  if (nranks == 1) return;
+#ifdef FLUCA_HOSTEMU
+  if (allsum_cb(ctx, dev, n)) throw Error(FL_ERR_INTERNAL, "allsum callback failed");
+#else
+  std::vector<double> h(n);
+  copy_d2h(ex, h.data(), dev, sizeof(double) * n);
+  ex.sync();
+  if (allsum_cb(ctx, h.data(), n)) throw Error(FL_ERR_INTERNAL, "allsum callback failed");
+  copy_h2d(ex, dev, h.data(), sizeof(double) * n);
+  ex.sync();
+#endif
+}
+void CallbackComm::allgather(Exec &ex, const double *send, double *recv, long count)
+{
+#ifdef FLUCA_HOSTEMU
+  if (allgather_cb(ctx, send, recv, count)) throw Error(FL_ERR_INTERNAL, "allgather callback failed");
+#else
+  std::vector<double> hs(count), hr(count * nranks);
+  copy_d2h(ex, hs.data(), send, sizeof(double) * count);
+  ex.sync();
+  if (allgather_cb(ctx, hs.data(), hr.data(), count)) throw Error(FL_ERR_INTERNAL, "allgather callback failed");
+  copy_h2d(ex, recv, hr.data(), sizeof(double) * count * nranks);
+  ex.sync();
+#endif
+}
+
+void halo_cells(Solver &s, const V3 &v)
+{
+  const Geom &g = s.gh.g;
+  if (g.dim != 3) return;
+  double *f[3] = {v.c[0], v.c[1], v.c[2]};
+  s.comm->halo(s.ex, f, 3, g.plane, g.nzl, g.t[2].per != 0);
+}
+void halo_scalar(Solver &s, double *p)
+{
+  const Geom &g = s.gh.g;
+  if (g.dim != 3) return;
+  double *f[1] = {p};
+  s.comm->halo(s.ex, f, 1, g.plane, g.nzl, g.t[2].per != 0);
+}
+void halo_faces(Solver &s, const V3 &U)
+{
+  // only the z-face field crosses slab boundaries (upper face of the last plane = BACK face of the
+  // next rank's first plane).  Its lower ghost plane is never read.
+  const Geom &g = s.gh.g;
+  if (g.dim != 3) return;
+  double *f[1] = {U.c[2]};
+  // on the last wall rank plane nzl holds owned FRONT faces: a non-periodic exchange never writes it
+  s.comm->halo(s.ex, f, 1, g.plane, g.nzl, g.t[2].per != 0);
+}
+
+void reduce_finish(Solver &s, int n, double *out)
+{
+  s.comm->allsum(s.ex, s.ex.d_result, n);
+  copy_d2h(s.ex, s.ex.h_result, s.ex.d_result, sizeof(double) * n);
+  s.ex.sync();
+  for (int i = 0; i < n; ++i) out[i] = s.ex.h_result[i];
+}
+
+// ------------------------------------------------------------------ setup
+void solver_setup(Solver &s, int dim, const int n[3], const double *const xf[3], const int bcin[6], double rho, double mu, double dt, const Options &opt, Comm *comm, int k0, int nzl)
+{
+  s.ex.init();
+  s.dim = dim;
+  s.opt = opt;
+  s.comm.reset(comm ? comm : new LocalComm());
+  int bc[6];
+  for (int b = 0; b < 6; ++b) bc[b] = (b < 2 * dim) ? bcin[b] : BC_NONE;
+  geom_build(s.gh, s.ex, dim, n, xf, bc, s.comm->rank, s.comm->nranks, k0, nzl);
+  const Geom &g = s.gh.g;
+  s.has_outlet = false;
+  for (int b = 0; b < 2 * dim; ++b)
+    if (bc[b] == BC_PRESSURE_OUTLET) s.has_outlet = true; // nsbasic.c:215-244
+  if (!(rho > 0.) || !(dt > 0.) || !(mu >= 0.)) throw Error(FL_ERR_ARG, "density and time step must be positive, viscosity non-negative");
+  s.sp.dt = dt, s.sp.rho = rho, s.sp.mu = mu;
+  s.sp.nu2   = 0.5 * mu * dt / rho;
+  s.sp.dtrho = dt / rho;
+  // cnlinearcart2d.c:2104,2109 scale by dt/rho; cnlinearcart3d.c:2977,2981 by 1
+  s.sp.sG = (dim == 3 && opt.quirk_bcg_scale) ? 1.0 : dt / rho;
+
+  memset(&s.bc, 0, sizeof(BcDev));
+  for (int b = 0; b < 2 * dim; ++b) {
+    const int d = b / 2;
+    long      np = d == 0 ? (long)g.ny * g.nzl : (d == 1 ? (long)g.nx * g.nzl : (long)g.nx * g.ny);
+    s.bc.npts[b] = np;
+    for (int slot = 0; slot < 2; ++slot) {
+      s.bc_store[b][0][slot] = (double *)dev_alloc(sizeof(double) * np * 3);
+      s.bc_store[b][1][slot] = (double *)dev_alloc(sizeof(double) * np);
+      s.bc.vel[b][slot]      = s.bc_store[b][0][slot];
+      s.bc.prs[b][slot]      = s.bc_store[b][1][slot];
+    }
+  }
+
+  s.v = s.alloc_v3(), s.U = s.alloc_v3(), s.v0 = s.alloc_v3(), s.U0 = s.alloc_v3();
+  s.p = s.alloc_field(), s.phalf = s.alloc_field();
+  s.rm = s.alloc_v3(), s.ri = s.alloc_v3(), s.rc = s.alloc_field();
+  s.xv = s.alloc_v3(), s.xU = s.alloc_v3(), s.xp = s.alloc_field();
+  s.vstar = s.alloc_v3(), s.Ustar = s.alloc_v3(), s.srhs = s.alloc_field();
+  s.kr = s.alloc_v3(), s.krh = s.alloc_v3(), s.kp = s.alloc_v3(), s.kv = s.alloc_v3(), s.ks = s.alloc_v3(), s.kt = s.alloc_v3();
+  s.pr = s.alloc_field(), s.pp = s.alloc_field(), s.pq = s.alloc_field();
+  if (s.has_outlet) s.ps = s.alloc_field(), s.pt = s.alloc_field(), s.prh = s.alloc_field();
+  s.tw = s.alloc_v3();
+  if (opt.mode == 0) {
+    s.basis_size = opt.outer_restart + 1;
+    s.basis.resize(s.basis_size);
+    for (auto &vec : s.basis) {
+      vec.resize(7, nullptr);
+      for (int f = 0; f < 7; ++f)
+        if (dim == 3 || (f != 2 && f != 5)) vec[f] = s.alloc_field();
+    }
+    s.wv = s.alloc_v3(), s.wU = s.alloc_v3(), s.wp = s.alloc_field();
+    s.zv = s.alloc_v3(), s.zU = s.alloc_v3(), s.zp = s.alloc_field();
+  }
+  mg_setup(s);
+  s.ex.sync();
+}
+
+void solver_destroy(Solver &s)
+{
+  s.ex.sync();
+  mg_destroy(s);
+  for (double *p : s.pool) dev_free(p);
+  s.pool.clear();
+  for (int b = 0; b < 6; ++b)
+    for (int k = 0; k < 2; ++k)
+      for (int sl = 0; sl < 2; ++sl) dev_free(s.bc_store[b][k][sl]), s.bc_store[b][k][sl] = nullptr;
+  s.comm.reset();
+  s.ex.destroy();
+}
+
+// ------------------------------------------------------------------ dispatch helpers
+#define DIM_DISPATCH(s, CALL2, CALL3) \
+  do { \
+    if ((s).dim == 2) { CALL2; } else { CALL3; } \
+  } while (0)
+
+static Box cell_box(const Solver &s)
+{
+  Box b = {s.gh.g.nx, s.gh.g.ny, s.gh.g.nzl};
+  return b;
+}
+
+// f(i, j, kl) over the cells adjacent to boundary b held by this rank
+template <class F>
+struct BoundaryAdapter {
+  F   f;
+  int d, fixed;
+  FL_HD void operator()(int a, int b, int c) const
+  {
+    if (d == 0) f(fixed, b, c);
+    else if (d == 1) f(a, fixed, c);
+    else f(a, b, fixed);
+  }
+};
+
+template <class F>
+static void for_boundary(Solver &s, int b, F f)
+{
+  const Geom &g = s.gh.g;
+  const int   d = b / 2, side = b % 2;
+  const Tab  &T = g.t[d];
+  if (T.per) return;
+  if (d == 2 && !(side ? T.wall_hi : T.wall_lo)) return;
+  const int          ext[3] = {g.nx, g.ny, g.nzl};
+  Box                box    = {d == 0 ? 1 : g.nx, d == 1 ? 1 : g.ny, d == 2 ? 1 : g.nzl};
+  BoundaryAdapter<F> ad     = {f, d, side ? ext[d] - 1 : 0};
+  for_box(s.ex, box, ad);
+}
+
+// ------------------------------------------------------------------ right-hand side (NSFormFunction)
+template <int DIM>
+static void build_rhs(Solver &s)
+{
+  const Geom      &g  = s.gh.g;
+  const bool       first = (s.step_index == 0);
+  double          *q  = first ? s.p : s.phalf; // cnlinearcart3d.c:2972-2982
+  halo_cells(s, s.v0);
+  halo_faces(s, s.U0);
+  halo_scalar(s, q);
+  MomentumRhs<DIM> mr;
+  mr.g = g, mr.sp = s.sp, mr.bc = s.bc, mr.v0 = CV3(s.v0), mr.q = q, mr.r = s.rm;
+  for_box(s.ex, cell_box(s), mr);
+
+  // r_int = bcT(t+dt) + (-T) dt/rho (bcG(tq) - bcG(th)) + dt/rho (bcGst(tq) - bcGst(th)),  :2998-3033
+  for (int d = 0; d < DIM; ++d) dev_zero(s.ex, s.ri.c[d], sizeof(double) * (size_t)g.nalloc);
+  dev_zero(s.ex, s.rc, sizeof(double) * (size_t)g.nalloc); // :3035
+  for (int b = 0; b < 2 * DIM; ++b) {
+    const int  d = b / 2, side = b % 2;
+    const Tab &T  = g.t[d];
+    const int  ty = side ? T.bc_hi : T.bc_lo;
+    double    *rid = s.ri.c[d];
+    const BcDev bc = s.bc;
+    const Geom  gg = g;
+    if (ty == BC_VELOCITY) {
+      for_boundary(s, b, FL_LAMBDA(int i, int j, int kl) {
+        Nbr<DIM> nb;
+        nbr<DIM>(gg, i, j, kl, nb);
+        const long pt = bc_pt(gg, b, i, j, kl);
+        const long f  = side ? nb.fu[d] : nb.c;
+        rid[f]        = bc.vel[b][1][d * bc.npts[b] + pt];
+      });
+    } else if (ty == BC_PRESSURE_OUTLET) {
+      const double dtrho = s.sp.dtrho;
+      for_boundary(s, b, FL_LAMBDA(int i, int j, int kl) {
+        Nbr<DIM> nb;
+        nbr<DIM>(gg, i, j, kl, nb);
+        const Tab   &TT = gg.t[d];
+        const long   pt = bc_pt(gg, b, i, j, kl);
+        const double dl = bc.prs[b][0][pt] - bc.prs[b][1][pt]; // p_b(t_q) - p_b(t+dt/2)
+        const int    n  = TT.n;
+        if (!side) {
+          const double g0 = dtrho * TT.gr_bc_lo * dl; // the only non-zero entry of dt/rho (bcG_q - bcG_h), at cell 0
+          rid[nb.c] += -TT.it_lo[1][0] * g0 + dtrho * TT.gst_bc_lo * dl;
+          rid[nb.p[d]] += -TT.itw[2 * 1 + 0] * g0; // face 1 interpolates cells (0, 1)
+        } else {
+          const double g0 = dtrho * TT.gr_bc_hi * dl;
+          rid[nb.fu[d]] += -TT.it_hi[1][1] * g0 + dtrho * TT.gst_bc_hi * dl;
+          rid[nb.c] += -TT.itw[2 * (n - 1) + 1] * g0; // face n-1 interpolates cells (n-2, n-1)
+        }
+      });
+    }
+  }
+}
+
+void prepare_step(Solver &s, double t, int step_index)
+{
+  s.t = t, s.step_index = step_index;
+  // sol0 = sol (nsbasic.c:281-282): the roles of the two buffers are swapped instead of copying
+  V3 tv = s.v0, tU = s.U0;
+  s.v0 = s.v, s.U0 = s.U;
+  s.v = tv, s.U = tU;
+  DIM_DISPATCH(s, build_rhs<2>(s), build_rhs<3>(s));
+  s.prepared = true;
+}
+
+// ------------------------------------------------------------------ operators
+template <int DIM>
+struct AApplyPlain {
+  Geom       g;
+  StepParams sp;
+  BcDev      bc;
+  CV3        x, v0, U0;
+  V3         y;
+  FL_HD void operator()(int i, int j, int kl) const
+  {
+    double r[DIM];
+    a_apply_cell<DIM>(g, sp, bc, x, v0, U0, i, j, kl, r);
+    const long c = g.idx(i, j, kl);
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) y.c[q][c] = r[q];
+  }
+};
+
+void a_apply(Solver &s, const V3 &x, const V3 &y)
+{
+  halo_cells(s, x);
+  if (s.dim == 2) {
+    AApplyPlain<2> f;
+    f.g = s.gh.g, f.sp = s.sp, f.bc = s.bc, f.x = CV3(x), f.v0 = CV3(s.v0), f.U0 = CV3(s.U0), f.y = y;
+    for_box(s.ex, cell_box(s), f);
+  } else {
+    AApplyPlain<3> f;
+    f.g = s.gh.g, f.sp = s.sp, f.bc = s.bc, f.x = CV3(x), f.v0 = CV3(s.v0), f.U0 = CV3(s.U0), f.y = y;
+    for_box(s.ex, cell_box(s), f);
+  }
+}
+
+static long global_cells(const Solver &s)
+{
+  const Geom &g = s.gh.g;
+  return (long)g.nx * g.ny * g.nzg;
+}
+
+static void remove_mean(Solver &s, double *f)
+{
+  const long off = interior_off(s), len = interior_len(s);
+  double    *a   = f + off;
+  for_range_reduce<1>(s.ex, len, FL_LAMBDA(long i, double acc[1]) { acc[0] += a[i]; });
+  double sum;
+  reduce_finish(s, 1, &sum);
+  // padding entries must stay zero: subtract on valid cells only
+  const double mean = sum / (double)global_cells(s);
+  const Geom   g    = s.gh.g;
+  for_box(s.ex, cell_box(s), FL_LAMBDA(int i, int j, int kl) { f[g.idx(i, j, kl)] -= mean; });
+}
+
+template <int DIM>
+static void abf_apply_t(Solver &s, const V3 &bm, const V3 &bi, const double *bcn, const V3 &ov, const V3 &oU, double *op)
+{
+  const Geom &g = s.gh.g;
+  // stage 1 (abfpc.c:72-77)
+  momentum_solve(s, bm, s.vstar);
+  halo_cells(s, s.vstar);
+  FaceCombine<DIM> fc;
+  fc.g = g, fc.a = 1., fc.b = 1., fc.c = 0., fc.in = CV3(bi), fc.w = CV3(s.vstar), fc.p = nullptr, fc.out = s.Ustar;
+  for_box(s.ex, cell_box(s), fc);
+  halo_faces(s, s.Ustar);
+  PoissonRhs<DIM> pr;
+  pr.g = g, pr.scale = s.sp.rho / s.sp.dt, pr.U = CV3(s.Ustar), pr.rc = bcn, pr.out = s.srhs;
+  for_box_reduce<1>(s.ex, cell_box(s), pr);
+  if (!s.has_outlet) {
+    // constant null space (abfpc.c:173-177): make the right-hand side compatible
+    double sum;
+    reduce_finish(s, 1, &sum);
+    const double mean = sum / (double)global_cells(s);
+    double      *sr   = s.srhs;
+    const Geom   gg   = g;
+    for_box(s.ex, cell_box(s), FL_LAMBDA(int i, int j, int kl) { sr[gg.idx(i, j, kl)] -= mean; });
+  }
+  poisson_solve(s, s.srhs, op);
+  if (!s.has_outlet) remove_mean(s, op);
+  // stage 2 (abfpc.c:80-101); the T*G~p terms of V cancel: V = V* - G~st p
+  halo_scalar(s, op);
+  ProjectCells<DIM> pc;
+  pc.g = g, pc.dtrho = s.sp.dtrho, pc.vs = CV3(s.vstar), pc.p = op, pc.v = ov;
+  for_box(s.ex, cell_box(s), pc);
+  fc.a = 1., fc.b = 0., fc.c = -s.sp.dtrho, fc.in = CV3(s.Ustar), fc.w = CV3(), fc.p = op, fc.out = oU;
+  for_box(s.ex, cell_box(s), fc);
+  s.stats.abf_applies++;
+}
+
+void abf_apply(Solver &s, const V3 &bm, const V3 &bi, const double *bcn, const V3 &ov, const V3 &oU, double *op)
+{
+  DIM_DISPATCH(s, abf_apply_t<2>(s, bm, bi, bcn, ov, oU, op), abf_apply_t<3>(s, bm, bi, bcn, ov, oU, op));
+}
+
+template <int DIM>
+static void coupled_apply_t(Solver &s, const V3 &xv, const V3 &xU, double *xp, const V3 &yv, const V3 &yU, double *yp)
+{
+  const Geom &g = s.gh.g;
+  halo_cells(s, xv);
+  halo_scalar(s, xp);
+  CoupledCells<DIM> cc;
+  cc.g = g, cc.sp = s.sp, cc.bc = s.bc, cc.x = CV3(xv), cc.v0 = CV3(s.v0), cc.U0 = CV3(s.U0), cc.p = xp, cc.y = yv, cc.w = s.tw;
+  for_box(s.ex, cell_box(s), cc);
+  halo_cells(s, s.tw);
+  FaceCombine<DIM> fc;
+  fc.g = g, fc.a = 1., fc.b = -1., fc.c = s.sp.dtrho, fc.in = CV3(xU), fc.w = CV3(s.tw), fc.p = xp, fc.out = yU;
+  for_box(s.ex, cell_box(s), fc);
+  halo_faces(s, xU);
+  DivCell<DIM> dc;
+  dc.g = g, dc.U = CV3(xU), dc.out = yp;
+  for_box(s.ex, cell_box(s), dc);
+}
+
+void coupled_apply(Solver &s, const V3 &xv, const V3 &xU, double *xp, const V3 &yv, const V3 &yU, double *yp)
+{
+  DIM_DISPATCH(s, coupled_apply_t<2>(s, xv, xU, xp, yv, yU, yp), coupled_apply_t<3>(s, xv, xU, xp, yv, yU, yp));
+}
+
+// S p in the reference's scaling: S = -(dt/rho) D Gst0  (abfpc.c:151-170)
+void schur_apply_reference_scaling(Solver &s, double *pin, double *out)
+{
+  poisson_apply(s, pin, out);
+  const Geom   g     = s.gh.g;
+  const double dtrho = s.sp.dtrho;
+  const int    dim   = s.dim;
+  for_box(s.ex, cell_box(s), FL_LAMBDA(int i, int j, int kl) {
+    double vol = g.t[0].h[i] * g.t[1].h[j];
+    if (dim == 3) vol *= g.t[2].h[g.k0 + kl];
+    out[g.idx(i, j, kl)] *= dtrho / vol;
+  });
+}
+
+// ------------------------------------------------------------------ 7-field vectors of the outer solve
+struct MV {
+  double *f[7];
+  long    len[7];
+  long    n; // max len
+};
+
+static MV make_mv(const Solver &s, const V3 &v, const V3 &U, double *p)
+{
+  MV         m;
+  const long off = interior_off(s), len = interior_len(s);
+  for (int c = 0; c < 3; ++c) {
+    m.f[c]       = v.c[c] ? v.c[c] + off : nullptr;
+    m.len[c]     = v.c[c] ? len : 0;
+    m.f[3 + c]   = U.c[c] ? U.c[c] + off : nullptr;
+    m.len[3 + c] = U.c[c] ? face_len(s, c) : 0;
+  }
+  m.f[6]   = p + off;
+  m.len[6] = len;
+  m.n      = 0;
+  for (int f = 0; f < 7; ++f)
+    if (m.len[f] > m.n) m.n = m.len[f];
+  return m;
+}
+static MV make_mv(const Solver &s, const std::vector<double *> &b)
+{
+  V3 v, U;
+  for (int c = 0; c < 3; ++c) v.c[c] = b[c], U.c[c] = b[3 + c];
+  return make_mv(s, v, U, b[6]);
+}
+
+static double mv_dot(Solver &s, const MV &a, const MV &b)
+{
+  for_range_reduce<1>(s.ex, a.n, FL_LAMBDA(long i, double acc[1]) {
+    double t = 0.;
+#pragma unroll
+    for (int f = 0; f < 7; ++f)
+      if (i < a.len[f]) t += a.f[f][i] * b.f[f][i];
+    acc[0] += t;
+  });
+  double r;
+  reduce_finish(s, 1, &r);
+  return r;
+}
+// y = alpha * x + beta * y   (beta == 0 overwrites)
+static void mv_axpby(Solver &s, double alpha, const MV &x, double beta, const MV &y)
+{
+  for_range(s.ex, x.n, FL_LAMBDA(long i) {
+#pragma unroll
+    for (int f = 0; f < 7; ++f)
+      if (i < x.len[f]) y.f[f][i] = alpha * x.f[f][i] + (beta == 0. ? 0. : beta * y.f[f][i]);
+  });
+}
+static void mv_zero(Solver &s, const MV &y)
+{
+  for_range(s.ex, y.n, FL_LAMBDA(long i) {
+#pragma unroll
+    for (int f = 0; f < 7; ++f)
+      if (i < y.len[f]) y.f[f][i] = 0.;
+  });
+}
+
+// right-preconditioned restarted GMRES on M x = b, PC = ABF, zero initial guess, true-residual
+// norm; x is built in (s.xv, s.xU, s.xp)
+static int outer_gmres(Solver &s)
+{
+  const int m = s.opt.outer_restart;
+  MV        X = make_mv(s, s.xv, s.xU, s.xp), Bv = make_mv(s, s.rm, s.ri, s.rc), W = make_mv(s, s.wv, s.wU, s.wp), Z = make_mv(s, s.zv, s.zU, s.zp);
+  std::vector<MV> V;
+  for (auto &b : s.basis) V.push_back(make_mv(s, b));
+  std::vector<double> H((size_t)(m + 1) * m, 0.), cs(m), sn(m), gvec(m + 1), y(m);
+  mv_zero(s, X);
+  int    its = 0;
+  double rnorm0 = -1., rnorm = 0.;
+  bool   done = false, first_cycle = true;
+  s.stats.nhist = 0;
+  while (!done) {
+    // r = b - M x
+    if (first_cycle) mv_axpby(s, 1., Bv, 0., V[0]);
+    else {
+      coupled_apply(s, s.xv, s.xU, s.xp, s.wv, s.wU, s.wp);
+      mv_axpby(s, 1., Bv, 0., V[0]);
+      mv_axpby(s, -1., W, 1., V[0]);
+    }
+    first_cycle = false;
+    rnorm = std::sqrt(mv_dot(s, V[0], V[0]));
+    if (rnorm0 < 0.) {
+      rnorm0 = rnorm;
+      if (s.stats.nhist < 128) s.stats.hist[s.stats.nhist++] = rnorm;
+    }
+    if (!(rnorm == rnorm)) throw Error(FL_ERR_DIVERGED, "outer residual is NaN");
+    if (rnorm <= s.opt.outer_rtol * rnorm0 || rnorm == 0.) {
+      s.stats.converged = 1;
+      break;
+    }
+    if (its >= s.opt.outer_maxit) break;
+    mv_axpby(s, 1. / rnorm, V[0], 0., V[0]);
+    std::fill(gvec.begin(), gvec.end(), 0.);
+    gvec[0] = rnorm;
+    int k = 0;
+    for (; k < m && its < s.opt.outer_maxit; ++k) {
+      // z = ABF(v_k); w = M z
+      V3 kv, kU;
+      for (int c = 0; c < 3; ++c) kv.c[c] = s.basis[k][c], kU.c[c] = s.basis[k][3 + c];
+      abf_apply(s, kv, kU, s.basis[k][6], s.zv, s.zU, s.zp);
+      V3 nv, nU;
+      for (int c = 0; c < 3; ++c) nv.c[c] = s.basis[k + 1][c], nU.c[c] = s.basis[k + 1][3 + c];
+      coupled_apply(s, s.zv, s.zU, s.zp, nv, nU, s.basis[k + 1][6]);
+      if (!s.has_outlet) remove_mean(s, s.basis[k + 1][6]); // null space of J (nsbasic.c:229-243)
+      for (int pass = 0; pass < 2; ++pass) // Gram-Schmidt with one refinement pass
+        for (int jx = 0; jx <= k; ++jx) {
+          double hj = mv_dot(s, V[jx], V[k + 1]);
+          mv_axpby(s, -hj, V[jx], 1., V[k + 1]);
+          if (pass == 0) H[(size_t)jx * m + k] = hj;
+          else H[(size_t)jx * m + k] += hj;
+        }
+      double hn = std::sqrt(mv_dot(s, V[k + 1], V[k + 1]));
+      H[(size_t)(k + 1) * m + k] = hn;
+      if (hn > 0.) mv_axpby(s, 1. / hn, V[k + 1], 0., V[k + 1]);
+      for (int jx = 0; jx < k; ++jx) {
+        double a = H[(size_t)jx * m + k], b = H[(size_t)(jx + 1) * m + k];
+        H[(size_t)jx * m + k]       = cs[jx] * a + sn[jx] * b;
+        H[(size_t)(jx + 1) * m + k] = -sn[jx] * a + cs[jx] * b;
+      }
+      {
+        double a = H[(size_t)k * m + k], b = H[(size_t)(k + 1) * m + k], r = std::hypot(a, b);
+        cs[k] = r > 0. ? a / r : 1.;
+        sn[k] = r > 0. ? b / r : 0.;
+        H[(size_t)k * m + k]       = r;
+        H[(size_t)(k + 1) * m + k] = 0.;
+        gvec[k + 1]                = -sn[k] * gvec[k];
+        gvec[k]                    = cs[k] * gvec[k];
+      }
+      its++;
+      rnorm = std::fabs(gvec[k + 1]);
+      if (s.stats.nhist < 128) s.stats.hist[s.stats.nhist++] = rnorm;
+      if (rnorm <= s.opt.outer_rtol * rnorm0 || hn == 0.) {
+        ++k;
+        done              = true;
+        s.stats.converged = 1;
+        break;
+      }
+    }
+    // x += ABF(V y)
+    for (int jx = k - 1; jx >= 0; --jx) {
+      double sum = gvec[jx];
+      for (int l = jx + 1; l < k; ++l) sum -= H[(size_t)jx * m + l] * y[l];
+      y[jx] = sum / H[(size_t)jx * m + jx];
+    }
+    mv_zero(s, W);
+    for (int jx = 0; jx < k; ++jx) mv_axpby(s, y[jx], V[jx], 1., W);
+    abf_apply(s, s.wv, s.wU, s.wp, s.zv, s.zU, s.zp);
+    mv_axpby(s, 1., Z, 1., X);
+    if (its >= s.opt.outer_maxit) done = true;
+  }
+  s.stats.outer_its    = its;
+  s.stats.outer_rnorm0 = rnorm0;
+  s.stats.outer_rnorm  = rnorm;
+  return s.stats.converged ? 0 : 1;
+}
+
+// ------------------------------------------------------------------ the step
+int do_step(Solver &s, double t, int step_index)
+{
+  const long l0 = s.ex.stats.launches;
+  s.stats       = Stats();
+  prepare_step(s, t, step_index);
+  if (!s.has_outlet) remove_mean(s, s.rc); // F(0) = -b with the null space removed (nsbasic.c:133-144)
+  int rc = 0;
+  if (s.opt.mode == 1) {
+    abf_apply(s, s.rm, s.ri, s.rc, s.xv, s.xU, s.xp);
+    s.stats.converged = 1;
+  } else {
+    rc = outer_gmres(s);
+  }
+  // sol <- x ; pressure extrapolation (cnlinearcart3d.c:2843-2854)
+  {
+    V3 tv = s.v, tU = s.U;
+    s.v = s.xv, s.U = s.xU;
+    s.xv = tv, s.xU = tU;
+    const long   off = interior_off(s), len = interior_len(s);
+    double      *p = s.p + off, *ph = s.phalf + off;
+    const double *dp = s.xp + off;
+    if (step_index == 0) {
+      for_range(s.ex, len, FL_LAMBDA(long i) {
+        const double p0 = p[i], d = dp[i];
+        p[i]  = p0 + 2. * d;
+        ph[i] = p0 + d;
+      });
+    } else {
+      for_range(s.ex, len, FL_LAMBDA(long i) {
+        const double h = ph[i], d = dp[i];
+        p[i]  = h + 1.5 * d;
+        ph[i] = h + d;
+      });
+    }
+  }
+  s.ex.sync();
+  s.stats.launches = s.ex.stats.launches - l0;
+  s.prepared       = false;
+  return rc;
+}
+
+} // namespace fluca

@@ -1,0 +1,170 @@
+/*
+ * fluca_b200.h -- C ABI of the B200-native Navier-Stokes time-step solver.
+ *
+ * This is the drop-in boundary for the hot path of thecasterian/fluca: a
+ * new NS type (registered with NSRegister, fluca/include/flucans.h:92, selected with
+ * -ns_type b200) calls these entry points from its NSOps (fluca/include/fluca/private/nsimpl.h:21-31).
+ * Plain C types only; every function returns 0 on success or a FLUCA_B200_ERR_* code, and
+ * fluca_b200_last_error() returns the message (the glue maps it to PETSC_ERR_LIB / ns->reason,
+ * nsbasic.c:293-297, :425-436).  INTEGRATION.md shows the reference-side binding.
+ *
+ * There is NO CPU fallback: creating a solver without a CUDA device fails with
+ * FLUCA_B200_ERR_NODEVICE.
+ *
+ * Field layout at this boundary (host or device memory, compact, no padding; one rank's z-slab):
+ *   cell fields     [nzl][ny][nx]             velocity: dim consecutive component blocks (SoA)
+ *   x-face field    [nzl][ny][nx + ex]        ex = 0 if x periodic else 1 (the extra RIGHT face)
+ *   y-face field    [nzl][ny + ey][nx]
+ *   z-face field    [nzl + ez][ny][nx]        ez = 1 only on the rank that holds the FRONT wall
+ * i.e. every cell owns its LEFT/DOWN/BACK face, the last rank the extra faces, as DMStag does
+ * (fluca/src/mesh/impl/cart/cart.c:85-120); the PETSc glue converts with DMStagVecGetArray +
+ * DMStagGetLocationSlot.
+ */
+#ifndef FLUCA_B200_H
+#define FLUCA_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLUCA_B200_OK 0
+#define FLUCA_B200_ERR_ARG 1
+#define FLUCA_B200_ERR_CUDA 2
+#define FLUCA_B200_ERR_NCCL 3
+#define FLUCA_B200_ERR_DIVERGED 4 /* -> ns->reason = NS_DIVERGED_NONLINEAR_SOLVE (flucans.h:18) */
+#define FLUCA_B200_ERR_NODEVICE 5
+#define FLUCA_B200_ERR_INTERNAL 6
+
+/* boundary condition types: numeric values of NSBoundaryConditionType (flucansbc.h:5-11) */
+#define FLUCA_B200_BC_NONE 0
+#define FLUCA_B200_BC_VELOCITY 1
+#define FLUCA_B200_BC_PRESSURE_OUTLET 2
+#define FLUCA_B200_BC_PERIODIC 3
+#define FLUCA_B200_BC_SYMMETRY 4
+
+/* solve modes (SURVEY.md section 7 "parity definition") */
+#define FLUCA_B200_MODE_COUPLED 0    /* reference default: outer GMRES on the coupled system, PC = ABF (nssol.c:21-29) */
+#define FLUCA_B200_MODE_FRACTIONAL 1 /* one ABF application = classical fractional step (abfpc.c:48-111) */
+
+typedef struct fluca_b200_solver fluca_b200_solver;
+typedef struct fluca_b200_comm   fluca_b200_comm;
+
+typedef struct {
+  int           dim;        /* 2 or 3 (MeshGetDimension) */
+  int           n[3];       /* global cells (MeshCartGetGlobalSizes) */
+  const double *xf[3];      /* n[d]+1 face coordinates per direction (MeshCartGetCoordinateArraysRead, slot PREV) */
+  int           bc_type[6]; /* LEFT, RIGHT, DOWN, UP, BACK, FRONT (cart.c:564-591; ns->bcs[b].type) */
+  double        rho, mu, dt; /* ns->rho, ns->mu, ns->dt (nsimpl.h:45-47) */
+  int           k0, nzl;    /* z-slab [k0, k0+nzl) of this rank (MeshCartGetCorners with -cart_ranks_z P); 2-D: 0, 1 */
+  /* solver options; 0 / 0.0 selects the default in brackets */
+  int    mode;            /* FLUCA_B200_MODE_* [COUPLED] */
+  double outer_rtol;      /* [1e-5]  -ns_ksp_rtol, nssol.c:24 */
+  int    outer_maxit;     /* [100] */
+  int    outer_restart;   /* [30]    GMRES restart (PETSc default) */
+  double mom_rtol;        /* [1e-5]  -ns_abf_momentum_ksp_rtol */
+  double schur_rtol;      /* [1e-5]  -ns_abf_schur_ksp_rtol */
+  int    inner_maxit;     /* [500] */
+  int    mg_nu1, mg_nu2;  /* [2, 2]  Jacobi pre / post sweeps of the pressure V-cycle */
+  int    mg_coarse_sweeps; /* [40] */
+  int    no_bcg_quirk;    /* 0: 3-D scales the outlet-gradient BC vector by 1 as cnlinearcart3d.c:2977 does; 1: by dt/rho */
+} fluca_b200_desc;
+
+typedef struct {
+  int    outer_its;    /* outer KSP iterations (-ns_ksp_monitor count) */
+  int    mom_its;      /* total momentum BiCGStab iterations */
+  int    schur_its;    /* total pressure Krylov iterations */
+  int    abf_applies;  /* PCApply_ABF count */
+  int    converged;
+  double outer_rnorm0, outer_rnorm;
+  int    nhist;
+  double hist[128];    /* outer true-residual history, the analogue of -ns_ksp_monitor */
+  long   launches;     /* kernels + device copies launched by this step */
+  double mom_last_rel, schur_last_rel;
+} fluca_b200_stats;
+
+const char *fluca_b200_last_error(void);
+/* 1 if the library was built as the CPU-only host-emulation test double (never the product build) */
+int fluca_b200_is_host_emulation(void);
+
+/* ---- communicator over the GPUs of one box (one process per GPU) ---- */
+/* rank 0 calls unique_id and ships the bytes to the others (MPI_Bcast in the glue, torch.distributed in bench.py) */
+int fluca_b200_comm_unique_id(void *out, int capacity, int *bytes);
+int fluca_b200_comm_create_nccl(const void *unique_id, int bytes, int rank, int nranks, fluca_b200_comm **out);
+/* host-callback flavour (MPI host without NCCL bootstrap; gloo in the CPU tests) */
+typedef int (*fluca_b200_halo_fn)(void *ctx, const double *send_down, double *recv_down, const double *send_up, double *recv_up, long count, int periodic);
+typedef int (*fluca_b200_allsum_fn)(void *ctx, double *vals, int n);
+typedef int (*fluca_b200_allgather_fn)(void *ctx, const double *send, double *recv, long count);
+int fluca_b200_comm_create_callbacks(int rank, int nranks, fluca_b200_halo_fn, fluca_b200_allsum_fn, fluca_b200_allgather_fn, void *ctx, fluca_b200_comm **out);
+/* a communicator handed to fluca_b200_create is owned (and destroyed) by the solver */
+
+/* ---- solver life cycle: NSCreate_<type> / ops->setup / ops->destroy ---- */
+int fluca_b200_create(const fluca_b200_desc *desc, fluca_b200_comm *comm /* NULL = single GPU */, fluca_b200_solver **out);
+int fluca_b200_destroy(fluca_b200_solver *s);
+
+/* ---- state: ns->sol sub-vectors Velocity / FaceNormalVelocity / Pressure + "PressureHalfStep" (cnlinear.c:54) ---- */
+/* host pointers; any argument may be NULL to skip that field */
+int fluca_b200_set_state(fluca_b200_solver *s, const double *v, const double *const U[3], const double *p, const double *phalf);
+int fluca_b200_get_state(fluca_b200_solver *s, double *v, double *const U[3], double *p, double *phalf);
+
+/* ---- boundary data: values of ns->bcs[b].velocity / .pressure (flucansbc.h:14) evaluated by the host at the
+ * boundary-face centres of this rank's slab: x boundaries [nzl][ny], y boundaries [nzl][nx], z boundaries [ny][nx];
+ * velocity: dim consecutive component blocks.
+ * velocity slots: 0 = t^n, 1 = t^n + dt.   pressure slots: 0 = t_q (t^n at step 0, else t^n - dt/2), 1 = t^n + dt/2 */
+int fluca_b200_set_boundary_velocity(fluca_b200_solver *s, int boundary, int slot, const double *values);
+int fluca_b200_set_boundary_pressure(fluca_b200_solver *s, int boundary, int slot, const double *values);
+
+/* ---- ops->step: one NSStep_CNLinear_Cart{2,3}d_Internal (cnlinearcart3d.c:2807-2863) ---- */
+int fluca_b200_step(fluca_b200_solver *s, double t, int step_index, fluca_b200_stats *stats);
+
+/* ---- operator-level entry points (parity tests; ops->formfunction / ops->formjacobian analogues) ---- */
+/* sol0 <- sol, builds b = (r_mom, r_int, r_con) of NSFormFunction (cnlinearcart3d.c:2945-3043) */
+int fluca_b200_prepare_step(fluca_b200_solver *s, double t, int step_index);
+int fluca_b200_get_rhs(fluca_b200_solver *s, double *rmom, double *const rint[3], double *rcon);
+/* y = A x, A = I + dt C - (nu dt/2) L of NSFormJacobian(UPDATE) (cnlinearcart3d.c:2930-2941); needs prepare_step */
+int fluca_b200_apply_momentum(fluca_b200_solver *s, const double *x, double *y);
+/* y = S p, S = -(dt/rho) D Gst (abfpc.c:151-170) */
+int fluca_b200_apply_schur(fluca_b200_solver *s, const double *p, double *y);
+/* y = M x of the coupled 3x3 block system (MatNest J, nsbasic.c:203-207) */
+int fluca_b200_apply_coupled(fluca_b200_solver *s, const double *xv, const double *const xU[3], const double *xp, double *yv, double *const yU[3], double *yp);
+/* x = PCApply_ABF(b) (abfpc.c:48-111) */
+int fluca_b200_apply_abf(fluca_b200_solver *s, const double *bv, const double *const bU[3], const double *bp, double *xv, double *const xU[3], double *xp, fluca_b200_stats *stats);
+
+/* ---- device-resident access (HBM-resident benchmarking, GPU-side consumers) ---- */
+/* copies the current state into / from a second device snapshot without touching the host */
+int fluca_b200_snapshot_save(fluca_b200_solver *s);
+int fluca_b200_snapshot_restore(fluca_b200_solver *s);
+/* padded device layout of every field: index(i,j,kl) = i + px*(j + py*(kl+1)) */
+int fluca_b200_device_layout(fluca_b200_solver *s, int *px, int *py, long *plane, long *nalloc);
+/* names: "v0".."v2", "U0".."U2", "p", "phalf" -> device pointer (double*) of the live state */
+int fluca_b200_device_field(fluca_b200_solver *s, const char *name, void **ptr);
+/* CUDA stream the solver launches on (cudaStream_t), for event timing */
+int fluca_b200_stream(fluca_b200_solver *s, void **stream);
+/* total kernel / device-copy launches since creation */
+long fluca_b200_launch_count(fluca_b200_solver *s);
+/* algorithmic bytes of one step with the given iteration counts (SURVEY.md 8d model, actual padded sizes) */
+double fluca_b200_step_model_bytes(fluca_b200_solver *s, const fluca_b200_stats *stats);
+
+/* ---- live per-class kernel timing (CUDA event pairs on the solver stream around each launch) ---- */
+#define FLUCA_B200_KT_MOMENTUM_APPLY 0 /* y = A x fused with two dot products */
+#define FLUCA_B200_KT_MOMENTUM_VEC 1
+#define FLUCA_B200_KT_POISSON_APPLY 2  /* q = P p fused with <p, q> */
+#define FLUCA_B200_KT_POISSON_VEC 3
+#define FLUCA_B200_KT_MG_SMOOTH 4      /* damped-Jacobi sweep, all levels */
+#define FLUCA_B200_KT_MG_TRANSFER 5    /* residual+restriction, prolongation+correction */
+#define FLUCA_B200_KT_RHS_PROJECT 6
+#define FLUCA_B200_KT_OUTER 7
+#define FLUCA_B200_KT_HALO 8
+#define FLUCA_B200_KT_NCLASS 9
+int fluca_b200_kernel_timing(fluca_b200_solver *s, int enable);
+/* accumulated milliseconds and launch counts per class since the last reset */
+int fluca_b200_kernel_times(fluca_b200_solver *s, double ms[FLUCA_B200_KT_NCLASS], long counts[FLUCA_B200_KT_NCLASS], int reset);
+
+/* ---- kernel-level timing hooks for bench.py's roofline (times with CUDA events on the solver stream) ---- */
+/* runs `reps` launches of the named kernel on scratch fields and returns the mean duration in ms and the
+ * algorithmic bytes of one launch.  names: "momentum_apply", "poisson_apply", "mg_smooth", "vector_update" */
+int fluca_b200_time_kernel(fluca_b200_solver *s, const char *name, int reps, double *ms, double *algorithmic_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

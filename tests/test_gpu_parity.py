@@ -1,0 +1,115 @@
+"""GPU parity tests proper: the CUDA product library (through the C ABI and the reference-style NS API)
+against the CPU oracle on the same seeded inputs.  fp64 tolerance: 1e-10 relative L2 on velocity and
+face velocity, 1e-9 on pressure, after K steps with both sides at tight solver tolerances
+(BASELINE.json north_star: "within 1e-10 relative L2 (fp64) after a fixed number of steps")."""
+import numpy as np
+import pytest
+
+import fluca_b200 as fb
+from oracle import oracle as O
+from tests import cases, parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    L = fb._lib.load()  # the CUDA library; raises if it is missing (no fallback)
+    assert L.fluca_b200_is_host_emulation() == 0
+    return L
+
+
+def _st(c):
+    c.stretch = 0.6
+    return c
+
+
+CASES = [
+    ("cavity2d_32", lambda: cases.cavity2d(n=32), None, 3),
+    ("cavity2d_nonuniform", lambda: _st(cases.cavity2d(n=24)), 3, 2),
+    ("cavity3d_sym_reference_geometry", lambda: cases.cavity3d(n=(16, 16, 8)), 5, 2),
+    ("cavity3d_full", lambda: cases.cavity3d_full(n=(16, 16, 16)), 9, 2),
+    ("tgv_dirichlet", lambda: cases.tgv(n=16, dt=0.05), None, 2),
+    ("tgv_periodic", lambda: cases.tgv(n=16, periodic=True, dt=0.05), None, 2),
+    ("channel2d_outlet_timedep", lambda: cases.channel2d(n=(32, 16), pout=0.3, time_dependent=True), 7, 2),
+    ("channel3d_outlet", lambda: cases.channel3d(n=(16, 12, 12), pout=0.2, dt=0.05), 11, 2),
+    ("channel3d_periodic_z", lambda: cases.channel3d(n=(16, 12, 12), periodic_z=True, dt=0.05), 13, 2),
+    ("ragged_sizes", lambda: cases.cavity3d_full(n=(13, 9, 7)), 17, 2),
+]
+
+
+@pytest.mark.parametrize("mode", ["fractional", "coupled"])
+@pytest.mark.parametrize("name,mk,seed,nsteps", CASES, ids=[c[0] for c in CASES])
+def test_step_matches_oracle(lib, name, mk, seed, nsteps, mode):
+    out = parity.compare_steps(mk(), lib, mode=mode, nsteps=nsteps, seed=seed, tol=1e-10)
+    if mode == "coupled":
+        for o in out:  # KSP residual histories track the oracle's (exact inner solves)
+            assert abs(o["outer"][0] - o["outer"][1]) <= 1
+            n = min(len(o["hist_gpu"]), len(o["hist_orc"]), 6)
+            for a, b in zip(o["hist_gpu"][:n], o["hist_orc"][:n]):
+                assert a == pytest.approx(b, rel=1e-6, abs=1e-12 * o["hist_orc"][0])
+
+
+def test_operator_level_parity(lib):
+    case = cases.channel3d(n=(16, 12, 12), pout=0.2, dt=0.05)
+    orc = cases.make_oracle(case)
+    state = case.initial_state(seed=21)
+    orc.set_state(*state)
+    ns = parity.make_ns(case, lib, "coupled", **parity.TIGHT)
+    parity.set_initial(ns, state)
+    rhs = orc.prepare_step()
+    rm, ri, rc = ns.ops["formfunction"](ns)
+    ov, oU, _ = orc.split(rhs)
+    assert parity.rel(rm, ov) < 1e-13 and parity.relU(ri, oU) < 1e-13 and np.abs(rc).max() == 0.0
+    s = fb.NSB200GetSolver(ns)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(orc.nsol)
+    xv, xU, xp = orc.split(x)
+    A, S = orc.matrix("A"), orc.matrix("S")
+    assert parity.rel(s.apply_momentum(xv).ravel(), A @ xv.ravel()) < 1e-13
+    assert parity.rel(s.apply_schur(xp).ravel(), S @ xp.ravel()) < 1e-12
+    G, negT, negR, D = (orc.matrix(k) for k in ("G", "negT", "negR", "D"))
+    xUc = np.concatenate([u.ravel() for u in xU])
+    gv, gU, gp = s.apply_coupled(xv, xU, xp)
+    assert parity.rel(gv.ravel(), A @ xv.ravel() + G @ xp.ravel()) < 1e-13
+    assert parity.rel(np.concatenate([u.ravel() for u in gU]), negT @ xv.ravel() + xUc + negR @ xp.ravel()) < 1e-13
+    assert parity.rel(gp.ravel(), D @ xUc) < 1e-13
+    xo, _ = orc.abf_apply(x, O.default_options(**parity.ORC_TIGHT))
+    av, aU, ap, st = s.apply_abf(xv, xU, xp)
+    o_v, o_U, o_p = orc.split(xo)
+    assert parity.rel(av, o_v) < 1e-10 and parity.relU(aU, o_U) < 1e-10 and parity.rel(ap, o_p) < 1e-9
+
+
+def test_reductions_are_bitwise_reproducible(lib):
+    case = cases.cavity3d_full(n=(24, 20, 12))
+    res = []
+    for _ in range(2):
+        ns = parity.make_ns(case, lib, "coupled")
+        parity.set_initial(ns, case.initial_state(seed=4))
+        for _ in range(2):
+            fb.NSStep(ns)
+        res.append(fb.NSB200GetSolver(ns).get_state()["v"].copy())
+        fb.NSDestroy(ns)
+    assert np.array_equal(res[0], res[1])
+
+
+def test_full_size_properties_256cube_fractional_step(lib):
+    """BASELINE config 3 at full size (256^3): size-independent properties instead of the oracle --
+    discrete continuity D U = 0 after the projection, zero-mean pressure increment, bounded solve counts."""
+    n = 256
+    case = cases.cavity3d_full(n=(n, n, n), Re=400.0)
+    ns = parity.make_ns(case, lib, "fractional", ns_abf_momentum_ksp_rtol=1e-10, ns_abf_schur_ksp_rtol=1e-10)
+    for _ in range(2):
+        fb.NSStep(ns)
+    st = fb.NSB200GetStats(ns)
+    assert st.mom_its <= 12 and st.schur_its <= 14  # mesh-independent multigrid
+    s = fb.NSB200GetSolver(ns).get_state()
+    h = 1.0 / n
+    U = s["U"]
+    div = (U[0][:, :, 1:] - U[0][:, :, :-1] + U[1][:, 1:, :] - U[1][:, :-1, :] + U[2][1:, :, :] - U[2][:-1, :, :]) / h
+    scale = np.abs(U[0]).max() / h
+    assert np.abs(div).max() <= 1e-7 * scale
+    # walls: face-normal velocity equals the boundary data exactly
+    assert np.abs(U[0][:, :, 0]).max() == 0.0 and np.abs(U[1][:, 0, :]).max() == 0.0 and np.abs(U[1][:, -1, :]).max() == 0.0
+    assert np.isfinite(s["p"]).all() and abs(s["p"].mean()) < 1e-8 * max(np.abs(s["p"]).max(), 1e-30)
+    fb.NSDestroy(ns)

@@ -1,0 +1,162 @@
+"""CPU tests of the HOST LOGIC of the solver library: step driver, Krylov / multigrid orchestration,
+boundary-data protocol, reference-style NS API.  They run the library's own sources compiled as the
+host-emulation test double (tests/hostemu/Makefile: every kernel functor in a serial host loop) and
+compare with the oracle.  The CUDA kernels themselves are covered by the -m gpu parity tests, which
+run the same comparisons through the product library."""
+import numpy as np
+import pytest
+
+import fluca_b200 as fb
+from oracle import oracle as O
+from tests import cases, parity
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return parity.hostemu_library()
+
+
+def _st(c):
+    c.stretch = 0.6
+    return c
+
+
+CASES = [
+    ("cavity2d", lambda: cases.cavity2d(n=16), None),
+    ("cavity2d_nonuniform", lambda: _st(cases.cavity2d(n=12)), 3),
+    ("cavity3d_sym", lambda: cases.cavity3d(n=(8, 8, 4)), 5),
+    ("tgv_periodic", lambda: cases.tgv(n=8, periodic=True, dt=0.05), None),
+    ("channel2d_outlet", lambda: cases.channel2d(n=(16, 8), pout=0.3, time_dependent=True), 7),
+    ("channel3d_outlet", lambda: cases.channel3d(n=(8, 6, 6), pout=0.2, dt=0.05), 11),
+    ("channel3d_periodic_z", lambda: cases.channel3d(n=(8, 6, 6), periodic_z=True, dt=0.05), 13),
+]
+
+
+@pytest.mark.parametrize("mode", ["fractional", "coupled"])
+@pytest.mark.parametrize("name,mk,seed", CASES, ids=[c[0] for c in CASES])
+def test_step_matches_oracle(lib, name, mk, seed, mode):
+    out = parity.compare_steps(mk(), lib, mode=mode, nsteps=2, seed=seed, tol=1e-10)
+    if mode == "coupled":
+        # with exact inner solves the outer Krylov history depends only on (M, M~, b): it tracks the oracle's
+        for o in out:
+            assert abs(o["outer"][0] - o["outer"][1]) <= 1
+            n = min(len(o["hist_gpu"]), len(o["hist_orc"]), 6)
+            for a, b in zip(o["hist_gpu"][:n], o["hist_orc"][:n]):
+                assert a == pytest.approx(b, rel=1e-6, abs=1e-12 * o["hist_orc"][0])
+
+
+def test_operator_level_parity(lib):
+    case = cases.channel3d(n=(8, 6, 6), pout=0.2, dt=0.05)
+    orc = cases.make_oracle(case)
+    state = case.initial_state(seed=21)
+    orc.set_state(*state)
+    ns = parity.make_ns(case, lib, "coupled", **parity.TIGHT)
+    parity.set_initial(ns, state)
+    rhs = orc.prepare_step()
+    rm, ri, rc = ns.ops["formfunction"](ns)
+    ov, oU, op = orc.split(rhs)
+    assert parity.rel(rm, ov) < 1e-13 and parity.relU(ri, oU) < 1e-13 and np.abs(rc).max() == 0.0
+    s = fb.NSB200GetSolver(ns)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(orc.nsol)
+    xv, xU, xp = orc.split(x)
+    # A
+    A = orc.matrix("A")
+    assert parity.rel(s.apply_momentum(xv).ravel(), A @ xv.ravel()) < 1e-13
+    # S = -(dt/rho) D Gst
+    S = orc.matrix("S")
+    assert parity.rel(s.apply_schur(xp).ravel(), S @ xp.ravel()) < 1e-12
+    # coupled operator
+    G, negT, negR, D = (orc.matrix(k) for k in ("G", "negT", "negR", "D"))
+    xUc = np.concatenate([u.ravel() for u in xU])
+    yv = A @ xv.ravel() + G @ xp.ravel()
+    yU = negT @ xv.ravel() + xUc + negR @ xp.ravel()
+    yp = D @ xUc
+    gv, gU, gp = s.apply_coupled(xv, xU, xp)
+    assert parity.rel(gv.ravel(), yv) < 1e-13
+    assert parity.rel(np.concatenate([u.ravel() for u in gU]), yU) < 1e-13
+    assert parity.rel(gp.ravel(), yp) < 1e-13
+    # one ABF application on a random right-hand side
+    xo, _ = orc.abf_apply(x, O.default_options(**parity.ORC_TIGHT))
+    av, aU, ap, st = s.apply_abf(xv, xU, xp)
+    o_v, o_U, o_p = orc.split(xo)
+    assert parity.rel(av, o_v) < 1e-10 and parity.relU(aU, o_U) < 1e-10 and parity.rel(ap, o_p) < 1e-9
+    assert st.abf_applies == 1 and st.mom_its > 0 and st.schur_its > 0
+
+
+def test_reference_style_driver_cavity(lib):
+    """The flow of fluca/tests/cavity_flow/cavity_flow_2d.c with -ns_type b200."""
+    mesh = fb.MeshCartCreate2d(None, fb.MESHCART_BOUNDARY_NONE, fb.MESHCART_BOUNDARY_NONE, 16, 16)
+    fb.MeshSetUp(mesh)
+    fb.MeshCartSetUniformCoordinates(mesh, 0.0, 1.0, 0.0, 1.0)
+    ns = fb.NSCreate()
+    fb.NSSetType(ns, fb.NSB200)
+    fb.NSB200SetLibrary(ns, lib)
+    fb.NSSetMesh(ns, mesh)
+    fb.NSSetDensity(ns, 1.0)
+    fb.NSSetViscosity(ns, 0.01)
+    wall = fb.NSBoundaryCondition(type=fb.NS_BC_VELOCITY, velocity=fb.constant_velocity(0.0, 0.0))
+    lid = fb.NSBoundaryCondition(type=fb.NS_BC_VELOCITY, velocity=fb.constant_velocity(1.0, 0.0))
+    for loc, bc in ((fb.MESHCART_LEFT, wall), (fb.MESHCART_RIGHT, wall), (fb.MESHCART_DOWN, wall), (fb.MESHCART_UP, lid)):
+        fb.NSSetBoundaryCondition(ns, fb.MeshCartGetBoundaryIndex(mesh, loc), bc)
+    seen = []
+    fb.NSMonitorSet(ns, lambda n: seen.append((n.step, n.t)))
+    fb.NSSetFromOptions(ns, {"ns_time_step_size": 0.01, "ns_max_steps": 3})
+    fb.NSSetUp(ns)
+    fb.NSSolve(ns)
+    assert ns.step == 3 and ns.reason == fb.NS_CONVERGED_ITS and ns.t == pytest.approx(0.03)
+    assert [s for s, _ in seen] == [0, 1, 2, 3]
+    # same run on the oracle at the reference's default tolerances: both are 1e-5-class answers
+    case = cases.cavity2d(n=16, dt=0.01)
+    orc = cases.make_oracle(case)
+    orc.set_state(*case.initial_state())
+    for _ in range(3):
+        orc.step(O.default_options())
+    v = fb.NSGetSolutionSubVector(ns, fb.NS_FIELD_VELOCITY)
+    assert parity.rel(v, orc.get_state()["v"]) < 1e-4
+    # checkpoint / restart round trip through viewsolution / loadsolution ("PressureHalfStep")
+    ck = {}
+    fb.NSViewSolution(ns, ck)
+    assert "PressureHalfStep" in ck and ck["step"] == 3
+    ns2 = parity.make_ns(case, lib, "coupled")
+    fb.NSLoadSolution(ns2, ck)
+    fb.NSSetMaxSteps(ns, 4), fb.NSSetMaxSteps(ns2, 4)
+    ns.reason = fb.NS_CONVERGED_ITERATING
+    fb.NSSolve(ns), fb.NSSolve(ns2)
+    assert parity.rel(fb.NSGetSolutionSubVector(ns2, fb.NS_FIELD_VELOCITY), fb.NSGetSolutionSubVector(ns, fb.NS_FIELD_VELOCITY)) < 1e-14
+    fb.NSDestroy(ns), fb.NSDestroy(ns2)
+
+
+def test_api_errors(lib):
+    ns = fb.NSCreate()
+    with pytest.raises(fb.FlucaError, match="Unknown ns type"):
+        fb.NSSetType(ns, "nosuchtype")
+    fb.NSSetType(ns, fb.NSB200)
+    with pytest.raises(fb.FlucaError, match="Mesh not set"):
+        fb.NSSetUp(ns)
+    mesh = fb.MeshCartCreate2d(None, 0, 0, 8, 8)
+    with pytest.raises(fb.FlucaError, match="after MeshSetUp"):
+        fb.MeshCartSetUniformCoordinates(mesh, 0, 1, 0, 1)
+    fb.MeshSetUp(mesh)
+    fb.MeshCartSetUniformCoordinates(mesh, 0, 1, 0, 1)
+    fb.NSB200SetLibrary(ns, lib)
+    fb.NSSetMesh(ns, mesh)
+    fb.NSSetDensity(ns, 1.0)
+    with pytest.raises(fb.FlucaError, match="Unsupported boundary condition type"):
+        fb.NSSetFromOptions(ns, {"ns_time_step_size": 0.1})
+        fb.NSSetUp(ns)
+    with pytest.raises(fb.FlucaError, match="max time or max steps"):
+        fb.NSSolve(ns)
+
+
+def test_divergence_is_reported_not_raised_when_asked(lib):
+    case = cases.cavity2d(n=16)
+    ns = parity.make_ns(case, lib, "coupled", ns_ksp_rtol=1e-14, ns_ksp_max_it=1)
+    parity.set_initial(ns, case.initial_state())
+    fb.NSSetErrorIfStepFailed(ns, False)
+    fb.NSStep(ns)
+    assert ns.reason == fb.NS_DIVERGED_NONLINEAR_SOLVE and ns.step == 0  # nsbasic.c:288-291
+    ns.reason = fb.NS_CONVERGED_ITERATING
+    fb.NSSetErrorIfStepFailed(ns, True)
+    with pytest.raises(fb.FlucaError, match="DIVERGED_NONLINEAR_SOLVE"):
+        fb.NSStep(ns)
