@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- Mcell-updates/s of one Navier-Stokes time step (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W                (our arm: CUDA kernels on N B200s)
+  python bench.py --impl reference --gpus N --steps K --warmup W   (reference arm: CPU restatement)
+
+One "step" = one full NS time step (NSStep) of the configured workload.  Prints ONE JSON line.
+See DESIGN.md section "Measurement" for every definition used here.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=0, help="cells per direction per GPU (default 256: BASELINE config 3)")
+    ap.add_argument("--mode", default="coupled", choices=["coupled", "fractional"])
+    ap.add_argument("--restart", type=int, default=10, help="outer GMRES restart (memory: (restart+1) x 7 fields)")
+    ap.add_argument("--cpu-n", type=int, default=48, help="cells per direction of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------- workload
+def cavity_case(n, nz, Re=400.0):
+    """BASELINE config 3: 3-D lid-driven cavity Re=400 on the unit cube, uniform h = 1/n, dt = 0.5 h,
+    zero initial state.  For the weak-scaling runs the box is extended in z (nz = n * N
+    cells, length N) so that every GPU keeps an n^3 slab."""
+    from tests import cases
+
+    c = cases.cavity3d_full(n=(n, n, nz), Re=Re, dt=0.5 / n)
+    c.hi = (1.0, 1.0, float(nz) / n)
+    return c
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        threading.Thread(target=self._read, daemon=True).start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.samples:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+def cpu_sample(n, steps, warmup, mode, threads):
+    """The CPU restatement of the reference algorithm (oracle, kind "port": assembled CSR operators,
+    GMRES(30) + block-Jacobi ILU(0), reference default tolerances) on an n^3 cavity, all host threads."""
+    from oracle import oracle as O
+    from tests import cases
+
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    case = cavity_case(n, n)
+    orc = cases.make_oracle_fast(case)
+    orc.set_state(*case.initial_state())
+    opt = O.default_options(mode=0 if mode == "coupled" else 1, ilu_blocks=threads)
+    infos = []
+    for _ in range(warmup):
+        orc.step(opt)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        infos.append(orc.step(opt))
+    dt = time.perf_counter() - t0
+    cells = float(n) ** 3
+    return dict(value=cells * steps / dt / 1e6, seconds=dt, steps=steps, n=n, outer=[i.outer_its for i in infos], mom=[i.mom_its for i in infos], schur=[i.schur_its for i in infos])
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = args.cpu_n
+    r = cpu_sample(n, args.steps, min(args.warmup, 1), args.mode, threads)
+    line = {
+        "impl": "reference",
+        "metric": "Mcell-updates/s per NS step",
+        "value": r["value"],
+        "unit": "Mcell-updates/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": min(args.warmup, 1),
+        "ms_per_step": 1e3 * r["seconds"] / r["steps"],
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"3-D lid-driven cavity Re=400 (BASELINE config 3), bounded CPU sample {n}^3, dt=0.5h, mode={args.mode}, reference default tolerances 1e-5", "mode": args.mode},
+        "cpu_baseline": {"value": r["value"], "unit": "Mcell-updates/s", "cores": threads, "kind": "port", "sample": f"{n}^3 cavity, {r['steps']} steps, outer its {r['outer']}, momentum its {r['mom']}, Schur its {r['schur']}; the reference (PETSc) cannot be built in this image, this is the repo's C restatement (oracle/)"},
+        "e2e": {"value": r["value"], "unit": "Mcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import fluca_b200 as fb
+    from tests import parity
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = fb._lib.load()  # CUDA library or a loud failure: there is no fallback
+    comm = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        # rank 0 makes the NCCL unique id of the solver's own communicator and ships it with torch.distributed
+        if rank == 0:
+            uid = np.frombuffer(fb.Comm.unique_id(lib), dtype=np.uint8).copy()
+            tid = torch.from_numpy(uid).to(dev)
+        else:
+            tid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        dist.broadcast(tid, 0)
+        uid_bytes = tid.cpu().numpy().tobytes()
+        comm = dict(rank=rank, nranks=world, make_comm=lambda L: fb.Comm.nccl(L, uid_bytes, rank, world))
+
+    n = args.n or 256
+    nzg = n * world  # weak scaling: an n^3 slab per GPU
+    case = cavity_case(n, nzg)
+    opts = {"ns_ksp_gmres_restart": args.restart}
+    ns = parity.make_ns(case, lib, args.mode, comm=comm, **opts)
+    s = fb.NSB200GetSolver(ns)
+    cells_total = float(n) * n * nzg
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value"): state lives in HBM, nothing crosses PCIe in the timed region
+    stream = torch.cuda.ExternalStream(s.stream(), device=dev)
+    for _ in range(args.warmup):
+        fb.NSStep(ns)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    s.kernel_times(reset=True)
+    s.kernel_timing(True)
+    l0 = s.launch_count()
+    stats = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            fb.NSStep(ns)
+            stats.append(fb.NSB200GetStats(ns))
+        e1.record(stream)
+    e1.synchronize()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = s.launch_count() - l0
+    ktimes = s.kernel_times(reset=True)
+    s.kernel_timing(False)
+    clocks = sampler.stop() if rank == 0 else None
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    value = cells_total * args.steps / (ms * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel class (live CUDA-event pairs around every launch in the timed region)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    cells_rank = float(n) ** 3
+    d3 = True
+    # algorithmic bytes per launch and cell (DESIGN.md "Kernels"): A apply + 2 dots reads x(3) v0(3) U0(3) a(3) writes y(3)
+    # momentum apply fused with two dots: reads x(3) v0(3) U0(3) (+ rhat(3) in the first of the two applies of a
+    # BiCGStab iteration), writes y(3): (120 + 96) / 2 = 108 B per cell and launch on average
+    per_launch = {"momentum_apply": 108.0, "poisson_apply": 16.0}
+    shares = {k: v[0] / ms for k, v in ktimes.items() if v[1] > 0}
+    roof = None
+    for name in ("momentum_apply", "poisson_apply"):
+        t, cnt = ktimes[name]
+        if cnt:
+            ach = per_launch[name] * cells_rank * cnt / (t * 1e-3) / 1e9
+            r = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "launches": cnt, "avg_ms": t / cnt, "share_of_step": t / ms, "peak_source": peak_src}
+            if roof is None or t > roof["_t"]:
+                roof = dict(r, _t=t)
+    if roof:
+        roof.pop("_t")
+    # whole-step model: algorithmic bytes of all kernels / elapsed
+    model_bytes = sum(s.model_bytes(st) for st in stats)
+    step_ach = model_bytes / (ms * 1e-3) / 1e9
+
+    line = {
+        "metric": "Mcell-updates/s per NS step",
+        "value": value,
+        "unit": "Mcell-updates/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": ms / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {
+            "workload": f"BASELINE config 3: 3-D lid-driven cavity Re=400, {n}x{n}x{nzg} cells ({n}^3 per GPU, z-slabs), dt=0.5h, zero initial state, NS type b200 mode={args.mode}, reference default tolerances (outer/momentum/Schur rtol 1e-5), GMRES restart {args.restart}; config 4 (512^3 sphere) needs the IBM coupling that is not built yet",
+            "mode": args.mode,
+            "l2": "inputs larger than L2 (each field 134 MB at 256^3 vs 126 MB L2; >50 fields streamed per step)",
+            "iterations_per_step": {"outer": [st.outer_its for st in stats], "momentum": [st.mom_its for st in stats], "schur": [st.schur_its for st in stats], "abf": [st.abf_applies for st in stats]},
+        },
+        "roofline": roof,
+        "step_roofline": {"algorithmic_GB_per_step": model_bytes / args.steps / 1e9, "achieved": step_ach * world, "peak": peak * world, "unit": "GB/s", "frac": step_ach / peak, "peak_source": peak_src},
+        "kernel_shares": {k: round(v, 4) for k, v in shares.items()},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+
+    # ---- end to end through the public API with HOST buffers (pinned): H2D of the step's inputs + step + D2H of the result
+    if not args.no_e2e:
+        st0 = s.get_state()
+        host = {k: torch.empty(v.shape, dtype=torch.float64).pin_memory().numpy() for k, v in (("v", st0["v"]), ("p", st0["p"]), ("phalf", st0["phalf"]))}
+        hostU = [torch.empty(u.shape, dtype=torch.float64).pin_memory().numpy() for u in st0["U"]]
+        for k in host:
+            host[k][...] = st0[k]
+        for a, u in zip(hostU, st0["U"]):
+            a[...] = u
+        h2d = sum(a.nbytes for a in host.values()) + sum(a.nbytes for a in hostU)
+        d2h = h2d
+        import ctypes as C
+
+        def ptrs(arrs):
+            p = (C.c_void_p * 3)()
+            for i, a in enumerate(arrs):
+                p[i] = a.ctypes.data
+            return p
+
+        ksteps = max(1, min(args.steps, 2))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            fb._lib.check(lib, lib.fluca_b200_set_state(s._h, host["v"].ctypes.data, ptrs(hostU), host["p"].ctypes.data, host["phalf"].ctypes.data))
+            fb.NSStep(ns)
+            fb._lib.check(lib, lib.fluca_b200_get_state(s._h, host["v"].ctypes.data, ptrs(hostU), host["p"].ctypes.data, host["phalf"].ctypes.data))
+        barrier()
+        te = time.perf_counter() - t0
+        tt = torch.tensor([te], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        te = float(tt.item())
+        line["e2e"] = {"value": cells_total * ksteps / te / 1e6, "unit": "Mcell-updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": ksteps, "note": "NSStep through the NS API with pinned host buffers: set_state (H2D) + boundary planes + step + get_state (D2H) inside the timed region"}
+
+    # ---- CPU baseline on the box's host cores (rank 0, N=1 only), bounded sample
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        r = cpu_sample(args.cpu_n, 1, 0, args.mode, threads)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "Mcell-updates/s", "cores": threads, "kind": "port", "sample": f"{args.cpu_n}^3 cavity (same BCs, dt=0.5h, mode={args.mode}, tolerances 1e-5), 1 step in {r['seconds']:.1f} s: the reference needs PETSc (absent) so this is the repo's C restatement"}
+    if rank == 0:
+        print(json.dumps(line))
+    fb.NSDestroy(ns)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -87,6 +87,7 @@ SYMBOLS = [
     "fluca_b200_get_rhs",
     "fluca_b200_apply_momentum",
     "fluca_b200_apply_schur",
+    "fluca_b200_apply_vcycle",
     "fluca_b200_apply_coupled",
     "fluca_b200_apply_abf",
     "fluca_b200_snapshot_save",
@@ -123,6 +124,7 @@ def _prototype(L):
     L.fluca_b200_get_rhs.argtypes = [_P, _P, _PD3, _P]
     L.fluca_b200_apply_momentum.argtypes = [_P, _P, _P]
     L.fluca_b200_apply_schur.argtypes = [_P, _P, _P]
+    L.fluca_b200_apply_vcycle.argtypes = [_P, _P, _P]
     L.fluca_b200_apply_coupled.argtypes = [_P, _P, _PD3, _P, _P, _PD3, _P]
     L.fluca_b200_apply_abf.argtypes = [_P, _P, _PD3, _P, _P, _PD3, _P, C.POINTER(Stats)]
     L.fluca_b200_snapshot_save.argtypes = [_P]

@@ -293,6 +293,17 @@ extern "C" int fluca_b200_apply_schur(fluca_b200_solver *h, const double *p, dou
   API_END
 }
 
+extern "C" int fluca_b200_apply_vcycle(fluca_b200_solver *h, const double *r, double *z)
+{
+  API_BEGIN
+  Solver &s = h->s;
+  put(s, s.pr, r, cell_ext(s.gh.g));
+  double *zf = mg_vcycle(s, s.pr);
+  get(s, z, zf, cell_ext(s.gh.g));
+  s.ex.sync();
+  API_END
+}
+
 extern "C" int fluca_b200_apply_coupled(fluca_b200_solver *h, const double *xv, const double *const xU[3], const double *xp, double *yv, double *const yU[3], double *yp)
 {
   API_BEGIN

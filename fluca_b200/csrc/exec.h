@@ -64,6 +64,7 @@ struct Exec {
   ExecStats stats;
   // optional per-class event timing
   bool      ktime_on = false;
+  int       kt_current = 7; // class charged by the launchers (KScope sets it); default KT_OUTER
 #ifndef FLUCA_HOSTEMU
   std::vector<cudaEvent_t> kt_ev;   // pairs
   std::vector<int>         kt_cls;
@@ -93,7 +94,11 @@ inline void *dev_alloc(size_t bytes)
   if (bytes == 0) bytes = 8;
 #ifndef FLUCA_HOSTEMU
   FL_CUDA(cudaMalloc(&p, bytes));
+  // cudaMemset runs on the legacy default stream and may return before it completes; the solver's
+  // stream is non-blocking, so without this synchronisation a later upload / kernel on that stream
+  // could be overtaken by the zero-fill (seen on B200: multigrid tables zeroed after their upload)
   FL_CUDA(cudaMemset(p, 0, bytes));
+  FL_CUDA(cudaDeviceSynchronize());
 #else
   p = calloc(1, bytes);
   if (!p) throw Error(FL_ERR_INTERNAL, "host allocation failed");
@@ -243,6 +248,14 @@ struct KTimer {
   }
 };
 
+// selects the class that the launchers below charge their event pairs to
+struct KScope {
+  Exec &ex;
+  int   prev;
+  KScope(Exec &e, int cls) : ex(e), prev(e.kt_current) { ex.kt_current = cls; }
+  ~KScope() { ex.kt_current = prev; }
+};
+
 inline void Exec::ktime_collect()
 {
 #ifndef FLUCA_HOSTEMU
@@ -265,15 +278,27 @@ struct Box {
 };
 
 #ifndef FLUCA_HOSTEMU
-static const int BX = 64, BY = 4; // 256 threads: x fastest for coalescing, 4 rows share y-neighbours in L1
+// 256 threads: one warp = one 32-cell row segment (256 B, coalesced); 8 rows share their y-neighbours in L1.
+// Every block marches a CONTIGUOUS chunk of planes: plane k+1 fetched for cell (i,j,k) is served from L1
+// again as the centre plane of k+1 and the lower plane of k+2, so z-neighbours cost no extra DRAM traffic.
+static const int BX = 32, BY = 8;
+
+FL_HD void z_chunk(int nz, int nchunks, int c, int &k0, int &k1)
+{
+  const int base = nz / nchunks, rem = nz % nchunks;
+  k0 = c * base + (c < rem ? c : rem);
+  k1 = k0 + base + (c < rem ? 1 : 0);
+}
 
 template <class F>
-__global__ void __launch_bounds__(BX *BY) k_box(Box b, F f)
+__global__ void __launch_bounds__(BX *BY, 2) k_box(Box b, F f)
 {
   const int i = blockIdx.x * BX + threadIdx.x;
   const int j = blockIdx.y * BY + threadIdx.y;
   if (i >= b.nx || j >= b.ny) return;
-  for (int k = blockIdx.z; k < b.nz; k += gridDim.z) f(i, j, k);
+  int k0, k1;
+  z_chunk(b.nz, gridDim.z, blockIdx.z, k0, k1);
+  for (int k = k0; k < k1; ++k) f(i, j, k);
 }
 
 template <class F>
@@ -334,15 +359,18 @@ __device__ __forceinline__ void block_reduce_and_finish(double (&acc)[NR], doubl
 }
 
 template <int NR, class F>
-__global__ void __launch_bounds__(BX *BY) k_box_reduce(Box b, F f, double *partials, double *result, unsigned *ticket)
+__global__ void __launch_bounds__(BX *BY, 2) k_box_reduce(Box b, F f, double *partials, double *result, unsigned *ticket)
 {
   const int i = blockIdx.x * BX + threadIdx.x;
   const int j = blockIdx.y * BY + threadIdx.y;
   double    acc[NR];
 #pragma unroll
   for (int r = 0; r < NR; ++r) acc[r] = 0.;
-  if (i < b.nx && j < b.ny)
-    for (int k = blockIdx.z; k < b.nz; k += gridDim.z) f(i, j, k, acc);
+  if (i < b.nx && j < b.ny) {
+    int k0, k1;
+    z_chunk(b.nz, gridDim.z, blockIdx.z, k0, k1);
+    for (int k = k0; k < k1; ++k) f(i, j, k, acc);
+  }
   const unsigned nblocks = gridDim.x * gridDim.y * gridDim.z;
   const unsigned bid     = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
   block_reduce_and_finish<NR>(acc, partials, result, ticket, nblocks, bid);
@@ -381,7 +409,8 @@ inline void for_box(Exec &ex, Box b, F f)
   if (b.nx <= 0 || b.ny <= 0 || b.nz <= 0) return;
   ex.stats.launches++;
 #ifndef FLUCA_HOSTEMU
-  dim3 g = box_grid(ex, b, 0);
+  dim3   g = box_grid(ex, b, 0);
+  KTimer kt(ex, ex.kt_current);
   k_box<<<g, dim3(BX, BY, 1), 0, ex.stream>>>(b, f);
   FL_CUDA(cudaGetLastError());
 #else
@@ -400,6 +429,7 @@ inline void for_range(Exec &ex, long n, F f)
 #ifndef FLUCA_HOSTEMU
   long blocks = (n + 255) / 256, cap = (long)ex.sm_count * 16;
   if (blocks > cap) blocks = cap;
+  KTimer kt(ex, ex.kt_current);
   k_range<<<(unsigned)blocks, 256, 0, ex.stream>>>(n, f);
   FL_CUDA(cudaGetLastError());
 #else
@@ -420,6 +450,7 @@ inline void for_box_reduce(Exec &ex, Box b, F f)
   }
   dim3 g = box_grid(ex, b, ex.max_blocks);
   if ((long)g.x * g.y * g.z > ex.max_blocks) throw Error(FL_ERR_INTERNAL, "reduction grid exceeds partial buffer");
+  KTimer kt(ex, ex.kt_current);
   k_box_reduce<NR><<<g, dim3(BX, BY, 1), 0, ex.stream>>>(b, f, ex.d_partials, ex.d_result, ex.d_ticket);
   FL_CUDA(cudaGetLastError());
 #else
@@ -445,6 +476,7 @@ inline void for_range_reduce(Exec &ex, long n, F f)
   long blocks = (n + 255) / 256, cap = (long)ex.sm_count * 8;
   if (blocks > cap) blocks = cap;
   if (blocks > ex.max_blocks) blocks = ex.max_blocks;
+  KTimer kt(ex, ex.kt_current);
   k_range_reduce<NR><<<(unsigned)blocks, 256, 0, ex.stream>>>(n, f, ex.d_partials, ex.d_result, ex.d_ticket);
   FL_CUDA(cudaGetLastError());
 #else

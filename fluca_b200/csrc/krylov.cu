@@ -50,7 +50,7 @@ static void a_apply_dots(Solver &s, const V3 &x, const V3 &y, const V3 &a, doubl
 {
   halo_cells(s, x);
   {
-    KTimer kt(s.ex, KT_MOMENTUM_APPLY);
+    KScope kt(s.ex, KT_MOMENTUM_APPLY);
     if (s.dim == 2) {
       AApplyDots<2> f;
       f.g = s.gh.g, f.sp = s.sp, f.bc = s.bc, f.x = CV3(x), f.v0 = CV3(s.v0), f.U0 = CV3(s.U0), f.a = CV3(a), f.y = y;
@@ -76,6 +76,7 @@ static P3 off3(const Solver &s, const V3 &v)
 
 int momentum_solve(Solver &s, const V3 &b, const V3 &x)
 {
+  KScope ks(s.ex, KT_MOMENTUM_VEC);
   const int    nc  = s.dim;
   const long   len = interior_len(s);
   const P3     B = off3(s, b), X = off3(s, x), R = off3(s, s.kr), RH = off3(s, s.krh), PV = off3(s, s.kp), VV = off3(s, s.kv), SV = off3(s, s.ks), TV = off3(s, s.kt);
@@ -83,7 +84,7 @@ int momentum_solve(Solver &s, const V3 &b, const V3 &x)
   // x = 0, r = rhat = p = b, rho = <b, b>
   for_range_reduce<1>(s.ex, len, FL_LAMBDA(long i, double acc[1]) {
     double t = 0.;
-    for (int q = 0; q < nc; ++q) {
+    _Pragma("unroll") for (int q = 0; q < 3; ++q) if (q < nc) {
       const double bv = B.c[q][i];
       X.c[q][i]  = 0.;
       R.c[q][i]  = bv;
@@ -110,7 +111,7 @@ int momentum_solve(Solver &s, const V3 &b, const V3 &x)
     // s = r - alpha v, |s|^2
     for_range_reduce<1>(s.ex, len, FL_LAMBDA(long i, double acc[1]) {
       double t = 0.;
-      for (int q = 0; q < nc; ++q) {
+      _Pragma("unroll") for (int q = 0; q < 3; ++q) if (q < nc) {
         const double sv = R.c[q][i] - alpha * VV.c[q][i];
         SV.c[q][i]      = sv;
         t += sv * sv;
@@ -121,7 +122,7 @@ int momentum_solve(Solver &s, const V3 &b, const V3 &x)
     ++it;
     if (std::sqrt(red[0]) <= tol) {
       for_range(s.ex, len, FL_LAMBDA(long i) {
-        for (int q = 0; q < nc; ++q) X.c[q][i] += alpha * PV.c[q][i];
+        _Pragma("unroll") for (int q = 0; q < 3; ++q) if (q < nc) X.c[q][i] += alpha * PV.c[q][i];
       });
       s.stats.mom_last_rel = std::sqrt(red[0]) / bnorm;
       break;
@@ -133,7 +134,7 @@ int momentum_solve(Solver &s, const V3 &b, const V3 &x)
     // x += alpha p + omega s ; r = s - omega t ; |r|^2, <rhat, r>
     for_range_reduce<2>(s.ex, len, FL_LAMBDA(long i, double acc[2]) {
       double t0 = 0., t1 = 0.;
-      for (int q = 0; q < nc; ++q) {
+      _Pragma("unroll") for (int q = 0; q < 3; ++q) if (q < nc) {
         const double sv = SV.c[q][i];
         X.c[q][i] += alpha * PV.c[q][i] + omega * sv;
         const double rv = sv - omega * TV.c[q][i];
@@ -154,7 +155,7 @@ int momentum_solve(Solver &s, const V3 &b, const V3 &x)
     rho               = rho_new;
     // p = r + beta (p - omega v)
     for_range(s.ex, len, FL_LAMBDA(long i) {
-      for (int q = 0; q < nc; ++q) PV.c[q][i] = R.c[q][i] + beta * (PV.c[q][i] - omega * VV.c[q][i]);
+      _Pragma("unroll") for (int q = 0; q < 3; ++q) if (q < nc) PV.c[q][i] = R.c[q][i] + beta * (PV.c[q][i] - omega * VV.c[q][i]);
     });
   }
   s.stats.mom_its += it;
@@ -181,7 +182,7 @@ static double poisson_apply_dot(Solver &s, double *pin, double *out, const doubl
 {
   halo_scalar(s, pin);
   {
-    KTimer kt(s.ex, KT_POISSON_APPLY);
+    KScope kt(s.ex, KT_POISSON_APPLY);
     if (s.dim == 2) {
       PoissonApplyDot<2> f;
       f.g = s.gh.g, f.p = pin, f.a = a, f.out = out;
@@ -204,6 +205,7 @@ void poisson_apply(Solver &s, double *pin, double *out)
 
 static int poisson_pcg(Solver &s, double *b, double *x)
 {
+  KScope ks(s.ex, KT_POISSON_VEC);
   const long off = interior_off(s), len = interior_len(s);
   double    *B = b + off, *X = x + off, *R = s.pr + off, *PP = s.pp + off, *Q = s.pq + off;
   double     red[2];
@@ -249,6 +251,7 @@ static int poisson_pcg(Solver &s, double *b, double *x)
     reduce_finish(s, 1, red);
     ++it;
     s.stats.schur_last_rel = std::sqrt(red[0]) / bnorm;
+    if (getenv("FLUCA_B200_DEBUG")) fprintf(stderr, "  pcg it %d rz %.15e pq %.15e alpha %.15e rel %.6e\n", it, rz, pq, alpha, s.stats.schur_last_rel);
     if (std::sqrt(red[0]) <= tol) break;
   }
   s.stats.schur_its += it;
@@ -258,6 +261,7 @@ static int poisson_pcg(Solver &s, double *b, double *x)
 // right-preconditioned BiCGStab (pressure outlet present: boundary rows of P are not symmetric)
 static int poisson_bicgstab(Solver &s, double *b, double *x)
 {
+  KScope ks(s.ex, KT_POISSON_VEC);
   const long off = interior_off(s), len = interior_len(s);
   double    *B = b + off, *X = x + off, *R = s.pr + off, *RH = s.prh + off, *PP = s.pp + off, *V = s.pq + off, *S = s.ps + off, *T = s.pt + off;
   double     red[2];

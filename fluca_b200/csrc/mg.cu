@@ -203,7 +203,7 @@ void smooth(Solver &s, MGLevel &L, bool zero_guess)
 {
   const double omega = (DIM == 3) ? 6. / 7. : 0.8;
   if (!zero_guess) level_halo(s, L, L.x);
-  KTimer        kt(s.ex, KT_MG_SMOOTH);
+  KScope        kt(s.ex, KT_MG_SMOOTH);
   MGSmooth<DIM> f;
   f.L = L, f.omega = omega, f.zero_guess = zero_guess ? 1 : 0, f.xin = L.x, f.b = L.b, f.xout = zero_guess ? L.x : L.t;
   for_box(s.ex, level_box(L), f);
@@ -229,7 +229,7 @@ void vcycle(Solver &s, size_t l)
   MGLevel &C = s.mg[l + 1];
   level_halo(s, L, L.x);
   {
-    KTimer               kt(s.ex, KT_MG_TRANSFER);
+    KScope               kt(s.ex, KT_MG_TRANSFER);
     MGResidRestrict<DIM> rr;
     rr.F = L, rr.C = C;
     for_box(s.ex, level_box(C), rr);
@@ -237,7 +237,7 @@ void vcycle(Solver &s, size_t l)
   vcycle<DIM>(s, l + 1);
   level_halo(s, C, C.x);
   {
-    KTimer         kt(s.ex, KT_MG_TRANSFER);
+    KScope         kt(s.ex, KT_MG_TRANSFER);
     MGProlong<DIM> pr;
     pr.F = L, pr.C = C;
     for_box(s.ex, level_box(L), pr);

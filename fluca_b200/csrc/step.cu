@@ -240,6 +240,7 @@ static void for_boundary(Solver &s, int b, F f)
 template <int DIM>
 static void build_rhs(Solver &s)
 {
+  KScope ks(s.ex, KT_RHS_PROJECT);
   const Geom      &g  = s.gh.g;
   const bool       first = (s.step_index == 0);
   double          *q  = first ? s.p : s.phalf; // cnlinearcart3d.c:2972-2982
@@ -356,6 +357,7 @@ static void remove_mean(Solver &s, double *f)
 template <int DIM>
 static void abf_apply_t(Solver &s, const V3 &bm, const V3 &bi, const double *bcn, const V3 &ov, const V3 &oU, double *op)
 {
+  KScope ks(s.ex, KT_RHS_PROJECT);
   const Geom &g = s.gh.g;
   // stage 1 (abfpc.c:72-77)
   momentum_solve(s, bm, s.vstar);
@@ -497,6 +499,7 @@ static void mv_zero(Solver &s, const MV &y)
 // norm; x is built in (s.xv, s.xU, s.xp)
 static int outer_gmres(Solver &s)
 {
+  KScope ks(s.ex, KT_OUTER);
   const int m = s.opt.outer_restart;
   MV        X = make_mv(s, s.xv, s.xU, s.xp), Bv = make_mv(s, s.rm, s.ri, s.rc), W = make_mv(s, s.wv, s.wU, s.wp), Z = make_mv(s, s.zv, s.zU, s.zp);
   std::vector<MV> V;

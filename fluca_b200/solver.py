@@ -207,6 +207,12 @@ class Solver:
         _lib.check(self.L, self.L.fluca_b200_apply_schur(self._h, p.ctypes.data, y.ctypes.data))
         return y
 
+    def apply_vcycle(self, r):
+        r = self._cells(r)
+        z = self.new_cells()
+        _lib.check(self.L, self.L.fluca_b200_apply_vcycle(self._h, r.ctypes.data, z.ctypes.data))
+        return z
+
     def apply_coupled(self, xv, xU, xp):
         xv, xU, xp = self._cells(xv, self.dim), self._faces(xU), self._cells(xp)
         yv, yU, yp = self.new_cells(self.dim), self.new_faces(), self.new_cells()

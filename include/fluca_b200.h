@@ -129,6 +129,9 @@ int fluca_b200_apply_coupled(fluca_b200_solver *s, const double *xv, const doubl
 /* x = PCApply_ABF(b) (abfpc.c:48-111) */
 int fluca_b200_apply_abf(fluca_b200_solver *s, const double *bv, const double *const bU[3], const double *bp, double *xv, double *const xU[3], double *xp, fluca_b200_stats *stats);
 
+/* z = one multigrid V-cycle applied to r (the pressure preconditioner alone), for tests */
+int fluca_b200_apply_vcycle(fluca_b200_solver *s, const double *r, double *z);
+
 /* ---- device-resident access (HBM-resident benchmarking, GPU-side consumers) ---- */
 /* copies the current state into / from a second device snapshot without touching the host */
 int fluca_b200_snapshot_save(fluca_b200_solver *s);

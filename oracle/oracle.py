@@ -129,6 +129,9 @@ class BC:
     type: int
     velocity: Optional[Callable] = None
     pressure: Optional[Callable] = None
+    # constants evaluated by the oracle's built-in C callbacks (timing runs: no Python in the loop)
+    const_velocity: Optional[Sequence[float]] = None
+    const_pressure: Optional[float] = None
 
 
 class Oracle:
@@ -148,9 +151,19 @@ class Oracle:
                 continue
             bc = bcs[b]
             cbcs[b].type = bc.type
-            if bc.velocity is not None:
+            if bc.const_velocity is not None:
+                arr = (C.c_double * 3)(*(list(bc.const_velocity) + [0.0] * 3)[:3])
+                self._keep.append(arr)
+                cbcs[b].velocity = C.cast(L.orc_bc_constant, _BCFN)
+                cbcs[b].ctx_velocity = C.cast(arr, C.c_void_p)
+            elif bc.velocity is not None:
                 cbcs[b].velocity = self._wrap_velocity(bc.velocity)
-            if bc.pressure is not None:
+            if bc.const_pressure is not None:
+                arr = (C.c_double * 1)(float(bc.const_pressure))
+                self._keep.append(arr)
+                cbcs[b].pressure = C.cast(L.orc_bc_constant_pressure, _BCFN)
+                cbcs[b].ctx_pressure = C.cast(arr, C.c_void_p)
+            elif bc.pressure is not None:
                 cbcs[b].pressure = self._wrap_pressure(bc.pressure)
         self._xf = [np.ascontiguousarray(a, dtype=np.float64) for a in xf]
         for d in range(self.dim):

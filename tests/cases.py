@@ -104,7 +104,19 @@ def _smooth(rng, grids, lo, hi):
 
 
 def _const(*vals):
-    return lambda dim, t, x: vals[:dim]
+    """Constant boundary velocity.  Works point-wise (x = list of floats, what the oracle's callback
+    passes) and vectorised (x = list of coordinate arrays, what the GPU host layer passes once per plane)."""
+
+    def f(dim, t, x):
+        shape = np.shape(x[0])
+        if shape:
+            return [np.full(shape, float(v)) for v in vals[:dim]]
+        return vals[:dim]
+
+    f.const = tuple(vals)
+    f.vectorized = True
+    f.time_independent = True
+    return f
 
 
 def cavity2d(n=16, Re=100.0, dt=None):
@@ -184,4 +196,15 @@ def make_oracle(case):
     from oracle import oracle as O
 
     bcs = [O.BC(b["type"], velocity=b["velocity"], pressure=b["pressure"]) for b in case.bcs]
+    return O.Oracle(case.n, case.faces(), case.rho, case.mu, case.dt, bcs)
+
+
+def make_oracle_fast(case):
+    """Same, but constant boundary data goes through the oracle's built-in C callbacks (timing runs)."""
+    from oracle import oracle as O
+
+    bcs = []
+    for b in case.bcs:
+        cv = getattr(b["velocity"], "const", None) if b["velocity"] is not None else None
+        bcs.append(O.BC(b["type"], velocity=b["velocity"], pressure=b["pressure"], const_velocity=cv))
     return O.Oracle(case.n, case.faces(), case.rho, case.mu, case.dt, bcs)

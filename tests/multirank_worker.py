@@ -1,0 +1,107 @@
+"""Worker of the world_size>1 CPU test: one process per rank, gloo backend, the solver library's
+host-emulation test double with a callback communicator (halo exchange = dist.isend/irecv of ghost
+planes, Krylov reductions = dist.all_reduce).  Exercises the slab partition, the halo protocol and
+the multi-rank multigrid / Krylov orchestration of the product sources without a GPU."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import fluca_b200 as fb
+from tests import cases, parity
+
+
+def make_comm_factory(rank, nranks):
+    def factory(L):
+        def view(ptr, count):
+            return np.ctypeslib.as_array(ptr, shape=(count,))
+
+        def halo(ctx, send_down, recv_down, send_up, recv_up, count, periodic):
+            down = rank - 1 if rank > 0 else (nranks - 1 if periodic else None)
+            up = rank + 1 if rank < nranks - 1 else (0 if periodic else None)
+            reqs, recvs = [], []
+            if down is not None:
+                reqs.append(dist.isend(torch.from_numpy(view(send_down, count).copy()), down, tag=0))
+                t = torch.empty(count, dtype=torch.float64)
+                reqs.append(dist.irecv(t, down, tag=1))
+                recvs.append((recv_down, t))
+            if up is not None:
+                reqs.append(dist.isend(torch.from_numpy(view(send_up, count).copy()), up, tag=1))
+                t = torch.empty(count, dtype=torch.float64)
+                reqs.append(dist.irecv(t, up, tag=0))
+                recvs.append((recv_up, t))
+            for r in reqs:
+                r.wait()
+            for ptr, t in recvs:
+                view(ptr, count)[:] = t.numpy()
+            return 0
+
+        def allsum(ctx, vals, n):
+            a = view(vals, n)
+            t = torch.from_numpy(a.copy())
+            dist.all_reduce(t)
+            a[:] = t.numpy()
+            return 0
+
+        def allgather(ctx, send, recv, count):
+            t = torch.from_numpy(view(send, count).copy())
+            out = [torch.empty(count, dtype=torch.float64) for _ in range(nranks)]
+            dist.all_gather(out, t)
+            view(recv, count * nranks)[:] = torch.cat(out).numpy()
+            return 0
+
+        return fb.Comm.callbacks(L, rank, nranks, halo, allsum, allgather)
+
+    return factory
+
+
+def main():
+    case_name, mode, out_path = sys.argv[1], sys.argv[2], sys.argv[3]
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = parity.hostemu_library() if rank == 0 else None
+    dist.barrier()
+    lib = lib or fb._lib.load(parity.HOSTEMU)
+    case = {
+        "channel3d": lambda: cases.channel3d(n=(8, 6, 8), pout=0.2, dt=0.05),
+        "cavity3d": lambda: cases.cavity3d_full(n=(8, 8, 8)),
+        "periodic_z": lambda: cases.channel3d(n=(8, 6, 8), periodic_z=True, dt=0.05),
+        "uneven": lambda: cases.cavity3d_full(n=(8, 6, 7)),
+        "three": lambda: cases.cavity3d_full(n=(8, 6, 9)),
+    }[case_name]()
+    comm = dict(rank=rank, nranks=world, make_comm=make_comm_factory(rank, world))
+    ns = parity.make_ns(case, lib, mode, comm=comm, **parity.TIGHT)
+    s = fb.NSB200GetSolver(ns)
+    v, U, p = case.initial_state(seed=31)
+    k0, nzl = s.k0, s.nzl
+    sl = slice(k0, k0 + nzl)
+    Uz = U[2][k0 : k0 + nzl + (1 if s.last_z else 0)]
+    s.set_state(v=v[:, sl], U=[U[0][sl], U[1][sl], Uz], p=p[sl])
+    its = []
+    for _ in range(2):
+        fb.NSStep(ns)
+        st = fb.NSB200GetStats(ns)
+        its.append((st.outer_its, st.mom_its, st.schur_its))
+    loc = s.get_state()
+    # gather slabs on rank 0
+    parts = [None] * world
+    dist.all_gather_object(parts, dict(k0=k0, nzl=nzl, v=loc["v"], U=loc["U"], p=loc["p"], phalf=loc["phalf"]))
+    if rank == 0:
+        parts.sort(key=lambda d: d["k0"])
+        gv = np.concatenate([d["v"] for d in parts], axis=1)
+        gp = np.concatenate([d["p"] for d in parts], axis=0)
+        gph = np.concatenate([d["phalf"] for d in parts], axis=0)
+        gU = [np.concatenate([d["U"][a] for d in parts], axis=0) for a in range(3)]
+        np.savez(out_path, v=gv, p=gp, phalf=gph, U0=gU[0], U1=gU[1], U2=gU[2], its=np.array(its))
+    fb.NSDestroy(ns)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

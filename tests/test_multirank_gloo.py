@@ -1,0 +1,70 @@
+"""world_size-2 (and 3) CPU tests of the N>1 path: the slab-partitioned solve must reproduce the
+single-domain oracle to 1e-10 and take the same number of outer iterations."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import cases, parity
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def run_world(case_name, mode, world, tmp_path):
+    out = str(tmp_path / f"{case_name}_{mode}_{world}.npz")
+    port = _free_port()
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "multirank_worker.py"), case_name, mode, out], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    logs = []
+    for p in procs:
+        try:
+            o, _ = p.communicate(timeout=600)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        logs.append(o)
+    assert all(p.returncode == 0 for p in procs), "\n".join(logs)
+    return np.load(out)
+
+
+CASEMAP = {
+    "channel3d": lambda: cases.channel3d(n=(8, 6, 8), pout=0.2, dt=0.05),
+    "cavity3d": lambda: cases.cavity3d_full(n=(8, 8, 8)),
+    "periodic_z": lambda: cases.channel3d(n=(8, 6, 8), periodic_z=True, dt=0.05),
+    "uneven": lambda: cases.cavity3d_full(n=(8, 6, 7)),
+    "three": lambda: cases.cavity3d_full(n=(8, 6, 9)),
+}
+
+
+@pytest.mark.parametrize(
+    "case_name,mode,world",
+    [("cavity3d", "coupled", 2), ("channel3d", "coupled", 2), ("periodic_z", "fractional", 2), ("uneven", "fractional", 2), ("three", "fractional", 3)],
+)
+def test_slab_partition_matches_oracle(case_name, mode, world, tmp_path):
+    parity.hostemu_library()
+    got = run_world(case_name, mode, world, tmp_path)
+    case = CASEMAP[case_name]()
+    orc = cases.make_oracle(case)
+    orc.set_state(*case.initial_state(seed=31))
+    infos = [orc.step(O.default_options(mode=0 if mode == "coupled" else 1, **parity.ORC_TIGHT)) for _ in range(2)]
+    ref = orc.get_state()
+    assert parity.rel(got["v"], ref["v"]) < 1e-10
+    assert parity.relU([got["U0"], got["U1"], got["U2"]], ref["U"]) < 1e-10
+    assert parity.rel(got["p"], ref["p"]) < 1e-9 and parity.rel(got["phalf"], ref["phalf"]) < 1e-9
+    if mode == "coupled":
+        assert [int(a) for a in got["its"][:, 0]] == [i.outer_its for i in infos]
