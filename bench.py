@@ -24,6 +24,9 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 
+print_json = print
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -140,7 +143,7 @@ def run_reference(args):
         "e2e": {"value": r["value"], "unit": "Mcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print_json(json.dumps(line))
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
@@ -312,7 +315,7 @@ def run_b200(args):
         r = cpu_sample(args.cpu_n, 1, 0, args.mode, threads)
         line["cpu_baseline"] = {"value": r["value"], "unit": "Mcell-updates/s", "cores": threads, "kind": "port", "sample": f"{args.cpu_n}^3 cavity (same BCs, dt=0.5h, mode={args.mode}, tolerances 1e-5), 1 step in {r['seconds']:.1f} s: the reference needs PETSc (absent) so this is the repo's C restatement"}
     if rank == 0:
-        print(json.dumps(line))
+        print_json(json.dumps(line))
     fb.NSDestroy(ns)
     if world > 1:
         dist.destroy_process_group()
@@ -320,6 +323,19 @@ def run_b200(args):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL prints its version there)
+    # are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(real_stdout, "w")
+
+    def emit(text):
+        out.write(text + "\n")
+        out.flush()
+
+    global print_json
+    print_json = emit
     if args.impl == "reference":
         run_reference(args)
     else:

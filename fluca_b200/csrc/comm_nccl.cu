@@ -37,16 +37,15 @@ struct NcclComm : public Comm {
       return;
     }
     FL_NCCL(ncclGroupStart());
+    // Post order matters when both neighbours are the same rank (2 ranks, periodic z): NCCL pairs the
+    // k-th send to a peer with that peer's k-th receive from us.  Sends: plane 0 (down), plane nzl-1 (up);
+    // receives: ghost nzl (their plane 0), ghost -1 (their plane nzl-1).
     for (int f = 0; f < nf; ++f) {
       double *a = fields[f];
-      if (down >= 0) {
-        FL_NCCL(ncclSend(a + plane, plane, ncclDouble, down, comm, ex.stream));     // my plane 0 -> their ghost nzl
-        FL_NCCL(ncclRecv(a, plane, ncclDouble, down, comm, ex.stream));             // their plane nzl-1 -> my ghost -1
-      }
-      if (up >= 0) {
-        FL_NCCL(ncclSend(a + plane * nzl, plane, ncclDouble, up, comm, ex.stream)); // my plane nzl-1 -> their ghost -1
-        FL_NCCL(ncclRecv(a + plane * (nzl + 1), plane, ncclDouble, up, comm, ex.stream));
-      }
+      if (down >= 0) FL_NCCL(ncclSend(a + plane, plane, ncclDouble, down, comm, ex.stream));
+      if (up >= 0) FL_NCCL(ncclSend(a + plane * nzl, plane, ncclDouble, up, comm, ex.stream));
+      if (up >= 0) FL_NCCL(ncclRecv(a + plane * (nzl + 1), plane, ncclDouble, up, comm, ex.stream));
+      if (down >= 0) FL_NCCL(ncclRecv(a, plane, ncclDouble, down, comm, ex.stream));
     }
     FL_NCCL(ncclGroupEnd());
     ex.stats.launches++;

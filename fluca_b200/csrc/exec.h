@@ -23,9 +23,19 @@
 #include <cuda_runtime.h>
 #define FL_HD __host__ __device__ __forceinline__
 #define FL_LAMBDA [=] __host__ __device__
+// read-only (non-coherent) load of coefficient-table entries; warp-uniform vote over the active lanes
+#ifdef __CUDA_ARCH__
+#define FL_LDG(p) __ldg(p)
+#define FL_WARP_ALL(pred) __all_sync(__activemask(), (pred))
+#else
+#define FL_LDG(p) (*(p))
+#define FL_WARP_ALL(pred) (pred)
+#endif
 #else
 #define FL_HD inline
 #define FL_LAMBDA [=]
+#define FL_LDG(p) (*(p))
+#define FL_WARP_ALL(pred) (pred)
 #ifndef __restrict__
 #define __restrict__
 #endif

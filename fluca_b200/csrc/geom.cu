@@ -194,6 +194,7 @@ void geom_build(GeomHost &gh, Exec &ex, int dim, const int n[3], const double *c
   g.py     = g.ny + 1;
   g.plane  = (long)g.px * g.py;
   g.nalloc = g.plane * (g.nzl + 2);
+  if ((long)g.px * g.py * (long)(g.nzl + 2) >= 2147483647L) throw Error(FL_ERR_ARG, "slab too large for 32-bit element indices: use more z-slabs (GPUs)");
   g.rank = rank, g.nranks = nranks;
   if (dim == 2 && nranks != 1) throw Error(FL_ERR_ARG, "2-D meshes run on one rank (the slab partition is along z)");
   if (g.k0 < 0 || g.nzl < 1 || g.k0 + g.nzl > g.nzg) throw Error(FL_ERR_ARG, "slab outside the mesh");

@@ -61,7 +61,8 @@ struct Geom {
   int  rank, nranks;
   Tab  t[3];
 
-  FL_HD long idx(int i, int j, int kl) const { return (long)i + (long)px * ((long)j + (long)py * (long)(kl + 1)); }
+  // 32-bit element index (geom_build refuses slabs with nalloc >= 2^31)
+  FL_HD int idx(int i, int j, int kl) const { return i + px * (j + py * (kl + 1)); }
   // neighbour cell index helpers along x / y: periodic wrap, or clamp (the clamped value always
   // meets a zero weight)
   FL_HD int im(int i) const { return i > 0 ? i - 1 : (t[0].per ? nx - 1 : 0); }

@@ -41,19 +41,20 @@ struct BcDev {
 };
 
 // boundary-plane point index of cell (i, j, kl) for boundary b
-FL_HD long bc_pt(const Geom &g, int b, int i, int j, int kl)
+FL_HD int bc_pt(const Geom &g, int b, int i, int j, int kl)
 {
   const int d = b >> 1;
-  return d == 0 ? (long)j + (long)g.ny * kl : (d == 1 ? (long)i + (long)g.nx * kl : (long)i + (long)g.nx * j);
+  return d == 0 ? j + g.ny * kl : (d == 1 ? i + g.nx * kl : i + g.nx * j);
 }
 
 template <int DIM>
 struct Nbr {
-  long c;
-  long m[DIM], p[DIM];   // cell neighbours -/+ along each direction (wrapped or clamped)
-  long fu[DIM];          // index of the upper face along each direction
-  int  ig[DIM];          // global cell index along each direction
-  long m2[DIM], p2[DIM]; // cells at -2 / +2 (only valid where the one-sided stencils need them)
+  int c;
+  int m[DIM], p[DIM];   // cell neighbours -/+ along each direction (wrapped or clamped)
+  int fu[DIM];          // index of the upper face along each direction
+  int ig[DIM];          // global cell index along each direction
+  int m2[DIM], p2[DIM]; // cells at -2 / +2 (only valid where the one-sided stencils need them)
+  bool interior;        // no non-periodic wall touches this cell
 };
 
 template <int DIM>
@@ -70,24 +71,27 @@ FL_HD void nbr(const Geom &g, int i, int j, int kl, Nbr<DIM> &n)
   n.p[1]  = g.idx(i, g.jp(j), kl);
   n.fu[1] = g.idx(i, g.fyp(j), kl);
   n.ig[1] = j;
-  n.m2[1] = n.c - 2 * (long)g.px;
-  n.p2[1] = n.c + 2 * (long)g.px;
+  n.m2[1] = n.c - 2 * g.px;
+  n.p2[1] = n.c + 2 * g.px;
+  bool inter = (g.t[0].per || (i > 0 && i < g.nx - 1)) && (g.t[1].per || (j > 0 && j < g.ny - 1));
   if (DIM == 3) {
-    n.m[DIM - 1]  = n.c - g.plane; // ghost planes hold the halo (or zeros at a wall)
-    n.p[DIM - 1]  = n.c + g.plane;
-    n.fu[DIM - 1] = n.c + g.plane;
+    const int pl  = (int)g.plane;
+    n.m[DIM - 1]  = n.c - pl; // ghost planes hold the halo (or zeros at a wall)
+    n.p[DIM - 1]  = n.c + pl;
+    n.fu[DIM - 1] = n.c + pl;
     n.ig[DIM - 1] = g.k0 + kl;
-    n.m2[DIM - 1] = n.c - 2 * g.plane;
-    n.p2[DIM - 1] = n.c + 2 * g.plane;
+    n.m2[DIM - 1] = n.c - 2 * pl;
+    n.p2[DIM - 1] = n.c + 2 * pl;
+    inter = inter && (g.t[2].per || (n.ig[DIM - 1] > 0 && n.ig[DIM - 1] < g.t[2].n - 1));
   }
+  n.interior = inter;
 }
 
 // ------------------------------------------------------------------ momentum operator A
-template <int DIM>
-FL_HD void a_apply_cell(const Geom &g, const StepParams &sp, const BcDev &bc, const CV3 &x, const CV3 &v0, const CV3 &U0, int i, int j, int kl, double y[DIM])
+// BND = false compiles the wall handling out: used for warps whose 32 cells are all interior
+template <int DIM, bool BND>
+FL_HD void a_apply_core(const Geom &g, const StepParams &sp, const BcDev &bc, const CV3 &x, const CV3 &v0, const CV3 &U0, const Nbr<DIM> &nb, int i, int j, int kl, double y[DIM])
 {
-  Nbr<DIM> nb;
-  nbr<DIM>(g, i, j, kl, nb);
   double xc[DIM], vc[DIM], conv[DIM], lap[DIM];
 #pragma unroll
   for (int c = 0; c < DIM; ++c) {
@@ -100,10 +104,10 @@ FL_HD void a_apply_cell(const Geom &g, const StepParams &sp, const BcDev &bc, co
   for (int d = 0; d < DIM; ++d) {
     const Tab   &T  = g.t[d];
     const int    ig = nb.ig[d];
-    const bool   lo = (!T.per && ig == 0), hi = (!T.per && ig == T.n - 1);
-    const double hh = 0.5 * T.hinv[ig];
+    const bool   lo = BND && (!T.per && ig == 0), hi = BND && (!T.per && ig == T.n - 1);
+    const double hh = 0.5 * FL_LDG(T.hinv + ig);
     const double Ul = U0.c[d][nb.c], Uu = U0.c[d][nb.fu[d]];
-    const double al = T.itw[2 * ig], bl = T.itw[2 * ig + 1], au = T.itw[2 * ig + 2], bu = T.itw[2 * ig + 3];
+    const double al = FL_LDG(T.itw + 2 * ig), bl = FL_LDG(T.itw + 2 * ig + 1), au = FL_LDG(T.itw + 2 * ig + 2), bu = FL_LDG(T.itw + 2 * ig + 3);
     double       xm[DIM], xp[DIM], vm[DIM], vp[DIM];
 #pragma unroll
     for (int c = 0; c < DIM; ++c) {
@@ -113,6 +117,8 @@ FL_HD void a_apply_cell(const Geom &g, const StepParams &sp, const BcDev &bc, co
       vp[c] = v0.c[c][nb.p[d]];
     }
     const long pt = (lo || hi) ? bc_pt(g, 2 * d, i, j, kl) : 0;
+    // interior rows of the second derivative are the same for normal and tangential components
+    const double lw0 = FL_LDG(T.lapw + (size_t)ig * 3), lw1 = FL_LDG(T.lapw + (size_t)ig * 3 + 1), lw2 = FL_LDG(T.lapw + (size_t)ig * 3 + 2);
     // normal-component interpolation of x to the two faces (second convection term)
     const double Ild = lo ? T.cv2_lo[0] * xc[d] + T.cv2_lo[1] * xp[d] : al * xm[d] + bl * xc[d];
     const double Iud = hi ? T.cv2_hi[0] * xm[d] + T.cv2_hi[1] * xc[d] : au * xc[d] + bu * xp[d];
@@ -132,15 +138,27 @@ FL_HD void a_apply_cell(const Geom &g, const StepParams &sp, const BcDev &bc, co
       const double Ilc = lo ? T.cv1_lo[w][0] * xc[c] + T.cv1_lo[w][1] * xp[c] : al * xm[c] + bl * xc[c];
       const double Iuc = hi ? T.cv1_hi[w][0] * xm[c] + T.cv1_hi[w][1] * xc[c] : au * xc[c] + bu * xp[c];
       conv[c] += hh * (Uu * Iuc + vbu * Iud - Ul * Ilc - vbl * Ild);
-      const double *lw = T.lapw + ((size_t)w * T.n + ig) * 3;
-      double        l  = lw[0] * xm[c] + lw[1] * xc[c] + lw[2] * xp[c];
-      if (lo) l += T.lap_lo2[w] * x.c[c][nb.p2[d]];
-      if (hi) l += T.lap_hi2[w] * x.c[c][nb.m2[d]];
+      double l;
+      if (lo || hi) {
+        const double *lw = T.lapw + ((size_t)w * T.n + ig) * 3;
+        l                = lw[0] * xm[c] + lw[1] * xc[c] + lw[2] * xp[c];
+        if (lo) l += T.lap_lo2[w] * x.c[c][nb.p2[d]];
+        if (hi) l += T.lap_hi2[w] * x.c[c][nb.m2[d]];
+      } else l = lw0 * xm[c] + lw1 * xc[c] + lw2 * xp[c];
       lap[c] += l;
     }
   }
 #pragma unroll
   for (int c = 0; c < DIM; ++c) y[c] = xc[c] + sp.dt * conv[c] - sp.nu2 * lap[c];
+}
+
+template <int DIM>
+FL_HD void a_apply_cell(const Geom &g, const StepParams &sp, const BcDev &bc, const CV3 &x, const CV3 &v0, const CV3 &U0, int i, int j, int kl, double y[DIM])
+{
+  Nbr<DIM> nb;
+  nbr<DIM>(g, i, j, kl, nb);
+  if (FL_WARP_ALL(nb.interior)) a_apply_core<DIM, false>(g, sp, bc, x, v0, U0, nb, i, j, kl, y);
+  else a_apply_core<DIM, true>(g, sp, bc, x, v0, U0, nb, i, j, kl, y);
 }
 
 // cell-centred pressure gradient, unscaled: (G0 q)_c at one cell (cnlinearcart3d.c:4-217)

@@ -63,10 +63,19 @@ def make_comm_factory(rank, nranks):
 def main():
     case_name, mode, out_path = sys.argv[1], sys.argv[2], sys.argv[3]
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    backend = os.environ.get("FLUCA_WORKER_BACKEND", "gloo")
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    lib = parity.hostemu_library() if rank == 0 else None
-    dist.barrier()
-    lib = lib or fb._lib.load(parity.HOSTEMU)
+    if backend == "nccl":
+        # the real thing: CUDA product library, one GPU per rank, the solver's own NCCL communicator
+        torch.cuda.set_device(rank)
+        lib = fb._lib.load()
+        box = [fb.Comm.unique_id(lib) if rank == 0 else None]
+        dist.broadcast_object_list(box, 0)
+        uid = box[0]
+    else:
+        lib = parity.hostemu_library() if rank == 0 else None
+        dist.barrier()
+        lib = lib or fb._lib.load(parity.HOSTEMU)
     case = {
         "channel3d": lambda: cases.channel3d(n=(8, 6, 8), pout=0.2, dt=0.05),
         "cavity3d": lambda: cases.cavity3d_full(n=(8, 8, 8)),
@@ -74,7 +83,10 @@ def main():
         "uneven": lambda: cases.cavity3d_full(n=(8, 6, 7)),
         "three": lambda: cases.cavity3d_full(n=(8, 6, 9)),
     }[case_name]()
-    comm = dict(rank=rank, nranks=world, make_comm=make_comm_factory(rank, world))
+    if backend == "nccl":
+        comm = dict(rank=rank, nranks=world, make_comm=lambda L: fb.Comm.nccl(L, uid, rank, world))
+    else:
+        comm = dict(rank=rank, nranks=world, make_comm=make_comm_factory(rank, world))
     ns = parity.make_ns(case, lib, mode, comm=comm, **parity.TIGHT)
     s = fb.NSB200GetSolver(ns)
     v, U, p = case.initial_state(seed=31)

@@ -22,12 +22,12 @@ def _free_port():
     return p
 
 
-def run_world(case_name, mode, world, tmp_path):
+def run_world(case_name, mode, world, tmp_path, backend="gloo"):
     out = str(tmp_path / f"{case_name}_{mode}_{world}.npz")
     port = _free_port()
     procs = []
     for r in range(world):
-        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1", FLUCA_WORKER_BACKEND=backend)
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "multirank_worker.py"), case_name, mode, out], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     logs = []
     for p in procs:
@@ -66,5 +66,26 @@ def test_slab_partition_matches_oracle(case_name, mode, world, tmp_path):
     assert parity.rel(got["v"], ref["v"]) < 1e-10
     assert parity.relU([got["U0"], got["U1"], got["U2"]], ref["U"]) < 1e-10
     assert parity.rel(got["p"], ref["p"]) < 1e-9 and parity.rel(got["phalf"], ref["phalf"]) < 1e-9
+    if mode == "coupled":
+        assert [int(a) for a in got["its"][:, 0]] == [i.outer_its for i in infos]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case_name,mode", [("cavity3d", "coupled"), ("channel3d", "coupled"), ("periodic_z", "fractional")])
+def test_nccl_two_gpus_match_oracle(case_name, mode, tmp_path):
+    """The same comparison with the CUDA library on 2 GPUs: NCCL halo exchange + allreduce."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    got = run_world(case_name, mode, 2, tmp_path, backend="nccl")
+    case = CASEMAP[case_name]()
+    orc = cases.make_oracle(case)
+    orc.set_state(*case.initial_state(seed=31))
+    infos = [orc.step(O.default_options(mode=0 if mode == "coupled" else 1, **parity.ORC_TIGHT)) for _ in range(2)]
+    ref = orc.get_state()
+    assert parity.rel(got["v"], ref["v"]) < 1e-10
+    assert parity.relU([got["U0"], got["U1"], got["U2"]], ref["U"]) < 1e-10
+    assert parity.rel(got["p"], ref["p"]) < 1e-9
     if mode == "coupled":
         assert [int(a) for a in got["its"][:, 0]] == [i.outer_its for i in infos]
