@@ -74,6 +74,7 @@ struct Exec {
   ExecStats stats;
   // optional per-class event timing
   bool      ktime_on = false;
+  bool      kt_grouped = false; // a KGroup is open: the launches inside share its one event pair
   int       kt_current = 7; // class charged by the launchers (KScope sets it); default KT_OUTER
 #ifndef FLUCA_HOSTEMU
   std::vector<cudaEvent_t> kt_ev;   // pairs
@@ -86,6 +87,7 @@ struct Exec {
   // reduction scratch
   double      *d_partials = nullptr; // [max_blocks * MAXR]
   double      *d_result   = nullptr; // [MAXR]
+  double      *d_carry    = nullptr; // [2][MAXR] partial sums handed from one launch of a reduction to the next
   unsigned    *d_ticket   = nullptr;
   double      *h_result   = nullptr; // pinned [MAXR]
   long         max_blocks = 0;
@@ -193,11 +195,13 @@ inline void Exec::init()
   max_blocks = 8192;
   d_partials = (double *)dev_alloc(sizeof(double) * max_blocks * MAXR);
   d_result   = (double *)dev_alloc(sizeof(double) * MAXR);
+  d_carry    = (double *)dev_alloc(sizeof(double) * MAXR * 2);
   d_ticket   = (unsigned *)dev_alloc(sizeof(unsigned));
   FL_CUDA(cudaMallocHost((void **)&h_result, sizeof(double) * MAXR));
 #else
   h_result = (double *)calloc(MAXR, sizeof(double));
   d_result = (double *)calloc(MAXR, sizeof(double));
+  d_carry  = (double *)calloc(2 * MAXR, sizeof(double));
 #endif
 }
 inline void Exec::destroy()
@@ -206,6 +210,7 @@ inline void Exec::destroy()
   if (stream) cudaStreamSynchronize(stream);
   dev_free(d_partials);
   dev_free(d_result);
+  dev_free(d_carry);
   dev_free(d_ticket);
   if (h_result) cudaFreeHost(h_result);
   for (cudaEvent_t e : kt_ev) cudaEventDestroy(e);
@@ -214,8 +219,9 @@ inline void Exec::destroy()
 #else
   free(h_result);
   free(d_result);
+  free(d_carry);
 #endif
-  d_partials = d_result = h_result = nullptr;
+  d_partials = d_result = h_result = d_carry = nullptr;
   d_ticket   = nullptr;
   stream     = nullptr;
 }
@@ -234,7 +240,7 @@ struct KTimer {
   KTimer(Exec &e, int cls) : ex(e)
   {
 #ifndef FLUCA_HOSTEMU
-    if (!ex.ktime_on) return;
+    if (!ex.ktime_on || ex.kt_grouped) return;
     if (ex.kt_used + 2 > ex.kt_ev.size()) {
       if (ex.kt_ev.size() >= 200000) return;
       size_t old = ex.kt_ev.size();
@@ -256,6 +262,15 @@ struct KTimer {
     if (slot >= 0) cudaEventRecord(ex.kt_ev[slot + 1], ex.stream);
 #endif
   }
+};
+
+// one event pair around a short sequence of launches that together form one operator application
+struct KGroup {
+  KTimer t;
+  Exec  &ex;
+  bool   prev;
+  KGroup(Exec &e, int cls) : t(e, cls), ex(e), prev(e.kt_grouped) { ex.kt_grouped = true; }
+  ~KGroup() { ex.kt_grouped = prev; } // runs before ~KTimer records the closing event
 };
 
 // selects the class that the launchers below charge their event pairs to
@@ -318,8 +333,9 @@ __global__ void __launch_bounds__(256) k_range(long n, F f)
 }
 
 template <int NR>
-__device__ __forceinline__ void block_reduce_and_finish(double (&acc)[NR], double *partials, double *result, unsigned *ticket, unsigned nblocks, unsigned bid)
+__device__ __forceinline__ void block_reduce_and_finish(double (&acc)[NR], const double *carry, double *partials, double *result, unsigned *ticket, unsigned nblocks, unsigned bid)
 {
+  // carry (optional): NR sums of an earlier launch of the same reduction (boundary planes), added last
   __shared__ double sm[NR][8];
   __shared__ bool   last;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -361,7 +377,7 @@ __device__ __forceinline__ void block_reduce_and_finish(double (&acc)[NR], doubl
       for (int r = 0; r < NR; ++r) {
         double v = 0.;
         for (int w = 0; w < 8; ++w) v += sm[r][w];
-        result[r] = v;
+        result[r] = carry ? v + carry[r] : v;
       }
       *ticket = 0u;
     }
@@ -369,7 +385,7 @@ __device__ __forceinline__ void block_reduce_and_finish(double (&acc)[NR], doubl
 }
 
 template <int NR, class F>
-__global__ void __launch_bounds__(BX *BY, 2) k_box_reduce(Box b, F f, double *partials, double *result, unsigned *ticket)
+__global__ void __launch_bounds__(BX *BY, 2) k_box_reduce(Box b, F f, const double *carry, double *partials, double *result, unsigned *ticket)
 {
   const int i = blockIdx.x * BX + threadIdx.x;
   const int j = blockIdx.y * BY + threadIdx.y;
@@ -383,17 +399,17 @@ __global__ void __launch_bounds__(BX *BY, 2) k_box_reduce(Box b, F f, double *pa
   }
   const unsigned nblocks = gridDim.x * gridDim.y * gridDim.z;
   const unsigned bid     = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-  block_reduce_and_finish<NR>(acc, partials, result, ticket, nblocks, bid);
+  block_reduce_and_finish<NR>(acc, carry, partials, result, ticket, nblocks, bid);
 }
 
 template <int NR, class F>
-__global__ void __launch_bounds__(256) k_range_reduce(long n, F f, double *partials, double *result, unsigned *ticket)
+__global__ void __launch_bounds__(256) k_range_reduce(long n, F f, const double *carry, double *partials, double *result, unsigned *ticket)
 {
   double acc[NR];
 #pragma unroll
   for (int r = 0; r < NR; ++r) acc[r] = 0.;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) f(i, acc);
-  block_reduce_and_finish<NR>(acc, partials, result, ticket, gridDim.x, blockIdx.x);
+  block_reduce_and_finish<NR>(acc, carry, partials, result, ticket, gridDim.x, blockIdx.x);
 }
 
 inline dim3 box_grid(const Exec &ex, Box b, long cap_blocks)
@@ -448,20 +464,24 @@ inline void for_range(Exec &ex, long n, F f)
 }
 
 // f(i, j, k, acc[NR]) accumulates into acc; the NR sums land in ex.d_result (device)
+// carry / result (device pointers, CUDA build): chain the sums of several launches of one reduction;
+// the default writes ex.d_result
 template <int NR, class F>
-inline void for_box_reduce(Exec &ex, Box b, F f)
+inline void for_box_reduce(Exec &ex, Box b, F f, const double *carry = nullptr, double *result = nullptr)
 {
   static_assert(NR <= Exec::MAXR, "too many simultaneous reductions");
   ex.stats.launches++;
+  if (!result) result = ex.d_result;
 #ifndef FLUCA_HOSTEMU
   if (b.nx <= 0 || b.ny <= 0 || b.nz <= 0) {
-    dev_zero(ex, ex.d_result, sizeof(double) * NR);
+    if (carry) copy_d2d(ex, result, carry, sizeof(double) * NR);
+    else dev_zero(ex, result, sizeof(double) * NR);
     return;
   }
   dim3 g = box_grid(ex, b, ex.max_blocks);
   if ((long)g.x * g.y * g.z > ex.max_blocks) throw Error(FL_ERR_INTERNAL, "reduction grid exceeds partial buffer");
   KTimer kt(ex, ex.kt_current);
-  k_box_reduce<NR><<<g, dim3(BX, BY, 1), 0, ex.stream>>>(b, f, ex.d_partials, ex.d_result, ex.d_ticket);
+  k_box_reduce<NR><<<g, dim3(BX, BY, 1), 0, ex.stream>>>(b, f, carry, ex.d_partials, result, ex.d_ticket);
   FL_CUDA(cudaGetLastError());
 #else
   double acc[NR];
@@ -469,7 +489,7 @@ inline void for_box_reduce(Exec &ex, Box b, F f)
   for (int k = 0; k < b.nz; ++k)
     for (int j = 0; j < b.ny; ++j)
       for (int i = 0; i < b.nx; ++i) f(i, j, k, acc);
-  for (int r = 0; r < NR; ++r) ex.d_result[r] = acc[r];
+  for (int r = 0; r < NR; ++r) result[r] = acc[r] + (carry ? carry[r] : 0.);
 #endif
 }
 
@@ -487,7 +507,7 @@ inline void for_range_reduce(Exec &ex, long n, F f)
   if (blocks > cap) blocks = cap;
   if (blocks > ex.max_blocks) blocks = ex.max_blocks;
   KTimer kt(ex, ex.kt_current);
-  k_range_reduce<NR><<<(unsigned)blocks, 256, 0, ex.stream>>>(n, f, ex.d_partials, ex.d_result, ex.d_ticket);
+  k_range_reduce<NR><<<(unsigned)blocks, 256, 0, ex.stream>>>(n, f, nullptr, ex.d_partials, ex.d_result, ex.d_ticket);
   FL_CUDA(cudaGetLastError());
 #else
   double acc[NR];

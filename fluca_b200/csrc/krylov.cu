@@ -21,34 +21,16 @@ static Box cell_box(const Solver &s)
   return b;
 }
 
-// y = A x fused with acc[0] += <a, y>, acc[1] += <y, y>
-template <int DIM>
-struct AApplyDots {
-  Geom       g;
-  StepParams sp;
-  BcDev      bc;
-  CV3        x, v0, U0, a;
-  V3         y;
-  FL_HD void operator()(int i, int j, int kl, double acc[2]) const
-  {
-    double r[DIM];
-    a_apply_cell<DIM>(g, sp, bc, x, v0, U0, i, j, kl, r);
-    const long c = g.idx(i, j, kl);
-    double     d0 = 0., d1 = 0.;
-#pragma unroll
-    for (int q = 0; q < DIM; ++q) {
-      y.c[q][c] = r[q];
-      d0 += a.c[q][c] * r[q];
-      d1 += r[q] * r[q];
-    }
-    acc[0] += d0;
-    acc[1] += d1;
-  }
-};
-
 static void a_apply_dots(Solver &s, const V3 &x, const V3 &y, const V3 &a, double out[2])
 {
   halo_cells(s, x);
+#ifndef FLUCA_HOSTEMU
+  if (tma_usable(s)) {
+    a_apply_dots_tma(s, x, y, a, true);
+    reduce_finish(s, 2, out);
+    return;
+  }
+#endif
   {
     KScope kt(s.ex, KT_MOMENTUM_APPLY);
     if (s.dim == 2) {

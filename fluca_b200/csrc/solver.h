@@ -159,6 +159,12 @@ void coupled_apply(Solver &s, const V3 &xv, const V3 &xU, double *xp, const V3 &
 void schur_apply_reference_scaling(Solver &s, double *pin, double *out);
 int  do_step(Solver &s, double t, int step_index);
 
+#ifndef FLUCA_HOSTEMU
+// TMA-staged versions of the hot 3-D operators (tiles.cu); tma_usable() says whether the mesh qualifies
+bool tma_usable(const Solver &s);
+void a_apply_dots_tma(Solver &s, const V3 &x, const V3 &y, const V3 &a, bool with_dots);
+#endif
+
 // Krylov / multigrid (krylov.cu, mg.cu)
 int  momentum_solve(Solver &s, const V3 &b, const V3 &x);
 int  poisson_solve(Solver &s, double *b, double *x);

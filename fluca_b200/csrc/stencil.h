@@ -161,6 +161,31 @@ FL_HD void a_apply_cell(const Geom &g, const StepParams &sp, const BcDev &bc, co
   else a_apply_core<DIM, true>(g, sp, bc, x, v0, U0, nb, i, j, kl, y);
 }
 
+// y = A x fused with acc[0] += <a, y>, acc[1] += <y, y>
+template <int DIM>
+struct AApplyDots {
+  Geom       g;
+  StepParams sp;
+  BcDev      bc;
+  CV3        x, v0, U0, a;
+  V3         y;
+  FL_HD void operator()(int i, int j, int kl, double acc[2]) const
+  {
+    double r[DIM];
+    a_apply_cell<DIM>(g, sp, bc, x, v0, U0, i, j, kl, r);
+    const long c = g.idx(i, j, kl);
+    double     d0 = 0., d1 = 0.;
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) {
+      y.c[q][c] = r[q];
+      d0 += a.c[q][c] * r[q];
+      d1 += r[q] * r[q];
+    }
+    acc[0] += d0;
+    acc[1] += d1;
+  }
+};
+
 // cell-centred pressure gradient, unscaled: (G0 q)_c at one cell (cnlinearcart3d.c:4-217)
 template <int DIM>
 FL_HD void grad_cell(const Geom &g, const double *__restrict__ q, const Nbr<DIM> &nb, double gq[DIM])

@@ -324,6 +324,12 @@ struct AApplyPlain {
 void a_apply(Solver &s, const V3 &x, const V3 &y)
 {
   halo_cells(s, x);
+#ifndef FLUCA_HOSTEMU
+  if (tma_usable(s)) {
+    a_apply_dots_tma(s, x, y, x, false);
+    return;
+  }
+#endif
   if (s.dim == 2) {
     AApplyPlain<2> f;
     f.g = s.gh.g, f.sp = s.sp, f.bc = s.bc, f.x = CV3(x), f.v0 = CV3(s.v0), f.U0 = CV3(s.U0), f.y = y;

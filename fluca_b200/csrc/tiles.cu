@@ -1,0 +1,228 @@
+// tiles.cu -- the TMA-staged versions of the hot 3-D stencil operators (see tma.h for the pipeline).
+//
+//   momentum operator  y = A x (+ two fused dot products)   reference: MatMult with the assembled A of
+//                      NSFormJacobian(UPDATE), cnlinearcart3d.c:2930-2941, inside KSPSolve(kspA) abfpc.c:72
+//   Poisson operator   q = P p (+ <a, q>)                   reference: MatMult with S inside KSPSolve(kspS) abfpc.c:77
+//
+// The arithmetic is that of a_apply_core / poisson_apply_cell in stencil.h (same tables, same
+// operation order per direction); only the operand source differs: shared-memory tiles filled by
+// TMA instead of global loads.  Planes that touch a physical z wall need the one-sided 4-point
+// rows (cells k +- 2) and are computed by the direct-load kernel on those two planes; their
+// partial sums are chained into the TMA launch through the `carry` argument of the reduction.
+#include "solver.h"
+#ifndef FLUCA_HOSTEMU
+#include "tma.h"
+#include <map>
+#include <mutex>
+#include <tuple>
+
+namespace fluca {
+
+// ------------------------------------------------------------------ tensor maps
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn()
+{
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void                           *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    // resolved through the runtime: the library does not link libcuda
+    FL_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) throw Error(FL_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+struct MapKey {
+  const double *p;
+  int           px, py, nz;
+  bool operator<(const MapKey &o) const { return std::tie(p, px, py, nz) < std::tie(o.p, o.px, o.py, o.nz); }
+};
+std::map<MapKey, CUtensorMap> g_maps;
+std::mutex                    g_maps_mutex;
+} // namespace
+
+const CUtensorMap &tensor_map_for(const double *field, int px, int py, int nplanes)
+{
+  std::lock_guard<std::mutex> lock(g_maps_mutex);
+  MapKey                      key = {field, px, py, nplanes};
+  auto                        it  = g_maps.find(key);
+  if (it != g_maps.end()) return it->second;
+  alignas(64) CUtensorMap m;
+  const cuuint64_t        dims[3]    = {(cuuint64_t)px, (cuuint64_t)py, (cuuint64_t)nplanes};
+  const cuuint64_t        strides[2] = {(cuuint64_t)px * sizeof(double), (cuuint64_t)px * py * sizeof(double)};
+  const cuuint32_t        box[3]     = {(cuuint32_t)TLX, (cuuint32_t)TLY, 1u};
+  const cuuint32_t        estr[3]    = {1u, 1u, 1u};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)field, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(FL_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  return g_maps.emplace(key, m).first->second;
+}
+
+void tensor_map_forget(const double *field)
+{
+  std::lock_guard<std::mutex> lock(g_maps_mutex);
+  for (auto it = g_maps.begin(); it != g_maps.end();) {
+    if (it->first.p == field) it = g_maps.erase(it);
+    else ++it;
+  }
+}
+
+bool tma_usable(const Solver &s)
+{
+  static const bool off = getenv("FLUCA_B200_NO_TMA") != nullptr;
+  const Geom       &g   = s.gh.g;
+  return !off && s.dim == 3 && !g.t[0].per && !g.t[1].per && g.nx >= TMX && g.ny >= TMY;
+}
+
+// ------------------------------------------------------------------ momentum operator from shared-memory tiles
+// field order inside a ring slot: x0 x1 x2 | v0_0 v0_1 v0_2 | U0_0 U0_1 U0_2
+template <bool BND>
+__device__ __forceinline__ void a_apply_tile(const Geom &g, const StepParams &sp, const BcDev &bc, const TileView &tv, int i, int j, int kl, double y[3])
+{
+  constexpr int FS = TILE_STRIDE;
+  const int     lc = tv.lc;
+  double        xc[3], vc[3], conv[3], lap[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    xc[c]   = tv.p0[c * FS + lc];
+    vc[c]   = tv.p0[(3 + c) * FS + lc];
+    conv[c] = 0.;
+    lap[c]  = 0.;
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const Tab    &T  = g.t[d];
+    const int     ig = d == 0 ? i : (d == 1 ? j : g.k0 + kl);
+    // planes that touch a z wall never reach this function (a_apply_dots sends them to the direct-load kernel)
+    const bool    lo = BND && d < 2 && ig == 0, hi = BND && d < 2 && ig == T.n - 1;
+    const double *nm = d == 2 ? tv.pm : tv.p0, *np = d == 2 ? tv.pp : tv.p0;
+    const int     st = d == 0 ? 1 : (d == 1 ? TLX : 0);
+    const int     om = lc - st, op = lc + st;
+    const double  hh = 0.5 * FL_LDG(T.hinv + ig);
+    const double  Ul = tv.p0[(6 + d) * FS + lc], Uu = np[(6 + d) * FS + op];
+    const double  al = FL_LDG(T.itw + 2 * ig), bl = FL_LDG(T.itw + 2 * ig + 1), au = FL_LDG(T.itw + 2 * ig + 2), bu = FL_LDG(T.itw + 2 * ig + 3);
+    const double  lw0 = FL_LDG(T.lapw + (size_t)ig * 3), lw1 = FL_LDG(T.lapw + (size_t)ig * 3 + 1), lw2 = FL_LDG(T.lapw + (size_t)ig * 3 + 2);
+    double        xm[3], xp[3], vm[3], vp[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      xm[c] = nm[c * FS + om];
+      xp[c] = np[c * FS + op];
+      vm[c] = nm[(3 + c) * FS + om];
+      vp[c] = np[(3 + c) * FS + op];
+    }
+    const long   pt  = (lo || hi) ? bc_pt(g, 2 * d, i, j, kl) : 0;
+    const double Ild = lo ? T.cv2_lo[0] * xc[d] + T.cv2_lo[1] * xp[d] : al * xm[d] + bl * xc[d];
+    const double Iud = hi ? T.cv2_hi[0] * xm[d] + T.cv2_hi[1] * xc[d] : au * xc[d] + bu * xp[d];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int w = (c == d) ? 1 : 0;
+      double    vbl, vbu;
+      if (lo) {
+        vbl = T.it_lo[w][0] * vc[c] + T.it_lo[w][1] * vp[c];
+        if (T.it_lo_bc != 0.) vbl += bc.vel[2 * d][0][c * bc.npts[2 * d] + pt];
+      } else vbl = al * vm[c] + bl * vc[c];
+      if (hi) {
+        vbu = T.it_hi[w][0] * vm[c] + T.it_hi[w][1] * vc[c];
+        if (T.it_hi_bc != 0.) vbu += bc.vel[2 * d + 1][0][c * bc.npts[2 * d + 1] + pt];
+      } else vbu = au * vc[c] + bu * vp[c];
+      const double Ilc = lo ? T.cv1_lo[w][0] * xc[c] + T.cv1_lo[w][1] * xp[c] : al * xm[c] + bl * xc[c];
+      const double Iuc = hi ? T.cv1_hi[w][0] * xm[c] + T.cv1_hi[w][1] * xc[c] : au * xc[c] + bu * xp[c];
+      conv[c] += hh * (Uu * Iuc + vbu * Iud - Ul * Ilc - vbl * Ild);
+      double l;
+      if (lo || hi) {
+        const double *lw = T.lapw + ((size_t)w * T.n + ig) * 3;
+        l                = lw[0] * xm[c] + lw[1] * xc[c] + lw[2] * xp[c];
+        if (lo) l += T.lap_lo2[w] * tv.p0[c * FS + lc + 2 * st];
+        if (hi) l += T.lap_hi2[w] * tv.p0[c * FS + lc - 2 * st];
+      } else l = lw0 * xm[c] + lw1 * xc[c] + lw2 * xp[c];
+      lap[c] += l;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) y[c] = xc[c] + sp.dt * conv[c] - sp.nu2 * lap[c];
+}
+
+template <int NRED>
+struct AApplyTile {
+  static const int NIN = 9, NR = NRED;
+  Geom             g;
+  StepParams       sp;
+  BcDev            bc;
+  const double    *a[3]; // dot partner (NR == 2); nullptr: the partner is x itself
+  double          *y[3];
+  __device__ void cell(const TileView &tv, int i, int j, int kl, double *acc) const
+  {
+    double     r[3];
+    const bool inter = i > 0 && i < g.nx - 1 && j > 0 && j < g.ny - 1;
+    if (__all_sync(__activemask(), inter)) a_apply_tile<false>(g, sp, bc, tv, i, j, kl, r);
+    else a_apply_tile<true>(g, sp, bc, tv, i, j, kl, r);
+    const int c = g.idx(i, j, kl);
+    double    d0 = 0., d1 = 0.;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      y[q][c] = r[q];
+      if (NRED > 0) {
+        const double av = a[q] ? a[q][c] : tv.p0[q * TILE_STRIDE + tv.lc];
+        d0 += av * r[q];
+        d1 += r[q] * r[q];
+      }
+    }
+    if (NRED > 0) acc[0] += d0, acc[1] += d1;
+  }
+};
+
+// shifts the plane index of a box functor (the z-wall planes are launched as 1-plane boxes)
+template <class F>
+struct PlaneAt {
+  F   f;
+  int kl;
+  FL_HD void operator()(int i, int j, int, double *acc) const { f(i, j, kl, acc); }
+};
+
+// y = A x ; out[0] = <a, y>, out[1] = <y, y> are left in ex.d_result (reduce_finish reads them)
+void a_apply_dots_tma(Solver &s, const V3 &x, const V3 &y, const V3 &a, bool with_dots)
+{
+  const Geom &g  = s.gh.g;
+  const bool  wl = g.t[2].wall_lo && !g.t[2].per, wh = g.t[2].wall_hi && !g.t[2].per;
+  KGroup      grp(s.ex, KT_MOMENTUM_APPLY);
+  // 1. the (up to two) planes at physical z walls: direct-load kernel with the one-sided rows
+  const double *carry = nullptr;
+  int           ncar  = 0;
+  AApplyDots<3> f;
+  f.g = g, f.sp = s.sp, f.bc = s.bc, f.x = CV3(x), f.v0 = CV3(s.v0), f.U0 = CV3(s.U0), f.a = CV3(with_dots ? a : x), f.y = y;
+  const Box plane_box = {g.nx, g.ny, 1};
+  const int kbeg = wl ? 1 : 0;
+  int       kend = wh ? g.nzl - 1 : g.nzl;
+  if (kend < kbeg) kend = kbeg;
+  if (wl) {
+    PlaneAt<AApplyDots<3>> pf = {f, 0};
+    double                *res = s.ex.d_carry + Exec::MAXR * ncar;
+    for_box_reduce<2>(s.ex, plane_box, pf, carry, res);
+    carry = res, ++ncar;
+  }
+  if (wh && g.nzl - 1 >= kbeg) {
+    PlaneAt<AApplyDots<3>> pf = {f, g.nzl - 1};
+    double                *res = s.ex.d_carry + Exec::MAXR * ncar;
+    for_box_reduce<2>(s.ex, plane_box, pf, carry, res);
+    carry = res, ++ncar;
+  }
+  // 2. everything else through the TMA pipeline
+  const double *fields[9] = {x.c[0], x.c[1], x.c[2], s.v0.c[0], s.v0.c[1], s.v0.c[2], s.U0.c[0], s.U0.c[1], s.U0.c[2]};
+  if (with_dots) {
+    AApplyTile<2> op;
+    op.g = g, op.sp = s.sp, op.bc = s.bc;
+    for (int c = 0; c < 3; ++c) op.a[c] = (a.c[c] == x.c[c]) ? nullptr : a.c[c], op.y[c] = y.c[c];
+    tma_launch(s.ex, op, fields, g.px, g.py, g.nzl + 2, g.nx, g.ny, kbeg, kend, carry);
+  } else {
+    AApplyTile<0> op;
+    op.g = g, op.sp = s.sp, op.bc = s.bc;
+    for (int c = 0; c < 3; ++c) op.a[c] = nullptr, op.y[c] = y.c[c];
+    tma_launch(s.ex, op, fields, g.px, g.py, g.nzl + 2, g.nx, g.ny, kbeg, kend, nullptr);
+  }
+}
+
+} // namespace fluca
+#endif // !FLUCA_HOSTEMU

@@ -35,6 +35,12 @@ CASES = [
     ("channel3d_outlet", lambda: cases.channel3d(n=(16, 12, 12), pout=0.2, dt=0.05), 11, 2),
     ("channel3d_periodic_z", lambda: cases.channel3d(n=(16, 12, 12), periodic_z=True, dt=0.05), 13, 2),
     ("ragged_sizes", lambda: cases.cavity3d_full(n=(13, 9, 7)), 17, 2),
+    # large enough in x / y for the TMA-staged tile kernels (>= 32 x 8 cells per plane); ragged extents put the
+    # shifted last tile, the in-tile one-sided wall rows and the direct-load z-wall planes all on the path
+    ("tma_cavity_ragged_nonuniform", lambda: _st(cases.cavity3d_full(n=(37, 13, 9))), 19, 2),
+    ("tma_cavity_sym", lambda: cases.cavity3d(n=(48, 24, 10)), 23, 1),
+    ("tma_channel_outlet", lambda: cases.channel3d(n=(40, 16, 10), pout=0.2, dt=0.05), 29, 1),
+    ("tma_channel_periodic_z", lambda: cases.channel3d(n=(33, 9, 8), periodic_z=True, dt=0.05), 31, 1),
 ]
 
 
@@ -50,8 +56,9 @@ def test_step_matches_oracle(lib, name, mk, seed, nsteps, mode):
                 assert a == pytest.approx(b, rel=1e-6, abs=1e-12 * o["hist_orc"][0])
 
 
-def test_operator_level_parity(lib):
-    case = cases.channel3d(n=(16, 12, 12), pout=0.2, dt=0.05)
+@pytest.mark.parametrize("n", [(16, 12, 12), (70, 19, 6)], ids=["direct", "tma"])
+def test_operator_level_parity(lib, n):
+    case = cases.channel3d(n=n, pout=0.2, dt=0.05)
     orc = cases.make_oracle(case)
     state = case.initial_state(seed=21)
     orc.set_state(*state)
