@@ -153,7 +153,19 @@ struct AApplyTile {
   BcDev            bc;
   const double    *a[3]; // dot partner (NR == 2); nullptr: the partner is x itself
   double          *y[3];
-  __device__ void cell(const TileView &tv, int i, int j, int kl, double *acc) const
+  struct Regs {
+    double a[3];
+  };
+  __device__ void prefetch(Regs &rg, int i, int j, int kl) const
+  {
+    if (NRED > 0) {
+      const int c = g.idx(i, j, kl);
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        if (a[q]) rg.a[q] = a[q][c];
+    }
+  }
+  __device__ void cell(const TileView &tv, const Regs &rg, int i, int j, int kl, double *acc) const
   {
     double     r[3];
     const bool inter = i > 0 && i < g.nx - 1 && j > 0 && j < g.ny - 1;
@@ -165,7 +177,7 @@ struct AApplyTile {
     for (int q = 0; q < 3; ++q) {
       y[q][c] = r[q];
       if (NRED > 0) {
-        const double av = a[q] ? a[q][c] : tv.p0[q * TILE_STRIDE + tv.lc];
+        const double av = a[q] ? rg.a[q] : tv.p0[q * TILE_STRIDE + tv.lc];
         d0 += av * r[q];
         d1 += r[q] * r[q];
       }

@@ -100,7 +100,9 @@ struct TileView {
 
 // Op interface:
 //   static const int NIN, NR;
-//   __device__ void cell(const TileView &tv, int i, int j, int kl, double *acc) const;   (acc has NR entries)
+//   struct Regs;                                                         per-thread operands that bypass the tiles
+//   __device__ void prefetch(Regs &r, int i, int j, int kl) const;       global loads for plane kl, issued one plane ahead
+//   __device__ void cell(const TileView &tv, const Regs &r, int i, int j, int kl, double *acc) const;   (acc: NR entries)
 template <class Op>
 __global__ void __launch_bounds__(TMX *TMY, 2) k_tma_march(const __grid_constant__ TmaIn<Op::NIN> in, const Op op, const TmaGrid tg, const double *carry, double *partials, double *result, unsigned *ticket)
 {
@@ -141,8 +143,14 @@ __global__ void __launch_bounds__(TMX *TMY, 2) k_tma_march(const __grid_constant
   TileView tv;
   tv.lc     = (ty + 1) * TLX + tx + THX;
   int ready = -1;
+  typename Op::Regs cur, nxt;
+  if (owned && k0 < k1) op.prefetch(nxt, i, j, k0);
   for (int k = k0; k < k1; ++k) {
     const int rc = k - k0 + 1;
+    cur = nxt;
+    // operands read straight from global memory (one value per cell, no reuse) are requested a whole plane
+    // ahead: their DRAM latency overlaps the arithmetic of the current plane
+    if (owned && k + 1 < k1) op.prefetch(nxt, i, j, k + 1);
     while (ready < rc + 1) {
       ++ready;
       mbar_wait(&full[ready % TMS], (unsigned)(ready / TMS) & 1u);
@@ -150,7 +158,7 @@ __global__ void __launch_bounds__(TMX *TMY, 2) k_tma_march(const __grid_constant
     tv.pm = ring + (size_t)((rc - 1) % TMS) * Op::NIN * TILE_STRIDE;
     tv.p0 = ring + (size_t)(rc % TMS) * Op::NIN * TILE_STRIDE;
     tv.pp = ring + (size_t)((rc + 1) % TMS) * Op::NIN * TILE_STRIDE;
-    if (owned) op.cell(tv, i, j, k, acc);
+    if (owned) op.cell(tv, cur, i, j, k, acc);
     __syncthreads(); // every thread is done with plane k-1: its slot may be refilled
     if (tid == 0) {
       const int r = rc - 1 + TMS;
