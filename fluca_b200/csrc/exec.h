@@ -92,7 +92,7 @@ struct Exec {
   double      *h_result   = nullptr; // pinned [MAXR]
   long         max_blocks = 0;
   int          sm_count   = 148;
-  static const int MAXR = 8;
+  static const int MAXR = 16;
 
   void init();
   void destroy();

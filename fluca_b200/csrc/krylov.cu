@@ -163,6 +163,12 @@ struct PoissonApplyDot { // out = P p ; acc[0] += <a, out>
 static double poisson_apply_dot(Solver &s, double *pin, double *out, const double *a)
 {
   halo_scalar(s, pin);
+#ifndef FLUCA_HOSTEMU
+  if (tma_usable(s)) {
+    KScope kt(s.ex, KT_POISSON_APPLY);
+    poisson_apply_dot_tma(s, pin, out, a);
+  } else
+#endif
   {
     KScope kt(s.ex, KT_POISSON_APPLY);
     if (s.dim == 2) {
@@ -206,9 +212,9 @@ static int poisson_pcg(Solver &s, double *b, double *x)
   double       rz = 0.;
   int          it = 0;
   for (; it < s.opt.inner_maxit;) {
-    const double *Z = mg_vcycle(s, s.pr) + off;
-    // rz_new = <r, z>
-    for_range_reduce<1>(s.ex, len, FL_LAMBDA(long i, double acc[1]) { acc[0] += R[i] * Z[i]; });
+    // z = V-cycle(r); its last smoothing sweep also accumulates rz_new = <r, z>
+    const double *Z = mg_vcycle(s, s.pr, s.opt.mg_nu2 > 0) + off;
+    if (s.opt.mg_nu2 <= 0) for_range_reduce<1>(s.ex, len, FL_LAMBDA(long i, double acc[1]) { acc[0] += R[i] * Z[i]; });
     reduce_finish(s, 1, red);
     const double rz_new = red[0];
     if (it == 0) {

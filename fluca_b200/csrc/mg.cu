@@ -11,46 +11,62 @@
 // direction while the (local) size stays even.  At pressure outlets the hierarchy uses a plain
 // first-order Dirichlet row; the Krylov method outside applies the exact one-sided operator.
 #include "solver.h"
+#ifndef FLUCA_HOSTEMU
+#include "tma.h"
+#endif
 
 namespace fluca {
 
 namespace {
 
+// row of the level operator from the centre value and the two neighbours per direction (out-of-range
+// neighbours are passed as 0: they meet k = 0 at Neumann walls and are the Dirichlet ghost at outlets)
 template <int DIM>
-FL_HD void mg_row(const MGLevel &L, const double *__restrict__ x, int i, int j, int kl, double &Ax, double &diag)
+FL_HD void mg_row_core(const MGLevel &L, int i, int j, int kl, double xc, const double xm[3], const double xp[3], double &Ax, double &diag)
 {
-  const long   c  = L.idx(i, j, kl);
-  const double xc = x[c];
   const double hx = L.h[0][i], hy = L.h[1][j];
   const double hz = (DIM == 3) ? L.h[2][L.k0 + kl] : 1.;
   const double ax = hy * hz, ay = hx * hz, az = hx * hy;
   double       s = 0., dg = 0.;
   {
-    const int    n  = L.n[0];
     const double kl_ = L.kf[0][i], ku = L.kf[0][i + 1];
-    const double xm = i > 0 ? x[c - 1] : (L.per[0] ? x[c + (n - 1)] : 0.);
-    const double xp = i < n - 1 ? x[c + 1] : (L.per[0] ? x[c - (n - 1)] : 0.);
-    s += ax * (kl_ * (xc - xm) + ku * (xc - xp));
+    s += ax * (kl_ * (xc - xm[0]) + ku * (xc - xp[0]));
     dg += ax * (kl_ + ku);
   }
   {
-    const int    n  = L.n[1];
     const double kl_ = L.kf[1][j], ku = L.kf[1][j + 1];
-    const double xm = j > 0 ? x[c - L.px] : (L.per[1] ? x[c + (long)(n - 1) * L.px] : 0.);
-    const double xp = j < n - 1 ? x[c + L.px] : (L.per[1] ? x[c - (long)(n - 1) * L.px] : 0.);
-    s += ay * (kl_ * (xc - xm) + ku * (xc - xp));
+    s += ay * (kl_ * (xc - xm[1]) + ku * (xc - xp[1]));
     dg += ay * (kl_ + ku);
   }
   if (DIM == 3) {
     const int    kg = L.k0 + kl;
     const double kl_ = L.kf[2][kg], ku = L.kf[2][kg + 1];
-    // ghost planes: neighbour rank / periodic wrap, or zeros at a wall
-    const double xm = x[c - L.plane], xp = x[c + L.plane];
-    s += az * (kl_ * (xc - xm) + ku * (xc - xp));
+    s += az * (kl_ * (xc - xm[2]) + ku * (xc - xp[2]));
     dg += az * (kl_ + ku);
   }
   Ax   = s;
   diag = dg;
+}
+
+template <int DIM>
+FL_HD void mg_row(const MGLevel &L, const double *__restrict__ x, int i, int j, int kl, double &Ax, double &diag)
+{
+  const long c = L.idx(i, j, kl);
+  double     xm[3], xp[3];
+  {
+    const int n = L.n[0];
+    xm[0] = i > 0 ? x[c - 1] : (L.per[0] ? x[c + (n - 1)] : 0.);
+    xp[0] = i < n - 1 ? x[c + 1] : (L.per[0] ? x[c - (n - 1)] : 0.);
+  }
+  {
+    const int n = L.n[1];
+    xm[1] = j > 0 ? x[c - L.px] : (L.per[1] ? x[c + (long)(n - 1) * L.px] : 0.);
+    xp[1] = j < n - 1 ? x[c + L.px] : (L.per[1] ? x[c - (long)(n - 1) * L.px] : 0.);
+  }
+  // ghost planes: neighbour rank / periodic wrap, or zeros at a wall
+  xm[2] = (DIM == 3) ? x[c - L.plane] : 0.;
+  xp[2] = (DIM == 3) ? x[c + L.plane] : 0.;
+  mg_row_core<DIM>(L, i, j, kl, x[c], xm, xp, Ax, diag);
 }
 
 template <int DIM>
@@ -60,7 +76,7 @@ struct MGSmooth {
   int           zero_guess;
   const double *xin, *b;
   double       *xout;
-  FL_HD void operator()(int i, int j, int kl) const
+  FL_HD double sweep(int i, int j, int kl) const
   {
     const long c = L.idx(i, j, kl);
     double     Ax, dg;
@@ -69,13 +85,46 @@ struct MGSmooth {
       const double hx = L.h[0][i], hy = L.h[1][j], hz = (DIM == 3) ? L.h[2][L.k0 + kl] : 1.;
       dg = hy * hz * (L.kf[0][i] + L.kf[0][i + 1]) + hx * hz * (L.kf[1][j] + L.kf[1][j + 1]);
       if (DIM == 3) dg += hx * hy * (L.kf[2][L.k0 + kl] + L.kf[2][L.k0 + kl + 1]);
-      xout[c] = dg > 0. ? omega * b[c] / dg : 0.;
-      return;
+      const double v = dg > 0. ? omega * b[c] / dg : 0.;
+      xout[c]        = v;
+      return b[c] * v;
     }
     mg_row<DIM>(L, xin, i, j, kl, Ax, dg);
-    xout[c] = dg > 0. ? xin[c] + omega * (b[c] - Ax) / dg : xin[c];
+    const double bc = b[c], v = dg > 0. ? xin[c] + omega * (bc - Ax) / dg : xin[c];
+    xout[c]         = v;
+    return bc * v;
+  }
+  FL_HD void operator()(int i, int j, int kl) const { (void)sweep(i, j, kl); }
+  // the last sweep of the cycle also accumulates <b, x> = <r, z> for the CG that called it
+  FL_HD void operator()(int i, int j, int kl, double acc[1]) const { acc[0] += sweep(i, j, kl); }
+};
+
+#ifndef FLUCA_HOSTEMU
+// the same sweep from TMA-staged tiles (3-D levels of at least one tile per plane, see tma.h)
+template <int NRED>
+struct MGSmoothTile {
+  static const int NIN = 1, NR = NRED, MINB = 4;
+  MGLevel          L;
+  double           omega;
+  const double    *b;
+  double          *xout;
+  struct Regs {
+    double b;
+  };
+  __device__ void prefetch(Regs &rg, int i, int j, int kl) const { rg.b = b[L.idx(i, j, kl)]; }
+  __device__ void cell(const TileView &tv, const Regs &rg, int i, int j, int kl, double *acc) const
+  {
+    const int    lc = tv.lc;
+    const double xc = tv.p0[lc];
+    const double xm[3] = {tv.p0[lc - 1], tv.p0[lc - TLX], tv.pm[lc]}, xp[3] = {tv.p0[lc + 1], tv.p0[lc + TLX], tv.pp[lc]};
+    double       Ax, dg;
+    mg_row_core<3>(L, i, j, kl, xc, xm, xp, Ax, dg);
+    const double v = dg > 0. ? xc + omega * (rg.b - Ax) / dg : xc;
+    xout[L.idx(i, j, kl)] = v;
+    if (NRED > 0) acc[0] += rg.b * v;
   }
 };
+#endif
 
 // coarse b = sum over children of (b - P x)
 template <int DIM>
@@ -198,15 +247,45 @@ void level_halo(Solver &s, MGLevel &L, double *x)
   s.comm->halo(s.ex, f, 1, L.plane, L.nzl, L.per[2] != 0);
 }
 
+bool level_tiled(const Solver &s, const MGLevel &L)
+{
+#ifndef FLUCA_HOSTEMU
+  return tma_usable(s) && L.n[0] >= TMX && L.n[1] >= TMY;
+#else
+  (void)s, (void)L;
+  return false;
+#endif
+}
+
+// one damped-Jacobi sweep; with_dot leaves <b, x_new> in ex.d_result
 template <int DIM>
-void smooth(Solver &s, MGLevel &L, bool zero_guess)
+void smooth(Solver &s, MGLevel &L, bool zero_guess, bool with_dot = false)
 {
   const double omega = (DIM == 3) ? 6. / 7. : 0.8;
   if (!zero_guess) level_halo(s, L, L.x);
   KScope        kt(s.ex, KT_MG_SMOOTH);
+#ifndef FLUCA_HOSTEMU
+  if (DIM == 3 && !zero_guess && level_tiled(s, L)) {
+    const double *fields[1] = {L.x};
+    if (with_dot) {
+      MGSmoothTile<1> op;
+      op.L = L, op.omega = omega, op.b = L.b, op.xout = L.t;
+      tma_launch(s.ex, op, fields, L.px, L.py, L.nzl + 2, L.n[0], L.n[1], 0, L.nzl, nullptr);
+    } else {
+      MGSmoothTile<0> op;
+      op.L = L, op.omega = omega, op.b = L.b, op.xout = L.t;
+      tma_launch(s.ex, op, fields, L.px, L.py, L.nzl + 2, L.n[0], L.n[1], 0, L.nzl, nullptr);
+    }
+    double *tmp = L.x;
+    L.x         = L.t;
+    L.t         = tmp;
+    return;
+  }
+#endif
   MGSmooth<DIM> f;
   f.L = L, f.omega = omega, f.zero_guess = zero_guess ? 1 : 0, f.xin = L.x, f.b = L.b, f.xout = zero_guess ? L.x : L.t;
-  for_box(s.ex, level_box(L), f);
+  if (with_dot) for_box_reduce<1>(s.ex, level_box(L), f);
+  else for_box(s.ex, level_box(L), f);
   if (!zero_guess) {
     double *tmp = L.x;
     L.x         = L.t;
@@ -215,13 +294,14 @@ void smooth(Solver &s, MGLevel &L, bool zero_guess)
 }
 
 template <int DIM>
-void vcycle(Solver &s, size_t l)
+void vcycle(Solver &s, size_t l, bool want_dot)
 {
   MGLevel &L = s.mg[l];
   const bool coarsest = (l + 1 == s.mg.size());
   if (coarsest) {
-    smooth<DIM>(s, L, true);
-    for (int k = 1; k < s.opt.mg_coarse_sweeps; ++k) smooth<DIM>(s, L, false);
+    const int ns = s.opt.mg_coarse_sweeps;
+    smooth<DIM>(s, L, true, want_dot && ns <= 1);
+    for (int k = 1; k < ns; ++k) smooth<DIM>(s, L, false, want_dot && k == ns - 1);
     return;
   }
   smooth<DIM>(s, L, true);
@@ -234,7 +314,7 @@ void vcycle(Solver &s, size_t l)
     rr.F = L, rr.C = C;
     for_box(s.ex, level_box(C), rr);
   }
-  vcycle<DIM>(s, l + 1);
+  vcycle<DIM>(s, l + 1, false);
   level_halo(s, C, C.x);
   {
     KScope         kt(s.ex, KT_MG_TRANSFER);
@@ -242,7 +322,7 @@ void vcycle(Solver &s, size_t l)
     pr.F = L, pr.C = C;
     for_box(s.ex, level_box(L), pr);
   }
-  for (int k = 0; k < s.opt.mg_nu2; ++k) smooth<DIM>(s, L, false);
+  for (int k = 0; k < s.opt.mg_nu2; ++k) smooth<DIM>(s, L, false, want_dot && k == s.opt.mg_nu2 - 1);
 }
 
 } // namespace
@@ -319,14 +399,14 @@ void mg_destroy(Solver &s)
   s.mg.clear();
 }
 
-// returns z = V-cycle(r) with zero initial guess.  r is a fine-level field (Geom layout); the result
+// returns z = V-cycle(r) with zero initial guess; want_dot: the last sweep leaves <r, z> in ex.d_result.  r is a fine-level field (Geom layout); the result
 // lives in a level-0 buffer (same layout, ghost planes included) that stays valid until the next call.
-double *mg_vcycle(Solver &s, double *r)
+double *mg_vcycle(Solver &s, double *r, bool want_dot)
 {
   MGLevel &L0 = s.mg[0];
   L0.b        = r;
-  if (s.dim == 2) vcycle<2>(s, 0);
-  else vcycle<3>(s, 0);
+  if (s.dim == 2) vcycle<2>(s, 0, want_dot);
+  else vcycle<3>(s, 0, want_dot);
   L0.b = nullptr;
   return L0.x;
 }

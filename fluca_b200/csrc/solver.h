@@ -163,6 +163,7 @@ int  do_step(Solver &s, double t, int step_index);
 // TMA-staged versions of the hot 3-D operators (tiles.cu); tma_usable() says whether the mesh qualifies
 bool tma_usable(const Solver &s);
 void a_apply_dots_tma(Solver &s, const V3 &x, const V3 &y, const V3 &a, bool with_dots);
+void poisson_apply_dot_tma(Solver &s, const double *pin, double *out, const double *a);
 #endif
 
 // Krylov / multigrid (krylov.cu, mg.cu)
@@ -170,7 +171,7 @@ int  momentum_solve(Solver &s, const V3 &b, const V3 &x);
 int  poisson_solve(Solver &s, double *b, double *x);
 void mg_setup(Solver &s);
 void mg_destroy(Solver &s);
-double *mg_vcycle(Solver &s, double *r);
+double *mg_vcycle(Solver &s, double *r, bool want_dot = false);
 void poisson_apply(Solver &s, double *pin, double *out);
 
 } // namespace fluca

@@ -385,29 +385,38 @@ struct DivCell { // y_p = D U (per unit volume, as the reference's D)
 
 // ------------------------------------------------------------------ Poisson operator, fine level
 // (P p)_c = vol * (-D Gst0 p)_c = sum_d area_d (g_lo - g_hi),  g = face-normal derivative
+// row of the Poisson operator from the centre value and the two neighbours per direction
 template <int DIM>
-FL_HD double poisson_apply_cell(const Geom &g, const double *__restrict__ p, const Nbr<DIM> &nb)
+FL_HD double poisson_row(const Geom &g, const int ig[DIM], double pc, const double pm[DIM], const double pp[DIM])
 {
   double h[DIM], vol = 1.;
 #pragma unroll
   for (int d = 0; d < DIM; ++d) {
-    h[d] = g.t[d].h[nb.ig[d]];
+    h[d] = g.t[d].h[ig[d]];
     vol *= h[d];
   }
-  const double pc = p[nb.c];
-  double       s  = 0.;
+  double s = 0.;
 #pragma unroll
   for (int d = 0; d < DIM; ++d) {
-    const Tab &T  = g.t[d];
-    const int  ig = nb.ig[d];
+    const Tab &T = g.t[d];
+    const int  i = ig[d];
     double     gl, gu;
-    if (!T.per && ig == 0) gl = T.gst_lo[0] * pc + T.gst_lo[1] * p[nb.p[d]];
-    else gl = T.gstw[ig] * (pc - p[nb.m[d]]);
-    if (!T.per && ig == T.n - 1) gu = T.gst_hi[0] * p[nb.m[d]] + T.gst_hi[1] * pc;
-    else gu = T.gstw[ig + 1] * (p[nb.p[d]] - pc);
+    if (!T.per && i == 0) gl = T.gst_lo[0] * pc + T.gst_lo[1] * pp[d];
+    else gl = T.gstw[i] * (pc - pm[d]);
+    if (!T.per && i == T.n - 1) gu = T.gst_hi[0] * pm[d] + T.gst_hi[1] * pc;
+    else gu = T.gstw[i + 1] * (pp[d] - pc);
     s += (vol / h[d]) * (gl - gu);
   }
   return s;
+}
+
+template <int DIM>
+FL_HD double poisson_apply_cell(const Geom &g, const double *__restrict__ p, const Nbr<DIM> &nb)
+{
+  double pm[DIM], pp[DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) pm[d] = p[nb.m[d]], pp[d] = p[nb.p[d]];
+  return poisson_row<DIM>(g, nb.ig, p[nb.c], pm, pp);
 }
 
 // v = v* - (dt/rho) G0 p   (abfpc.c:80,95)

@@ -501,6 +501,67 @@ static void mv_zero(Solver &s, const MV &y)
   });
 }
 
+
+// ---- fused classical Gram-Schmidt step: h_j = <V_j, w> (j < nv), ww = <w, w>; w -= sum_j h_j V_j; nrm2 = |w|^2
+struct MVSet {
+  static const int MAXV = 15; // projections per sweep (one more reduction slot carries <w, w>)
+  const double    *f[MAXV][7];
+};
+
+struct MVCoef {
+  double c[MVSet::MAXV];
+};
+
+static void mv_project(Solver &s, const std::vector<MV> &V, int nv, const MV &w, double *h, double &ww, double &nrm2)
+{
+  ww = 0.;
+  for (int j0 = 0; j0 < nv; j0 += MVSet::MAXV) {
+    const int nc = nv - j0 < MVSet::MAXV ? nv - j0 : MVSet::MAXV;
+    MVSet     S;
+    for (int j = 0; j < MVSet::MAXV; ++j)
+      for (int f = 0; f < 7; ++f) S.f[j][f] = j < nc ? V[j0 + j].f[f] : nullptr;
+    for_range_reduce<MVSet::MAXV + 1>(s.ex, w.n, FL_LAMBDA(long i, double acc[MVSet::MAXV + 1]) {
+      double wv[7];
+#pragma unroll
+      for (int f = 0; f < 7; ++f) wv[f] = i < w.len[f] ? w.f[f][i] : 0.;
+      double t = 0.;
+#pragma unroll
+      for (int f = 0; f < 7; ++f) t += wv[f] * wv[f];
+      acc[MVSet::MAXV] += t;
+#pragma unroll
+      for (int j = 0; j < MVSet::MAXV; ++j)
+        if (j < nc) {
+          double d = 0.;
+#pragma unroll
+          for (int f = 0; f < 7; ++f)
+            if (i < w.len[f]) d += S.f[j][f][i] * wv[f];
+          acc[j] += d;
+        }
+    });
+    double red[MVSet::MAXV + 1];
+    reduce_finish(s, MVSet::MAXV + 1, red);
+    if (j0 == 0) ww = red[MVSet::MAXV];
+    MVCoef C;
+    for (int j = 0; j < MVSet::MAXV; ++j) C.c[j] = j < nc ? red[j] : 0.;
+    for (int j = 0; j < nc; ++j) h[j0 + j] = red[j];
+    for_range_reduce<1>(s.ex, w.n, FL_LAMBDA(long i, double acc[1]) {
+      double t = 0.;
+#pragma unroll
+      for (int f = 0; f < 7; ++f)
+        if (i < w.len[f]) {
+          double wv = w.f[f][i];
+#pragma unroll
+          for (int j = 0; j < MVSet::MAXV; ++j)
+            if (j < nc) wv -= C.c[j] * S.f[j][f][i];
+          w.f[f][i] = wv;
+          t += wv * wv;
+        }
+      acc[0] += t;
+    });
+    reduce_finish(s, 1, &nrm2);
+  }
+}
+
 // right-preconditioned restarted GMRES on M x = b, PC = ABF, zero initial guess, true-residual
 // norm; x is built in (s.xv, s.xU, s.xp)
 static int outer_gmres(Solver &s)
@@ -549,14 +610,19 @@ static int outer_gmres(Solver &s)
       for (int c = 0; c < 3; ++c) nv.c[c] = s.basis[k + 1][c], nU.c[c] = s.basis[k + 1][3 + c];
       coupled_apply(s, s.zv, s.zU, s.zp, nv, nU, s.basis[k + 1][6]);
       if (!s.has_outlet) remove_mean(s, s.basis[k + 1][6]); // null space of J (nsbasic.c:229-243)
-      for (int pass = 0; pass < 2; ++pass) // Gram-Schmidt with one refinement pass
-        for (int jx = 0; jx <= k; ++jx) {
-          double hj = mv_dot(s, V[jx], V[k + 1]);
-          mv_axpby(s, -hj, V[jx], 1., V[k + 1]);
-          if (pass == 0) H[(size_t)jx * m + k] = hj;
-          else H[(size_t)jx * m + k] += hj;
-        }
-      double hn = std::sqrt(mv_dot(s, V[k + 1], V[k + 1]));
+      // classical Gram-Schmidt, all projections in one pass (PETSc's GMRES default,
+      // KSPGMRESClassicalGramSchmidtOrthogonalization), re-orthogonalised only when the norm dropped by more
+      // than 1/sqrt(2) (the "refine if needed" criterion): 2 sweeps over k+2 vectors instead of 5 (k+1)
+      std::vector<double> hcolv(m + 1, 0.);
+      double             *hcol = hcolv.data(), ww = 0., nrm2 = 0.;
+      mv_project(s, V, k + 1, V[k + 1], hcol, ww, nrm2);
+      for (int jx = 0; jx <= k; ++jx) H[(size_t)jx * m + k] = hcol[jx];
+      if (nrm2 < 0.5 * ww) {
+        double ww2;
+        mv_project(s, V, k + 1, V[k + 1], hcol, ww2, nrm2);
+        for (int jx = 0; jx <= k; ++jx) H[(size_t)jx * m + k] += hcol[jx];
+      }
+      double hn = std::sqrt(nrm2);
       H[(size_t)(k + 1) * m + k] = hn;
       if (hn > 0.) mv_axpby(s, 1. / hn, V[k + 1], 0., V[k + 1]);
       for (int jx = 0; jx < k; ++jx) {

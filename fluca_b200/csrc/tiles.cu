@@ -147,7 +147,7 @@ __device__ __forceinline__ void a_apply_tile(const Geom &g, const StepParams &sp
 
 template <int NRED>
 struct AApplyTile {
-  static const int NIN = 9, NR = NRED;
+  static const int NIN = 9, NR = NRED, MINB = 2;
   Geom             g;
   StepParams       sp;
   BcDev            bc;
@@ -234,6 +234,42 @@ void a_apply_dots_tma(Solver &s, const V3 &x, const V3 &y, const V3 &a, bool wit
     for (int c = 0; c < 3; ++c) op.a[c] = nullptr, op.y[c] = y.c[c];
     tma_launch(s.ex, op, fields, g.px, g.py, g.nzl + 2, g.nx, g.ny, kbeg, kend, nullptr);
   }
+}
+
+// ------------------------------------------------------------------ Poisson operator from shared-memory tiles
+// No plane needs special treatment: the wall rows of P use the cells (c, c+1) / (c-1, c) only.
+template <int NRED>
+struct PoissonTile {
+  static const int NIN = 1, NR = NRED, MINB = 4;
+  Geom             g;
+  const double    *a; // dot partner; nullptr: p itself
+  double          *out;
+  struct Regs {
+    double a;
+  };
+  __device__ void prefetch(Regs &rg, int i, int j, int kl) const
+  {
+    if (NRED > 0 && a) rg.a = a[g.idx(i, j, kl)];
+  }
+  __device__ void cell(const TileView &tv, const Regs &rg, int i, int j, int kl, double *acc) const
+  {
+    const int    lc = tv.lc, ig[3] = {i, j, g.k0 + kl};
+    const double pc = tv.p0[lc];
+    const double pm[3] = {tv.p0[lc - 1], tv.p0[lc - TLX], tv.pm[lc]}, pp[3] = {tv.p0[lc + 1], tv.p0[lc + TLX], tv.pp[lc]};
+    const double v = poisson_row<3>(g, ig, pc, pm, pp);
+    out[g.idx(i, j, kl)] = v;
+    if (NRED > 0) acc[0] += (a ? rg.a : pc) * v;
+  }
+};
+
+// out = P p ; <a, out> is left in ex.d_result
+void poisson_apply_dot_tma(Solver &s, const double *pin, double *out, const double *a)
+{
+  const Geom    &g = s.gh.g;
+  PoissonTile<1> op;
+  op.g = g, op.a = (a == pin) ? nullptr : a, op.out = out;
+  const double *fields[1] = {pin};
+  tma_launch(s.ex, op, fields, g.px, g.py, g.nzl + 2, g.nx, g.ny, 0, g.nzl, nullptr);
 }
 
 } // namespace fluca

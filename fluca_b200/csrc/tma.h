@@ -99,12 +99,12 @@ struct TileView {
 };
 
 // Op interface:
-//   static const int NIN, NR;
+//   static const int NIN, NR, MINB;                                     inputs, reductions, resident CTAs per SM aimed at
 //   struct Regs;                                                         per-thread operands that bypass the tiles
 //   __device__ void prefetch(Regs &r, int i, int j, int kl) const;       global loads for plane kl, issued one plane ahead
 //   __device__ void cell(const TileView &tv, const Regs &r, int i, int j, int kl, double *acc) const;   (acc: NR entries)
 template <class Op>
-__global__ void __launch_bounds__(TMX *TMY, 2) k_tma_march(const __grid_constant__ TmaIn<Op::NIN> in, const Op op, const TmaGrid tg, const double *carry, double *partials, double *result, unsigned *ticket)
+__global__ void __launch_bounds__(TMX *TMY, Op::MINB) k_tma_march(const __grid_constant__ TmaIn<Op::NIN> in, const Op op, const TmaGrid tg, const double *carry, double *partials, double *result, unsigned *ticket)
 {
   extern __shared__ __align__(128) unsigned char tma_smem[];
   double   *ring = reinterpret_cast<double *>(tma_smem);
@@ -206,7 +206,7 @@ inline void tma_launch(Exec &ex, const Op &op, const double *const *fields, int 
   TmaGrid tg;
   tg.nx = nx, tg.ny = ny, tg.kbeg = kbeg, tg.kend = kend;
   tg.ntx = (nx + TMX - 1) / TMX, tg.nty = (ny + TMY - 1) / TMY;
-  tg.nchunk = tma_pick_chunks(tg.ntx * tg.nty, kend - kbeg, 2 * ex.sm_count, ex.max_blocks);
+  tg.nchunk = tma_pick_chunks(tg.ntx * tg.nty, kend - kbeg, Op::MINB * ex.sm_count, ex.max_blocks);
   const size_t smem = (size_t)TMS * Op::NIN * TILE_STRIDE * sizeof(double) + TMS * sizeof(uint64_t);
   static bool  configured = false; // per template instantiation
   if (!configured) {
