@@ -100,8 +100,13 @@ SYMBOLS = [
     "fluca_b200_kernel_timing",
     "fluca_b200_kernel_times",
     "fluca_b200_time_kernel",
+    "fluca_b200_set_markers",
+    "fluca_b200_get_marker_forces",
+    "fluca_b200_ibm_interpolate",
+    "fluca_b200_ibm_spread",
+    "fluca_b200_set_ibm_iterations",
 ]
-KT_NAMES = ["momentum_apply", "momentum_vec", "poisson_apply", "poisson_vec", "mg_smooth", "mg_transfer", "rhs_project", "outer", "halo"]
+KT_NAMES = ["momentum_apply", "momentum_vec", "poisson_apply", "poisson_vec", "mg_smooth", "mg_transfer", "rhs_project", "outer", "halo", "ibm"]
 
 _P = C.c_void_p
 _PD3 = C.POINTER(C.c_void_p)
@@ -139,6 +144,11 @@ def _prototype(L):
     L.fluca_b200_kernel_timing.argtypes = [_P, C.c_int]
     L.fluca_b200_kernel_times.argtypes = [_P, C.POINTER(C.c_double), C.POINTER(C.c_long), C.c_int]
     L.fluca_b200_time_kernel.argtypes = [_P, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.fluca_b200_set_markers.argtypes = [_P, C.c_long, _P, _P, _P, C.c_int]
+    L.fluca_b200_get_marker_forces.argtypes = [_P, _P, _P]
+    L.fluca_b200_ibm_interpolate.argtypes = [_P, _P, _P]
+    L.fluca_b200_ibm_spread.argtypes = [_P, _P, _P]
+    L.fluca_b200_set_ibm_iterations.argtypes = [_P, C.c_int]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("fluca_b200_is_host_emulation",):

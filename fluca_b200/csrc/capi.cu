@@ -494,3 +494,60 @@ extern "C" int fluca_b200_time_kernel(fluca_b200_solver *h, const char *name, in
 #endif
   API_END
 }
+
+// ------------------------------------------------------------------ immersed boundary
+extern "C" int fluca_b200_set_markers(fluca_b200_solver *h, long n, const double *X, const double *Ud, const double *dV, int delta_points)
+{
+  API_BEGIN
+  ibm_set_markers(h->s, n, X, Ud, dV, delta_points);
+  API_END
+}
+
+extern "C" int fluca_b200_get_marker_forces(fluca_b200_solver *h, double *F, double *Um)
+{
+  API_BEGIN
+  Solver &s = h->s;
+  const Ibm &b = s.ibm;
+  for (int d = 0; d < s.dim && b.n > 0; ++d) {
+    if (F) copy_d2h(s.ex, F + (size_t)b.n * d, b.F[d], sizeof(double) * b.n);
+    if (Um) copy_d2h(s.ex, Um + (size_t)b.n * d, b.Um[d], sizeof(double) * b.n);
+  }
+  s.ex.sync();
+  API_END
+}
+
+extern "C" int fluca_b200_ibm_interpolate(fluca_b200_solver *h, const double *v, double *Um)
+{
+  API_BEGIN
+  Solver &s = h->s;
+  if (s.ibm.n <= 0) throw Error(FL_ERR_ARG, "no markers set");
+  put_cells(s, s.vstar, v);
+  ibm_interpolate(s, s.vstar);
+  for (int d = 0; d < s.dim; ++d) copy_d2h(s.ex, Um + (size_t)s.ibm.n * d, s.ibm.Um[d], sizeof(double) * s.ibm.n);
+  s.ex.sync();
+  API_END
+}
+
+extern "C" int fluca_b200_ibm_spread(fluca_b200_solver *h, const double *Fm, double *f)
+{
+  API_BEGIN
+  Solver &s = h->s;
+  Ibm    &b = s.ibm;
+  if (b.n <= 0) throw Error(FL_ERR_ARG, "no markers set");
+  for (int d = 0; d < s.dim; ++d) {
+    copy_h2d(s.ex, b.Dl[d], Fm + (size_t)b.n * d, sizeof(double) * b.n);
+    dev_zero(s.ex, s.vstar.c[d], sizeof(double) * (size_t)s.gh.g.nalloc);
+  }
+  ibm_spread(s, b.Dl, s.vstar);
+  get_cells(s, f, s.vstar);
+  s.ex.sync();
+  API_END
+}
+
+extern "C" int fluca_b200_set_ibm_iterations(fluca_b200_solver *h, int passes)
+{
+  API_BEGIN
+  if (passes < 1 || passes > 64) throw Error(FL_ERR_ARG, "forcing passes must be in [1, 64]");
+  h->s.ibm.iters = passes;
+  API_END
+}

@@ -67,7 +67,7 @@ struct ExecStats {
 };
 
 // kernel classes timed live with CUDA events (bench.py roofline): see KTimer below
-enum { KT_MOMENTUM_APPLY = 0, KT_MOMENTUM_VEC, KT_POISSON_APPLY, KT_POISSON_VEC, KT_MG_SMOOTH, KT_MG_TRANSFER, KT_RHS_PROJECT, KT_OUTER, KT_HALO, KT_NCLASS };
+enum { KT_MOMENTUM_APPLY = 0, KT_MOMENTUM_VEC, KT_POISSON_APPLY, KT_POISSON_VEC, KT_MG_SMOOTH, KT_MG_TRANSFER, KT_RHS_PROJECT, KT_OUTER, KT_HALO, KT_IBM, KT_NCLASS };
 
 struct Exec {
   Stream    stream    = nullptr;

@@ -2,6 +2,7 @@
 #pragma once
 #include "geom.h"
 #include "stencil.h"
+#include "ibm.h"
 #include <memory>
 
 namespace fluca {
@@ -124,6 +125,8 @@ struct Solver {
   V3      wv, wU, zv, zU, tw;
   double *wp = nullptr, *zp = nullptr;
   int     basis_size = 0;
+
+  Ibm    ibm; // immersed-boundary markers (empty unless fluca_b200_set_markers was called)
 
   Stats  stats;
   int    step_index = 0;

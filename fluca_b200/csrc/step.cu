@@ -187,6 +187,7 @@ void solver_setup(Solver &s, int dim, const int n[3], const double *const xf[3],
 void solver_destroy(Solver &s)
 {
   s.ex.sync();
+  ibm_destroy(s);
   mg_destroy(s);
   for (double *p : s.pool) dev_free(p);
   s.pool.clear();
@@ -673,6 +674,7 @@ int do_step(Solver &s, double t, int step_index)
   const long l0 = s.ex.stats.launches;
   s.stats       = Stats();
   prepare_step(s, t, step_index);
+  if (s.ibm.n > 0) ibm_force_rhs(s); // immersed-boundary forcing joins the momentum right-hand side (ibm.h)
   if (!s.has_outlet) remove_mean(s, s.rc); // F(0) = -b with the null space removed (nsbasic.c:133-144)
   int rc = 0;
   if (s.opt.mode == 1) {

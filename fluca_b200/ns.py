@@ -587,5 +587,18 @@ def NSB200GetSolver(ns: NS) -> Solver:
     return ns.data.solver
 
 
+def NSB200SetMarkers(ns: NS, X, Ud, dV, delta_points: int = 4, iterations: int = 1):
+    """Immersed-boundary markers of the b200 type (no counterpart in the reference, which only plans IBM:
+    README.md:14, THEORY_GUIDE.md:130-132).  Call after NSSetUp; call again whenever the body moves."""
+    if not ns.setupcalled:
+        raise FlucaError("This function must be called after NSSetUp()")
+    ns.data.solver.set_markers(X, Ud, dV, delta_points, iterations)
+
+
+def NSB200GetMarkerForces(ns: NS):
+    """(F, Um): force of every marker on the fluid and the interpolated predictor velocity of the last step."""
+    return ns.data.solver.marker_forces()
+
+
 def NSB200GetStats(ns: NS):
     return ns.data.last_stats

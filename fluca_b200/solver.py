@@ -226,6 +226,33 @@ class Solver:
         _lib.check(self.L, self.L.fluca_b200_apply_abf(self._h, bv.ctypes.data, self._ptrs(bU), bp.ctypes.data, xv.ctypes.data, self._ptrs(xU), xp.ctypes.data, C.byref(st)))
         return xv, xU, xp, st
 
+    # ------------------------------------------------------------------ immersed boundary
+    def set_markers(self, X, Ud, dV, delta_points: int = 4, iterations: int = 1):
+        """X, Ud: (dim, n) marker positions / prescribed velocities; dV: (n,) volume weights (replicated on every rank)."""
+        X = np.ascontiguousarray(X, dtype=np.float64).reshape(self.dim, -1)
+        self.nm = X.shape[1]
+        Ud = np.ascontiguousarray(Ud, dtype=np.float64).reshape(self.dim, self.nm)
+        dV = np.ascontiguousarray(dV, dtype=np.float64).reshape(self.nm)
+        _lib.check(self.L, self.L.fluca_b200_set_markers(self._h, self.nm, X.ctypes.data, Ud.ctypes.data, dV.ctypes.data, int(delta_points)))
+        _lib.check(self.L, self.L.fluca_b200_set_ibm_iterations(self._h, int(iterations)))
+
+    def marker_forces(self):
+        F, Um = np.zeros((self.dim, self.nm)), np.zeros((self.dim, self.nm))
+        _lib.check(self.L, self.L.fluca_b200_get_marker_forces(self._h, F.ctypes.data, Um.ctypes.data))
+        return F, Um
+
+    def ibm_interpolate(self, v):
+        v = self._cells(v, self.dim)
+        Um = np.zeros((self.dim, self.nm))
+        _lib.check(self.L, self.L.fluca_b200_ibm_interpolate(self._h, v.ctypes.data, Um.ctypes.data))
+        return Um
+
+    def ibm_spread(self, Fm):
+        Fm = np.ascontiguousarray(Fm, dtype=np.float64).reshape(self.dim, self.nm)
+        f = self.new_cells(self.dim)
+        _lib.check(self.L, self.L.fluca_b200_ibm_spread(self._h, Fm.ctypes.data, f.ctypes.data))
+        return f
+
     # ------------------------------------------------------------------ device-resident helpers
     def snapshot_save(self):
         _lib.check(self.L, self.L.fluca_b200_snapshot_save(self._h))

@@ -113,6 +113,21 @@ int fluca_b200_get_state(fluca_b200_solver *s, double *v, double *const U[3], do
 int fluca_b200_set_boundary_velocity(fluca_b200_solver *s, int boundary, int slot, const double *values);
 int fluca_b200_set_boundary_pressure(fluca_b200_solver *s, int boundary, int slot, const double *values);
 
+/* ---- immersed boundary.  The reference advertises the method (README.md:14) but has no code
+ * for it (THEORY_GUIDE.md:130-132 is a TODO), so these entry points replace no reference interface; they are what an
+ * IBM-enabled NS type would add next to NSSetBoundaryCondition.  Markers are replicated: every rank passes the same
+ * global list.  X, Ud, F, Um: dim consecutive blocks of n doubles; dV: n doubles (Lagrangian volume weights).
+ * delta_points: 4 (Peskin, default for 0) or 3 (Roma).  n = 0 removes the markers.
+ * Coupling: direct forcing with an implicit predictor, added to the momentum right-hand side of the step. */
+int fluca_b200_set_markers(fluca_b200_solver *s, long n, const double *X, const double *Ud, const double *dV, int delta_points);
+/* multi-direct forcing: passes of (interpolate, spread) per step, each acting on the corrected predictor [1] */
+int fluca_b200_set_ibm_iterations(fluca_b200_solver *s, int passes);
+/* force of every marker on the fluid, rho (Ud - Um) dV / dt, and the interpolated predictor velocity Um of the last step */
+int fluca_b200_get_marker_forces(fluca_b200_solver *s, double *F, double *Um);
+/* operator-level (tests): Um = interpolation of the cell field v; f = spreading of Fm (f is overwritten) */
+int fluca_b200_ibm_interpolate(fluca_b200_solver *s, const double *v, double *Um);
+int fluca_b200_ibm_spread(fluca_b200_solver *s, const double *Fm, double *f);
+
 /* ---- ops->step: one NSStep_CNLinear_Cart{2,3}d_Internal (cnlinearcart3d.c:2807-2863) ---- */
 int fluca_b200_step(fluca_b200_solver *s, double t, int step_index, fluca_b200_stats *stats);
 
@@ -157,7 +172,8 @@ double fluca_b200_step_model_bytes(fluca_b200_solver *s, const fluca_b200_stats 
 #define FLUCA_B200_KT_RHS_PROJECT 6
 #define FLUCA_B200_KT_OUTER 7
 #define FLUCA_B200_KT_HALO 8
-#define FLUCA_B200_KT_NCLASS 9
+#define FLUCA_B200_KT_IBM 9          /* marker interpolation / spreading */
+#define FLUCA_B200_KT_NCLASS 10
 int fluca_b200_kernel_timing(fluca_b200_solver *s, int enable);
 /* accumulated milliseconds and launch counts per class since the last reset */
 int fluca_b200_kernel_times(fluca_b200_solver *s, double ms[FLUCA_B200_KT_NCLASS], long counts[FLUCA_B200_KT_NCLASS], int reset);

@@ -96,6 +96,15 @@ void orc_abf_apply(Orc *o, const OrcOptions *opt, const double *b, double *x, Or
 /* 1-D stencil formulas of cartdiscret.c, by name, on an explicit coordinate tuple; returns ncols */
 int orc_formula(const char *name, const double *xs, double h, double vf, double w[4], int off[4]);
 
+/* ---- immersed boundary: NOT a restatement (the reference has no IBM code); it defines the
+ * direct-forcing coupling the CUDA path implements (see the IBM section of src/ns.c).  PARITY UNPINNED.
+ * X, Ud, Um, F: dim consecutive blocks of n; dV: n.  npts: 4 (Peskin) or 3 (Roma). */
+void orc_set_markers(Orc *o, long n, const double *X, const double *Ud, const double *dV, int npts);
+void orc_set_ibm_iterations(Orc *o, int n); /* multi-direct forcing passes per step (default 1) */
+void orc_ibm_interpolate(const Orc *o, const double *v, double *Um);
+void orc_ibm_spread(const Orc *o, const double *Fm, double *f); /* f += spread(Fm * dV / vol) */
+void orc_get_marker_forces(const Orc *o, double *F, double *Um); /* of the last step; either may be NULL */
+
 /* built-in BC callbacks for timing runs (ctx = double[3] constant value) */
 int orc_bc_constant(int dim, double t, const double x[], double val[], void *ctx);
 /* pressure flavour: ctx = double[1] */

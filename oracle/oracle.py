@@ -94,6 +94,11 @@ def lib():
         L.orc_abf_apply.argtypes = [C.c_void_p, C.POINTER(OrcOptions), C.c_void_p, C.c_void_p, C.POINTER(OrcStepInfo)]
         L.orc_formula.restype = C.c_int
         L.orc_formula.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.orc_set_markers.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_set_ibm_iterations.argtypes = [C.c_void_p, C.c_int]
+        L.orc_ibm_interpolate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_ibm_spread.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_get_marker_forces.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -279,6 +284,34 @@ class Oracle:
         i = np.ctypeslib.as_array(idx, shape=(max(nnz.value, 1),))[: nnz.value].copy()
         v = np.ctypeslib.as_array(val, shape=(max(nnz.value, 1),))[: nnz.value].copy()
         return sp.csr_matrix((v, i, p), shape=(nr.value, nc.value))
+
+    # ---- immersed boundary (defined by the oracle itself: the reference has none; parity unpinned) ----
+    def set_markers(self, X, Ud, dV, npts=4, iterations=1):
+        """X, Ud: (dim, n); dV: (n,)."""
+        X = np.ascontiguousarray(X, dtype=np.float64).reshape(self.dim, -1)
+        Ud = np.ascontiguousarray(Ud, dtype=np.float64).reshape(self.dim, -1)
+        dV = np.ascontiguousarray(dV, dtype=np.float64).ravel()
+        self.nm = X.shape[1]
+        assert Ud.shape == X.shape and dV.shape == (self.nm,)
+        lib().orc_set_markers(self._h, self.nm, X.ctypes.data, Ud.ctypes.data, dV.ctypes.data, int(npts))
+        lib().orc_set_ibm_iterations(self._h, int(iterations))
+
+    def ibm_interpolate(self, v):
+        v = np.ascontiguousarray(v, dtype=np.float64).reshape(self.dim, *self.cell_shape)
+        Um = np.zeros((self.dim, self.nm))
+        lib().orc_ibm_interpolate(self._h, v.ctypes.data, Um.ctypes.data)
+        return Um
+
+    def ibm_spread(self, Fm):
+        Fm = np.ascontiguousarray(Fm, dtype=np.float64).reshape(self.dim, self.nm)
+        f = np.zeros((self.dim,) + self.cell_shape)
+        lib().orc_ibm_spread(self._h, Fm.ctypes.data, f.ctypes.data)
+        return f
+
+    def marker_forces(self):
+        F, Um = np.zeros((self.dim, self.nm)), np.zeros((self.dim, self.nm))
+        lib().orc_get_marker_forces(self._h, F.ctypes.data, Um.ctypes.data)
+        return F, Um
 
     # split / join a solution-sized vector into (v, [U_d], p) views
     def split(self, x: np.ndarray):

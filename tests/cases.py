@@ -208,3 +208,24 @@ def make_oracle_fast(case):
         cv = getattr(b["velocity"], "const", None) if b["velocity"] is not None else None
         bcs.append(O.BC(b["type"], velocity=b["velocity"], pressure=b["pressure"], const_velocity=cv))
     return O.Oracle(case.n, case.faces(), case.rho, case.mu, case.dt, bcs)
+
+
+# ------------------------------------------------------------------ immersed-boundary marker sets
+def cylinder_markers(centre, D, n, h, Ud=(0.0, 0.0), npts=4):
+    """n markers equally spaced in angle on a circle (BASELINE config 2: theta_k = 2 pi k / n, SURVEY.md 8d);
+    volume weight = arc length x h."""
+    th = 2 * np.pi * np.arange(n) / n
+    X = np.stack([centre[0] + 0.5 * D * np.cos(th), centre[1] + 0.5 * D * np.sin(th)])
+    dV = np.full(n, np.pi * D / n * h)
+    return dict(X=X, Ud=np.tile(np.asarray(Ud, dtype=float)[:, None], (1, n)), dV=dV, npts=npts)
+
+
+def sphere_markers(centre, D, n, h, Ud=(0.0, 0.0, 0.0), npts=4):
+    """n markers on a Fibonacci-sphere lattice (BASELINE configs 4 and 5); volume weight = area / n x h."""
+    k = np.arange(n) + 0.5
+    z = 1.0 - 2.0 * k / n
+    r = np.sqrt(np.maximum(0.0, 1.0 - z * z))
+    ph = np.pi * (1.0 + 5.0**0.5) * k
+    X = np.stack([centre[0] + 0.5 * D * r * np.cos(ph), centre[1] + 0.5 * D * r * np.sin(ph), centre[2] + 0.5 * D * z])
+    dV = np.full(n, np.pi * D * D / n * h)
+    return dict(X=X, Ud=np.tile(np.asarray(Ud, dtype=float)[:, None], (1, n)), dV=dV, npts=npts)

@@ -68,13 +68,16 @@ def set_initial(ns, state):
     fb.NSSetSolutionSubVector(ns, fb.NS_FIELD_PRESSURE, p)
 
 
-def compare_steps(case, library=None, mode="coupled", nsteps=2, seed=None, tol=1e-10, ptol=None):
+def compare_steps(case, library=None, mode="coupled", nsteps=2, seed=None, tol=1e-10, ptol=None, markers=None):
     """K steps on both sides at tight tolerances; returns the per-step relative L2 differences."""
     orc = cases.make_oracle(case)
     state = case.initial_state(seed=seed)
     orc.set_state(*state)
     ns = make_ns(case, library, mode, **TIGHT)
     set_initial(ns, state)
+    if markers is not None:  # immersed boundary: the same marker list on both sides
+        orc.set_markers(markers["X"], markers["Ud"], markers["dV"], markers.get("npts", 4), markers.get("iterations", 1))
+        fb.NSB200SetMarkers(ns, markers["X"], markers["Ud"], markers["dV"], markers.get("npts", 4), markers.get("iterations", 1))
     out = []
     oopt = O.default_options(mode=0 if mode == "coupled" else 1, **ORC_TIGHT)
     for _ in range(nsteps):
@@ -84,6 +87,10 @@ def compare_steps(case, library=None, mode="coupled", nsteps=2, seed=None, tol=1
         a, b = orc.get_state(), fb.NSB200GetSolver(ns).get_state()
         ev, eU, ep, eh = rel(b["v"], a["v"]), relU(b["U"], a["U"]), rel(b["p"], a["p"]), rel(b["phalf"], a["phalf"])
         out.append(dict(v=ev, U=eU, p=ep, phalf=eh, outer=(st.outer_its, oi.outer_its), hist_gpu=[st.hist[i] for i in range(st.nhist)], hist_orc=[oi.hist[i] for i in range(oi.nhist)], mom=st.mom_its, schur=st.schur_its))
+        if markers is not None:
+            (Fo, Uo), (Fg, Ug) = orc.marker_forces(), fb.NSB200GetMarkerForces(ns)
+            out[-1]["F"], out[-1]["Um"] = rel(Fg, Fo), rel(Ug, Uo)
+            assert out[-1]["F"] <= 100 * tol and out[-1]["Um"] <= tol, (case.name, mode, out[-1])
         assert ev <= tol and eU <= tol, (case.name, mode, out[-1])
         assert ep <= (ptol or 10 * tol) and eh <= (ptol or 10 * tol), (case.name, mode, out[-1])
     fb.NSDestroy(ns)
