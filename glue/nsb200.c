@@ -1,0 +1,551 @@
+/*
+ * glue/nsb200.c -- NS type "b200": the reference-side binding of libfluca_b200.so.
+ *
+ * This translation unit belongs in the reference tree (fluca/src/ns/impl/b200/nsb200.c); it is plain
+ * C on PETSc like every other file there and holds NO arithmetic: fields live on the GPU, all operators are
+ * CUDA kernels behind include/fluca_b200.h.  It fills the nine NSOps of the reference's type interface
+ * (fluca/include/fluca/private/nsimpl.h:21-31; model: NSCreate_CNLinear, fluca/src/ns/impl/linearcn/cnlinear.c:164-187)
+ * and is registered with NSRegister (fluca/include/flucans.h:92), so apps select it with -ns_type b200.
+ *
+ * PETSc, MPI, HDF5 and CGNS are not installed in the build image of this repository, so this file
+ * cannot be compiled there; tests/test_glue_syntax.py compiles it against a declaration-only stub of the PETSc /
+ * Fluca API subset it uses (tests/petsc_stub/).  INTEGRATION.md shows the build line for a real PETSc tree.
+ *
+ * What stays on the host, as in the reference: options (nsopts.c:179-194), the time loop and failure policy
+ * (nsbasic.c:276-351), monitors, CGNS output of ns->sol (nssol.c:130-204), evaluation of the user's boundary
+ * callbacks (flucansbc.h:14).  Decomposition: 1 MPI rank <-> 1 GPU, z-slabs (-cart_ranks_x 1 -cart_ranks_y 1
+ * -cart_ranks_z P), NCCL bootstrapped by broadcasting the unique id over the NS communicator.
+ */
+#include <fluca/private/nsimpl.h>
+#include <flucameshcart.h>
+#include <flucaviewer.h>
+#include <petscdmstag.h>
+#include <fluca_b200.h>
+
+#define NSB200 "b200"
+
+typedef struct {
+  fluca_b200_solver *solver;
+  Vec                phalf;        /* "PressureHalfStep", restart-compatible with cnlinear (cnlinear.c:54,146-162) */
+  /* options */
+  PetscInt  mode;                  /* 0 coupled (reference default semantics), 1 fractional (one PCApply_ABF) */
+  PetscInt  restart, outer_maxit, inner_maxit;
+  PetscReal outer_rtol, mom_rtol, schur_rtol;
+  PetscInt  sync_interval;         /* download ns->sol every k steps (1 = every step; 0 = only on demand) */
+  /* geometry of this rank's slab */
+  PetscInt dim, M, N, P, k0, nzl;
+  PetscBool lastz, per[3];
+  /* host staging in the C-ABI layout (pinned by PETSc's allocator is not required) */
+  double *hv, *hU[3], *hp, *hph, *hbc;
+  size_t  ncell, nface[3];
+  /* coherence between ns->sol (host) and the device state */
+  PetscObjectState solstate;
+  PetscBool        device_current, host_current;
+  fluca_b200_stats stats;
+} NS_B200;
+
+#define B200Call(ns, call) \
+  do { \
+    int rc_ = (call); \
+    PetscCheck(rc_ == FLUCA_B200_OK, PetscObjectComm((PetscObject)(ns)), PETSC_ERR_LIB, "fluca_b200: %s", fluca_b200_last_error()); \
+  } while (0)
+
+/* ------------------------------------------------------------------ DMStag <-> C-ABI layout
+ * Per-element entry order and the extra faces of the last rank are DMStag's business: everything goes through
+ * DMStagVecGetArray + DMStagGetLocationSlot (SURVEY.md 8b "do not assume raw DMStag global ordering"). */
+static PetscErrorCode B200Upload_Private(DM dm, Vec g, DMStagStencilLocation loc, PetscInt c, PetscInt ex, PetscInt ey, PetscInt ez, double *host)
+{
+  PetscInt x, y, z, m, n, p, dim, slot, i, j, k;
+  Vec      l;
+
+  PetscFunctionBegin;
+  PetscCall(DMGetDimension(dm, &dim));
+  PetscCall(DMStagGetCorners(dm, &x, &y, &z, &m, &n, &p, NULL, NULL, NULL));
+  PetscCall(DMStagGetLocationSlot(dm, loc, c, &slot));
+  PetscCall(DMGetLocalVector(dm, &l));
+  PetscCall(DMGlobalToLocal(dm, g, INSERT_VALUES, l));
+  if (dim == 2) {
+    const PetscScalar ***a;
+    PetscCall(DMStagVecGetArrayRead(dm, l, &a));
+    for (j = 0; j < n + ey; ++j)
+      for (i = 0; i < m + ex; ++i) host[i + (size_t)(m + ex) * j] = PetscRealPart(a[y + j][x + i][slot]);
+    PetscCall(DMStagVecRestoreArrayRead(dm, l, &a));
+  } else {
+    const PetscScalar ****a;
+    PetscCall(DMStagVecGetArrayRead(dm, l, &a));
+    for (k = 0; k < p + ez; ++k)
+      for (j = 0; j < n + ey; ++j)
+        for (i = 0; i < m + ex; ++i) host[i + (size_t)(m + ex) * (j + (size_t)(n + ey) * k)] = PetscRealPart(a[z + k][y + j][x + i][slot]);
+    PetscCall(DMStagVecRestoreArrayRead(dm, l, &a));
+  }
+  PetscCall(DMRestoreLocalVector(dm, &l));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+/* One local round trip per slot: this runs only when a host observer needs ns->sol, so clarity wins.  The slots of
+ * one Vec are accumulated with ADD_VALUES (every entry is owned by exactly one rank): the caller zeroes the Vec first. */
+static PetscErrorCode B200Download_Private(DM dm, Vec g, DMStagStencilLocation loc, PetscInt c, PetscInt ex, PetscInt ey, PetscInt ez, const double *host)
+{
+  PetscInt x, y, z, m, n, p, dim, slot, i, j, k;
+  Vec      l;
+
+  PetscFunctionBegin;
+  PetscCall(DMGetDimension(dm, &dim));
+  PetscCall(DMStagGetCorners(dm, &x, &y, &z, &m, &n, &p, NULL, NULL, NULL));
+  PetscCall(DMStagGetLocationSlot(dm, loc, c, &slot));
+  PetscCall(DMGetLocalVector(dm, &l));
+  PetscCall(VecZeroEntries(l));
+  if (dim == 2) {
+    PetscScalar ***a;
+    PetscCall(DMStagVecGetArray(dm, l, &a));
+    for (j = 0; j < n + ey; ++j)
+      for (i = 0; i < m + ex; ++i) a[y + j][x + i][slot] = host[i + (size_t)(m + ex) * j];
+    PetscCall(DMStagVecRestoreArray(dm, l, &a));
+  } else {
+    PetscScalar ****a;
+    PetscCall(DMStagVecGetArray(dm, l, &a));
+    for (k = 0; k < p + ez; ++k)
+      for (j = 0; j < n + ey; ++j)
+        for (i = 0; i < m + ex; ++i) a[z + k][y + j][x + i][slot] = host[i + (size_t)(m + ex) * (j + (size_t)(n + ey) * k)];
+    PetscCall(DMStagVecRestoreArray(dm, l, &a));
+  }
+  PetscCall(DMLocalToGlobal(dm, l, ADD_VALUES, g));
+  PetscCall(DMRestoreLocalVector(dm, &l));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+static const DMStagStencilLocation B200FaceLoc[3] = {DMSTAG_LEFT, DMSTAG_DOWN, DMSTAG_BACK};
+
+static PetscErrorCode B200HostToDevice_Private(NS ns)
+{
+  NS_B200 *b = (NS_B200 *)ns->data;
+  DM       sdm, vdm, Sdm;
+  Vec      v, V, p;
+  PetscInt d;
+
+  PetscFunctionBegin;
+  PetscCall(MeshGetDM(ns->mesh, MESH_DM_SCALAR, &sdm));
+  PetscCall(MeshGetDM(ns->mesh, MESH_DM_VECTOR, &vdm));
+  PetscCall(MeshGetDM(ns->mesh, MESH_DM_STAG_SCALAR, &Sdm));
+  PetscCall(NSGetSolutionSubVector(ns, NS_FIELD_VELOCITY, &v));
+  PetscCall(NSGetSolutionSubVector(ns, NS_FIELD_FACE_NORMAL_VELOCITY, &V));
+  PetscCall(NSGetSolutionSubVector(ns, NS_FIELD_PRESSURE, &p));
+  for (d = 0; d < b->dim; ++d) PetscCall(B200Upload_Private(vdm, v, DMSTAG_ELEMENT, d, 0, 0, 0, b->hv + b->ncell * d));
+  for (d = 0; d < b->dim; ++d) PetscCall(B200Upload_Private(Sdm, V, B200FaceLoc[d], 0, d == 0 && !b->per[0], d == 1 && !b->per[1], d == 2 && b->lastz, b->hU[d]));
+  PetscCall(B200Upload_Private(sdm, p, DMSTAG_ELEMENT, 0, 0, 0, 0, b->hp));
+  PetscCall(B200Upload_Private(sdm, b->phalf, DMSTAG_ELEMENT, 0, 0, 0, 0, b->hph));
+  PetscCall(NSRestoreSolutionSubVector(ns, NS_FIELD_VELOCITY, &v));
+  PetscCall(NSRestoreSolutionSubVector(ns, NS_FIELD_FACE_NORMAL_VELOCITY, &V));
+  PetscCall(NSRestoreSolutionSubVector(ns, NS_FIELD_PRESSURE, &p));
+  {
+    const double *U[3] = {b->hU[0], b->hU[1], b->hU[2]};
+    B200Call(ns, fluca_b200_set_state(b->solver, b->hv, U, b->hp, b->hph));
+  }
+  b->device_current = PETSC_TRUE;
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+static PetscErrorCode B200DeviceToHost_Private(NS ns)
+{
+  NS_B200 *b = (NS_B200 *)ns->data;
+  DM       sdm, vdm, Sdm;
+  Vec      v, V, p;
+  PetscInt d;
+
+  PetscFunctionBegin;
+  {
+    double *U[3] = {b->hU[0], b->hU[1], b->hU[2]};
+    B200Call(ns, fluca_b200_get_state(b->solver, b->hv, U, b->hp, b->hph));
+  }
+  PetscCall(MeshGetDM(ns->mesh, MESH_DM_SCALAR, &sdm));
+  PetscCall(MeshGetDM(ns->mesh, MESH_DM_VECTOR, &vdm));
+  PetscCall(MeshGetDM(ns->mesh, MESH_DM_STAG_SCALAR, &Sdm));
+  PetscCall(NSGetSolutionSubVector(ns, NS_FIELD_VELOCITY, &v));
+  PetscCall(NSGetSolutionSubVector(ns, NS_FIELD_FACE_NORMAL_VELOCITY, &V));
+  PetscCall(NSGetSolutionSubVector(ns, NS_FIELD_PRESSURE, &p));
+  PetscCall(VecZeroEntries(v));
+  PetscCall(VecZeroEntries(V));
+  PetscCall(VecZeroEntries(p));
+  PetscCall(VecZeroEntries(b->phalf));
+  for (d = 0; d < b->dim; ++d) PetscCall(B200Download_Private(vdm, v, DMSTAG_ELEMENT, d, 0, 0, 0, b->hv + b->ncell * d));
+  for (d = 0; d < b->dim; ++d) PetscCall(B200Download_Private(Sdm, V, B200FaceLoc[d], 0, d == 0 && !b->per[0], d == 1 && !b->per[1], d == 2 && b->lastz, b->hU[d]));
+  PetscCall(B200Download_Private(sdm, p, DMSTAG_ELEMENT, 0, 0, 0, 0, b->hp));
+  PetscCall(B200Download_Private(sdm, b->phalf, DMSTAG_ELEMENT, 0, 0, 0, 0, b->hph));
+  PetscCall(NSRestoreSolutionSubVector(ns, NS_FIELD_VELOCITY, &v));
+  PetscCall(NSRestoreSolutionSubVector(ns, NS_FIELD_FACE_NORMAL_VELOCITY, &V));
+  PetscCall(NSRestoreSolutionSubVector(ns, NS_FIELD_PRESSURE, &p));
+  PetscCall(PetscObjectStateGet((PetscObject)ns->sol, &b->solstate));
+  b->host_current = PETSC_TRUE;
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+/* ------------------------------------------------------------------ boundary callbacks -> boundary planes
+ * The user's NSBoundaryConditionFunction (flucansbc.h:14) is an arbitrary host function of (t, x): evaluate it at the
+ * boundary-face centres of this rank's slab, at the times the step needs (cnlinearcart3d.c:2967-3033), and upload. */
+static PetscErrorCode B200UploadBoundaryData_Private(NS ns)
+{
+  NS_B200            *b = (NS_B200 *)ns->data;
+  const PetscScalar **ax, **ay, **az = NULL;
+  PetscInt            iprev, ielem, x, y, z, m, n, p, bnd, slot, i, j, c;
+  DM                  sdm;
+  const PetscReal     tq = ns->step == 0 ? ns->t : ns->t - 0.5 * ns->dt;
+
+  PetscFunctionBegin;
+  PetscCall(MeshGetDM(ns->mesh, MESH_DM_SCALAR, &sdm));
+  PetscCall(DMStagGetCorners(sdm, &x, &y, &z, &m, &n, &p, NULL, NULL, NULL));
+  PetscCall(DMStagGetProductCoordinateArraysRead(sdm, &ax, &ay, &az));
+  PetscCall(DMStagGetProductCoordinateLocationSlot(sdm, DMSTAG_LEFT, &iprev));
+  PetscCall(DMStagGetProductCoordinateLocationSlot(sdm, DMSTAG_ELEMENT, &ielem));
+  if (b->dim == 2) p = 1, z = 0;
+  for (bnd = 0; bnd < 2 * b->dim; ++bnd) {
+    const NSBoundaryCondition *bc = &ns->bcs[bnd];
+    const PetscInt d = bnd / 2, side = bnd % 2;
+    const PetscInt n0 = d == 0 ? n : m, n1 = d == 2 ? n : p; /* fastest, slowest extent of the plane */
+    const PetscInt gl[3] = {b->M, b->N, b->P};
+    const size_t   np = (size_t)n0 * n1;
+    if (bc->type != NS_BC_VELOCITY && bc->type != NS_BC_PRESSURE_OUTLET) continue;
+    for (slot = 0; slot < 2; ++slot) {
+      const PetscReal t = bc->type == NS_BC_VELOCITY ? (slot ? ns->t + ns->dt : ns->t) : (slot ? ns->t + 0.5 * ns->dt : tq);
+      for (j = 0; j < n1; ++j)
+        for (i = 0; i < n0; ++i) {
+          PetscReal   xb[3] = {0., 0., 0.};
+          PetscScalar val[3] = {0., 0., 0.};
+          PetscInt    ci[3];
+          /* plane coordinates: x boundaries [k][j], y boundaries [k][i], z boundaries [j][i] (include/fluca_b200.h) */
+          ci[0] = d == 0 ? 0 : x + i;
+          ci[1] = d == 0 ? y + i : (d == 1 ? 0 : y + j);
+          ci[2] = d == 2 ? 0 : z + j;
+          xb[0] = d == 0 ? ax[side ? gl[0] : 0][iprev] : ax[ci[0]][ielem];
+          xb[1] = d == 1 ? ay[side ? gl[1] : 0][iprev] : ay[ci[1]][ielem];
+          if (b->dim == 3) xb[2] = d == 2 ? az[side ? gl[2] : 0][iprev] : az[ci[2]][ielem];
+          if (bc->type == NS_BC_VELOCITY) {
+            PetscCall(bc->velocity(b->dim, t, xb, val, bc->ctx_velocity));
+            for (c = 0; c < b->dim; ++c) b->hbc[c * np + i + (size_t)n0 * j] = PetscRealPart(val[c]);
+          } else {
+            PetscCall(bc->pressure(b->dim, t, xb, val, bc->ctx_pressure));
+            b->hbc[i + (size_t)n0 * j] = PetscRealPart(val[0]);
+          }
+        }
+      if (bc->type == NS_BC_VELOCITY) B200Call(ns, fluca_b200_set_boundary_velocity(b->solver, (int)bnd, (int)slot, b->hbc));
+      else B200Call(ns, fluca_b200_set_boundary_pressure(b->solver, (int)bnd, (int)slot, b->hbc));
+    }
+  }
+  PetscCall(DMStagRestoreProductCoordinateArraysRead(sdm, &ax, &ay, &az));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+/* ------------------------------------------------------------------ NSOps */
+static PetscErrorCode NSSetFromOptions_B200(NS ns, PetscOptionItems PetscOptionsObject)
+{
+  NS_B200 *b = (NS_B200 *)ns->data;
+
+  PetscFunctionBegin;
+  PetscOptionsHeadBegin(PetscOptionsObject, "NSB200 Options"); /* pattern: cnlinear.c:5-12 */
+  PetscCall(PetscOptionsInt("-ns_b200_mode", "0: coupled solve, PC = ABF (reference default); 1: one ABF application (classical fractional step)", "", b->mode, &b->mode, NULL));
+  PetscCall(PetscOptionsInt("-ns_b200_gmres_restart", "restart of the outer GMRES ((restart + 1) x 7 fields of device memory)", "", b->restart, &b->restart, NULL));
+  PetscCall(PetscOptionsReal("-ns_b200_outer_rtol", "outer relative tolerance (nssol.c:24 sets 1e-5)", "", b->outer_rtol, &b->outer_rtol, NULL));
+  PetscCall(PetscOptionsReal("-ns_b200_momentum_rtol", "momentum solve relative tolerance", "", b->mom_rtol, &b->mom_rtol, NULL));
+  PetscCall(PetscOptionsReal("-ns_b200_schur_rtol", "pressure solve relative tolerance", "", b->schur_rtol, &b->schur_rtol, NULL));
+  PetscCall(PetscOptionsInt("-ns_b200_sync_interval", "copy the device state into ns->sol every k steps (0: only for viewers)", "", b->sync_interval, &b->sync_interval, NULL));
+  PetscOptionsHeadEnd();
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+/* NSSetUp builds a MatNest J and calls formjacobian(INIT) before ops->setup, then MatCreateVecs(J) (nsbasic.c:203-208).
+ * A matrix-free type has nothing to assemble: identity placeholders on the diagonal give J valid row/column layouts.
+ * The SNES / PCABF objects the base class builds on top of J are never used by ops->step. */
+static PetscErrorCode NSFormJacobian_B200(NS ns, Vec x, Mat J, NSFormJacobianType type)
+{
+  PetscFunctionBegin;
+  (void)x;
+  if (type == NS_INIT_JACOBIAN) {
+    const MeshDMType dmt[3] = {MESH_DM_VECTOR, MESH_DM_STAG_SCALAR, MESH_DM_SCALAR};
+    PetscInt         f;
+    for (f = 0; f < 3; ++f) {
+      DM       dm;
+      Mat      I;
+      PetscInt entries;
+      PetscCall(MeshGetDM(ns->mesh, dmt[f], &dm));
+      PetscCall(DMStagGetEntries(dm, &entries));
+      PetscCall(MatCreateConstantDiagonal(PetscObjectComm((PetscObject)ns), entries, entries, PETSC_DETERMINE, PETSC_DETERMINE, 1., &I));
+      PetscCall(MatNestSetSubMat(J, f, f, I));
+      PetscCall(MatDestroy(&I));
+    }
+    PetscCall(MatAssemblyBegin(J, MAT_FINAL_ASSEMBLY));
+    PetscCall(MatAssemblyEnd(J, MAT_FINAL_ASSEMBLY));
+  }
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+static PetscErrorCode NSSetup_B200(NS ns)
+{
+  NS_B200        *b = (NS_B200 *)ns->data;
+  MPI_Comm        comm;
+  PetscMPIInt     rank, size;
+  PetscInt        rx, ry, rz, x, y, z, m, n, p, d, nb, i, iprev;
+  PetscBool       iscart, lx, ly, lz;
+  MeshCartBoundaryType bt[3] = {MESHCART_BOUNDARY_NONE, MESHCART_BOUNDARY_NONE, MESHCART_BOUNDARY_NONE};
+  const PetscScalar **ax, **ay, **az = NULL;
+  double         *xf[3] = {NULL, NULL, NULL};
+  fluca_b200_desc desc;
+  fluca_b200_comm *gcomm = NULL;
+
+  PetscFunctionBegin;
+  PetscCall(PetscObjectGetComm((PetscObject)ns, &comm));
+  PetscCallMPI(MPI_Comm_rank(comm, &rank));
+  PetscCallMPI(MPI_Comm_size(comm, &size));
+  PetscCall(PetscObjectTypeCompare((PetscObject)ns->mesh, MESHCART, &iscart));
+  PetscCheck(iscart, comm, PETSC_ERR_ARG_WRONG, "Unsupported Mesh type");
+  PetscCall(MeshGetDimension(ns->mesh, &b->dim));
+  PetscCall(MeshCartGetGlobalSizes(ns->mesh, &b->M, &b->N, &b->P));
+  PetscCall(MeshCartGetNumRanks(ns->mesh, &rx, &ry, &rz));
+  PetscCheck(rx == 1 && ry == 1, comm, PETSC_ERR_SUP, "NS type b200 partitions the mesh in z-slabs: run with -cart_ranks_x 1 -cart_ranks_y 1 -cart_ranks_z <ranks>");
+  PetscCheck(b->dim == 3 || size == 1, comm, PETSC_ERR_SUP, "2-D meshes run on one rank");
+  PetscCall(MeshCartGetCorners(ns->mesh, &x, &y, &z, &m, &n, &p));
+  PetscCall(MeshCartGetIsLastRank(ns->mesh, &lx, &ly, &lz));
+  PetscCall(MeshCartGetBoundaryTypes(ns->mesh, &bt[0], &bt[1], &bt[2]));
+  for (d = 0; d < 3; ++d) b->per[d] = (PetscBool)(d < b->dim && bt[d] == MESHCART_BOUNDARY_PERIODIC);
+  b->k0    = b->dim == 3 ? z : 0;
+  b->nzl   = b->dim == 3 ? p : 1;
+  b->lastz = (PetscBool)(b->dim == 3 && lz && !b->per[2]);
+
+  /* global face coordinates per direction (slot PREV; cart.c:56-151): every rank holds x and y fully; z is gathered */
+  PetscCall(MeshCartGetCoordinateArraysRead(ns->mesh, &ax, &ay, &az));
+  PetscCall(MeshCartGetCoordinateLocationSlot(ns->mesh, MESHCART_PREV, &iprev));
+  PetscCall(PetscMalloc1(b->M + 1, &xf[0]));
+  PetscCall(PetscMalloc1(b->N + 1, &xf[1]));
+  for (i = 0; i <= b->M; ++i) xf[0][i] = PetscRealPart(ax[i][iprev]);
+  for (i = 0; i <= b->N; ++i) xf[1][i] = PetscRealPart(ay[i][iprev]);
+  if (b->dim == 3) {
+    PetscCall(PetscCalloc1(b->P + 1, &xf[2]));
+    for (i = z; i < z + p + (lz ? 1 : 0); ++i) xf[2][i] = PetscRealPart(az[i][iprev]);
+    if (b->per[2] && lz) xf[2][b->P] = PetscRealPart(az[b->P][iprev]);
+    PetscCallMPI(MPI_Allreduce(MPI_IN_PLACE, xf[2], (PetscMPIInt)(b->P + 1), MPI_DOUBLE, MPI_SUM, comm)); /* every face is owned by one rank */
+  }
+  PetscCall(MeshCartRestoreCoordinateArraysRead(ns->mesh, &ax, &ay, &az));
+
+  PetscCall(PetscMemzero(&desc, sizeof(desc)));
+  desc.dim  = (int)b->dim;
+  desc.n[0] = (int)b->M, desc.n[1] = (int)b->N, desc.n[2] = (int)(b->dim == 3 ? b->P : 1);
+  for (d = 0; d < b->dim; ++d) desc.xf[d] = xf[d];
+  PetscCall(MeshGetNumberBoundaries(ns->mesh, &nb));
+  for (i = 0; i < nb; ++i) desc.bc_type[i] = (int)ns->bcs[i].type; /* same numeric values (flucansbc.h:5-11) */
+  desc.rho = ns->rho, desc.mu = ns->mu, desc.dt = ns->dt;          /* baked in at setup, like the reference */
+  desc.k0 = (int)b->k0, desc.nzl = (int)b->nzl;
+  desc.mode          = (int)b->mode;
+  desc.outer_rtol    = b->outer_rtol;
+  desc.outer_restart = (int)b->restart;
+  desc.mom_rtol      = b->mom_rtol;
+  desc.schur_rtol    = b->schur_rtol;
+
+  if (size > 1) { /* NCCL over the GPUs of the box: rank 0 makes the id, MPI ships it */
+    char id[256];
+    int  nbytes = 0;
+    if (rank == 0) B200Call(ns, fluca_b200_comm_unique_id(id, (int)sizeof(id), &nbytes));
+    PetscCallMPI(MPI_Bcast(&nbytes, 1, MPI_INT, 0, comm));
+    PetscCallMPI(MPI_Bcast(id, nbytes, MPI_BYTE, 0, comm));
+    B200Call(ns, fluca_b200_comm_create_nccl(id, nbytes, (int)rank, (int)size, &gcomm));
+  }
+  B200Call(ns, fluca_b200_create(&desc, gcomm, &b->solver));
+  for (d = 0; d < 3; ++d) PetscCall(PetscFree(xf[d]));
+
+  b->ncell    = (size_t)m * n * b->nzl;
+  b->nface[0] = (size_t)(m + (b->per[0] ? 0 : 1)) * n * b->nzl;
+  b->nface[1] = (size_t)m * (n + (b->per[1] ? 0 : 1)) * b->nzl;
+  b->nface[2] = b->dim == 3 ? (size_t)m * n * (b->nzl + (b->lastz ? 1 : 0)) : 0;
+  PetscCall(PetscMalloc1(b->ncell * b->dim, &b->hv));
+  for (d = 0; d < b->dim; ++d) PetscCall(PetscMalloc1(b->nface[d], &b->hU[d]));
+  PetscCall(PetscMalloc1(b->ncell, &b->hp));
+  PetscCall(PetscMalloc1(b->ncell, &b->hph));
+  {
+    size_t big = (size_t)PetscMax(PetscMax(m * n, m * b->nzl), n * b->nzl);
+    PetscCall(PetscMalloc1(big * 3, &b->hbc));
+  }
+  PetscCall(MeshCreateGlobalVector(ns->mesh, MESH_DM_SCALAR, &b->phalf));
+  PetscCall(PetscObjectSetName((PetscObject)b->phalf, "PressureHalfStep"));
+  b->device_current = PETSC_FALSE;
+  b->host_current   = PETSC_TRUE;
+  b->solstate       = -1;
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+static PetscErrorCode NSStep_B200(NS ns)
+{
+  NS_B200         *b = (NS_B200 *)ns->data;
+  PetscObjectState st;
+  int              rc;
+
+  PetscFunctionBegin;
+  /* initial conditions, restarts and user edits arrive through the host Vec (cavity_flow_2d.c:74-75,
+     taylor_green_vortex.c:113-178, nssol.c:191-196): upload when ns->sol changed since the last download */
+  PetscCall(PetscObjectStateGet((PetscObject)ns->sol, &st));
+  if (!b->device_current || st != b->solstate) PetscCall(B200HostToDevice_Private(ns));
+  PetscCall(B200UploadBoundaryData_Private(ns));
+
+  rc = fluca_b200_step(b->solver, (double)ns->t, (int)ns->step, &b->stats);
+  if (rc == FLUCA_B200_ERR_DIVERGED) {
+    ns->reason = NS_DIVERGED_NONLINEAR_SOLVE; /* NSCheckDiverged (nsbasic.c:425-436); NSStep applies the failure policy (:293-297) */
+    PetscFunctionReturn(PETSC_SUCCESS);
+  }
+  PetscCheck(rc == FLUCA_B200_OK, PetscObjectComm((PetscObject)ns), PETSC_ERR_LIB, "fluca_b200: %s", fluca_b200_last_error());
+  PetscCall(PetscInfo(ns, "b200 step %" PetscInt_FMT ": outer its %d, momentum its %d, Schur its %d, ABF applications %d, |r|/|r0| %g\n", ns->step, b->stats.outer_its, b->stats.mom_its, b->stats.schur_its, b->stats.abf_applies, b->stats.outer_rnorm0 > 0 ? b->stats.outer_rnorm / b->stats.outer_rnorm0 : 0.));
+
+  b->host_current = PETSC_FALSE;
+  if (b->sync_interval > 0 && (ns->step + 1) % b->sync_interval == 0) PetscCall(B200DeviceToHost_Private(ns));
+  else PetscCall(PetscObjectStateGet((PetscObject)ns->sol, &b->solstate)); /* the base class copied sol -> sol0 only */
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+/* right-hand side b = (r_mom, r_int, r_con) of the current step, for callers of NSFormFunction */
+static PetscErrorCode NSFormFunction_B200(NS ns, Vec x, Vec f)
+{
+  NS_B200 *b = (NS_B200 *)ns->data;
+  DM       sdm, vdm, Sdm;
+  IS       vis, Vis, pis;
+  Vec      fv, fV, fp;
+  PetscInt d;
+
+  PetscFunctionBegin;
+  (void)x; /* the system is linear and the guess is zero (nsbasic.c:146-151): F(0) = -b */
+  if (!b->device_current) PetscCall(B200HostToDevice_Private(ns));
+  PetscCall(B200UploadBoundaryData_Private(ns));
+  B200Call(ns, fluca_b200_prepare_step(b->solver, (double)ns->t, (int)ns->step));
+  {
+    double *U[3] = {b->hU[0], b->hU[1], b->hU[2]};
+    B200Call(ns, fluca_b200_get_rhs(b->solver, b->hv, U, b->hp));
+  }
+  PetscCall(MeshGetDM(ns->mesh, MESH_DM_SCALAR, &sdm));
+  PetscCall(MeshGetDM(ns->mesh, MESH_DM_VECTOR, &vdm));
+  PetscCall(MeshGetDM(ns->mesh, MESH_DM_STAG_SCALAR, &Sdm));
+  PetscCall(NSGetField(ns, NS_FIELD_VELOCITY, NULL, NULL, &vis));
+  PetscCall(NSGetField(ns, NS_FIELD_FACE_NORMAL_VELOCITY, NULL, NULL, &Vis));
+  PetscCall(NSGetField(ns, NS_FIELD_PRESSURE, NULL, NULL, &pis));
+  PetscCall(VecGetSubVector(f, vis, &fv));
+  PetscCall(VecGetSubVector(f, Vis, &fV));
+  PetscCall(VecGetSubVector(f, pis, &fp));
+  PetscCall(VecZeroEntries(fv));
+  PetscCall(VecZeroEntries(fV));
+  PetscCall(VecZeroEntries(fp));
+  for (d = 0; d < b->dim; ++d) PetscCall(B200Download_Private(vdm, fv, DMSTAG_ELEMENT, d, 0, 0, 0, b->hv + b->ncell * d));
+  for (d = 0; d < b->dim; ++d) PetscCall(B200Download_Private(Sdm, fV, B200FaceLoc[d], 0, d == 0 && !b->per[0], d == 1 && !b->per[1], d == 2 && b->lastz, b->hU[d]));
+  PetscCall(B200Download_Private(sdm, fp, DMSTAG_ELEMENT, 0, 0, 0, 0, b->hp));
+  PetscCall(VecScale(f, -1.)); /* FormFunction returns A x - b at x = 0 */
+  PetscCall(VecRestoreSubVector(f, vis, &fv));
+  PetscCall(VecRestoreSubVector(f, Vis, &fV));
+  PetscCall(VecRestoreSubVector(f, pis, &fp));
+  b->device_current = PETSC_FALSE; /* prepare_step rotated the device buffers: reload before the next step */
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+static PetscErrorCode NSDestroy_B200(NS ns)
+{
+  NS_B200 *b = (NS_B200 *)ns->data;
+  PetscInt d;
+
+  PetscFunctionBegin;
+  if (b->solver) B200Call(ns, fluca_b200_destroy(b->solver));
+  PetscCall(VecDestroy(&b->phalf));
+  PetscCall(PetscFree(b->hv));
+  for (d = 0; d < 3; ++d) PetscCall(PetscFree(b->hU[d]));
+  PetscCall(PetscFree(b->hp));
+  PetscCall(PetscFree(b->hph));
+  PetscCall(PetscFree(b->hbc));
+  PetscCall(PetscFree(ns->data));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+static PetscErrorCode NSView_B200(NS ns, PetscViewer viewer)
+{
+  NS_B200  *b = (NS_B200 *)ns->data;
+  PetscBool isascii;
+
+  PetscFunctionBegin;
+  PetscCall(PetscObjectTypeCompare((PetscObject)viewer, PETSCVIEWERASCII, &isascii));
+  if (isascii) {
+    PetscCall(PetscViewerASCIIPrintf(viewer, "  b200: mode %s, slab planes [%" PetscInt_FMT ", %" PetscInt_FMT "), outer restart %" PetscInt_FMT "\n", b->mode ? "fractional" : "coupled", b->k0, b->k0 + b->nzl, b->restart));
+    PetscCall(PetscViewerASCIIPrintf(viewer, "  last step: outer %d, momentum %d, Schur %d iterations\n", b->stats.outer_its, b->stats.mom_its, b->stats.schur_its));
+  }
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+/* the base class views every field of ns->sol before calling this (nssol.c:130-175): refresh the host copy first.
+ * NSViewSolution has no pre-hook, so a run that writes output uses -ns_b200_sync_interval equal to its output interval. */
+static PetscErrorCode NSViewSolution_B200(NS ns, PetscViewer viewer)
+{
+  NS_B200 *b = (NS_B200 *)ns->data;
+
+  PetscFunctionBegin;
+  if (!b->host_current) PetscCall(B200DeviceToHost_Private(ns));
+  PetscCall(VecView(b->phalf, viewer)); /* cnlinear.c:146-152 */
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+static PetscErrorCode NSLoadSolution_B200(NS ns, PetscViewer viewer)
+{
+  NS_B200 *b = (NS_B200 *)ns->data;
+
+  PetscFunctionBegin;
+  PetscCall(FlucaVecLoad(b->phalf, viewer)); /* cnlinear.c:154-162 */
+  b->device_current = PETSC_FALSE;
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+PetscErrorCode NSCreate_B200(NS ns)
+{
+  NS_B200 *b;
+
+  PetscFunctionBegin;
+  PetscCall(PetscNew(&b));
+  ns->data = (void *)b;
+  b->mode          = FLUCA_B200_MODE_COUPLED;
+  b->restart       = 30;   /* PETSc's GMRES default */
+  b->outer_rtol    = 1e-5; /* nssol.c:22-25 */
+  b->mom_rtol      = 1e-5;
+  b->schur_rtol    = 1e-5;
+  b->sync_interval = 1;
+
+  ns->ops->setfromoptions = NSSetFromOptions_B200;
+  ns->ops->setup          = NSSetup_B200;
+  ns->ops->step           = NSStep_B200;
+  ns->ops->formjacobian   = NSFormJacobian_B200;
+  ns->ops->formfunction   = NSFormFunction_B200;
+  ns->ops->destroy        = NSDestroy_B200;
+  ns->ops->view           = NSView_B200;
+  ns->ops->viewsolution   = NSViewSolution_B200;
+  ns->ops->loadsolution   = NSLoadSolution_B200;
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+/* One line in NSRegisterAll (nsreg.c:13-20) ...                         NSRegister(NSB200, NSCreate_B200);
+ * ... or no change to the reference at all: ship this file as a shared library and run with
+ * -dll_append libfluca_nsb200.so ; PETSc calls this hook when it loads the library. */
+PETSC_EXTERN PetscErrorCode PetscDLLibraryRegister_fluca_nsb200(void)
+{
+  PetscFunctionBegin;
+  PetscCall(NSRegister(NSB200, NSCreate_B200));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+/* immersed-boundary markers of the b200 type (the reference only plans IBM: README.md:14, THEORY_GUIDE.md:130-132) */
+PetscErrorCode NSB200SetMarkers(NS ns, PetscInt n, const PetscReal X[], const PetscReal Ud[], const PetscReal dV[], PetscInt delta_points)
+{
+  NS_B200  *b;
+  PetscBool match;
+
+  PetscFunctionBegin;
+  PetscCall(PetscObjectTypeCompare((PetscObject)ns, NSB200, &match));
+  PetscCheck(match, PetscObjectComm((PetscObject)ns), PETSC_ERR_ARG_WRONG, "NS type is not b200");
+  PetscCheck(ns->setupcalled, PetscObjectComm((PetscObject)ns), PETSC_ERR_ARG_WRONGSTATE, "This function must be called after NSSetUp()");
+  b = (NS_B200 *)ns->data;
+  B200Call(ns, fluca_b200_set_markers(b->solver, (long)n, X, Ud, dV, (int)delta_points));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+PetscErrorCode NSB200GetMarkerForces(NS ns, PetscReal F[], PetscReal Um[])
+{
+  NS_B200 *b = (NS_B200 *)ns->data;
+
+  PetscFunctionBegin;
+  B200Call(ns, fluca_b200_get_marker_forces(b->solver, F, Um));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}

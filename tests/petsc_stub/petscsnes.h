@@ -1,0 +1,1 @@
+#include "petsc_fluca_stub.h"

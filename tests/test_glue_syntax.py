@@ -1,0 +1,26 @@
+"""The reference-side binding glue/nsb200.c (NS type "b200") cannot be compiled here for real -- PETSc, MPI and
+the Fluca headers it includes are absent from this image -- so it is compiled with `gcc -fsyntax-only` against a
+declaration-only stub of the API subset it uses (tests/petsc_stub/), with include/fluca_b200.h as the real header:
+every call into the C ABI is type-checked against the declarations the CUDA library exports."""
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_glue_compiles_against_the_api_stub():
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    r = subprocess.run([cc, "-std=gnu11", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-Wno-unused-parameter", "-I", os.path.join(ROOT, "tests", "petsc_stub"), "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "glue", "nsb200.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_glue_fills_every_ns_op_and_registers_the_type():
+    src = open(os.path.join(ROOT, "glue", "nsb200.c")).read()
+    for op in ("setfromoptions", "setup", "step", "formjacobian", "formfunction", "destroy", "view", "viewsolution", "loadsolution"):  # nsimpl.h:21-31
+        assert re.search(rf"ns->ops->{op}\s*=\s*NS\w+_B200;", src), op
+    assert 'NSRegister(NSB200, NSCreate_B200)' in src
+    # every C-ABI symbol the glue calls is declared in the public header
+    hdr = open(os.path.join(ROOT, "include", "fluca_b200.h")).read()
+    for sym in set(re.findall(r"\b(fluca_b200_\w+)\s*\(", src)):
+        assert re.search(rf"\b{sym}\s*\(", hdr), sym
