@@ -33,10 +33,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=0, help="cells per direction per GPU (default 256: BASELINE config 3)")
+    ap.add_argument("--workload", default="sphere", choices=["sphere", "cavity"], help="sphere: BASELINE config 4 (3-D IBM sphere Re=300, 512^3, 100k markers), the configuration the metric is quoted on; cavity: config 3 (256^3 lid-driven cavity, no IBM)")
+    ap.add_argument("--n", type=int, default=0, help="cells per direction per GPU (default: 512 sphere, 256 cavity)")
+    ap.add_argument("--markers", type=int, default=100000)
     ap.add_argument("--mode", default="coupled", choices=["coupled", "fractional"])
-    ap.add_argument("--restart", type=int, default=10, help="outer GMRES restart (memory: (restart+1) x 7 fields)")
-    ap.add_argument("--cpu-n", type=int, default=48, help="cells per direction of the bounded CPU sample")
+    ap.add_argument("--restart", type=int, default=0, help="outer GMRES restart (memory: (restart+1) x 7 fields; default 5 at 512^3, 10 below)")
+    ap.add_argument("--cpu-n", type=int, default=64, help="cells per direction of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -52,6 +54,51 @@ def cavity_case(n, nz, Re=400.0):
     c = cases.cavity3d_full(n=(n, n, nz), Re=Re, dt=0.5 / n)
     c.hi = (1.0, 1.0, float(nz) / n)
     return c
+
+
+def sphere_case(n, nz, Re=300.0):
+    """BASELINE config 4: flow past a sphere (D = 1 at the origin, U_inf = 1) by the immersed-boundary coupling on
+    [-4,12] x [-8,8]^2 with n^3 cells (h = 16/n; 512^3 -> h = 1/32), inflow LEFT, pressure outlet RIGHT (p = 0), symmetry on
+    the four side boundaries, dt = 0.5 h (CFL 0.5), initial state uniform U_inf.  Weak scaling extends the
+    box in z (nz = n * N cells) so that every GPU keeps an n^3 slab; the sphere stays at the origin."""
+    from tests import cases
+
+    c = cases.channel3d(n=(n, n, nz), Re=Re, dt=0.5 * 16.0 / n)
+    c.lo, c.hi = (-4.0, -8.0, -8.0), (12.0, 8.0, -8.0 + 16.0 * nz / n)
+    for b in c.bcs:  # constant boundary data, evaluated once per plane
+        for k in ("velocity", "pressure"):
+            if b[k] is not None:
+                b[k] = cases._const(1.0, 0.0, 0.0) if k == "velocity" else cases._constp(0.0)
+    return c
+
+
+def make_case(args, n, nz):
+    return sphere_case(n, nz) if args.workload == "sphere" else cavity_case(n, nz)
+
+
+def markers_for(args, n):
+    from tests import cases
+
+    if args.workload != "sphere":
+        return None
+    return cases.sphere_markers((0.0, 0.0, 0.0), 1.0, args.markers, 16.0 / n)
+
+
+def uniform_inflow_state(case):
+    cell, face = case.shapes()
+    v = np.zeros((3,) + cell)
+    v[0] = 1.0
+    U = [np.zeros(s) for s in face]
+    U[0][...] = 1.0
+    return v, U, np.zeros(cell)
+
+
+def workload_text(args, n, nzg, restart):
+    if args.workload == "sphere":
+        return (f"BASELINE config 4: 3-D flow past a sphere by IBM, Re=300, {n}x{n}x{nzg} cells ({n}^3 per GPU, z-slabs), h=16/{n}, {args.markers} Fibonacci markers, 4-point delta, "
+                f"inflow/pressure-outlet/symmetry, dt=0.5h, uniform initial state, NS type b200 mode={args.mode}, reference default tolerances (outer/momentum/Schur rtol 1e-5), GMRES restart {restart}")
+    return (f"BASELINE config 3: 3-D lid-driven cavity Re=400, {n}x{n}x{nzg} cells ({n}^3 per GPU, z-slabs), dt=0.5h, zero initial state, NS type b200 mode={args.mode}, "
+            f"reference default tolerances (outer/momentum/Schur rtol 1e-5), GMRES restart {restart}")
 
 
 # ---------------------------------------------------------------------------------------------- clocks
@@ -95,16 +142,21 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
-def cpu_sample(n, steps, warmup, mode, threads):
+def cpu_sample(args, n, steps, warmup, mode, threads):
     """The CPU restatement of the reference algorithm (oracle, kind "port": assembled CSR operators,
-    GMRES(30) + block-Jacobi ILU(0), reference default tolerances) on an n^3 cavity, all host threads."""
+    GMRES(30) + block-Jacobi ILU(0), reference default tolerances) on an n^3 sample of the workload, all host threads."""
     from oracle import oracle as O
     from tests import cases
 
     os.environ.setdefault("OMP_NUM_THREADS", str(threads))
-    case = cavity_case(n, n)
+    case = make_case(args, n, n)
     orc = cases.make_oracle_fast(case)
-    orc.set_state(*case.initial_state())
+    if args.workload == "sphere":
+        orc.set_state(*uniform_inflow_state(case))
+        mk = cases.sphere_markers((0.0, 0.0, 0.0), 1.0, max(64, int(args.markers * (n / 512.0) ** 2)), 16.0 / n)
+        orc.set_markers(mk["X"], mk["Ud"], mk["dV"], 4)
+    else:
+        orc.set_state(*case.initial_state())
     opt = O.default_options(mode=0 if mode == "coupled" else 1, ilu_blocks=threads)
     infos = []
     for _ in range(warmup):
@@ -123,7 +175,7 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     n = args.cpu_n
-    r = cpu_sample(n, args.steps, min(args.warmup, 1), args.mode, threads)
+    r = cpu_sample(args, n, args.steps, min(args.warmup, 1), args.mode, threads)
     line = {
         "impl": "reference",
         "metric": "Mcell-updates/s per NS step",
@@ -138,8 +190,8 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"3-D lid-driven cavity Re=400 (BASELINE config 3), bounded CPU sample {n}^3, dt=0.5h, mode={args.mode}, reference default tolerances 1e-5", "mode": args.mode},
-        "cpu_baseline": {"value": r["value"], "unit": "Mcell-updates/s", "cores": threads, "kind": "port", "sample": f"{n}^3 cavity, {r['steps']} steps, outer its {r['outer']}, momentum its {r['mom']}, Schur its {r['schur']}; the reference (PETSc) cannot be built in this image, this is the repo's C restatement (oracle/)"},
+        "config": {"workload": workload_text(args, args.n or (512 if args.workload == "sphere" else 256), (args.n or (512 if args.workload == "sphere" else 256)) * args.gpus, args.restart or 5) + f"; CPU arm: bounded sample {n}^3 of the same case (markers scaled with the surface cell count)", "mode": args.mode},
+        "cpu_baseline": {"value": r["value"], "unit": "Mcell-updates/s", "cores": threads, "kind": "port", "sample": f"{n}^3 sample of the workload, {r['steps']} steps, outer its {r['outer']}, momentum its {r['mom']}, Schur its {r['schur']}; the reference (PETSc) cannot be built in this image, this is the repo's C restatement (oracle/)"},
         "e2e": {"value": r["value"], "unit": "Mcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -174,13 +226,21 @@ def run_b200(args):
         uid_bytes = tid.cpu().numpy().tobytes()
         comm = dict(rank=rank, nranks=world, make_comm=lambda L: fb.Comm.nccl(L, uid_bytes, rank, world))
 
-    n = args.n or 256
+    n = args.n or (512 if args.workload == "sphere" else 256)
     nzg = n * world  # weak scaling: an n^3 slab per GPU
-    case = cavity_case(n, nzg)
-    opts = {"ns_ksp_gmres_restart": args.restart}
+    restart = args.restart or (5 if n >= 512 else 10)
+    case = make_case(args, n, nzg)
+    opts = {"ns_ksp_gmres_restart": restart}
     ns = parity.make_ns(case, lib, args.mode, comm=comm, **opts)
     s = fb.NSB200GetSolver(ns)
     cells_total = float(n) * n * nzg
+    if args.workload == "sphere":
+        v0_, U0_, p0_ = uniform_inflow_state(case)
+        k0_, nzl_ = s.k0, s.nzl
+        s.set_state(v=v0_[:, k0_ : k0_ + nzl_], U=[U0_[0][k0_ : k0_ + nzl_], U0_[1][k0_ : k0_ + nzl_], U0_[2][k0_ : k0_ + nzl_ + (1 if s.last_z else 0)]], p=p0_[k0_ : k0_ + nzl_], phalf=p0_[k0_ : k0_ + nzl_])
+        del v0_, U0_, p0_
+        mk = markers_for(args, n)
+        fb.NSB200SetMarkers(ns, mk["X"], mk["Ud"], mk["dV"], 4)
 
     def barrier():
         if world > 1:
@@ -235,12 +295,16 @@ def run_b200(args):
     # BiCGStab iteration), writes y(3): (120 + 96) / 2 = 108 B per cell and launch on average
     per_launch = {"momentum_apply": 108.0, "poisson_apply": 16.0}
     shares = {k: v[0] / ms for k, v in ktimes.items() if v[1] > 0}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        traffic = {}
     roof = None
     for name in ("momentum_apply", "poisson_apply"):
         t, cnt = ktimes[name]
         if cnt:
             ach = per_launch[name] * cells_rank * cnt / (t * 1e-3) / 1e9
-            r = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "launches": cnt, "avg_ms": t / cnt, "share_of_step": t / ms, "peak_source": peak_src}
+            r = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": (traffic[name]["bytes_per_cell"] * cells_rank / 1e9 if name in traffic else None), "traffic_unit": "GB per launch (ncu dram bytes per cell of the committed capture x cells of this launch)", "traffic_source": traffic.get(name, {}).get("capture"), "algorithmic_GB_per_launch": per_launch[name] * cells_rank / 1e9, "launches": cnt, "avg_ms": t / cnt, "share_of_step": t / ms, "peak_source": peak_src}
             if roof is None or t > roof["_t"]:
                 roof = dict(r, _t=t)
     if roof:
@@ -263,9 +327,9 @@ def run_b200(args):
         "dtype": "f64",
         "data": "synthetic",
         "config": {
-            "workload": f"BASELINE config 3: 3-D lid-driven cavity Re=400, {n}x{n}x{nzg} cells ({n}^3 per GPU, z-slabs), dt=0.5h, zero initial state, NS type b200 mode={args.mode}, reference default tolerances (outer/momentum/Schur rtol 1e-5), GMRES restart {args.restart}; config 4 (512^3 sphere) needs the IBM coupling that is not built yet",
+            "workload": workload_text(args, n, nzg, restart),
             "mode": args.mode,
-            "l2": "inputs larger than L2 (each field 134 MB at 256^3 vs 126 MB L2; >50 fields streamed per step)",
+            "l2": f"inputs larger than L2 (each field {8 * n**3 / 1e6:.0f} MB vs 126 MB L2; >50 fields streamed per step), no flush",
             "iterations_per_step": {"outer": [st.outer_its for st in stats], "momentum": [st.mom_its for st in stats], "schur": [st.schur_its for st in stats], "abf": [st.abf_applies for st in stats]},
         },
         "roofline": roof,
@@ -312,8 +376,8 @@ def run_b200(args):
     # ---- CPU baseline on the box's host cores (rank 0, N=1 only), bounded sample
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        r = cpu_sample(args.cpu_n, 1, 0, args.mode, threads)
-        line["cpu_baseline"] = {"value": r["value"], "unit": "Mcell-updates/s", "cores": threads, "kind": "port", "sample": f"{args.cpu_n}^3 cavity (same BCs, dt=0.5h, mode={args.mode}, tolerances 1e-5), 1 step in {r['seconds']:.1f} s: the reference needs PETSc (absent) so this is the repo's C restatement"}
+        r = cpu_sample(args, args.cpu_n, 1, 0, args.mode, threads)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "Mcell-updates/s", "cores": threads, "kind": "port", "sample": f"{args.cpu_n}^3 sample of the workload (same BCs, dt=0.5h, mode={args.mode}, tolerances 1e-5), 1 step in {r['seconds']:.1f} s: the reference needs PETSc (absent) so this is the repo's C restatement"}
     if rank == 0:
         print_json(json.dumps(line))
     fb.NSDestroy(ns)

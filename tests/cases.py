@@ -119,6 +119,19 @@ def _const(*vals):
     return f
 
 
+def _constp(val):
+    """Constant boundary pressure, point-wise or vectorised (see _const)."""
+
+    def f(dim, t, x):
+        shape = np.shape(x[0])
+        return np.full(shape, float(val)) if shape else float(val)
+
+    f.constp = float(val)
+    f.vectorized = True
+    f.time_independent = True
+    return f
+
+
 def cavity2d(n=16, Re=100.0, dt=None):
     wall = dict(type=BC_VELOCITY, velocity=_const(0.0, 0.0), pressure=None)
     lid = dict(type=BC_VELOCITY, velocity=_const(1.0, 0.0), pressure=None)
@@ -206,7 +219,8 @@ def make_oracle_fast(case):
     bcs = []
     for b in case.bcs:
         cv = getattr(b["velocity"], "const", None) if b["velocity"] is not None else None
-        bcs.append(O.BC(b["type"], velocity=b["velocity"], pressure=b["pressure"], const_velocity=cv))
+        cp = getattr(b["pressure"], "constp", None) if b["pressure"] is not None else None
+        bcs.append(O.BC(b["type"], velocity=b["velocity"], pressure=b["pressure"], const_velocity=cv, const_pressure=cp))
     return O.Oracle(case.n, case.faces(), case.rho, case.mu, case.dt, bcs)
 
 
