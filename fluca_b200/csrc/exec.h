@@ -43,6 +43,28 @@
 
 namespace fluca {
 
+// Store of a kernel result.  In the CUDA build it is an asm store WITHOUT a memory clobber: the functors take their
+// arrays through struct members, which carry no __restrict__ information, so with a plain store the compiler must
+// keep every load of the next plane behind it; with this form it may hoist them (software pipelining of the plane
+// loop in k_box: two planes of loads in flight per thread).  No functor reads, in a later iteration, an element that
+// an earlier iteration of the same thread stored, so the reordering is safe.
+#if !defined(FLUCA_HOSTEMU) && defined(__CUDA_ARCH__)
+__device__ __forceinline__ void fl_store(double *p, double v) { asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v)); }
+#else
+inline void fl_store(double *p, double v) { *p = v; }
+#endif
+
+// L2 prefetch of the element a direct-load stencil functor will need PF planes later.  The plane loop of k_box keeps
+// only one plane of loads in flight per thread (profiles/r01l: FaceCombine issue slots 11 % busy, 48 warps stalled on
+// the long scoreboard per issue); the prefetch costs no register and no scoreboard entry and turns the later demand
+// loads into L2 hits.
+#if !defined(FLUCA_HOSTEMU) && defined(__CUDA_ARCH__)
+__device__ __forceinline__ void fl_prefetch(const double *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#else
+inline void fl_prefetch(const double *) { }
+#endif
+static const int FL_PF = 2; // planes ahead
+
 struct Error : public std::runtime_error {
   int code;
   Error(int c, const std::string &m) : std::runtime_error(m), code(c) { }
@@ -315,7 +337,7 @@ FL_HD void z_chunk(int nz, int nchunks, int c, int &k0, int &k1)
   k1 = k0 + base + (c < rem ? 1 : 0);
 }
 
-template <class F>
+template <int U, class F>
 __global__ void __launch_bounds__(BX *BY, 2) k_box(Box b, F f)
 {
   const int i = blockIdx.x * BX + threadIdx.x;
@@ -323,6 +345,7 @@ __global__ void __launch_bounds__(BX *BY, 2) k_box(Box b, F f)
   if (i >= b.nx || j >= b.ny) return;
   int k0, k1;
   z_chunk(b.nz, gridDim.z, blockIdx.z, k0, k1);
+#pragma unroll U
   for (int k = k0; k < k1; ++k) f(i, j, k);
 }
 
@@ -428,8 +451,8 @@ inline dim3 box_grid(const Exec &ex, Box b, long cap_blocks)
 }
 #endif // !FLUCA_HOSTEMU
 
-// f(i, j, k) for every point of the box
-template <class F>
+// f(i, j, k) for every point of the box; U: planes per loop trip of a thread (loads of U planes in flight)
+template <int U = 1, class F>
 inline void for_box(Exec &ex, Box b, F f)
 {
   if (b.nx <= 0 || b.ny <= 0 || b.nz <= 0) return;
@@ -437,7 +460,7 @@ inline void for_box(Exec &ex, Box b, F f)
 #ifndef FLUCA_HOSTEMU
   dim3   g = box_grid(ex, b, 0);
   KTimer kt(ex, ex.kt_current);
-  k_box<<<g, dim3(BX, BY, 1), 0, ex.stream>>>(b, f);
+  k_box<U><<<g, dim3(BX, BY, 1), 0, ex.stream>>>(b, f);
   FL_CUDA(cudaGetLastError());
 #else
   for (int k = 0; k < b.nz; ++k)

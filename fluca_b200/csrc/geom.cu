@@ -67,6 +67,15 @@ void build_dir(GeomHost &gh, Exec &ex, Tab &T, const Dir &D, int off, int nloc)
     h[i]    = D.F(i + 1) - D.F(i);
     hinv[i] = 1.0 / h[i];
   }
+  {
+    // uniform direction (what MeshCartSetUniformCoordinates produces, cart.c:458-465): the interior rows of every
+    // table are the same numbers up to the rounding of the coordinates, and kernels may use constants instead
+    const double hbar = D.len / n;
+    double       dev  = 0.;
+    for (int i = 0; i < n; ++i) dev = std::fmax(dev, std::fabs(h[i] - hbar));
+    T.uni = dev <= 1e-12 * hbar ? 1 : 0;
+    T.uh  = hbar;
+  }
   // interior rows: cartdiscret.c:210-232 (second derivative), :64-77 (first derivative)
   for (int i = 0; i < n; ++i) {
     bool lo = (!D.per && i == 0), hi = (!D.per && i == n - 1);

@@ -31,6 +31,8 @@ struct Tab {
   int per; // periodic direction
   int bc_lo, bc_hi;
   int wall_lo, wall_hi; // this rank holds the physical lower / upper boundary of the direction
+  int uni;              // every cell of the direction has the same width uh (to round-off): interior rows are constants
+  double uh;
   // global-index tables (device pointers)
   const double *hinv; // [n]         1 / cell width
   const double *h;    // [n]         cell width

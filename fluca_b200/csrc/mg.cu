@@ -86,12 +86,13 @@ struct MGSmooth {
       dg = hy * hz * (L.kf[0][i] + L.kf[0][i + 1]) + hx * hz * (L.kf[1][j] + L.kf[1][j + 1]);
       if (DIM == 3) dg += hx * hy * (L.kf[2][L.k0 + kl] + L.kf[2][L.k0 + kl + 1]);
       const double v = dg > 0. ? omega * b[c] / dg : 0.;
-      xout[c]        = v;
+      fl_store(xout + c, v);
       return b[c] * v;
     }
+    if (DIM == 3 && kl + FL_PF < L.nzl) fl_prefetch(xin + c + FL_PF * L.plane), fl_prefetch(b + c + FL_PF * L.plane);
     mg_row<DIM>(L, xin, i, j, kl, Ax, dg);
     const double bc = b[c], v = dg > 0. ? xin[c] + omega * (bc - Ax) / dg : xin[c];
-    xout[c]         = v;
+    fl_store(xout + c, v);
     return bc * v;
   }
   FL_HD void operator()(int i, int j, int kl) const { (void)sweep(i, j, kl); }
@@ -138,11 +139,12 @@ struct MGResidRestrict {
       for (int dj = 0; dj < F.cf[1]; ++dj)
         for (int di = 0; di < F.cf[0]; ++di) {
           const int i = F.cf[0] * I + di, j = F.cf[1] * J + dj, kl = cfz * K + dk;
+          if (DIM == 3 && kl + 2 * FL_PF < F.nzl) fl_prefetch(F.x + F.idx(i, j, kl + 2 * FL_PF)), fl_prefetch(F.b + F.idx(i, j, kl + 2 * FL_PF));
           double    Ax, dg;
           mg_row<DIM>(F, F.x, i, j, kl, Ax, dg);
           s += F.b[F.idx(i, j, kl)] - Ax;
         }
-    C.b[C.idx(I, J, K)] = s;
+    fl_store(C.b + C.idx(I, J, K), s);
   }
 };
 
@@ -177,6 +179,7 @@ struct MGProlong {
     interp1(j, F.cf[1], C.n[1], C.per[1], J0, J1, wj);
     const double *e = C.x;
     double        v;
+    if (DIM == 3 && kl + FL_PF < F.nzl) fl_prefetch(F.x + F.idx(i, j, kl + FL_PF));
     if (DIM == 3) {
       // z: local coarse index with ghost planes; clamp only at a physical wall
       int    K0, K1;
@@ -195,7 +198,7 @@ struct MGProlong {
     } else {
       v = (1. - wi) * ((1. - wj) * e[C.idx(I0, J0, 0)] + wj * e[C.idx(I0, J1, 0)]) + wi * ((1. - wj) * e[C.idx(I1, J0, 0)] + wj * e[C.idx(I1, J1, 0)]);
     }
-    F.x[F.idx(i, j, kl)] += v;
+    fl_store(F.x + F.idx(i, j, kl), F.x[F.idx(i, j, kl)] + v);
   }
 };
 
@@ -285,7 +288,7 @@ void smooth(Solver &s, MGLevel &L, bool zero_guess, bool with_dot = false)
   MGSmooth<DIM> f;
   f.L = L, f.omega = omega, f.zero_guess = zero_guess ? 1 : 0, f.xin = L.x, f.b = L.b, f.xout = zero_guess ? L.x : L.t;
   if (with_dot) for_box_reduce<1>(s.ex, level_box(L), f);
-  else for_box(s.ex, level_box(L), f);
+  else for_box<2>(s.ex, level_box(L), f);
   if (!zero_guess) {
     double *tmp = L.x;
     L.x         = L.t;
@@ -312,7 +315,7 @@ void vcycle(Solver &s, size_t l, bool want_dot)
     KScope               kt(s.ex, KT_MG_TRANSFER);
     MGResidRestrict<DIM> rr;
     rr.F = L, rr.C = C;
-    for_box(s.ex, level_box(C), rr);
+    for_box<2>(s.ex, level_box(C), rr);
   }
   vcycle<DIM>(s, l + 1, false);
   level_halo(s, C, C.x);
@@ -320,7 +323,7 @@ void vcycle(Solver &s, size_t l, bool want_dot)
     KScope         kt(s.ex, KT_MG_TRANSFER);
     MGProlong<DIM> pr;
     pr.F = L, pr.C = C;
-    for_box(s.ex, level_box(L), pr);
+    for_box<2>(s.ex, level_box(L), pr);
   }
   for (int k = 0; k < s.opt.mg_nu2; ++k) smooth<DIM>(s, L, false, want_dot && k == s.opt.mg_nu2 - 1);
 }

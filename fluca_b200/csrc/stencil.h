@@ -313,19 +313,28 @@ struct FaceCombine {
   {
     Nbr<DIM> nb;
     nbr<DIM>(g, i, j, kl, nb);
+    if (DIM == 3 && kl + FL_PF < g.nzl) {
+      const long ahead = nb.c + FL_PF * g.plane;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) {
+        fl_prefetch(in.c[d] + ahead);
+        if (b != 0.) fl_prefetch(w.c[d] + ahead);
+      }
+      if (c != 0.) fl_prefetch(p + ahead);
+    }
 #pragma unroll
     for (int d = 0; d < DIM; ++d) {
       const Tab &T = g.t[d];
       double     s = a * in.c[d][nb.c];
       if (b != 0.) s += b * t_face_lo<DIM>(g, d, w.c[d], nb);
       if (c != 0.) s += c * gst_face_lo<DIM>(g, d, p, nb);
-      out.c[d][nb.c] = s;
+      fl_store(out.c[d] + nb.c, s);
       if (!T.per && nb.ig[d] == T.n - 1) {
         const long fw = nb.fu[d];
         double     e  = a * in.c[d][fw];
         if (b != 0.) e += b * t_face_wall_hi<DIM>(g, d, w.c[d], nb);
         if (c != 0.) e += c * gst_face_wall_hi<DIM>(g, d, p, nb);
-        out.c[d][fw] = e;
+        fl_store(out.c[d] + fw, e);
       }
     }
   }
@@ -335,16 +344,14 @@ struct FaceCombine {
 template <int DIM>
 FL_HD double div_flux(const Geom &g, const CV3 &U, const Nbr<DIM> &nb, double &vol)
 {
-  double h[DIM];
-  vol = 1.;
+  double h[3] = {1., 1., 1.};
 #pragma unroll
-  for (int d = 0; d < DIM; ++d) {
-    h[d] = g.t[d].h[nb.ig[d]];
-    vol *= h[d];
-  }
+  for (int d = 0; d < DIM; ++d) h[d] = g.t[d].h[nb.ig[d]];
+  const double area[3] = {h[1] * h[2], h[0] * h[2], h[0] * h[1]};
+  vol = h[0] * h[1] * h[2];
   double s = 0.;
 #pragma unroll
-  for (int d = 0; d < DIM; ++d) s += (vol / h[d]) * (U.c[d][nb.fu[d]] - U.c[d][nb.c]);
+  for (int d = 0; d < DIM; ++d) s += area[d] * (U.c[d][nb.fu[d]] - U.c[d][nb.c]);
   return s;
 }
 
@@ -362,6 +369,12 @@ struct PoissonRhs {
   {
     Nbr<DIM> nb;
     nbr<DIM>(g, i, j, kl, nb);
+    if (DIM == 3 && kl + FL_PF < g.nzl) {
+      const long ahead = nb.c + FL_PF * g.plane;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) fl_prefetch(U.c[d] + ahead);
+      if (rc) fl_prefetch(rc + ahead);
+    }
     double vol, fl = div_flux<DIM>(g, U, nb, vol);
     double s = scale * ((rc ? vol * rc[nb.c] : 0.) - fl);
     out[nb.c] = s;
@@ -378,8 +391,13 @@ struct DivCell { // y_p = D U (per unit volume, as the reference's D)
   {
     Nbr<DIM> nb;
     nbr<DIM>(g, i, j, kl, nb);
+    if (DIM == 3 && kl + FL_PF < g.nzl) {
+      const long ahead = nb.c + FL_PF * g.plane;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) fl_prefetch(U.c[d] + ahead);
+    }
     double vol, fl = div_flux<DIM>(g, U, nb, vol);
-    out[nb.c] = fl / vol;
+    fl_store(out + nb.c, fl / vol);
   }
 };
 
@@ -389,23 +407,22 @@ struct DivCell { // y_p = D U (per unit volume, as the reference's D)
 template <int DIM>
 FL_HD double poisson_row(const Geom &g, const int ig[DIM], double pc, const double pm[DIM], const double pp[DIM])
 {
-  double h[DIM], vol = 1.;
+  double h[3] = {1., 1., 1.};
 #pragma unroll
-  for (int d = 0; d < DIM; ++d) {
-    h[d] = g.t[d].h[ig[d]];
-    vol *= h[d];
-  }
-  double s = 0.;
+  for (int d = 0; d < DIM; ++d) h[d] = FL_LDG(g.t[d].h + ig[d]);
+  // face areas by products (a division per direction made this row instruction-bound: profiles/r01h)
+  const double area[3] = {h[1] * h[2], h[0] * h[2], h[0] * h[1]};
+  double       s = 0.;
 #pragma unroll
   for (int d = 0; d < DIM; ++d) {
     const Tab &T = g.t[d];
     const int  i = ig[d];
     double     gl, gu;
     if (!T.per && i == 0) gl = T.gst_lo[0] * pc + T.gst_lo[1] * pp[d];
-    else gl = T.gstw[i] * (pc - pm[d]);
+    else gl = FL_LDG(T.gstw + i) * (pc - pm[d]);
     if (!T.per && i == T.n - 1) gu = T.gst_hi[0] * pm[d] + T.gst_hi[1] * pc;
-    else gu = T.gstw[i + 1] * (pp[d] - pc);
-    s += (vol / h[d]) * (gl - gu);
+    else gu = FL_LDG(T.gstw + i + 1) * (pp[d] - pc);
+    s += area[d] * (gl - gu);
   }
   return s;
 }
@@ -431,10 +448,16 @@ struct ProjectCells {
   {
     Nbr<DIM> nb;
     nbr<DIM>(g, i, j, kl, nb);
+    if (DIM == 3 && kl + FL_PF < g.nzl) {
+      const long ahead = nb.c + FL_PF * g.plane;
+#pragma unroll
+      for (int c = 0; c < DIM; ++c) fl_prefetch(vs.c[c] + ahead);
+      fl_prefetch(p + ahead);
+    }
     double gp[DIM];
     grad_cell<DIM>(g, p, nb, gp);
 #pragma unroll
-    for (int c = 0; c < DIM; ++c) v.c[c][nb.c] = vs.c[c][nb.c] - dtrho * gp[c];
+    for (int c = 0; c < DIM; ++c) fl_store(v.c[c] + nb.c, vs.c[c][nb.c] - dtrho * gp[c]);
   }
 };
 
@@ -451,13 +474,19 @@ struct CoupledCells {
   {
     Nbr<DIM> nb;
     nbr<DIM>(g, i, j, kl, nb);
+    if (DIM == 3 && kl + FL_PF < g.nzl) {
+      const long ahead = nb.c + FL_PF * g.plane;
+#pragma unroll
+      for (int c = 0; c < DIM; ++c) fl_prefetch(x.c[c] + ahead), fl_prefetch(v0.c[c] + ahead), fl_prefetch(U0.c[c] + ahead);
+      fl_prefetch(p + ahead);
+    }
     double av[DIM], gp[DIM];
     a_apply_cell<DIM>(g, sp, bc, x, v0, U0, i, j, kl, av);
     grad_cell<DIM>(g, p, nb, gp);
 #pragma unroll
     for (int c = 0; c < DIM; ++c) {
-      y.c[c][nb.c] = av[c] + sp.dtrho * gp[c];
-      w.c[c][nb.c] = x.c[c][nb.c] + sp.dtrho * gp[c];
+      fl_store(y.c[c] + nb.c, av[c] + sp.dtrho * gp[c]);
+      fl_store(w.c[c] + nb.c, x.c[c][nb.c] + sp.dtrho * gp[c]);
     }
   }
 };

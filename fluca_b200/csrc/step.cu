@@ -371,7 +371,7 @@ static void abf_apply_t(Solver &s, const V3 &bm, const V3 &bi, const double *bcn
   halo_cells(s, s.vstar);
   FaceCombine<DIM> fc;
   fc.g = g, fc.a = 1., fc.b = 1., fc.c = 0., fc.in = CV3(bi), fc.w = CV3(s.vstar), fc.p = nullptr, fc.out = s.Ustar;
-  for_box(s.ex, cell_box(s), fc);
+  for_box<2>(s.ex, cell_box(s), fc);
   halo_faces(s, s.Ustar);
   PoissonRhs<DIM> pr;
   pr.g = g, pr.scale = s.sp.rho / s.sp.dt, pr.U = CV3(s.Ustar), pr.rc = bcn, pr.out = s.srhs;
@@ -391,9 +391,9 @@ static void abf_apply_t(Solver &s, const V3 &bm, const V3 &bi, const double *bcn
   halo_scalar(s, op);
   ProjectCells<DIM> pc;
   pc.g = g, pc.dtrho = s.sp.dtrho, pc.vs = CV3(s.vstar), pc.p = op, pc.v = ov;
-  for_box(s.ex, cell_box(s), pc);
+  for_box<2>(s.ex, cell_box(s), pc);
   fc.a = 1., fc.b = 0., fc.c = -s.sp.dtrho, fc.in = CV3(s.Ustar), fc.w = CV3(), fc.p = op, fc.out = oU;
-  for_box(s.ex, cell_box(s), fc);
+  for_box<2>(s.ex, cell_box(s), fc);
   s.stats.abf_applies++;
 }
 
@@ -414,11 +414,11 @@ static void coupled_apply_t(Solver &s, const V3 &xv, const V3 &xU, double *xp, c
   halo_cells(s, s.tw);
   FaceCombine<DIM> fc;
   fc.g = g, fc.a = 1., fc.b = -1., fc.c = s.sp.dtrho, fc.in = CV3(xU), fc.w = CV3(s.tw), fc.p = xp, fc.out = yU;
-  for_box(s.ex, cell_box(s), fc);
+  for_box<2>(s.ex, cell_box(s), fc);
   halo_faces(s, xU);
   DivCell<DIM> dc;
   dc.g = g, dc.U = CV3(xU), dc.out = yp;
-  for_box(s.ex, cell_box(s), dc);
+  for_box<2>(s.ex, cell_box(s), dc);
 }
 
 void coupled_apply(Solver &s, const V3 &xv, const V3 &xU, double *xp, const V3 &yv, const V3 &yU, double *yp)

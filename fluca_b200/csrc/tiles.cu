@@ -145,12 +145,65 @@ __device__ __forceinline__ void a_apply_tile(const Geom &g, const StepParams &sp
   for (int c = 0; c < 3; ++c) y[c] = xc[c] + sp.dt * conv[c] - sp.nu2 * lap[c];
 }
 
+// Interior cells of a mesh that is uniform in all three directions: every interior table row is a constant
+// (interpolation 1/2, 1/2; second derivative (1, -2, 1)/h^2; flux divergence 1/h), so the operator needs no table
+// load at all and the sums x_c + x_neighbour are shared between the convection and the diffusion terms:
+//   conv_c = sum_d 1/(4 h_d) [ 2 Uu (x_c + x_c^+) - 2 Ul (x_c^- + x_c) + (v_c + v_c^+)(x_d + x_d^+)/... ]   (same algebra
+// as a_apply_tile<false> with al = bl = au = bu = 1/2; the results differ from the table path by rounding only)
+struct UniCoef {
+  double q[3]; // 1 / (4 h_d)
+  double l[3]; // 1 / h_d^2
+  double l4;   // 4 (l_0 + l_1 + l_2)
+};
+
+__device__ __forceinline__ void a_apply_tile_uniform(const UniCoef &u, const StepParams &sp, const TileView &tv, double y[3])
+{
+  constexpr int FS = TILE_STRIDE;
+  const int     lc = tv.lc;
+  double        xc[3], vc[3], conv[3], lap[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    xc[c]   = tv.p0[c * FS + lc];
+    vc[c]   = tv.p0[(3 + c) * FS + lc];
+    conv[c] = 0.;
+    lap[c]  = 0.;
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double *nm = d == 2 ? tv.pm : tv.p0, *np = d == 2 ? tv.pp : tv.p0;
+    const int     st = d == 0 ? 1 : (d == 1 ? TLX : 0);
+    const int     om = lc - st, op = lc + st;
+    const double  Ul = tv.p0[(6 + d) * FS + lc], Uu = np[(6 + d) * FS + op];
+    double        sxl[3], sxu[3], svl[3], svu[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      sxl[c] = nm[c * FS + om] + xc[c];
+      sxu[c] = xc[c] + np[c * FS + op];
+      svl[c] = nm[(3 + c) * FS + om] + vc[c];
+      svu[c] = vc[c] + np[(3 + c) * FS + op];
+    }
+    const double hl = 0.5 * sxl[d], hu = 0.5 * sxu[d];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double t = Uu * sxu[c] - Ul * sxl[c];
+      t        = fma(svu[c], hu, t);
+      t        = fma(-svl[c], hl, t);
+      conv[c]  = fma(u.q[d], t, conv[c]);
+      lap[c]   = fma(u.l[d], sxl[c] + sxu[c], lap[c]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) y[c] = xc[c] + sp.dt * conv[c] - sp.nu2 * (lap[c] - u.l4 * xc[c]);
+}
+
 template <int NRED>
 struct AApplyTile {
   static const int NIN = 9, NR = NRED, MINB = 2;
   Geom             g;
   StepParams       sp;
   BcDev            bc;
+  UniCoef          uc;
+  int              uniform; // all three directions uniform: interior warps use a_apply_tile_uniform
   const double    *a[3]; // dot partner (NR == 2); nullptr: the partner is x itself
   double          *y[3];
   struct Regs {
@@ -169,8 +222,10 @@ struct AApplyTile {
   {
     double     r[3];
     const bool inter = i > 0 && i < g.nx - 1 && j > 0 && j < g.ny - 1;
-    if (__all_sync(__activemask(), inter)) a_apply_tile<false>(g, sp, bc, tv, i, j, kl, r);
-    else a_apply_tile<true>(g, sp, bc, tv, i, j, kl, r);
+    if (__all_sync(__activemask(), inter)) {
+      if (uniform) a_apply_tile_uniform(uc, sp, tv, r);
+      else a_apply_tile<false>(g, sp, bc, tv, i, j, kl, r);
+    } else a_apply_tile<true>(g, sp, bc, tv, i, j, kl, r);
     const int c = g.idx(i, j, kl);
     double    d0 = 0., d1 = 0.;
 #pragma unroll
@@ -223,14 +278,19 @@ void a_apply_dots_tma(Solver &s, const V3 &x, const V3 &y, const V3 &a, bool wit
   }
   // 2. everything else through the TMA pipeline
   const double *fields[9] = {x.c[0], x.c[1], x.c[2], s.v0.c[0], s.v0.c[1], s.v0.c[2], s.U0.c[0], s.U0.c[1], s.U0.c[2]};
+  UniCoef       uc;
+  static const bool no_uni = getenv("FLUCA_B200_NO_UNIFORM") != nullptr;
+  const int     uniform = (!no_uni && g.t[0].uni && g.t[1].uni && g.t[2].uni) ? 1 : 0;
+  uc.l4 = 0.;
+  for (int d = 0; d < 3; ++d) uc.q[d] = 0.25 / g.t[d].uh, uc.l[d] = 1. / (g.t[d].uh * g.t[d].uh), uc.l4 += 4. * uc.l[d];
   if (with_dots) {
     AApplyTile<2> op;
-    op.g = g, op.sp = s.sp, op.bc = s.bc;
+    op.g = g, op.sp = s.sp, op.bc = s.bc, op.uc = uc, op.uniform = uniform;
     for (int c = 0; c < 3; ++c) op.a[c] = (a.c[c] == x.c[c]) ? nullptr : a.c[c], op.y[c] = y.c[c];
     tma_launch(s.ex, op, fields, g.px, g.py, g.nzl + 2, g.nx, g.ny, kbeg, kend, carry);
   } else {
     AApplyTile<0> op;
-    op.g = g, op.sp = s.sp, op.bc = s.bc;
+    op.g = g, op.sp = s.sp, op.bc = s.bc, op.uc = uc, op.uniform = uniform;
     for (int c = 0; c < 3; ++c) op.a[c] = nullptr, op.y[c] = y.c[c];
     tma_launch(s.ex, op, fields, g.px, g.py, g.nzl + 2, g.nx, g.ny, kbeg, kend, nullptr);
   }
