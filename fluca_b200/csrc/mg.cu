@@ -104,7 +104,7 @@ struct MGSmooth {
 // the same sweep from TMA-staged tiles (3-D levels of at least one tile per plane, see tma.h)
 template <int NRED>
 struct MGSmoothTile {
-  static const int NIN = 1, NR = NRED, MINB = 4;
+  static const int NIN = 1, NR = NRED, MINB = 4, STAGES = 8;
   MGLevel          L;
   double           omega;
   const double    *b;
@@ -112,17 +112,81 @@ struct MGSmoothTile {
   struct Regs {
     double b;
   };
-  __device__ void prefetch(Regs &rg, int i, int j, int kl) const { rg.b = b[L.idx(i, j, kl)]; }
-  __device__ void cell(const TileView &tv, const Regs &rg, int i, int j, int kl, double *acc) const
+  __device__ int flags(int i, int j) const { return (L.uni && i > 0 && i < L.n[0] - 1 && j > 0 && j < L.n[1] - 1) ? 1 : 0; }
+  __device__ void prefetch(Regs &rg, int off, int kl) const { rg.b = b[off]; }
+  __device__ void cell(const TileView &tv, const Regs &rg, int fl, int i, int j, int kl, int off, double *acc) const
   {
     const int    lc = tv.lc;
     const double xc = tv.p0[lc];
     const double xm[3] = {tv.p0[lc - 1], tv.p0[lc - TLX], tv.pm[lc]}, xp[3] = {tv.p0[lc + 1], tv.p0[lc + TLX], tv.pp[lc]};
-    double       Ax, dg;
-    mg_row_core<3>(L, i, j, kl, xc, xm, xp, Ax, dg);
-    const double v = dg > 0. ? xc + omega * (rg.b - Ax) / dg : xc;
-    xout[L.idx(i, j, kl)] = v;
+    const int    kg = L.k0 + kl;
+    const bool   inter = fl && (L.per[2] || (kg > 0 && kg < L.n[2] - 1));
+    double       v;
+    if (__all_sync(__activemask(), inter)) {
+      // uniform level, no wall in reach: constant row, no table load, no division
+      const double Ax = L.cd[0] * (2. * xc - xm[0] - xp[0]) + L.cd[1] * (2. * xc - xm[1] - xp[1]) + L.cd[2] * (2. * xc - xm[2] - xp[2]);
+      v               = xc + (omega * L.idg) * (rg.b - Ax);
+    } else {
+      double Ax, dg;
+      mg_row_core<3>(L, i, j, kl, xc, xm, xp, Ax, dg);
+      v = dg > 0. ? xc + omega * (rg.b - Ax) / dg : xc;
+    }
+    xout[off] = v;
     if (NRED > 0) acc[0] += rg.b * v;
+  }
+};
+
+// diagonal of the level operator at cell (i, j, global plane kg)
+__device__ __forceinline__ double mg_diag3(const MGLevel &L, int i, int j, int kg)
+{
+  const double hx = L.h[0][i], hy = L.h[1][j], hz = L.h[2][kg];
+  return hy * hz * (L.kf[0][i] + L.kf[0][i + 1]) + hx * hz * (L.kf[1][j] + L.kf[1][j + 1]) + hx * hy * (L.kf[2][kg] + L.kf[2][kg + 1]);
+}
+
+// The first two pre-smoothing sweeps of a V-cycle in one pass: with a zero guess the first sweep is x1 = omega b / diag,
+// so the second one, x2 = x1 + omega (b - P x1) / diag, needs only b at the cell and its six neighbours.  The tile holds b
+// (ghost planes exchanged by the caller); x1 is never stored: 16 B/cell instead of 16 + 24.
+struct MGFirstTwoTile {
+  static const int NIN = 1, NR = 0, MINB = 4, STAGES = 8;
+  MGLevel          L;
+  double           omega;
+  double          *xout;
+  struct Regs {
+  };
+  __device__ int  flags(int i, int j) const { return (L.uni && i >= 2 && i <= L.n[0] - 3 && j >= 2 && j <= L.n[1] - 3) ? 1 : 0; }
+  __device__ void prefetch(Regs &, int, int) const { }
+  __device__ double first(double bv, int i, int j, int kg) const
+  {
+    const double dg = mg_diag3(L, i, j, kg);
+    return dg > 0. ? omega * bv / dg : 0.;
+  }
+  __device__ void cell(const TileView &tv, const Regs &, int fl, int i, int j, int kl, int off, double *) const
+  {
+    const int    lc = tv.lc, kg = L.k0 + kl, n2 = L.n[2];
+    const double bc = tv.p0[lc];
+    const double bm[3] = {tv.p0[lc - 1], tv.p0[lc - TLX], tv.pm[lc]}, bp[3] = {tv.p0[lc + 1], tv.p0[lc + TLX], tv.pp[lc]};
+    const bool   inter = fl && (L.per[2] || (kg >= 2 && kg <= n2 - 3));
+    double       v;
+    if (__all_sync(__activemask(), inter)) {
+      // uniform level, the cell and its neighbours away from every wall: x1 = w b with one constant w
+      const double w  = omega * L.idg;
+      const double Ab = L.cd[0] * (2. * bc - bm[0] - bp[0]) + L.cd[1] * (2. * bc - bm[1] - bp[1]) + L.cd[2] * (2. * bc - bm[2] - bp[2]);
+      v               = w * (2. * bc - w * Ab);
+    } else {
+      // neighbours outside the domain count as zero (Neumann: zero conductance; outlet: Dirichlet ghost), as in mg_row
+      const double x1c = first(bc, i, j, kg);
+      double       xm[3], xp[3];
+      xm[0] = i > 0 ? first(bm[0], i - 1, j, kg) : 0.;
+      xp[0] = i < L.n[0] - 1 ? first(bp[0], i + 1, j, kg) : 0.;
+      xm[1] = j > 0 ? first(bm[1], i, j - 1, kg) : 0.;
+      xp[1] = j < L.n[1] - 1 ? first(bp[1], i, j + 1, kg) : 0.;
+      xm[2] = kg > 0 ? first(bm[2], i, j, kg - 1) : (L.per[2] ? first(bm[2], i, j, n2 - 1) : 0.);
+      xp[2] = kg < n2 - 1 ? first(bp[2], i, j, kg + 1) : (L.per[2] ? first(bp[2], i, j, 0) : 0.);
+      double Ax, dg;
+      mg_row_core<3>(L, i, j, kl, x1c, xm, xp, Ax, dg);
+      v = dg > 0. ? x1c + omega * (bc - Ax) / dg : x1c;
+    }
+    xout[off] = v;
   }
 };
 #endif
@@ -235,6 +299,22 @@ void level_tables(Solver &s, MGLevel &L, const std::vector<double> xf[3], const 
     L.h[d]  = upload_mg(s, h);
     L.kf[d] = upload_mg(s, kf);
   }
+  // constant interior rows of a level that is uniform in every direction
+  L.uni = 1;
+  double hu[3] = {1., 1., 1.};
+  for (int d = 0; d < s.dim; ++d) {
+    const int    n = L.n[d];
+    const double hbar = (xf[d][n] - xf[d][0]) / n;
+    for (int i = 0; i < n; ++i)
+      if (std::fabs((xf[d][i + 1] - xf[d][i]) - hbar) > 1e-12 * hbar) L.uni = 0;
+    hu[d] = hbar;
+  }
+  double dsum = 0.;
+  for (int d = 0; d < 3; ++d) {
+    L.cd[d] = d < s.dim ? (hu[0] * hu[1] * hu[2] / hu[d]) / hu[d] : 0.;
+    dsum += 2. * L.cd[d];
+  }
+  L.idg = 1. / dsum;
 }
 
 Box level_box(const MGLevel &L)
@@ -307,8 +387,21 @@ void vcycle(Solver &s, size_t l, bool want_dot)
     for (int k = 1; k < ns; ++k) smooth<DIM>(s, L, false, want_dot && k == ns - 1);
     return;
   }
-  smooth<DIM>(s, L, true);
-  for (int k = 1; k < s.opt.mg_nu1; ++k) smooth<DIM>(s, L, false);
+  int done = 0;
+#ifndef FLUCA_HOSTEMU
+  const bool no_fuse = getenv("FLUCA_B200_NO_MG_FUSION") != nullptr; // read per call: the parity test toggles it
+  if (DIM == 3 && !no_fuse && s.opt.mg_nu1 >= 2 && level_tiled(s, L)) {
+    level_halo(s, L, L.b);
+    KScope         kt(s.ex, KT_MG_SMOOTH);
+    MGFirstTwoTile op;
+    op.L = L, op.omega = 6. / 7., op.xout = L.x;
+    const double *fields[1] = {L.b};
+    tma_launch(s.ex, op, fields, L.px, L.py, L.nzl + 2, L.n[0], L.n[1], 0, L.nzl, nullptr);
+    done = 2;
+  }
+#endif
+  if (!done) smooth<DIM>(s, L, true), done = 1;
+  for (int k = done; k < s.opt.mg_nu1; ++k) smooth<DIM>(s, L, false);
   MGLevel &C = s.mg[l + 1];
   level_halo(s, L, L.x);
   {

@@ -62,6 +62,8 @@ struct MGLevel {
   const double *h[3]; // [n[d]]     cell widths
   const double *kf[3]; // [n[d]+1]  face conductance 1/dist, 0 at Neumann walls, 1/(xc-xw) at outlet walls
   int  wall_lo_z, wall_hi_z;
+  int  uni;           // every direction has constant cell width: interior rows are cd[d] (2 x - x- - x+), diagonal 1 / idg
+  double cd[3], idg;
   double *x, *b, *t;  // solution, right-hand side, scratch (Jacobi double buffer)
   bool own_x, own_b;
   FL_HD long idx(int i, int j, int kl) const { return (long)i + (long)px * ((long)j + (long)py * (long)(kl + 1)); }

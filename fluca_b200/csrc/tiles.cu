@@ -198,7 +198,7 @@ __device__ __forceinline__ void a_apply_tile_uniform(const UniCoef &u, const Ste
 
 template <int NRED>
 struct AApplyTile {
-  static const int NIN = 9, NR = NRED, MINB = 2;
+  static const int NIN = 9, NR = NRED, MINB = 2, STAGES = 4;
   Geom             g;
   StepParams       sp;
   BcDev            bc;
@@ -209,24 +209,22 @@ struct AApplyTile {
   struct Regs {
     double a[3];
   };
-  __device__ void prefetch(Regs &rg, int i, int j, int kl) const
+  __device__ int flags(int i, int j) const { return (i > 0 && i < g.nx - 1 && j > 0 && j < g.ny - 1) ? 1 : 0; }
+  __device__ void prefetch(Regs &rg, int off, int kl) const
   {
     if (NRED > 0) {
-      const int c = g.idx(i, j, kl);
 #pragma unroll
       for (int q = 0; q < 3; ++q)
-        if (a[q]) rg.a[q] = a[q][c];
+        if (a[q]) rg.a[q] = a[q][off];
     }
   }
-  __device__ void cell(const TileView &tv, const Regs &rg, int i, int j, int kl, double *acc) const
+  __device__ void cell(const TileView &tv, const Regs &rg, int fl, int i, int j, int kl, int c, double *acc) const
   {
     double     r[3];
-    const bool inter = i > 0 && i < g.nx - 1 && j > 0 && j < g.ny - 1;
-    if (__all_sync(__activemask(), inter)) {
+    if (__all_sync(__activemask(), fl != 0)) {
       if (uniform) a_apply_tile_uniform(uc, sp, tv, r);
       else a_apply_tile<false>(g, sp, bc, tv, i, j, kl, r);
     } else a_apply_tile<true>(g, sp, bc, tv, i, j, kl, r);
-    const int c = g.idx(i, j, kl);
     double    d0 = 0., d1 = 0.;
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
@@ -300,24 +298,30 @@ void a_apply_dots_tma(Solver &s, const V3 &x, const V3 &y, const V3 &a, bool wit
 // No plane needs special treatment: the wall rows of P use the cells (c, c+1) / (c-1, c) only.
 template <int NRED>
 struct PoissonTile {
-  static const int NIN = 1, NR = NRED, MINB = 4;
+  static const int NIN = 1, NR = NRED, MINB = 4, STAGES = 8;
   Geom             g;
   const double    *a; // dot partner; nullptr: p itself
   double          *out;
+  int              uniform; // all directions uniform: interior warps use the constant row cd[d] (2 p - p- - p+)
+  double           cd[3];
   struct Regs {
     double a;
   };
-  __device__ void prefetch(Regs &rg, int i, int j, int kl) const
+  __device__ int flags(int i, int j) const { return (uniform && i > 0 && i < g.nx - 1 && j > 0 && j < g.ny - 1) ? 1 : 0; }
+  __device__ void prefetch(Regs &rg, int off, int kl) const
   {
-    if (NRED > 0 && a) rg.a = a[g.idx(i, j, kl)];
+    if (NRED > 0 && a) rg.a = a[off];
   }
-  __device__ void cell(const TileView &tv, const Regs &rg, int i, int j, int kl, double *acc) const
+  __device__ void cell(const TileView &tv, const Regs &rg, int fl, int i, int j, int kl, int off, double *acc) const
   {
     const int    lc = tv.lc, ig[3] = {i, j, g.k0 + kl};
     const double pc = tv.p0[lc];
     const double pm[3] = {tv.p0[lc - 1], tv.p0[lc - TLX], tv.pm[lc]}, pp[3] = {tv.p0[lc + 1], tv.p0[lc + TLX], tv.pp[lc]};
-    const double v = poisson_row<3>(g, ig, pc, pm, pp);
-    out[g.idx(i, j, kl)] = v;
+    const bool   inter = fl && (g.t[2].per || (ig[2] > 0 && ig[2] < g.t[2].n - 1));
+    double       v;
+    if (__all_sync(__activemask(), inter)) v = cd[0] * (2. * pc - pm[0] - pp[0]) + cd[1] * (2. * pc - pm[1] - pp[1]) + cd[2] * (2. * pc - pm[2] - pp[2]);
+    else v = poisson_row<3>(g, ig, pc, pm, pp);
+    out[off] = v;
     if (NRED > 0) acc[0] += (a ? rg.a : pc) * v;
   }
 };
@@ -328,6 +332,12 @@ void poisson_apply_dot_tma(Solver &s, const double *pin, double *out, const doub
   const Geom    &g = s.gh.g;
   PoissonTile<1> op;
   op.g = g, op.a = (a == pin) ? nullptr : a, op.out = out;
+  static const bool no_uni = getenv("FLUCA_B200_NO_UNIFORM") != nullptr;
+  op.uniform = (!no_uni && g.t[0].uni && g.t[1].uni && g.t[2].uni) ? 1 : 0;
+  {
+    const double hu[3] = {g.t[0].uh, g.t[1].uh, g.t[2].uh};
+    for (int d = 0; d < 3; ++d) op.cd[d] = (hu[0] * hu[1] * hu[2] / hu[d]) / hu[d];
+  }
   const double *fields[1] = {pin};
   tma_launch(s.ex, op, fields, g.px, g.py, g.nzl + 2, g.nx, g.ny, 0, g.nzl, nullptr);
 }

@@ -33,7 +33,9 @@ static const int THX = 2;
 static const int TLX = TMX + 2 * THX, TLY = TMY + 2;
 static const int TILE_ELEMS = TLX * TLY;        // 360 doubles = 2880 B per field and plane
 static const int TILE_STRIDE = 368;             // doubles between consecutive field tiles (2944 B, 128-B aligned)
-static const int TMS = 4;                       // ring slots: planes k-1, k, k+1 live + one in flight (two while a plane is computed)
+// ring slots per operator (Op::STAGES): planes k-1, k, k+1 live + (STAGES - 3) in flight.  Operators with few input
+// fields need a deep ring: with 4 slots a 1-field operator keeps 4 CTAs x 1 plane x 2.9 KB = 12 KB in flight per SM, far
+// below the ~40 KB that saturate HBM (measured: the smoother ran at 45 % of peak); 8 slots give 58 KB.
 
 template <int NIN>
 struct alignas(64) TmaIn {
@@ -41,6 +43,7 @@ struct alignas(64) TmaIn {
 };
 
 struct TmaGrid {
+  int px, py;     // padded row length / rows per plane of every field of the launch
   int nx, ny;     // cells
   int kbeg, kend; // local planes [kbeg, kend) computed by this launch
   int ntx, nty, nchunk;
@@ -98,17 +101,40 @@ struct TileView {
   int           lc;           // element index of this thread's cell inside a field tile
 };
 
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar, unsigned parity)
+{
+  unsigned ok, spins = 0;
+  do {
+    asm volatile("{\n\t.reg .pred P_OUT;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P_OUT, [%1], %2;\n\t"
+                 "selp.b32 %0, 1, 0, P_OUT;\n\t}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    if (!ok && ++spins > (1u << 22)) __trap(); // a protocol bug traps after ~seconds instead of hanging the GPU
+  } while (!ok);
+}
+
 // Op interface:
-//   static const int NIN, NR, MINB;                                     inputs, reductions, resident CTAs per SM aimed at
+//   static const int NIN, NR, MINB, STAGES;                             inputs, reductions, resident CTAs per SM aimed at, ring slots
 //   struct Regs;                                                         per-thread operands that bypass the tiles
-//   __device__ void prefetch(Regs &r, int i, int j, int kl) const;       global loads for plane kl, issued one plane ahead
-//   __device__ void cell(const TileView &tv, const Regs &r, int i, int j, int kl, double *acc) const;   (acc: NR entries)
+//   __device__ int  flags(int i, int j) const;                           per-thread constants of the column (wall tests), computed once
+//   __device__ void prefetch(Regs &r, int off, int kl) const;            global loads for plane kl, issued one plane ahead
+//   __device__ void cell(const TileView &tv, const Regs &r, int flags, int i, int j, int kl, int off, double *acc) const;
+// off = element offset of cell (i, j, kl) in the padded arrays of the launch (all fields of a launch share one layout,
+// 32-bit: geom_build refuses slabs of 2^31 elements); the framework advances it by one plane per iteration, and every
+// ring / barrier index is a running counter -- the plane loop of the 1-field operators was instruction-bound on index
+// arithmetic (profiles/r01p: 180 warp instructions per warp-cell for 14 of arithmetic).
 template <class Op>
 __global__ void __launch_bounds__(TMX *TMY, Op::MINB) k_tma_march(const __grid_constant__ TmaIn<Op::NIN> in, const Op op, const TmaGrid tg, const double *carry, double *partials, double *result, unsigned *ticket)
 {
   extern __shared__ __align__(128) unsigned char tma_smem[];
-  double   *ring = reinterpret_cast<double *>(tma_smem);
-  uint64_t *full = reinterpret_cast<uint64_t *>(tma_smem + (size_t)TMS * Op::NIN * TILE_STRIDE * sizeof(double));
+  constexpr int      TMS  = Op::STAGES;
+  constexpr int      SLOT = Op::NIN * TILE_STRIDE; // doubles per ring slot
+  constexpr unsigned TX_BYTES = Op::NIN * TILE_ELEMS * sizeof(double);
+  double            *ring = reinterpret_cast<double *>(tma_smem);
+  uint64_t          *full = reinterpret_cast<uint64_t *>(tma_smem + (size_t)TMS * SLOT * sizeof(double));
+  const uint32_t     ring_s = smem_u32(ring), full_s = smem_u32(full);
   const int tid = threadIdx.x, tx = tid & (TMX - 1), ty = tid / TMX;
   const int ntile = tg.ntx * tg.nty;
   const int tile = blockIdx.x % ntile, bz = blockIdx.x / ntile;
@@ -120,7 +146,7 @@ __global__ void __launch_bounds__(TMX *TMY, Op::MINB) k_tma_march(const __grid_c
   const int  i = i0 + tx, j = j0 + ty;
   const bool owned = (i >= bx * TMX) && (i < tg.nx) && (j >= by * TMY);
   const int  nplanes = k1 - k0 + 2; // ring index r <-> local plane k0 - 1 + r
-  constexpr unsigned TX_BYTES = Op::NIN * TILE_ELEMS * sizeof(double);
+  const int  cx = i0 - THX, cy = j0 - 1;
 
   if (tid == 0) {
 #pragma unroll
@@ -129,46 +155,56 @@ __global__ void __launch_bounds__(TMX *TMY, Op::MINB) k_tma_march(const __grid_c
   }
   __syncthreads();
   if (tid == 0) {
-    const int ahead = nplanes < TMS ? nplanes : TMS; // fill every slot: planes k0-1 .. k0+2
+    const int ahead = nplanes < TMS ? nplanes : TMS; // fill every slot
     for (int r = 0; r < ahead; ++r) {
-      const int s = r % TMS;
-      mbar_arrive_expect_tx(&full[s], TX_BYTES);
+      mbar_arrive_expect_tx(&full[r], TX_BYTES);
 #pragma unroll
-      for (int f = 0; f < Op::NIN; ++f) tma_load_box(ring + ((size_t)s * Op::NIN + f) * TILE_STRIDE, &in.m[f], i0 - THX, j0 - 1, k0 + r, &full[s]);
+      for (int f = 0; f < Op::NIN; ++f) tma_load_box(ring + (size_t)r * SLOT + f * TILE_STRIDE, &in.m[f], cx, cy, k0 + r, &full[r]);
     }
   }
   double acc[Op::NR > 0 ? Op::NR : 1];
 #pragma unroll
   for (int r = 0; r < (Op::NR > 0 ? Op::NR : 1); ++r) acc[r] = 0.;
-  TileView tv;
-  tv.lc     = (ty + 1) * TLX + tx + THX;
-  int ready = -1;
+  const int pstride = tg.px * tg.py;
+  int       off = i + tg.px * (j + tg.py * (k0 + 1));
+  const int fl  = owned ? op.flags(i, j) : 0;
   typename Op::Regs cur, nxt;
-  if (owned && k0 < k1) op.prefetch(nxt, i, j, k0);
+  if (owned && k0 < k1) op.prefetch(nxt, off, k0);
+  if (k0 < k1) {
+    mbar_wait_addr(full_s, 0);
+    mbar_wait_addr(full_s + 8, 0);
+  }
+  TileView tv;
+  tv.lc = (ty + 1) * TLX + tx + THX;
+  tv.p0 = ring;        // shifted into pm / p0 at the top of the first iteration
+  tv.pp = ring + SLOT;
+  int      sc = 1;          // ring slot of plane k+1 (after the advance at the top of the loop)
+  unsigned par = 0;        // phase parity of slot sc
+  int      zload = k0 + TMS; // TMA z coordinate of the next plane to request
   for (int k = k0; k < k1; ++k) {
-    const int rc = k - k0 + 1;
     cur = nxt;
-    // operands read straight from global memory (one value per cell, no reuse) are requested a whole plane
-    // ahead: their DRAM latency overlaps the arithmetic of the current plane
-    if (owned && k + 1 < k1) op.prefetch(nxt, i, j, k + 1);
-    while (ready < rc + 1) {
-      ++ready;
-      mbar_wait(&full[ready % TMS], (unsigned)(ready / TMS) & 1u);
-    }
-    tv.pm = ring + (size_t)((rc - 1) % TMS) * Op::NIN * TILE_STRIDE;
-    tv.p0 = ring + (size_t)(rc % TMS) * Op::NIN * TILE_STRIDE;
-    tv.pp = ring + (size_t)((rc + 1) % TMS) * Op::NIN * TILE_STRIDE;
-    if (owned) op.cell(tv, cur, i, j, k, acc);
+    // operands read straight from global memory (one value per cell, no reuse) are requested a whole plane ahead
+    if (owned && k + 1 < k1) op.prefetch(nxt, off + pstride, k + 1);
+    sc = sc + 1 == TMS ? 0 : sc + 1;
+    if (sc == 0) par ^= 1u;
+    mbar_wait_addr(full_s + 8u * sc, par);
+    tv.pm = tv.p0;
+    tv.p0 = tv.pp;
+    tv.pp = ring + sc * SLOT;
+    if (owned) op.cell(tv, cur, fl, i, j, k, off, acc);
+    off += pstride;
     __syncthreads(); // every thread is done with plane k-1: its slot may be refilled
-    if (tid == 0) {
-      const int r = rc - 1 + TMS;
-      if (r < nplanes) {
-        const int s = r % TMS;
-        mbar_arrive_expect_tx(&full[s], TX_BYTES);
+    if (tid == 0 && zload < k0 + nplanes) {
+      // the slot of plane k-1 is two behind sc
+      const int      sr  = sc >= 2 ? sc - 2 : sc - 2 + TMS;
+      const uint32_t bar = full_s + 8u * sr, dst = ring_s + (uint32_t)(sr * SLOT * sizeof(double));
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(TX_BYTES) : "memory");
 #pragma unroll
-        for (int f = 0; f < Op::NIN; ++f) tma_load_box(ring + ((size_t)s * Op::NIN + f) * TILE_STRIDE, &in.m[f], i0 - THX, j0 - 1, k0 + r, &full[s]);
-      }
+      for (int f = 0; f < Op::NIN; ++f)
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst + (uint32_t)(f * TILE_STRIDE * sizeof(double))), "l"(&in.m[f]), "r"(cx), "r"(cy), "r"(zload), "r"(bar)
+                     : "memory");
     }
+    ++zload;
   }
   if (Op::NR > 0) block_reduce_and_finish<(Op::NR > 0 ? Op::NR : 1)>(acc, carry, partials, result, ticket, gridDim.x, blockIdx.x);
 }
@@ -204,10 +240,10 @@ inline void tma_launch(Exec &ex, const Op &op, const double *const *fields, int 
   TmaIn<Op::NIN> in;
   for (int f = 0; f < Op::NIN; ++f) in.m[f] = tensor_map_for(fields[f], px, py, nplanes_alloc);
   TmaGrid tg;
-  tg.nx = nx, tg.ny = ny, tg.kbeg = kbeg, tg.kend = kend;
+  tg.px = px, tg.py = py, tg.nx = nx, tg.ny = ny, tg.kbeg = kbeg, tg.kend = kend;
   tg.ntx = (nx + TMX - 1) / TMX, tg.nty = (ny + TMY - 1) / TMY;
   tg.nchunk = tma_pick_chunks(tg.ntx * tg.nty, kend - kbeg, Op::MINB * ex.sm_count, ex.max_blocks);
-  const size_t smem = (size_t)TMS * Op::NIN * TILE_STRIDE * sizeof(double) + TMS * sizeof(uint64_t);
+  const size_t smem = (size_t)Op::STAGES * Op::NIN * TILE_STRIDE * sizeof(double) + Op::STAGES * sizeof(uint64_t);
   static bool  configured = false; // per template instantiation
   if (!configured) {
     FL_CUDA(cudaFuncSetAttribute(k_tma_march<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
