@@ -503,63 +503,150 @@ static void mv_zero(Solver &s, const MV &y)
 }
 
 
-// ---- fused classical Gram-Schmidt step: h_j = <V_j, w> (j < nv), ww = <w, w>; w -= sum_j h_j V_j; nrm2 = |w|^2
-struct MVSet {
-  static const int MAXV = 15; // projections per sweep (one more reduction slot carries <w, w>)
-  const double    *f[MAXV][7];
+// ---- multi-vector kernels of the outer GMRES.  A 7-field vector is streamed as NA active fields of one common length
+// plus the extra FRONT-face plane of the z-face field on the last wall rank (the only field that can be longer); the
+// number of basis vectors per launch is a template parameter, so the loops carry no run-time predicate.
+struct MVC { // compacted view
+  double *f[7];
+  int     na;   // active fields (7 in 3-D, 5 in 2-D)
+  long    len;  // common length
+  double *tail; // field with extra entries, positioned at its entry `len`; nullptr if none
+  long    ntail;
 };
+static MVC compact(const MV &m)
+{
+  MVC c;
+  c.na = 0, c.len = 0, c.tail = nullptr, c.ntail = 0;
+  for (int f = 0; f < 7; ++f) c.f[f] = nullptr;
+  for (int f = 0; f < 7; ++f)
+    if (m.len[f] > 0 && (c.len == 0 || m.len[f] < c.len)) c.len = m.len[f];
+  for (int f = 0; f < 7; ++f)
+    if (m.len[f] > 0) {
+      if (m.len[f] > c.len) c.tail = m.f[f] + c.len, c.ntail = m.len[f] - c.len;
+      c.f[c.na++] = m.f[f];
+    }
+  return c;
+}
+static const int MVB = 8; // basis vectors per launch
+template <int NC>
+struct MVCSet {
+  MVC v[NC];
+};
+
+// red[j] = <V_j, w> (j < NC), red[NC] = <w, w>
+template <int NC>
+static void mv_dots_t(Solver &s, const MV *V, const MV &w, double *red)
+{
+  MVCSet<NC> S;
+  for (int j = 0; j < NC; ++j) S.v[j] = compact(V[j]);
+  const MVC W = compact(w);
+  for_range_reduce<NC + 1>(s.ex, W.len, FL_LAMBDA(long i, double acc[NC + 1]) {
+    double t = 0., d[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) d[j] = 0.;
+#pragma unroll
+    for (int f = 0; f < 7; ++f)
+      if (f < W.na) {
+        const double wv = W.f[f][i];
+        t += wv * wv;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) d[j] += S.v[j].f[f][i] * wv;
+      }
+    if (i < W.ntail) {
+      const double wv = W.tail[i];
+      t += wv * wv;
+#pragma unroll
+      for (int j = 0; j < NC; ++j) d[j] += S.v[j].tail[i] * wv;
+    }
+#pragma unroll
+    for (int j = 0; j < NC; ++j) acc[j] += d[j];
+    acc[NC] += t;
+  });
+  reduce_finish(s, NC + 1, red);
+}
 
 struct MVCoef {
-  double c[MVSet::MAXV];
+  double c[MVB];
 };
 
+// out = beta * w + sum_j c_j V_j ; returns |out|^2.  out may be w itself.
+template <int NC>
+static double mv_comb_t(Solver &s, const MV *V, const double *c, double beta, const MV &w, const MV &out)
+{
+  MVCSet<NC> S;
+  for (int j = 0; j < NC; ++j) S.v[j] = compact(V[j]);
+  const MVC W = compact(w), O = compact(out);
+  MVCoef    C;
+  for (int j = 0; j < MVB; ++j) C.c[j] = j < NC ? c[j] : 0.;
+  for_range_reduce<1>(s.ex, W.len, FL_LAMBDA(long i, double acc[1]) {
+    double t = 0.;
+#pragma unroll
+    for (int f = 0; f < 7; ++f)
+      if (f < W.na) {
+        double wv = beta == 0. ? 0. : beta * W.f[f][i];
+#pragma unroll
+        for (int j = 0; j < NC; ++j) wv += C.c[j] * S.v[j].f[f][i];
+        O.f[f][i] = wv;
+        t += wv * wv;
+      }
+    if (i < W.ntail) {
+      double wv = beta == 0. ? 0. : beta * W.tail[i];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) wv += C.c[j] * S.v[j].tail[i];
+      O.tail[i] = wv;
+      t += wv * wv;
+    }
+    acc[0] += t;
+  });
+  double r;
+  reduce_finish(s, 1, &r);
+  return r;
+}
+
+#define MV_DISPATCH(nc, CALL) \
+  switch (nc) { \
+  case 1: CALL(1); break; \
+  case 2: CALL(2); break; \
+  case 3: CALL(3); break; \
+  case 4: CALL(4); break; \
+  case 5: CALL(5); break; \
+  case 6: CALL(6); break; \
+  case 7: CALL(7); break; \
+  default: CALL(8); break; \
+  }
+
+// out = beta * w + sum_{j < nv} c_j V_j in blocks of MVB vectors; returns |out|^2
+static double mv_lincomb(Solver &s, const std::vector<MV> &V, int nv, const double *c, double beta, const MV &w, const MV &out)
+{
+  double nrm2 = 0.;
+  if (nv == 0) {
+    mv_axpby(s, beta, w, 0., out);
+    return mv_dot(s, out, out);
+  }
+  for (int j0 = 0; j0 < nv; j0 += MVB) {
+    const int nc = nv - j0 < MVB ? nv - j0 : MVB;
+#define CALL(N) nrm2 = mv_comb_t<N>(s, &V[j0], c + j0, j0 == 0 ? beta : 1., j0 == 0 ? w : out, out)
+    MV_DISPATCH(nc, CALL)
+#undef CALL
+  }
+  return nrm2;
+}
+
+// fused classical Gram-Schmidt step: h_j = <V_j, w> (j < nv), ww = <w, w>; w -= sum_j h_j V_j; nrm2 = |w|^2
 static void mv_project(Solver &s, const std::vector<MV> &V, int nv, const MV &w, double *h, double &ww, double &nrm2)
 {
   ww = 0.;
-  for (int j0 = 0; j0 < nv; j0 += MVSet::MAXV) {
-    const int nc = nv - j0 < MVSet::MAXV ? nv - j0 : MVSet::MAXV;
-    MVSet     S;
-    for (int j = 0; j < MVSet::MAXV; ++j)
-      for (int f = 0; f < 7; ++f) S.f[j][f] = j < nc ? V[j0 + j].f[f] : nullptr;
-    for_range_reduce<MVSet::MAXV + 1>(s.ex, w.n, FL_LAMBDA(long i, double acc[MVSet::MAXV + 1]) {
-      double wv[7];
-#pragma unroll
-      for (int f = 0; f < 7; ++f) wv[f] = i < w.len[f] ? w.f[f][i] : 0.;
-      double t = 0.;
-#pragma unroll
-      for (int f = 0; f < 7; ++f) t += wv[f] * wv[f];
-      acc[MVSet::MAXV] += t;
-#pragma unroll
-      for (int j = 0; j < MVSet::MAXV; ++j)
-        if (j < nc) {
-          double d = 0.;
-#pragma unroll
-          for (int f = 0; f < 7; ++f)
-            if (i < w.len[f]) d += S.f[j][f][i] * wv[f];
-          acc[j] += d;
-        }
-    });
-    double red[MVSet::MAXV + 1];
-    reduce_finish(s, MVSet::MAXV + 1, red);
-    if (j0 == 0) ww = red[MVSet::MAXV];
-    MVCoef C;
-    for (int j = 0; j < MVSet::MAXV; ++j) C.c[j] = j < nc ? red[j] : 0.;
-    for (int j = 0; j < nc; ++j) h[j0 + j] = red[j];
-    for_range_reduce<1>(s.ex, w.n, FL_LAMBDA(long i, double acc[1]) {
-      double t = 0.;
-#pragma unroll
-      for (int f = 0; f < 7; ++f)
-        if (i < w.len[f]) {
-          double wv = w.f[f][i];
-#pragma unroll
-          for (int j = 0; j < MVSet::MAXV; ++j)
-            if (j < nc) wv -= C.c[j] * S.f[j][f][i];
-          w.f[f][i] = wv;
-          t += wv * wv;
-        }
-      acc[0] += t;
-    });
-    reduce_finish(s, 1, &nrm2);
+  for (int j0 = 0; j0 < nv; j0 += MVB) {
+    const int nc = nv - j0 < MVB ? nv - j0 : MVB;
+    double    red[MVB + 1], neg[MVB];
+#define CALL(N) mv_dots_t<N>(s, &V[j0], w, red)
+    MV_DISPATCH(nc, CALL)
+#undef CALL
+    if (j0 == 0) ww = red[nc];
+    for (int j = 0; j < nc; ++j) h[j0 + j] = red[j], neg[j] = -red[j];
+#define CALL(N) nrm2 = mv_comb_t<N>(s, &V[j0], neg, 1., w, w)
+    MV_DISPATCH(nc, CALL)
+#undef CALL
   }
 }
 
@@ -580,14 +667,13 @@ static int outer_gmres(Solver &s)
   s.stats.nhist = 0;
   while (!done) {
     // r = b - M x
-    if (first_cycle) mv_axpby(s, 1., Bv, 0., V[0]);
+    const double one = 1.;
+    if (first_cycle) rnorm = std::sqrt(mv_comb_t<1>(s, &Bv, &one, 0., V[0], V[0])); // V0 = b and its norm in one pass
     else {
       coupled_apply(s, s.xv, s.xU, s.xp, s.wv, s.wU, s.wp);
-      mv_axpby(s, 1., Bv, 0., V[0]);
-      mv_axpby(s, -1., W, 1., V[0]);
+      rnorm = std::sqrt(mv_comb_t<1>(s, &Bv, &one, -1., W, V[0])); // V0 = b - M x
     }
     first_cycle = false;
-    rnorm = std::sqrt(mv_dot(s, V[0], V[0]));
     if (rnorm0 < 0.) {
       rnorm0 = rnorm;
       if (s.stats.nhist < 128) s.stats.hist[s.stats.nhist++] = rnorm;
@@ -656,8 +742,7 @@ static int outer_gmres(Solver &s)
       for (int l = jx + 1; l < k; ++l) sum -= H[(size_t)jx * m + l] * y[l];
       y[jx] = sum / H[(size_t)jx * m + jx];
     }
-    mv_zero(s, W);
-    for (int jx = 0; jx < k; ++jx) mv_axpby(s, y[jx], V[jx], 1., W);
+    (void)mv_lincomb(s, V, k, y.data(), 0., W, W); // W = sum_j y_j V_j in one pass
     abf_apply(s, s.wv, s.wU, s.wp, s.zv, s.zU, s.zp);
     mv_axpby(s, 1., Z, 1., X);
     if (its >= s.opt.outer_maxit) done = true;
