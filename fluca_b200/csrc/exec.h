@@ -109,7 +109,7 @@ struct Exec {
   // reduction scratch
   double      *d_partials = nullptr; // [max_blocks * MAXR]
   double      *d_result   = nullptr; // [MAXR]
-  double      *d_carry    = nullptr; // [2][MAXR] partial sums handed from one launch of a reduction to the next
+  double      *d_carry    = nullptr; // [4][MAXR] partial sums handed from one launch of a reduction to the next
   unsigned    *d_ticket   = nullptr;
   double      *h_result   = nullptr; // pinned [MAXR]
   long         max_blocks = 0;
@@ -217,13 +217,13 @@ inline void Exec::init()
   max_blocks = 8192;
   d_partials = (double *)dev_alloc(sizeof(double) * max_blocks * MAXR);
   d_result   = (double *)dev_alloc(sizeof(double) * MAXR);
-  d_carry    = (double *)dev_alloc(sizeof(double) * MAXR * 2);
+  d_carry    = (double *)dev_alloc(sizeof(double) * MAXR * 4);
   d_ticket   = (unsigned *)dev_alloc(sizeof(unsigned));
   FL_CUDA(cudaMallocHost((void **)&h_result, sizeof(double) * MAXR));
 #else
   h_result = (double *)calloc(MAXR, sizeof(double));
   d_result = (double *)calloc(MAXR, sizeof(double));
-  d_carry  = (double *)calloc(2 * MAXR, sizeof(double));
+  d_carry  = (double *)calloc(4 * MAXR, sizeof(double));
 #endif
 }
 inline void Exec::destroy()

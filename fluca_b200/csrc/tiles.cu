@@ -209,7 +209,9 @@ struct AApplyTile {
   struct Regs {
     double a[3];
   };
-  __device__ int flags(int i, int j) const { return (i > 0 && i < g.nx - 1 && j > 0 && j < g.ny - 1) ? 1 : 0; }
+  // bit 0: no wall in reach in x and y; bit 1: x-wall column, computed by the transposed wall launch instead (a single
+  // wall lane would send its whole warp down the table-driven path: 12-25 % of the warps, profiles/r01p)
+  __device__ int flags(int i, int j) const { return ((i > 0 && i < g.nx - 1 && j > 0 && j < g.ny - 1) ? 1 : 0) | ((i == 0 || i == g.nx - 1) ? 2 : 0); }
   __device__ void prefetch(Regs &rg, int off, int kl) const
   {
     if (NRED > 0) {
@@ -221,7 +223,8 @@ struct AApplyTile {
   __device__ void cell(const TileView &tv, const Regs &rg, int fl, int i, int j, int kl, int c, double *acc) const
   {
     double     r[3];
-    if (__all_sync(__activemask(), fl != 0)) {
+    if (fl & 2) return;
+    if (__all_sync(__activemask(), (fl & 1) != 0)) {
       if (uniform) a_apply_tile_uniform(uc, sp, tv, r);
       else a_apply_tile<false>(g, sp, bc, tv, i, j, kl, r);
     } else a_apply_tile<true>(g, sp, bc, tv, i, j, kl, r);
@@ -245,6 +248,14 @@ struct PlaneAt {
   F   f;
   int kl;
   FL_HD void operator()(int i, int j, int, double *acc) const { f(i, j, kl, acc); }
+};
+
+// the two x-wall columns of planes [kbeg, kend): threads run over j so that a warp holds 32 wall cells
+template <class F>
+struct XWallAt {
+  F   f;
+  int i, kbeg;
+  FL_HD void operator()(int a, int, int c, double *acc) const { f(i, a, kbeg + c, acc); }
 };
 
 // y = A x ; out[0] = <a, y>, out[1] = <y, y> are left in ex.d_result (reduce_finish reads them)
@@ -274,7 +285,17 @@ void a_apply_dots_tma(Solver &s, const V3 &x, const V3 &y, const V3 &a, bool wit
     for_box_reduce<2>(s.ex, plane_box, pf, carry, res);
     carry = res, ++ncar;
   }
-  // 2. everything else through the TMA pipeline
+  // 2. the x-wall columns of the remaining planes
+  if (kend > kbeg) {
+    const Box wall_box = {g.ny, 1, kend - kbeg};
+    for (int side = 0; side < 2; ++side) {
+      XWallAt<AApplyDots<3>> xf = {f, side ? g.nx - 1 : 0, kbeg};
+      double                *res = s.ex.d_carry + Exec::MAXR * ncar;
+      for_box_reduce<2>(s.ex, wall_box, xf, carry, res);
+      carry = res, ++ncar;
+    }
+  }
+  // 3. everything else through the TMA pipeline
   const double *fields[9] = {x.c[0], x.c[1], x.c[2], s.v0.c[0], s.v0.c[1], s.v0.c[2], s.U0.c[0], s.U0.c[1], s.U0.c[2]};
   UniCoef       uc;
   static const bool no_uni = getenv("FLUCA_B200_NO_UNIFORM") != nullptr;
@@ -292,6 +313,7 @@ void a_apply_dots_tma(Solver &s, const V3 &x, const V3 &y, const V3 &a, bool wit
     for (int c = 0; c < 3; ++c) op.a[c] = nullptr, op.y[c] = y.c[c];
     tma_launch(s.ex, op, fields, g.px, g.py, g.nzl + 2, g.nx, g.ny, kbeg, kend, nullptr);
   }
+  (void)ncar;
 }
 
 // ------------------------------------------------------------------ Poisson operator from shared-memory tiles
