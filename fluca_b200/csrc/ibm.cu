@@ -462,7 +462,7 @@ void ibm_force_rhs(Solver &s)
 {
   Ibm &b = s.ibm;
   if (b.n <= 0) return;
-  momentum_solve(s, s.rm, s.vstar); // predictor v~ = A^-1 r_mom
+  momentum_solve(s, s.rm, s.vstar, s.have_guess); // predictor v~ = A^-1 r_mom (guess: previous velocity, do_step)
   const int    dim = s.dim, passes = b.iters > 1 ? b.iters : 1;
   const long   n = b.n;
   const double fscale = s.sp.rho / s.sp.dt;
@@ -481,8 +481,11 @@ void ibm_force_rhs(Solver &s)
         }
       });
     }
-    ibm_spread(s, b.Dl, s.rm, passes > 1 ? &s.vstar : nullptr);
+    // the increment also goes into the predictor: multi-direct forcing needs it, and v~ + f is the guess of the first
+    // momentum solve of the step (A (v~ + f) = r_mom + f + O(dt) f)
+    ibm_spread(s, b.Dl, s.rm, &s.vstar);
   }
+  s.have_guess = s.allow_guess;
 }
 
 } // namespace fluca

@@ -56,33 +56,59 @@ static P3 off3(const Solver &s, const V3 &v)
   return r;
 }
 
-int momentum_solve(Solver &s, const V3 &b, const V3 &x)
+// guess: x holds an initial guess on entry (the previous velocity, or the forced predictor of the IBM coupling); the
+// tolerance stays relative to |b|, as PETSc's default convergence test does with a non-zero guess
+int momentum_solve(Solver &s, const V3 &b, const V3 &x, bool guess)
 {
   KScope ks(s.ex, KT_MOMENTUM_VEC);
   const int    nc  = s.dim;
   const long   len = interior_len(s);
   const P3     B = off3(s, b), X = off3(s, x), R = off3(s, s.kr), RH = off3(s, s.krh), PV = off3(s, s.kp), VV = off3(s, s.kv), SV = off3(s, s.ks), TV = off3(s, s.kt);
   double       red[4];
-  // x = 0, r = rhat = p = b, rho = <b, b>
-  for_range_reduce<1>(s.ex, len, FL_LAMBDA(long i, double acc[1]) {
-    double t = 0.;
-    _Pragma("unroll") for (int q = 0; q < 3; ++q) if (q < nc) {
-      const double bv = B.c[q][i];
-      X.c[q][i]  = 0.;
-      R.c[q][i]  = bv;
-      RH.c[q][i] = bv;
-      PV.c[q][i] = bv;
-      t += bv * bv;
-    }
-    acc[0] += t;
-  });
-  reduce_finish(s, 1, red);
-  const double bnorm = std::sqrt(red[0]);
+  if (!guess) {
+    // x = 0, r = rhat = p = b, rho = <b, b>
+    for_range_reduce<2>(s.ex, len, FL_LAMBDA(long i, double acc[2]) {
+      double t = 0.;
+      _Pragma("unroll") for (int q = 0; q < 3; ++q) if (q < nc) {
+        const double bv = B.c[q][i];
+        X.c[q][i]  = 0.;
+        R.c[q][i]  = bv;
+        RH.c[q][i] = bv;
+        PV.c[q][i] = bv;
+        t += bv * bv;
+      }
+      acc[0] += t;
+      acc[1] += t;
+    });
+  } else {
+    // r = rhat = p = b - A x, rho = <r, r>
+    a_apply(s, x, s.kv);
+    for_range_reduce<2>(s.ex, len, FL_LAMBDA(long i, double acc[2]) {
+      double t = 0., tb = 0.;
+      _Pragma("unroll") for (int q = 0; q < 3; ++q) if (q < nc) {
+        const double bv = B.c[q][i], rv = bv - VV.c[q][i];
+        R.c[q][i]  = rv;
+        RH.c[q][i] = rv;
+        PV.c[q][i] = rv;
+        t += rv * rv;
+        tb += bv * bv;
+      }
+      acc[0] += t;
+      acc[1] += tb;
+    });
+  }
+  reduce_finish(s, 2, red);
+  const double bnorm = std::sqrt(red[1]);
   s.stats.mom_last_rel = 0.;
-  if (bnorm == 0.) return 0;
+  if (bnorm == 0.) {
+    if (guess) for_range(s.ex, len, FL_LAMBDA(long i) { _Pragma("unroll") for (int q = 0; q < 3; ++q) if (q < nc) X.c[q][i] = 0.; });
+    return 0;
+  }
   if (!(bnorm == bnorm)) throw Error(FL_ERR_DIVERGED, "momentum right-hand side is NaN");
   const double tol = s.opt.mom_rtol * bnorm;
   double       rho = red[0], alpha = 1., omega = 1.;
+  s.stats.mom_last_rel = std::sqrt(red[0]) / bnorm;
+  if (std::sqrt(red[0]) <= tol) return 0; // the guess already meets the tolerance
   int          it = 0;
   for (; it < s.opt.inner_maxit;) {
     // v = A p, <rhat, v>

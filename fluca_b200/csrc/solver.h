@@ -134,6 +134,8 @@ struct Solver {
   int    step_index = 0;
   double t          = 0.;
   bool   prepared   = false;
+  bool   allow_guess = true;  // FLUCA_B200_NO_GUESS unsets it (A/B timing)
+  bool   have_guess = false; // s.vstar holds a guess of the first momentum solve of the step (unscaled)
 
   double *alloc_field();
   V3      alloc_v3();
@@ -159,7 +161,8 @@ long face_len(const Solver &s, int d);              // interior_len (+ one plane
 // operators (step.cu)
 void prepare_step(Solver &s, double t, int step_index);
 void a_apply(Solver &s, const V3 &x, const V3 &y);
-void abf_apply(Solver &s, const V3 &bm, const V3 &bi, const double *bcn, const V3 &ov, const V3 &oU, double *op);
+// guess: s.vstar holds an initial guess of the momentum solve
+void abf_apply(Solver &s, const V3 &bm, const V3 &bi, const double *bcn, const V3 &ov, const V3 &oU, double *op, bool guess = false);
 void coupled_apply(Solver &s, const V3 &xv, const V3 &xU, double *xp, const V3 &yv, const V3 &yU, double *yp);
 void schur_apply_reference_scaling(Solver &s, double *pin, double *out);
 int  do_step(Solver &s, double t, int step_index);
@@ -172,7 +175,7 @@ void poisson_apply_dot_tma(Solver &s, const double *pin, double *out, const doub
 #endif
 
 // Krylov / multigrid (krylov.cu, mg.cu)
-int  momentum_solve(Solver &s, const V3 &b, const V3 &x);
+int  momentum_solve(Solver &s, const V3 &b, const V3 &x, bool guess = false);
 int  poisson_solve(Solver &s, double *b, double *x);
 void mg_setup(Solver &s);
 void mg_destroy(Solver &s);

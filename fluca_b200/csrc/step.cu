@@ -362,12 +362,12 @@ static void remove_mean(Solver &s, double *f)
 }
 
 template <int DIM>
-static void abf_apply_t(Solver &s, const V3 &bm, const V3 &bi, const double *bcn, const V3 &ov, const V3 &oU, double *op)
+static void abf_apply_t(Solver &s, const V3 &bm, const V3 &bi, const double *bcn, const V3 &ov, const V3 &oU, double *op, bool guess)
 {
   KScope ks(s.ex, KT_RHS_PROJECT);
   const Geom &g = s.gh.g;
   // stage 1 (abfpc.c:72-77)
-  momentum_solve(s, bm, s.vstar);
+  momentum_solve(s, bm, s.vstar, guess);
   halo_cells(s, s.vstar);
   FaceCombine<DIM> fc;
   fc.g = g, fc.a = 1., fc.b = 1., fc.c = 0., fc.in = CV3(bi), fc.w = CV3(s.vstar), fc.p = nullptr, fc.out = s.Ustar;
@@ -397,9 +397,9 @@ static void abf_apply_t(Solver &s, const V3 &bm, const V3 &bi, const double *bcn
   s.stats.abf_applies++;
 }
 
-void abf_apply(Solver &s, const V3 &bm, const V3 &bi, const double *bcn, const V3 &ov, const V3 &oU, double *op)
+void abf_apply(Solver &s, const V3 &bm, const V3 &bi, const double *bcn, const V3 &ov, const V3 &oU, double *op, bool guess)
 {
-  DIM_DISPATCH(s, abf_apply_t<2>(s, bm, bi, bcn, ov, oU, op), abf_apply_t<3>(s, bm, bi, bcn, ov, oU, op));
+  DIM_DISPATCH(s, abf_apply_t<2>(s, bm, bi, bcn, ov, oU, op, guess), abf_apply_t<3>(s, bm, bi, bcn, ov, oU, op, guess));
 }
 
 template <int DIM>
@@ -692,7 +692,20 @@ static int outer_gmres(Solver &s)
       // z = ABF(v_k); w = M z
       V3 kv, kU;
       for (int c = 0; c < 3; ++c) kv.c[c] = s.basis[k][c], kU.c[c] = s.basis[k][3 + c];
-      abf_apply(s, kv, kU, s.basis[k][6], s.zv, s.zU, s.zp);
+      bool guess = false;
+      if (s.have_guess && its == 0) {
+        // the right-hand side of this application is b / |b|: scale the guess of A^-1 b_mom likewise
+        const double sc = 1. / rnorm;
+        const long   off = interior_off(s), len = interior_len(s);
+        double      *g0 = s.vstar.c[0] + off, *g1 = s.vstar.c[1] + off, *g2 = s.dim == 3 ? s.vstar.c[2] + off : nullptr;
+        for_range(s.ex, len, FL_LAMBDA(long i) {
+          g0[i] *= sc;
+          g1[i] *= sc;
+          if (g2) g2[i] *= sc;
+        });
+        guess = true;
+      }
+      abf_apply(s, kv, kU, s.basis[k][6], s.zv, s.zU, s.zp, guess);
       V3 nv, nU;
       for (int c = 0; c < 3; ++c) nv.c[c] = s.basis[k + 1][c], nU.c[c] = s.basis[k + 1][3 + c];
       coupled_apply(s, s.zv, s.zU, s.zp, nv, nU, s.basis[k + 1][6]);
@@ -759,11 +772,16 @@ int do_step(Solver &s, double t, int step_index)
   const long l0 = s.ex.stats.launches;
   s.stats       = Stats();
   prepare_step(s, t, step_index);
+  // initial guess of the first momentum solve: the velocity of the previous step (v* = v^n + O(dt))
+  s.allow_guess = getenv("FLUCA_B200_NO_GUESS") == nullptr;
+  s.have_guess  = s.allow_guess && step_index > 0;
+  if (s.have_guess)
+    for (int c = 0; c < s.dim; ++c) copy_d2d(s.ex, s.vstar.c[c], s.v0.c[c], sizeof(double) * (size_t)s.gh.g.nalloc);
   if (s.ibm.n > 0) ibm_force_rhs(s); // immersed-boundary forcing joins the momentum right-hand side (ibm.h)
   if (!s.has_outlet) remove_mean(s, s.rc); // F(0) = -b with the null space removed (nsbasic.c:133-144)
   int rc = 0;
   if (s.opt.mode == 1) {
-    abf_apply(s, s.rm, s.ri, s.rc, s.xv, s.xU, s.xp);
+    abf_apply(s, s.rm, s.ri, s.rc, s.xv, s.xU, s.xp, s.have_guess);
     s.stats.converged = 1;
   } else {
     rc = outer_gmres(s);
