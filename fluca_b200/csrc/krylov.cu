@@ -56,9 +56,9 @@ static P3 off3(const Solver &s, const V3 &v)
   return r;
 }
 
-// guess: x holds an initial guess on entry (the previous velocity, or the forced predictor of the IBM coupling); the
+// the system solved is A x = bscale * b.  guess: x holds an initial guess on entry (the previous velocity, or the forced predictor of the IBM coupling); the
 // tolerance stays relative to |b|, as PETSc's default convergence test does with a non-zero guess
-int momentum_solve(Solver &s, const V3 &b, const V3 &x, bool guess)
+int momentum_solve(Solver &s, const V3 &b, const V3 &x, bool guess, double bscale)
 {
   KScope ks(s.ex, KT_MOMENTUM_VEC);
   const int    nc  = s.dim;
@@ -70,7 +70,7 @@ int momentum_solve(Solver &s, const V3 &b, const V3 &x, bool guess)
     for_range_reduce<2>(s.ex, len, FL_LAMBDA(long i, double acc[2]) {
       double t = 0.;
       _Pragma("unroll") for (int q = 0; q < 3; ++q) if (q < nc) {
-        const double bv = B.c[q][i];
+        const double bv = bscale * B.c[q][i];
         X.c[q][i]  = 0.;
         R.c[q][i]  = bv;
         RH.c[q][i] = bv;
@@ -86,7 +86,7 @@ int momentum_solve(Solver &s, const V3 &b, const V3 &x, bool guess)
     for_range_reduce<2>(s.ex, len, FL_LAMBDA(long i, double acc[2]) {
       double t = 0., tb = 0.;
       _Pragma("unroll") for (int q = 0; q < 3; ++q) if (q < nc) {
-        const double bv = B.c[q][i], rv = bv - VV.c[q][i];
+        const double bv = bscale * B.c[q][i], rv = bv - VV.c[q][i];
         R.c[q][i]  = rv;
         RH.c[q][i] = rv;
         PV.c[q][i] = rv;

@@ -123,7 +123,7 @@ struct Solver {
   std::vector<MGLevel> mg;
   std::vector<void *>  mg_owned;
   // outer GMRES basis: (restart + 1) vectors of 7 fields, plus work vectors
-  std::vector<std::vector<double *>> basis;
+  std::vector<std::vector<double *>> basis, zbasis; // zbasis[k] = ABF(basis[k]) (flexible GMRES: no final application)
   V3      wv, wU, zv, zU, tw;
   double *wp = nullptr, *zp = nullptr;
   int     basis_size = 0;
@@ -162,7 +162,8 @@ long face_len(const Solver &s, int d);              // interior_len (+ one plane
 void prepare_step(Solver &s, double t, int step_index);
 void a_apply(Solver &s, const V3 &x, const V3 &y);
 // guess: s.vstar holds an initial guess of the momentum solve
-void abf_apply(Solver &s, const V3 &bm, const V3 &bi, const double *bcn, const V3 &ov, const V3 &oU, double *op, bool guess = false);
+// in_scale: the application acts on in_scale * (bm, bi, bcn) (the outer Krylov basis is stored unnormalised)
+void abf_apply(Solver &s, const V3 &bm, const V3 &bi, const double *bcn, const V3 &ov, const V3 &oU, double *op, bool guess = false, double in_scale = 1.);
 void coupled_apply(Solver &s, const V3 &xv, const V3 &xU, double *xp, const V3 &yv, const V3 &yU, double *yp);
 void schur_apply_reference_scaling(Solver &s, double *pin, double *out);
 int  do_step(Solver &s, double t, int step_index);
@@ -175,7 +176,7 @@ void poisson_apply_dot_tma(Solver &s, const double *pin, double *out, const doub
 #endif
 
 // Krylov / multigrid (krylov.cu, mg.cu)
-int  momentum_solve(Solver &s, const V3 &b, const V3 &x, bool guess = false);
+int  momentum_solve(Solver &s, const V3 &b, const V3 &x, bool guess = false, double bscale = 1.);
 int  poisson_solve(Solver &s, double *b, double *x);
 void mg_setup(Solver &s);
 void mg_destroy(Solver &s);

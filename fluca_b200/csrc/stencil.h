@@ -362,6 +362,7 @@ template <int DIM>
 struct PoissonRhs {
   Geom          g;
   double        scale;
+  double        rcscale; // the continuity right-hand side enters as rcscale * rc
   CV3           U;
   const double *rc;
   double       *out;
@@ -376,7 +377,7 @@ struct PoissonRhs {
       if (rc) fl_prefetch(rc + ahead);
     }
     double vol, fl = div_flux<DIM>(g, U, nb, vol);
-    double s = scale * ((rc ? vol * rc[nb.c] : 0.) - fl);
+    double s = scale * ((rc ? vol * rcscale * rc[nb.c] : 0.) - fl);
     out[nb.c] = s;
     acc[0] += s;
   }

@@ -177,8 +177,15 @@ void solver_setup(Solver &s, int dim, const int n[3], const double *const xf[3],
       for (int f = 0; f < 7; ++f)
         if (dim == 3 || (f != 2 && f != 5)) vec[f] = s.alloc_field();
     }
+    s.zbasis.resize(opt.outer_restart);
+    for (auto &vec : s.zbasis) {
+      vec.resize(7, nullptr);
+      for (int f = 0; f < 7; ++f)
+        if (dim == 3 || (f != 2 && f != 5)) vec[f] = s.alloc_field();
+    }
     s.wv = s.alloc_v3(), s.wU = s.alloc_v3(), s.wp = s.alloc_field();
-    s.zv = s.alloc_v3(), s.zU = s.alloc_v3(), s.zp = s.alloc_field();
+    for (int c = 0; c < 3; ++c) s.zv.c[c] = s.zbasis[0][c], s.zU.c[c] = s.zbasis[0][3 + c];
+    s.zp = s.zbasis[0][6];
   }
   mg_setup(s);
   s.ex.sync();
@@ -362,19 +369,19 @@ static void remove_mean(Solver &s, double *f)
 }
 
 template <int DIM>
-static void abf_apply_t(Solver &s, const V3 &bm, const V3 &bi, const double *bcn, const V3 &ov, const V3 &oU, double *op, bool guess)
+static void abf_apply_t(Solver &s, const V3 &bm, const V3 &bi, const double *bcn, const V3 &ov, const V3 &oU, double *op, bool guess, double in_scale)
 {
   KScope ks(s.ex, KT_RHS_PROJECT);
   const Geom &g = s.gh.g;
   // stage 1 (abfpc.c:72-77)
-  momentum_solve(s, bm, s.vstar, guess);
+  momentum_solve(s, bm, s.vstar, guess, in_scale);
   halo_cells(s, s.vstar);
   FaceCombine<DIM> fc;
-  fc.g = g, fc.a = 1., fc.b = 1., fc.c = 0., fc.in = CV3(bi), fc.w = CV3(s.vstar), fc.p = nullptr, fc.out = s.Ustar;
+  fc.g = g, fc.a = in_scale, fc.b = 1., fc.c = 0., fc.in = CV3(bi), fc.w = CV3(s.vstar), fc.p = nullptr, fc.out = s.Ustar;
   for_box<2>(s.ex, cell_box(s), fc);
   halo_faces(s, s.Ustar);
   PoissonRhs<DIM> pr;
-  pr.g = g, pr.scale = s.sp.rho / s.sp.dt, pr.U = CV3(s.Ustar), pr.rc = bcn, pr.out = s.srhs;
+  pr.g = g, pr.scale = s.sp.rho / s.sp.dt, pr.rcscale = in_scale, pr.U = CV3(s.Ustar), pr.rc = bcn, pr.out = s.srhs;
   for_box_reduce<1>(s.ex, cell_box(s), pr);
   if (!s.has_outlet) {
     // constant null space (abfpc.c:173-177): make the right-hand side compatible
@@ -397,9 +404,9 @@ static void abf_apply_t(Solver &s, const V3 &bm, const V3 &bi, const double *bcn
   s.stats.abf_applies++;
 }
 
-void abf_apply(Solver &s, const V3 &bm, const V3 &bi, const double *bcn, const V3 &ov, const V3 &oU, double *op, bool guess)
+void abf_apply(Solver &s, const V3 &bm, const V3 &bi, const double *bcn, const V3 &ov, const V3 &oU, double *op, bool guess, double in_scale)
 {
-  DIM_DISPATCH(s, abf_apply_t<2>(s, bm, bi, bcn, ov, oU, op, guess), abf_apply_t<3>(s, bm, bi, bcn, ov, oU, op, guess));
+  DIM_DISPATCH(s, abf_apply_t<2>(s, bm, bi, bcn, ov, oU, op, guess, in_scale), abf_apply_t<3>(s, bm, bi, bcn, ov, oU, op, guess, in_scale));
 }
 
 template <int DIM>
@@ -632,8 +639,9 @@ static double mv_lincomb(Solver &s, const std::vector<MV> &V, int nv, const doub
   return nrm2;
 }
 
-// fused classical Gram-Schmidt step: h_j = <V_j, w> (j < nv), ww = <w, w>; w -= sum_j h_j V_j; nrm2 = |w|^2
-static void mv_project(Solver &s, const std::vector<MV> &V, int nv, const MV &w, double *h, double &ww, double &nrm2)
+// fused classical Gram-Schmidt step against the UNNORMALISED basis V_j (norms vn_j): h_j = <V_j, w> / vn_j (j < nv),
+// ww = <w, w>; w -= sum_j (h_j / vn_j) V_j; nrm2 = |w|^2
+static void mv_project(Solver &s, const std::vector<MV> &V, const double *vn, int nv, const MV &w, double *h, double &ww, double &nrm2)
 {
   ww = 0.;
   for (int j0 = 0; j0 < nv; j0 += MVB) {
@@ -643,32 +651,37 @@ static void mv_project(Solver &s, const std::vector<MV> &V, int nv, const MV &w,
     MV_DISPATCH(nc, CALL)
 #undef CALL
     if (j0 == 0) ww = red[nc];
-    for (int j = 0; j < nc; ++j) h[j0 + j] = red[j], neg[j] = -red[j];
+    for (int j = 0; j < nc; ++j) h[j0 + j] = red[j] / vn[j0 + j], neg[j] = -h[j0 + j] / vn[j0 + j];
 #define CALL(N) nrm2 = mv_comb_t<N>(s, &V[j0], neg, 1., w, w)
     MV_DISPATCH(nc, CALL)
 #undef CALL
   }
 }
 
-// right-preconditioned restarted GMRES on M x = b, PC = ABF, zero initial guess, true-residual
-// norm; x is built in (s.xv, s.xU, s.xp)
+// Right-preconditioned restarted GMRES on M x = b, PC = ABF, zero initial guess, true-residual norm (the outer KSP of
+// nssol.c:13-30); x is built in (s.xv, s.xU, s.xp).  Two things differ from a textbook loop, neither changes the iterates:
+//  * the preconditioned vectors z_k = ABF(v_k) are kept (flexible form), so the solution update x += sum_k y_k z_k needs no
+//    further ABF application -- PETSc's KSPGMRES applies the preconditioner once more per cycle to build the solution;
+//  * basis vectors are stored unnormalised with their norms on the host (the first one is b itself, never copied): the
+//    scale goes into the ABF application and the Gram-Schmidt coefficients instead of an extra pass over 7 fields.
 static int outer_gmres(Solver &s)
 {
   KScope ks(s.ex, KT_OUTER);
   const int m = s.opt.outer_restart;
-  MV        X = make_mv(s, s.xv, s.xU, s.xp), Bv = make_mv(s, s.rm, s.ri, s.rc), W = make_mv(s, s.wv, s.wU, s.wp), Z = make_mv(s, s.zv, s.zU, s.zp);
-  std::vector<MV> V;
+  MV        X = make_mv(s, s.xv, s.xU, s.xp), Bv = make_mv(s, s.rm, s.ri, s.rc), W = make_mv(s, s.wv, s.wU, s.wp);
+  std::vector<MV> V, Zb;
   for (auto &b : s.basis) V.push_back(make_mv(s, b));
-  std::vector<double> H((size_t)(m + 1) * m, 0.), cs(m), sn(m), gvec(m + 1), y(m);
-  mv_zero(s, X);
+  for (auto &b : s.zbasis) Zb.push_back(make_mv(s, b));
+  std::vector<double> H((size_t)(m + 1) * m, 0.), cs(m), sn(m), gvec(m + 1), y(m), vn(m + 1, 1.);
   int    its = 0;
   double rnorm0 = -1., rnorm = 0.;
-  bool   done = false, first_cycle = true;
+  bool   done = false, first_cycle = true, x_zero = true;
   s.stats.nhist = 0;
   while (!done) {
-    // r = b - M x
+    // r = b - M x; in the first cycle x = 0 and the first basis vector is b in place
     const double one = 1.;
-    if (first_cycle) rnorm = std::sqrt(mv_comb_t<1>(s, &Bv, &one, 0., V[0], V[0])); // V0 = b and its norm in one pass
+    const bool   alias_b = first_cycle;
+    if (first_cycle) rnorm = std::sqrt(mv_dot(s, Bv, Bv));
     else {
       coupled_apply(s, s.xv, s.xU, s.xp, s.wv, s.wU, s.wp);
       rnorm = std::sqrt(mv_comb_t<1>(s, &Bv, &one, -1., W, V[0])); // V0 = b - M x
@@ -684,14 +697,21 @@ static int outer_gmres(Solver &s)
       break;
     }
     if (its >= s.opt.outer_maxit) break;
-    mv_axpby(s, 1. / rnorm, V[0], 0., V[0]);
+    std::vector<MV> Vl(V);
+    if (alias_b) Vl[0] = Bv;
+    vn[0] = rnorm;
     std::fill(gvec.begin(), gvec.end(), 0.);
     gvec[0] = rnorm;
     int k = 0;
     for (; k < m && its < s.opt.outer_maxit; ++k) {
-      // z = ABF(v_k); w = M z
-      V3 kv, kU;
-      for (int c = 0; c < 3; ++c) kv.c[c] = s.basis[k][c], kU.c[c] = s.basis[k][3 + c];
+      // z_k = ABF(v_k), v_k = V_k / vn_k; w = M z_k
+      V3      kv, kU, zv, zU;
+      double *kp = (k == 0 && alias_b) ? s.rc : s.basis[k][6], *zp = s.zbasis[k][6];
+      for (int c = 0; c < 3; ++c) {
+        kv.c[c] = (k == 0 && alias_b) ? s.rm.c[c] : s.basis[k][c];
+        kU.c[c] = (k == 0 && alias_b) ? s.ri.c[c] : s.basis[k][3 + c];
+        zv.c[c] = s.zbasis[k][c], zU.c[c] = s.zbasis[k][3 + c];
+      }
       bool guess = false;
       if (s.have_guess && its == 0) {
         // the right-hand side of this application is b / |b|: scale the guess of A^-1 b_mom likewise
@@ -705,26 +725,26 @@ static int outer_gmres(Solver &s)
         });
         guess = true;
       }
-      abf_apply(s, kv, kU, s.basis[k][6], s.zv, s.zU, s.zp, guess);
+      abf_apply(s, kv, kU, kp, zv, zU, zp, guess, 1. / vn[k]);
       V3 nv, nU;
       for (int c = 0; c < 3; ++c) nv.c[c] = s.basis[k + 1][c], nU.c[c] = s.basis[k + 1][3 + c];
-      coupled_apply(s, s.zv, s.zU, s.zp, nv, nU, s.basis[k + 1][6]);
+      coupled_apply(s, zv, zU, zp, nv, nU, s.basis[k + 1][6]);
       if (!s.has_outlet) remove_mean(s, s.basis[k + 1][6]); // null space of J (nsbasic.c:229-243)
       // classical Gram-Schmidt, all projections in one pass (PETSc's GMRES default,
       // KSPGMRESClassicalGramSchmidtOrthogonalization), re-orthogonalised only when the norm dropped by more
-      // than 1/sqrt(2) (the "refine if needed" criterion): 2 sweeps over k+2 vectors instead of 5 (k+1)
+      // than 1/sqrt(2) (the "refine if needed" criterion)
       std::vector<double> hcolv(m + 1, 0.);
       double             *hcol = hcolv.data(), ww = 0., nrm2 = 0.;
-      mv_project(s, V, k + 1, V[k + 1], hcol, ww, nrm2);
+      mv_project(s, Vl, vn.data(), k + 1, V[k + 1], hcol, ww, nrm2);
       for (int jx = 0; jx <= k; ++jx) H[(size_t)jx * m + k] = hcol[jx];
       if (nrm2 < 0.5 * ww) {
         double ww2;
-        mv_project(s, V, k + 1, V[k + 1], hcol, ww2, nrm2);
+        mv_project(s, Vl, vn.data(), k + 1, V[k + 1], hcol, ww2, nrm2);
         for (int jx = 0; jx <= k; ++jx) H[(size_t)jx * m + k] += hcol[jx];
       }
       double hn = std::sqrt(nrm2);
       H[(size_t)(k + 1) * m + k] = hn;
-      if (hn > 0.) mv_axpby(s, 1. / hn, V[k + 1], 0., V[k + 1]);
+      vn[k + 1]                  = hn > 0. ? hn : 1.;
       for (int jx = 0; jx < k; ++jx) {
         double a = H[(size_t)jx * m + k], b = H[(size_t)(jx + 1) * m + k];
         H[(size_t)jx * m + k]       = cs[jx] * a + sn[jx] * b;
@@ -749,17 +769,17 @@ static int outer_gmres(Solver &s)
         break;
       }
     }
-    // x += ABF(V y)
+    // x += sum_j y_j z_j
     for (int jx = k - 1; jx >= 0; --jx) {
       double sum = gvec[jx];
       for (int l = jx + 1; l < k; ++l) sum -= H[(size_t)jx * m + l] * y[l];
       y[jx] = sum / H[(size_t)jx * m + jx];
     }
-    (void)mv_lincomb(s, V, k, y.data(), 0., W, W); // W = sum_j y_j V_j in one pass
-    abf_apply(s, s.wv, s.wU, s.wp, s.zv, s.zU, s.zp);
-    mv_axpby(s, 1., Z, 1., X);
+    (void)mv_lincomb(s, Zb, k, y.data(), x_zero ? 0. : 1., X, X);
+    x_zero = false;
     if (its >= s.opt.outer_maxit) done = true;
   }
+  if (x_zero) mv_zero(s, X);
   s.stats.outer_its    = its;
   s.stats.outer_rnorm0 = rnorm0;
   s.stats.outer_rnorm  = rnorm;
