@@ -136,3 +136,72 @@ def test_fused_presmoothing_equals_two_sweeps(lib, mk, monkeypatch):
     z1 = s.apply_vcycle(r)
     assert parity.rel(z1, z0) < 1e-12
     fb.NSDestroy(ns)
+
+
+def test_config1_cavity2d_128_matches_oracle(lib):
+    """BASELINE config 1 at its full size (2-D lid-driven cavity Re=100, 128x128, dt=0.5h): three coupled steps at tight
+    tolerances against the oracle"""
+    out = parity.compare_steps(cases.cavity2d(n=128), lib, mode="coupled", nsteps=3, tol=1e-10)
+    assert all(o["outer"][0] == o["outer"][1] for o in out)
+
+
+def test_config2_cylinder2d_full_size_properties(lib):
+    """BASELINE config 2 at its full size (2-D cylinder by IBM, 1024x512 on [-8,24]x[-8,8], 1024 markers, inflow / outlet /
+    symmetry): size-independent properties -- discrete continuity after the projection, the forcing reduces the slip at the
+    markers, the body decelerates the fluid"""
+    n = (1024, 512)
+    c = cases.channel2d(n=n, Re=100.0, dt=0.5 / 32.0)
+    c.lo, c.hi = (-8.0, -8.0), (24.0, 8.0)
+    c.bcs[0]["velocity"] = cases._const(1.0, 0.0)
+    c.bcs[1]["pressure"] = cases._constp(0.0)
+    ns = parity.make_ns(c, lib, "fractional", ns_abf_momentum_ksp_rtol=1e-10, ns_abf_schur_ksp_rtol=1e-10)
+    cell, face = c.shapes()
+    v = np.zeros((2,) + cell)
+    v[0] = 1.0
+    U = [np.zeros(s) for s in face]
+    U[0][...] = 1.0
+    parity.set_initial(ns, (v, U, np.zeros(cell)))
+    mk = cases.cylinder_markers((0.0, 0.0), 1.0, 1024, 1.0 / 32.0)
+    fb.NSB200SetMarkers(ns, mk["X"], mk["Ud"], mk["dV"], 4, iterations=3)
+    s = fb.NSB200GetSolver(ns)
+    slips = []
+    for _ in range(3):
+        fb.NSStep(ns)
+        slips.append(float(np.sqrt((s.ibm_interpolate(s.get_state()["v"]) ** 2).sum(0)).mean()))
+    st = s.get_state()
+    Ux, Uy = st["U"][0][0], st["U"][1][0]
+    h = 1.0 / 32.0
+    div = (Ux[:, 1:] - Ux[:, :-1] + Uy[1:, :] - Uy[:-1, :]) / h
+    assert np.abs(div).max() <= 1e-6 * np.abs(Ux).max() / h
+    F, _ = fb.NSB200GetMarkerForces(ns)
+    assert slips[2] < slips[1] < slips[0] < 0.8 and slips[2] < 0.55, slips  # free stream is 1
+    assert F[0].sum() < 0.0 and np.isfinite(st["p"]).all()
+    fb.NSDestroy(ns)
+
+
+def test_config4_sphere512_full_size_properties(lib):
+    """BASELINE config 4 at its full size (512^3, 100k markers) in fractional mode: one step; discrete continuity, finite
+    fields, forcing acts against the free stream"""
+    import bench
+
+    n = 512
+    c = bench.sphere_case(n, n)
+    ns = parity.make_ns(c, lib, "fractional", ns_abf_momentum_ksp_rtol=1e-8, ns_abf_schur_ksp_rtol=1e-8)
+    s = fb.NSB200GetSolver(ns)
+    v, U, p = bench.uniform_inflow_state(c)
+    s.set_state(v=v, U=U, p=p, phalf=p)
+    del v, U, p
+    mk = cases.sphere_markers((0.0, 0.0, 0.0), 1.0, 100000, 16.0 / n)
+    fb.NSB200SetMarkers(ns, mk["X"], mk["Ud"], mk["dV"], 4)
+    fb.NSStep(ns)
+    stt = fb.NSB200GetStats(ns)
+    assert stt.mom_its <= 16 and stt.schur_its <= 16
+    st = s.get_state()
+    U = st["U"]
+    h = 16.0 / n
+    k = slice(200, 312)  # a slab through the sphere is enough for the host-side check
+    div = (U[0][k, :, 1:] - U[0][k, :, :-1] + U[1][k, 1:, :] - U[1][k, :-1, :] + U[2][201:313, :, :] - U[2][200:312, :, :]) / h
+    assert np.abs(div).max() <= 1e-5 / h
+    F, Um = fb.NSB200GetMarkerForces(ns)
+    assert F[0].sum() < 0.0 and np.isfinite(st["p"]).all() and np.abs(Um[0]).max() <= 1.5
+    fb.NSDestroy(ns)
