@@ -250,12 +250,13 @@ struct PlaneAt {
   FL_HD void operator()(int i, int j, int, double *acc) const { f(i, j, kl, acc); }
 };
 
-// the two x-wall columns of planes [kbeg, kend): threads run over j so that a warp holds 32 wall cells
+// the two x-wall columns of planes [kbeg, kend): a block covers 32 rows j x 8 planes, so that a warp holds 32 wall cells
+// and all eight warps of a block work (box = {ny, planes, 1})
 template <class F>
 struct XWallAt {
   F   f;
   int i, kbeg;
-  FL_HD void operator()(int a, int, int c, double *acc) const { f(i, a, kbeg + c, acc); }
+  FL_HD void operator()(int a, int b, int, double *acc) const { f(i, a, kbeg + b, acc); }
 };
 
 // y = A x ; out[0] = <a, y>, out[1] = <y, y> are left in ex.d_result (reduce_finish reads them)
@@ -287,7 +288,7 @@ void a_apply_dots_tma(Solver &s, const V3 &x, const V3 &y, const V3 &a, bool wit
   }
   // 2. the x-wall columns of the remaining planes
   if (kend > kbeg) {
-    const Box wall_box = {g.ny, 1, kend - kbeg};
+    const Box wall_box = {g.ny, kend - kbeg, 1};
     for (int side = 0; side < 2; ++side) {
       XWallAt<AApplyDots<3>> xf = {f, side ? g.nx - 1 : 0, kbeg};
       double                *res = s.ex.d_carry + Exec::MAXR * ncar;
