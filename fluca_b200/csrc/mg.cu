@@ -103,7 +103,7 @@ struct MGSmooth {
 #ifndef FLUCA_HOSTEMU
 // the same sweep from TMA-staged tiles (3-D levels of at least one tile per plane, see tma.h)
 template <int NRED>
-struct MGSmoothTile {
+struct MGSmoothTile : TileOpDefaults {
   static const int NIN = 1, NR = NRED, MINB = 4, STAGES = 8;
   MGLevel          L;
   double           omega;
@@ -146,7 +146,7 @@ __device__ __forceinline__ double mg_diag3(const MGLevel &L, int i, int j, int k
 // The first two pre-smoothing sweeps of a V-cycle in one pass: with a zero guess the first sweep is x1 = omega b / diag,
 // so the second one, x2 = x1 + omega (b - P x1) / diag, needs only b at the cell and its six neighbours.  The tile holds b
 // (ghost planes exchanged by the caller); x1 is never stored: 16 B/cell instead of 16 + 24.
-struct MGFirstTwoTile {
+struct MGFirstTwoTile : TileOpDefaults {
   static const int NIN = 1, NR = 0, MINB = 4, STAGES = 8;
   MGLevel          L;
   double           omega, omega2; // weights of the first and the second sweep
@@ -187,6 +187,42 @@ struct MGFirstTwoTile {
       v = dg > 0. ? x1c + omega2 * (bc - Ax) / dg : x1c;
     }
     xout[off] = v;
+  }
+};
+
+// coarse b = sum over the 2 x 2 x 2 children of (b - P x), from TMA-staged tiles of x.  A thread forms the residual of its
+// fine cell; x-pairs are summed with a warp shuffle, y-pairs through CTA scratch after the plane barrier, z-pairs in a
+// register across two consecutive planes (chunks start at even planes: ZALIGN = 2).
+struct MGResidTile : TileOpDefaults {
+  static const int  NIN = 1, NR = 0, MINB = 4, STAGES = 8, ZALIGN = 2, SCRATCH = 2 * TMY * (TMX / 2) * (int)sizeof(double);
+  static const bool POST = true;
+  MGLevel           F, C;
+  struct Regs {
+    double b;
+  };
+  __device__ int  flags(int i, int j) const { return (F.uni && i > 0 && i < F.n[0] - 1 && j > 0 && j < F.n[1] - 1) ? 1 : 0; }
+  __device__ void prefetch(Regs &rg, int off, int) const { rg.b = F.b[off]; }
+  __device__ void cell(const TileView &tv, const Regs &rg, int fl, int i, int j, int kl, int, double *) const
+  {
+    const int    lc = tv.lc, kg = F.k0 + kl, tx = threadIdx.x & (TMX - 1), ty = threadIdx.x / TMX;
+    const double xc = tv.p0[lc];
+    const double xm[3] = {tv.p0[lc - 1], tv.p0[lc - TLX], tv.pm[lc]}, xp[3] = {tv.p0[lc + 1], tv.p0[lc + TLX], tv.pp[lc]};
+    const bool   inter = fl && (F.per[2] || (kg > 0 && kg < F.n[2] - 1));
+    double       Ax, dg;
+    if (__all_sync(__activemask(), inter)) Ax = F.cd[0] * (2. * xc - xm[0] - xp[0]) + F.cd[1] * (2. * xc - xm[1] - xp[1]) + F.cd[2] * (2. * xc - xm[2] - xp[2]);
+    else mg_row_core<3>(F, i, j, kl, xc, xm, xp, Ax, dg);
+    double r = rg.b - Ax;
+    r += __shfl_xor_sync(__activemask(), r, 1); // cells (2m, 2m+1) of a row are owned together (tile origins are even)
+    if (!(tx & 1)) tv.scratch[((kl & 1) * TMY + ty) * (TMX / 2) + (tx >> 1)] = r;
+  }
+  __device__ void post(const TileView &tv, int, bool owned, int i, int j, int kl, double &zsum) const
+  {
+    const int tx = threadIdx.x & (TMX - 1), ty = threadIdx.x / TMX;
+    if (!owned || (tx & 1) || (ty & 1)) return;
+    const double *row = tv.scratch + ((kl & 1) * TMY + ty) * (TMX / 2) + (tx >> 1);
+    const double  s   = row[0] + row[TMX / 2];
+    if (!(kl & 1)) zsum = s;
+    else C.b[C.idx(i >> 1, j >> 1, kl >> 1)] = zsum + s;
   }
 };
 #endif
@@ -419,10 +455,22 @@ void vcycle(Solver &s, size_t l, bool want_dot)
   MGLevel &C = s.mg[l + 1];
   level_halo(s, L, L.x);
   {
-    KScope               kt(s.ex, KT_MG_TRANSFER);
-    MGResidRestrict<DIM> rr;
-    rr.F = L, rr.C = C;
-    for_box<2>(s.ex, level_box(C), rr);
+    KScope kt(s.ex, KT_MG_TRANSFER);
+    bool   tiled = false;
+#ifndef FLUCA_HOSTEMU
+    if (DIM == 3 && getenv("FLUCA_B200_NO_MG_FUSION") == nullptr && level_tiled(s, L) && L.cf[0] == 2 && L.cf[1] == 2 && L.cf[2] == 2 && L.nzl % 2 == 0) {
+      MGResidTile op;
+      op.F = L, op.C = C;
+      const double *fields[1] = {L.x};
+      tma_launch(s.ex, op, fields, L.px, L.py, L.nzl + 2, L.n[0], L.n[1], 0, L.nzl, nullptr);
+      tiled = true;
+    }
+#endif
+    if (!tiled) {
+      MGResidRestrict<DIM> rr;
+      rr.F = L, rr.C = C;
+      for_box<2>(s.ex, level_box(C), rr);
+    }
   }
   vcycle<DIM>(s, l + 1, false);
   level_halo(s, C, C.x);

@@ -197,7 +197,7 @@ __device__ __forceinline__ void a_apply_tile_uniform(const UniCoef &u, const Ste
 }
 
 template <int NRED>
-struct AApplyTile {
+struct AApplyTile : TileOpDefaults {
   static const int NIN = 9, NR = NRED, MINB = 2, STAGES = 4;
   Geom             g;
   StepParams       sp;
@@ -320,7 +320,7 @@ void a_apply_dots_tma(Solver &s, const V3 &x, const V3 &y, const V3 &a, bool wit
 // ------------------------------------------------------------------ Poisson operator from shared-memory tiles
 // No plane needs special treatment: the wall rows of P use the cells (c, c+1) / (c-1, c) only.
 template <int NRED>
-struct PoissonTile {
+struct PoissonTile : TileOpDefaults {
   static const int NIN = 1, NR = NRED, MINB = 4, STAGES = 8;
   Geom             g;
   const double    *a; // dot partner; nullptr: p itself

@@ -99,6 +99,14 @@ __device__ __forceinline__ void tma_load_box(void *dst, const CUtensorMap *map, 
 struct TileView {
   const double *pm, *p0, *pp; // slot bases of planes k-1, k, k+1; field f starts at + f * TILE_STRIDE
   int           lc;           // element index of this thread's cell inside a field tile
+  double       *scratch;      // Op::SCRATCH bytes of shared memory for exchanges between the threads of the CTA
+};
+
+// defaults of the optional parts of the operator interface
+struct TileOpDefaults {
+  static const int  ZALIGN  = 1;     // chunk boundaries are multiples of ZALIGN planes
+  static const int  SCRATCH = 0;     // bytes of CTA scratch in shared memory
+  static const bool POST    = false; // post(...) is called after the plane barrier (sees what every thread wrote to scratch)
 };
 
 __device__ __forceinline__ void mbar_wait_addr(uint32_t bar, unsigned parity)
@@ -121,6 +129,8 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t bar, unsigned parity)
 //   __device__ int  flags(int i, int j) const;                           per-thread constants of the column (wall tests), computed once
 //   __device__ void prefetch(Regs &r, int off, int kl) const;            global loads for plane kl, issued one plane ahead
 //   __device__ void cell(const TileView &tv, const Regs &r, int flags, int i, int j, int kl, int off, double *acc) const;
+//   optional (TileOpDefaults): ZALIGN, SCRATCH, POST and
+//   __device__ void post(const TileView &tv, int flags, bool owned, int i, int j, int kl, double &state) const;
 // off = element offset of cell (i, j, kl) in the padded arrays of the launch (all fields of a launch share one layout,
 // 32-bit: geom_build refuses slabs of 2^31 elements); the framework advances it by one plane per iteration, and every
 // ring / barrier index is a running counter -- the plane loop of the 1-field operators was instruction-bound on index
@@ -134,6 +144,7 @@ __global__ void __launch_bounds__(TMX *TMY, Op::MINB) k_tma_march(const __grid_c
   constexpr unsigned TX_BYTES = Op::NIN * TILE_ELEMS * sizeof(double);
   double            *ring = reinterpret_cast<double *>(tma_smem);
   uint64_t          *full = reinterpret_cast<uint64_t *>(tma_smem + (size_t)TMS * SLOT * sizeof(double));
+  double            *scratch = reinterpret_cast<double *>(tma_smem + (size_t)TMS * SLOT * sizeof(double) + TMS * sizeof(uint64_t));
   const uint32_t     ring_s = smem_u32(ring), full_s = smem_u32(full);
   const int tid = threadIdx.x, tx = tid & (TMX - 1), ty = tid / TMX;
   const int ntile = tg.ntx * tg.nty;
@@ -141,8 +152,8 @@ __global__ void __launch_bounds__(TMX *TMY, Op::MINB) k_tma_march(const __grid_c
   const int bx = tile % tg.ntx, by = tile / tg.ntx;
   const int i0 = min(bx * TMX, (tg.nx - TMX + 1) & ~1), j0 = min(by * TMY, tg.ny - TMY); // i0 even
   int       k0, k1;
-  z_chunk(tg.kend - tg.kbeg, tg.nchunk, bz, k0, k1);
-  k0 += tg.kbeg, k1 += tg.kbeg;
+  z_chunk((tg.kend - tg.kbeg) / Op::ZALIGN, tg.nchunk, bz, k0, k1);
+  k0 = k0 * Op::ZALIGN + tg.kbeg, k1 = k1 * Op::ZALIGN + tg.kbeg;
   const int  i = i0 + tx, j = j0 + ty;
   const bool owned = (i >= bx * TMX) && (i < tg.nx) && (j >= by * TMY);
   const int  nplanes = k1 - k0 + 2; // ring index r <-> local plane k0 - 1 + r
@@ -175,7 +186,9 @@ __global__ void __launch_bounds__(TMX *TMY, Op::MINB) k_tma_march(const __grid_c
     mbar_wait_addr(full_s + 8, 0);
   }
   TileView tv;
-  tv.lc = (ty + 1) * TLX + tx + THX;
+  tv.lc      = (ty + 1) * TLX + tx + THX;
+  tv.scratch = scratch;
+  double pstate = 0.;
   tv.p0 = ring;        // shifted into pm / p0 at the top of the first iteration
   tv.pp = ring + SLOT;
   int      sc = 1;          // ring slot of plane k+1 (after the advance at the top of the loop)
@@ -194,6 +207,7 @@ __global__ void __launch_bounds__(TMX *TMY, Op::MINB) k_tma_march(const __grid_c
     if (owned) op.cell(tv, cur, fl, i, j, k, off, acc);
     off += pstride;
     __syncthreads(); // every thread is done with plane k-1: its slot may be refilled
+    if constexpr (Op::POST) op.post(tv, fl, owned, i, j, k, pstate);
     if (tid == 0 && zload < k0 + nplanes) {
       // the slot of plane k-1 is two behind sc
       const int      sr  = sc >= 2 ? sc - 2 : sc - 2 + TMS;
@@ -242,8 +256,9 @@ inline void tma_launch(Exec &ex, const Op &op, const double *const *fields, int 
   TmaGrid tg;
   tg.px = px, tg.py = py, tg.nx = nx, tg.ny = ny, tg.kbeg = kbeg, tg.kend = kend;
   tg.ntx = (nx + TMX - 1) / TMX, tg.nty = (ny + TMY - 1) / TMY;
-  tg.nchunk = tma_pick_chunks(tg.ntx * tg.nty, kend - kbeg, Op::MINB * ex.sm_count, ex.max_blocks);
-  const size_t smem = (size_t)Op::STAGES * Op::NIN * TILE_STRIDE * sizeof(double) + Op::STAGES * sizeof(uint64_t);
+  if ((kend - kbeg) % Op::ZALIGN) throw Error(FL_ERR_INTERNAL, "plane range of a tile launch is not a multiple of the operator's alignment");
+  tg.nchunk = tma_pick_chunks(tg.ntx * tg.nty, (kend - kbeg) / Op::ZALIGN, Op::MINB * ex.sm_count, ex.max_blocks);
+  const size_t smem = (size_t)Op::STAGES * Op::NIN * TILE_STRIDE * sizeof(double) + Op::STAGES * sizeof(uint64_t) + Op::SCRATCH;
   static bool  configured = false; // per template instantiation
   if (!configured) {
     FL_CUDA(cudaFuncSetAttribute(k_tma_march<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
