@@ -15,6 +15,13 @@
 
 namespace fluca {
 
+// relative tolerance of an inner solve: the user's, relaxed by the outer solver as its residual drops (step.cu outer_gmres)
+static double inner_rtol(const Solver &s, double rtol)
+{
+  const double r = rtol > s.tol_floor ? rtol : s.tol_floor;
+  return r < 0.1 ? r : 0.1;
+}
+
 static Box cell_box(const Solver &s)
 {
   Box b = {s.gh.g.nx, s.gh.g.ny, s.gh.g.nzl};
@@ -105,7 +112,7 @@ int momentum_solve(Solver &s, const V3 &b, const V3 &x, bool guess, double bscal
     return 0;
   }
   if (!(bnorm == bnorm)) throw Error(FL_ERR_DIVERGED, "momentum right-hand side is NaN");
-  const double tol = s.opt.mom_rtol * bnorm;
+  const double tol = inner_rtol(s, s.opt.mom_rtol) * bnorm;
   double       rho = red[0], alpha = 1., omega = 1.;
   s.stats.mom_last_rel = std::sqrt(red[0]) / bnorm;
   if (std::sqrt(red[0]) <= tol) return 0; // the guess already meets the tolerance
@@ -234,7 +241,7 @@ static int poisson_pcg(Solver &s, double *b, double *x)
   s.stats.schur_last_rel = 0.;
   if (bnorm == 0.) return 0;
   if (!(bnorm == bnorm)) throw Error(FL_ERR_DIVERGED, "Poisson right-hand side is NaN");
-  const double tol = s.opt.schur_rtol * bnorm;
+  const double tol = inner_rtol(s, s.opt.schur_rtol) * bnorm;
   double       rz = 0.;
   int          it = 0;
   for (; it < s.opt.inner_maxit;) {
@@ -292,7 +299,7 @@ static int poisson_bicgstab(Solver &s, double *b, double *x)
   s.stats.schur_last_rel = 0.;
   if (bnorm == 0.) return 0;
   if (!(bnorm == bnorm)) throw Error(FL_ERR_DIVERGED, "Poisson right-hand side is NaN");
-  const double tol = s.opt.schur_rtol * bnorm;
+  const double tol = inner_rtol(s, s.opt.schur_rtol) * bnorm;
   double       rho = red[0], alpha = 1., omega = 1.;
   int          it = 0;
   for (; it < s.opt.inner_maxit;) {

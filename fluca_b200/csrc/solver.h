@@ -134,6 +134,7 @@ struct Solver {
   int    step_index = 0;
   double t          = 0.;
   bool   prepared   = false;
+  double tol_floor  = 0.;     // lower bound of the inner relative tolerances, set per ABF application by the outer solver
   bool   allow_guess = true;  // FLUCA_B200_NO_GUESS unsets it (A/B timing)
   bool   have_guess = false; // s.vstar holds a guess of the first momentum solve of the step (unscaled)
 

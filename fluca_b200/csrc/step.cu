@@ -673,6 +673,7 @@ static int outer_gmres(Solver &s)
   for (auto &b : s.basis) V.push_back(make_mv(s, b));
   for (auto &b : s.zbasis) Zb.push_back(make_mv(s, b));
   std::vector<double> H((size_t)(m + 1) * m, 0.), cs(m), sn(m), gvec(m + 1), y(m), vn(m + 1, 1.);
+  const double relax_c = getenv("FLUCA_B200_RELAX") ? atof(getenv("FLUCA_B200_RELAX")) : 0.05; // 0 switches the relaxation off; measured: 0.05 keeps the outer counts, 0.2 adds outer iterations
   int    its = 0;
   double rnorm0 = -1., rnorm = 0.;
   bool   done = false, first_cycle = true, x_zero = true;
@@ -725,7 +726,13 @@ static int outer_gmres(Solver &s)
         });
         guess = true;
       }
+      // Inexact flexible GMRES: the Arnoldi relation M Z = V H holds whatever the accuracy of z_k = ABF(v_k), so the
+      // residual estimate stays the true residual; an inner error of eta_k only needs eta_k |r_k| below the target
+      // (Simoncini & Szyld 2003): inner rtol = max(user's, c * outer_rtol * |r_0| / |r_k|), at most 0.1.  The first
+      // application (|r_0| = |b|) keeps the user's tolerances.
+      s.tol_floor = (relax_c > 0. && rnorm > 0. && rnorm < rnorm0) ? relax_c * s.opt.outer_rtol * rnorm0 / rnorm : 0.;
       abf_apply(s, kv, kU, kp, zv, zU, zp, guess, 1. / vn[k]);
+      s.tol_floor = 0.;
       V3 nv, nU;
       for (int c = 0; c < 3; ++c) nv.c[c] = s.basis[k + 1][c], nU.c[c] = s.basis[k + 1][3 + c];
       coupled_apply(s, zv, zU, zp, nv, nU, s.basis[k + 1][6]);
