@@ -96,9 +96,9 @@ def uniform_inflow_state(case):
 def workload_text(args, n, nzg, restart):
     if args.workload == "sphere":
         return (f"BASELINE config 4: 3-D flow past a sphere by IBM, Re=300, {n}x{n}x{nzg} cells ({n}^3 per GPU, z-slabs), h=16/{n}, {args.markers} Fibonacci markers, 4-point delta, "
-                f"inflow/pressure-outlet/symmetry, dt=0.5h, uniform initial state, NS type b200 mode={args.mode}, reference default tolerances (outer/momentum/Schur rtol 1e-5), GMRES restart {restart}")
+                f"inflow/pressure-outlet/symmetry, dt=0.5h, uniform initial state, NS type b200 mode={args.mode}, reference default tolerances (outer/momentum/Schur rtol 1e-5; inner tolerances relaxed by the inexact-Krylov rule as the outer residual drops, DESIGN.md 5), flexible GMRES restart {restart}")
     return (f"BASELINE config 3: 3-D lid-driven cavity Re=400, {n}x{n}x{nzg} cells ({n}^3 per GPU, z-slabs), dt=0.5h, zero initial state, NS type b200 mode={args.mode}, "
-            f"reference default tolerances (outer/momentum/Schur rtol 1e-5), GMRES restart {restart}")
+            f"reference default tolerances (outer/momentum/Schur rtol 1e-5; inner tolerances relaxed by the inexact-Krylov rule, DESIGN.md 5), flexible GMRES restart {restart}")
 
 
 # ---------------------------------------------------------------------------------------------- clocks

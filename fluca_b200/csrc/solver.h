@@ -174,6 +174,7 @@ int  do_step(Solver &s, double t, int step_index);
 bool tma_usable(const Solver &s);
 void a_apply_dots_tma(Solver &s, const V3 &x, const V3 &y, const V3 &a, bool with_dots);
 void poisson_apply_dot_tma(Solver &s, const double *pin, double *out, const double *a);
+void coupled_cells_tma(Solver &s, const V3 &x, const double *p, const V3 &y, const V3 &w);
 #endif
 
 // Krylov / multigrid (krylov.cu, mg.cu)

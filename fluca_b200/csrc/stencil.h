@@ -462,6 +462,25 @@ struct ProjectCells {
   }
 };
 
+// w = (dt/rho) G0 p   (first half of the coupled velocity block when the momentum operator runs from TMA tiles)
+template <int DIM>
+struct GradCells {
+  Geom          g;
+  double        dtrho;
+  const double *p;
+  V3            w;
+  FL_HD void operator()(int i, int j, int kl) const
+  {
+    Nbr<DIM> nb;
+    nbr<DIM>(g, i, j, kl, nb);
+    if (DIM == 3 && kl + FL_PF < g.nzl) fl_prefetch(p + nb.c + FL_PF * g.plane);
+    double gp[DIM];
+    grad_cell<DIM>(g, p, nb, gp);
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) fl_store(w.c[c] + nb.c, dtrho * gp[c]);
+  }
+};
+
 // coupled operator, velocity block: y_v = A v + (dt/rho) G0 p ; also w = v + (dt/rho) G0 p
 template <int DIM>
 struct CoupledCells {

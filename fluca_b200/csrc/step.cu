@@ -415,9 +415,18 @@ static void coupled_apply_t(Solver &s, const V3 &xv, const V3 &xU, double *xp, c
   const Geom &g = s.gh.g;
   halo_cells(s, xv);
   halo_scalar(s, xp);
-  CoupledCells<DIM> cc;
-  cc.g = g, cc.sp = s.sp, cc.bc = s.bc, cc.x = CV3(xv), cc.v0 = CV3(s.v0), cc.U0 = CV3(s.U0), cc.p = xp, cc.y = yv, cc.w = s.tw;
-  for_box(s.ex, cell_box(s), cc);
+  bool tiled = false;
+#ifndef FLUCA_HOSTEMU
+  if (DIM == 3 && tma_usable(s)) {
+    coupled_cells_tma(s, xv, xp, yv, s.tw);
+    tiled = true;
+  }
+#endif
+  if (!tiled) {
+    CoupledCells<DIM> cc;
+    cc.g = g, cc.sp = s.sp, cc.bc = s.bc, cc.x = CV3(xv), cc.v0 = CV3(s.v0), cc.U0 = CV3(s.U0), cc.p = xp, cc.y = yv, cc.w = s.tw;
+    for_box(s.ex, cell_box(s), cc);
+  }
   halo_cells(s, s.tw);
   FaceCombine<DIM> fc;
   fc.g = g, fc.a = 1., fc.b = -1., fc.c = s.sp.dtrho, fc.in = CV3(xU), fc.w = CV3(s.tw), fc.p = xp, fc.out = yU;
@@ -738,13 +747,15 @@ static int outer_gmres(Solver &s)
       coupled_apply(s, zv, zU, zp, nv, nU, s.basis[k + 1][6]);
       if (!s.has_outlet) remove_mean(s, s.basis[k + 1][6]); // null space of J (nsbasic.c:229-243)
       // classical Gram-Schmidt, all projections in one pass (PETSc's GMRES default,
-      // KSPGMRESClassicalGramSchmidtOrthogonalization), re-orthogonalised only when the norm dropped by more
-      // than 1/sqrt(2) (the "refine if needed" criterion)
+      // KSPGMRESClassicalGramSchmidtOrthogonalization; its default refinement type is "never").  w = M z_k is nearly
+      // parallel to v_k (ABF is a good preconditioner), so the remainder is small; one more pass removes the cancellation
+      // error, which only matters when the requested tolerance comes near it: remainder / |w| against 1e-12 / outer_rtol
       std::vector<double> hcolv(m + 1, 0.);
       double             *hcol = hcolv.data(), ww = 0., nrm2 = 0.;
       mv_project(s, Vl, vn.data(), k + 1, V[k + 1], hcol, ww, nrm2);
       for (int jx = 0; jx <= k; ++jx) H[(size_t)jx * m + k] = hcol[jx];
-      if (nrm2 < 0.5 * ww) {
+      const double cancel = 1e-12 / s.opt.outer_rtol; // round-off left in the remainder, relative to the target
+      if (nrm2 < 0.5 * ww && nrm2 < cancel * cancel * 1e4 * ww) {
         double ww2;
         mv_project(s, Vl, vn.data(), k + 1, V[k + 1], hcol, ww2, nrm2);
         for (int jx = 0; jx <= k; ++jx) H[(size_t)jx * m + k] += hcol[jx];

@@ -206,6 +206,7 @@ struct AApplyTile : TileOpDefaults {
   int              uniform; // all three directions uniform: interior warps use a_apply_tile_uniform
   const double    *a[3]; // dot partner (NR == 2); nullptr: the partner is x itself
   double          *y[3];
+  double          *wout[3]; // coupled velocity block: on entry g = (dt/rho) G p; y = A x + g, wout = x + g (nullptr otherwise)
   struct Regs {
     double a[3];
   };
@@ -218,6 +219,9 @@ struct AApplyTile : TileOpDefaults {
 #pragma unroll
       for (int q = 0; q < 3; ++q)
         if (a[q]) rg.a[q] = a[q][off];
+    } else if (wout[0]) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) rg.a[q] = wout[q][off];
     }
   }
   __device__ void cell(const TileView &tv, const Regs &rg, int fl, int i, int j, int kl, int c, double *acc) const
@@ -229,6 +233,14 @@ struct AApplyTile : TileOpDefaults {
       else a_apply_tile<false>(g, sp, bc, tv, i, j, kl, r);
     } else a_apply_tile<true>(g, sp, bc, tv, i, j, kl, r);
     double    d0 = 0., d1 = 0.;
+    if (NRED == 0 && wout[0]) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        y[q][c]    = r[q] + rg.a[q];
+        wout[q][c] = tv.p0[q * TILE_STRIDE + tv.lc] + rg.a[q];
+      }
+      return;
+    }
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
       y[q][c] = r[q];
@@ -306,15 +318,73 @@ void a_apply_dots_tma(Solver &s, const V3 &x, const V3 &y, const V3 &a, bool wit
   if (with_dots) {
     AApplyTile<2> op;
     op.g = g, op.sp = s.sp, op.bc = s.bc, op.uc = uc, op.uniform = uniform;
-    for (int c = 0; c < 3; ++c) op.a[c] = (a.c[c] == x.c[c]) ? nullptr : a.c[c], op.y[c] = y.c[c];
+    for (int c = 0; c < 3; ++c) op.a[c] = (a.c[c] == x.c[c]) ? nullptr : a.c[c], op.y[c] = y.c[c], op.wout[c] = nullptr;
     tma_launch(s.ex, op, fields, g.px, g.py, g.nzl + 2, g.nx, g.ny, kbeg, kend, carry);
   } else {
     AApplyTile<0> op;
     op.g = g, op.sp = s.sp, op.bc = s.bc, op.uc = uc, op.uniform = uniform;
-    for (int c = 0; c < 3; ++c) op.a[c] = nullptr, op.y[c] = y.c[c];
+    for (int c = 0; c < 3; ++c) op.a[c] = nullptr, op.y[c] = y.c[c], op.wout[c] = nullptr;
     tma_launch(s.ex, op, fields, g.px, g.py, g.nzl + 2, g.nx, g.ny, kbeg, kend, nullptr);
   }
   (void)ncar;
+}
+
+// plain (no reduction) versions of the wall adapters
+template <class F>
+struct PlaneAtPlain {
+  F   f;
+  int kl;
+  FL_HD void operator()(int i, int j, int) const { f(i, j, kl); }
+};
+template <class F>
+struct XWallAtPlain {
+  F   f;
+  int i, kbeg;
+  FL_HD void operator()(int a, int b, int) const { f(i, a, kbeg + b); }
+};
+
+// velocity block of the coupled operator: y = A x + (dt/rho) G p, w = x + (dt/rho) G p
+void coupled_cells_tma(Solver &s, const V3 &x, const double *p, const V3 &y, const V3 &w)
+{
+  const Geom &g = s.gh.g;
+  // 1. w = (dt/rho) G p everywhere (the tile kernel reads it as a per-cell operand and overwrites it)
+  GradCells<3> gc;
+  gc.g = g, gc.dtrho = s.sp.dtrho, gc.p = p, gc.w = w;
+  const Box all = {g.nx, g.ny, g.nzl};
+  for_box<2>(s.ex, all, gc);
+  // 2. wall planes and wall columns with the direct-load functor (it forms the gradient itself)
+  const bool wl = g.t[2].wall_lo && !g.t[2].per, wh = g.t[2].wall_hi && !g.t[2].per;
+  CoupledCells<3> f;
+  f.g = g, f.sp = s.sp, f.bc = s.bc, f.x = CV3(x), f.v0 = CV3(s.v0), f.U0 = CV3(s.U0), f.p = p, f.y = y, f.w = w;
+  const Box plane_box = {g.nx, g.ny, 1};
+  const int kbeg = wl ? 1 : 0;
+  int       kend = wh ? g.nzl - 1 : g.nzl;
+  if (kend < kbeg) kend = kbeg;
+  if (wl) {
+    PlaneAtPlain<CoupledCells<3>> pf = {f, 0};
+    for_box(s.ex, plane_box, pf);
+  }
+  if (wh && g.nzl - 1 >= kbeg) {
+    PlaneAtPlain<CoupledCells<3>> pf = {f, g.nzl - 1};
+    for_box(s.ex, plane_box, pf);
+  }
+  if (kend > kbeg) {
+    const Box wall_box = {g.ny, kend - kbeg, 1};
+    for (int side = 0; side < 2; ++side) {
+      XWallAtPlain<CoupledCells<3>> xf = {f, side ? g.nx - 1 : 0, kbeg};
+      for_box(s.ex, wall_box, xf);
+    }
+  }
+  // 3. everything else from TMA tiles
+  const double *fields[9] = {x.c[0], x.c[1], x.c[2], s.v0.c[0], s.v0.c[1], s.v0.c[2], s.U0.c[0], s.U0.c[1], s.U0.c[2]};
+  UniCoef       uc;
+  static const bool no_uni = getenv("FLUCA_B200_NO_UNIFORM") != nullptr;
+  uc.l4 = 0.;
+  for (int d = 0; d < 3; ++d) uc.q[d] = 0.25 / g.t[d].uh, uc.l[d] = 1. / (g.t[d].uh * g.t[d].uh), uc.l4 += 4. * uc.l[d];
+  AApplyTile<0> op;
+  op.g = g, op.sp = s.sp, op.bc = s.bc, op.uc = uc, op.uniform = (!no_uni && g.t[0].uni && g.t[1].uni && g.t[2].uni) ? 1 : 0;
+  for (int c = 0; c < 3; ++c) op.a[c] = nullptr, op.y[c] = y.c[c], op.wout[c] = w.c[c];
+  tma_launch(s.ex, op, fields, g.px, g.py, g.nzl + 2, g.nx, g.ny, kbeg, kend, nullptr);
 }
 
 // ------------------------------------------------------------------ Poisson operator from shared-memory tiles
