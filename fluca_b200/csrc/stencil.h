@@ -216,6 +216,12 @@ struct MomentumRhs {
   {
     Nbr<DIM> nb;
     nbr<DIM>(g, i, j, kl, nb);
+    if (DIM == 3 && kl + FL_PF < g.nzl) {
+      const long ahead = nb.c + FL_PF * g.plane;
+#pragma unroll
+      for (int c = 0; c < DIM; ++c) fl_prefetch(v0.c[c] + ahead);
+      fl_prefetch(q + ahead);
+    }
     double vc[DIM], lap[DIM], bcc[DIM], gq[DIM], bcg[DIM];
 #pragma unroll
     for (int c = 0; c < DIM; ++c) {

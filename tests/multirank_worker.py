@@ -82,7 +82,12 @@ def main():
         "periodic_z": lambda: cases.channel3d(n=(8, 6, 8), periodic_z=True, dt=0.05),
         "uneven": lambda: cases.cavity3d_full(n=(8, 6, 7)),
         "three": lambda: cases.cavity3d_full(n=(8, 6, 9)),
+        "sphere_ibm": lambda: cases.channel3d(n=(12, 8, 8), pout=0.1, dt=0.05),
+        "sphere_ibm_tma": lambda: cases.channel3d(n=(40, 16, 16), pout=0.1, dt=0.02),
     }[case_name]()
+    markers = None
+    if case_name.startswith("sphere_ibm"):  # the body straddles the slab interface: gather and scatter both cross it
+        markers = cases.sphere_markers((0.1, 0.0, 0.05), 1.2, 120, 4.0 / case.n[1])
     if backend == "nccl":
         comm = dict(rank=rank, nranks=world, make_comm=lambda L: fb.Comm.nccl(L, uid, rank, world))
     else:
@@ -94,6 +99,8 @@ def main():
     sl = slice(k0, k0 + nzl)
     Uz = U[2][k0 : k0 + nzl + (1 if s.last_z else 0)]
     s.set_state(v=v[:, sl], U=[U[0][sl], U[1][sl], Uz], p=p[sl])
+    if markers is not None:
+        fb.NSB200SetMarkers(ns, markers["X"], markers["Ud"], markers["dV"], 4, iterations=2)
     its = []
     for _ in range(2):
         fb.NSStep(ns)
@@ -109,7 +116,11 @@ def main():
         gp = np.concatenate([d["p"] for d in parts], axis=0)
         gph = np.concatenate([d["phalf"] for d in parts], axis=0)
         gU = [np.concatenate([d["U"][a] for d in parts], axis=0) for a in range(3)]
-        np.savez(out_path, v=gv, p=gp, phalf=gph, U0=gU[0], U1=gU[1], U2=gU[2], its=np.array(its))
+        extra = {}
+        if markers is not None:
+            F, Um = fb.NSB200GetMarkerForces(ns)
+            extra = dict(F=F, Um=Um)
+        np.savez(out_path, v=gv, p=gp, phalf=gph, U0=gU[0], U1=gU[1], U2=gU[2], its=np.array(its), **extra)
     fb.NSDestroy(ns)
     dist.barrier()
     dist.destroy_process_group()

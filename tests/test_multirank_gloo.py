@@ -48,30 +48,43 @@ CASEMAP = {
     "periodic_z": lambda: cases.channel3d(n=(8, 6, 8), periodic_z=True, dt=0.05),
     "uneven": lambda: cases.cavity3d_full(n=(8, 6, 7)),
     "three": lambda: cases.cavity3d_full(n=(8, 6, 9)),
+    "sphere_ibm": lambda: cases.channel3d(n=(12, 8, 8), pout=0.1, dt=0.05),
+    "sphere_ibm_tma": lambda: cases.channel3d(n=(40, 16, 16), pout=0.1, dt=0.02),
 }
+
+
+def _oracle_reference(case_name, mode):
+    case = CASEMAP[case_name]()
+    orc = cases.make_oracle(case)
+    orc.set_state(*case.initial_state(seed=31))
+    if case_name.startswith("sphere_ibm"):
+        mk = cases.sphere_markers((0.1, 0.0, 0.05), 1.2, 120, 4.0 / case.n[1])
+        orc.set_markers(mk["X"], mk["Ud"], mk["dV"], 4, 2)
+    infos = [orc.step(O.default_options(mode=0 if mode == "coupled" else 1, **parity.ORC_TIGHT)) for _ in range(2)]
+    return orc, infos
 
 
 @pytest.mark.parametrize(
     "case_name,mode,world",
-    [("cavity3d", "coupled", 2), ("channel3d", "coupled", 2), ("periodic_z", "fractional", 2), ("uneven", "fractional", 2), ("three", "fractional", 3)],
+    [("cavity3d", "coupled", 2), ("channel3d", "coupled", 2), ("periodic_z", "fractional", 2), ("uneven", "fractional", 2), ("three", "fractional", 3), ("sphere_ibm", "coupled", 2)],
 )
 def test_slab_partition_matches_oracle(case_name, mode, world, tmp_path):
     parity.hostemu_library()
     got = run_world(case_name, mode, world, tmp_path)
-    case = CASEMAP[case_name]()
-    orc = cases.make_oracle(case)
-    orc.set_state(*case.initial_state(seed=31))
-    infos = [orc.step(O.default_options(mode=0 if mode == "coupled" else 1, **parity.ORC_TIGHT)) for _ in range(2)]
+    orc, infos = _oracle_reference(case_name, mode)
     ref = orc.get_state()
     assert parity.rel(got["v"], ref["v"]) < 1e-10
     assert parity.relU([got["U0"], got["U1"], got["U2"]], ref["U"]) < 1e-10
     assert parity.rel(got["p"], ref["p"]) < 1e-9 and parity.rel(got["phalf"], ref["phalf"]) < 1e-9
+    if "F" in got.files:  # immersed boundary across the slab interface: marker velocities are summed over the ranks
+        Fo, Uo = orc.marker_forces()
+        assert parity.rel(got["Um"], Uo) < 1e-10 and parity.rel(got["F"], Fo) < 1e-8
     if mode == "coupled":
         assert [int(a) for a in got["its"][:, 0]] == [i.outer_its for i in infos]
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case_name,mode", [("cavity3d", "coupled"), ("channel3d", "coupled"), ("periodic_z", "fractional")])
+@pytest.mark.parametrize("case_name,mode", [("cavity3d", "coupled"), ("channel3d", "coupled"), ("periodic_z", "fractional"), ("sphere_ibm", "coupled"), ("sphere_ibm_tma", "fractional")])
 def test_nccl_two_gpus_match_oracle(case_name, mode, tmp_path):
     """The same comparison with the CUDA library on 2 GPUs: NCCL halo exchange + allreduce."""
     import torch
@@ -79,11 +92,11 @@ def test_nccl_two_gpus_match_oracle(case_name, mode, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     got = run_world(case_name, mode, 2, tmp_path, backend="nccl")
-    case = CASEMAP[case_name]()
-    orc = cases.make_oracle(case)
-    orc.set_state(*case.initial_state(seed=31))
-    infos = [orc.step(O.default_options(mode=0 if mode == "coupled" else 1, **parity.ORC_TIGHT)) for _ in range(2)]
+    orc, infos = _oracle_reference(case_name, mode)
     ref = orc.get_state()
+    if "F" in got.files:
+        Fo, Uo = orc.marker_forces()
+        assert parity.rel(got["Um"], Uo) < 1e-10 and parity.rel(got["F"], Fo) < 1e-8
     assert parity.rel(got["v"], ref["v"]) < 1e-10
     assert parity.relU([got["U0"], got["U1"], got["U2"]], ref["U"]) < 1e-10
     assert parity.rel(got["p"], ref["p"]) < 1e-9
