@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--workload", default="sphere", choices=["sphere", "cavity"], help="sphere: BASELINE config 4 (3-D IBM sphere Re=300, 512^3, 100k markers), the configuration the metric is quoted on; cavity: config 3 (256^3 lid-driven cavity, no IBM)")
     ap.add_argument("--n", type=int, default=0, help="cells per direction per GPU (default: 512 sphere, 256 cavity)")
     ap.add_argument("--markers", type=int, default=100000)
+    ap.add_argument("--strong", action="store_true", help="strong scaling: the n^3 grid is split over the GPUs (default: weak, n^3 per GPU)")
     ap.add_argument("--mode", default="coupled", choices=["coupled", "fractional"])
     ap.add_argument("--restart", type=int, default=0, help="outer GMRES restart (memory: (restart+1) x 7 fields; default 3 at 512^3, 10 below; the flexible form also keeps restart x 7 fields of preconditioned vectors)")
     ap.add_argument("--cpu-n", type=int, default=64, help="cells per direction of the bounded CPU sample")
@@ -95,7 +96,7 @@ def uniform_inflow_state(case):
 
 def workload_text(args, n, nzg, restart):
     if args.workload == "sphere":
-        return (f"BASELINE config 4: 3-D flow past a sphere by IBM, Re=300, {n}x{n}x{nzg} cells ({n}^3 per GPU, z-slabs), h=16/{n}, {args.markers} Fibonacci markers, 4-point delta, "
+        return (f"BASELINE config 4: 3-D flow past a sphere by IBM, Re=300, {n}x{n}x{nzg} cells ({'z-slabs of the one grid' if getattr(args, 'strong', False) else f'{n}^3 per GPU, z-slabs'}), h=16/{n}, {args.markers} Fibonacci markers, 4-point delta, "
                 f"inflow/pressure-outlet/symmetry, dt=0.5h, uniform initial state, NS type b200 mode={args.mode}, reference default tolerances (outer/momentum/Schur rtol 1e-5; inner tolerances relaxed by the inexact-Krylov rule as the outer residual drops, DESIGN.md 5), flexible GMRES restart {restart}")
     return (f"BASELINE config 3: 3-D lid-driven cavity Re=400, {n}x{n}x{nzg} cells ({n}^3 per GPU, z-slabs), dt=0.5h, zero initial state, NS type b200 mode={args.mode}, "
             f"reference default tolerances (outer/momentum/Schur rtol 1e-5; inner tolerances relaxed by the inexact-Krylov rule, DESIGN.md 5), flexible GMRES restart {restart}")
@@ -227,7 +228,7 @@ def run_b200(args):
         comm = dict(rank=rank, nranks=world, make_comm=lambda L: fb.Comm.nccl(L, uid_bytes, rank, world))
 
     n = args.n or (512 if args.workload == "sphere" else 256)
-    nzg = n * world  # weak scaling: an n^3 slab per GPU
+    nzg = n if args.strong else n * world  # weak scaling (default): an n^3 slab per GPU; strong: n / N planes per GPU
     restart = args.restart or (3 if n >= 512 else 10)
     case = make_case(args, n, nzg)
     opts = {"ns_ksp_gmres_restart": restart}
@@ -288,7 +289,7 @@ def run_b200(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    cells_rank = float(n) ** 3
+    cells_rank = float(n) * n * (nzg / world)
     d3 = True
     # algorithmic bytes per launch and cell (DESIGN.md "Kernels"): A apply + 2 dots reads x(3) v0(3) U0(3) a(3) writes y(3)
     # momentum apply fused with two dots: reads x(3) v0(3) U0(3) (+ rhat(3) in the first of the two applies of a
@@ -322,7 +323,7 @@ def run_b200(args):
         "warmup": args.warmup,
         "ms_per_step": ms / args.steps,
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": "strong" if args.strong else "weak",
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
