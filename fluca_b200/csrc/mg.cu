@@ -363,7 +363,8 @@ void level_halo(Solver &s, MGLevel &L, double *x)
 {
   if (s.dim != 3) return;
   double *f[1] = {x};
-  s.comm->halo(s.ex, f, 1, L.plane, L.nzl, L.per[2] != 0);
+  Comm   *c    = L.replicated ? s.local_comm.get() : s.comm.get();
+  c->halo(s.ex, f, 1, L.plane, L.nzl, L.per[2] != 0);
 }
 
 bool level_tiled(const Solver &s, const MGLevel &L)
@@ -426,10 +427,24 @@ void smooth(Solver &s, MGLevel &L, bool zero_guess, bool with_dot, double omega)
 }
 
 template <int DIM>
-void vcycle(Solver &s, size_t l, bool want_dot)
+void vcycle(Solver &s, std::vector<MGLevel> &levels, size_t l, bool want_dot)
 {
-  MGLevel &L = s.mg[l];
-  const bool coarsest = (l + 1 == s.mg.size());
+  MGLevel &L = levels[l];
+  const bool coarsest = (l + 1 == levels.size());
+  if (coarsest && &levels == &s.mg && !s.mg_agg.empty()) {
+    // Coarse-grid agglomeration: below this level a slab is a few planes thick and every smoothing sweep would cost a
+    // latency-bound halo exchange (two thirds of the ~50 exchanges of a V-cycle sit on levels of <= 64^3 cells).  One
+    // allgather puts the level's right-hand side on every rank, the rest of the cycle runs on the whole coarse grid
+    // without communication (redundantly: it is tiny), and each rank copies its planes and their ghosts back.
+    KScope   kt(s.ex, KT_MG_TRANSFER);
+    MGLevel &A0 = s.mg_agg[0];
+    s.comm->allgather(s.ex, L.b + L.plane, A0.b + A0.plane, L.plane * L.nzl);
+    vcycle<DIM>(s, s.mg_agg, 0, false);
+    if (A0.per[2]) level_halo(s, A0, A0.x);
+    copy_d2d(s.ex, L.x, A0.x + A0.plane * L.k0, sizeof(double) * (size_t)L.plane * (L.nzl + 2));
+    s.ex.stats.launches++;
+    return;
+  }
   if (coarsest) {
     const int    ns = s.opt.mg_coarse_sweeps;
     const double om = sweep_weight(DIM, true, ns, 0, false);
@@ -452,7 +467,7 @@ void vcycle(Solver &s, size_t l, bool want_dot)
 #endif
   if (!done) smooth<DIM>(s, L, true, false, sweep_weight(DIM, false, s.opt.mg_nu1, 0, false)), done = 1;
   for (int k = done; k < s.opt.mg_nu1; ++k) smooth<DIM>(s, L, false, false, sweep_weight(DIM, false, s.opt.mg_nu1, k, false));
-  MGLevel &C = s.mg[l + 1];
+  MGLevel &C = levels[l + 1];
   level_halo(s, L, L.x);
   {
     KScope kt(s.ex, KT_MG_TRANSFER);
@@ -472,8 +487,9 @@ void vcycle(Solver &s, size_t l, bool want_dot)
       for_box<2>(s.ex, level_box(C), rr);
     }
   }
-  vcycle<DIM>(s, l + 1, false);
-  level_halo(s, C, C.x);
+  vcycle<DIM>(s, levels, l + 1, false);
+  const bool gathered = (&levels == &s.mg && !s.mg_agg.empty() && l + 2 == levels.size()); // ghosts came with the copy
+  if (!gathered) level_halo(s, C, C.x);
   {
     KScope         kt(s.ex, KT_MG_TRANSFER);
     MGProlong<DIM> pr;
@@ -485,29 +501,19 @@ void vcycle(Solver &s, size_t l, bool want_dot)
 
 } // namespace
 
-void mg_setup(Solver &s)
+// builds a hierarchy from level L (sizes, slab and layout filled in) down; nranks = 1 for the replicated hierarchy.
+// agg_cells > 0: stop at the first level below the finest with at most that many global cells (it will be gathered).
+static void build_levels(Solver &s, std::vector<MGLevel> &levels, MGLevel L, std::vector<double> xf[3], const int bc[6], int nranks, bool equal_slabs, long agg_cells, bool borrow_b0)
 {
-  const Geom &g = s.gh.g;
-  int         bc[6];
-  for (int d = 0; d < 3; ++d) bc[2 * d] = g.t[d].bc_lo, bc[2 * d + 1] = g.t[d].bc_hi;
-  std::vector<double> xf[3];
-  for (int d = 0; d < s.dim; ++d) xf[d] = s.gh.xf[d];
-  const bool equal_slabs = (g.nzl * g.nranks == g.nzg);
-
-  MGLevel L;
-  memset(&L, 0, sizeof(L));
-  L.n[0] = g.nx, L.n[1] = g.ny, L.n[2] = g.nzg;
-  L.nzl = g.nzl, L.k0 = g.k0, L.px = g.px, L.py = g.py, L.plane = g.plane, L.nalloc = g.nalloc;
-  for (int d = 0; d < 3; ++d) L.per[d] = d < s.dim ? g.t[d].per : 0;
-  L.wall_lo_z = g.t[2].wall_lo, L.wall_hi_z = g.t[2].wall_hi;
   for (int lev = 0; lev < 24; ++lev) {
     level_tables(s, L, xf, bc);
-    // level 0 borrows b from the Krylov solver (mg_vcycle); x and the Jacobi scratch t are owned
-    L.own_x = true, L.own_b = (lev > 0);
+    // level 0 of the distributed hierarchy borrows b from the Krylov solver (mg_vcycle); x and the Jacobi scratch t are owned
+    const bool own_b = !(borrow_b0 && lev == 0);
+    L.own_x = true, L.own_b = own_b;
     L.b = nullptr;
     L.x = (double *)dev_alloc(sizeof(double) * (size_t)L.nalloc);
     s.mg_owned.push_back(L.x);
-    if (lev > 0) {
+    if (own_b) {
       L.b = (double *)dev_alloc(sizeof(double) * (size_t)L.nalloc);
       s.mg_owned.push_back(L.b);
     }
@@ -518,16 +524,25 @@ void mg_setup(Solver &s)
     bool any   = false;
     for (int d = 0; d < s.dim; ++d) {
       bool ok = (L.n[d] % 2 == 0) && (L.n[d] >= 4);
-      if (d == 2) ok = (L.n[2] % 2 == 0) && equal_slabs && (L.nzl % 2 == 0) && (g.nranks > 1 ? L.nzl >= 2 : L.n[2] >= 4);
+      if (d == 2) ok = (L.n[2] % 2 == 0) && equal_slabs && (L.nzl % 2 == 0) && (nranks > 1 ? L.nzl >= 2 : L.n[2] >= 4);
       if (ok) cf[d] = 2, any = true;
     }
-    if (!any) {
+    const bool gather_here = agg_cells > 0 && lev > 0 && (long)L.n[0] * L.n[1] * L.n[2] <= agg_cells;
+    if (!any || gather_here) {
       L.cf[0] = L.cf[1] = L.cf[2] = 0;
-      s.mg.push_back(L);
+      levels.push_back(L);
+      if (gather_here) {
+        // the replicated hierarchy starts from this level's global grid
+        MGLevel A = L;
+        A.nzl = L.n[2], A.k0 = 0, A.nalloc = A.plane * (A.nzl + 2);
+        A.wall_lo_z = A.wall_hi_z = L.per[2] ? 0 : 1;
+        A.replicated = 1;
+        build_levels(s, s.mg_agg, A, xf, bc, 1, true, 0, false);
+      }
       break;
     }
     for (int d = 0; d < 3; ++d) L.cf[d] = cf[d];
-    s.mg.push_back(L);
+    levels.push_back(L);
     // next level
     MGLevel Cn;
     memset(&Cn, 0, sizeof(Cn));
@@ -546,8 +561,31 @@ void mg_setup(Solver &s)
     Cn.plane  = (long)Cn.px * Cn.py;
     Cn.nalloc = Cn.plane * (Cn.nzl + 2);
     Cn.wall_lo_z = L.wall_lo_z, Cn.wall_hi_z = L.wall_hi_z;
+    Cn.replicated = L.replicated;
     L = Cn;
   }
+}
+
+void mg_setup(Solver &s)
+{
+  const Geom &g = s.gh.g;
+  int         bc[6];
+  for (int d = 0; d < 3; ++d) bc[2 * d] = g.t[d].bc_lo, bc[2 * d + 1] = g.t[d].bc_hi;
+  std::vector<double> xf[3];
+  for (int d = 0; d < s.dim; ++d) xf[d] = s.gh.xf[d];
+  const bool equal_slabs = (g.nzl * g.nranks == g.nzg);
+  if (!s.local_comm) s.local_comm.reset(new LocalComm());
+
+  MGLevel L;
+  memset(&L, 0, sizeof(L));
+  L.n[0] = g.nx, L.n[1] = g.ny, L.n[2] = g.nzg;
+  L.nzl = g.nzl, L.k0 = g.k0, L.px = g.px, L.py = g.py, L.plane = g.plane, L.nalloc = g.nalloc;
+  for (int d = 0; d < 3; ++d) L.per[d] = d < s.dim ? g.t[d].per : 0;
+  L.wall_lo_z = g.t[2].wall_lo, L.wall_hi_z = g.t[2].wall_hi;
+  // coarse levels of at most 64^3 cells are gathered on every rank (multi-rank 3-D runs with equal slabs)
+  long agg = 0;
+  if (g.nranks > 1 && s.dim == 3 && equal_slabs) agg = getenv("FLUCA_B200_MG_AGG") ? atol(getenv("FLUCA_B200_MG_AGG")) : 64L * 64 * 64;
+  build_levels(s, s.mg, L, xf, bc, g.nranks, equal_slabs, agg, true);
 }
 
 void mg_destroy(Solver &s)
@@ -555,6 +593,7 @@ void mg_destroy(Solver &s)
   for (void *p : s.mg_owned) dev_free(p);
   s.mg_owned.clear();
   s.mg.clear();
+  s.mg_agg.clear();
 }
 
 // returns z = V-cycle(r) with zero initial guess; want_dot: the last sweep leaves <r, z> in ex.d_result.  r is a fine-level field (Geom layout); the result
@@ -563,8 +602,8 @@ double *mg_vcycle(Solver &s, double *r, bool want_dot)
 {
   MGLevel &L0 = s.mg[0];
   L0.b        = r;
-  if (s.dim == 2) vcycle<2>(s, 0, want_dot);
-  else vcycle<3>(s, 0, want_dot);
+  if (s.dim == 2) vcycle<2>(s, s.mg, 0, want_dot);
+  else vcycle<3>(s, s.mg, 0, want_dot);
   L0.b = nullptr;
   return L0.x;
 }

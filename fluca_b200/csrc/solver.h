@@ -62,6 +62,7 @@ struct MGLevel {
   const double *h[3]; // [n[d]]     cell widths
   const double *kf[3]; // [n[d]+1]  face conductance 1/dist, 0 at Neumann walls, 1/(xc-xw) at outlet walls
   int  wall_lo_z, wall_hi_z;
+  int  replicated;    // every rank holds the whole level (agglomerated coarse levels): ghost planes need no exchange
   int  uni;           // every direction has constant cell width: interior rows are cd[d] (2 x - x- - x+), diagonal 1 / idg
   double cd[3], idg;
   double *x, *b, *t;  // solution, right-hand side, scratch (Jacobi double buffer)
@@ -120,7 +121,9 @@ struct Solver {
   V3      kr, krh, kp, kv, ks, kt;
   // Poisson Krylov
   double *pr = nullptr, *pp = nullptr, *pq = nullptr, *ps = nullptr, *pt = nullptr, *prh = nullptr;
-  std::vector<MGLevel> mg;
+  std::vector<MGLevel> mg;     // distributed levels (z-slabs); the last one is gathered when mg_agg is in use
+  std::vector<MGLevel> mg_agg; // agglomerated coarse levels: the global grid on every rank, solved redundantly
+  std::unique_ptr<Comm> local_comm; // single-rank halo (periodic wrap) of the replicated levels
   std::vector<void *>  mg_owned;
   // outer GMRES basis: (restart + 1) vectors of 7 fields, plus work vectors
   std::vector<std::vector<double *>> basis, zbasis; // zbasis[k] = ABF(basis[k]) (flexible GMRES: no final application)

@@ -48,6 +48,7 @@ CASEMAP = {
     "periodic_z": lambda: cases.channel3d(n=(8, 6, 8), periodic_z=True, dt=0.05),
     "uneven": lambda: cases.cavity3d_full(n=(8, 6, 7)),
     "three": lambda: cases.cavity3d_full(n=(8, 6, 9)),
+    "cavity32": lambda: cases.cavity3d_full(n=(32, 32, 32)),
     "sphere_ibm": lambda: cases.channel3d(n=(12, 8, 8), pout=0.1, dt=0.05),
     "sphere_ibm_tma": lambda: cases.channel3d(n=(40, 16, 16), pout=0.1, dt=0.02),
 }
