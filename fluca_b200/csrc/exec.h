@@ -43,16 +43,11 @@
 
 namespace fluca {
 
-// Store of a kernel result.  In the CUDA build it is an asm store WITHOUT a memory clobber: the functors take their
-// arrays through struct members, which carry no __restrict__ information, so with a plain store the compiler must
-// keep every load of the next plane behind it; with this form it may hoist them (software pipelining of the plane
-// loop in k_box: two planes of loads in flight per thread).  No functor reads, in a later iteration, an element that
-// an earlier iteration of the same thread stored, so the reordering is safe.
-#if !defined(FLUCA_HOSTEMU) && defined(__CUDA_ARCH__)
-__device__ __forceinline__ void fl_store(double *p, double v) { asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v)); }
-#else
-inline void fl_store(double *p, double v) { *p = v; }
-#endif
+// Store of a kernel result (one place to change the store flavour of every stencil functor).  An asm store without a
+// memory clobber was tried here so that the compiler could hoist the next plane's loads above it (the functors take their
+// arrays through struct members, which carry no __restrict__ information); it changed neither the schedule nor the timing
+// (DESIGN.md section 9), so this is a plain store.
+FL_HD void fl_store(double *p, double v) { *p = v; }
 
 // L2 prefetch of the element a direct-load stencil functor will need PF planes later.  The plane loop of k_box keeps
 // only one plane of loads in flight per thread (profiles/r01l: FaceCombine issue slots 11 % busy, 48 warps stalled on

@@ -272,7 +272,6 @@ static int poisson_pcg(Solver &s, double *b, double *x)
     reduce_finish(s, 1, red);
     ++it;
     s.stats.schur_last_rel = std::sqrt(red[0]) / bnorm;
-    if (getenv("FLUCA_B200_DEBUG")) fprintf(stderr, "  pcg it %d rz %.15e pq %.15e alpha %.15e rel %.6e\n", it, rz, pq, alpha, s.stats.schur_last_rel);
     if (std::sqrt(red[0]) <= tol) break;
   }
   s.stats.schur_its += it;

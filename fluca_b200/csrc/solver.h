@@ -175,6 +175,7 @@ int  do_step(Solver &s, double t, int step_index);
 #ifndef FLUCA_HOSTEMU
 // TMA-staged versions of the hot 3-D operators (tiles.cu); tma_usable() says whether the mesh qualifies
 bool tma_usable(const Solver &s);
+void tensor_map_forget(const double *field); // drops the cached tensor maps of a field that is about to be freed
 void a_apply_dots_tma(Solver &s, const V3 &x, const V3 &y, const V3 &a, bool with_dots);
 void poisson_apply_dot_tma(Solver &s, const double *pin, double *out, const double *a);
 void coupled_cells_tma(Solver &s, const V3 &x, const double *p, const V3 &y, const V3 &w);

@@ -195,6 +195,10 @@ void solver_destroy(Solver &s)
 {
   s.ex.sync();
   ibm_destroy(s);
+#ifndef FLUCA_HOSTEMU
+  for (double *p : s.pool) tensor_map_forget(p); // the cache is keyed by address: a later solver may get the same one
+  for (void *p : s.mg_owned) tensor_map_forget((const double *)p);
+#endif
   mg_destroy(s);
   for (double *p : s.pool) dev_free(p);
   s.pool.clear();
