@@ -35,6 +35,7 @@ typedef struct {
   /* geometry of this rank's slab */
   PetscInt dim, M, N, P, k0, nzl;
   PetscBool lastz, per[3];
+  PetscBool wallz[2];             /* this rank holds the BACK / FRONT boundary plane */
   /* host staging in the C-ABI layout (pinned by PETSc's allocator is not required) */
   double *hv, *hU[3], *hp, *hph, *hbc;
   size_t  ncell, nface[3];
@@ -204,6 +205,7 @@ static PetscErrorCode B200UploadBoundaryData_Private(NS ns)
     const PetscInt gl[3] = {b->M, b->N, b->P};
     const size_t   np = (size_t)n0 * n1;
     if (bc->type != NS_BC_VELOCITY && bc->type != NS_BC_PRESSURE_OUTLET) continue;
+    if (d == 2 && !b->wallz[side]) continue; /* only the first / last slab holds (and has coordinates for) a z boundary */
     for (slot = 0; slot < 2; ++slot) {
       const PetscReal t = bc->type == NS_BC_VELOCITY ? (slot ? ns->t + ns->dt : ns->t) : (slot ? ns->t + 0.5 * ns->dt : tq);
       for (j = 0; j < n1; ++j)
@@ -283,7 +285,7 @@ static PetscErrorCode NSSetup_B200(NS ns)
   MPI_Comm        comm;
   PetscMPIInt     rank, size;
   PetscInt        rx, ry, rz, x, y, z, m, n, p, d, nb, i, iprev;
-  PetscBool       iscart, lx, ly, lz;
+  PetscBool       iscart, lx, ly, lz, fx, fy, fz;
   MeshCartBoundaryType bt[3] = {MESHCART_BOUNDARY_NONE, MESHCART_BOUNDARY_NONE, MESHCART_BOUNDARY_NONE};
   const PetscScalar **ax, **ay, **az = NULL;
   double         *xf[3] = {NULL, NULL, NULL};
@@ -303,11 +305,14 @@ static PetscErrorCode NSSetup_B200(NS ns)
   PetscCheck(b->dim == 3 || size == 1, comm, PETSC_ERR_SUP, "2-D meshes run on one rank");
   PetscCall(MeshCartGetCorners(ns->mesh, &x, &y, &z, &m, &n, &p));
   PetscCall(MeshCartGetIsLastRank(ns->mesh, &lx, &ly, &lz));
+  PetscCall(MeshCartGetIsFirstRank(ns->mesh, &fx, &fy, &fz));
   PetscCall(MeshCartGetBoundaryTypes(ns->mesh, &bt[0], &bt[1], &bt[2]));
   for (d = 0; d < 3; ++d) b->per[d] = (PetscBool)(d < b->dim && bt[d] == MESHCART_BOUNDARY_PERIODIC);
   b->k0    = b->dim == 3 ? z : 0;
   b->nzl   = b->dim == 3 ? p : 1;
   b->lastz = (PetscBool)(b->dim == 3 && lz && !b->per[2]);
+  b->wallz[0] = (PetscBool)(b->dim == 3 && fz && !b->per[2]);
+  b->wallz[1] = b->lastz;
 
   /* global face coordinates per direction (slot PREV; cart.c:56-151): every rank holds x and y fully; z is gathered */
   PetscCall(MeshCartGetCoordinateArraysRead(ns->mesh, &ax, &ay, &az));
