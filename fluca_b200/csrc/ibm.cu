@@ -127,7 +127,7 @@ void ibm_set_markers(Solver &s, long n, const double *X, const double *Ud, const
   if (npts != 0 && npts != 3 && npts != 4) throw Error(FL_ERR_ARG, "the discrete delta function has 3 or 4 points");
   if (n >= (1L << 31) / 4) throw Error(FL_ERR_ARG, "too many markers");
   s.ex.sync();
-  if (n > b.cap || n == 0) {
+  if (n != b.cap || n == 0) { // the arrays are laid out with stride n (Um is one contiguous block for the allreduce)
     ibm_free_markers(b);
     if (n == 0) return;
     const int dim = s.dim;

@@ -174,3 +174,24 @@ def test_gpu_many_markers_per_cell_conserve_force(cuda):
     v = rng.standard_normal((3,) + orc.cell_shape)
     assert parity.rel(s.ibm_interpolate(v), orc.ibm_interpolate(v)) < 1e-13
     fb.NSDestroy(ns)
+
+
+def test_marker_count_may_change_between_calls(emu):
+    """set_markers again with fewer / more markers (a body that is re-meshed): the arrays are re-laid out and results still
+    match the definition"""
+    case = CASES["3d"]()
+    orc = cases.make_oracle(case)
+    ns = parity.make_ns(case, emu, "fractional")
+    s = fb.NSB200GetSolver(ns)
+    rng = np.random.default_rng(11)
+    v = rng.standard_normal((3,) + orc.cell_shape)
+    for n in (120, 40, 200):
+        mk = _random_markers(case, n, n, 4)
+        orc.set_markers(mk["X"], mk["Ud"], mk["dV"], 4)
+        fb.NSB200SetMarkers(ns, mk["X"], mk["Ud"], mk["dV"], 4)
+        assert parity.rel(s.ibm_interpolate(v), orc.ibm_interpolate(v)) < 1e-13
+        F = rng.standard_normal((3, n))
+        assert parity.rel(s.ibm_spread(F), orc.ibm_spread(F)) < 1e-13
+    fb.NSB200SetMarkers(ns, np.zeros((3, 0)), np.zeros((3, 0)), np.zeros(0), 4)  # n = 0 removes the markers
+    fb.NSStep(ns)
+    fb.NSDestroy(ns)
