@@ -105,7 +105,11 @@ SYMBOLS = [
     "fluca_b200_ibm_interpolate",
     "fluca_b200_ibm_spread",
     "fluca_b200_set_ibm_iterations",
+    "fluca_b200_set_abf_ainv_types",
 ]
+# PCABFAinvType (flucans.h:99-103) and its option strings PCABFAinvTypes[] (abfpc.c)
+AINV_ID, AINV_DIAG, AINV_ROWSUM = 0, 1, 2
+AINV_NAMES = {"id": AINV_ID, "diag": AINV_DIAG, "rowsum": AINV_ROWSUM}
 KT_NAMES = ["momentum_apply", "momentum_vec", "poisson_apply", "poisson_vec", "mg_smooth", "mg_transfer", "rhs_project", "outer", "halo", "ibm"]
 
 _P = C.c_void_p
@@ -149,6 +153,7 @@ def _prototype(L):
     L.fluca_b200_ibm_interpolate.argtypes = [_P, _P, _P]
     L.fluca_b200_ibm_spread.argtypes = [_P, _P, _P]
     L.fluca_b200_set_ibm_iterations.argtypes = [_P, C.c_int]
+    L.fluca_b200_set_abf_ainv_types.argtypes = [_P, C.c_int, C.c_int]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("fluca_b200_is_host_emulation",):

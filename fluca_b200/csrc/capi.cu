@@ -544,6 +544,14 @@ extern "C" int fluca_b200_ibm_spread(fluca_b200_solver *h, const double *Fm, dou
   API_END
 }
 
+extern "C" int fluca_b200_set_abf_ainv_types(fluca_b200_solver *h, int schur_type, int upper_type)
+{
+  API_BEGIN
+  if (!h) throw Error(FL_ERR_ARG, "null solver");
+  set_ainv_types(h->s, schur_type, upper_type);
+  API_END
+}
+
 extern "C" int fluca_b200_set_ibm_iterations(fluca_b200_solver *h, int passes)
 {
   API_BEGIN

@@ -193,8 +193,45 @@ struct PoissonApplyDot { // out = P p ; acc[0] += <a, out>
   }
 };
 
+// DIAG / ROWSUM Schur complement (abfpc.c:155-170): out = P p + vol D T ((1 - a1) .* G0 p), two passes with the
+// cell field w = (1 - a1) .* G0 p in between (its halo plane is needed by T across a slab face); returns <a, out>
+double schur_variant_apply_dot(Solver &s, double *pin, double *out, const double *a)
+{
+  if (!s.ainv_s.c[0] || !s.prepared) throw Error(FL_ERR_ARG, "the DIAG / ROWSUM Schur complement needs the momentum operator of a prepared step");
+  halo_scalar(s, pin);
+  {
+    KScope kt(s.ex, KT_POISSON_APPLY);
+    if (s.dim == 2) {
+      GradScaleCells<2> gs;
+      gs.g = s.gh.g, gs.scale = 1., gs.ainv = CV3(s.ainv_s), gs.p = pin, gs.vs = CV3(), gs.v = s.tw, gs.w = s.tw;
+      for_box(s.ex, cell_box(s), gs);
+    } else {
+      GradScaleCells<3> gs;
+      gs.g = s.gh.g, gs.scale = 1., gs.ainv = CV3(s.ainv_s), gs.p = pin, gs.vs = CV3(), gs.v = s.tw, gs.w = s.tw;
+      for_box(s.ex, cell_box(s), gs);
+    }
+  }
+  halo_cells(s, s.tw);
+  {
+    KScope kt(s.ex, KT_POISSON_APPLY);
+    if (s.dim == 2) {
+      SchurVariantApplyDot<2> f;
+      f.g = s.gh.g, f.p = pin, f.a = a, f.w = CV3(s.tw), f.out = out;
+      for_box_reduce<1>(s.ex, cell_box(s), f);
+    } else {
+      SchurVariantApplyDot<3> f;
+      f.g = s.gh.g, f.p = pin, f.a = a, f.w = CV3(s.tw), f.out = out;
+      for_box_reduce<1>(s.ex, cell_box(s), f);
+    }
+  }
+  double r;
+  reduce_finish(s, 1, &r);
+  return r;
+}
+
 static double poisson_apply_dot(Solver &s, double *pin, double *out, const double *a)
 {
+  if (s.opt.schur_ainv != 0) return schur_variant_apply_dot(s, pin, out, a);
   halo_scalar(s, pin);
 #ifndef FLUCA_HOSTEMU
   if (tma_usable(s)) {
@@ -346,7 +383,9 @@ static int poisson_bicgstab(Solver &s, double *b, double *x)
 
 int poisson_solve(Solver &s, double *b, double *x)
 {
-  return s.has_outlet ? poisson_bicgstab(s, b, x) : poisson_pcg(s, b, x);
+  // the DIAG / ROWSUM Schur complements are not symmetric either; the V-cycle of P stays their preconditioner
+  // (S' - S = D T (I - a1) G~ is O(dt) relative to S)
+  return (s.has_outlet || s.opt.schur_ainv != 0) ? poisson_bicgstab(s, b, x) : poisson_pcg(s, b, x);
 }
 
 } // namespace fluca

@@ -80,6 +80,8 @@ struct Options {
   int    inner_maxit   = 500;
   int    mg_nu1 = 2, mg_nu2 = 2, mg_coarse_sweeps = 40;
   int    quirk_bcg_scale = 1;
+  // approximation of A^-1 inside the ABF factors: 0 ID (default, abfpc.c:328-329), 1 DIAG, 2 ROWSUM (PCABFAinvType, flucans.h:99-103)
+  int    schur_ainv = 0, upper_ainv = 0;
 };
 
 struct Stats {
@@ -117,6 +119,9 @@ struct Solver {
   // ABF temporaries
   V3      vstar, Ustar;
   double *srhs = nullptr;
+  // DIAG / ROWSUM variants of the ABF factors: 1 / diag(A) or 1 / rowsum(A), rebuilt with A every step (PCSetUp_ABF)
+  V3      ainv_store[2] = {};
+  V3      ainv_s = {}, ainv_u = {}; // Schur complement / upper triangular factor (the same fields when the types agree)
   // momentum BiCGStab
   V3      kr, krh, kp, kv, ks, kt;
   // Poisson Krylov
@@ -170,6 +175,9 @@ void a_apply(Solver &s, const V3 &x, const V3 &y);
 void abf_apply(Solver &s, const V3 &bm, const V3 &bi, const double *bcn, const V3 &ov, const V3 &oU, double *op, bool guess = false, double in_scale = 1.);
 void coupled_apply(Solver &s, const V3 &xv, const V3 &xU, double *xp, const V3 &yv, const V3 &yU, double *yp);
 void schur_apply_reference_scaling(Solver &s, double *pin, double *out);
+void set_ainv_types(Solver &s, int schur_type, int upper_type); // PCABFSetSchurComplementAinvType / ...UpperTriangular...
+// out = vol (rho/dt) S' p for the DIAG / ROWSUM Schur complement, returns <a, out> (uses s.tw)
+double schur_variant_apply_dot(Solver &s, double *pin, double *out, const double *a);
 int  do_step(Solver &s, double t, int step_index);
 
 #ifndef FLUCA_HOSTEMU

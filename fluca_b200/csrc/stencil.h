@@ -161,6 +161,78 @@ FL_HD void a_apply_cell(const Geom &g, const StepParams &sp, const BcDev &bc, co
   else a_apply_core<DIM, true>(g, sp, bc, x, v0, U0, nb, i, j, kl, y);
 }
 
+// ------------------------------------------------------------------ diagonal / row sums of A (PCABF DIAG and ROWSUM variants)
+// The reference approximates A^-1 by the reciprocal of MatGetDiagonal(A) or MatGetRowSum(A) (abfpc.c:81-94, 151-168).
+// Matrix-free: the row of a_apply_core is evaluated on x = e_P (the cell's own entry of component c: ROWSUM = false) or on
+// x = 1 (every column: ROWSUM = true) with the same tables; out[c] = 1 / that value.
+template <int DIM, bool ROWSUM>
+FL_HD void a_row_inverse(const Geom &g, const StepParams &sp, const BcDev &bc, const CV3 &v0, const CV3 &U0, const Nbr<DIM> &nb, int i, int j, int kl, double out[DIM])
+{
+  const double e = ROWSUM ? 1. : 0.; // value of every column other than the diagonal one
+  double       vc[DIM], conv[DIM], lap[DIM];
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) vc[c] = v0.c[c][nb.c], conv[c] = 0., lap[c] = 0.;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) {
+    const Tab   &T  = g.t[d];
+    const int    ig = nb.ig[d];
+    const bool   lo = (!T.per && ig == 0), hi = (!T.per && ig == T.n - 1);
+    const double hh = 0.5 * T.hinv[ig];
+    const double Ul = U0.c[d][nb.c], Uu = U0.c[d][nb.fu[d]];
+    const double al = T.itw[2 * ig], bl = T.itw[2 * ig + 1], au = T.itw[2 * ig + 2], bu = T.itw[2 * ig + 3];
+    const long   pt = (lo || hi) ? bc_pt(g, 2 * d, i, j, kl) : 0;
+    // weights of (own cell, neighbour) in the normal-component interpolation to the two faces
+    const double Ild_c = lo ? T.cv2_lo[0] : bl, Ild_n = lo ? T.cv2_lo[1] : al;
+    const double Iud_c = hi ? T.cv2_hi[1] : au, Iud_n = hi ? T.cv2_hi[0] : bu;
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) {
+      const int w = (c == d) ? 1 : 0;
+      double    vbl, vbu;
+      if (lo) {
+        vbl = T.it_lo[w][0] * vc[c] + T.it_lo[w][1] * v0.c[c][nb.p[d]];
+        if (T.it_lo_bc != 0.) vbl += bc.vel[2 * d][0][c * bc.npts[2 * d] + pt];
+      } else vbl = al * v0.c[c][nb.m[d]] + bl * vc[c];
+      if (hi) {
+        vbu = T.it_hi[w][0] * v0.c[c][nb.m[d]] + T.it_hi[w][1] * vc[c];
+        if (T.it_hi_bc != 0.) vbu += bc.vel[2 * d + 1][0][c * bc.npts[2 * d + 1] + pt];
+      } else vbu = au * vc[c] + bu * v0.c[c][nb.p[d]];
+      // second convection term: columns of component d; the diagonal column is among them only when d == c
+      const double own = (c == d) ? 1. : e;
+      const double Ild = own * Ild_c + e * Ild_n, Iud = own * Iud_c + e * Iud_n;
+      const double Ilc = lo ? T.cv1_lo[w][0] + e * T.cv1_lo[w][1] : e * al + bl;
+      const double Iuc = hi ? e * T.cv1_hi[w][0] + T.cv1_hi[w][1] : au + e * bu;
+      conv[c] += hh * (Uu * Iuc + vbu * Iud - Ul * Ilc - vbl * Ild);
+      const double *lw = T.lapw + ((size_t)((lo || hi) ? w : 0) * T.n + ig) * 3;
+      double        l  = e * lw[0] + lw[1] + e * lw[2];
+      if (lo) l += e * T.lap_lo2[w];
+      if (hi) l += e * T.lap_hi2[w];
+      lap[c] += l;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) out[c] = 1. / (1. + sp.dt * conv[c] - sp.nu2 * lap[c]);
+}
+
+template <int DIM>
+struct AinvCells { // ainv = 1 / diag(A) (type 1) or 1 / rowsum(A) (type 2)
+  Geom       g;
+  StepParams sp;
+  BcDev      bc;
+  CV3        v0, U0;
+  int        type;
+  V3         ainv;
+  FL_HD void operator()(int i, int j, int kl) const
+  {
+    Nbr<DIM> nb;
+    nbr<DIM>(g, i, j, kl, nb);
+    double r[DIM];
+    if (type == 2) a_row_inverse<DIM, true>(g, sp, bc, v0, U0, nb, i, j, kl, r);
+    else a_row_inverse<DIM, false>(g, sp, bc, v0, U0, nb, i, j, kl, r);
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) ainv.c[c][nb.c] = r[c];
+  }
+};
+
 // y = A x fused with acc[0] += <a, y>, acc[1] += <y, y>
 template <int DIM>
 struct AApplyDots {
@@ -484,6 +556,67 @@ struct GradCells {
     grad_cell<DIM>(g, p, nb, gp);
 #pragma unroll
     for (int c = 0; c < DIM; ++c) fl_store(w.c[c] + nb.c, dtrho * gp[c]);
+  }
+};
+
+// PCABF with a DIAG / ROWSUM approximation a1 of A^-1 (abfpc.c:81-94, 151-168):
+//   w = scale * (1 - a1) .* G0 p            and, when vs is given,   v = vs - scale * a1 .* G0 p  (abfpc.c:80-95)
+// w is what the ID variant cancels analytically: T w is the face term left over in S and in the face update.
+template <int DIM>
+struct GradScaleCells {
+  Geom          g;
+  double        scale;
+  CV3           ainv;
+  const double *p;
+  CV3           vs; // may be empty
+  V3            v;
+  V3            w;
+  FL_HD void operator()(int i, int j, int kl) const
+  {
+    Nbr<DIM> nb;
+    nbr<DIM>(g, i, j, kl, nb);
+    double gp[DIM];
+    grad_cell<DIM>(g, p, nb, gp);
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) {
+      const double a1 = ainv.c[c][nb.c], sg = scale * gp[c];
+      w.c[c][nb.c]    = (1. - a1) * sg;
+      if (vs.c[0]) v.c[c][nb.c] = vs.c[c][nb.c] - a1 * sg;
+    }
+  }
+};
+
+// Schur complement of the DIAG / ROWSUM variants in the scaling of the pressure solve:
+//   out = vol * (rho/dt) S' p = P p + vol * D T w,   w = (1 - a1) .* G0 p   (abfpc.c:155-170; S' = D((-T) a1 G~ - (-R)))
+// fused with acc[0] += <a, out>
+template <int DIM>
+struct SchurVariantApplyDot {
+  Geom          g;
+  const double *p, *a;
+  CV3           w;
+  double       *out;
+  FL_HD void operator()(int i, int j, int kl, double acc[1]) const
+  {
+    Nbr<DIM> nb;
+    nbr<DIM>(g, i, j, kl, nb);
+    double s = poisson_apply_cell<DIM>(g, p, nb);
+    double h[3] = {1., 1., 1.};
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) h[d] = g.t[d].h[nb.ig[d]];
+    const double area[3] = {h[1] * h[2], h[0] * h[2], h[0] * h[1]};
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      const Tab    &T  = g.t[d];
+      const int     ig = nb.ig[d];
+      const double *f  = w.c[d];
+      const double  lo = t_face_lo<DIM>(g, d, f, nb);
+      double        up;
+      if (!T.per && ig == T.n - 1) up = t_face_wall_hi<DIM>(g, d, f, nb);
+      else up = T.itw[2 * ig + 2] * f[nb.c] + T.itw[2 * ig + 3] * f[nb.p[d]];
+      s += area[d] * (up - lo);
+    }
+    out[nb.c] = s;
+    acc[0] += a[nb.c] * s;
   }
 };
 

@@ -304,6 +304,40 @@ static void build_rhs(Solver &s)
   }
 }
 
+// PCABFSetSchurComplementAinvType / PCABFSetUpperTriangularAinvType (abfpc.c:300-318; -ns_pc_abf_{schur,upper}_ainv_type)
+void set_ainv_types(Solver &s, int schur_type, int upper_type)
+{
+  if (schur_type < 0 || schur_type > 2 || upper_type < 0 || upper_type > 2) throw Error(FL_ERR_ARG, "unknown A-inverse type (0 ID, 1 DIAG, 2 ROWSUM)");
+  s.opt.schur_ainv = schur_type, s.opt.upper_ainv = upper_type;
+  if (schur_type != 0) {
+    if (!s.ainv_store[0].c[0]) s.ainv_store[0] = s.alloc_v3();
+    if (!s.ps) s.ps = s.alloc_field(), s.pt = s.alloc_field(), s.prh = s.alloc_field(); // the Schur complement loses its symmetry: BiCGStab
+  }
+  if (upper_type != 0 && upper_type != schur_type && !s.ainv_store[1].c[0]) s.ainv_store[1] = s.alloc_v3();
+  s.ainv_s = schur_type != 0 ? s.ainv_store[0] : V3{};
+  s.ainv_u = upper_type == 0 ? V3{} : (upper_type == schur_type ? s.ainv_store[0] : s.ainv_store[1]);
+  s.prepared = false; // the vectors belong to the A of a step: rebuilt by the next prepare_step
+}
+
+// 1 / diag(A) or 1 / rowsum(A) of the step's momentum operator (PCSetUp_ABF runs once per step, abfpc.c:155-160)
+static void build_ainv(Solver &s)
+{
+  for (int which = 0; which < 2; ++which) {
+    const int type = which == 0 ? s.opt.schur_ainv : s.opt.upper_ainv;
+    const V3 &dst  = which == 0 ? s.ainv_s : s.ainv_u;
+    if (type == 0 || (which == 1 && type == s.opt.schur_ainv)) continue;
+    if (s.dim == 2) {
+      AinvCells<2> f;
+      f.g = s.gh.g, f.sp = s.sp, f.bc = s.bc, f.v0 = CV3(s.v0), f.U0 = CV3(s.U0), f.type = type, f.ainv = dst;
+      for_box(s.ex, cell_box(s), f);
+    } else {
+      AinvCells<3> f;
+      f.g = s.gh.g, f.sp = s.sp, f.bc = s.bc, f.v0 = CV3(s.v0), f.U0 = CV3(s.U0), f.type = type, f.ainv = dst;
+      for_box(s.ex, cell_box(s), f);
+    }
+  }
+}
+
 void prepare_step(Solver &s, double t, int step_index)
 {
   s.t = t, s.step_index = step_index;
@@ -312,6 +346,7 @@ void prepare_step(Solver &s, double t, int step_index)
   s.v0 = s.v, s.U0 = s.U;
   s.v = tv, s.U = tU;
   DIM_DISPATCH(s, build_rhs<2>(s), build_rhs<3>(s));
+  build_ainv(s); // after build_rhs: it exchanged the ghost planes of v0 and U0
   s.prepared = true;
 }
 
@@ -400,11 +435,21 @@ static void abf_apply_t(Solver &s, const V3 &bm, const V3 &bi, const double *bcn
   if (!s.has_outlet) remove_mean(s, op);
   // stage 2 (abfpc.c:80-101); the T*G~p terms of V cancel: V = V* - G~st p
   halo_scalar(s, op);
-  ProjectCells<DIM> pc;
-  pc.g = g, pc.dtrho = s.sp.dtrho, pc.vs = CV3(s.vstar), pc.p = op, pc.v = ov;
-  for_box<2>(s.ex, cell_box(s), pc);
-  fc.a = 1., fc.b = 0., fc.c = -s.sp.dtrho, fc.in = CV3(s.Ustar), fc.w = CV3(), fc.p = op, fc.out = oU;
-  for_box<2>(s.ex, cell_box(s), fc);
+  if (s.opt.upper_ainv == 0) {
+    ProjectCells<DIM> pc;
+    pc.g = g, pc.dtrho = s.sp.dtrho, pc.vs = CV3(s.vstar), pc.p = op, pc.v = ov;
+    for_box<2>(s.ex, cell_box(s), pc);
+    fc.a = 1., fc.b = 0., fc.c = -s.sp.dtrho, fc.in = CV3(s.Ustar), fc.w = CV3(), fc.p = op, fc.out = oU;
+    for_box<2>(s.ex, cell_box(s), fc);
+  } else {
+    // DIAG / ROWSUM (abfpc.c:81-99): v = v* - a1 G~ p,  V = V* - T (a1 G~ p) - (-R) p = V* - G~st p + T w,  w = (1 - a1) G~ p
+    GradScaleCells<DIM> gs;
+    gs.g = g, gs.scale = s.sp.dtrho, gs.ainv = CV3(s.ainv_u), gs.p = op, gs.vs = CV3(s.vstar), gs.v = ov, gs.w = s.tw;
+    for_box(s.ex, cell_box(s), gs);
+    halo_cells(s, s.tw);
+    fc.a = 1., fc.b = 1., fc.c = -s.sp.dtrho, fc.in = CV3(s.Ustar), fc.w = CV3(s.tw), fc.p = op, fc.out = oU;
+    for_box<2>(s.ex, cell_box(s), fc);
+  }
   s.stats.abf_applies++;
 }
 
@@ -446,7 +491,7 @@ void coupled_apply(Solver &s, const V3 &xv, const V3 &xU, double *xp, const V3 &
   DIM_DISPATCH(s, coupled_apply_t<2>(s, xv, xU, xp, yv, yU, yp), coupled_apply_t<3>(s, xv, xU, xp, yv, yU, yp));
 }
 
-// S p in the reference's scaling: S = -(dt/rho) D Gst0  (abfpc.c:151-170)
+// S p in the reference's scaling: S = -(dt/rho) D Gst0, or D((-T) a1 G~ - (-R)) for the DIAG / ROWSUM variants (abfpc.c:151-170)
 void schur_apply_reference_scaling(Solver &s, double *pin, double *out)
 {
   poisson_apply(s, pin, out);

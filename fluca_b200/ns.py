@@ -460,6 +460,15 @@ def _b200_setup(ns: NS):
         dat.solver = Solver(mesh.n, mesh.xf, [bc.type for bc in ns.bcs], ns.rho, ns.mu, ns.dt, mode=mode, k0=k0, nzl=nzl, comm=comm, library=lib, **kw)
     except _lib.FlucaB200Error as e:
         raise FlucaError(str(e)) from e
+    # -ns_pc_abf_schur_ainv_type / -ns_pc_abf_upper_ainv_type <ID|DIAG|ROWSUM> (abfpc.c:246-247 under the "ns_" prefix of nssol.c:17)
+    ainv = []
+    for key in ("ns_pc_abf_schur_ainv_type", "ns_pc_abf_upper_ainv_type"):
+        name = str(o.get(key, "ID")).lower()
+        if name not in _lib.AINV_NAMES:
+            raise FlucaError(f"-{key}: unknown A-inverse type {o[key]!r} (ID, DIAG, ROWSUM)")
+        ainv.append(_lib.AINV_NAMES[name])
+    if any(ainv):
+        dat.solver.set_abf_ainv_types(*ainv)
     dat.pts = [_boundary_points(mesh, dat.solver, b) for b in range(2 * mesh.dim)]
     dat.bc_cache = {}
     dat.history = []
@@ -598,6 +607,22 @@ def NSB200SetMarkers(ns: NS, X, Ud, dV, delta_points: int = 4, iterations: int =
 def NSB200GetMarkerForces(ns: NS):
     """(F, Um): force of every marker on the fluid and the interpolated predictor velocity of the last step."""
     return ns.data.solver.marker_forces()
+
+
+def PCABFSetSchurComplementAinvType(ns: NS, type_: int):
+    """flucans.h:106 (abfpc.c:300-308), addressed through the NS object because the b200 type owns its ABF factors."""
+    if not ns.setupcalled:
+        raise FlucaError("This function must be called after NSSetUp()")
+    s = ns.data.solver
+    s.set_abf_ainv_types(int(type_), s.ainv_types[1])
+
+
+def PCABFSetUpperTriangularAinvType(ns: NS, type_: int):
+    """flucans.h:107 (abfpc.c:310-318)."""
+    if not ns.setupcalled:
+        raise FlucaError("This function must be called after NSSetUp()")
+    s = ns.data.solver
+    s.set_abf_ainv_types(s.ainv_types[0], int(type_))
 
 
 def NSB200GetStats(ns: NS):

@@ -106,6 +106,7 @@ class Solver:
         _lib.check(self.L, self.L.fluca_b200_create(C.byref(d), comm.handle if comm else None, C.byref(h)))
         self._h = h
         self.rho, self.mu, self.dt, self.mode = rho, mu, dt, mode
+        self.ainv_types = (0, 0)
         nx, ny = self.n[0], self.n[1]
         self.cell_shape = (self.nzl, ny, nx)
         self.face_shape = []
@@ -225,6 +226,11 @@ class Solver:
         st = _lib.Stats()
         _lib.check(self.L, self.L.fluca_b200_apply_abf(self._h, bv.ctypes.data, self._ptrs(bU), bp.ctypes.data, xv.ctypes.data, self._ptrs(xU), xp.ctypes.data, C.byref(st)))
         return xv, xU, xp, st
+
+    def set_abf_ainv_types(self, schur_type: int = 0, upper_type: int = 0):
+        """PCABFSetSchurComplementAinvType / PCABFSetUpperTriangularAinvType (flucans.h:106-107): 0 ID, 1 DIAG, 2 ROWSUM."""
+        _lib.check(self.L, self.L.fluca_b200_set_abf_ainv_types(self._h, int(schur_type), int(upper_type)))
+        self.ainv_types = (int(schur_type), int(upper_type))
 
     # ------------------------------------------------------------------ immersed boundary
     def set_markers(self, X, Ud, dV, delta_points: int = 4, iterations: int = 1):

@@ -101,6 +101,16 @@ int fluca_b200_comm_create_callbacks(int rank, int nranks, fluca_b200_halo_fn, f
 int fluca_b200_create(const fluca_b200_desc *desc, fluca_b200_comm *comm /* NULL = single GPU */, fluca_b200_solver **out);
 int fluca_b200_destroy(fluca_b200_solver *s);
 
+/* ---- PCABF variants: PCABFSetSchurComplementAinvType / PCABFSetUpperTriangularAinvType (flucans.h:99-107,
+ * abfpc.c:300-318; options -ns_pc_abf_schur_ainv_type / -ns_pc_abf_upper_ainv_type, abfpc.c:246-247).  The approximation
+ * of A^-1 used in the Schur complement S = D((-T) A~^-1 G~ - (-R)) (abfpc.c:151-170) and in the upper triangular factor
+ * (abfpc.c:80-99): ID (default), the reciprocal diagonal of A, or the reciprocal row sums of A, rebuilt matrix-free with A
+ * at every step.  Takes effect from the next fluca_b200_prepare_step / fluca_b200_step. */
+#define FLUCA_B200_AINV_ID 0     /* PC_ABF_AINV_ID */
+#define FLUCA_B200_AINV_DIAG 1   /* PC_ABF_AINV_DIAG */
+#define FLUCA_B200_AINV_ROWSUM 2 /* PC_ABF_AINV_ROWSUM */
+int fluca_b200_set_abf_ainv_types(fluca_b200_solver *s, int schur_type, int upper_type);
+
 /* ---- state: ns->sol sub-vectors Velocity / FaceNormalVelocity / Pressure + "PressureHalfStep" (cnlinear.c:54) ---- */
 /* host pointers; any argument may be NULL to skip that field */
 int fluca_b200_set_state(fluca_b200_solver *s, const double *v, const double *const U[3], const double *p, const double *phalf);
@@ -137,7 +147,7 @@ int fluca_b200_prepare_step(fluca_b200_solver *s, double t, int step_index);
 int fluca_b200_get_rhs(fluca_b200_solver *s, double *rmom, double *const rint[3], double *rcon);
 /* y = A x, A = I + dt C - (nu dt/2) L of NSFormJacobian(UPDATE) (cnlinearcart3d.c:2930-2941); needs prepare_step */
 int fluca_b200_apply_momentum(fluca_b200_solver *s, const double *x, double *y);
-/* y = S p, S = -(dt/rho) D Gst (abfpc.c:151-170) */
+/* y = S p, S = -(dt/rho) D Gst (abfpc.c:151-170); with a DIAG / ROWSUM Schur type S depends on A: needs prepare_step */
 int fluca_b200_apply_schur(fluca_b200_solver *s, const double *p, double *y);
 /* y = M x of the coupled 3x3 block system (MatNest J, nsbasic.c:203-207) */
 int fluca_b200_apply_coupled(fluca_b200_solver *s, const double *xv, const double *const xU[3], const double *xp, double *yv, double *const yU[3], double *yp);

@@ -55,6 +55,8 @@ typedef struct {
   int    exact_schur;     /* 0: S by sparse products as abfpc.c:151-170; 1: S = -D*Gst assembled directly */
   int    quirk_bcg_scale; /* 1 (default): 3-D RHS scales the outlet gradient BC vector by 1 like
                              cnlinearcart3d.c:2977; 0: use dt/rho as the 2-D file does */
+  int    schur_ainv;      /* -ns_pc_abf_schur_ainv_type: 0 ID (default, abfpc.c:328), 1 DIAG, 2 ROWSUM (abfpc.c:151-168) */
+  int    upper_ainv;      /* -ns_pc_abf_upper_ainv_type: same values (abfpc.c:80-94) */
 } OrcOptions;
 
 typedef struct {

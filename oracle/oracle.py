@@ -45,6 +45,8 @@ class OrcOptions(C.Structure):
         ("ilu_blocks", C.c_int),
         ("exact_schur", C.c_int),
         ("quirk_bcg_scale", C.c_int),
+        ("schur_ainv", C.c_int),
+        ("upper_ainv", C.c_int),
     ]
 
 

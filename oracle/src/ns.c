@@ -894,6 +894,8 @@ void orc_default_options(OrcOptions *o)
   o->inner_maxit     = 10000;
   o->ilu_blocks      = 1;
   o->exact_schur     = 0;
+  o->schur_ainv      = 0;
+  o->upper_ainv      = 0;
   o->quirk_bcg_scale = 1;
 }
 
@@ -1059,15 +1061,40 @@ static void form_jacobian_update(Orc *g)
   csr_free(dtC), csr_free(t1);
 }
 
-/* PCSetUp_ABF, abfpc.c:113-182 (Ainv type ID) */
+/* reciprocal of diag(A) (type 1) or of the row sums of A (type 2): MatGetDiagonal / MatGetRowSum + VecReciprocal,
+ * abfpc.c:84-87, 157-160 */
+static void abf_ainv_vector(const Orc *g, int type, double *out)
+{
+  const Csr *A = g->A;
+  for (int r = 0; r < A->nrows; ++r) {
+    double s = 0.;
+    for (int k = A->ptr[r]; k < A->ptr[r + 1]; ++k)
+      if (type == 2 || A->idx[k] == r) s += A->val[k];
+    out[r] = 1. / s;
+  }
+}
+
+/* PCSetUp_ABF, abfpc.c:113-182 */
 static void abf_setup(Orc *g, const OrcOptions *opt)
 {
   csr_free(g->S);
   bjilu0_free(g->iluA), bjilu0_free(g->iluS);
-  if (opt->exact_schur) {
+  if (opt->exact_schur && opt->schur_ainv == 0) {
     Csr *dg = csr_matmat(g->D, g->Gst);
     csr_scale(dg, -1.);
     g->S = dg;
+  } else if (opt->schur_ainv != 0) {
+    /* S = D ((-T) A1^-1 G - (-R)), A1 = diag(A) or the row sums of A (abfpc.c:155-168) */
+    long    nv = g->dim * g->N;
+    double *ad = malloc(sizeof(double) * (size_t)nv);
+    abf_ainv_vector(g, opt->schur_ainv, ad);
+    Csr *Gd = csr_copy(g->G);
+    for (int r = 0; r < Gd->nrows; ++r)
+      for (int k = Gd->ptr[r]; k < Gd->ptr[r + 1]; ++k) Gd->val[k] *= ad[r]; /* MatDiagonalScale(Gdup, Adiag, NULL) :161 */
+    Csr *tmp  = csr_matmat(g->negT, Gd);        /* :163 */
+    Csr *tmp2 = csr_axpy(tmp, -1., g->negR);    /* :169 */
+    g->S      = csr_matmat(g->D, tmp2);         /* :170 */
+    csr_free(Gd), csr_free(tmp), csr_free(tmp2), free(ad);
   } else {
     Csr *tmp  = csr_matmat(g->negT, g->G);      /* :153 */
     Csr *tmp2 = csr_axpy(tmp, -1., g->negR);    /* :169 */
@@ -1122,6 +1149,12 @@ static void abf_apply_internal(Orc *g, const OrcOptions *opt, const double *b, d
   g->schur_its += ki.its;
   /* stage 2 */
   csr_mult(g->G, p, gp);                                               /* :80 */
+  if (opt->upper_ainv != 0) {                                          /* :81-94 */
+    double *ad = malloc(sizeof(double) * (size_t)nv);
+    abf_ainv_vector(g, opt->upper_ainv, ad);
+    for (k = 0; k < nv; ++k) gp[k] *= ad[k];
+    free(ad);
+  }
   for (k = 0; k < nv; ++k) v[k] = vstar[k] - gp[k];                    /* :95 */
   csr_mult_add(g->negT, gp, Vstar, V);                                 /* :96 */
   csr_mult(g->negR, p, negRp);                                         /* :99 */

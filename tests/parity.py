@@ -68,18 +68,22 @@ def set_initial(ns, state):
     fb.NSSetSolutionSubVector(ns, fb.NS_FIELD_PRESSURE, p)
 
 
-def compare_steps(case, library=None, mode="coupled", nsteps=2, seed=None, tol=1e-10, ptol=None, markers=None):
-    """K steps on both sides at tight tolerances; returns the per-step relative L2 differences."""
+AINV_OPTION = {0: "ID", 1: "DIAG", 2: "ROWSUM"}  # PCABFAinvTypes[], abfpc.c:4
+
+
+def compare_steps(case, library=None, mode="coupled", nsteps=2, seed=None, tol=1e-10, ptol=None, markers=None, ainv=(0, 0)):
+    """K steps on both sides at tight tolerances; returns the per-step relative L2 differences.
+    ainv = (schur, upper) PCABFAinvType of both sides (-ns_pc_abf_{schur,upper}_ainv_type)."""
     orc = cases.make_oracle(case)
     state = case.initial_state(seed=seed)
     orc.set_state(*state)
-    ns = make_ns(case, library, mode, **TIGHT)
+    ns = make_ns(case, library, mode, ns_pc_abf_schur_ainv_type=AINV_OPTION[ainv[0]], ns_pc_abf_upper_ainv_type=AINV_OPTION[ainv[1]], **TIGHT)
     set_initial(ns, state)
     if markers is not None:  # immersed boundary: the same marker list on both sides
         orc.set_markers(markers["X"], markers["Ud"], markers["dV"], markers.get("npts", 4), markers.get("iterations", 1))
         fb.NSB200SetMarkers(ns, markers["X"], markers["Ud"], markers["dV"], markers.get("npts", 4), markers.get("iterations", 1))
     out = []
-    oopt = O.default_options(mode=0 if mode == "coupled" else 1, **ORC_TIGHT)
+    oopt = O.default_options(mode=0 if mode == "coupled" else 1, schur_ainv=ainv[0], upper_ainv=ainv[1], **ORC_TIGHT)
     for _ in range(nsteps):
         oi = orc.step(oopt)
         fb.NSStep(ns)
