@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--strong", action="store_true", help="strong scaling: the n^3 grid is split over the GPUs (default: weak, n^3 per GPU)")
     ap.add_argument("--mode", default="coupled", choices=["coupled", "fractional"])
     ap.add_argument("--restart", type=int, default=0, help="outer GMRES restart (memory: (restart+1) x 7 fields; default 3 at 512^3, 10 below; the flexible form also keeps restart x 7 fields of preconditioned vectors)")
+    ap.add_argument("--schur-ainv", default="ID", choices=["ID", "DIAG", "ROWSUM"], help="-ns_pc_abf_schur_ainv_type (abfpc.c:246); the headline numbers use the reference default ID")
+    ap.add_argument("--upper-ainv", default="ID", choices=["ID", "DIAG", "ROWSUM"], help="-ns_pc_abf_upper_ainv_type (abfpc.c:247)")
     ap.add_argument("--cpu-n", type=int, default=64, help="cells per direction of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -158,7 +160,8 @@ def cpu_sample(args, n, steps, warmup, mode, threads):
         orc.set_markers(mk["X"], mk["Ud"], mk["dV"], 4)
     else:
         orc.set_state(*case.initial_state())
-    opt = O.default_options(mode=0 if mode == "coupled" else 1, ilu_blocks=threads)
+    ainv = {"ID": 0, "DIAG": 1, "ROWSUM": 2}
+    opt = O.default_options(mode=0 if mode == "coupled" else 1, ilu_blocks=threads, schur_ainv=ainv[args.schur_ainv], upper_ainv=ainv[args.upper_ainv])
     infos = []
     for _ in range(warmup):
         orc.step(opt)
@@ -231,7 +234,7 @@ def run_b200(args):
     nzg = n if args.strong else n * world  # weak scaling (default): an n^3 slab per GPU; strong: n / N planes per GPU
     restart = args.restart or (3 if n >= 512 else 10)
     case = make_case(args, n, nzg)
-    opts = {"ns_ksp_gmres_restart": restart}
+    opts = {"ns_ksp_gmres_restart": restart, "ns_pc_abf_schur_ainv_type": args.schur_ainv, "ns_pc_abf_upper_ainv_type": args.upper_ainv}
     ns = parity.make_ns(case, lib, args.mode, comm=comm, **opts)
     s = fb.NSB200GetSolver(ns)
     cells_total = float(n) * n * nzg
@@ -295,6 +298,10 @@ def run_b200(args):
     # momentum apply fused with two dots: reads x(3) v0(3) U0(3) (+ rhat(3) in the first of the two applies of a
     # BiCGStab iteration), writes y(3): (120 + 96) / 2 = 108 B per cell and launch on average
     per_launch = {"momentum_apply": 108.0, "poisson_apply": 16.0}
+    if args.schur_ainv != "ID":
+        # DIAG / ROWSUM Schur complement = two launches per apply: w = (1 - a1) G0 p reads p, a1(3) writes w(3) = 56 B;
+        # out = P p + vol D T w reads p, w(3), a writes out = 48 B; mean 52 B per cell and launch
+        per_launch["poisson_apply"] = 52.0
     shares = {k: v[0] / ms for k, v in ktimes.items() if v[1] > 0}
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -330,6 +337,7 @@ def run_b200(args):
         "config": {
             "workload": workload_text(args, n, nzg, restart),
             "mode": args.mode,
+            "abf_ainv": {"schur": args.schur_ainv, "upper": args.upper_ainv},
             "l2": f"inputs larger than L2 (each field {8 * n**3 / 1e6:.0f} MB vs 126 MB L2; >50 fields streamed per step), no flush",
             "iterations_per_step": {"outer": [st.outer_its for st in stats], "momentum": [st.mom_its for st in stats], "schur": [st.schur_its for st in stats], "abf": [st.abf_applies for st in stats]},
         },

@@ -93,7 +93,8 @@ def main():
         comm = dict(rank=rank, nranks=world, make_comm=lambda L: fb.Comm.nccl(L, uid, rank, world))
     else:
         comm = dict(rank=rank, nranks=world, make_comm=make_comm_factory(rank, world))
-    ns = parity.make_ns(case, lib, mode, comm=comm, **parity.TIGHT)
+    ainv = [int(a) for a in os.environ.get("FLUCA_WORKER_AINV", "0,0").split(",")]  # PCABFAinvType of (Schur, upper)
+    ns = parity.make_ns(case, lib, mode, comm=comm, ns_pc_abf_schur_ainv_type=parity.AINV_OPTION[ainv[0]], ns_pc_abf_upper_ainv_type=parity.AINV_OPTION[ainv[1]], **parity.TIGHT)
     s = fb.NSB200GetSolver(ns)
     v, U, p = case.initial_state(seed=31)
     k0, nzl = s.k0, s.nzl

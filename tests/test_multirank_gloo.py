@@ -22,12 +22,12 @@ def _free_port():
     return p
 
 
-def run_world(case_name, mode, world, tmp_path, backend="gloo"):
+def run_world(case_name, mode, world, tmp_path, backend="gloo", ainv=(0, 0)):
     out = str(tmp_path / f"{case_name}_{mode}_{world}.npz")
     port = _free_port()
     procs = []
     for r in range(world):
-        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1", FLUCA_WORKER_BACKEND=backend)
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1", FLUCA_WORKER_BACKEND=backend, FLUCA_WORKER_AINV=f"{ainv[0]},{ainv[1]}")
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "multirank_worker.py"), case_name, mode, out], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     logs = []
     for p in procs:
@@ -54,14 +54,14 @@ CASEMAP = {
 }
 
 
-def _oracle_reference(case_name, mode):
+def _oracle_reference(case_name, mode, ainv=(0, 0)):
     case = CASEMAP[case_name]()
     orc = cases.make_oracle(case)
     orc.set_state(*case.initial_state(seed=31))
     if case_name.startswith("sphere_ibm"):
         mk = cases.sphere_markers((0.1, 0.0, 0.05), 1.2, 120, 4.0 / case.n[1])
         orc.set_markers(mk["X"], mk["Ud"], mk["dV"], 4, 2)
-    infos = [orc.step(O.default_options(mode=0 if mode == "coupled" else 1, **parity.ORC_TIGHT)) for _ in range(2)]
+    infos = [orc.step(O.default_options(mode=0 if mode == "coupled" else 1, schur_ainv=ainv[0], upper_ainv=ainv[1], **parity.ORC_TIGHT)) for _ in range(2)]
     return orc, infos
 
 
@@ -80,6 +80,20 @@ def test_slab_partition_matches_oracle(case_name, mode, world, tmp_path):
     if "F" in got.files:  # immersed boundary across the slab interface: marker velocities are summed over the ranks
         Fo, Uo = orc.marker_forces()
         assert parity.rel(got["Um"], Uo) < 1e-10 and parity.rel(got["F"], Fo) < 1e-8
+    if mode == "coupled":
+        assert [int(a) for a in got["its"][:, 0]] == [i.outer_its for i in infos]
+
+
+@pytest.mark.parametrize("case_name,mode,world,ainv", [("cavity3d", "coupled", 2, (1, 1)), ("periodic_z", "fractional", 2, (2, 1)), ("three", "fractional", 3, (1, 0))])
+def test_slab_partition_abf_variants_match_oracle(case_name, mode, world, ainv, tmp_path):
+    """PCABF DIAG / ROWSUM factors across slab faces: the cell field (1 - a1) G~ p needs its own ghost planes for T."""
+    parity.hostemu_library()
+    got = run_world(case_name, mode, world, tmp_path, ainv=ainv)
+    orc, infos = _oracle_reference(case_name, mode, ainv)
+    ref = orc.get_state()
+    assert parity.rel(got["v"], ref["v"]) < 1e-10
+    assert parity.relU([got["U0"], got["U1"], got["U2"]], ref["U"]) < 1e-10
+    assert parity.rel(got["p"], ref["p"]) < 1e-9 and parity.rel(got["phalf"], ref["phalf"]) < 1e-9
     if mode == "coupled":
         assert [int(a) for a in got["its"][:, 0]] == [i.outer_its for i in infos]
 
