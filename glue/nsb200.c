@@ -32,6 +32,7 @@ typedef struct {
   PetscInt  restart, outer_maxit, inner_maxit;
   PetscReal outer_rtol, mom_rtol, schur_rtol;
   PetscInt  sync_interval;         /* download ns->sol every k steps (1 = every step; 0 = only on demand) */
+  PCABFAinvType schur_ainv, upper_ainv; /* the PCABF variants (flucans.h:99-107): ID, DIAG or ROWSUM approximation of A^-1 */
   /* geometry of this rank's slab */
   PetscInt dim, M, N, P, k0, nzl;
   PetscBool lastz, per[3];
@@ -249,6 +250,10 @@ static PetscErrorCode NSSetFromOptions_B200(NS ns, PetscOptionItems PetscOptions
   PetscCall(PetscOptionsReal("-ns_b200_momentum_rtol", "momentum solve relative tolerance", "", b->mom_rtol, &b->mom_rtol, NULL));
   PetscCall(PetscOptionsReal("-ns_b200_schur_rtol", "pressure solve relative tolerance", "", b->schur_rtol, &b->schur_rtol, NULL));
   PetscCall(PetscOptionsInt("-ns_b200_sync_interval", "copy the device state into ns->sol every k steps (0: only for viewers)", "", b->sync_interval, &b->sync_interval, NULL));
+  /* the options of the PC "abf" the base class creates under the "ns_" prefix (abfpc.c:246-247, nssol.c:17): this type never
+   * applies that PC, so it reads the same two names and hands the choice to the device-side ABF factors */
+  PetscCall(PetscOptionsEnum("-ns_pc_abf_schur_ainv_type", "Type of approximation used in Schur complement", "PCABFSetSchurComplementAinvType", PCABFAinvTypes, (PetscEnum)b->schur_ainv, (PetscEnum *)&b->schur_ainv, NULL));
+  PetscCall(PetscOptionsEnum("-ns_pc_abf_upper_ainv_type", "Type of approximation used in upper triangular matrix", "PCABFSetUpperTriangularAinvType", PCABFAinvTypes, (PetscEnum)b->upper_ainv, (PetscEnum *)&b->upper_ainv, NULL));
   PetscOptionsHeadEnd();
   PetscFunctionReturn(PETSC_SUCCESS);
 }
@@ -352,6 +357,7 @@ static PetscErrorCode NSSetup_B200(NS ns)
     B200Call(ns, fluca_b200_comm_create_nccl(id, nbytes, (int)rank, (int)size, &gcomm));
   }
   B200Call(ns, fluca_b200_create(&desc, gcomm, &b->solver));
+  if (b->schur_ainv != PC_ABF_AINV_ID || b->upper_ainv != PC_ABF_AINV_ID) B200Call(ns, fluca_b200_set_abf_ainv_types(b->solver, (int)b->schur_ainv, (int)b->upper_ainv)); /* same numeric values */
   for (d = 0; d < 3; ++d) PetscCall(PetscFree(xf[d]));
 
   b->ncell    = (size_t)m * n * b->nzl;
@@ -468,6 +474,7 @@ static PetscErrorCode NSView_B200(NS ns, PetscViewer viewer)
   PetscCall(PetscObjectTypeCompare((PetscObject)viewer, PETSCVIEWERASCII, &isascii));
   if (isascii) {
     PetscCall(PetscViewerASCIIPrintf(viewer, "  b200: mode %s, slab planes [%" PetscInt_FMT ", %" PetscInt_FMT "), outer restart %" PetscInt_FMT "\n", b->mode ? "fractional" : "coupled", b->k0, b->k0 + b->nzl, b->restart));
+    PetscCall(PetscViewerASCIIPrintf(viewer, "  ABF factors: Schur complement A inverse type %s, upper triangular A inverse type %s\n", PCABFAinvTypes[b->schur_ainv], PCABFAinvTypes[b->upper_ainv])); /* as PCView_ABF, abfpc.c:265-266 */
     PetscCall(PetscViewerASCIIPrintf(viewer, "  last step: outer %d, momentum %d, Schur %d iterations\n", b->stats.outer_its, b->stats.mom_its, b->stats.schur_its));
   }
   PetscFunctionReturn(PETSC_SUCCESS);
@@ -508,6 +515,8 @@ PetscErrorCode NSCreate_B200(NS ns)
   b->mom_rtol      = 1e-5;
   b->schur_rtol    = 1e-5;
   b->sync_interval = 1;
+  b->schur_ainv    = PC_ABF_AINV_ID; /* abfpc.c:328-329 */
+  b->upper_ainv    = PC_ABF_AINV_ID;
 
   ns->ops->setfromoptions = NSSetFromOptions_B200;
   ns->ops->setup          = NSSetup_B200;

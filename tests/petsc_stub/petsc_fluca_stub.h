@@ -81,6 +81,9 @@ PetscErrorCode PetscOptionsIntStub(PetscOptionItems, const char *, const char *,
 PetscErrorCode PetscOptionsRealStub(PetscOptionItems, const char *, const char *, const char *, PetscReal, PetscReal *, PetscBool *);
 #define PetscOptionsInt(a, b, c, d, e, f) PetscOptionsIntStub(PetscOptionsObject, a, b, c, d, e, f)
 #define PetscOptionsReal(a, b, c, d, e, f) PetscOptionsRealStub(PetscOptionsObject, a, b, c, d, e, f)
+typedef int PetscEnum;
+PetscErrorCode PetscOptionsEnumStub(PetscOptionItems, const char *, const char *, const char *, const char *const *, PetscEnum, PetscEnum *, PetscBool *);
+#define PetscOptionsEnum(a, b, c, d, e, f, g) PetscOptionsEnumStub(PetscOptionsObject, a, b, c, d, e, f, g)
 
 int MPI_Comm_rank(MPI_Comm, int *);
 int MPI_Comm_size(MPI_Comm, int *);
@@ -159,6 +162,8 @@ typedef enum { NS_INIT_JACOBIAN, NS_UPDATE_JACOBIAN } NSFormJacobianType;
 #define NS_FIELD_FACE_NORMAL_VELOCITY "FaceNormalVelocity"
 #define NS_FIELD_PRESSURE "Pressure"
 PetscErrorCode NSRegister(const char[], PetscErrorCode (*)(NS));
+typedef enum { PC_ABF_AINV_ID, PC_ABF_AINV_DIAG, PC_ABF_AINV_ROWSUM } PCABFAinvType; /* flucans.h:99-103 */
+extern const char *const PCABFAinvTypes[];                                             /* flucans.h:104 */
 PetscErrorCode NSGetField(NS, const char[], PetscInt *, MeshDMType *, IS *);
 PetscErrorCode NSGetSolutionSubVector(NS, const char[], Vec *);
 PetscErrorCode NSRestoreSolutionSubVector(NS, const char[], Vec *);

@@ -55,7 +55,7 @@ def test_oracle_coupled_solution_does_not_depend_on_the_preconditioner_variant(a
 
 
 def test_oracle_diag_fractional_step_is_closer_to_the_coupled_solution():
-    """What the variants are for (THEORY_GUIDE.md:299-308): at nu dt / h^2 ~ 0.8 one DIAG application
+    """What the variants are for (THEORY_GUIDE.md:299-308): on the 32^2 cavity at dt = 0.02 one DIAG application
     leaves less splitting error than one ID application."""
     case = cases.cavity2d(n=32, Re=100.0, dt=0.02)
 
