@@ -23,18 +23,23 @@ TIGHT = dict(outer_rtol=1e-13, mom_rtol=1e-13, schur_rtol=1e-13)
 
 
 def fixtures():
-    """name -> (case, seed, markers or None); kept tiny: the file is a few tens of kB"""
+    """name -> (case, seed, markers or None, (Schur, upper) PCABFAinvType); kept tiny: the file is a few hundred kB"""
     c3 = cases.channel3d(n=(12, 8, 8), pout=0.1, dt=0.05)
+    ID, DIAG, ROWSUM = 0, 1, 2  # PCABFAinvType, flucans.h:99-103
     return {
-        "cavity2d_8": (cases.cavity2d(n=8), 3, None),
-        "cavity3d_sym_6x6x4": (cases.cavity3d(n=(6, 6, 4)), 5, None),
-        "channel3d_outlet_8x6x6": (cases.channel3d(n=(8, 6, 6), pout=0.2, dt=0.05), 11, None),
-        "tgv_periodic_8": (cases.tgv(n=8, periodic=True, dt=0.05), None, None),
-        "sphere_ibm_12x8x8": (c3, 31, cases.sphere_markers((0.1, 0.0, 0.05), 1.2, 60, 0.5)),
+        "cavity2d_8": (cases.cavity2d(n=8), 3, None, (ID, ID)),
+        "cavity3d_sym_6x6x4": (cases.cavity3d(n=(6, 6, 4)), 5, None, (ID, ID)),
+        "channel3d_outlet_8x6x6": (cases.channel3d(n=(8, 6, 6), pout=0.2, dt=0.05), 11, None, (ID, ID)),
+        "tgv_periodic_8": (cases.tgv(n=8, periodic=True, dt=0.05), None, None, (ID, ID)),
+        "sphere_ibm_12x8x8": (c3, 31, cases.sphere_markers((0.1, 0.0, 0.05), 1.2, 60, 0.5), (ID, ID)),
+        # PCABF variants (abfpc.c:81-94, 151-168)
+        "cavity2d_8_abf_diag": (cases.cavity2d(n=8), 3, None, (DIAG, DIAG)),
+        "cavity3d_sym_6x6x4_abf_rowsum_diag": (cases.cavity3d(n=(6, 6, 4)), None, None, (ROWSUM, DIAG)),
+        "channel3d_outlet_8x6x6_abf_diag": (cases.channel3d(n=(8, 6, 6), pout=0.2, dt=0.05), 11, None, (DIAG, DIAG)),
     }
 
 
-def run(case, seed, markers, mode, nsteps=2):
+def run(case, seed, markers, mode, nsteps=2, ainv=(0, 0)):
     orc = cases.make_oracle(case)
     state = case.initial_state(seed=seed)
     orc.set_state(*state)
@@ -44,7 +49,7 @@ def run(case, seed, markers, mode, nsteps=2):
     orc.set_state(*state)  # prepare_step does not advance, but keep the two uses independent
     its = []
     for _ in range(nsteps):
-        info = orc.step(O.default_options(mode=mode, **TIGHT))
+        info = orc.step(O.default_options(mode=mode, schur_ainv=ainv[0], upper_ainv=ainv[1], **TIGHT))
         its.append(info.outer_its)
     out = orc.get_state()
     return state, rhs, out, its
@@ -52,9 +57,9 @@ def run(case, seed, markers, mode, nsteps=2):
 
 def main():
     data = {}
-    for name, (case, seed, markers) in fixtures().items():
+    for name, (case, seed, markers, ainv) in fixtures().items():
         for mode, tag in ((0, "coupled"), (1, "fractional")):
-            state, rhs, out, its = run(case, seed, markers, mode)
+            state, rhs, out, its = run(case, seed, markers, mode, ainv=ainv)
             k = f"{name}/{tag}"
             if tag == "coupled":
                 data[f"{name}/in_v"], data[f"{name}/in_p"] = state[0], state[2]

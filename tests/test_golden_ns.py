@@ -26,9 +26,9 @@ def _inputs(name, dim):
 
 @pytest.mark.parametrize("name", NAMES)
 def test_oracle_reproduces_the_committed_fixtures(name):
-    case, seed, markers = FIX[name]
+    case, seed, markers, ainv = FIX[name]
     for mode, tag in ((0, "coupled"), (1, "fractional")):
-        state, rhs, out, its = _gen.run(case, seed, markers, mode)
+        state, rhs, out, its = _gen.run(case, seed, markers, mode, ainv=ainv)
         if tag == "coupled":
             assert np.array_equal(state[0], G[f"{name}/in_v"])  # the seeded inputs themselves
             assert parity.rel(rhs, G[f"{name}/rhs"]) < 1e-13
@@ -37,8 +37,8 @@ def test_oracle_reproduces_the_committed_fixtures(name):
 
 
 def _product_matches(lib, name, mode):
-    case, seed, markers = FIX[name]
-    ns = parity.make_ns(case, lib, mode, **parity.TIGHT)
+    case, seed, markers, ainv = FIX[name]
+    ns = parity.make_ns(case, lib, mode, ns_pc_abf_schur_ainv_type=parity.AINV_OPTION[ainv[0]], ns_pc_abf_upper_ainv_type=parity.AINV_OPTION[ainv[1]], **parity.TIGHT)
     parity.set_initial(ns, _inputs(name, case.dim))
     if markers is not None:
         fb.NSB200SetMarkers(ns, markers["X"], markers["Ud"], markers["dV"], markers.get("npts", 4))
