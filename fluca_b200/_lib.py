@@ -106,6 +106,8 @@ SYMBOLS = [
     "fluca_b200_ibm_spread",
     "fluca_b200_set_ibm_iterations",
     "fluca_b200_set_abf_ainv_types",
+    "fluca_b200_stage_state",
+    "fluca_b200_staged_state",
 ]
 # PCABFAinvType (flucans.h:99-103) and its option strings PCABFAinvTypes[] (abfpc.c)
 AINV_ID, AINV_DIAG, AINV_ROWSUM = 0, 1, 2
@@ -154,6 +156,8 @@ def _prototype(L):
     L.fluca_b200_ibm_spread.argtypes = [_P, _P, _P]
     L.fluca_b200_set_ibm_iterations.argtypes = [_P, C.c_int]
     L.fluca_b200_set_abf_ainv_types.argtypes = [_P, C.c_int, C.c_int]
+    L.fluca_b200_stage_state.argtypes = [_P]
+    L.fluca_b200_staged_state.argtypes = [_P, C.POINTER(_P), _PD3, C.POINTER(_P), C.POINTER(_P)]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("fluca_b200_is_host_emulation",):

@@ -195,6 +195,7 @@ extern "C" int fluca_b200_set_state(fluca_b200_solver *h, const double *v, const
 {
   API_BEGIN
   Solver &s = h->s;
+  view_fence(s);
   if (v) put_cells(s, s.v, v);
   if (U)
     for (int d = 0; d < s.dim; ++d)
@@ -216,6 +217,92 @@ extern "C" int fluca_b200_get_state(fluca_b200_solver *h, double *v, double *con
   if (p) get(s, p, s.p, cell_ext(s.gh.g));
   if (phalf) get(s, phalf, s.phalf, cell_ext(s.gh.g));
   s.ex.sync();
+  API_END
+}
+
+// ------------------------------------------------------------------ asynchronous solution view (StateView, solver.h)
+namespace {
+void *pinned_alloc(size_t bytes)
+{
+  void *p = nullptr;
+  if (bytes == 0) bytes = 8;
+#ifndef FLUCA_HOSTEMU
+  FL_CUDA(cudaMallocHost(&p, bytes));
+#else
+  p = malloc(bytes);
+  if (!p) throw Error(FL_ERR_INTERNAL, "host allocation failed");
+#endif
+  return p;
+}
+// compact copy of one padded field to the host on the view stream
+void view_get(Solver &s, double *host, const double *dev, Ext e)
+{
+  const Geom &g = s.gh.g;
+  for (int k = 0; k < e.planes; ++k) {
+    double       *dst = host + (size_t)k * e.w * e.hgt;
+    const double *src = dev + g.idx(0, 0, k);
+#ifndef FLUCA_HOSTEMU
+    FL_CUDA(cudaMemcpy2DAsync(dst, sizeof(double) * e.w, src, sizeof(double) * g.px, sizeof(double) * e.w, e.hgt, cudaMemcpyDeviceToHost, s.view.stream));
+#else
+    for (int r = 0; r < e.hgt; ++r) memcpy(dst + (size_t)r * e.w, src + (size_t)r * g.px, sizeof(double) * e.w);
+#endif
+  }
+}
+} // namespace
+
+extern "C" int fluca_b200_stage_state(fluca_b200_solver *h)
+{
+  API_BEGIN
+  if (!h) throw Error(FL_ERR_ARG, "null solver");
+  Solver    &s = h->s;
+  StateView &w = s.view;
+  const Geom &g = s.gh.g;
+  if (!w.v) {
+    w.v = (double *)pinned_alloc(sizeof(double) * ext_count(cell_ext(g)) * s.dim);
+    for (int d = 0; d < s.dim; ++d) w.U[d] = (double *)pinned_alloc(sizeof(double) * ext_count(face_ext(g, d)));
+    w.p     = (double *)pinned_alloc(sizeof(double) * ext_count(cell_ext(g)));
+    w.phalf = (double *)pinned_alloc(sizeof(double) * ext_count(cell_ext(g)));
+#ifndef FLUCA_HOSTEMU
+    FL_CUDA(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+    FL_CUDA(cudaEventCreateWithFlags(&w.ready, cudaEventDisableTiming));
+    FL_CUDA(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
+#endif
+  }
+#ifndef FLUCA_HOSTEMU
+  // after everything already submitted on the solver stream (the step that produced this state) ...
+  FL_CUDA(cudaEventRecord(w.ready, s.ex.stream));
+  FL_CUDA(cudaStreamWaitEvent(w.stream, w.ready, 0));
+#endif
+  const Ext ce = cell_ext(g);
+  for (int c = 0; c < s.dim; ++c) view_get(s, w.v + c * ext_count(ce), s.v.c[c], ce);
+  for (int d = 0; d < s.dim; ++d) view_get(s, w.U[d], s.U.c[d], face_ext(g, d));
+  view_get(s, w.p, s.p, ce);
+  view_get(s, w.phalf, s.phalf, ce);
+#ifndef FLUCA_HOSTEMU
+  // ... and before the solver next overwrites what the copy reads (view_fence)
+  FL_CUDA(cudaEventRecord(w.done, w.stream));
+  w.pending = true;
+#endif
+  w.valid      = true;
+  w.step_index = s.step_index;
+  w.t          = s.t;
+  API_END
+}
+
+extern "C" int fluca_b200_staged_state(fluca_b200_solver *h, const double **v, const double *U[3], const double **p, const double **phalf)
+{
+  API_BEGIN
+  if (!h) throw Error(FL_ERR_ARG, "null solver");
+  StateView &w = h->s.view;
+  if (!w.valid) throw Error(FL_ERR_ARG, "no staged state: call fluca_b200_stage_state first");
+#ifndef FLUCA_HOSTEMU
+  FL_CUDA(cudaEventSynchronize(w.done)); // the host waits for the copy only; the solver stream keeps running
+#endif
+  if (v) *v = w.v;
+  if (U)
+    for (int d = 0; d < 3; ++d) U[d] = w.U[d];
+  if (p) *p = w.p;
+  if (phalf) *phalf = w.phalf;
   API_END
 }
 
@@ -370,6 +457,7 @@ extern "C" int fluca_b200_snapshot_restore(fluca_b200_solver *h)
   API_BEGIN
   Solver &s = h->s;
   if (!h->have_snap) throw Error(FL_ERR_ARG, "no snapshot saved");
+  view_fence(s);
   const size_t nb = sizeof(double) * (size_t)s.gh.g.nalloc;
   for (int c = 0; c < s.dim; ++c) copy_d2d(s.ex, s.v.c[c], h->sv.c[c], nb), copy_d2d(s.ex, s.U.c[c], h->sU.c[c], nb);
   copy_d2d(s.ex, s.p, h->sp, nb), copy_d2d(s.ex, s.phalf, h->sph, nb);

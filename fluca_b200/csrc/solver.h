@@ -97,6 +97,23 @@ struct Field {
   double *d = nullptr;
 };
 
+// Asynchronous solution view (monitors, NSViewSolution, CGNS output -- nssol.c:130-174, cartvec.c:4-25):
+// a copy of the state in library-owned PINNED host memory (compact C-ABI layout), made by a second stream that is ordered
+// after the step that produced the state.  The solver stream waits for the copy only before it first overwrites what the
+// copy reads (p and p-half at the end of the next step; the velocity buffers are not reused before that), so the download
+// of step n overlaps the compute of step n + 1.
+struct StateView {
+  double *v = nullptr, *U[3] = {nullptr, nullptr, nullptr}, *p = nullptr, *phalf = nullptr;
+  bool    pending = false; // a copy is in flight on the view stream
+  bool    valid   = false; // the buffers hold (or will hold, once waited for) the state of step_index
+  int     step_index = 0;
+  double  t = 0.;
+#ifndef FLUCA_HOSTEMU
+  cudaStream_t stream = nullptr;
+  cudaEvent_t  ready = nullptr, done = nullptr;
+#endif
+};
+
 struct Solver {
   Exec      ex;
   GeomHost  gh;
@@ -136,6 +153,7 @@ struct Solver {
   double *wp = nullptr, *zp = nullptr;
   int     basis_size = 0;
 
+  StateView view;
   Ibm    ibm; // immersed-boundary markers (empty unless fluca_b200_set_markers was called)
 
   Stats  stats;
@@ -153,6 +171,9 @@ struct Solver {
 // construction
 void solver_setup(Solver &s, int dim, const int n[3], const double *const xf[3], const int bc[6], double rho, double mu, double dt, const Options &opt, Comm *comm, int k0, int nzl);
 void solver_destroy(Solver &s);
+
+// orders the solver stream after a pending view copy; call before anything overwrites the live state
+void view_fence(Solver &s);
 
 // halo helpers
 void halo_cells(Solver &s, const V3 &v);

@@ -126,6 +126,15 @@ void reduce_finish(Solver &s, int n, double *out)
   for (int i = 0; i < n; ++i) out[i] = s.ex.h_result[i];
 }
 
+void view_fence(Solver &s)
+{
+  if (!s.view.pending) return;
+#ifndef FLUCA_HOSTEMU
+  FL_CUDA(cudaStreamWaitEvent(s.ex.stream, s.view.done, 0));
+#endif
+  s.view.pending = false;
+}
+
 // ------------------------------------------------------------------ setup
 void solver_setup(Solver &s, int dim, const int n[3], const double *const xf[3], const int bcin[6], double rho, double mu, double dt, const Options &opt, Comm *comm, int k0, int nzl)
 {
@@ -195,6 +204,17 @@ void solver_destroy(Solver &s)
 {
   s.ex.sync();
   ibm_destroy(s);
+#ifndef FLUCA_HOSTEMU
+  if (s.view.stream) cudaStreamSynchronize(s.view.stream);
+  if (s.view.ready) cudaEventDestroy(s.view.ready);
+  if (s.view.done) cudaEventDestroy(s.view.done);
+  if (s.view.stream) cudaStreamDestroy(s.view.stream);
+  for (double *hp : {s.view.v, s.view.U[0], s.view.U[1], s.view.U[2], s.view.p, s.view.phalf})
+    if (hp) cudaFreeHost(hp);
+#else
+  for (double *hp : {s.view.v, s.view.U[0], s.view.U[1], s.view.U[2], s.view.p, s.view.phalf}) free(hp);
+#endif
+  s.view = StateView();
 #ifndef FLUCA_HOSTEMU
   for (double *p : s.pool) tensor_map_forget(p); // the cache is keyed by address: a later solver may get the same one
   for (void *p : s.mg_owned) tensor_map_forget((const double *)p);
@@ -874,6 +894,7 @@ int do_step(Solver &s, double t, int step_index)
     rc = outer_gmres(s);
   }
   // sol <- x ; pressure extrapolation (cnlinearcart3d.c:2843-2854)
+  view_fence(s); // a view of the previous state may still be reading p and p-half (its velocity buffers are not written by this step)
   {
     V3 tv = s.v, tU = s.U;
     s.v = s.xv, s.U = s.xU;

@@ -174,6 +174,23 @@ class Solver:
         _lib.check(self.L, self.L.fluca_b200_get_state(self._h, v.ctypes.data, self._ptrs(U), p.ctypes.data, ph.ctypes.data))
         return dict(v=v, U=U, p=p, phalf=ph)
 
+    def stage_state(self):
+        """Enqueue an asynchronous device -> pinned-host copy of the current state (returns at once)."""
+        _lib.check(self.L, self.L.fluca_b200_stage_state(self._h))
+
+    def staged_state(self, copy: bool = True):
+        """Wait for the staged copy; dict like get_state().  copy=False returns views of the library's pinned buffers
+        (valid until the next stage_state)."""
+        v, p, ph = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        U = (C.c_void_p * 3)()
+        _lib.check(self.L, self.L.fluca_b200_staged_state(self._h, C.byref(v), U, C.byref(p), C.byref(ph)))
+
+        def arr(ptr, shape):
+            a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=shape)
+            return a.copy() if copy else a
+
+        return dict(v=arr(v, (self.dim,) + self.cell_shape), U=[arr(U[d], self.face_shape[d]) for d in range(self.dim)], p=arr(p, self.cell_shape), phalf=arr(ph, self.cell_shape))
+
     def set_boundary_velocity(self, b, slot, values):
         a = np.ascontiguousarray(values, dtype=np.float64).reshape((self.dim,) + self.bc_shape[b])
         _lib.check(self.L, self.L.fluca_b200_set_boundary_velocity(self._h, b, slot, a.ctypes.data))

@@ -116,6 +116,16 @@ int fluca_b200_set_abf_ainv_types(fluca_b200_solver *s, int schur_type, int uppe
 int fluca_b200_set_state(fluca_b200_solver *s, const double *v, const double *const U[3], const double *p, const double *phalf);
 int fluca_b200_get_state(fluca_b200_solver *s, double *v, double *const U[3], double *p, double *phalf);
 
+/* ---- asynchronous solution views: what a monitor, NSViewSolution or the CGNS writer needs (NSViewSolution nssol.c:130-174,
+ * VecView_Cart cartvec.c:4-25) without stalling the time loop.
+ * stage_state  enqueues a copy of the current state into library-owned PINNED host buffers on a second CUDA stream, ordered
+ *              after the work already submitted, and returns at once.  Steps issued afterwards run concurrently with the
+ *              copy: the solver orders only its next overwrite of the copied fields after it.
+ * staged_state blocks the HOST until that copy is complete and returns the buffers (compact layout of get_state; U[d] is
+ *              NULL for d >= dim).  They stay valid, and unchanged, until the next stage_state or destroy. */
+int fluca_b200_stage_state(fluca_b200_solver *s);
+int fluca_b200_staged_state(fluca_b200_solver *s, const double **v, const double *U[3], const double **p, const double **phalf);
+
 /* ---- boundary data: values of ns->bcs[b].velocity / .pressure (flucansbc.h:14) evaluated by the host at the
  * boundary-face centres of this rank's slab: x boundaries [nzl][ny], y boundaries [nzl][nx], z boundaries [ny][nx];
  * velocity: dim consecutive component blocks.
