@@ -625,5 +625,26 @@ def PCABFSetUpperTriangularAinvType(ns: NS, type_: int):
     s.set_abf_ainv_types(s.ainv_types[0], int(type_))
 
 
+def NSB200StageSolution(ns: NS):
+    """Start an asynchronous download of the current state into pinned host memory; the time loop may go on
+    (glue/nsb200.c NSB200StageSolution; fluca_b200_stage_state)."""
+    if not ns.setupcalled:
+        raise FlucaError("This function must be called after NSSetUp()")
+    ns.data.solver.stage_state()
+    ns.data.staged_step = (ns.step, ns.t)
+
+
+def NSB200SyncSolution(ns: NS):
+    """Wait for the staged download; returns ({field name: array}, (step, t)) of the staged state -- what the C glue
+    unpacks into ns->sol before NSViewSolution."""
+    if not ns.setupcalled:
+        raise FlucaError("This function must be called after NSSetUp()")
+    if getattr(ns.data, "staged_step", None) is None:
+        NSB200StageSolution(ns)
+    st = ns.data.solver.staged_state()
+    tag, ns.data.staged_step = ns.data.staged_step, None
+    return {NS_FIELD_VELOCITY: st["v"], NS_FIELD_FACE_NORMAL_VELOCITY: st["U"], NS_FIELD_PRESSURE: st["p"], "PressureHalfStep": st["phalf"]}, tag
+
+
 def NSB200GetStats(ns: NS):
     return ns.data.last_stats

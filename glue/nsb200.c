@@ -43,6 +43,7 @@ typedef struct {
   /* coherence between ns->sol (host) and the device state */
   PetscObjectState solstate;
   PetscBool        device_current, host_current;
+  PetscBool        staged;        /* fluca_b200_stage_state is in flight or complete and not yet unpacked into ns->sol */
   fluca_b200_stats stats;
 } NS_B200;
 
@@ -154,11 +155,14 @@ static PetscErrorCode B200DeviceToHost_Private(NS ns)
   Vec      v, V, p;
   PetscInt d;
 
+  const double *hv, *hU[3], *hp, *hph;
+
   PetscFunctionBegin;
-  {
-    double *U[3] = {b->hU[0], b->hU[1], b->hU[2]};
-    B200Call(ns, fluca_b200_get_state(b->solver, b->hv, U, b->hp, b->hph));
-  }
+  /* the library's own pinned buffers (fluca_b200_stage_state): full-rate DMA and no second host copy.  If the user staged
+     the state earlier (NSB200StageSolution) the copy has been running behind the steps issued since. */
+  if (!b->staged) B200Call(ns, fluca_b200_stage_state(b->solver));
+  B200Call(ns, fluca_b200_staged_state(b->solver, &hv, hU, &hp, &hph));
+  b->staged = PETSC_FALSE;
   PetscCall(MeshGetDM(ns->mesh, MESH_DM_SCALAR, &sdm));
   PetscCall(MeshGetDM(ns->mesh, MESH_DM_VECTOR, &vdm));
   PetscCall(MeshGetDM(ns->mesh, MESH_DM_STAG_SCALAR, &Sdm));
@@ -169,10 +173,10 @@ static PetscErrorCode B200DeviceToHost_Private(NS ns)
   PetscCall(VecZeroEntries(V));
   PetscCall(VecZeroEntries(p));
   PetscCall(VecZeroEntries(b->phalf));
-  for (d = 0; d < b->dim; ++d) PetscCall(B200Download_Private(vdm, v, DMSTAG_ELEMENT, d, 0, 0, 0, b->hv + b->ncell * d));
-  for (d = 0; d < b->dim; ++d) PetscCall(B200Download_Private(Sdm, V, B200FaceLoc[d], 0, d == 0 && !b->per[0], d == 1 && !b->per[1], d == 2 && b->lastz, b->hU[d]));
-  PetscCall(B200Download_Private(sdm, p, DMSTAG_ELEMENT, 0, 0, 0, 0, b->hp));
-  PetscCall(B200Download_Private(sdm, b->phalf, DMSTAG_ELEMENT, 0, 0, 0, 0, b->hph));
+  for (d = 0; d < b->dim; ++d) PetscCall(B200Download_Private(vdm, v, DMSTAG_ELEMENT, d, 0, 0, 0, hv + b->ncell * d));
+  for (d = 0; d < b->dim; ++d) PetscCall(B200Download_Private(Sdm, V, B200FaceLoc[d], 0, d == 0 && !b->per[0], d == 1 && !b->per[1], d == 2 && b->lastz, hU[d]));
+  PetscCall(B200Download_Private(sdm, p, DMSTAG_ELEMENT, 0, 0, 0, 0, hp));
+  PetscCall(B200Download_Private(sdm, b->phalf, DMSTAG_ELEMENT, 0, 0, 0, 0, hph));
   PetscCall(NSRestoreSolutionSubVector(ns, NS_FIELD_VELOCITY, &v));
   PetscCall(NSRestoreSolutionSubVector(ns, NS_FIELD_FACE_NORMAL_VELOCITY, &V));
   PetscCall(NSRestoreSolutionSubVector(ns, NS_FIELD_PRESSURE, &p));
@@ -552,6 +556,34 @@ PetscErrorCode NSB200SetMarkers(NS ns, PetscInt n, const PetscReal X[], const Pe
   PetscCheck(ns->setupcalled, PetscObjectComm((PetscObject)ns), PETSC_ERR_ARG_WRONGSTATE, "This function must be called after NSSetUp()");
   b = (NS_B200 *)ns->data;
   B200Call(ns, fluca_b200_set_markers(b->solver, (long)n, X, Ud, dV, (int)delta_points));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+/* Asynchronous output for runs with -ns_b200_sync_interval 0.  NSViewSolution views ns->sol BEFORE it calls the
+ * type's hook (nssol.c:143-149), so a device-authoritative type cannot refresh lazily from inside it; an application that
+ * knows its output cadence instead brackets the steps it wants to overlap:
+ *     NSStep(ns); NSB200StageSolution(ns);     -- state n starts flowing to pinned host memory on its own stream
+ *     NSStep(ns); ...                           -- the time loop continues on the device
+ *     NSB200SyncSolution(ns); NSViewSolution(ns, viewer);   -- ns->sol (+ p-half) = state n, then written as usual */
+PetscErrorCode NSB200StageSolution(NS ns)
+{
+  NS_B200 *b = (NS_B200 *)ns->data;
+
+  PetscFunctionBegin;
+  PetscCheck(ns->setupcalled && b->solver, PetscObjectComm((PetscObject)ns), PETSC_ERR_ARG_WRONGSTATE, "This function must be called after NSSetUp()");
+  B200Call(ns, fluca_b200_stage_state(b->solver));
+  b->staged = PETSC_TRUE;
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+PetscErrorCode NSB200SyncSolution(NS ns)
+{
+  NS_B200 *b = (NS_B200 *)ns->data;
+
+  PetscFunctionBegin;
+  PetscCheck(ns->setupcalled && b->solver, PetscObjectComm((PetscObject)ns), PETSC_ERR_ARG_WRONGSTATE, "This function must be called after NSSetUp()");
+  PetscCall(B200DeviceToHost_Private(ns)); /* waits for the staged copy (or stages now) and unpacks through DMStag */
+  /* ns->sol may now be older than the device state: the next NSStep must not mistake it for a user edit */
   PetscFunctionReturn(PETSC_SUCCESS);
 }
 

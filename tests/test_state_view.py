@@ -50,6 +50,25 @@ def test_staged_view_host_emulation(name, mk, mode, between):
     _check(parity.hostemu_library(), mk(), mode, between)
 
 
+def test_ns_api_stage_and_sync():
+    """The application-level pair of glue/nsb200.c: stage after step n, keep stepping, sync before the viewer runs."""
+    case = cases.cavity2d(n=12)
+    ns = parity.make_ns(case, parity.hostemu_library(), "fractional")
+    parity.set_initial(ns, case.initial_state())
+    fb.NSStep(ns)
+    want = {k: fb.NSGetSolutionSubVector(ns, k) for k in (fb.NS_FIELD_VELOCITY, fb.NS_FIELD_PRESSURE)}
+    fb.NSB200StageSolution(ns)
+    step_staged = fb.NSGetTimeStep(ns)
+    fb.NSStep(ns)
+    fb.NSStep(ns)
+    got, (step, t) = fb.NSB200SyncSolution(ns)
+    assert step == step_staged and np.array_equal(got[fb.NS_FIELD_VELOCITY], want[fb.NS_FIELD_VELOCITY]) and np.array_equal(got[fb.NS_FIELD_PRESSURE], want[fb.NS_FIELD_PRESSURE])
+    # without an earlier staging the sync stages the current state itself
+    got, (step, t) = fb.NSB200SyncSolution(ns)
+    assert step == fb.NSGetTimeStep(ns) and np.array_equal(got[fb.NS_FIELD_VELOCITY], fb.NSGetSolutionSubVector(ns, fb.NS_FIELD_VELOCITY))
+    fb.NSDestroy(ns)
+
+
 GPU_CASES = [
     ("cavity2d_64", lambda: cases.cavity2d(n=64), "coupled", 2),
     # large enough for the copy (7 fields of 2.4 MB) to still be in flight when the next steps start
