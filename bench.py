@@ -145,6 +145,23 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
+def poisson_solve_rate(ktimes, schur_its, cells_rank, outlet, variant, peak):
+    """Algorithmic HBM rate of the pressure solves of the timed region: iterations x bytes per iteration and cell (3-D: PCG +
+    V(2,2) cycle = 227 B; BiCGStab with a pressure outlet or a DIAG / ROWSUM Schur complement = two applies + two V-cycles,
+    2 x 227 resp. 2 x (227 - 16 + 104) B -- the model of fluca_b200_step_model_bytes) over the event-timed duration of the
+    four kernel classes that make up the solve.  None if nothing was timed."""
+    try:
+        t_ms = sum(float(ktimes[k][0]) for k in ("poisson_apply", "poisson_vec", "mg_smooth", "mg_transfer") if k in ktimes)
+        its = int(sum(schur_its))
+        if t_ms <= 0.0 or its <= 0:
+            return None
+        per_iter = 2.0 * (227.0 - 16.0 + 104.0) if variant else (2.0 * 227.0 if outlet else 227.0)
+        ach = its * per_iter * cells_rank / (t_ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "iterations": its, "bytes_per_iteration_per_cell": per_iter, "ms": t_ms, "krylov": "bicgstab+mg" if (variant or outlet) else "pcg+mg"}
+    except Exception:  # a reporting extra must never cost the bench line
+        return None
+
+
 def cpu_sample(args, n, steps, warmup, mode, threads):
     """The CPU restatement of the reference algorithm (oracle, kind "port": assembled CSR operators,
     GMRES(30) + block-Jacobi ILU(0), reference default tolerances) on an n^3 sample of the workload, all host threads."""
@@ -317,6 +334,8 @@ def run_b200(args):
                 roof = dict(r, _t=t)
     if roof:
         roof.pop("_t")
+    # second half of BASELINE.json's metric, "Poisson solve HBM GB/s vs peak" (SURVEY.md 8d): n_cg x 227 B x cells / t_poisson
+    poisson = poisson_solve_rate(ktimes, [st.schur_its for st in stats], cells_rank, outlet=(args.workload == "sphere"), variant=(args.schur_ainv != "ID"), peak=peak)
     # whole-step model: algorithmic bytes of all kernels / elapsed
     model_bytes = sum(s.model_bytes(st) for st in stats)
     step_ach = model_bytes / (ms * 1e-3) / 1e9
@@ -342,6 +361,7 @@ def run_b200(args):
             "iterations_per_step": {"outer": [st.outer_its for st in stats], "momentum": [st.mom_its for st in stats], "schur": [st.schur_its for st in stats], "abf": [st.abf_applies for st in stats]},
         },
         "roofline": roof,
+        "poisson_solve": poisson,
         "step_roofline": {"algorithmic_GB_per_step": model_bytes / args.steps / 1e9, "achieved": step_ach * world, "peak": peak * world, "unit": "GB/s", "frac": step_ach / peak, "peak_source": peak_src},
         "kernel_shares": {k: round(v, 4) for k, v in shares.items()},
         "gpu_launches": int(launches),

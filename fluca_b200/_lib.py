@@ -158,10 +158,8 @@ def _prototype(L):
     L.fluca_b200_set_abf_ainv_types.argtypes = [_P, C.c_int, C.c_int]
     L.fluca_b200_stage_state.argtypes = [_P]
     L.fluca_b200_staged_state.argtypes = [_P, C.POINTER(_P), _PD3, C.POINTER(_P), C.POINTER(_P)]
-    for name in SYMBOLS:
-        fn = getattr(L, name)
-        if fn.restype is C.c_int and name not in ("fluca_b200_is_host_emulation",):
-            pass
+    for name in SYMBOLS:  # every declared symbol must resolve (a stale .so fails here, not at first use)
+        getattr(L, name)
     return L
 
 

@@ -511,8 +511,10 @@ extern "C" double fluca_b200_step_model_bytes(fluca_b200_solver *h, const fluca_
   const bool    d3  = (s.dim == 3);
   const double  rhs = d3 ? 56 : 40, bicg = d3 ? 552 : 368, prhs = d3 ? 32 : 24, pcg = d3 ? 227 : 251, proj = d3 ? 104 : 80;
   const double  coup = d3 ? 176 : 128, vec7 = d3 ? 56 : 40;
-  // with a pressure outlet the pressure Krylov method is BiCGStab: two applies + two V-cycles per iteration
-  const double  piter = s.has_outlet ? 2. * pcg : pcg;
+  // with a pressure outlet the pressure Krylov method is BiCGStab: two applies + two V-cycles per iteration; the DIAG /
+  // ROWSUM Schur complement is BiCGStab too and its apply is the two-launch form (3-D: 56 + 48 B instead of 16)
+  const double  papply = s.opt.schur_ainv != 0 ? (d3 ? 104. : 80.) : 16.;
+  const double  piter  = (s.has_outlet || s.opt.schur_ainv != 0) ? 2. * (pcg - 16. + papply) : pcg;
   double        B = rhs + st->abf_applies * (prhs + proj) + st->mom_its * bicg + st->schur_its * piter;
   if (s.opt.mode == 0)
     for (int k = 0; k < st->outer_its; ++k) B += coup + (2. * (k % s.opt.outer_restart) + 3.) * vec7;

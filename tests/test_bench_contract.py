@@ -36,3 +36,19 @@ def test_workload_builders_match_the_baseline_configs():
     assert np.isclose(c2.faces()[2][-1], 24.0)
     k = bench.cavity_case(256, 256)  # config 3
     assert np.isclose(k.mu, 1.0 / 400.0) and np.isclose(k.dt, 0.5 / 256.0)
+
+
+def test_poisson_solve_rate_is_the_second_half_of_the_baseline_metric():
+    """'Poisson solve HBM GB/s vs peak' = iterations x bytes per iteration and cell x cells / event-timed solve time."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    kt = {"poisson_apply": (2.0, 10), "poisson_vec": (3.0, 30), "mg_smooth": (4.0, 100), "mg_transfer": (1.0, 50), "momentum_apply": (99.0, 5)}
+    r = bench.poisson_solve_rate(kt, [5, 5], 1.0e6, outlet=False, variant=False, peak=6530.3)
+    assert np.isclose(r["achieved"], 10 * 227.0 * 1.0e6 / 10.0e-3 / 1e9) and np.isclose(r["frac"], r["achieved"] / 6530.3) and r["krylov"] == "pcg+mg"
+    assert bench.poisson_solve_rate(kt, [5, 5], 1.0e6, outlet=True, variant=False, peak=1.0)["bytes_per_iteration_per_cell"] == 454.0
+    assert bench.poisson_solve_rate(kt, [5, 5], 1.0e6, outlet=False, variant=True, peak=1.0)["bytes_per_iteration_per_cell"] == 630.0
+    # never raises, never divides by zero: a reporting extra must not cost the bench line
+    assert bench.poisson_solve_rate({}, [5], 1.0e6, False, False, 1.0) is None
+    assert bench.poisson_solve_rate(kt, [], 1.0e6, False, False, 1.0) is None
+    assert bench.poisson_solve_rate(None, None, None, False, False, 0.0) is None
