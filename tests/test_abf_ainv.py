@@ -172,6 +172,14 @@ def test_hostlogic_types_can_change_between_steps_and_bad_types_are_rejected(emu
         parity.make_ns(case, emu, "fractional", ns_pc_abf_schur_ainv_type="LUMPED")
 
 
+@pytest.mark.parametrize("mode", ["fractional", "coupled"])
+def test_hostlogic_immersed_boundary_under_variant_factors(emu, mode):
+    """The direct-forcing term is a right-hand-side term: it composes with any ABF variant."""
+    case = cases.channel3d(n=(12, 8, 8), pout=0.1, dt=0.05)
+    mk = cases.sphere_markers((0.1, 0.0, 0.05), 1.2, 60, 0.5)
+    parity.compare_steps(case, emu, mode, nsteps=2, seed=31, markers=mk, ainv=(DIAG, DIAG))
+
+
 # ------------------------------------------------------------------ CUDA product library
 @pytest.fixture(scope="module")
 def lib():
