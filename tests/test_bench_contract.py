@@ -52,3 +52,26 @@ def test_poisson_solve_rate_is_the_second_half_of_the_baseline_metric():
     assert bench.poisson_solve_rate({}, [5], 1.0e6, False, False, 1.0) is None
     assert bench.poisson_solve_rate(kt, [], 1.0e6, False, False, 1.0) is None
     assert bench.poisson_solve_rate(None, None, None, False, False, 0.0) is None
+
+
+def test_resident_e2e_loop_reads_every_step_result():
+    """bench.py's e2e_resident loop (the glue's time loop with staged downloads), run here on the host-emulation double."""
+    sys.path.insert(0, ROOT)
+    import time
+
+    import bench
+    import fluca_b200 as fb
+    from tests import cases, parity
+
+    case = cases.cavity3d(n=(8, 8, 4))
+    ns = parity.make_ns(case, parity.hostemu_library(), "fractional")
+    parity.set_initial(ns, case.initial_state(seed=2))
+    s = fb.NSB200GetSolver(ns)
+    step0 = fb.NSGetTimeStep(ns)
+    seconds, nbytes, acc = bench.e2e_resident_loop(ns, s, 3, lambda: None, time.perf_counter)
+    assert fb.NSGetTimeStep(ns) == step0 + 3 and seconds > 0 and np.isfinite(acc)
+    st = s.get_state()
+    assert nbytes == st["v"].nbytes + st["p"].nbytes + st["phalf"].nbytes + sum(u.nbytes for u in st["U"])
+    last = s.staged_state()  # the drained copy is the final state
+    assert np.array_equal(last["v"], st["v"]) and np.array_equal(last["p"], st["p"])
+    fb.NSDestroy(ns)
