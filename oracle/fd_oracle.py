@@ -372,6 +372,62 @@ class Sum(FD):
         return st
 
 
+class Scale(FD):
+    """FLUCAFDSCALE, scale.c:18-93: the operand's stencil times a constant or times a field sampled at the output point"""
+
+    def __init__(self, operand: FD, constant: Optional[float] = None, vector=None, vec_loc: Optional[str] = None, vec_c: int = 0):
+        super().__init__(operand.grid, operand.output_loc, operand.output_c, operand.output_loc, operand.output_c)
+        self.operand, self.constant, self.vector = operand, constant, vector
+        self.vec_loc, self.vec_c = (vec_loc if vec_loc is not None else operand.output_loc), vec_c
+        if (constant is None) == (vector is None):
+            raise ValueError("exactly one of constant / vector")
+        self.terms = [t.copy() for t in operand.terms]
+
+    def check(self):
+        """the consistency checks of FlucaFDSetUp_Scale (scale.c:24-30), after options may have changed the locations"""
+        if not (self.operand.output_c == self.input_c == self.output_c and self.operand.output_loc == self.input_loc == self.output_loc):
+            raise ValueError("Cannot change component / location")
+        if self.vector is not None and self.operand.output_loc != self.vec_loc:
+            raise ValueError("Operand and vector must have the same location")
+        return self
+
+    def _raw(self, i, j, k):
+        s = self.constant if self.constant is not None else self.vector(i, j, k, self.vec_loc, self.vec_c)
+        return [(c, v * s) for c, v in self.operand.stencil_raw(i, j, k)]
+
+
+class Composition(FD):
+    """FLUCAFDCOMPOSITION, composition.c:3-76: outer(inner(.)); terms multiply (orders add, accuracies take the minimum)"""
+
+    def __init__(self, inner: FD, outer: FD):
+        super().__init__(inner.grid, inner.input_loc, inner.input_c, outer.output_loc, outer.output_c)
+        if inner.output_c != outer.input_c or inner.output_loc != outer.input_loc:
+            raise ValueError("Inner output must match outer input")
+        self.inner, self.outer = inner, outer
+        for ot in outer.terms:
+            for it in inner.terms:
+                t = Term(input_loc=it.input_loc, input_c=it.input_c)
+                for d in range(3):
+                    if it.deriv_order[d] == -1:
+                        t.deriv_order[d] = ot.deriv_order[d]
+                    elif ot.deriv_order[d] == -1:
+                        t.deriv_order[d] = it.deriv_order[d]
+                    else:
+                        t.deriv_order[d] = it.deriv_order[d] + ot.deriv_order[d]
+                    t.accu_order[d] = min(it.accu_order[d], ot.accu_order[d])
+                _merge_terms(self.terms, [t])
+
+    def _raw(self, i, j, k):
+        st = []
+        for oc, ov in self.outer.stencil_raw(i, j, k):
+            if oc.c < 0:  # constant or boundary marker of the outer operator passes through
+                add_point(st, oc, ov)
+                continue
+            for ic, iv in self.inner.stencil_raw(oc.i, oc.j, oc.k):
+                add_point(st, ic, ov * iv)
+        return st
+
+
 # ------------------------------------------------------------------ printing as the reference's tests do (fdtest.h, ex*.c)
 def sort_key(item):
     """CompareDMStagStencil, fdtest.h:9-36: boundary markers last, then component, location, i, j, k"""

@@ -73,7 +73,31 @@ def run_ex2(o):
     return [f"Sum stencil at (i,j,k)=({idx[0]},{idx[1]},{idx[2]}):"] + F.print_stencil(s.stencil(*idx), 3)
 
 
-RUNNERS = {"ex1": run_ex1, "ex2": run_ex2}
+def run_ex3(o):
+    """fluca/tests/fd/ex3.c:22-72: 1-D derivative scaled by a constant (default 1, -scale_flucafd_constant) or by the field of
+    FillScaleVector (ex3.c:75-95): 2 i at the LEFT points, 2 i + 1 at the element centres"""
+    g = grid_from(o, 1)
+    deriv = fd_options(derivative(g, o, "deriv_", 0), o, "deriv_")
+    if o.get("const", "true") == "true":
+        sc = F.Scale(deriv, constant=float(o.get("scale_flucafd_constant", 1.0)))
+    else:
+        sc = F.Scale(deriv, vector=lambda i, j, k, loc, c: float(2 * i if loc == "left" else 2 * i + 1), vec_loc=o.get("scale_flucafd_vec_loc", deriv.output_loc))
+    fd_options(sc, o, "scale_").check()
+    i = int(o.get("i", g.N[0] // 2))
+    return [f"Scaled stencil at i={i}:"] + F.print_stencil(sc.stencil(i, 0, 0), 1)
+
+
+def run_ex4(o):
+    """fluca/tests/fd/ex4.c:20-75: 2-D 8 x 8 on the unit square, outer(inner(.)) of two derivative operators"""
+    g = grid_from(o, 2)
+    inner = fd_options(derivative(g, o, "inner_", 0), o, "inner_")
+    outer = fd_options(derivative(g, o, "outer_", 0), o, "outer_")
+    comp = fd_options(F.Composition(inner, outer), o, "comp_")
+    idx = [int(o.get(a, g.N[d] // 2)) for d, a in enumerate("ij")]
+    return [f"Sum stencil at (i,j)=({idx[0]},{idx[1]}):"]  # sic: ex4.c prints the header of ex2 + F.print_stencil(comp.stencil(idx[0], idx[1], 0), 2)
+
+
+RUNNERS = {"ex1": run_ex1, "ex2": run_ex2, "ex3": run_ex3, "ex4": run_ex4}
 NAMES = sorted(k for k, v in GOLD.items() if v["program"] in RUNNERS)
 
 
