@@ -94,7 +94,8 @@ def run_ex4(o):
     outer = fd_options(derivative(g, o, "outer_", 0), o, "outer_")
     comp = fd_options(F.Composition(inner, outer), o, "comp_")
     idx = [int(o.get(a, g.N[d] // 2)) for d, a in enumerate("ij")]
-    return [f"Sum stencil at (i,j)=({idx[0]},{idx[1]}):"]  # sic: ex4.c prints the header of ex2 + F.print_stencil(comp.stencil(idx[0], idx[1], 0), 2)
+    header = f"Sum stencil at (i,j)=({idx[0]},{idx[1]}):"  # sic: ex4.c prints the header of ex2
+    return [header] + F.print_stencil(comp.stencil(idx[0], idx[1], 0), 2)
 
 
 RUNNERS = {"ex1": run_ex1, "ex2": run_ex2, "ex3": run_ex3, "ex4": run_ex4}
