@@ -428,6 +428,92 @@ class Composition(FD):
         return st
 
 
+# flux limiters psi(r), secondordertvdlimiter.c:3-82 (registered names: secondordertvd.c:19-36)
+LIMITERS = {
+    "superbee": lambda r: max(0.0, max(min(2.0 * r, 1.0), min(r, 2.0))),
+    "minmod": lambda r: max(0.0, min(r, 1.0)),
+    "mc": lambda r: max(0.0, min(min(2.0 * r, (1.0 + r) / 2.0), 2.0)),
+    "vanleer": lambda r: (r + abs(r)) / (1.0 + abs(r)),
+    "vanalbada": lambda r: 0.0 if r <= 0.0 else (r * r + r) / (r * r + 1.0),
+    "barthjesperson": lambda r: 0.0 if r <= 0.0 else (1.0 + r) / 2.0 * min(1.0, min(4.0 * r / (1.0 + r), 4.0 / (1.0 + r))),
+    "venkatakrishnan": lambda r: 0.0 if r <= 0.0 else (1.0 + r) / 2.0 * min(4.0 * r * (3.0 * r + 1.0) / (11.0 * r * r + 4.0 * r + 1.0), 4.0 * (r + 3.0) / (r * r + 4.0 * r + 11.0)),
+    "koren": lambda r: max(0.0, min(min(2.0 * r, (1.0 + 2.0 * r) / 3.0), 2.0)),
+    "upwind": lambda r: 0.0,
+    "sou": lambda r: r,
+    "quick": lambda r: (3.0 + r) / 4.0,
+}
+
+
+class SecondOrderTVD(FD):
+    """FLUCAFDSECONDORDERTVD, secondordertvd.c:53-356: element values -> face value, upwind plus a limited correction that
+    enters the stencil as a CONSTANT term evaluated on the current solution (deferred correction).
+    velocity(i, j, k): advecting velocity at the face; phi(i, j, k): current solution at element centres (the reference reads
+    its ghosted local array there; beyond a non-periodic end that array holds 0, as the stored outputs show)."""
+
+    def __init__(self, grid, direction: int, input_c=0, output_c=0, limiter="superbee", velocity=None, phi=None):
+        super().__init__(grid, "element", input_c, ("left", "down", "back")[direction], output_c)
+        self.dir, self.limiter, self.velocity, self.phi = direction, LIMITERS[limiter], velocity, phi
+        t = Term(input_loc="element", input_c=input_c)
+        t.deriv_order[direction], t.accu_order[direction] = 0, 2  # interpolation, second order (:131-139)
+        self.terms = [t]
+        self._grad = None
+
+    def _alpha(self, idx):
+        """alpha_plus, alpha_minus of face idx (:86-128): the face's position between the two centres it separates"""
+        g, d = self.grid, self.dir
+        if (idx == 0 or idx == g.N[d]) and not g.periodic[d]:
+            return 0.5, 0.5
+        xf, xl, xr = g.array_coord(d, idx, True), g.array_coord(d, idx - 1, False), g.array_coord(d, idx, False)
+        dx = xr - xl
+        return ((xf - xl) / dx, (xr - xf) / dx) if abs(dx) > 1e-14 else (0.5, 0.5)
+
+    def _phi(self, i, j, k):
+        g = self.grid
+        for d, idx in enumerate((i, j, k)[: g.dim]):
+            gxs, gxm, _ = g.ghost_corners(d, False)
+            if not gxs <= idx < gxs + gxm:
+                return 0.0
+        return self.phi(i, j, k)
+
+    def _face_gradient(self, i, j, k):
+        """ComputeFaceCenteredGradient_Private, :150-185: d phi / dx at a face from the first-order element -> face
+        derivative with this operator's boundary condition types (fixed at set-up, :76-78) and current boundary values"""
+        if self._grad is None:
+            self._grad = Derivative(self.grid, self.dir, 1, 1, "element", self.input_c, self.output_loc, 0)
+            self._grad.bcs = list(self.bcs)
+        s = 0.0
+        for col, v in self._grad.stencil(i, j, k):
+            s += v * (self._phi(col.i, col.j, col.k) if col.c >= 0 else self.bcs[-col.c - 1][1])
+        return s
+
+    def _raw(self, i, j, k):
+        g, d = self.grid, self.dir
+        p = [i, j, k]
+        idx = p[d]
+        lo = list(p)
+        lo[d] -= 1
+        up = list(p)
+        up[d] += 1
+        vel = self.velocity(i, j, k)
+        here, below = Col(p[0], p[1], p[2], "element", self.input_c), Col(lo[0], lo[1], lo[2], "element", self.input_c)
+        at_prev = idx == 0 and not g.periodic[d]
+        at_next = idx == g.N[d] and not g.periodic[d]
+        const = Col(0, 0, 0, "element", CONSTANT)
+        if vel > 0:  # upwind element is the one below the face
+            if at_prev:
+                return [(below, 0.5), (here, 0.5)]
+            alpha = self._alpha(idx)[0]
+            gfu, gfc = self._face_gradient(*lo), self._face_gradient(*p)
+            psi = self.limiter(gfu / gfc if abs(gfc) > 1e-30 else 1.0)
+            return [(below, 1.0), (const, alpha * psi * (self._phi(*p) - self._phi(*lo)))]
+        if at_next:
+            return [(here, 0.5), (below, 0.5)]
+        alpha = self._alpha(idx)[1]
+        gfu, gfc = self._face_gradient(*up), self._face_gradient(*p)
+        psi = self.limiter(gfu / gfc if abs(gfc) > 1e-30 else 1.0)
+        return [(here, 1.0), (const, alpha * psi * (self._phi(*lo) - self._phi(*p)))]
+
+
 # ------------------------------------------------------------------ printing as the reference's tests do (fdtest.h, ex*.c)
 def sort_key(item):
     """CompareDMStagStencil, fdtest.h:9-36: boundary markers last, then component, location, i, j, k"""
@@ -446,6 +532,9 @@ def fmt_g(v: float) -> str:
 def print_stencil(st, dim: int) -> List[str]:
     out = [f"  ncols = {len(st)}"]
     for n, (col, v) in enumerate(sorted(st, key=sort_key)):
+        if col.c == CONSTANT:  # ex7.c prints the deferred-correction term without a position
+            out.append(f"  col[{n}]: constant, v={fmt_g(v)}")
+            continue
         where = f"i={col.i}" if dim == 1 else (f"i={col.i}, j={col.j}" if dim == 2 else f"i={col.i}, j={col.j}, k={col.k}")
         comp = f"{BOUNDARY_NAMES[-col.c - 1]}_boundary" if -6 <= col.c < 0 else ("constant" if col.c == CONSTANT else str(col.c))
         out.append(f"  col[{n}]: {where}, loc={col.loc.upper()}, c={comp}, v={fmt_g(v)}")
