@@ -6,3 +6,4 @@ ns.py   host-side mirror of the reference's NS / MeshCart API for this path (typ
 from . import _lib  # noqa: F401
 from .solver import Comm, Solver, slab_partition  # noqa: F401
 from .ns import *  # noqa: F401,F403
+from . import fd  # noqa: F401

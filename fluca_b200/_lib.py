@@ -108,7 +108,31 @@ SYMBOLS = [
     "fluca_b200_set_abf_ainv_types",
     "fluca_b200_stage_state",
     "fluca_b200_staged_state",
+    # FlucaFD stencil layer (host-side; csrc/fd.cu)
+    "fluca_b200_fd_last_error",
+    "fluca_b200_fd_grid_create",
+    "fluca_b200_fd_grid_destroy",
+    "fluca_b200_fd_derivative_create",
+    "fluca_b200_fd_sum_create",
+    "fluca_b200_fd_scale_create_constant",
+    "fluca_b200_fd_scale_create_vector",
+    "fluca_b200_fd_scale_set_vector_location",
+    "fluca_b200_fd_composition_create",
+    "fluca_b200_fd_tvd_create",
+    "fluca_b200_fd_tvd_set_limiter",
+    "fluca_b200_fd_tvd_set_velocity",
+    "fluca_b200_fd_tvd_set_current_solution",
+    "fluca_b200_fd_set_locations",
+    "fluca_b200_fd_set_boundary_condition",
+    "fluca_b200_fd_setup",
+    "fluca_b200_fd_get_stencil",
+    "fluca_b200_fd_destroy",
 ]
+FD_MAX_STENCIL = 32
+
+
+class FDCol(C.Structure):
+    _fields_ = [("i", C.c_int), ("j", C.c_int), ("k", C.c_int), ("loc", C.c_int), ("c", C.c_int)]
 # PCABFAinvType (flucans.h:99-103) and its option strings PCABFAinvTypes[] (abfpc.c)
 AINV_ID, AINV_DIAG, AINV_ROWSUM = 0, 1, 2
 AINV_NAMES = {"id": AINV_ID, "diag": AINV_DIAG, "rowsum": AINV_ROWSUM}
@@ -156,6 +180,24 @@ def _prototype(L):
     L.fluca_b200_ibm_spread.argtypes = [_P, _P, _P]
     L.fluca_b200_set_ibm_iterations.argtypes = [_P, C.c_int]
     L.fluca_b200_set_abf_ainv_types.argtypes = [_P, C.c_int, C.c_int]
+    L.fluca_b200_fd_last_error.restype = C.c_char_p
+    L.fluca_b200_fd_grid_create.argtypes = [C.c_int, C.POINTER(C.c_int), _PD3, _PD3, C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]
+    L.fluca_b200_fd_grid_destroy.argtypes = [_P]
+    L.fluca_b200_fd_derivative_create.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]
+    L.fluca_b200_fd_sum_create.argtypes = [C.c_int, C.POINTER(_P), C.POINTER(_P)]
+    L.fluca_b200_fd_scale_create_constant.argtypes = [_P, C.c_double, C.POINTER(_P)]
+    L.fluca_b200_fd_scale_create_vector.argtypes = [_P, _P, C.c_int, C.c_int, C.POINTER(_P)]
+    L.fluca_b200_fd_scale_set_vector_location.argtypes = [_P, C.c_int, C.c_int]
+    L.fluca_b200_fd_composition_create.argtypes = [_P, _P, C.POINTER(_P)]
+    L.fluca_b200_fd_tvd_create.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]
+    L.fluca_b200_fd_tvd_set_limiter.argtypes = [_P, C.c_char_p]
+    L.fluca_b200_fd_tvd_set_velocity.argtypes = [_P, _P]
+    L.fluca_b200_fd_tvd_set_current_solution.argtypes = [_P, _P]
+    L.fluca_b200_fd_set_locations.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.fluca_b200_fd_set_boundary_condition.argtypes = [_P, C.c_int, C.c_int, C.c_double]
+    L.fluca_b200_fd_setup.argtypes = [_P]
+    L.fluca_b200_fd_get_stencil.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(FDCol), C.POINTER(C.c_double)]
+    L.fluca_b200_fd_destroy.argtypes = [_P]
     L.fluca_b200_stage_state.argtypes = [_P]
     L.fluca_b200_staged_state.argtypes = [_P, C.POINTER(_P), _PD3, C.POINTER(_P), C.POINTER(_P)]
     for name in SYMBOLS:  # every declared symbol must resolve (a stale .so fails here, not at first use)

@@ -1,0 +1,830 @@
+// fd.cu -- stencil layer of the FlucaFD operator family behind the C ABI.
+//
+// Host-side C++ only (no kernels in this file): what the reference computes in FlucaFDSetUp / FlucaFDGetStencil for its
+// five operator types -- the part every matrix-free device apply of a composed operator is generated from.  Restated from
+//   fluca/src/fd/interface/fdapply.c:22-45         FlucaFDGetStencilRaw, FlucaFDGetStencil
+//   fluca/src/fd/utils/fdutils.c:56-100            coordinates beyond the local grid, ghost corners, Gaussian elimination
+//   fluca/src/fd/utils/fdutils.c:102-489           stencil accumulation, off-grid removal per boundary condition, zero removal
+//   fluca/src/fd/impls/{derivative,sum,scale,composition,secondordertvd}/*.c
+// for one rank.  tests/test_fd_stencils.py drives it through the C ABI on the command lines of the reference's own tests
+// (fluca/tests/fd/ex*.c) and compares with their stored outputs, character for character.
+#include "../../include/fluca_b200.h"
+#include "exec.h"
+#include <climits>
+#include <memory>
+
+namespace fluca {
+namespace fd {
+
+static const int    MAXS           = FLUCA_B200_FD_MAX_STENCIL; // FLUCAFD_MAX_STENCIL_SIZE, flucafdimpl.h:8
+static const double ZERO_PIVOT_TOL = 1e-14;                     // flucafdimpl.h:9
+static const double COEFF_ATOL     = 1e-10;                     // flucafdimpl.h:10
+static const double COEFF_RTOL     = 1e-8;                      // flucafdimpl.h:11
+static const int    CONSTANT       = -7;                        // FLUCAFD_CONSTANT, flucafd.h:52
+
+// DMStagStencilLocation values (petscdmstag.h): only ELEMENT, LEFT, DOWN, BACK and their combinations are inputs / outputs
+enum { LOC_BACK_DOWN_LEFT = 1, LOC_BACK_DOWN = 2, LOC_BACK_LEFT = 4, LOC_BACK = 5, LOC_DOWN_LEFT = 10, LOC_DOWN = 11, LOC_LEFT = 13, LOC_ELEMENT = 14 };
+
+static bool valid_location(int loc)
+{
+  switch (loc) { // FlucaFDValidateStencilLocation_Internal, fdutils.c:16-34
+  case LOC_ELEMENT: case LOC_LEFT: case LOC_DOWN: case LOC_BACK: case LOC_DOWN_LEFT: case LOC_BACK_LEFT: case LOC_BACK_DOWN: case LOC_BACK_DOWN_LEFT: return true;
+  default: return false;
+  }
+}
+// bit d set: the location lies on the LEFT (0) / DOWN (1) / BACK (2) face
+static int face_bits(int loc)
+{
+  switch (loc) {
+  case LOC_LEFT: return 1;
+  case LOC_DOWN: return 2;
+  case LOC_BACK: return 4;
+  case LOC_DOWN_LEFT: return 3;
+  case LOC_BACK_LEFT: return 5;
+  case LOC_BACK_DOWN: return 6;
+  case LOC_BACK_DOWN_LEFT: return 7;
+  default: return 0;
+  }
+}
+static int location_of_bits(int b)
+{
+  static const int t[8] = {LOC_ELEMENT, LOC_LEFT, LOC_DOWN, LOC_DOWN_LEFT, LOC_BACK, LOC_BACK_LEFT, LOC_BACK_DOWN, LOC_BACK_DOWN_LEFT};
+  return t[b & 7];
+}
+static bool use_face(int loc, int d) { return (face_bits(loc) >> d) & 1; }                          // fdutils.c:36-54
+static int  boundary_location(int loc, int d) { return location_of_bits(face_bits(loc) | (1 << d)); } // fdutils.c:198-252
+
+// FlucaFDSolveLinearSystem_Internal, fdutils.c:79-100: Gaussian elimination without pivoting (A is n x n, row-major)
+static void solve(int n, double *A, double *b, double *x)
+{
+  for (int k = 0; k < n - 1; ++k) {
+    if (!(std::fabs(A[k * n + k]) > ZERO_PIVOT_TOL)) throw Error(FL_ERR_INTERNAL, "zero pivot during forward elimination");
+    for (int i = k + 1; i < n; ++i) {
+      const double f = A[i * n + k] / A[k * n + k];
+      for (int j = k; j < n; ++j) A[i * n + j] -= f * A[k * n + j];
+      b[i] -= f * b[k];
+    }
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    if (!(std::fabs(A[i * n + i]) > ZERO_PIVOT_TOL)) throw Error(FL_ERR_INTERNAL, "zero pivot during back substitution");
+    double s = 0.;
+    for (int j = i + 1; j < n; ++j) s += A[i * n + j] * x[j];
+    x[i] = (b[i] - s) / A[i * n + i];
+  }
+}
+static double ipow(double h, int r)
+{
+  double p = 1.;
+  for (int q = 0; q < r; ++q) p *= h;
+  return p;
+}
+
+struct Col {
+  int i, j, k, loc, c;
+  int  idx(int d) const { return d == 0 ? i : (d == 1 ? j : k); }
+  void set(int d, int v) { (d == 0 ? i : (d == 1 ? j : k)) = v; }
+  bool operator==(const Col &o) const { return i == o.i && j == o.j && k == o.k && loc == o.loc && c == o.c; }
+};
+struct Stencil {
+  int    n = 0;
+  Col    col[MAXS];
+  double v[MAXS];
+  void add(const Col &c, double w) // FlucaFDAddStencilPoint_Internal, fdutils.c:102-124
+  {
+    for (int q = 0; q < n; ++q)
+      if (col[q] == c) {
+        v[q] += w;
+        return;
+      }
+    if (n >= MAXS) throw Error(FL_ERR_ARG, "Resulting stencil is too large");
+    col[n] = c, v[n] = w, ++n;
+  }
+  void erase(int q)
+  {
+    for (int r = q; r < n - 1; ++r) col[r] = col[r + 1], v[r] = v[r + 1];
+    --n;
+  }
+  void remove_zero() // FlucaFDRemoveZeroStencilPoints_Internal, fdutils.c:465-489
+  {
+    double s = 0.;
+    for (int q = 0; q < n; ++q) s += std::fabs(v[q]);
+    int m = 0;
+    for (int q = 0; q < n; ++q)
+      if (!(std::fabs(v[q]) < COEFF_ATOL || std::fabs(v[q] / s) < COEFF_RTOL)) col[m] = col[q], v[m] = v[q], ++m;
+    n = m;
+  }
+};
+
+struct Term { // FlucaFDTermLink
+  int deriv[3] = {-1, -1, -1}, accu[3] = {INT_MAX, INT_MAX, INT_MAX};
+  int input_loc = LOC_ELEMENT, input_c = 0;
+  bool operator==(const Term &o) const
+  {
+    for (int d = 0; d < 3; ++d)
+      if (deriv[d] != o.deriv[d] || accu[d] != o.accu[d]) return false;
+    return input_loc == o.input_loc && input_c == o.input_c;
+  }
+};
+static void merge_terms(std::vector<Term> &dst, const std::vector<Term> &src)
+{
+  for (const Term &t : src) {
+    bool found = false;
+    for (const Term &u : dst) found = found || (u == t);
+    if (!found) dst.push_back(t);
+  }
+}
+
+// the DMStag facts FlucaFDSetUp reads (fdbasic.c:165-186), one rank: sizes, periodicity, stencil width, product coordinates
+struct Grid {
+  int                 dim = 1, N[3] = {1, 1, 1}, per[3] = {0, 0, 0}, sw = 1;
+  std::vector<double> xf[3], xc[3]; // N + 1 faces, N centres
+  int                 refs = 1;
+  // product coordinate array entry, ghost elements of a periodic direction included (they continue the grid by its period)
+  double array_coord(int d, int idx, bool face) const
+  {
+    const int    n = N[d];
+    const double L = xf[d][n] - xf[d][0];
+    int          w = idx, shift = 0;
+    const int    top = face ? n : n - 1; // last stored index
+    while (w < 0) w += n, --shift;
+    while (w > top) w -= n, ++shift;
+    return (face ? xf[d][w] : xc[d][w]) + shift * L;
+  }
+  void ghost_corners(int d, bool face, int &gxs, int &gxm, int &gxe) const // FlucaFDGetGhostCorners_Internal, fdutils.c:67-77
+  {
+    gxs = per[d] ? -sw : 0;
+    gxm = N[d] + (per[d] ? 2 * sw : 0);
+    gxe = (face && !per[d]) ? 1 : 0;
+  }
+  // FlucaFDGetCoordinate_Internal, fdutils.c:56-65
+  double coordinate(int d, int idx, bool face, int x, int n, double hp, double hn) const
+  {
+    if (x <= idx && idx < x + n) return array_coord(d, idx, face);
+    if (idx < x) return array_coord(d, x, face) - (x - idx) * hp;
+    return array_coord(d, x + n - 1, face) + (idx - (x + n - 1)) * hn;
+  }
+  void end_spacings(int d, int gxs, int gxm, double &hp, double &hn) const // derivative.c:79-82, fdutils.c:300-303
+  {
+    const int first = gxs, last = gxs + gxm - (per[d] ? 1 : 0);
+    hp = array_coord(d, first + 1, true) - array_coord(d, first, true);
+    hn = array_coord(d, last, true) - array_coord(d, last - 1, true);
+  }
+};
+
+struct Op {
+  Grid             *g = nullptr;
+  int               input_loc = LOC_ELEMENT, input_c = 0, output_loc = LOC_ELEMENT, output_c = 0;
+  int               bc_type[6] = {0, 0, 0, 0, 0, 0};
+  double            bc_value[6] = {0, 0, 0, 0, 0, 0};
+  std::vector<Term> terms;
+  bool              setupcalled = false;
+  int               refs = 1;
+  virtual ~Op() { }
+  virtual void setup() = 0;
+  virtual void raw(int i, int j, int k, Stencil &st) = 0;
+  void stencil_raw(int i, int j, int k, Stencil &st) // FlucaFDGetStencilRaw, fdapply.c:22-32
+  {
+    if (!setupcalled) throw Error(FL_ERR_ARG, "FlucaFD not setup");
+    st.n = 0;
+    raw(i, j, k, st);
+    st.remove_zero();
+  }
+  void stencil(int i, int j, int k, Stencil &st); // FlucaFDGetStencil, fdapply.c:34-45
+};
+
+// IsOffGrid_Private, fdutils.c:126-168
+static bool off_grid(const Op &fd, const Col &c, int &dir, bool &low)
+{
+  if (c.c < 0) return false;
+  for (int d = 0; d < fd.g->dim; ++d) {
+    int gxs, gxm, gxe;
+    fd.g->ghost_corners(d, use_face(c.loc, d), gxs, gxm, gxe);
+    if (c.idx(d) < gxs) {
+      dir = d, low = true;
+      return true;
+    }
+    if (c.idx(d) >= gxs + gxm + gxe) {
+      dir = d, low = false;
+      return true;
+    }
+  }
+  return false;
+}
+
+// FlucaFDRemoveOffGridPoints_Internal, fdutils.c:254-463
+static void remove_off_grid(const Op &fd, Stencil &st)
+{
+  const Grid &g = *fd.g;
+  int         iter = 0;
+  for (; iter < 100; ++iter) {
+    int  off = -1, d = 0;
+    bool low = false;
+    for (int q = 0; q < st.n; ++q)
+      if (off_grid(fd, st.col[q], d, low)) {
+        off = q;
+        break;
+      }
+    if (off < 0) break;
+    const Col    oc = st.col[off];
+    const double ov = st.v[off];
+    const bool   per = g.per[d] != 0;
+    const int    bc  = (low && !per) ? fd.bc_type[2 * d] : ((!low && !per) ? fd.bc_type[2 * d + 1] : FLUCA_B200_FD_BC_NONE);
+    const bool   face = use_face(oc.loc, d);
+    // GetStencilSizeForOffGridPoint_Private, fdutils.c:170-196
+    int size = INT_MAX;
+    for (const Term &t : fd.terms)
+      if (t.deriv[d] != -1 && t.accu[d] != INT_MAX && t.input_loc == oc.loc && t.input_c == oc.c) size = std::min(size, t.deriv[d] + t.accu[d]);
+    if (size == INT_MAX) throw Error(FL_ERR_ARG, "Cannot find a term from the given stencil point");
+    if (size < 1) size = 1;
+    if (size > MAXS) throw Error(FL_ERR_ARG, "Stencil size exceeds maximum");
+    int gxs, gxm, gxe;
+    g.ghost_corners(d, face, gxs, gxm, gxe);
+    double hp, hn;
+    g.end_spacings(d, gxs, gxm, hp, hn);
+    const double off_x = g.coordinate(d, oc.idx(d), face, gxs, gxm + gxe, hp, hn);
+    st.erase(off);
+    double xs[MAXS], w[MAXS], A[MAXS * MAXS], b[MAXS];
+    if (bc == FLUCA_B200_FD_BC_NONE) { // :326-356
+      const int start = low ? gxs : gxs + gxm + gxe - size;
+      for (int m = 0; m < size; ++m) xs[m] = g.coordinate(d, start + m, face, gxs, gxm + gxe, hp, hn);
+      for (int r = 0; r < size; ++r) {
+        for (int m = 0; m < size; ++m) A[r * size + m] = ipow(xs[m] - off_x, r);
+        b[r] = r == 0 ? 1. : 0.;
+      }
+      solve(size, A, b, w);
+      for (int m = 0; m < size; ++m) {
+        Col c = oc;
+        c.set(d, start + m);
+        st.add(c, ov * w[m]);
+      }
+    } else if (bc == FLUCA_B200_FD_BC_DIRICHLET || bc == FLUCA_B200_FD_BC_NEUMANN) {
+      int start = low ? gxs : gxs + gxm + gxe - (size - 1);
+      if (bc == FLUCA_B200_FD_BC_DIRICHLET && face) start += low ? 1 : -1; // remove duplicate (:361-365)
+      const int    bnd = low ? 0 : g.N[d];
+      const double bx  = g.coordinate(d, bnd, true, gxs, gxm + gxe, hp, hn);
+      Col          marker;
+      marker.i = d == 0 ? bnd : oc.i, marker.j = d == 1 ? bnd : oc.j, marker.k = d == 2 ? bnd : oc.k;
+      marker.loc = boundary_location(oc.loc, d);
+      marker.c   = -(2 * d + (low ? 1 : 2));
+      if (bc == FLUCA_B200_FD_BC_DIRICHLET) { // value from the boundary value and size - 1 on-grid points (:358-404)
+        xs[0] = bx;
+        for (int m = 0; m < size - 1; ++m) xs[m + 1] = g.coordinate(d, start + m, face, gxs, gxm + gxe, hp, hn);
+        for (int r = 0; r < size; ++r) {
+          for (int m = 0; m < size; ++m) A[r * size + m] = ipow(xs[m] - off_x, r);
+          b[r] = r == 0 ? 1. : 0.;
+        }
+        solve(size, A, b, w);
+        st.add(marker, ov * w[0]);
+        for (int m = 0; m < size - 1; ++m) {
+          Col c = oc;
+          c.set(d, start + m);
+          st.add(c, ov * w[m + 1]);
+        }
+      } else { // first derivative on the boundary from the off-grid point and size - 1 on-grid points, solved for the former (:406-452)
+        xs[0] = off_x;
+        for (int m = 0; m < size - 1; ++m) xs[m + 1] = g.coordinate(d, start + m, face, gxs, gxm + gxe, hp, hn);
+        for (int r = 0; r < size; ++r) {
+          for (int m = 0; m < size; ++m) A[r * size + m] = ipow(xs[m] - bx, r);
+          b[r] = r == 1 ? 1. : 0.;
+        }
+        solve(size, A, b, w);
+        if (std::fabs(w[0]) < COEFF_ATOL) throw Error(FL_ERR_ARG, "Neumann BC coefficient for off-grid point is too small");
+        st.add(marker, ov / w[0]);
+        for (int m = 0; m < size - 1; ++m) {
+          Col c = oc;
+          c.set(d, start + m);
+          st.add(c, -ov * w[m + 1] / w[0]);
+        }
+      }
+    } else throw Error(FL_ERR_ARG, "Unsupported boundary condition type");
+  }
+  if (iter >= 100) throw Error(FL_ERR_INTERNAL, "Failed to remove all off-grid points");
+  st.remove_zero();
+}
+
+void Op::stencil(int i, int j, int k, Stencil &st)
+{
+  stencil_raw(i, j, k, st);
+  remove_off_grid(*this, st);
+  st.remove_zero();
+}
+
+// ------------------------------------------------------------------ FLUCAFDDERIVATIVE, derivative.c:16-150
+struct Derivative : Op {
+  int    dir = 0, deriv_order = 1, accu_order = 1;
+  int    size = 0, offset = 0, gxs = 0, gxm = 0, gxe = 0, v_start = 0, v_end = 0;
+  bool   fin = false, fout = false;
+  double hp = 0., hn = 0.;
+  std::vector<std::vector<double>> w; // weights for indices v_start - 1 .. v_end (the ends are v_prev / v_next)
+  void setup() override
+  {
+    if (dir >= g->dim) throw Error(FL_ERR_ARG, "Cannot compute derivative in that direction on this DM");
+    if (deriv_order < 0 || accu_order < 1) throw Error(FL_ERR_ARG, "Order of derivative must be non-negative and order of accuracy positive");
+    fin = use_face(input_loc, dir), fout = use_face(output_loc, dir);
+    bool valid = fin != fout;
+    for (int d = 0; d < g->dim; ++d)
+      if (d != dir && use_face(input_loc, d) != use_face(output_loc, d)) valid = false;
+    if (!(input_loc == output_loc || valid)) throw Error(FL_ERR_ARG, "Cannot compute derivative between these stencil locations");
+    size = deriv_order + accu_order;
+    if (size > MAXS) throw Error(FL_ERR_ARG, "Required stencil size exceeds maximum");
+    offset = -((size - 1) / 2);
+    if (!fin && fout) offset -= 1;
+    g->ghost_corners(dir, fin, gxs, gxm, gxe);
+    v_start = gxs - (offset + size - 1);
+    v_end   = gxs + gxm + gxe - offset;
+    g->end_spacings(dir, gxs, gxm, hp, hn);
+    w.assign(v_end - v_start + 2, std::vector<double>());
+    for (int i = v_start - 1; i < v_end + 1; ++i) {
+      double       A[MAXS * MAXS], b[MAXS];
+      const double out_x = g->coordinate(dir, i, fout, gxs, gxm, hp, hn);
+      for (int c = 0; c < size; ++c) {
+        const double h = g->coordinate(dir, i + offset + c, fin, gxs, gxm + gxe, hp, hn) - out_x;
+        for (int r = 0; r < size; ++r) A[r * size + c] = ipow(h, r);
+      }
+      double fact = 1.;
+      for (int o = 1; o <= deriv_order; ++o) fact *= o;
+      for (int c = 0; c < size; ++c) b[c] = c == deriv_order ? fact : 0.;
+      std::vector<double> &x = w[i - (v_start - 1)];
+      x.resize(size);
+      solve(size, A, b, x.data());
+    }
+    Term t;
+    t.deriv[dir] = deriv_order, t.accu[dir] = accu_order, t.input_loc = input_loc, t.input_c = input_c;
+    terms.assign(1, t);
+  }
+  void raw(int i, int j, int k, Stencil &st) override
+  {
+    const int idx = dir == 0 ? i : (dir == 1 ? j : k);
+    const int q   = std::min(std::max(idx, v_start - 1), v_end) - (v_start - 1);
+    for (int c = 0; c < size; ++c) {
+      Col p = {i, j, k, input_loc, input_c};
+      p.set(dir, idx + offset + c);
+      st.col[st.n] = p, st.v[st.n] = w[q][c], ++st.n;
+    }
+  }
+};
+
+// ------------------------------------------------------------------ FLUCAFDSUM, sum.c:3-52
+struct Sum : Op {
+  std::vector<Op *> ops;
+  ~Sum() override;
+  void setup() override
+  {
+    if (ops.empty()) throw Error(FL_ERR_ARG, "No operands set");
+    if (input_loc != output_loc || input_c != output_c) throw Error(FL_ERR_ARG, "Cannot change location / component");
+    for (Op *o : ops)
+      if (o->output_loc != output_loc || o->output_c != output_c) throw Error(FL_ERR_ARG, "All operands must have the same output stencil location and component");
+    terms.clear();
+    for (Op *o : ops) merge_terms(terms, o->terms);
+  }
+  void raw(int i, int j, int k, Stencil &st) override
+  {
+    for (Op *o : ops) {
+      Stencil s;
+      o->stencil_raw(i, j, k, s);
+      for (int q = 0; q < s.n; ++q) st.add(s.col[q], s.v[q]);
+    }
+  }
+};
+
+// compact host field of one location / component: [nz + ez][ny + ey][nx + ex], e = 1 on a non-periodic face direction
+struct HostField {
+  std::vector<double> a;
+  int                 ext[3] = {1, 1, 1};
+  bool                set = false;
+  void assign(const Grid &g, int loc, const double *src)
+  {
+    size_t n = 1;
+    for (int d = 0; d < 3; ++d) {
+      ext[d] = d < g.dim ? g.N[d] + ((use_face(loc, d) && !g.per[d]) ? 1 : 0) : 1;
+      n *= (size_t)ext[d];
+    }
+    a.assign(src, src + n);
+    set = true;
+  }
+  // periodic directions wrap (the reference reads its ghosted local array); beyond a non-periodic end that array holds 0
+  double at(const Grid &g, int i, int j, int k) const
+  {
+    int p[3] = {i, j, k};
+    for (int d = 0; d < g.dim; ++d) {
+      if (g.per[d]) p[d] = ((p[d] % ext[d]) + ext[d]) % ext[d];
+      else if (p[d] < 0 || p[d] >= ext[d]) return 0.;
+    }
+    return a[(size_t)p[0] + (size_t)ext[0] * ((size_t)(g.dim > 1 ? p[1] : 0) + (size_t)ext[1] * (size_t)(g.dim > 2 ? p[2] : 0))];
+  }
+};
+
+// ------------------------------------------------------------------ FLUCAFDSCALE, scale.c:18-93
+struct Scale : Op {
+  Op       *operand = nullptr;
+  bool      is_constant = true;
+  double    constant = 1.;
+  HostField vec;
+  int       vec_loc = LOC_ELEMENT, vec_c = 0;
+  ~Scale() override;
+  void setup() override
+  {
+    if (!operand) throw Error(FL_ERR_ARG, "Operand not set");
+    if (!(operand->output_c == input_c && input_c == output_c)) throw Error(FL_ERR_ARG, "Cannot change component");
+    if (!(operand->output_loc == input_loc && input_loc == output_loc)) throw Error(FL_ERR_ARG, "Cannot change location");
+    if (!is_constant) {
+      if (!vec.set) throw Error(FL_ERR_ARG, "Neither constant nor vector scale specified");
+      if (operand->output_loc != vec_loc) throw Error(FL_ERR_ARG, "Operand and vector must have the same location");
+    }
+    terms = operand->terms;
+  }
+  void raw(int i, int j, int k, Stencil &st) override
+  {
+    operand->stencil_raw(i, j, k, st);
+    const double s = is_constant ? constant : vec.at(*g, i, j, k);
+    for (int q = 0; q < st.n; ++q) st.v[q] *= s;
+  }
+};
+
+// ------------------------------------------------------------------ FLUCAFDCOMPOSITION, composition.c:3-76
+struct Composition : Op {
+  Op *inner = nullptr, *outer = nullptr;
+  ~Composition() override;
+  void setup() override
+  {
+    if (!inner || !outer) throw Error(FL_ERR_ARG, "Inner / outer operator not set");
+    if (inner->output_c != outer->input_c) throw Error(FL_ERR_ARG, "Inner output component must match outer input component");
+    if (inner->output_loc != outer->input_loc) throw Error(FL_ERR_ARG, "Inner output location must match outer input location");
+    terms.clear();
+    for (const Term &ot : outer->terms)
+      for (const Term &it : inner->terms) {
+        Term t;
+        for (int d = 0; d < 3; ++d) {
+          if (it.deriv[d] == -1) t.deriv[d] = ot.deriv[d];
+          else if (ot.deriv[d] == -1) t.deriv[d] = it.deriv[d];
+          else t.deriv[d] = it.deriv[d] + ot.deriv[d];
+          t.accu[d] = std::min(it.accu[d], ot.accu[d]);
+        }
+        t.input_loc = it.input_loc, t.input_c = it.input_c;
+        merge_terms(terms, std::vector<Term>(1, t));
+      }
+  }
+  void raw(int i, int j, int k, Stencil &st) override
+  {
+    Stencil so;
+    outer->stencil_raw(i, j, k, so);
+    for (int oc = 0; oc < so.n; ++oc) {
+      if (so.col[oc].c < 0) { // constant or boundary marker of the outer operator passes through
+        st.add(so.col[oc], so.v[oc]);
+        continue;
+      }
+      Stencil si;
+      inner->stencil_raw(so.col[oc].i, so.col[oc].j, so.col[oc].k, si);
+      for (int ic = 0; ic < si.n; ++ic) st.add(si.col[ic], so.v[oc] * si.v[ic]);
+    }
+  }
+};
+
+// ------------------------------------------------------------------ FLUCAFDSECONDORDERTVD, secondordertvd.c:53-356
+typedef double (*Limiter)(double);
+static double lim_superbee(double r) { return std::max(0., std::max(std::min(2. * r, 1.), std::min(r, 2.))); }
+static double lim_minmod(double r) { return std::max(0., std::min(r, 1.)); }
+static double lim_mc(double r) { return std::max(0., std::min(std::min(2. * r, (1. + r) / 2.), 2.)); }
+static double lim_vanleer(double r) { return (r + std::fabs(r)) / (1. + std::fabs(r)); }
+static double lim_vanalbada(double r) { return r <= 0. ? 0. : (r * r + r) / (r * r + 1.); }
+static double lim_barthjesperson(double r) { return r <= 0. ? 0. : (1. + r) / 2. * std::min(1., std::min(4. * r / (1. + r), 4. / (1. + r))); }
+static double lim_venkatakrishnan(double r) { return r <= 0. ? 0. : (1. + r) / 2. * std::min(4. * r * (3. * r + 1.) / (11. * r * r + 4. * r + 1.), 4. * (r + 3.) / (r * r + 4. * r + 11.)); }
+static double lim_koren(double r) { return std::max(0., std::min(std::min(2. * r, (1. + 2. * r) / 3.), 2.)); }
+static double lim_upwind(double) { return 0.; }
+static double lim_sou(double r) { return r; }
+static double lim_quick(double r) { return (3. + r) / 4.; }
+static Limiter find_limiter(const std::string &name) // FlucaFDLimiterRegisterAll, secondordertvd.c:19-36
+{
+  static const struct { const char *n; Limiter f; } tab[] = {{"superbee", lim_superbee}, {"minmod", lim_minmod}, {"mc", lim_mc}, {"vanleer", lim_vanleer}, {"vanalbada", lim_vanalbada}, {"barthjesperson", lim_barthjesperson}, {"venkatakrishnan", lim_venkatakrishnan}, {"koren", lim_koren}, {"upwind", lim_upwind}, {"sou", lim_sou}, {"quick", lim_quick}};
+  for (const auto &e : tab)
+    if (name == e.n) return e.f;
+  throw Error(FL_ERR_ARG, "Unknown limiter type: " + name);
+}
+
+struct TVD : Op {
+  int                         dir = 0;
+  Limiter                     limiter = lim_superbee;
+  HostField                   vel, phi; // face velocity (location of the output), element-centred current solution
+  std::unique_ptr<Derivative> grad;
+  void setup() override
+  {
+    static const int face_of[3] = {LOC_LEFT, LOC_DOWN, LOC_BACK};
+    if (input_loc != LOC_ELEMENT) throw Error(FL_ERR_ARG, "Input location must be DMSTAG_ELEMENT for TVD interpolation");
+    if (dir >= g->dim || output_loc != face_of[dir]) throw Error(FL_ERR_ARG, "Output location must match direction (LEFT for X, DOWN for Y, BACK for Z)");
+    grad.reset(new Derivative()); // d phi / dx, element -> face, first order, this operator's boundary condition TYPES (:76-78)
+    grad->g = g, grad->dir = dir, grad->deriv_order = 1, grad->accu_order = 1;
+    grad->input_loc = input_loc, grad->input_c = input_c, grad->output_loc = output_loc, grad->output_c = 0;
+    for (int b = 0; b < 6; ++b) grad->bc_type[b] = bc_type[b], grad->bc_value[b] = bc_value[b];
+    grad->setup();
+    grad->setupcalled = true;
+    Term t;
+    t.deriv[dir] = 0, t.accu[dir] = 2, t.input_loc = input_loc, t.input_c = input_c; // interpolation, second order (:131-139)
+    terms.assign(1, t);
+  }
+  void alpha(int idx, double &plus, double &minus) const // :86-128
+  {
+    plus = minus = 0.5;
+    if ((idx == 0 || idx == g->N[dir]) && !g->per[dir]) return;
+    const double xf = g->array_coord(dir, idx, true), xl = g->array_coord(dir, idx - 1, false), xr = g->array_coord(dir, idx, false), dx = xr - xl;
+    if (std::fabs(dx) > 1e-14) plus = (xf - xl) / dx, minus = (xr - xf) / dx;
+  }
+  double face_gradient(int i, int j, int k) // ComputeFaceCenteredGradient_Private, :150-185
+  {
+    Stencil s;
+    grad->stencil(i, j, k, s);
+    double r = 0.;
+    for (int q = 0; q < s.n; ++q) {
+      if (s.col[q].c >= 0) r += s.v[q] * phi.at(*g, s.col[q].i, s.col[q].j, s.col[q].k);
+      else if (s.col[q].c >= -6) r += s.v[q] * bc_value[-s.col[q].c - 1]; // the CURRENT boundary values of this operator
+      else throw Error(FL_ERR_ARG, "Unsupported stencil point");
+    }
+    return r;
+  }
+  void raw(int i, int j, int k, Stencil &st) override
+  {
+    if (!vel.set || !phi.set) throw Error(FL_ERR_ARG, "Velocity / current solution not set");
+    int       p[3] = {i, j, k}, lo[3] = {i, j, k}, up[3] = {i, j, k};
+    const int idx = p[dir];
+    lo[dir] -= 1, up[dir] += 1;
+    int gxs, gxm, gxe;
+    g->ghost_corners(dir, true, gxs, gxm, gxe);
+    if (!(gxs <= idx && idx < gxs + gxm + gxe)) throw Error(FL_ERR_ARG, "Face index out of range");
+    const double u = vel.at(*g, i, j, k);
+    const bool   at_prev = idx == 0 && !g->per[dir], at_next = idx == g->N[dir] && !g->per[dir];
+    const Col    here = {p[0], p[1], p[2], input_loc, input_c}, below = {lo[0], lo[1], lo[2], input_loc, input_c}, cst = {0, 0, 0, LOC_ELEMENT, CONSTANT};
+    double       ap, am;
+    alpha(idx, ap, am);
+    st.n = 2;
+    if (u > 0) {
+      if (at_prev) {
+        st.col[0] = below, st.v[0] = 0.5, st.col[1] = here, st.v[1] = 0.5;
+        return;
+      }
+      const double gfu = face_gradient(lo[0], lo[1], lo[2]), gfc = face_gradient(p[0], p[1], p[2]);
+      const double psi = limiter(std::fabs(gfc) > 1e-30 ? gfu / gfc : 1.);
+      st.col[0] = below, st.v[0] = 1.;
+      st.col[1] = cst, st.v[1] = ap * psi * (phi.at(*g, p[0], p[1], p[2]) - phi.at(*g, lo[0], lo[1], lo[2]));
+    } else {
+      if (at_next) {
+        st.col[0] = here, st.v[0] = 0.5, st.col[1] = below, st.v[1] = 0.5;
+        return;
+      }
+      const double gfu = face_gradient(up[0], up[1], up[2]), gfc = face_gradient(p[0], p[1], p[2]);
+      const double psi = limiter(std::fabs(gfc) > 1e-30 ? gfu / gfc : 1.);
+      st.col[0] = here, st.v[0] = 1.;
+      st.col[1] = cst, st.v[1] = am * psi * (phi.at(*g, lo[0], lo[1], lo[2]) - phi.at(*g, p[0], p[1], p[2]));
+    }
+  }
+};
+
+// reference counting as PETSc's (operands are referenced by their parents; the user's destroy drops one reference)
+static void unref(Op *o);
+Sum::~Sum()
+{
+  for (Op *o : ops) unref(o);
+}
+Scale::~Scale() { unref(operand); }
+Composition::~Composition()
+{
+  unref(inner);
+  unref(outer);
+}
+static void unref(Grid *g)
+{
+  if (g && --g->refs == 0) delete g;
+}
+static void unref(Op *o)
+{
+  if (!o || --o->refs > 0) return;
+  Grid *g = o->g;
+  delete o;
+  unref(g);
+}
+
+} // namespace fd
+} // namespace fluca
+
+using namespace fluca;
+using namespace fluca::fd;
+
+struct fluca_b200_fd_grid {
+  Grid *g;
+};
+struct fluca_b200_fd {
+  Op *op;
+};
+
+static thread_local std::string g_fd_err;
+extern "C" const char *fluca_b200_fd_last_error(void) { return g_fd_err.c_str(); }
+
+#define FD_BEGIN try {
+#define FD_END \
+  } \
+  catch (const fluca::Error &e) \
+  { \
+    g_fd_err = e.what(); \
+    return e.code; \
+  } \
+  catch (const std::exception &e) \
+  { \
+    g_fd_err = e.what(); \
+    return FLUCA_B200_ERR_INTERNAL; \
+  } \
+  return FLUCA_B200_OK;
+
+static fluca_b200_fd *wrap(Op *o, Grid *g)
+{
+  o->g = g;
+  ++g->refs;
+  fluca_b200_fd *h = new fluca_b200_fd;
+  h->op            = o;
+  return h;
+}
+static Op *operand_of(const fluca_b200_fd *h)
+{
+  if (!h || !h->op) throw Error(FL_ERR_ARG, "null operator");
+  if (!h->op->setupcalled) throw Error(FL_ERR_ARG, "Operand FlucaFD is not set up. Call fluca_b200_fd_setup() on the operand first");
+  return h->op;
+}
+
+extern "C" int fluca_b200_fd_grid_create(int dim, const int n[3], const double *const xf[3], const double *const xc[3], const int periodic[3], int stencil_width, fluca_b200_fd_grid **out)
+{
+  FD_BEGIN
+  if (dim < 1 || dim > 3 || !n || !xf || !out || stencil_width < 1) throw Error(FL_ERR_ARG, "bad grid arguments");
+  std::unique_ptr<Grid> g(new Grid());
+  g->dim = dim, g->sw = stencil_width;
+  for (int d = 0; d < dim; ++d) {
+    if (n[d] < 2 || !xf[d]) throw Error(FL_ERR_ARG, "a direction needs at least 2 elements and its face coordinates");
+    g->N[d]   = n[d];
+    g->per[d] = periodic ? (periodic[d] != 0) : 0;
+    g->xf[d].assign(xf[d], xf[d] + n[d] + 1);
+    g->xc[d].resize(n[d]);
+    for (int i = 0; i < n[d]; ++i) g->xc[d][i] = (xc && xc[d]) ? xc[d][i] : 0.5 * (xf[d][i] + xf[d][i + 1]);
+  }
+  fluca_b200_fd_grid *h = new fluca_b200_fd_grid;
+  h->g                  = g.release();
+  *out                  = h;
+  FD_END
+}
+extern "C" int fluca_b200_fd_grid_destroy(fluca_b200_fd_grid *h)
+{
+  FD_BEGIN
+  if (h) {
+    unref(h->g);
+    delete h;
+  }
+  FD_END
+}
+
+extern "C" int fluca_b200_fd_derivative_create(fluca_b200_fd_grid *grid, int dir, int deriv_order, int accu_order, int input_loc, int input_c, int output_loc, int output_c, fluca_b200_fd **out)
+{
+  FD_BEGIN
+  if (!grid || !out) throw Error(FL_ERR_ARG, "null argument");
+  if (!valid_location(input_loc) || !valid_location(output_loc)) throw Error(FL_ERR_ARG, "Invalid stencil location; only ELEMENT, LEFT, DOWN, BACK, and their combinations are allowed");
+  Derivative *d  = new Derivative();
+  d->dir         = dir, d->deriv_order = deriv_order, d->accu_order = accu_order;
+  d->input_loc   = input_loc, d->input_c = input_c, d->output_loc = output_loc, d->output_c = output_c;
+  *out           = wrap(d, grid->g);
+  FD_END
+}
+extern "C" int fluca_b200_fd_sum_create(int n, fluca_b200_fd *const ops[], fluca_b200_fd **out)
+{
+  FD_BEGIN
+  if (n < 1 || !ops || !out) throw Error(FL_ERR_ARG, "Number of operands must be positive");
+  Op  *first = operand_of(ops[0]);
+  Sum *s     = new Sum();
+  s->input_loc = s->output_loc = first->output_loc, s->input_c = s->output_c = first->output_c;
+  for (int q = 0; q < n; ++q) {
+    Op *o = operand_of(ops[q]);
+    ++o->refs;
+    s->ops.push_back(o);
+  }
+  *out = wrap(s, first->g);
+  FD_END
+}
+extern "C" int fluca_b200_fd_scale_create_constant(fluca_b200_fd *operand, double constant, fluca_b200_fd **out)
+{
+  FD_BEGIN
+  if (!out) throw Error(FL_ERR_ARG, "null argument");
+  Op    *o = operand_of(operand);
+  Scale *s = new Scale();
+  s->operand = o, ++o->refs;
+  s->is_constant = true, s->constant = constant;
+  s->input_loc = s->output_loc = o->output_loc, s->input_c = s->output_c = o->output_c;
+  *out = wrap(s, o->g);
+  FD_END
+}
+extern "C" int fluca_b200_fd_scale_create_vector(fluca_b200_fd *operand, const double *field, int vec_loc, int vec_c, fluca_b200_fd **out)
+{
+  FD_BEGIN
+  if (!out || !field) throw Error(FL_ERR_ARG, "null argument");
+  if (!valid_location(vec_loc)) throw Error(FL_ERR_ARG, "Invalid stencil location");
+  Op    *o = operand_of(operand);
+  Scale *s = new Scale();
+  s->operand = o, ++o->refs;
+  s->is_constant = false, s->vec_loc = vec_loc, s->vec_c = vec_c;
+  s->vec.assign(*o->g, vec_loc, field);
+  s->input_loc = s->output_loc = o->output_loc, s->input_c = s->output_c = o->output_c;
+  *out = wrap(s, o->g);
+  FD_END
+}
+extern "C" int fluca_b200_fd_composition_create(fluca_b200_fd *inner, fluca_b200_fd *outer, fluca_b200_fd **out)
+{
+  FD_BEGIN
+  if (!out) throw Error(FL_ERR_ARG, "null argument");
+  Op          *in = operand_of(inner), *ou = operand_of(outer);
+  Composition *c  = new Composition();
+  c->inner = in, c->outer = ou, ++in->refs, ++ou->refs;
+  c->input_loc = in->input_loc, c->input_c = in->input_c, c->output_loc = ou->output_loc, c->output_c = ou->output_c;
+  *out = wrap(c, in->g);
+  FD_END
+}
+extern "C" int fluca_b200_fd_tvd_create(fluca_b200_fd_grid *grid, int dir, int input_c, int output_c, fluca_b200_fd **out)
+{
+  FD_BEGIN
+  if (!grid || !out || dir < 0 || dir > 2) throw Error(FL_ERR_ARG, "bad argument");
+  static const int face_of[3] = {LOC_LEFT, LOC_DOWN, LOC_BACK};
+  TVD *t = new TVD();
+  t->dir = dir, t->input_loc = LOC_ELEMENT, t->input_c = input_c, t->output_loc = face_of[dir], t->output_c = output_c;
+  *out = wrap(t, grid->g);
+  FD_END
+}
+extern "C" int fluca_b200_fd_tvd_set_limiter(fluca_b200_fd *h, const char *name)
+{
+  FD_BEGIN
+  TVD *t = h ? dynamic_cast<TVD *>(h->op) : nullptr;
+  if (!t || !name) throw Error(FL_ERR_ARG, "not a secondordertvd operator");
+  t->limiter = find_limiter(name);
+  FD_END
+}
+extern "C" int fluca_b200_fd_tvd_set_velocity(fluca_b200_fd *h, const double *face_velocity)
+{
+  FD_BEGIN
+  TVD *t = h ? dynamic_cast<TVD *>(h->op) : nullptr;
+  if (!t || !face_velocity) throw Error(FL_ERR_ARG, "not a secondordertvd operator");
+  t->vel.assign(*t->g, t->output_loc, face_velocity);
+  FD_END
+}
+extern "C" int fluca_b200_fd_tvd_set_current_solution(fluca_b200_fd *h, const double *phi)
+{
+  FD_BEGIN
+  TVD *t = h ? dynamic_cast<TVD *>(h->op) : nullptr;
+  if (!t || !phi) throw Error(FL_ERR_ARG, "not a secondordertvd operator");
+  t->phi.assign(*t->g, LOC_ELEMENT, phi);
+  FD_END
+}
+extern "C" int fluca_b200_fd_set_locations(fluca_b200_fd *h, int input_loc, int input_c, int output_loc, int output_c)
+{
+  FD_BEGIN
+  if (!h || !h->op) throw Error(FL_ERR_ARG, "null operator");
+  if (!valid_location(input_loc) || !valid_location(output_loc)) throw Error(FL_ERR_ARG, "Invalid stencil location; only ELEMENT, LEFT, DOWN, BACK, and their combinations are allowed");
+  h->op->input_loc = input_loc, h->op->input_c = input_c, h->op->output_loc = output_loc, h->op->output_c = output_c;
+  h->op->setupcalled = false;
+  FD_END
+}
+extern "C" int fluca_b200_fd_scale_set_vector_location(fluca_b200_fd *h, int vec_loc, int vec_c)
+{
+  FD_BEGIN
+  Scale *s = h ? dynamic_cast<Scale *>(h->op) : nullptr;
+  if (!s || s->is_constant) throw Error(FL_ERR_ARG, "not a vector scale operator");
+  if (!valid_location(vec_loc)) throw Error(FL_ERR_ARG, "Invalid stencil location");
+  s->vec_loc = vec_loc, s->vec_c = vec_c;
+  FD_END
+}
+extern "C" int fluca_b200_fd_set_boundary_condition(fluca_b200_fd *h, int boundary, int type, double value)
+{
+  FD_BEGIN
+  if (!h || !h->op || boundary < 0 || boundary > 5) throw Error(FL_ERR_ARG, "bad boundary");
+  if (type != FLUCA_B200_FD_BC_NONE && type != FLUCA_B200_FD_BC_DIRICHLET && type != FLUCA_B200_FD_BC_NEUMANN) throw Error(FL_ERR_ARG, "Unsupported boundary condition type");
+  h->op->bc_type[boundary] = type, h->op->bc_value[boundary] = value;
+  FD_END
+}
+extern "C" int fluca_b200_fd_setup(fluca_b200_fd *h)
+{
+  FD_BEGIN
+  if (!h || !h->op) throw Error(FL_ERR_ARG, "null operator");
+  if (!h->op->setupcalled) {
+    h->op->setup();
+    h->op->setupcalled = true;
+  }
+  FD_END
+}
+extern "C" int fluca_b200_fd_get_stencil(fluca_b200_fd *h, int i, int j, int k, int *ncols, fluca_b200_fd_col col[FLUCA_B200_FD_MAX_STENCIL], double v[FLUCA_B200_FD_MAX_STENCIL])
+{
+  FD_BEGIN
+  if (!h || !h->op || !ncols || !col || !v) throw Error(FL_ERR_ARG, "null argument");
+  Stencil st;
+  h->op->stencil(i, j, k, st);
+  *ncols = st.n;
+  for (int q = 0; q < st.n; ++q) col[q].i = st.col[q].i, col[q].j = st.col[q].j, col[q].k = st.col[q].k, col[q].loc = st.col[q].loc, col[q].c = st.col[q].c, v[q] = st.v[q];
+  FD_END
+}
+extern "C" int fluca_b200_fd_destroy(fluca_b200_fd *h)
+{
+  FD_BEGIN
+  if (h) {
+    unref(h->op);
+    delete h;
+  }
+  FD_END
+}

@@ -203,6 +203,49 @@ int fluca_b200_kernel_times(fluca_b200_solver *s, double ms[FLUCA_B200_KT_NCLASS
  * algorithmic bytes of one launch.  names: "momentum_apply", "poisson_apply", "mg_smooth", "vector_update" */
 int fluca_b200_time_kernel(fluca_b200_solver *s, const char *name, int reps, double *ms, double *algorithmic_bytes);
 
+/* ==== FlucaFD: finite-difference operator family (fluca/include/flucafd.h), stencil layer ====
+ * Host-side entry points (no device needed): the composed stencil the reference's FlucaFDGetStencil returns at an output
+ * point, from which a matrix-free device apply is generated.  One rank.  Names and argument meaning follow flucafd.h:
+ *   grid_create          the DMStag facts FlucaFDSetUp reads (fdbasic.c:165-186): sizes, periodicity, stencil width and the
+ *                        product coordinates (xf[d]: n[d]+1 faces; xc[d]: n[d] centres, NULL = face midpoints)
+ *   *_create             FlucaFDDerivativeCreate / SumCreate / ScaleCreateConstant / ScaleCreateVector / CompositionCreate /
+ *                        SecondOrderTVDCreate (flucafd.h:82-109); operands must be set up first, as in the reference
+ *   set_locations        FlucaFDSetInputLocation + FlucaFDSetOutputLocation (flucafd.h:64-65; -flucafd_input_loc ...)
+ *   set_boundary_condition  FlucaFDSetBoundaryConditions for one of LEFT, RIGHT, DOWN, UP, BACK, FRONT (flucafd.h:66)
+ *   setup                FlucaFDSetUp (flucafd.h:59)
+ *   get_stencil          FlucaFDGetStencil (flucafd.h:74): raw stencil, off-grid points removed per boundary condition
+ * loc arguments are DMStagStencilLocation values (ELEMENT 14, LEFT 13, DOWN 11, BACK 5, DOWN_LEFT 10, BACK_LEFT 4,
+ * BACK_DOWN 2, BACK_DOWN_LEFT 1); col.c < 0 marks a boundary value (-1 left ... -6 front, flucafd.h:44-50) or the constant
+ * term (-7, flucafd.h:52).  Host fields are compact [nz+ez][ny+ey][nx+ex] arrays of one location (e = 1 on a non-periodic
+ * face direction).  Errors: return code + fluca_b200_fd_last_error(). */
+#define FLUCA_B200_FD_MAX_STENCIL 32 /* FLUCAFD_MAX_STENCIL_SIZE */
+#define FLUCA_B200_FD_BC_NONE 0      /* FlucaFDBoundaryConditionType, flucafd.h:31-36 */
+#define FLUCA_B200_FD_BC_DIRICHLET 1
+#define FLUCA_B200_FD_BC_NEUMANN 2
+typedef struct fluca_b200_fd_grid fluca_b200_fd_grid;
+typedef struct fluca_b200_fd      fluca_b200_fd;
+typedef struct {
+  int i, j, k, loc, c; /* DMStagStencil */
+} fluca_b200_fd_col;
+const char *fluca_b200_fd_last_error(void);
+int fluca_b200_fd_grid_create(int dim, const int n[3], const double *const xf[3], const double *const xc[3], const int periodic[3], int stencil_width, fluca_b200_fd_grid **out);
+int fluca_b200_fd_grid_destroy(fluca_b200_fd_grid *grid);
+int fluca_b200_fd_derivative_create(fluca_b200_fd_grid *grid, int dir, int deriv_order, int accu_order, int input_loc, int input_c, int output_loc, int output_c, fluca_b200_fd **out);
+int fluca_b200_fd_sum_create(int n, fluca_b200_fd *const ops[], fluca_b200_fd **out);
+int fluca_b200_fd_scale_create_constant(fluca_b200_fd *operand, double constant, fluca_b200_fd **out);
+int fluca_b200_fd_scale_create_vector(fluca_b200_fd *operand, const double *field, int vec_loc, int vec_c, fluca_b200_fd **out);
+int fluca_b200_fd_scale_set_vector_location(fluca_b200_fd *fd, int vec_loc, int vec_c); /* FlucaFDScaleSetVector's location, -flucafd_vec_loc */
+int fluca_b200_fd_composition_create(fluca_b200_fd *inner, fluca_b200_fd *outer, fluca_b200_fd **out);
+int fluca_b200_fd_tvd_create(fluca_b200_fd_grid *grid, int dir, int input_c, int output_c, fluca_b200_fd **out);
+int fluca_b200_fd_tvd_set_limiter(fluca_b200_fd *fd, const char *name);              /* FlucaFDSecondOrderTVDSetLimiter */
+int fluca_b200_fd_tvd_set_velocity(fluca_b200_fd *fd, const double *face_velocity);  /* FlucaFDSecondOrderTVDSetVelocity */
+int fluca_b200_fd_tvd_set_current_solution(fluca_b200_fd *fd, const double *phi);    /* FlucaFDSecondOrderTVDSetCurrentSolution */
+int fluca_b200_fd_set_locations(fluca_b200_fd *fd, int input_loc, int input_c, int output_loc, int output_c);
+int fluca_b200_fd_set_boundary_condition(fluca_b200_fd *fd, int boundary, int type, double value);
+int fluca_b200_fd_setup(fluca_b200_fd *fd);
+int fluca_b200_fd_get_stencil(fluca_b200_fd *fd, int i, int j, int k, int *ncols, fluca_b200_fd_col col[FLUCA_B200_FD_MAX_STENCIL], double v[FLUCA_B200_FD_MAX_STENCIL]);
+int fluca_b200_fd_destroy(fluca_b200_fd *fd);
+
 #ifdef __cplusplus
 }
 #endif
