@@ -126,6 +126,8 @@ SYMBOLS = [
     "fluca_b200_fd_set_boundary_condition",
     "fluca_b200_fd_setup",
     "fluca_b200_fd_get_stencil",
+    "fluca_b200_fd_apply_inputs",
+    "fluca_b200_fd_apply",
     "fluca_b200_fd_destroy",
 ]
 FD_MAX_STENCIL = 32
@@ -197,6 +199,8 @@ def _prototype(L):
     L.fluca_b200_fd_set_boundary_condition.argtypes = [_P, C.c_int, C.c_int, C.c_double]
     L.fluca_b200_fd_setup.argtypes = [_P]
     L.fluca_b200_fd_get_stencil.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(FDCol), C.POINTER(C.c_double)]
+    L.fluca_b200_fd_apply_inputs.argtypes = [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.fluca_b200_fd_apply.argtypes = [_P, C.c_int, C.POINTER(_P), _P]
     L.fluca_b200_fd_destroy.argtypes = [_P]
     L.fluca_b200_stage_state.argtypes = [_P]
     L.fluca_b200_staged_state.argtypes = [_P, C.POINTER(_P), _PD3, C.POINTER(_P), C.POINTER(_P)]

@@ -819,6 +819,231 @@ extern "C" int fluca_b200_fd_get_stencil(fluca_b200_fd *h, int i, int j, int k, 
   for (int q = 0; q < st.n; ++q) col[q].i = st.col[q].i, col[q].j = st.col[q].j, col[q].k = st.col[q].k, col[q].loc = st.col[q].loc, col[q].c = st.col[q].c, v[q] = st.v[q];
   FD_END
 }
+// ------------------------------------------------------------------ matrix-free device apply (FlucaFDApply, fdapply.c:47-121)
+// v1: operators whose stencil depends on the output point only through its distance class from the non-periodic boundaries
+// -- derivative / sum / constant scale / composition on uniform product coordinates.  The host generates the stencil of one
+// representative point per class triple with the stencil layer above ((2R + 1)^dim variants, R = reach of the composed
+// stencil), folds boundary values and constant terms into one number per variant, and the kernel evaluates
+//   y(P) = const[variant(P)] + sum_taps w * x_slot(P + offset)            (periodic directions wrap)
+// straight from the input fields: nothing is assembled per point.  Field-dependent operators (vector scale, TVD) and
+// non-uniform coordinates are rejected, not approximated.  Status: parity-tested in the host-emulation build; the CUDA
+// path has not run on a B200 yet.
+namespace fluca {
+namespace fd {
+
+static const int MAX_SLOTS = 4;
+
+struct ApplyFunctor {
+  int           dim, R;
+  int           E[3];         // output extents
+  int           per[3];
+  int           ncls[3];
+  const int    *tap_start;    // [nvar + 1]
+  const int    *tap_meta;     // [ntaps][4]: di, dj, dk, slot
+  const double *tap_w;        // [ntaps]
+  const double *var_const;    // [nvar]
+  const double *in[MAX_SLOTS];
+  int           in_ext[MAX_SLOTS][3];
+  double       *out;
+  FL_HD int cls(int d, int idx) const
+  {
+    if (d >= dim || per[d]) return 0; // one class: a periodic direction is translation invariant
+    if (idx < R) return idx;
+    if (idx >= E[d] - R) return R + 1 + (idx - (E[d] - R));
+    return R;
+  }
+  FL_HD void operator()(int i, int j, int k) const
+  {
+    const int    v  = (cls(2, k) * ncls[1] + cls(1, j)) * ncls[0] + cls(0, i);
+    double       acc = var_const[v];
+    const int    p[3] = {i, j, k};
+    for (int t = tap_start[v]; t < tap_start[v + 1]; ++t) {
+      const int *m = tap_meta + 4 * t;
+      const int  s = m[3];
+      int        q[3];
+      for (int d = 0; d < 3; ++d) {
+        q[d] = p[d] + m[d];
+        if (d < dim && per[d]) {
+          const int n = in_ext[s][d];
+          q[d]        = ((q[d] % n) + n) % n;
+        }
+      }
+      acc += tap_w[t] * in[s][(long)q[0] + (long)in_ext[s][0] * ((long)q[1] + (long)in_ext[s][1] * (long)q[2])];
+    }
+    out[(long)i + (long)E[0] * ((long)j + (long)E[1] * (long)k)] = acc;
+  }
+};
+
+static void field_extents(const Grid &g, int loc, int ext[3])
+{
+  for (int d = 0; d < 3; ++d) ext[d] = d < g.dim ? g.N[d] + ((use_face(loc, d) && !g.per[d]) ? 1 : 0) : 1;
+}
+static bool field_dependent(const Op *o)
+{
+  if (dynamic_cast<const TVD *>(o)) return true;
+  if (const Scale *s = dynamic_cast<const Scale *>(o)) return !s->is_constant || field_dependent(s->operand);
+  if (const Sum *s = dynamic_cast<const Sum *>(o)) {
+    for (const Op *q : s->ops)
+      if (field_dependent(q)) return true;
+    return false;
+  }
+  if (const Composition *c = dynamic_cast<const Composition *>(o)) return field_dependent(c->inner) || field_dependent(c->outer);
+  return false;
+}
+
+struct Plan {
+  int                 R = 0, ncls[3] = {1, 1, 1}, E[3] = {1, 1, 1};
+  std::vector<int>    tap_start, tap_meta;
+  std::vector<double> tap_w, var_const;
+  int                 nslots = 0, slot_loc[MAX_SLOTS], slot_c[MAX_SLOTS];
+};
+
+// representative output index of class c along direction d
+static int representative(const Plan &p, const Grid &g, int d, int c)
+{
+  if (d >= g.dim) return 0;
+  if (g.per[d]) return p.E[d] / 2;
+  if (c < p.R) return c;
+  if (c == p.R) return p.R;
+  return p.E[d] - p.R + (c - p.R - 1);
+}
+
+static void build_plan(Op &op, Plan &p)
+{
+  const Grid &g = *op.g;
+  if (!op.setupcalled) throw Error(FL_ERR_ARG, "FlucaFD not setup");
+  if (field_dependent(&op)) throw Error(FL_ERR_ARG, "the device apply (v1) covers derivative / sum / constant scale / composition; vector scale and TVD operators are not supported yet");
+  for (int d = 0; d < g.dim; ++d) { // uniform coordinates: the class table relies on translation invariance
+    const double h = (g.xf[d][g.N[d]] - g.xf[d][0]) / g.N[d];
+    for (int i = 0; i < g.N[d]; ++i)
+      if (std::fabs((g.xf[d][i + 1] - g.xf[d][i]) - h) > 1e-12 * std::fabs(h) || std::fabs(g.xc[d][i] - 0.5 * (g.xf[d][i] + g.xf[d][i + 1])) > 1e-12 * std::fabs(h)) throw Error(FL_ERR_ARG, "the device apply (v1) needs uniform product coordinates");
+  }
+  field_extents(g, op.output_loc, p.E);
+  // reach of the composed stencil: the widest tap offset seen at a mid-grid point, in any direction
+  Stencil st;
+  int     mid[3] = {0, 0, 0};
+  for (int d = 0; d < g.dim; ++d) mid[d] = p.E[d] / 2;
+  op.stencil_raw(mid[0], mid[1], mid[2], st);
+  int reach = 1;
+  for (int q = 0; q < st.n; ++q)
+    if (st.col[q].c >= 0)
+      for (int d = 0; d < g.dim; ++d) {
+        const int r = std::abs(st.col[q].idx(d) - mid[d]) + 1;
+        reach       = std::max(reach, r);
+        // beyond its ghost elements the reference extrapolates even in a periodic direction (fdutils.c:306-356); the class
+        // table treats periodic directions as translation invariant, which is only the same thing while taps stay inside
+        if (g.per[d] && r - 1 > g.sw) throw Error(FL_ERR_ARG, "the stencil is wider than the DMStag stencil width in a periodic direction");
+      }
+  p.R = reach + 1; // one more: the one-sided closures of the first interior row still see the boundary
+  for (int d = 0; d < 3; ++d) {
+    p.ncls[d] = (d < g.dim && !g.per[d]) ? 2 * p.R + 1 : 1;
+    if (d < g.dim && !g.per[d] && p.E[d] < 2 * p.R + 2) throw Error(FL_ERR_ARG, "grid too small for this operator's boundary classes");
+  }
+  const int nvar = p.ncls[0] * p.ncls[1] * p.ncls[2];
+  p.tap_start.assign(1, 0);
+  p.var_const.assign(nvar, 0.);
+  p.nslots = 0;
+  for (int cz = 0; cz < p.ncls[2]; ++cz)
+    for (int cy = 0; cy < p.ncls[1]; ++cy)
+      for (int cx = 0; cx < p.ncls[0]; ++cx) {
+        const int cc[3] = {cx, cy, cz};
+        int       r[3];
+        for (int d = 0; d < 3; ++d) r[d] = representative(p, g, d, g.per[d] ? p.R : cc[d]);
+        op.stencil(r[0], r[1], r[2], st);
+        const int v = (cz * p.ncls[1] + cy) * p.ncls[0] + cx;
+        for (int q = 0; q < st.n; ++q) {
+          const Col &c = st.col[q];
+          if (c.c == CONSTANT) p.var_const[v] += st.v[q];
+          else if (c.c < 0) p.var_const[v] += st.v[q] * op.bc_value[-c.c - 1]; // fdapply.c:99-104
+          else {
+            int slot = -1;
+            for (int s2 = 0; s2 < p.nslots; ++s2)
+              if (p.slot_loc[s2] == c.loc && p.slot_c[s2] == c.c) slot = s2;
+            if (slot < 0) {
+              if (p.nslots >= MAX_SLOTS) throw Error(FL_ERR_ARG, "too many distinct input fields");
+              slot = p.nslots++, p.slot_loc[slot] = c.loc, p.slot_c[slot] = c.c;
+            }
+            p.tap_meta.push_back(c.i - r[0]), p.tap_meta.push_back(c.j - r[1]), p.tap_meta.push_back(c.k - r[2]), p.tap_meta.push_back(slot);
+            p.tap_w.push_back(st.v[q]);
+          }
+        }
+        p.tap_start.push_back((int)p.tap_w.size());
+      }
+}
+
+} // namespace fd
+} // namespace fluca
+
+extern "C" int fluca_b200_fd_apply_inputs(fluca_b200_fd *h, int *ninputs, int loc[4], int c[4])
+{
+  FD_BEGIN
+  if (!h || !h->op || !ninputs || !loc || !c) throw Error(FL_ERR_ARG, "null argument");
+  Plan p;
+  build_plan(*h->op, p);
+  *ninputs = p.nslots;
+  for (int s = 0; s < p.nslots; ++s) loc[s] = p.slot_loc[s], c[s] = p.slot_c[s];
+  FD_END
+}
+
+extern "C" int fluca_b200_fd_apply(fluca_b200_fd *h, int ninputs, const double *const inputs[], double *output)
+{
+  FD_BEGIN
+  if (!h || !h->op || !inputs || !output) throw Error(FL_ERR_ARG, "null argument");
+#ifndef FLUCA_HOSTEMU
+  {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) throw Error(FL_ERR_NODEVICE, "fluca_b200 needs a CUDA device (sm_100a); there is no CPU fallback");
+  }
+#endif
+  Op         &op = *h->op;
+  const Grid &g  = *op.g;
+  Plan        p;
+  build_plan(op, p);
+  if (ninputs != p.nslots) throw Error(FL_ERR_ARG, "number of input fields does not match fluca_b200_fd_apply_inputs");
+  Exec ex;
+  ex.init();
+  std::vector<void *> owned;
+  auto up = [&](const void *src, size_t bytes) {
+    void *d = dev_alloc(bytes);
+    owned.push_back(d);
+    copy_h2d(ex, d, src, bytes);
+    return d;
+  };
+  try {
+    ApplyFunctor f;
+    f.dim = g.dim, f.R = p.R;
+    for (int d = 0; d < 3; ++d) f.E[d] = p.E[d], f.per[d] = d < g.dim ? g.per[d] : 0, f.ncls[d] = p.ncls[d];
+    f.tap_start = (const int *)up(p.tap_start.data(), sizeof(int) * p.tap_start.size());
+    f.tap_meta  = (const int *)up(p.tap_meta.data(), sizeof(int) * std::max<size_t>(p.tap_meta.size(), 1));
+    f.tap_w     = (const double *)up(p.tap_w.data(), sizeof(double) * std::max<size_t>(p.tap_w.size(), 1));
+    f.var_const = (const double *)up(p.var_const.data(), sizeof(double) * p.var_const.size());
+    for (int s = 0; s < MAX_SLOTS; ++s) {
+      f.in[s] = nullptr;
+      for (int d = 0; d < 3; ++d) f.in_ext[s][d] = 1;
+    }
+    for (int s = 0; s < p.nslots; ++s) {
+      if (!inputs[s]) throw Error(FL_ERR_ARG, "null input field");
+      field_extents(g, p.slot_loc[s], f.in_ext[s]);
+      f.in[s] = (const double *)up(inputs[s], sizeof(double) * (size_t)f.in_ext[s][0] * f.in_ext[s][1] * f.in_ext[s][2]);
+    }
+    const size_t nout = (size_t)p.E[0] * p.E[1] * p.E[2];
+    f.out             = (double *)dev_alloc(sizeof(double) * nout);
+    owned.push_back(f.out);
+    Box b = {p.E[0], p.E[1], p.E[2]};
+    for_box(ex, b, f);
+    copy_d2h(ex, output, f.out, sizeof(double) * nout);
+    ex.sync();
+  } catch (...) {
+    ex.sync();
+    for (void *d : owned) dev_free(d);
+    ex.destroy();
+    throw;
+  }
+  for (void *d : owned) dev_free(d);
+  ex.destroy();
+  FD_END
+}
+
 extern "C" int fluca_b200_fd_destroy(fluca_b200_fd *h)
 {
   FD_BEGIN

@@ -95,6 +95,25 @@ class FlucaFD:
         _check(self.L, self.L.fluca_b200_fd_get_stencil(self._h, i, j, k, C.byref(n), col, v))
         return [((col[q].i, col[q].j, col[q].k, col[q].loc, col[q].c), v[q]) for q in range(n.value)]
 
+    def ApplyInputs(self) -> List[Tuple[int, int]]:
+        """(location, component) of every input field the composed operator reads, in the order Apply expects them"""
+        n, loc, c = C.c_int(), (C.c_int * 4)(), (C.c_int * 4)()
+        _check(self.L, self.L.fluca_b200_fd_apply_inputs(self._h, C.byref(n), loc, c))
+        return [(loc[q], c[q]) for q in range(n.value)]
+
+    def Apply(self, inputs, output_loc: int) -> np.ndarray:
+        """FlucaFDApply (flucafd.h:75) on the device.  inputs: {(loc, c): field} or a list in ApplyInputs() order."""
+        order = self.ApplyInputs()
+        if isinstance(inputs, dict):
+            inputs = [inputs[k] for k in order]
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in inputs]
+        for a, (loc, _) in zip(arrs, order):
+            assert a.shape == self.grid.field_shape(loc), (a.shape, self.grid.field_shape(loc))
+        ptr = (C.c_void_p * max(len(arrs), 1))(*[a.ctypes.data for a in arrs])
+        out = np.zeros(self.grid.field_shape(output_loc))
+        _check(self.L, self.L.fluca_b200_fd_apply(self._h, len(arrs), ptr, out.ctypes.data))
+        return out
+
     def Destroy(self):
         if getattr(self, "_h", None):
             self.L.fluca_b200_fd_destroy(self._h)

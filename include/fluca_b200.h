@@ -244,6 +244,13 @@ int fluca_b200_fd_set_locations(fluca_b200_fd *fd, int input_loc, int input_c, i
 int fluca_b200_fd_set_boundary_condition(fluca_b200_fd *fd, int boundary, int type, double value);
 int fluca_b200_fd_setup(fluca_b200_fd *fd);
 int fluca_b200_fd_get_stencil(fluca_b200_fd *fd, int i, int j, int k, int *ncols, fluca_b200_fd_col col[FLUCA_B200_FD_MAX_STENCIL], double v[FLUCA_B200_FD_MAX_STENCIL]);
+/* FlucaFDApply (flucafd.h:75, fdapply.c:47-121) as a matrix-free device kernel generated from the stencil layer; v1 covers
+ * derivative / sum / constant scale / composition on uniform product coordinates and rejects anything else with an error
+ * (csrc/fd.cu).  apply_inputs reports which input fields (location, component) the composed operator reads, in the order
+ * apply expects them; inputs / output are host arrays in the compact layout above (copied to and from the device inside).
+ * Needs a CUDA device (FLUCA_B200_ERR_NODEVICE otherwise). */
+int fluca_b200_fd_apply_inputs(fluca_b200_fd *fd, int *ninputs, int loc[4], int c[4]);
+int fluca_b200_fd_apply(fluca_b200_fd *fd, int ninputs, const double *const inputs[], double *output);
 int fluca_b200_fd_destroy(fluca_b200_fd *fd);
 
 #ifdef __cplusplus

@@ -1,0 +1,146 @@
+"""FlucaFDApply as a matrix-free kernel generated from the stencil layer (csrc/fd.cu, v1: derivative / sum / constant scale /
+composition on uniform coordinates) against the point-by-point definition of fdapply.c:85-106 evaluated with the
+golden-pinned stencil layer (tests/test_fd_stencils.py) at EVERY output point, boundary closures and corners included.
+
+CPU: the host-emulation build of the same sources.  The GPU cases are skipped, not claimed: the kernel was written after this
+round's GPU budget was spent and has not run on a B200 yet; they are the first thing to enable next round.
+(The file sorts last on purpose.)"""
+import numpy as np
+import pytest
+
+import fluca_b200 as fb
+from fluca_b200 import fd as FD
+from tests import parity
+
+E, L, D, B = FD.DMSTAG_ELEMENT, FD.DMSTAG_LEFT, FD.DMSTAG_DOWN, FD.DMSTAG_BACK
+
+
+def reference_apply(op, grid, fields, out_loc, bc_values):
+    """fdapply.c:85-106 in plain loops over FlucaFDGetStencil"""
+    shape = grid.field_shape(out_loc)
+    full = (1,) * (3 - len(shape)) + shape
+    out = np.zeros(full)
+    per = list(grid.periodic) + [False] * (3 - grid.dim)
+    for k in range(full[0]):
+        for j in range(full[1]):
+            for i in range(full[2]):
+                r = 0.0
+                for (ci, cj, ck, loc, c), v in op.GetStencil(i, j, k):
+                    if c >= 0:
+                        f = fields[(loc, c)]
+                        f3 = f.reshape((1,) * (3 - f.ndim) + f.shape)
+                        idx = [ck, cj, ci]
+                        for a, d in ((2, 0), (1, 1), (0, 2)):
+                            if per[d]:
+                                idx[a] %= f3.shape[a]
+                        r += v * f3[idx[0], idx[1], idx[2]]
+                    elif c == FD.FLUCAFD_CONSTANT:
+                        r += v
+                    else:
+                        r += v * bc_values[-c - 1]
+                out[k, j, i] = r
+    return out.reshape(shape)
+
+
+def field(grid, loc, seed):
+    return np.random.default_rng(seed).standard_normal(grid.field_shape(loc))
+
+
+def deriv(g, d, order, accu, il, ol):
+    return FD.FlucaFDDerivativeCreate(g, d, order, accu, il, 0, ol, 0)
+
+
+def case_second_derivative_1d(lib):
+    g = FD.FDGrid.uniform([16], [0.0], [2.0], library=lib)
+    op = deriv(g, 0, 2, 2, E, E)
+    bc = [0.0] * 6
+    op.SetBoundaryCondition(0, FD.FLUCAFD_BC_DIRICHLET, 0.7), op.SetBoundaryCondition(1, FD.FLUCAFD_BC_NEUMANN, -1.3)
+    bc[0], bc[1] = 0.7, -1.3
+    return g, op.SetUp(), E, bc
+
+
+def case_laplacian_3d_mixed(lib):
+    g = FD.FDGrid.uniform([10, 9, 8], [0.0, 0.0, 0.0], [1.0, 2.0, 1.5], periodic=[False, False, True], library=lib)
+    ops = [deriv(g, d, 2, 2, E, E).SetUp() for d in range(3)]
+    s = FD.FlucaFDSumCreate(ops)
+    bc = [0.3, 0.0, -0.4, 1.1, 0.0, 0.0]
+    s.SetBoundaryCondition(0, FD.FLUCAFD_BC_DIRICHLET, bc[0]), s.SetBoundaryCondition(2, FD.FLUCAFD_BC_NEUMANN, bc[2]), s.SetBoundaryCondition(3, FD.FLUCAFD_BC_DIRICHLET, bc[3])
+    return g, s.SetUp(), E, bc
+
+
+def case_divergence_of_face_fields(lib):
+    g = FD.FDGrid.uniform([10, 9, 8], [0.0] * 3, [1.0] * 3, library=lib)
+    ops = [deriv(g, d, 1, 2, loc, E).SetUp() for d, loc in enumerate((L, D, B))]
+    return g, FD.FlucaFDSumCreate(ops).SetUp(), E, [0.0] * 6
+
+
+def case_compact_laplacian_2d(lib):
+    g = FD.FDGrid.uniform([12, 10], [0.0, 0.0], [1.0, 1.0], library=lib)
+    inner = deriv(g, 0, 1, 2, E, L).SetUp()
+    outer = deriv(g, 0, 1, 2, L, E).SetUp()
+    comp = FD.FlucaFDCompositionCreate(inner, outer)
+    comp.SetBoundaryCondition(0, FD.FLUCAFD_BC_DIRICHLET, 0.25), comp.SetBoundaryCondition(1, FD.FLUCAFD_BC_NEUMANN, 2.0)
+    sc = FD.FlucaFDScaleCreateConstant(comp.SetUp(), -0.5)
+    sc.SetBoundaryCondition(0, FD.FLUCAFD_BC_DIRICHLET, 0.25), sc.SetBoundaryCondition(1, FD.FLUCAFD_BC_NEUMANN, 2.0)
+    return g, sc.SetUp(), E, [0.25, 2.0, 0, 0, 0, 0]
+
+
+def case_gradient_to_faces_periodic(lib):
+    g = FD.FDGrid.uniform([9, 8], [0.0, 0.0], [3.0, 1.0], periodic=[True, False], library=lib)
+    op = deriv(g, 1, 1, 2, E, D)
+    op.SetBoundaryCondition(2, FD.FLUCAFD_BC_DIRICHLET, 0.5)
+    return g, op.SetUp(), D, [0, 0, 0.5, 0, 0, 0]
+
+
+CASES = [case_second_derivative_1d, case_laplacian_3d_mixed, case_divergence_of_face_fields, case_compact_laplacian_2d, case_gradient_to_faces_periodic]
+
+
+def _check(lib, make):
+    g, op, out_loc, bc = make(lib)
+    order = op.ApplyInputs()
+    fields = {key: field(g, key[0], 10 + n) for n, key in enumerate(order)}
+    got = op.Apply(fields, out_loc)
+    want = reference_apply(op, g, fields, out_loc, bc)
+    assert got.shape == want.shape and np.abs(got - want).max() <= 1e-11 * max(1.0, np.abs(want).max()), (make.__name__, np.abs(got - want).max())
+
+
+@pytest.mark.parametrize("make", CASES, ids=[c.__name__[5:] for c in CASES])
+def test_apply_host_emulation(make):
+    _check(parity.hostemu_library(), make)
+
+
+def test_what_v1_does_not_cover_is_rejected_not_approximated():
+    lib = parity.hostemu_library()
+    g = FD.FDGrid.uniform([8], [0.0], [1.0], library=lib)
+    d = deriv(g, 0, 1, 2, E, E).SetUp()
+    sv = FD.FlucaFDScaleCreateVector(d, np.arange(8.0), E).SetUp()
+    with pytest.raises(FD.FlucaFDError, match="vector scale and TVD"):
+        sv.ApplyInputs()
+    gn = FD.FDGrid([8], [np.linspace(0, 1, 9) ** 1.5], library=lib)
+    with pytest.raises(FD.FlucaFDError, match="uniform product coordinates"):
+        deriv(gn, 0, 1, 2, E, E).SetUp().ApplyInputs()
+    gp = FD.FDGrid.uniform([8], [0.0], [1.0], periodic=[True], stencil_width=1, library=lib)
+    with pytest.raises(FD.FlucaFDError, match="wider than the DMStag stencil width"):
+        deriv(gp, 0, 3, 2, E, E).SetUp().ApplyInputs()
+
+
+def test_product_library_refuses_to_apply_without_a_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = fb._lib.load()
+    g = FD.FDGrid.uniform([8], [0.0], [1.0], library=lib)
+    d = deriv(g, 0, 1, 2, E, E).SetUp()
+    assert d.ApplyInputs() == [(E, 0)]  # planning is host work
+    with pytest.raises(FD.FlucaFDError, match="no CPU fallback"):
+        d.Apply([np.zeros(8)], E)
+
+
+@pytest.mark.gpu
+@pytest.mark.skip(reason="written after this round's GPU budget was spent: not yet run on a B200 (enable first thing next round)")
+@pytest.mark.parametrize("make", CASES, ids=[c.__name__[5:] for c in CASES])
+def test_apply_cuda(make):
+    L_ = fb._lib.load()
+    assert L_.fluca_b200_is_host_emulation() == 0
+    _check(L_, make)
