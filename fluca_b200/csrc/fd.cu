@@ -1,7 +1,8 @@
-// fd.cu -- stencil layer of the FlucaFD operator family behind the C ABI.
+// fd.cu -- the FlucaFD operator family behind the C ABI: the stencil layer (host C++) and, at the end
+// of the file, the matrix-free device apply generated from it.
 //
-// Host-side C++ only (no kernels in this file): what the reference computes in FlucaFDSetUp / FlucaFDGetStencil for its
-// five operator types -- the part every matrix-free device apply of a composed operator is generated from.  Restated from
+// Stencil layer: what the reference computes in FlucaFDSetUp / FlucaFDGetStencil for its five operator types -- the part
+// every matrix-free apply of a composed operator is generated from.  Restated from
 //   fluca/src/fd/interface/fdapply.c:22-45         FlucaFDGetStencilRaw, FlucaFDGetStencil
 //   fluca/src/fd/utils/fdutils.c:56-100            coordinates beyond the local grid, ghost corners, Gaussian elimination
 //   fluca/src/fd/utils/fdutils.c:102-489           stencil accumulation, off-grid removal per boundary condition, zero removal

@@ -5,6 +5,8 @@ golden-pinned stencil layer (tests/test_fd_stencils.py) at EVERY output point, b
 CPU: the host-emulation build of the same sources.  The GPU cases are skipped, not claimed: the kernel was written after this
 round's GPU budget was spent and has not run on a B200 yet; they are the first thing to enable next round.
 (The file sorts last on purpose.)"""
+import os
+
 import numpy as np
 import pytest
 
@@ -138,7 +140,7 @@ def test_product_library_refuses_to_apply_without_a_device():
 
 
 @pytest.mark.gpu
-@pytest.mark.skip(reason="written after this round's GPU budget was spent: not yet run on a B200 (enable first thing next round)")
+@pytest.mark.skipif(not os.environ.get("FLUCA_B200_RUN_UNVERIFIED"), reason="written after this round's GPU budget was spent: not yet run on a B200; FLUCA_B200_RUN_UNVERIFIED=1 runs it (tools/next_round_gpu.sh)")
 @pytest.mark.parametrize("make", CASES, ids=[c.__name__[5:] for c in CASES])
 def test_apply_cuda(make):
     L_ = fb._lib.load()
