@@ -611,8 +611,15 @@ using namespace fluca::fd;
 struct fluca_b200_fd_grid {
   Grid *g;
 };
+namespace fluca {
+namespace fd {
+struct DevicePlan; // tables of the generated apply kernel on the device (end of this file)
+void free_device_plan(DevicePlan *p);
+} // namespace fd
+} // namespace fluca
 struct fluca_b200_fd {
-  Op *op;
+  Op                    *op;
+  fluca::fd::DevicePlan *plan = nullptr; // built at the first apply; dropped when locations or boundary data change
 };
 
 static thread_local std::string g_fd_err;
@@ -637,7 +644,7 @@ static fluca_b200_fd *wrap(Op *o, Grid *g)
 {
   o->g = g;
   ++g->refs;
-  fluca_b200_fd *h = new fluca_b200_fd;
+  fluca_b200_fd *h = new fluca_b200_fd();
   h->op            = o;
   return h;
 }
@@ -781,6 +788,7 @@ extern "C" int fluca_b200_fd_set_locations(fluca_b200_fd *h, int input_loc, int 
   if (!valid_location(input_loc) || !valid_location(output_loc)) throw Error(FL_ERR_ARG, "Invalid stencil location; only ELEMENT, LEFT, DOWN, BACK, and their combinations are allowed");
   h->op->input_loc = input_loc, h->op->input_c = input_c, h->op->output_loc = output_loc, h->op->output_c = output_c;
   h->op->setupcalled = false;
+  free_device_plan(h->plan), h->plan = nullptr;
   FD_END
 }
 extern "C" int fluca_b200_fd_scale_set_vector_location(fluca_b200_fd *h, int vec_loc, int vec_c)
@@ -798,6 +806,7 @@ extern "C" int fluca_b200_fd_set_boundary_condition(fluca_b200_fd *h, int bounda
   if (!h || !h->op || boundary < 0 || boundary > 5) throw Error(FL_ERR_ARG, "bad boundary");
   if (type != FLUCA_B200_FD_BC_NONE && type != FLUCA_B200_FD_BC_DIRICHLET && type != FLUCA_B200_FD_BC_NEUMANN) throw Error(FL_ERR_ARG, "Unsupported boundary condition type");
   h->op->bc_type[boundary] = type, h->op->bc_value[boundary] = value;
+  free_device_plan(h->plan), h->plan = nullptr; // boundary values are folded into the kernel's per-variant constants
   FD_END
 }
 extern "C" int fluca_b200_fd_setup(fluca_b200_fd *h)
@@ -986,62 +995,137 @@ extern "C" int fluca_b200_fd_apply_inputs(fluca_b200_fd *h, int *ninputs, int lo
   FD_END
 }
 
-extern "C" int fluca_b200_fd_apply(fluca_b200_fd *h, int ninputs, const double *const inputs[], double *output)
+namespace fluca {
+namespace fd {
+struct DevicePlan {
+  Exec                ex;
+  Plan                p;
+  ApplyFunctor        f; // table pointers filled in; in[] / out set per launch
+  std::vector<void *> owned;
+};
+void free_device_plan(DevicePlan *dp)
 {
-  FD_BEGIN
-  if (!h || !h->op || !inputs || !output) throw Error(FL_ERR_ARG, "null argument");
+  if (!dp) return;
+  try {
+    dp->ex.sync();
+  } catch (...) {
+  }
+  for (void *d : dp->owned) dev_free(d);
+  dp->ex.destroy();
+  delete dp;
+}
+static DevicePlan *device_plan(fluca_b200_fd *h)
+{
+  if (h->plan) return h->plan;
 #ifndef FLUCA_HOSTEMU
   {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) throw Error(FL_ERR_NODEVICE, "fluca_b200 needs a CUDA device (sm_100a); there is no CPU fallback");
   }
 #endif
-  Op         &op = *h->op;
-  const Grid &g  = *op.g;
-  Plan        p;
-  build_plan(op, p);
-  if (ninputs != p.nslots) throw Error(FL_ERR_ARG, "number of input fields does not match fluca_b200_fd_apply_inputs");
-  Exec ex;
-  ex.init();
-  std::vector<void *> owned;
-  auto up = [&](const void *src, size_t bytes) {
+  std::unique_ptr<DevicePlan> dp(new DevicePlan());
+  build_plan(*h->op, dp->p);
+  dp->ex.init();
+  const Grid &g = *h->op->g;
+  const Plan &p = dp->p;
+  auto        up = [&](const void *src, size_t bytes) {
     void *d = dev_alloc(bytes);
-    owned.push_back(d);
-    copy_h2d(ex, d, src, bytes);
+    dp->owned.push_back(d);
+    copy_h2d(dp->ex, d, src, bytes);
     return d;
   };
+  ApplyFunctor &f = dp->f;
   try {
-    ApplyFunctor f;
     f.dim = g.dim, f.R = p.R;
     for (int d = 0; d < 3; ++d) f.E[d] = p.E[d], f.per[d] = d < g.dim ? g.per[d] : 0, f.ncls[d] = p.ncls[d];
     f.tap_start = (const int *)up(p.tap_start.data(), sizeof(int) * p.tap_start.size());
     f.tap_meta  = (const int *)up(p.tap_meta.data(), sizeof(int) * std::max<size_t>(p.tap_meta.size(), 1));
     f.tap_w     = (const double *)up(p.tap_w.data(), sizeof(double) * std::max<size_t>(p.tap_w.size(), 1));
     f.var_const = (const double *)up(p.var_const.data(), sizeof(double) * p.var_const.size());
-    for (int s = 0; s < MAX_SLOTS; ++s) {
-      f.in[s] = nullptr;
-      for (int d = 0; d < 3; ++d) f.in_ext[s][d] = 1;
+    for (int s2 = 0; s2 < MAX_SLOTS; ++s2) {
+      f.in[s2] = nullptr;
+      for (int d = 0; d < 3; ++d) f.in_ext[s2][d] = 1;
     }
+    for (int s2 = 0; s2 < p.nslots; ++s2) field_extents(g, p.slot_loc[s2], f.in_ext[s2]);
+    f.out = nullptr;
+    dp->ex.sync(); // the tables were staged from this function's host vectors
+  } catch (...) {
+    free_device_plan(dp.release());
+    throw;
+  }
+  h->plan = dp.release();
+  return h->plan;
+}
+} // namespace fd
+} // namespace fluca
+
+// device-resident form: inputs / output are device pointers (compact layout); the launch is asynchronous on the operator's
+// stream (fluca_b200_fd_stream), ordered with nothing else -- the caller synchronises (fluca_b200_fd_sync or its own events)
+extern "C" int fluca_b200_fd_apply_device(fluca_b200_fd *h, int ninputs, const double *const dev_inputs[], double *dev_output)
+{
+  FD_BEGIN
+  if (!h || !h->op || !dev_inputs || !dev_output) throw Error(FL_ERR_ARG, "null argument");
+  DevicePlan *dp = device_plan(h);
+  if (ninputs != dp->p.nslots) throw Error(FL_ERR_ARG, "number of input fields does not match fluca_b200_fd_apply_inputs");
+  ApplyFunctor f = dp->f;
+  for (int s = 0; s < ninputs; ++s) {
+    if (!dev_inputs[s]) throw Error(FL_ERR_ARG, "null input field");
+    f.in[s] = dev_inputs[s];
+  }
+  f.out = dev_output;
+  Box b = {dp->p.E[0], dp->p.E[1], dp->p.E[2]};
+  for_box(dp->ex, b, f);
+  FD_END
+}
+extern "C" int fluca_b200_fd_stream(fluca_b200_fd *h, void **stream)
+{
+  FD_BEGIN
+  if (!h || !h->op || !stream) throw Error(FL_ERR_ARG, "null argument");
+  *stream = (void *)device_plan(h)->ex.stream;
+  FD_END
+}
+extern "C" int fluca_b200_fd_sync(fluca_b200_fd *h)
+{
+  FD_BEGIN
+  if (!h || !h->op) throw Error(FL_ERR_ARG, "null argument");
+  if (h->plan) h->plan->ex.sync();
+  FD_END
+}
+
+extern "C" int fluca_b200_fd_apply(fluca_b200_fd *h, int ninputs, const double *const inputs[], double *output)
+{
+  FD_BEGIN
+  if (!h || !h->op || !inputs || !output) throw Error(FL_ERR_ARG, "null argument");
+  DevicePlan *dp = device_plan(h);
+  const Plan &p  = dp->p;
+  if (ninputs != p.nslots) throw Error(FL_ERR_ARG, "number of input fields does not match fluca_b200_fd_apply_inputs");
+  std::vector<void *> tmp;
+  try {
+    ApplyFunctor f = dp->f;
     for (int s = 0; s < p.nslots; ++s) {
       if (!inputs[s]) throw Error(FL_ERR_ARG, "null input field");
-      field_extents(g, p.slot_loc[s], f.in_ext[s]);
-      f.in[s] = (const double *)up(inputs[s], sizeof(double) * (size_t)f.in_ext[s][0] * f.in_ext[s][1] * f.in_ext[s][2]);
+      const size_t bytes = sizeof(double) * (size_t)f.in_ext[s][0] * f.in_ext[s][1] * f.in_ext[s][2];
+      void        *d     = dev_alloc(bytes);
+      tmp.push_back(d);
+      copy_h2d(dp->ex, d, inputs[s], bytes);
+      f.in[s] = (const double *)d;
     }
     const size_t nout = (size_t)p.E[0] * p.E[1] * p.E[2];
     f.out             = (double *)dev_alloc(sizeof(double) * nout);
-    owned.push_back(f.out);
+    tmp.push_back(f.out);
     Box b = {p.E[0], p.E[1], p.E[2]};
-    for_box(ex, b, f);
-    copy_d2h(ex, output, f.out, sizeof(double) * nout);
-    ex.sync();
+    for_box(dp->ex, b, f);
+    copy_d2h(dp->ex, output, f.out, sizeof(double) * nout);
+    dp->ex.sync();
   } catch (...) {
-    ex.sync();
-    for (void *d : owned) dev_free(d);
-    ex.destroy();
+    try {
+      dp->ex.sync();
+    } catch (...) {
+    }
+    for (void *d : tmp) dev_free(d);
     throw;
   }
-  for (void *d : owned) dev_free(d);
-  ex.destroy();
+  for (void *d : tmp) dev_free(d);
   FD_END
 }
 
@@ -1049,6 +1133,7 @@ extern "C" int fluca_b200_fd_destroy(fluca_b200_fd *h)
 {
   FD_BEGIN
   if (h) {
+    free_device_plan(h->plan);
     unref(h->op);
     delete h;
   }

@@ -114,6 +114,19 @@ class FlucaFD:
         _check(self.L, self.L.fluca_b200_fd_apply(self._h, len(arrs), ptr, out.ctypes.data))
         return out
 
+    def ApplyDevice(self, dev_inputs: Sequence[int], dev_output: int):
+        """device pointers (ints) in ApplyInputs() order; asynchronous on Stream(); Sync() waits"""
+        ptr = (C.c_void_p * max(len(dev_inputs), 1))(*dev_inputs)
+        _check(self.L, self.L.fluca_b200_fd_apply_device(self._h, len(dev_inputs), ptr, dev_output))
+
+    def Stream(self) -> int:
+        st = C.c_void_p()
+        _check(self.L, self.L.fluca_b200_fd_stream(self._h, C.byref(st)))
+        return st.value or 0
+
+    def Sync(self):
+        _check(self.L, self.L.fluca_b200_fd_sync(self._h))
+
     def Destroy(self):
         if getattr(self, "_h", None):
             self.L.fluca_b200_fd_destroy(self._h)

@@ -251,6 +251,12 @@ int fluca_b200_fd_get_stencil(fluca_b200_fd *fd, int i, int j, int k, int *ncols
  * Needs a CUDA device (FLUCA_B200_ERR_NODEVICE otherwise). */
 int fluca_b200_fd_apply_inputs(fluca_b200_fd *fd, int *ninputs, int loc[4], int c[4]);
 int fluca_b200_fd_apply(fluca_b200_fd *fd, int ninputs, const double *const inputs[], double *output);
+/* device-resident form: device pointers, asynchronous launch on the operator's own stream (cudaStream_t through
+ * fluca_b200_fd_stream, for event timing); fluca_b200_fd_sync waits for it.  The kernel's tables are built at the first
+ * apply and rebuilt after set_locations / set_boundary_condition. */
+int fluca_b200_fd_apply_device(fluca_b200_fd *fd, int ninputs, const double *const dev_inputs[], double *dev_output);
+int fluca_b200_fd_stream(fluca_b200_fd *fd, void **stream);
+int fluca_b200_fd_sync(fluca_b200_fd *fd);
 int fluca_b200_fd_destroy(fluca_b200_fd *fd);
 
 #ifdef __cplusplus

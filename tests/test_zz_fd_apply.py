@@ -111,6 +111,27 @@ def test_apply_host_emulation(make):
     _check(parity.hostemu_library(), make)
 
 
+def test_device_resident_form_and_plan_rebuild_host_emulation():
+    """apply_device takes device pointers (host pointers in the test double) and reuses the cached tables; changing a
+    boundary value rebuilds them (the values are folded into the per-variant constants)."""
+    lib = parity.hostemu_library()
+    g, op, out_loc, bc = case_laplacian_3d_mixed(lib)
+    order = op.ApplyInputs()
+    fields = {key: field(g, key[0], 3) for key in order}
+    out = np.zeros(g.field_shape(out_loc))
+    for _ in range(2):
+        op.ApplyDevice([fields[k].ctypes.data for k in order], out.ctypes.data)
+        op.Sync()
+        assert np.abs(out - reference_apply(op, g, fields, out_loc, bc)).max() < 1e-11
+    bc2 = list(bc)
+    bc2[0] = -2.5
+    op.SetBoundaryCondition(0, FD.FLUCAFD_BC_DIRICHLET, bc2[0])
+    want = reference_apply(op, g, fields, out_loc, bc2)
+    op.ApplyDevice([fields[k].ctypes.data for k in order], out.ctypes.data)
+    op.Sync()
+    assert np.abs(out - want).max() < 1e-11 and np.abs(want - reference_apply(op, g, fields, out_loc, bc)).max() > 1e-3
+
+
 def test_what_v1_does_not_cover_is_rejected_not_approximated():
     lib = parity.hostemu_library()
     g = FD.FDGrid.uniform([8], [0.0], [1.0], library=lib)

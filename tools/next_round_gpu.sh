@@ -6,6 +6,7 @@ set -u
 mkdir -p gpurun_out
 # 1. the FlucaFD apply kernel has only run in host emulation
 FLUCA_B200_RUN_UNVERIFIED=1 timeout 120 python -m pytest tests/test_zz_fd_apply.py -m gpu -q --timeout 60 > gpurun_out/next_fd_apply.log 2>&1
+timeout 200 python tools/fd_bench.py --n 512 --reps 20 > gpurun_out/next_fd_bench.json 2> gpurun_out/next_fd_bench.err
 # 2. whole GPU suite (the new files of this round included)
 timeout 400 python -m pytest tests -m gpu -x -q --timeout 120 > gpurun_out/next_gpu_suite.log 2>&1
 # 3. bench with the resident / overlapped end-to-end loop and the Poisson-solve rate; DIAG and ROWSUM variants at 256^3
