@@ -116,7 +116,6 @@ SYMBOLS = [
     "fluca_b200_fd_sum_create",
     "fluca_b200_fd_scale_create_constant",
     "fluca_b200_fd_scale_create_vector",
-    "fluca_b200_fd_scale_set_vector_location",
     "fluca_b200_fd_composition_create",
     "fluca_b200_fd_tvd_create",
     "fluca_b200_fd_tvd_set_limiter",
@@ -192,7 +191,6 @@ def _prototype(L):
     L.fluca_b200_fd_sum_create.argtypes = [C.c_int, C.POINTER(_P), C.POINTER(_P)]
     L.fluca_b200_fd_scale_create_constant.argtypes = [_P, C.c_double, C.POINTER(_P)]
     L.fluca_b200_fd_scale_create_vector.argtypes = [_P, _P, C.c_int, C.c_int, C.POINTER(_P)]
-    L.fluca_b200_fd_scale_set_vector_location.argtypes = [_P, C.c_int, C.c_int]
     L.fluca_b200_fd_composition_create.argtypes = [_P, _P, C.POINTER(_P)]
     L.fluca_b200_fd_tvd_create.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]
     L.fluca_b200_fd_tvd_set_limiter.argtypes = [_P, C.c_char_p]

@@ -699,6 +699,7 @@ extern "C" int fluca_b200_fd_sum_create(int n, fluca_b200_fd *const ops[], fluca
 {
   FD_BEGIN
   if (n < 1 || !ops || !out) throw Error(FL_ERR_ARG, "Number of operands must be positive");
+  for (int q = 0; q < n; ++q) (void)operand_of(ops[q]); // all operands set up (sum.c:120-123) before any reference is taken
   Op  *first = operand_of(ops[0]);
   Sum *s     = new Sum();
   s->input_loc = s->output_loc = first->output_loc, s->input_c = s->output_c = first->output_c;
@@ -789,15 +790,6 @@ extern "C" int fluca_b200_fd_set_locations(fluca_b200_fd *h, int input_loc, int 
   h->op->input_loc = input_loc, h->op->input_c = input_c, h->op->output_loc = output_loc, h->op->output_c = output_c;
   h->op->setupcalled = false;
   free_device_plan(h->plan), h->plan = nullptr;
-  FD_END
-}
-extern "C" int fluca_b200_fd_scale_set_vector_location(fluca_b200_fd *h, int vec_loc, int vec_c)
-{
-  FD_BEGIN
-  Scale *s = h ? dynamic_cast<Scale *>(h->op) : nullptr;
-  if (!s || s->is_constant) throw Error(FL_ERR_ARG, "not a vector scale operator");
-  if (!valid_location(vec_loc)) throw Error(FL_ERR_ARG, "Invalid stencil location");
-  s->vec_loc = vec_loc, s->vec_c = vec_c;
   FD_END
 }
 extern "C" int fluca_b200_fd_set_boundary_condition(fluca_b200_fd *h, int boundary, int type, double value)

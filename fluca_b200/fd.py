@@ -164,10 +164,6 @@ def FlucaFDScaleCreateVector(operand: FlucaFD, field: np.ndarray, vec_loc: int, 
     return _new(operand.grid, operand.L.fluca_b200_fd_scale_create_vector, operand._h, f.ctypes.data, vec_loc, vec_c, keep=[operand])
 
 
-def FlucaFDScaleSetVectorLocation(fd: FlucaFD, vec_loc: int, vec_c: int = 0):
-    _check(fd.L, fd.L.fluca_b200_fd_scale_set_vector_location(fd._h, vec_loc, vec_c))
-
-
 def FlucaFDCompositionCreate(inner: FlucaFD, outer: FlucaFD) -> FlucaFD:  # flucafd.h:86
     return _new(inner.grid, inner.L.fluca_b200_fd_composition_create, inner._h, outer._h, keep=[inner, outer])
 

@@ -234,7 +234,6 @@ int fluca_b200_fd_derivative_create(fluca_b200_fd_grid *grid, int dir, int deriv
 int fluca_b200_fd_sum_create(int n, fluca_b200_fd *const ops[], fluca_b200_fd **out);
 int fluca_b200_fd_scale_create_constant(fluca_b200_fd *operand, double constant, fluca_b200_fd **out);
 int fluca_b200_fd_scale_create_vector(fluca_b200_fd *operand, const double *field, int vec_loc, int vec_c, fluca_b200_fd **out);
-int fluca_b200_fd_scale_set_vector_location(fluca_b200_fd *fd, int vec_loc, int vec_c); /* FlucaFDScaleSetVector's location, -flucafd_vec_loc */
 int fluca_b200_fd_composition_create(fluca_b200_fd *inner, fluca_b200_fd *outer, fluca_b200_fd **out);
 int fluca_b200_fd_tvd_create(fluca_b200_fd_grid *grid, int dir, int input_c, int output_c, fluca_b200_fd **out);
 int fluca_b200_fd_tvd_set_limiter(fluca_b200_fd *fd, const char *name);              /* FlucaFDSecondOrderTVDSetLimiter */
