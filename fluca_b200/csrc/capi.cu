@@ -257,17 +257,18 @@ extern "C" int fluca_b200_stage_state(fluca_b200_solver *h)
   Solver    &s = h->s;
   StateView &w = s.view;
   const Geom &g = s.gh.g;
-  if (!w.v) {
-    w.v = (double *)pinned_alloc(sizeof(double) * ext_count(cell_ext(g)) * s.dim);
-    for (int d = 0; d < s.dim; ++d) w.U[d] = (double *)pinned_alloc(sizeof(double) * ext_count(face_ext(g, d)));
-    w.p     = (double *)pinned_alloc(sizeof(double) * ext_count(cell_ext(g)));
-    w.phalf = (double *)pinned_alloc(sizeof(double) * ext_count(cell_ext(g)));
+  // first use: pinned buffers, the view stream and its two events; every piece is guarded on its own so that a failed
+  // allocation (8.6 GB of pinned memory at 512^3) leaves a state the next call can complete instead of half a view
+  if (!w.v) w.v = (double *)pinned_alloc(sizeof(double) * ext_count(cell_ext(g)) * s.dim);
+  for (int d = 0; d < s.dim; ++d)
+    if (!w.U[d]) w.U[d] = (double *)pinned_alloc(sizeof(double) * ext_count(face_ext(g, d)));
+  if (!w.p) w.p = (double *)pinned_alloc(sizeof(double) * ext_count(cell_ext(g)));
+  if (!w.phalf) w.phalf = (double *)pinned_alloc(sizeof(double) * ext_count(cell_ext(g)));
 #ifndef FLUCA_HOSTEMU
-    FL_CUDA(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
-    FL_CUDA(cudaEventCreateWithFlags(&w.ready, cudaEventDisableTiming));
-    FL_CUDA(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
+  if (!w.stream) FL_CUDA(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+  if (!w.ready) FL_CUDA(cudaEventCreateWithFlags(&w.ready, cudaEventDisableTiming));
+  if (!w.done) FL_CUDA(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
 #endif
-  }
 #ifndef FLUCA_HOSTEMU
   // after everything already submitted on the solver stream (the step that produced this state) ...
   FL_CUDA(cudaEventRecord(w.ready, s.ex.stream));
