@@ -5,7 +5,11 @@ by itself --, marker spacing ~ h, two direct-forcing passes, fractional mode at 
 algorithm in the host-emulation build (CPU; the CUDA kernels are checked against the same definition by tests/test_ibm.py).
 Literature: C_D ~ 1.33-1.38, St ~ 0.164-0.166 (not from the reference).
 
-    python tools/ibm_cylinder_validation.py <cells per unit length> <steps> <history.json>
+    python tools/ibm_cylinder_validation.py <cells per unit length> <steps> <history.json> [marker retraction / h] [half height]
+
+The two optional arguments probe the two effects that raise the drag above the unbounded-domain literature value: markers
+placed on a circle of radius D/2 - retraction * h (the regularised delta makes the body act larger), and symmetry planes at
++- half height instead of BASELINE config 2's +- 8 (blockage).
 """
 import json
 import os
@@ -18,7 +22,9 @@ from tests import cases, parity
 import fluca_b200 as fb
 lib = parity.hostemu_library()
 hinv = int(sys.argv[1]); nsteps = int(sys.argv[2]); out = sys.argv[3]
-n = (32*hinv, 16*hinv)
+retract = float(sys.argv[4]) if len(sys.argv) > 4 else 0.0
+half = float(sys.argv[5]) if len(sys.argv) > 5 else 8.0
+n = (32*hinv, int(2*half*hinv))
 h = 1.0/hinv
 def inflow(dim, t, x):
     shape = np.shape(x[0])
@@ -30,13 +36,13 @@ pout.vectorized = True; pout.time_independent = True
 inl = dict(type=cases.BC_VELOCITY, velocity=inflow, pressure=None)
 outl = dict(type=cases.BC_PRESSURE_OUTLET, velocity=None, pressure=pout)
 sym = dict(type=cases.BC_SYMMETRY, velocity=None, pressure=None)
-case = cases.Case("cylinder2d", n, (-8.0, -8.0), (24.0, 8.0), 1.0, 1.0/100.0, 0.5*h, [inl, outl, sym, sym])
+case = cases.Case("cylinder2d", n, (-8.0, -half), (24.0, half), 1.0, 1.0/100.0, 0.5*h, [inl, outl, sym, sym])
 ns = parity.make_ns(case, lib, "fractional")
 v, U, p = case.initial_state()
 v[0] = 1.0; U[0][...] = 1.0
 parity.set_initial(ns, (v, U, p))
 nm = int(np.ceil(np.pi*1.0/h))  # marker spacing ~ h
-mk = cases.cylinder_markers((0.0, 0.0137), 1.0, nm, h)
+mk = cases.cylinder_markers((0.0, 0.0137), 1.0 - 2.0*retract*h, nm, h)
 fb.NSB200SetMarkers(ns, mk["X"], mk["Ud"], mk["dV"], 4, 2)
 hist = []
 t0 = time.time()
