@@ -5,7 +5,7 @@ by itself --, marker spacing ~ h, two direct-forcing passes, fractional mode at 
 algorithm in the host-emulation build (CPU; the CUDA kernels are checked against the same definition by tests/test_ibm.py).
 Literature: C_D ~ 1.33-1.38, St ~ 0.164-0.166 (not from the reference).
 
-    python tools/ibm_cylinder_validation.py <cells per unit length> <steps> <history.json> [marker retraction / h] [half height]
+    python tools/ibm_cylinder_validation.py <cells per unit length> <steps> <history.json> [marker retraction / h] [half height] [marker count]
 
 The two optional arguments probe the two effects that raise the drag above the unbounded-domain literature value: markers
 placed on a circle of radius D/2 - retraction * h (the regularised delta makes the body act larger), and symmetry planes at
@@ -41,7 +41,7 @@ ns = parity.make_ns(case, lib, "fractional")
 v, U, p = case.initial_state()
 v[0] = 1.0; U[0][...] = 1.0
 parity.set_initial(ns, (v, U, p))
-nm = int(np.ceil(np.pi*1.0/h))  # marker spacing ~ h
+nm = int(sys.argv[6]) if len(sys.argv) > 6 else int(np.ceil(np.pi*1.0/h))  # default: marker spacing ~ h; BASELINE config 2 fixes 1024
 mk = cases.cylinder_markers((0.0, 0.0137), 1.0 - 2.0*retract*h, nm, h)
 fb.NSB200SetMarkers(ns, mk["X"], mk["Ud"], mk["dV"], 4, 2)
 hist = []
