@@ -5,7 +5,7 @@ by itself --, marker spacing ~ h, two direct-forcing passes, fractional mode at 
 algorithm in the host-emulation build (CPU; the CUDA kernels are checked against the same definition by tests/test_ibm.py).
 Literature: C_D ~ 1.33-1.38, St ~ 0.164-0.166 (not from the reference).
 
-    python tools/ibm_cylinder_validation.py <cells per unit length> <steps> <history.json> [marker retraction / h] [half height] [marker count]
+    python tools/ibm_cylinder_validation.py <cells per unit length> <steps> <history.json> [marker retraction / h] [half height] [marker count] [mode] [upstream length]
 
 The two optional arguments probe the two effects that raise the drag above the unbounded-domain literature value: markers
 placed on a circle of radius D/2 - retraction * h (the regularised delta makes the body act larger), and symmetry planes at
@@ -24,7 +24,9 @@ lib = parity.hostemu_library()
 hinv = int(sys.argv[1]); nsteps = int(sys.argv[2]); out = sys.argv[3]
 retract = float(sys.argv[4]) if len(sys.argv) > 4 else 0.0
 half = float(sys.argv[5]) if len(sys.argv) > 5 else 8.0
-n = (32*hinv, int(2*half*hinv))
+mode = sys.argv[7] if len(sys.argv) > 7 else "fractional"
+upstream = float(sys.argv[8]) if len(sys.argv) > 8 else 8.0
+n = (int((upstream + 24.0)*hinv), int(2*half*hinv))
 h = 1.0/hinv
 def inflow(dim, t, x):
     shape = np.shape(x[0])
@@ -36,12 +38,12 @@ pout.vectorized = True; pout.time_independent = True
 inl = dict(type=cases.BC_VELOCITY, velocity=inflow, pressure=None)
 outl = dict(type=cases.BC_PRESSURE_OUTLET, velocity=None, pressure=pout)
 sym = dict(type=cases.BC_SYMMETRY, velocity=None, pressure=None)
-case = cases.Case("cylinder2d", n, (-8.0, -half), (24.0, half), 1.0, 1.0/100.0, 0.5*h, [inl, outl, sym, sym])
-ns = parity.make_ns(case, lib, "fractional")
+case = cases.Case("cylinder2d", n, (-upstream, -half), (24.0, half), 1.0, 1.0/100.0, 0.5*h, [inl, outl, sym, sym])
+ns = parity.make_ns(case, lib, mode)
 v, U, p = case.initial_state()
 v[0] = 1.0; U[0][...] = 1.0
 parity.set_initial(ns, (v, U, p))
-nm = int(sys.argv[6]) if len(sys.argv) > 6 else int(np.ceil(np.pi*1.0/h))  # default: marker spacing ~ h; BASELINE config 2 fixes 1024
+nm = int(sys.argv[6]) if len(sys.argv) > 6 and int(sys.argv[6]) > 0 else int(np.ceil(np.pi*1.0/h))  # default: marker spacing ~ h; BASELINE config 2 fixes 1024
 mk = cases.cylinder_markers((0.0, 0.0137), 1.0 - 2.0*retract*h, nm, h)
 fb.NSB200SetMarkers(ns, mk["X"], mk["Ud"], mk["dV"], 4, 2)
 hist = []
