@@ -5,6 +5,9 @@
   python bench.py --impl reference --gpus N --steps K --warmup W   (reference arm: CPU restatement)
 
 One "step" = one full NS time step (NSStep) of the configured workload.  Prints ONE JSON line.
+Workload: BASELINE config 4 (3-D sphere by IBM, 512^3, 100k markers).  At N > 1 the headline `value` is STRONG scaling of
+that one grid (what config 4 names: "512^3 grid ... at 1/2/4/8 GPUs"), and the same line carries the weak-scaling run
+(512^3 per GPU) under "weak".  Before anything is timed an N-rank parity case is run against the CPU oracle ("parity").
 See DESIGN.md section "Measurement" for every definition used here.
 """
 from __future__ import annotations
@@ -33,10 +36,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="sphere", choices=["sphere", "cavity"], help="sphere: BASELINE config 4 (3-D IBM sphere Re=300, 512^3, 100k markers), the configuration the metric is quoted on; cavity: config 3 (256^3 lid-driven cavity, no IBM)")
-    ap.add_argument("--n", type=int, default=0, help="cells per direction per GPU (default: 512 sphere, 256 cavity)")
+    ap.add_argument("--workload", default="sphere", choices=["sphere", "cavity", "channel"], help="sphere: BASELINE config 4 (3-D IBM sphere Re=300, 512^3, 100k markers), the configuration the metric is quoted on; cavity: config 3 (256^3 lid-driven cavity, no IBM); channel: config 5 (multi-body channel, periodic x, 2048x1024x1024 on 8 GPUs = 268 M cells per GPU, 1 M markers; weak scaling)")
+    ap.add_argument("--n", type=int, default=0, help="cells per direction (default: 512 sphere, 256 cavity; channel: cells in y and z, x = 2 n)")
     ap.add_argument("--markers", type=int, default=100000)
-    ap.add_argument("--strong", action="store_true", help="strong scaling: the n^3 grid is split over the GPUs (default: weak, n^3 per GPU)")
+    ap.add_argument("--scaling", default="both", choices=["both", "strong", "weak"], help="N > 1: strong (the one n^3 grid split in z-slabs; the headline), weak (n^3 per GPU), or both (default)")
+    ap.add_argument("--strong", action="store_true", help="same as --scaling strong")
     ap.add_argument("--mode", default="coupled", choices=["coupled", "fractional"])
     ap.add_argument("--restart", type=int, default=0, help="outer GMRES restart (memory: (restart+1) x 7 fields; default 3 at 512^3, 10 below; the flexible form also keeps restart x 7 fields of preconditioned vectors)")
     ap.add_argument("--schur-ainv", default="ID", choices=["ID", "DIAG", "ROWSUM"], help="-ns_pc_abf_schur_ainv_type (abfpc.c:246); the headline numbers use the reference default ID")
@@ -44,64 +48,64 @@ def parse():
     ap.add_argument("--cpu-n", type=int, default=64, help="cells per direction of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed N-rank parity case against the oracle")
+    a = ap.parse_args()
+    if a.strong:
+        a.scaling = "strong"
+    return a
 
 
 # ---------------------------------------------------------------------------------------------- workload
-def cavity_case(n, nz, Re=400.0):
-    """BASELINE config 3: 3-D lid-driven cavity Re=400 on the unit cube, uniform h = 1/n, dt = 0.5 h,
-    zero initial state.  For the weak-scaling runs the box is extended in z (nz = n * N
-    cells, length N) so that every GPU keeps an n^3 slab."""
-    from tests import cases
-
-    c = cases.cavity3d_full(n=(n, n, nz), Re=Re, dt=0.5 / n)
-    c.hi = (1.0, 1.0, float(nz) / n)
-    return c
-
-
-def sphere_case(n, nz, Re=300.0):
-    """BASELINE config 4: flow past a sphere (D = 1 at the origin, U_inf = 1) by the immersed-boundary coupling on
-    [-4,12] x [-8,8]^2 with n^3 cells (h = 16/n; 512^3 -> h = 1/32), inflow LEFT, pressure outlet RIGHT (p = 0), symmetry on
-    the four side boundaries, dt = 0.5 h (CFL 0.5), initial state uniform U_inf.  Weak scaling extends the
-    box in z (nz = n * N cells) so that every GPU keeps an n^3 slab; the sphere stays at the origin."""
-    from tests import cases
-
-    c = cases.channel3d(n=(n, n, nz), Re=Re, dt=0.5 * 16.0 / n)
-    c.lo, c.hi = (-4.0, -8.0, -8.0), (12.0, 8.0, -8.0 + 16.0 * nz / n)
-    for b in c.bcs:  # constant boundary data, evaluated once per plane
-        for k in ("velocity", "pressure"):
-            if b[k] is not None:
-                b[k] = cases._const(1.0, 0.0, 0.0) if k == "velocity" else cases._constp(0.0)
-    return c
+def default_n(args):
+    return args.n or {"sphere": 512, "cavity": 256, "channel": 1024}[args.workload]
 
 
 def make_case(args, n, nz):
-    return sphere_case(n, nz) if args.workload == "sphere" else cavity_case(n, nz)
+    """n: cells in x and y (channel: y and z-per-unit), nz: global cells in z."""
+    from fluca_b200 import workloads as W
 
-
-def markers_for(args, n):
-    from tests import cases
-
-    if args.workload != "sphere":
-        return None
-    return cases.sphere_markers((0.0, 0.0, 0.0), 1.0, args.markers, 16.0 / n)
-
-
-def uniform_inflow_state(case):
-    cell, face = case.shapes()
-    v = np.zeros((3,) + cell)
-    v[0] = 1.0
-    U = [np.zeros(s) for s in face]
-    U[0][...] = 1.0
-    return v, U, np.zeros(cell)
-
-
-def workload_text(args, n, nzg, restart):
     if args.workload == "sphere":
-        return (f"BASELINE config 4: 3-D flow past a sphere by IBM, Re=300, {n}x{n}x{nzg} cells ({'z-slabs of the one grid' if getattr(args, 'strong', False) else f'{n}^3 per GPU, z-slabs'}), h=16/{n}, {args.markers} Fibonacci markers, 4-point delta, "
-                f"inflow/pressure-outlet/symmetry, dt=0.5h, uniform initial state, NS type b200 mode={args.mode}, reference default tolerances (outer/momentum/Schur rtol 1e-5; inner tolerances relaxed by the inexact-Krylov rule as the outer residual drops, DESIGN.md 5), flexible GMRES restart {restart}")
-    return (f"BASELINE config 3: 3-D lid-driven cavity Re=400, {n}x{n}x{nzg} cells ({n}^3 per GPU, z-slabs), dt=0.5h, zero initial state, NS type b200 mode={args.mode}, "
-            f"reference default tolerances (outer/momentum/Schur rtol 1e-5; inner tolerances relaxed by the inexact-Krylov rule, DESIGN.md 5), flexible GMRES restart {restart}")
+        return W.sphere_bench_case(n, nz)
+    if args.workload == "cavity":
+        return W.cavity_bench_case(n, nz)
+    # config 5: 2048 x 1024 x 1024 on 8 GPUs (h = 1/64); the slab direction z carries the GPUs.  The x extent is 2 n.
+    return W.channel_bench_case((2 * n, n, nz))
+
+
+def markers_for(args, case, n, nz):
+    from fluca_b200 import workloads as W
+
+    if args.workload == "sphere":
+        return W.sphere_markers((0.0, 0.0, 0.0), 1.0, args.markers, 16.0 / n)
+    if args.workload == "channel":
+        # 80 spheres x 12 500 markers at full size (1.0 M); the count scales with the volume of the box that is run
+        h = case.hi[0] / case.n[0]
+        full = 2048.0 * 1024 * 1024
+        nsph = max(1, int(round(80 * (case.n[0] * case.n[1] * case.n[2]) / full)))
+        centres = W.channel_sphere_centres(case.lo, case.hi, nsph)
+        return W.multi_sphere_markers(centres, 1.0, 12500, h)
+    return None
+
+
+def set_initial_state(args, case, solver):
+    """Uniform stream for the external flows (zero state for the cavity), written slab by slab: every rank only ever
+    allocates its own planes on the host."""
+    from fluca_b200 import workloads as W
+
+    if args.workload in ("sphere", "channel"):
+        v, U, p = W.uniform_inflow_state(case, slab=(solver.k0, solver.nzl, solver.last_z))
+        solver.set_state(v=v, U=U, p=p, phalf=p)
+
+
+def workload_text(args, case, scaling, world, restart, nmark):
+    nx, ny, nz = case.n
+    tol = f"NS type b200 mode={args.mode}, reference default tolerances (outer/momentum/Schur rtol 1e-5; inner tolerances relaxed by the inexact-Krylov rule as the outer residual drops, DESIGN.md 5), flexible GMRES restart {restart}"
+    part = "one GPU" if world == 1 else (f"STRONG scaling: the one grid in {world} z-slabs of {nz // world} planes" if scaling == "strong" else f"WEAK scaling: {nz // world} planes ({nx}x{ny}x{nz // world} cells) per GPU, {world} z-slabs")
+    if args.workload == "sphere":
+        return f"BASELINE config 4: 3-D flow past a sphere by IBM, Re=300, {nx}x{ny}x{nz} cells, {part}, h=16/{nx}, {nmark} Fibonacci markers, 4-point delta, inflow/pressure-outlet/symmetry, dt=0.5h, uniform initial state, {tol}"
+    if args.workload == "channel":
+        return f"BASELINE config 5: 3-D multi-body channel by IBM, {nx}x{ny}x{nz} cells, {part}, h=32/{nx}, periodic x and z, no-slip walls in y, {nmark} markers on spheres of D=1 (12500 Fibonacci markers each), bulk velocity 1, dt=0.5h, {tol}"
+    return f"BASELINE config 3: 3-D lid-driven cavity Re=400, {nx}x{ny}x{nz} cells, {part}, dt=0.5h, zero initial state, {tol}"
 
 
 # ---------------------------------------------------------------------------------------------- clocks
@@ -145,21 +149,211 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
-def poisson_solve_rate(ktimes, schur_its, cells_rank, outlet, variant, peak):
-    """Algorithmic HBM rate of the pressure solves of the timed region: iterations x bytes per iteration and cell (3-D: PCG +
-    V(2,2) cycle = 227 B; BiCGStab with a pressure outlet or a DIAG / ROWSUM Schur complement = two applies + two V-cycles,
-    2 x 227 resp. 2 x (227 - 16 + 104) B -- the model of fluca_b200_step_model_bytes) over the event-timed duration of the
-    four kernel classes that make up the solve.  None if nothing was timed."""
-    try:
-        t_ms = sum(float(ktimes[k][0]) for k in ("poisson_apply", "poisson_vec", "mg_smooth", "mg_transfer") if k in ktimes)
-        its = int(sum(schur_its))
-        if t_ms <= 0.0 or its <= 0:
+def reference_build_probe():
+    """a PETSc build of the reference may be provided on the GPU box; it never was."""
+    petsc = os.environ.get("PETSC_DIR")
+    ref = os.path.isdir(os.path.join(ROOT, "baseline", "_ref")) or os.path.isdir(os.path.join(ROOT, "oracle", "_ref"))
+    if petsc or ref:
+        return f"present (PETSC_DIR={petsc!r}, _ref dir={ref}) but not used: no build recipe for the reference exists in this repo (it needs MPI, HDF5 and parallel CGNS as well)"
+    return "absent (no $PETSC_DIR, no baseline/_ref, no oracle/_ref): the reference needs PETSc >= 3.23 + MPI + HDF5 + CGNS; the CPU arm is the repo's C restatement (oracle/, kind 'port')"
+
+
+def cpu_sample(args, n, steps, warmup, mode):
+    """The CPU restatement of the reference algorithm (oracle, kind "port": assembled CSR operators, GMRES(30) + block-Jacobi
+    ILU(0), reference default tolerances) on an n^3 sample of the sphere / cavity workload, on all host threads.  The thread
+    count is forced through OpenMP's API (a launcher such as torchrun pre-sets OMP_NUM_THREADS=1) and what a parallel
+    region actually gets is what is reported."""
+    want = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(want)
+    from oracle import oracle as O
+    from tests import cases
+
+    threads = O.set_threads(want)
+    sub = argparse.Namespace(**vars(args))
+    if sub.workload == "channel":
+        sub.workload = "sphere"
+    case = make_case(sub, n, n)
+    orc = cases.make_oracle_fast(case)
+    nm = 0
+    if sub.workload == "sphere":
+        orc.set_state(*cases.uniform_inflow_state(case))
+        nm = max(64, int(args.markers * (n / 512.0) ** 2))
+        mk = cases.sphere_markers((0.0, 0.0, 0.0), 1.0, nm, 16.0 / n)
+        orc.set_markers(mk["X"], mk["Ud"], mk["dV"], 4)
+    else:
+        orc.set_state(*case.initial_state())
+    ainv = {"ID": 0, "DIAG": 1, "ROWSUM": 2}
+    opt = O.default_options(mode=0 if mode == "coupled" else 1, ilu_blocks=threads, schur_ainv=ainv[args.schur_ainv], upper_ainv=ainv[args.upper_ainv])
+    infos = []
+    for _ in range(warmup):
+        orc.step(opt)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        infos.append(orc.step(opt))
+    dt = time.perf_counter() - t0
+    cells = float(n) ** 3
+    return dict(value=cells * steps / dt / 1e6, seconds=dt, steps=steps, warmup=warmup, n=n, threads=threads, markers=nm, outer=[i.outer_its for i in infos], mom=[i.mom_its for i in infos], schur=[i.schur_its for i in infos])
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.cpu_n
+    r = cpu_sample(args, n, args.steps, args.warmup, args.mode)
+    sub = argparse.Namespace(**vars(args))
+    full = default_n(args)
+    case = make_case(sub, full, full if args.workload != "channel" else full)
+    line = {
+        "impl": "reference",
+        "metric": "Mcell-updates/s per NS step",
+        "value": r["value"],
+        "unit": "Mcell-updates/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": r["warmup"],
+        "ms_per_step": 1e3 * r["seconds"] / r["steps"],
+        "higher_is_better": True,
+        "scaling": "strong" if args.scaling != "weak" and args.workload != "channel" else "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_text(args, case, "strong", 1, args.restart or 3, args.markers) + f"; CPU arm: bounded sample {n}^3 of the same case ({r['markers']} markers: scaled with the surface cell count)", "mode": args.mode},
+        "cpu_baseline": {"value": r["value"], "unit": "Mcell-updates/s", "cores": r["threads"], "kind": "port", "sample": f"{n}^3 sample of the workload, {r['warmup']} warm-up + {r['steps']} timed steps on {r['threads']} OpenMP threads (of {os.cpu_count()} host CPUs), outer its {r['outer']}, momentum its {r['mom']}, Schur its {r['schur']}", "reference_build": reference_build_probe()},
+        "e2e": {"value": r["value"], "unit": "Mcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print_json(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+class Ctx:
+    """torch / torch.distributed plumbing of one rank."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def comm(self):
+        """NS communicator description: every solver gets its own NCCL communicator (a fresh unique id from rank 0)."""
+        if self.world == 1:
             return None
-        per_iter = 2.0 * (227.0 - 16.0 + 104.0) if variant else (2.0 * 227.0 if outlet else 227.0)
-        ach = its * per_iter * cells_rank / (t_ms * 1e-3) / 1e9
-        return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "iterations": its, "bytes_per_iteration_per_cell": per_iter, "ms": t_ms, "krylov": "bicgstab+mg" if (variant or outlet) else "pcg+mg"}
-    except Exception:  # a reporting extra must never cost the bench line
+        import fluca_b200 as fb
+
+        torch, dist, rank, world, dev = self.torch, self.dist, self.rank, self.world, self.dev
+
+        def factory(L):
+            if rank == 0:
+                tid = torch.from_numpy(np.frombuffer(fb.Comm.unique_id(L), dtype=np.uint8).copy()).to(dev)
+            else:
+                tid = torch.zeros(128, dtype=torch.uint8, device=dev)
+            dist.broadcast(tid, 0)
+            return fb.Comm.nccl(L, tid.cpu().numpy().tobytes(), rank, world)
+
+        return dict(rank=rank, nranks=world, make_comm=factory)
+
+    def stream_timer(self, solver):
+        """(start, stop) around the timed region: CUDA events on the solver's own stream; stop() returns milliseconds."""
+        torch = self.torch
+        stream = torch.cuda.ExternalStream(solver.stream(), device=self.dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def start():
+            e0.record(stream)
+
+        def stop():
+            e1.record(stream)
+            e1.synchronize()
+            return e0.elapsed_time(e1)
+
+        return start, stop
+
+    def pinned(self, shape):
+        return self.torch.empty(shape, dtype=self.torch.float64).pin_memory().numpy()
+
+    def gather_z(self, arrs, axis):
+        """rank 0 gets the z-concatenation of every rank's slab (small arrays only)."""
+        if self.world == 1:
+            return arrs
+        out = [None] * self.world if self.rank == 0 else None
+        self.dist.gather_object(arrs, out, dst=0)
+        return np.concatenate(out, axis=axis) if self.rank == 0 else None
+
+
+def parity_selfcheck(ctx, lib):
+    """Untimed N-rank correctness of what is about to be timed: the sphere workload builder (inflow / outlet / symmetry /
+    immersed boundary), coupled mode, tight tolerances, on the NCCL slab partition of this run, against the CPU oracle on
+    rank 0 (the oracle is the checker here, never the thing measured).  Two steps with the reference-default ABF factors
+    and one step with the DIAG / ROWSUM variants."""
+    import fluca_b200 as fb
+    from fluca_b200 import workloads as W
+
+    world, rank = ctx.world, ctx.rank
+    nx, ny, nz = 32, 16, max(16, 8 * world)
+    case = W.sphere_bench_case(ny, nz)
+    case.n, case.dt = (nx, ny, nz), 0.5 * 16.0 / nx
+    case.hi = (12.0, 8.0, 8.0)  # the same box whatever the rank count: z in [-8, 8]
+    mk = W.sphere_markers((0.0, 0.0, 0.0), 1.2, 300, 16.0 / ny)
+    state = W.uniform_inflow_state(case)
+    tight = {"ns_ksp_rtol": 1e-13, "ns_abf_momentum_ksp_rtol": 1e-13, "ns_abf_schur_ksp_rtol": 1e-13, "ns_ksp_max_it": 60}
+    runs = (("ID/ID", "ID", "ID", 2), ("DIAG/ROWSUM", "DIAG", "ROWSUM", 1))
+    got = {}
+    for label, sa, ua, nsteps in runs:
+        ns = W.make_ns(case, lib, "coupled", comm=ctx.comm(), ns_pc_abf_schur_ainv_type=sa, ns_pc_abf_upper_ainv_type=ua, **tight)
+        W.set_initial_slab(ns, state)
+        fb.NSB200SetMarkers(ns, mk["X"], mk["Ud"], mk["dV"], 4)
+        outer = []
+        for _ in range(nsteps):
+            fb.NSStep(ns)
+            outer.append(fb.NSB200GetStats(ns).outer_its)
+        st = fb.NSB200GetSolver(ns).get_state()
+        g = dict(v=ctx.gather_z(st["v"], 1), p=ctx.gather_z(st["p"], 0), U=[ctx.gather_z(u, 0) for u in st["U"]], outer=outer)
+        fb.NSDestroy(ns)
+        got[label] = g
+    if rank != 0:
         return None
+    from oracle import oracle as O  # checker
+    from tests import cases
+
+    O.set_threads(os.cpu_count() or 1)
+
+    def rel(a, b):
+        return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300))
+
+    res, ok, tol = {}, True, 1e-10
+    for label, sa, ua, nsteps in runs:
+        orc = cases.make_oracle_fast(case)
+        orc.set_state(*state)
+        orc.set_markers(mk["X"], mk["Ud"], mk["dV"], 4)
+        opt = O.default_options(mode=0, outer_rtol=1e-13, mom_rtol=1e-13, schur_rtol=1e-13, schur_ainv={"ID": 0, "DIAG": 1, "ROWSUM": 2}[sa], upper_ainv={"ID": 0, "DIAG": 1, "ROWSUM": 2}[ua])
+        oo = [orc.step(opt).outer_its for _ in range(nsteps)]
+        a, g = orc.get_state(), got[label]
+        eU = float(np.sqrt(sum(np.sum((x - y) ** 2) for x, y in zip(g["U"], a["U"]))) / np.sqrt(sum(np.sum(y**2) for y in a["U"])))
+        e = dict(v=rel(g["v"], a["v"]), U=eU, p=rel(g["p"], a["p"]), steps=nsteps, outer_its_gpu=g["outer"], outer_its_oracle=oo)
+        ok = ok and e["v"] <= tol and e["U"] <= tol and e["p"] <= 10 * tol
+        res[label] = e
+    return {"ok": bool(ok), "ranks": world, "tolerance": "rel. L2 <= 1e-10 (v, U), 1e-9 (p) against the CPU oracle at tight tolerances", "case": f"sphere workload builder at {nx}x{ny}x{nz} (inflow/outlet/symmetry, 300 IBM markers), coupled mode, {world} z-slab(s) over {'NCCL' if world > 1 else 'one GPU'}; ABF factor variants schur/upper", "runs": res, "oracle": "parity unpinned: the oracle is this repo's restatement (DESIGN.md 2)"}
 
 
 def e2e_resident_loop(ns, solver, ksteps, barrier, clock):
@@ -188,221 +382,133 @@ def e2e_resident_loop(ns, solver, ksteps, barrier, clock):
     return clock() - t0, nbytes, acc
 
 
-def cpu_sample(args, n, steps, warmup, mode, threads):
-    """The CPU restatement of the reference algorithm (oracle, kind "port": assembled CSR operators,
-    GMRES(30) + block-Jacobi ILU(0), reference default tolerances) on an n^3 sample of the workload, all host threads."""
-    from oracle import oracle as O
-    from tests import cases
-
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
-    case = make_case(args, n, n)
-    orc = cases.make_oracle_fast(case)
-    if args.workload == "sphere":
-        orc.set_state(*uniform_inflow_state(case))
-        mk = cases.sphere_markers((0.0, 0.0, 0.0), 1.0, max(64, int(args.markers * (n / 512.0) ** 2)), 16.0 / n)
-        orc.set_markers(mk["X"], mk["Ud"], mk["dV"], 4)
-    else:
-        orc.set_state(*case.initial_state())
-    ainv = {"ID": 0, "DIAG": 1, "ROWSUM": 2}
-    opt = O.default_options(mode=0 if mode == "coupled" else 1, ilu_blocks=threads, schur_ainv=ainv[args.schur_ainv], upper_ainv=ainv[args.upper_ainv])
-    infos = []
-    for _ in range(warmup):
-        orc.step(opt)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        infos.append(orc.step(opt))
-    dt = time.perf_counter() - t0
-    cells = float(n) ** 3
-    return dict(value=cells * steps / dt / 1e6, seconds=dt, steps=steps, n=n, outer=[i.outer_its for i in infos], mom=[i.mom_its for i in infos], schur=[i.schur_its for i in infos])
+def load_peaks():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        peaks = {}
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    src = "measured copy bandwidth (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    return peak, src
 
 
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    threads = os.cpu_count() or 1
-    n = args.cpu_n
-    r = cpu_sample(args, n, args.steps, min(args.warmup, 1), args.mode, threads)
-    line = {
-        "impl": "reference",
-        "metric": "Mcell-updates/s per NS step",
-        "value": r["value"],
-        "unit": "Mcell-updates/s",
-        "n_gpus": args.gpus,
-        "steps": args.steps,
-        "warmup": min(args.warmup, 1),
-        "ms_per_step": 1e3 * r["seconds"] / r["steps"],
-        "higher_is_better": True,
-        "scaling": "weak",
-        "vs_baseline": None,
-        "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": workload_text(args, args.n or (512 if args.workload == "sphere" else 256), (args.n or (512 if args.workload == "sphere" else 256)) * args.gpus, args.restart or 3) + f"; CPU arm: bounded sample {n}^3 of the same case (markers scaled with the surface cell count)", "mode": args.mode},
-        "cpu_baseline": {"value": r["value"], "unit": "Mcell-updates/s", "cores": threads, "kind": "port", "sample": f"{n}^3 sample of the workload, {r['steps']} steps, outer its {r['outer']}, momentum its {r['mom']}, Schur its {r['schur']}; the reference (PETSc) cannot be built in this image, this is the repo's C restatement (oracle/)"},
-        "e2e": {"value": r["value"], "unit": "Mcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    print_json(json.dumps(line))
-
-
-# ---------------------------------------------------------------------------------------------- GPU arm
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
-
+def measure(ctx, lib, args, scaling, with_e2e):
+    """Builds the workload on this run's ranks, warms up, times K steps device-resident, and (optionally) end to end."""
     import fluca_b200 as fb
-    from tests import parity
+    from fluca_b200 import workloads as W
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    lib = fb._lib.load()  # CUDA library or a loud failure: there is no fallback
-    comm = None
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-        # rank 0 makes the NCCL unique id of the solver's own communicator and ships it with torch.distributed
-        if rank == 0:
-            uid = np.frombuffer(fb.Comm.unique_id(lib), dtype=np.uint8).copy()
-            tid = torch.from_numpy(uid).to(dev)
-        else:
-            tid = torch.zeros(128, dtype=torch.uint8, device=dev)
-        dist.broadcast(tid, 0)
-        uid_bytes = tid.cpu().numpy().tobytes()
-        comm = dict(rank=rank, nranks=world, make_comm=lambda L: fb.Comm.nccl(L, uid_bytes, rank, world))
-
-    n = args.n or (512 if args.workload == "sphere" else 256)
-    nzg = n if args.strong else n * world  # weak scaling (default): an n^3 slab per GPU; strong: n / N planes per GPU
-    restart = args.restart or (3 if n >= 512 else 10)
+    world, rank = ctx.world, ctx.rank
+    n = default_n(args)
+    nzg = n if scaling == "strong" else n * world
+    if args.workload == "channel":
+        nzg = n * world // 8 if scaling == "weak" else n  # config 5: 2048 x 1024 x 1024 on 8 GPUs = 128 z-planes per GPU
+        nzg = max(nzg, 8 * world)
+    big = (float(n) ** 2 * nzg / world) * (2 if args.workload == "channel" else 1) >= 100e6
+    restart = args.restart or (3 if big else 10)
     case = make_case(args, n, nzg)
     opts = {"ns_ksp_gmres_restart": restart, "ns_pc_abf_schur_ainv_type": args.schur_ainv, "ns_pc_abf_upper_ainv_type": args.upper_ainv}
-    ns = parity.make_ns(case, lib, args.mode, comm=comm, **opts)
+    ns = W.make_ns(case, lib, args.mode, comm=ctx.comm(), **opts)
     s = fb.NSB200GetSolver(ns)
-    cells_total = float(n) * n * nzg
-    if args.workload == "sphere":
-        v0_, U0_, p0_ = uniform_inflow_state(case)
-        k0_, nzl_ = s.k0, s.nzl
-        s.set_state(v=v0_[:, k0_ : k0_ + nzl_], U=[U0_[0][k0_ : k0_ + nzl_], U0_[1][k0_ : k0_ + nzl_], U0_[2][k0_ : k0_ + nzl_ + (1 if s.last_z else 0)]], p=p0_[k0_ : k0_ + nzl_], phalf=p0_[k0_ : k0_ + nzl_])
-        del v0_, U0_, p0_
-        mk = markers_for(args, n)
+    cells_total = float(case.n[0]) * case.n[1] * case.n[2]
+    cells_rank = float(case.n[0]) * case.n[1] * s.nzl
+    set_initial_state(args, case, s)
+    mk = markers_for(args, case, n, nzg)
+    nmark = 0
+    if mk is not None:
         fb.NSB200SetMarkers(ns, mk["X"], mk["Ud"], mk["dV"], 4)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        nmark = int(mk["dV"].shape[0])
 
     # ---- device-resident throughput ("value"): state lives in HBM, nothing crosses PCIe in the timed region
-    stream = torch.cuda.ExternalStream(s.stream(), device=dev)
     for _ in range(args.warmup):
         fb.NSStep(ns)
-    barrier()
-    sampler = ClockSampler(local)
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local)
     if rank == 0:
         sampler.start()
     s.kernel_times(reset=True)
     s.kernel_timing(True)
     l0 = s.launch_count()
     stats = []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    with torch.cuda.stream(stream):
-        e0.record(stream)
-        for _ in range(args.steps):
-            fb.NSStep(ns)
-            stats.append(fb.NSB200GetStats(ns))
-        e1.record(stream)
-    e1.synchronize()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    start, stop = ctx.stream_timer(s)
+    ctx.barrier()
+    start()
+    for _ in range(args.steps):
+        fb.NSStep(ns)
+        stats.append(fb.NSB200GetStats(ns))
+    ms = stop()
+    ctx.barrier()
+    ms = ctx.max_over_ranks(ms)
     launches = s.launch_count() - l0
     ktimes = s.kernel_times(reset=True)
     s.kernel_timing(False)
     clocks = sampler.stop() if rank == 0 else None
-    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms = float(tms.item())
     value = cells_total * args.steps / (ms * 1e-3) / 1e6
 
-    # ---- roofline of the dominant kernel class (live CUDA-event pairs around every launch in the timed region)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    cells_rank = float(n) * n * (nzg / world)
-    d3 = True
-    # algorithmic bytes per launch and cell (DESIGN.md "Kernels"): A apply + 2 dots reads x(3) v0(3) U0(3) a(3) writes y(3)
-    # momentum apply fused with two dots: reads x(3) v0(3) U0(3) (+ rhat(3) in the first of the two applies of a
-    # BiCGStab iteration), writes y(3): (120 + 96) / 2 = 108 B per cell and launch on average (DESIGN.md)
-    per_launch = {"momentum_apply": 108.0, "poisson_apply": 16.0}
-    if args.schur_ainv != "ID":
-        # DIAG / ROWSUM Schur complement = two launches per apply: w = (1 - a1) G0 p reads p, a1(3) writes w(3) = 56 B;
-        # out = P p + vol D T w reads p, w(3), a writes out = 48 B; mean 52 B per cell and launch (DESIGN.md)
-        per_launch["poisson_apply"] = 52.0
-    shares = {k: v[0] / ms for k, v in ktimes.items() if v[1] > 0}
+    # ---- rooflines (live CUDA-event pairs around every launch of the timed region; this rank's kernels)
+    peak, peak_src = load_peaks()
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
         traffic = {}
     roof = None
-    for name in ("momentum_apply", "poisson_apply"):
-        t, cnt = ktimes[name]
-        if cnt:
-            ach = per_launch[name] * cells_rank * cnt / (t * 1e-3) / 1e9
-            r = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": (traffic[name]["bytes_per_cell"] * cells_rank / 1e9 if name in traffic else None), "traffic_unit": "GB per launch (ncu dram bytes per cell of the committed capture x cells of this launch)", "traffic_source": traffic.get(name, {}).get("capture"), "algorithmic_GB_per_launch": per_launch[name] * cells_rank / 1e9, "launches": cnt, "avg_ms": t / cnt, "share_of_step": t / ms, "peak_source": peak_src}
-            if roof is None or t > roof["_t"]:
-                roof = dict(r, _t=t)
-    if roof:
-        roof.pop("_t")
-    # second half of BASELINE.json's metric, "Poisson solve HBM GB/s vs peak" (SURVEY.md 8d): n_cg x 227 B x cells / t_poisson
-    poisson = poisson_solve_rate(ktimes, [st.schur_its for st in stats], cells_rank, outlet=(args.workload == "sphere"), variant=(args.schur_ainv != "ID"), peak=peak)
-    # whole-step model (SURVEY.md 8d): algorithmic bytes of all kernels / elapsed
+    t_ma, cnt_ma = ktimes["momentum_apply"]
+    if cnt_ma:
+        # SURVEY.md 8(d): A_apply = R x(3) v0(3) U0(3) W y(3) = 96 B per cell.  Every other apply of a BiCGStab iteration also
+        # reads the separate dot partner r^ (3 more fields, 120 B), which 8(d) books under the 15 vector passes; both are given.
+        ach = 96.0 * cells_rank * cnt_ma / (t_ma * 1e-3) / 1e9
+        tr = traffic.get("momentum_apply", {})
+        roof = {"kernel": "k_tma_march<AApplyTile> + wall launches (momentum operator y = A x fused with <a, y>, <y, y>)", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": (tr["bytes_per_cell"] * cells_rank / 1e9 if "bytes_per_cell" in tr else None), "traffic_unit": "GB per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum per cell of the committed capture x cells of this launch)", "traffic_source": tr.get("capture"),
+                "algorithmic_GB_per_launch": 96.0 * cells_rank / 1e9, "algorithmic_bytes_per_cell": 96.0, "launches": cnt_ma, "avg_ms": t_ma / cnt_ma, "share_of_step": t_ma / ms, "peak_source": peak_src,
+                "achieved_counting_the_dot_partner": 108.0 * cells_rank * cnt_ma / (t_ma * 1e-3) / 1e9, "note": "achieved = SURVEY 8(d)'s 96 B/cell x cells of one launch / mean CUDA-event duration of one operator application in the timed region; the second figure adds the dot partner r^ that every other application reads (108 B/cell mean)"}
+    # per class: the step model (SURVEY.md 8d, fluca_b200_step_model_bytes_split) over the event time of the class
+    split = {}
+    for st in stats:
+        for k, v in s.model_bytes_split(st).items():
+            split[k] = split.get(k, 0.0) + v
+    classes = {}
+    for k, (t, cnt) in ktimes.items():
+        if cnt and t > 0:
+            by = split.get(k, 0.0)
+            classes[k] = {"ms_per_step": t / args.steps, "launch_groups": cnt, "share_of_step": round(t / ms, 4), "model_GB_per_step": by / args.steps / 1e9, "achieved": (by / (t * 1e-3) / 1e9) if by else None, "frac": (by / (t * 1e-3) / 1e9 / peak) if by else None}
+    t_solve = sum(ktimes[k][0] for k in ("poisson_apply", "poisson_vec", "mg_smooth", "mg_transfer"))
+    b_solve = sum(split.get(k, 0.0) for k in ("poisson_apply", "poisson_vec", "mg_smooth", "mg_transfer"))
+    its_p = int(sum(st.schur_its for st in stats))
+    poisson = None
+    if t_solve > 0 and its_p > 0:
+        ach = b_solve / (t_solve * 1e-3) / 1e9
+        poisson = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "iterations": its_p, "bytes_per_iteration_per_cell": b_solve / its_p / cells_rank, "ms": t_solve, "krylov": "bicgstab+mg" if (args.workload == "sphere" or args.schur_ainv != "ID") else "pcg+mg"}
     model_bytes = sum(s.model_bytes(st) for st in stats)
     step_ach = model_bytes / (ms * 1e-3) / 1e9
+    kernel_ms = sum(t for t, c in ktimes.values())
 
-    line = {
-        "metric": "Mcell-updates/s per NS step",
+    res = {
         "value": value,
-        "unit": "Mcell-updates/s",
-        "n_gpus": world,
-        "steps": args.steps,
-        "warmup": args.warmup,
         "ms_per_step": ms / args.steps,
-        "higher_is_better": True,
-        "scaling": "strong" if args.strong else "weak",
-        "vs_baseline": None,
-        "dtype": "f64",
-        "data": "synthetic",
-        "config": {
-            "workload": workload_text(args, n, nzg, restart),
-            "mode": args.mode,
-            "abf_ainv": {"schur": args.schur_ainv, "upper": args.upper_ainv},
-            "l2": f"inputs larger than L2 (each field {8 * n**3 / 1e6:.0f} MB vs 126 MB L2; >50 fields streamed per step), no flush",
-            "iterations_per_step": {"outer": [st.outer_its for st in stats], "momentum": [st.mom_its for st in stats], "schur": [st.schur_its for st in stats], "abf": [st.abf_applies for st in stats]},
-        },
+        "scaling": scaling,
+        "cells": cells_total,
+        "workload": workload_text(args, case, scaling, world, restart, nmark),
+        "iterations_per_step": {"outer": [st.outer_its for st in stats], "momentum": [st.mom_its for st in stats], "schur": [st.schur_its for st in stats], "abf": [st.abf_applies for st in stats]},
         "roofline": roof,
         "poisson_solve": poisson,
-        "step_roofline": {"algorithmic_GB_per_step": model_bytes / args.steps / 1e9, "achieved": step_ach * world, "peak": peak * world, "unit": "GB/s", "frac": step_ach / peak, "peak_source": peak_src},
-        "kernel_shares": {k: round(v, 4) for k, v in shares.items()},
+        "step_roofline": {"algorithmic_GB_per_step": model_bytes / args.steps / 1e9 * world, "achieved": step_ach * world, "peak": peak * world, "unit": "GB/s", "frac": step_ach / peak, "peak_source": peak_src, "note": "SURVEY 8(d) step model bytes (this rank's cells) / step time / peak"},
+        "class_rooflines": classes,
+        "time_outside_kernels_frac": max(0.0, 1.0 - kernel_ms / ms),
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "l2": f"inputs larger than L2 (each field {8 * cells_rank / 1e6:.0f} MB per GPU vs 126 MB L2; >50 fields streamed per step), no flush",
     }
 
     # ---- end to end through the public API with HOST buffers (pinned): H2D of the step's inputs + step + D2H of the result
-    if not args.no_e2e:
+    if with_e2e:
         st0 = s.get_state()
-        host = {k: torch.empty(v.shape, dtype=torch.float64).pin_memory().numpy() for k, v in (("v", st0["v"]), ("p", st0["p"]), ("phalf", st0["phalf"]))}
-        hostU = [torch.empty(u.shape, dtype=torch.float64).pin_memory().numpy() for u in st0["U"]]
+        host = {k: ctx.pinned(v.shape) for k, v in (("v", st0["v"]), ("p", st0["p"]), ("phalf", st0["phalf"]))}
+        hostU = [ctx.pinned(u.shape) for u in st0["U"]]
         for k in host:
             host[k][...] = st0[k]
         for a, u in zip(hostU, st0["U"]):
             a[...] = u
+        del st0
         h2d = sum(a.nbytes for a in host.values()) + sum(a.nbytes for a in hostU)
         d2h = h2d
         import ctypes as C
@@ -414,42 +520,92 @@ def run_b200(args):
             return p
 
         ksteps = max(1, min(args.steps, 2))
-        barrier()
+        ctx.barrier()
         t0 = time.perf_counter()
         for _ in range(ksteps):
             fb._lib.check(lib, lib.fluca_b200_set_state(s._h, host["v"].ctypes.data, ptrs(hostU), host["p"].ctypes.data, host["phalf"].ctypes.data))
             fb.NSStep(ns)
             fb._lib.check(lib, lib.fluca_b200_get_state(s._h, host["v"].ctypes.data, ptrs(hostU), host["p"].ctypes.data, host["phalf"].ctypes.data))
-        barrier()
-        te = time.perf_counter() - t0
-        tt = torch.tensor([te], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        te = float(tt.item())
-        line["e2e"] = {"value": cells_total * ksteps / te / 1e6, "unit": "Mcell-updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": ksteps, "note": "NSStep through the NS API with pinned host buffers: set_state (H2D) + boundary planes + step + get_state (D2H) inside the timed region"}
-
+        ctx.barrier()
+        te = ctx.max_over_ranks(time.perf_counter() - t0)
+        res["e2e"] = {"value": cells_total * ksteps / te / 1e6, "unit": "Mcell-updates/s", "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world, "steps": ksteps, "note": "NSStep through the NS API with pinned host buffers: set_state (H2D) + boundary planes + step + get_state (D2H) inside the timed region; bytes summed over ranks"}
+        del host, hostU
         # ---- the same loop as the glue runs it: resident state, result staged to pinned memory behind the next step's compute
-        try:  # N=1 only: an exception on one rank must not strand the others in a collective
-            if world > 1:
-                raise StopIteration
-            ko = max(2, args.steps)
-            to, d2h_o, _ = e2e_resident_loop(ns, s, ko, barrier, time.perf_counter)
-            line["e2e_resident"] = {"value": cells_total * ko / to / 1e6, "unit": "Mcell-updates/s", "ms_per_step": to / ko * 1e3, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(d2h_o), "steps": ko, "note": "NOT the contract's e2e (above): state resident on the device as in glue/nsb200.c, constant boundary planes (nothing to re-send), every step's full result copied to pinned host memory by fluca_b200_stage_state on a second stream and read by the host after the next step; the final copy is drained inside the timed region"}
-        except StopIteration:
-            pass
-        except Exception as exc:  # an extra: it must never cost the bench line
-            line["e2e_resident"] = {"error": repr(exc)[:200]}
+        if world == 1:  # N=1 only: an exception on one rank must not strand the others in a collective
+            try:
+                ko = max(2, args.steps)
+                to, d2h_o, _ = e2e_resident_loop(ns, s, ko, ctx.barrier, time.perf_counter)
+                res["e2e_resident"] = {"value": cells_total * ko / to / 1e6, "unit": "Mcell-updates/s", "ms_per_step": to / ko * 1e3, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(d2h_o), "steps": ko, "note": "NOT the contract's e2e (above): state resident on the device as in glue/nsb200.c, constant boundary planes (nothing to re-send), every step's full result copied to pinned host memory by fluca_b200_stage_state on a second stream and read by the host after the next step; the final copy is drained inside the timed region"}
+            except Exception as exc:  # an extra: it must never cost the bench line
+                res["e2e_resident"] = {"error": repr(exc)[:200]}
+    fb.NSDestroy(ns)
+    return res
+
+
+def run_b200(args, ctx=None, lib=None):
+    import fluca_b200 as fb
+
+    ctx = ctx or Ctx()
+    lib = lib or fb._lib.load()  # CUDA library or a loud failure: there is no fallback (tests pass the host-emulation double)
+    world, rank = ctx.world, ctx.rank
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = parity_selfcheck(ctx, lib)
+        except Exception as exc:  # reported, never fatal for the timing that follows; every rank leaves the same way
+            parity = {"ok": False, "error": repr(exc)[:300]}
+    ctx.barrier()
+    if args.workload == "channel":
+        order = ["weak"]  # config 5 is sized per GPU (268 M cells each); the full grid only exists at 8 GPUs
+    elif world == 1:
+        order = ["strong"]
+    else:
+        order = {"both": ["strong", "weak"], "strong": ["strong"], "weak": ["weak"]}[args.scaling]
+    runs = {}
+    for i, sc in enumerate(order):
+        runs[sc] = measure(ctx, lib, args, sc, with_e2e=(i == 0 and not args.no_e2e))
+        ctx.barrier()
+    head = runs[order[0]]
+    line = {
+        "metric": "Mcell-updates/s per NS step",
+        "value": head["value"],
+        "unit": "Mcell-updates/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": head["ms_per_step"],
+        "higher_is_better": True,
+        "scaling": order[0] if world > 1 else ("weak" if args.workload == "channel" else "strong"),
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": head["workload"], "mode": args.mode, "abf_ainv": {"schur": args.schur_ainv, "upper": args.upper_ainv}, "l2": head["l2"], "iterations_per_step": head["iterations_per_step"]},
+        "roofline": head["roofline"],
+        "poisson_solve": head["poisson_solve"],
+        "step_roofline": head["step_roofline"],
+        "class_rooflines": head["class_rooflines"],
+        "time_outside_kernels_frac": head["time_outside_kernels_frac"],
+        "gpu_launches": head["gpu_launches"],
+        "clocks": head["clocks"],
+        "parity": parity,
+    }
+    for k in ("e2e", "e2e_resident"):
+        if k in head:
+            line[k] = head[k]
+    if "weak" in runs and order[0] != "weak":
+        w = runs["weak"]
+        line["weak"] = {k: w[k] for k in ("value", "ms_per_step", "cells", "workload", "iterations_per_step", "step_roofline", "time_outside_kernels_frac", "gpu_launches")}
+        line["weak"]["unit"] = "Mcell-updates/s"
 
     # ---- CPU baseline on the box's host cores (rank 0, N=1 only), bounded sample
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        r = cpu_sample(args, args.cpu_n, 1, 0, args.mode, threads)
-        line["cpu_baseline"] = {"value": r["value"], "unit": "Mcell-updates/s", "cores": threads, "kind": "port", "sample": f"{args.cpu_n}^3 sample of the workload (same BCs, dt=0.5h, mode={args.mode}, tolerances 1e-5), 1 step in {r['seconds']:.1f} s: the reference needs PETSc (absent) so this is the repo's C restatement"}
+        r = cpu_sample(args, args.cpu_n, 3, 1, args.mode)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "Mcell-updates/s", "cores": r["threads"], "kind": "port", "sample": f"{args.cpu_n}^3 sample of the workload (same BCs, dt=0.5h, mode={args.mode}, tolerances 1e-5), 1 warm-up + 3 timed steps in {r['seconds']:.1f} s on {r['threads']} OpenMP threads", "reference_build": reference_build_probe()}
     if rank == 0:
         print_json(json.dumps(line))
-    fb.NSDestroy(ns)
     if world > 1:
-        dist.destroy_process_group()
+        ctx.dist.destroy_process_group()
+    return line
 
 
 def main():

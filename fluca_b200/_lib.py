@@ -122,6 +122,7 @@ SYMBOLS = [
     "fluca_b200_fd_tvd_set_velocity",
     "fluca_b200_fd_tvd_set_current_solution",
     "fluca_b200_fd_set_locations",
+    "fluca_b200_step_model_bytes_split",
     "fluca_b200_fd_set_boundary_condition",
     "fluca_b200_fd_setup",
     "fluca_b200_fd_get_stencil",
@@ -175,6 +176,7 @@ def _prototype(L):
     L.fluca_b200_launch_count.restype = C.c_long
     L.fluca_b200_step_model_bytes.argtypes = [_P, C.POINTER(Stats)]
     L.fluca_b200_step_model_bytes.restype = C.c_double
+    L.fluca_b200_step_model_bytes_split.argtypes = [_P, C.POINTER(Stats), C.POINTER(C.c_double)]
     L.fluca_b200_kernel_timing.argtypes = [_P, C.c_int]
     L.fluca_b200_kernel_times.argtypes = [_P, C.POINTER(C.c_double), C.POINTER(C.c_long), C.c_int]
     L.fluca_b200_time_kernel.argtypes = [_P, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]

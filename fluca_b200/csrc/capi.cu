@@ -81,6 +81,8 @@ extern "C" int fluca_b200_comm_create_callbacks(int rank, int nranks, fluca_b200
 {
   API_BEGIN
   if (!h || !a) throw Error(FL_ERR_ARG, "halo and allsum callbacks are required");
+  // multigrid gathers its coarse levels on every rank (mg.cu): without the callback a multi-rank run would call a null pointer
+  if (nranks > 1 && !g) throw Error(FL_ERR_ARG, "the allgather callback is required with more than one rank");
   CallbackComm *cc = new CallbackComm;
   cc->rank = rank, cc->nranks = nranks, cc->halo_cb = h, cc->allsum_cb = a, cc->allgather_cb = g, cc->ctx = ctx;
   fluca_b200_comm *c = new fluca_b200_comm;
@@ -202,6 +204,7 @@ extern "C" int fluca_b200_set_state(fluca_b200_solver *h, const double *v, const
       if (U[d]) put(s, s.U.c[d], U[d], face_ext(s.gh.g, d));
   if (p) put(s, s.p, p, cell_ext(s.gh.g));
   if (phalf) put(s, s.phalf, phalf, cell_ext(s.gh.g));
+  s.prepared = false, s.rhs_valid = false; // a right-hand side formed from the old state no longer belongs to it
   s.ex.sync();
   API_END
 }
@@ -348,7 +351,9 @@ extern "C" int fluca_b200_get_rhs(fluca_b200_solver *h, double *rmom, double *co
 {
   API_BEGIN
   Solver &s = h->s;
-  if (!s.prepared) throw Error(FL_ERR_ARG, "call fluca_b200_prepare_step first");
+  // valid after fluca_b200_prepare_step, and after fluca_b200_step (then with the immersed-boundary forcing the step added
+  // and, without a pressure outlet, the mean of r_con removed: the b the outer solve saw)
+  if (!s.rhs_valid) throw Error(FL_ERR_ARG, "call fluca_b200_prepare_step or fluca_b200_step first");
   if (rmom) get_cells(s, rmom, s.rm);
   if (rint)
     for (int d = 0; d < s.dim; ++d)
@@ -462,6 +467,7 @@ extern "C" int fluca_b200_snapshot_restore(fluca_b200_solver *h)
   const size_t nb = sizeof(double) * (size_t)s.gh.g.nalloc;
   for (int c = 0; c < s.dim; ++c) copy_d2d(s.ex, s.v.c[c], h->sv.c[c], nb), copy_d2d(s.ex, s.U.c[c], h->sU.c[c], nb);
   copy_d2d(s.ex, s.p, h->sp, nb), copy_d2d(s.ex, s.phalf, h->sph, nb);
+  s.prepared = false, s.rhs_valid = false;
   s.ex.sync();
   API_END
 }
@@ -500,26 +506,51 @@ extern "C" int fluca_b200_stream(fluca_b200_solver *h, void **stream)
 
 extern "C" long fluca_b200_launch_count(fluca_b200_solver *h) { return h ? h->s.ex.stats.launches : 0; }
 
-extern "C" double fluca_b200_step_model_bytes(fluca_b200_solver *h, const fluca_b200_stats *st)
+// algorithmic bytes per cell (each distinct array element read once, written once per kernel), fp64, split by the
+// kernel classes of the live timing.  3-D: rhs 56, BiCGStab iteration 552 = 2 applies x 96 + 15 vector passes x 24,
+// poisson_rhs 32, PCG + V(2,2) iteration 227 = apply 16 + vector updates 72 + V-cycle 139 (smoothing 88 + transfers 34, x 8/7),
+// project 104, coupled residual 176, orthogonalisation (2k+3) x 56 at GMRES index k.
+static void model_bytes_split(const Solver &s, const fluca_b200_stats *st, double out[KT_NCLASS])
 {
-  // algorithmic bytes per cell (each distinct array element read once, written once
-  // per kernel), fp64.  3-D: rhs 56, BiCGStab iteration 552, poisson_rhs 32, PCG+V(2,2) iteration 227,
-  // project 104, coupled residual 176, orthogonalisation (2k+3)*56 at GMRES index k.
-  if (!h || !st) return 0.;
-  const Solver &s   = h->s;
+  for (int c = 0; c < KT_NCLASS; ++c) out[c] = 0.;
   const Geom   &g   = s.gh.g;
   const double  N   = (double)g.nx * g.ny * g.nzl;
   const bool    d3  = (s.dim == 3);
-  const double  rhs = d3 ? 56 : 40, bicg = d3 ? 552 : 368, prhs = d3 ? 32 : 24, pcg = d3 ? 227 : 251, proj = d3 ? 104 : 80;
+  const double  rhs = d3 ? 56 : 40, prhs = d3 ? 32 : 24, proj = d3 ? 104 : 80;
+  const double  mapply = d3 ? 192 : 128, mvec = d3 ? 360 : 240;
   const double  coup = d3 ? 176 : 128, vec7 = d3 ? 56 : 40;
+  const double  lev = d3 ? 8. / 7. : 4. / 3.; // all levels over the fine one
+  const double  pvec = 72., smooth = 88. * lev, transfer = 34. * lev;
   // with a pressure outlet the pressure Krylov method is BiCGStab: two applies + two V-cycles per iteration; the DIAG /
   // ROWSUM Schur complement is BiCGStab too and its apply is the two-launch form (3-D: 56 + 48 B instead of 16)
   const double  papply = s.opt.schur_ainv != 0 ? (d3 ? 104. : 80.) : 16.;
-  const double  piter  = (s.has_outlet || s.opt.schur_ainv != 0) ? 2. * (pcg - 16. + papply) : pcg;
-  double        B = rhs + st->abf_applies * (prhs + proj) + st->mom_its * bicg + st->schur_its * piter;
+  const double  twice  = (s.has_outlet || s.opt.schur_ainv != 0) ? 2. : 1.;
+  out[KT_RHS_PROJECT]    = N * (rhs + st->abf_applies * (prhs + proj));
+  out[KT_MOMENTUM_APPLY] = N * st->mom_its * mapply;
+  out[KT_MOMENTUM_VEC]   = N * st->mom_its * mvec;
+  out[KT_POISSON_APPLY]  = N * st->schur_its * twice * papply;
+  out[KT_POISSON_VEC]    = N * st->schur_its * twice * pvec;
+  out[KT_MG_SMOOTH]      = N * st->schur_its * twice * smooth;
+  out[KT_MG_TRANSFER]    = N * st->schur_its * twice * transfer;
   if (s.opt.mode == 0)
-    for (int k = 0; k < st->outer_its; ++k) B += coup + (2. * (k % s.opt.outer_restart) + 3.) * vec7;
-  return B * N;
+    for (int k = 0; k < st->outer_its; ++k) out[KT_OUTER] += N * (coup + (2. * (k % s.opt.outer_restart) + 3.) * vec7);
+}
+
+extern "C" double fluca_b200_step_model_bytes(fluca_b200_solver *h, const fluca_b200_stats *st)
+{
+  if (!h || !st) return 0.;
+  double by[KT_NCLASS], B = 0.;
+  model_bytes_split(h->s, st, by);
+  for (int c = 0; c < KT_NCLASS; ++c) B += by[c];
+  return B;
+}
+
+extern "C" int fluca_b200_step_model_bytes_split(fluca_b200_solver *h, const fluca_b200_stats *st, double bytes[FLUCA_B200_KT_NCLASS])
+{
+  API_BEGIN
+  if (!h || !st || !bytes) throw Error(FL_ERR_ARG, "null argument");
+  model_bytes_split(h->s, st, bytes);
+  API_END
 }
 
 extern "C" int fluca_b200_kernel_timing(fluca_b200_solver *h, int enable)

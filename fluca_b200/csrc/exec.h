@@ -209,7 +209,7 @@ inline void Exec::init()
   FL_CUDA(cudaGetDevice(&dev));
   FL_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
   FL_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-  max_blocks = 8192;
+  max_blocks = 32768; // BASELINE config 5 has 8192 tiles per plane (2048 x 1024 cells)
   d_partials = (double *)dev_alloc(sizeof(double) * max_blocks * MAXR);
   d_result   = (double *)dev_alloc(sizeof(double) * MAXR);
   d_carry    = (double *)dev_alloc(sizeof(double) * MAXR * 4);

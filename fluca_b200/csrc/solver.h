@@ -128,7 +128,9 @@ struct Solver {
 
   std::vector<double *> pool; // every field allocation (freed in destroy)
   // state
-  V3      v, U, v0, U0;
+  V3      v, U;         // live state (time n; n + 1 once do_step has rotated the buffers)
+  V3      v0, U0;       // time-n fields of the prepared step: aliases of v, U (prepare_step)
+  V3      vprev, Uprev; // buffers of the previous state / spare of the rotation
   double *p = nullptr, *phalf = nullptr;
   // right-hand side b = (rm, ri, rc) and solve vector x = (xv, xU, xp)
   V3      rm, ri, xv, xU;
@@ -160,6 +162,7 @@ struct Solver {
   int    step_index = 0;
   double t          = 0.;
   bool   prepared   = false;
+  bool   rhs_valid  = false;  // (rm, ri, rc) hold the right-hand side of the prepared / last step (with the IBM forcing once do_step ran)
   double tol_floor  = 0.;     // lower bound of the inner relative tolerances, set per ABF application by the outer solver
   bool   allow_guess = true;  // FLUCA_B200_NO_GUESS unsets it (A/B timing)
   bool   have_guess = false; // s.vstar holds a guess of the first momentum solve of the step (unscaled)

@@ -169,7 +169,8 @@ void solver_setup(Solver &s, int dim, const int n[3], const double *const xf[3],
     }
   }
 
-  s.v = s.alloc_v3(), s.U = s.alloc_v3(), s.v0 = s.alloc_v3(), s.U0 = s.alloc_v3();
+  s.v = s.alloc_v3(), s.U = s.alloc_v3(), s.vprev = s.alloc_v3(), s.Uprev = s.alloc_v3();
+  s.v0 = s.v, s.U0 = s.U;
   s.p = s.alloc_field(), s.phalf = s.alloc_field();
   s.rm = s.alloc_v3(), s.ri = s.alloc_v3(), s.rc = s.alloc_field();
   s.xv = s.alloc_v3(), s.xU = s.alloc_v3(), s.xp = s.alloc_field();
@@ -361,13 +362,13 @@ static void build_ainv(Solver &s)
 void prepare_step(Solver &s, double t, int step_index)
 {
   s.t = t, s.step_index = step_index;
-  // sol0 = sol (nsbasic.c:281-282): the roles of the two buffers are swapped instead of copying
-  V3 tv = s.v0, tU = s.U0;
+  // sol0 = sol (nsbasic.c:281-282) without a copy: during a step the time-n fields ARE the live state (nothing writes
+  // s.v / s.U before the rotation at the end of do_step), so forming the right-hand side has no side effect on the state
+  // and may be repeated (NSFormFunction between two steps, as VecCopy(sol, sol0) may)
   s.v0 = s.v, s.U0 = s.U;
-  s.v = tv, s.U = tU;
   DIM_DISPATCH(s, build_rhs<2>(s), build_rhs<3>(s));
   build_ainv(s); // after build_rhs: it exchanged the ghost planes of v0 and U0
-  s.prepared = true;
+  s.prepared = true, s.rhs_valid = true;
 }
 
 // ------------------------------------------------------------------ operators
@@ -896,7 +897,10 @@ int do_step(Solver &s, double t, int step_index)
   // sol <- x ; pressure extrapolation (cnlinearcart3d.c:2843-2854)
   view_fence(s); // a view of the previous state may still be reading p and p-half (its velocity buffers are not written by this step)
   {
-    V3 tv = s.v, tU = s.U;
+    // three buffers rotate: the solution becomes the state, the old state is kept untouched for one more step (a pending
+    // view copy may still read it; it is the solve vector of step n + 2), the spare becomes the next solve vector
+    V3 tv = s.vprev, tU = s.Uprev;
+    s.vprev = s.v, s.Uprev = s.U;
     s.v = s.xv, s.U = s.xU;
     s.xv = tv, s.xU = tU;
     const long   off = interior_off(s), len = interior_len(s);

@@ -258,6 +258,8 @@ inline void tma_launch(Exec &ex, const Op &op, const double *const *fields, int 
   tg.ntx = (nx + TMX - 1) / TMX, tg.nty = (ny + TMY - 1) / TMY;
   if ((kend - kbeg) % Op::ZALIGN) throw Error(FL_ERR_INTERNAL, "plane range of a tile launch is not a multiple of the operator's alignment");
   tg.nchunk = tma_pick_chunks(tg.ntx * tg.nty, (kend - kbeg) / Op::ZALIGN, Op::MINB * ex.sm_count, ex.max_blocks);
+  // one block partial per CTA: a reducing operator must not start more CTAs than ex.d_partials has room for
+  if (Op::NR > 0 && (long)tg.ntx * tg.nty * tg.nchunk > ex.max_blocks) throw Error(FL_ERR_INTERNAL, "tile launch of a reducing operator exceeds the partial buffer");
   const size_t smem = (size_t)Op::STAGES * Op::NIN * TILE_STRIDE * sizeof(double) + Op::STAGES * sizeof(uint64_t) + Op::SCRATCH;
   static bool  configured = false; // per template instantiation
   if (!configured) {

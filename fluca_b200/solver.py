@@ -297,6 +297,13 @@ class Solver:
     def kernel_timing(self, enable: bool):
         _lib.check(self.L, self.L.fluca_b200_kernel_timing(self._h, 1 if enable else 0))
 
+    def model_bytes_split(self, stats):
+        """SURVEY.md 8d model bytes of one step with these iteration counts, per kernel class name."""
+        n = len(_lib.KT_NAMES)
+        by = (C.c_double * n)()
+        _lib.check(self.L, self.L.fluca_b200_step_model_bytes_split(self._h, C.byref(stats), by))
+        return {_lib.KT_NAMES[i]: by[i] for i in range(n)}
+
     def kernel_times(self, reset: bool = True):
         n = len(_lib.KT_NAMES)
         ms, cnt = (C.c_double * n)(), (C.c_long * n)()

@@ -422,7 +422,15 @@ static PetscErrorCode NSFormFunction_B200(NS ns, Vec x, Vec f)
 
   PetscFunctionBegin;
   (void)x; /* the system is linear and the guess is zero (nsbasic.c:146-151): F(0) = -b */
-  if (!b->device_current) PetscCall(B200HostToDevice_Private(ns));
+  {
+    /* same coherence rule as NSStep_B200: a user edit of ns->sol since the last download goes up first */
+    PetscObjectState st;
+    PetscCall(PetscObjectStateGet((PetscObject)ns->sol, &st));
+    if (!b->device_current || st != b->solstate) {
+      PetscCall(B200HostToDevice_Private(ns));
+      b->solstate = st;
+    }
+  }
   PetscCall(B200UploadBoundaryData_Private(ns));
   B200Call(ns, fluca_b200_prepare_step(b->solver, (double)ns->t, (int)ns->step));
   {
@@ -448,7 +456,8 @@ static PetscErrorCode NSFormFunction_B200(NS ns, Vec x, Vec f)
   PetscCall(VecRestoreSubVector(f, vis, &fv));
   PetscCall(VecRestoreSubVector(f, Vis, &fV));
   PetscCall(VecRestoreSubVector(f, pis, &fp));
-  b->device_current = PETSC_FALSE; /* prepare_step rotated the device buffers: reload before the next step */
+  /* fluca_b200_prepare_step has no side effect on the device state (the time-n fields alias the live state, as the
+     reference's VecCopy(sol, sol0) is idempotent), so nothing is invalidated here */
   PetscFunctionReturn(PETSC_SUCCESS);
 }
 

@@ -154,6 +154,8 @@ int fluca_b200_step(fluca_b200_solver *s, double t, int step_index, fluca_b200_s
 /* ---- operator-level entry points (parity tests; ops->formfunction / ops->formjacobian analogues) ---- */
 /* sol0 <- sol, builds b = (r_mom, r_int, r_con) of NSFormFunction (cnlinearcart3d.c:2945-3043) */
 int fluca_b200_prepare_step(fluca_b200_solver *s, double t, int step_index);
+/* the right-hand side of the prepared step; also valid after fluca_b200_step, then it is the b the solve of that step saw
+ * (immersed-boundary forcing added to r_mom; mean of r_con removed when no pressure outlet exists, nsbasic.c:133-144) */
 int fluca_b200_get_rhs(fluca_b200_solver *s, double *rmom, double *const rint[3], double *rcon);
 /* y = A x, A = I + dt C - (nu dt/2) L of NSFormJacobian(UPDATE) (cnlinearcart3d.c:2930-2941); needs prepare_step */
 int fluca_b200_apply_momentum(fluca_b200_solver *s, const double *x, double *y);
@@ -195,6 +197,8 @@ double fluca_b200_step_model_bytes(fluca_b200_solver *s, const fluca_b200_stats 
 #define FLUCA_B200_KT_IBM 9          /* marker interpolation / spreading */
 #define FLUCA_B200_KT_NCLASS 10
 int fluca_b200_kernel_timing(fluca_b200_solver *s, int enable);
+/* the model of fluca_b200_step_model_bytes split by kernel class (the roofline numerator of each class) */
+int fluca_b200_step_model_bytes_split(fluca_b200_solver *s, const fluca_b200_stats *stats, double bytes[FLUCA_B200_KT_NCLASS]);
 /* accumulated milliseconds and launch counts per class since the last reset */
 int fluca_b200_kernel_times(fluca_b200_solver *s, double ms[FLUCA_B200_KT_NCLASS], long counts[FLUCA_B200_KT_NCLASS], int reset);
 

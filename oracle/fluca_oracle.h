@@ -112,6 +112,10 @@ int orc_bc_constant(int dim, double t, const double x[], double val[], void *ctx
 /* pressure flavour: ctx = double[1] */
 int orc_bc_constant_pressure(int dim, double t, const double x[], double val[], void *ctx);
 
+/* OpenMP threads of the timed CPU legs: set (n > 0) and report what the runtime will use / actually spawns */
+int orc_set_threads(int n);
+int orc_get_threads(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -101,8 +101,18 @@ def lib():
         L.orc_ibm_interpolate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_ibm_spread.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_get_marker_forces.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_set_threads.argtypes = [C.c_int]
+        L.orc_set_threads.restype = C.c_int
+        L.orc_get_threads.restype = C.c_int
         _lib = L
     return _lib
+
+
+def set_threads(n: int) -> int:
+    """Force the OpenMP thread count of the oracle (overrides an inherited OMP_NUM_THREADS); returns the count a parallel
+    region actually gets."""
+    lib().orc_set_threads(int(n))
+    return int(lib().orc_get_threads())
 
 
 def default_options(**kw) -> OrcOptions:

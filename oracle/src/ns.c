@@ -1452,3 +1452,20 @@ int orc_bc_constant_pressure(int dim, double t, const double x[], double val[], 
   val[0] = *(const double *)ctx;
   return 0;
 }
+
+/* ---- OpenMP thread control for the timed CPU legs of bench.py (a launcher such as torchrun pre-sets OMP_NUM_THREADS=1) ---- */
+int orc_set_threads(int n)
+{
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+}
+int orc_get_threads(void)
+{
+  int n = 1;
+#pragma omp parallel
+  {
+#pragma omp single
+    n = omp_get_num_threads();
+  }
+  return n;
+}

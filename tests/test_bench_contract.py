@@ -24,34 +24,86 @@ def test_reference_arm_prints_one_json_line():
 
 
 def test_workload_builders_match_the_baseline_configs():
-    sys.path.insert(0, ROOT)
-    import bench
+    from fluca_b200 import workloads as W
 
-    c = bench.sphere_case(512, 512)  # config 4: [-4,12] x [-8,8]^2, h = 1/32, Re = 300, dt = 0.5 h
+    c = W.sphere_bench_case(512, 512)  # config 4: [-4,12] x [-8,8]^2, h = 1/32, Re = 300, dt = 0.5 h
     f = c.faces()
     assert (f[0][0], f[0][-1], f[1][0], f[1][-1], f[2][0], f[2][-1]) == (-4.0, 12.0, -8.0, 8.0, -8.0, 8.0)
     assert np.isclose(f[0][1] - f[0][0], 1.0 / 32.0) and np.isclose(c.dt, 0.5 / 32.0) and np.isclose(c.mu, 1.0 / 300.0)
     assert [b["type"] for b in c.bcs] == [1, 2, 4, 4, 4, 4]  # inflow, pressure outlet, symmetry x 4
-    c2 = bench.sphere_case(512, 1024)  # weak scaling: the box grows in z, the cell size does not
+    c2 = W.sphere_bench_case(512, 1024)  # weak scaling: the box grows in z, the cell size does not
     assert np.isclose(c2.faces()[2][-1], 24.0)
-    k = bench.cavity_case(256, 256)  # config 3
+    k = W.cavity_bench_case(256, 256)  # config 3
     assert np.isclose(k.mu, 1.0 / 400.0) and np.isclose(k.dt, 0.5 / 256.0)
+    ch = W.channel_bench_case()  # config 5: 32 x 16 x 16 at h = 1/64, periodic x (and z), walls in y
+    assert ch.n == (2048, 1024, 1024) and np.isclose(ch.hi[0], 32.0) and np.isclose(ch.hi[1], 16.0) and np.isclose(ch.dt, 0.5 / 64.0)
+    assert [b["type"] for b in ch.bcs] == [3, 3, 1, 1, 3, 3]
+    cen = np.array(W.channel_sphere_centres(ch.lo, ch.hi, 80))
+    d = np.linalg.norm(cen[:, None] - cen[None], axis=2) + 99.0 * np.eye(80)
+    assert cen.shape == (80, 3) and d.min() >= 1.5 and cen[:, 1].min() >= 1.0 and cen[:, 1].max() <= 15.0
+    mk = W.multi_sphere_markers(cen[:3], 1.0, 12500, 1.0 / 64.0)
+    assert mk["X"].shape == (3, 37500) and mk["dV"].shape == (37500,)
 
 
-def test_poisson_solve_rate_is_the_second_half_of_the_baseline_metric():
-    """'Poisson solve HBM GB/s vs peak' = iterations x bytes per iteration and cell x cells / event-timed solve time."""
+class _CpuCtx:
+    """bench.Ctx without CUDA: one rank, wall-clock timer (the GPU arm's logic run on the host-emulation double)."""
+
+    rank, world, local, dev = 0, 1, 0, None
+
+    def barrier(self):
+        pass
+
+    def max_over_ranks(self, x):
+        return x
+
+    def comm(self):
+        return None
+
+    def stream_timer(self, solver):
+        import time
+
+        t = [0.0]
+
+        def start():
+            t[0] = time.perf_counter()
+
+        return start, lambda: 1e3 * (time.perf_counter() - t[0])
+
+    def pinned(self, shape):
+        return np.empty(shape)
+
+    def gather_z(self, arrs, axis):
+        return arrs
+
+
+def test_gpu_arm_logic_on_the_test_double():
+    """The whole GPU arm of bench.py (parity self-check against the oracle, timed loop, rooflines per class, end-to-end loops)
+    on the host-emulation library at a tiny size: the JSON line has every key of the contract and the parity case is green."""
     sys.path.insert(0, ROOT)
-    import bench
+    import argparse
 
-    kt = {"poisson_apply": (2.0, 10), "poisson_vec": (3.0, 30), "mg_smooth": (4.0, 100), "mg_transfer": (1.0, 50), "momentum_apply": (99.0, 5)}
-    r = bench.poisson_solve_rate(kt, [5, 5], 1.0e6, outlet=False, variant=False, peak=6530.3)
-    assert np.isclose(r["achieved"], 10 * 227.0 * 1.0e6 / 10.0e-3 / 1e9) and np.isclose(r["frac"], r["achieved"] / 6530.3) and r["krylov"] == "pcg+mg"
-    assert bench.poisson_solve_rate(kt, [5, 5], 1.0e6, outlet=True, variant=False, peak=1.0)["bytes_per_iteration_per_cell"] == 454.0
-    assert bench.poisson_solve_rate(kt, [5, 5], 1.0e6, outlet=False, variant=True, peak=1.0)["bytes_per_iteration_per_cell"] == 630.0
-    # never raises, never divides by zero: a reporting extra must not cost the bench line
-    assert bench.poisson_solve_rate({}, [5], 1.0e6, False, False, 1.0) is None
-    assert bench.poisson_solve_rate(kt, [], 1.0e6, False, False, 1.0) is None
-    assert bench.poisson_solve_rate(None, None, None, False, False, 0.0) is None
+    import bench
+    from tests import parity
+
+    out = []
+    bench.print_json = out.append
+    args = argparse.Namespace(gpus=1, steps=2, warmup=1, impl="b200", workload="sphere", n=16, markers=300, scaling="both", strong=False, mode="coupled", restart=0, schur_ainv="ID", upper_ainv="ID", cpu_n=8, no_cpu_baseline=False, no_e2e=False, no_parity=False)
+    bench.run_b200(args, ctx=_CpuCtx(), lib=parity.hostemu_library())
+    assert len(out) == 1
+    d = json.loads(out[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "parity", "class_rooflines", "step_roofline", "poisson_solve"):
+        assert key in d, key
+    assert d["parity"]["ok"], d["parity"]
+    assert set(d["parity"]["runs"]) == {"ID/ID", "DIAG/ROWSUM"}
+    assert d["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["value"] > 0 and d["gpu_launches"] > 0
+    assert d["cpu_baseline"]["cores"] >= 1 and "absent" in d["cpu_baseline"]["reference_build"]
+    assert d["config"]["workload"].startswith("BASELINE config 4")
+    for args.workload, args.n in (("cavity", 16), ("channel", 16)):
+        out.clear()
+        args.no_parity = args.no_cpu_baseline = args.no_e2e = True
+        bench.run_b200(args, ctx=_CpuCtx(), lib=parity.hostemu_library())
+        d = json.loads(out[0])
+        assert d["value"] > 0 and d["config"]["iterations_per_step"]["outer"]
 
 
 def test_resident_e2e_loop_reads_every_step_result():

@@ -194,3 +194,34 @@ def test_default_tolerances_meet_the_outer_criterion_with_relaxed_inner_solves(m
     assert st.converged and true_rel <= 1e-5 * 1.001
     assert true_rel == pytest.approx(st.outer_rnorm / st.outer_rnorm0, rel=2e-2)
     fb.NSDestroy(ns)
+
+
+def _formfunction_between_steps(lib, case, seed):
+    """step, NSFormFunction, step must equal step, step: forming the right-hand side has no side effect on the state
+    (the reference's VecCopy(sol, sol0) is idempotent, nsbasic.c:281-282)."""
+    state = case.initial_state(seed=seed)
+    runs = []
+    for poke in (False, True):
+        ns = parity.make_ns(case, lib, "coupled", **parity.TIGHT)
+        parity.set_initial(ns, state)
+        fb.NSStep(ns)
+        if poke:
+            before = fb.NSB200GetSolver(ns).get_state()
+            r1 = ns.ops["formfunction"](ns)
+            r2 = ns.ops["formfunction"](ns)  # twice: still no effect, same right-hand side
+            after = fb.NSB200GetSolver(ns).get_state()
+            assert parity.rel(r2[0], r1[0]) == 0.0 and parity.relU(r2[1], r1[1]) == 0.0
+            assert parity.rel(after["v"], before["v"]) == 0.0 and parity.relU(after["U"], before["U"]) == 0.0
+            assert parity.rel(after["p"], before["p"]) == 0.0 and parity.rel(after["phalf"], before["phalf"]) == 0.0
+            xv = np.random.default_rng(3).standard_normal(before["v"].shape)
+            fb.NSB200GetSolver(ns).apply_momentum(xv)  # operator access on the prepared step
+        fb.NSStep(ns)
+        runs.append(fb.NSB200GetSolver(ns).get_state())
+        fb.NSDestroy(ns)
+    a, b = runs
+    assert parity.rel(b["v"], a["v"]) < 1e-13 and parity.relU(b["U"], a["U"]) < 1e-13 and parity.rel(b["p"], a["p"]) < 1e-12
+
+
+def test_formfunction_has_no_side_effect_on_the_state(lib):
+    _formfunction_between_steps(lib, cases.cavity2d(n=16), 4)
+    _formfunction_between_steps(lib, cases.channel3d(n=(8, 6, 6), pout=0.2, dt=0.05), 9)

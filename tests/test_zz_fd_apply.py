@@ -161,7 +161,6 @@ def test_product_library_refuses_to_apply_without_a_device():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.environ.get("FLUCA_B200_RUN_UNVERIFIED"), reason="written after this round's GPU budget was spent: not yet run on a B200; FLUCA_B200_RUN_UNVERIFIED=1 runs it (tools/next_round_gpu.sh)")
 @pytest.mark.parametrize("make", CASES, ids=[c.__name__[5:] for c in CASES])
 def test_apply_cuda(make):
     L_ = fb._lib.load()
