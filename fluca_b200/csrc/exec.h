@@ -254,10 +254,10 @@ inline void Exec::sync()
 struct KTimer {
   Exec &ex;
   int   slot = -1;
-  KTimer(Exec &e, int cls) : ex(e)
+  KTimer(Exec &e, int cls, bool active = true) : ex(e)
   {
 #ifndef FLUCA_HOSTEMU
-    if (!ex.ktime_on || ex.kt_grouped) return;
+    if (!active || !ex.ktime_on || ex.kt_grouped) return;
     if (ex.kt_used + 2 > ex.kt_ev.size()) {
       if (ex.kt_ev.size() >= 200000) return;
       size_t old = ex.kt_ev.size();
@@ -270,7 +270,7 @@ struct KTimer {
     ex.kt_cls[slot / 2] = cls;
     cudaEventRecord(ex.kt_ev[slot], ex.stream);
 #else
-    (void)cls;
+    (void)cls, (void)active;
 #endif
   }
   ~KTimer()

@@ -847,6 +847,14 @@ struct ApplyFunctor {
   const double *in[MAX_SLOTS];
   int           in_ext[MAX_SLOTS][3];
   double       *out;
+  // fast path of the points whose whole stencil is the interior variant and stays inside the arrays (no wrap): the taps
+  // travel with the kernel arguments (constant bank) as precomputed linear offsets -- no table load, no index arithmetic per tap
+  int           fast_n;      // 0: no fast path
+  int           fast_lo[3], fast_hi[3]; // output indices [lo, hi) per direction that qualify
+  int           fast_slot[FLUCA_B200_FD_MAX_STENCIL];
+  int           fast_off[FLUCA_B200_FD_MAX_STENCIL];
+  double        fast_w[FLUCA_B200_FD_MAX_STENCIL];
+  double        fast_const;
   FL_HD int cls(int d, int idx) const
   {
     if (d >= dim || per[d]) return 0; // one class: a periodic direction is translation invariant
@@ -856,6 +864,17 @@ struct ApplyFunctor {
   }
   FL_HD void operator()(int i, int j, int k) const
   {
+    const bool fast = fast_n > 0 && i >= fast_lo[0] && i < fast_hi[0] && j >= fast_lo[1] && j < fast_hi[1] && k >= fast_lo[2] && k < fast_hi[2];
+    if (FL_WARP_ALL(fast)) {
+      double acc = fast_const;
+      for (int t = 0; t < fast_n; ++t) {
+        const int  s    = fast_slot[t];
+        const long base = (long)i + (long)in_ext[s][0] * ((long)j + (long)in_ext[s][1] * (long)k); // index of P in slot s
+        acc += fast_w[t] * in[s][base + fast_off[t]];
+      }
+      out[(long)i + (long)E[0] * ((long)j + (long)E[1] * (long)k)] = acc;
+      return;
+    }
     const int    v  = (cls(2, k) * ncls[1] + cls(1, j)) * ncls[0] + cls(0, i);
     double       acc = var_const[v];
     const int    p[3] = {i, j, k};
@@ -1040,6 +1059,32 @@ static DevicePlan *device_plan(fluca_b200_fd *h)
     }
     for (int s2 = 0; s2 < p.nslots; ++s2) field_extents(g, p.slot_loc[s2], f.in_ext[s2]);
     f.out = nullptr;
+    {
+      // interior variant: class R in every non-periodic direction (class 0 in periodic ones)
+      int cv[3];
+      for (int d = 0; d < 3; ++d) cv[d] = (d < g.dim && !g.per[d]) ? p.R : 0;
+      const int v = (cv[2] * p.ncls[1] + cv[1]) * p.ncls[0] + cv[0];
+      const int t0 = p.tap_start[v], t1 = p.tap_start[v + 1];
+      f.fast_n = 0;
+      if (t1 - t0 <= FLUCA_B200_FD_MAX_STENCIL) {
+        f.fast_n     = t1 - t0;
+        f.fast_const = p.var_const[v];
+        int reach[3] = {0, 0, 0};
+        for (int t = t0; t < t1; ++t) {
+          const int *m = &p.tap_meta[4 * (size_t)t];
+          const int  sl = m[3];
+          f.fast_slot[t - t0] = sl;
+          f.fast_off[t - t0]  = m[0] + f.in_ext[sl][0] * (m[1] + f.in_ext[sl][1] * m[2]);
+          f.fast_w[t - t0]    = p.tap_w[t];
+          for (int d = 0; d < 3; ++d) reach[d] = std::max(reach[d], std::abs(m[d]) + 1); // + 1: face inputs have one more entry
+        }
+        for (int d = 0; d < 3; ++d) {
+          if (d >= g.dim) f.fast_lo[d] = 0, f.fast_hi[d] = 1;
+          else if (g.per[d]) f.fast_lo[d] = reach[d], f.fast_hi[d] = p.E[d] - reach[d]; // taps must not wrap
+          else f.fast_lo[d] = p.R, f.fast_hi[d] = p.E[d] - p.R;                           // the interior class
+        }
+      }
+    }
     dp->ex.sync(); // the tables were staged from this function's host vectors
   } catch (...) {
     free_device_plan(dp.release());

@@ -364,6 +364,7 @@ void level_halo(Solver &s, MGLevel &L, double *x)
   if (s.dim != 3) return;
   double *f[1] = {x};
   Comm   *c    = L.replicated ? s.local_comm.get() : s.comm.get();
+  KTimer  kt(s.ex, KT_HALO, c->nranks > 1 || L.per[2]);
   c->halo(s.ex, f, 1, L.plane, L.nzl, L.per[2] != 0);
 }
 
@@ -438,7 +439,10 @@ void vcycle(Solver &s, std::vector<MGLevel> &levels, size_t l, bool want_dot)
     // without communication (redundantly: it is tiny), and each rank copies its planes and their ghosts back.
     KScope   kt(s.ex, KT_MG_TRANSFER);
     MGLevel &A0 = s.mg_agg[0];
-    s.comm->allgather(s.ex, L.b + L.plane, A0.b + A0.plane, L.plane * L.nzl);
+    {
+      KTimer kh(s.ex, KT_HALO, s.comm->nranks > 1);
+      s.comm->allgather(s.ex, L.b + L.plane, A0.b + A0.plane, L.plane * L.nzl);
+    }
     vcycle<DIM>(s, s.mg_agg, 0, false);
     if (A0.per[2]) level_halo(s, A0, A0.x);
     copy_d2d(s.ex, L.x, A0.x + A0.plane * L.k0, sizeof(double) * (size_t)L.plane * (L.nzl + 2));

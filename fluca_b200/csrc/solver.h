@@ -210,7 +210,8 @@ bool tma_usable(const Solver &s);
 void tensor_map_forget(const double *field); // drops the cached tensor maps of a field that is about to be freed
 void a_apply_dots_tma(Solver &s, const V3 &x, const V3 &y, const V3 &a, bool with_dots);
 void poisson_apply_dot_tma(Solver &s, const double *pin, double *out, const double *a);
-void coupled_cells_tma(Solver &s, const V3 &x, const double *p, const V3 &y, const V3 &w);
+// w carries (dt/rho) G p into the tile kernel; keep_w: it leaves as x + (dt/rho) G p (the operand of the face block)
+void coupled_cells_tma(Solver &s, const V3 &x, const double *p, const V3 &y, const V3 &w, bool keep_w);
 #endif
 
 // Krylov / multigrid (krylov.cu, mg.cu)

@@ -480,6 +480,99 @@ struct DivCell { // y_p = D U (per unit volume, as the reference's D)
   }
 };
 
+// ------------------------------------------------------------------ fused stages of the ABF application
+// Stage 1 in one pass (abfpc.c:73-76):  U* = a * in + T w  on every face the cell owns, and the Poisson right-hand side
+//   out = scale * (vol * rcscale * rc - flux divergence of U*)
+// from the cell's own faces: the upper face values are recomputed from (in, w) instead of being re-read after a halo exchange
+// of U* (they are the neighbour cell's lower face, formed by the same expression).  Algorithmic traffic in 3-D: in(3) w(3) rc
+// -> U*(3) out = 88 B per cell instead of 72 + 40 for FaceCombine followed by PoissonRhs.  acc[0] += out (for the mean removal).
+template <int DIM>
+struct FaceStarRhs {
+  Geom          g;
+  double        a;       // scale of `in` (the outer Krylov basis is stored unnormalised)
+  double        scale;   // rho / dt
+  double        rcscale; // the continuity right-hand side enters as rcscale * rc
+  CV3           in;      // r_int
+  CV3           w;       // v*
+  const double *rc;      // may be null
+  V3            Us;      // U*
+  double       *out;     // Poisson right-hand side
+  FL_HD void operator()(int i, int j, int kl, double acc[1]) const
+  {
+    Nbr<DIM> nb;
+    nbr<DIM>(g, i, j, kl, nb);
+    if (DIM == 3 && kl + FL_PF < g.nzl) {
+      const long ahead = nb.c + FL_PF * g.plane;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) fl_prefetch(in.c[d] + ahead), fl_prefetch(w.c[d] + ahead);
+      if (rc) fl_prefetch(rc + ahead);
+    }
+    double h[3] = {1., 1., 1.};
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) h[d] = g.t[d].h[nb.ig[d]];
+    const double area[3] = {h[1] * h[2], h[0] * h[2], h[0] * h[1]};
+    const double vol     = h[0] * h[1] * h[2];
+    double       fl      = 0.;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      const Tab    &T  = g.t[d];
+      const int     ig = nb.ig[d];
+      const double *f  = w.c[d];
+      double        lo = a * in.c[d][nb.c];
+      lo += t_face_lo<DIM>(g, d, f, nb);
+      fl_store(Us.c[d] + nb.c, lo);
+      const long fw = nb.fu[d];
+      double     up = a * in.c[d][fw];
+      if (!T.per && ig == T.n - 1) {
+        up += t_face_wall_hi<DIM>(g, d, f, nb);
+        fl_store(Us.c[d] + fw, up); // the extra wall face of a last cell
+      } else {
+        // lower face of the next cell (face index wraps to 0 in a periodic direction: itw[n] = itw[0])
+        up += T.itw[2 * ig + 2] * f[nb.c] + T.itw[2 * ig + 3] * f[nb.p[d]];
+      }
+      fl += area[d] * (up - lo);
+    }
+    const double sv = scale * ((rc ? vol * rcscale * rc[nb.c] : 0.) - fl);
+    out[nb.c]       = sv;
+    acc[0] += sv;
+  }
+};
+
+// Stage 2 in one pass (abfpc.c:80-101 with the ID upper factor):  v = v* - (dt/rho) G0 p  and  U = U* - (dt/rho) Gst0 p on every
+// face the cell owns.  3-D traffic: v*(3) U*(3) p -> v(3) U(3) = 104 B per cell (the figure of SURVEY.md 8d) in one launch
+// instead of ProjectCells (56) + FaceCombine (56).
+template <int DIM>
+struct ProjectAll {
+  Geom          g;
+  double        dtrho;
+  CV3           vs, Us;
+  const double *p;
+  V3            v, U;
+  FL_HD void operator()(int i, int j, int kl) const
+  {
+    Nbr<DIM> nb;
+    nbr<DIM>(g, i, j, kl, nb);
+    if (DIM == 3 && kl + FL_PF < g.nzl) {
+      const long ahead = nb.c + FL_PF * g.plane;
+#pragma unroll
+      for (int c = 0; c < DIM; ++c) fl_prefetch(vs.c[c] + ahead), fl_prefetch(Us.c[c] + ahead);
+      fl_prefetch(p + ahead);
+    }
+    double gp[DIM];
+    grad_cell<DIM>(g, p, nb, gp);
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      const Tab &T = g.t[d];
+      fl_store(v.c[d] + nb.c, vs.c[d][nb.c] - dtrho * gp[d]);
+      fl_store(U.c[d] + nb.c, Us.c[d][nb.c] - dtrho * gst_face_lo<DIM>(g, d, p, nb));
+      if (!T.per && nb.ig[d] == T.n - 1) {
+        const long fw = nb.fu[d];
+        fl_store(U.c[d] + fw, Us.c[d][fw] - dtrho * gst_face_wall_hi<DIM>(g, d, p, nb));
+      }
+    }
+  }
+};
+
 // ------------------------------------------------------------------ Poisson operator, fine level
 // (P p)_c = vol * (-D Gst0 p)_c = sum_d area_d (g_lo - g_hi),  g = face-normal derivative
 // row of the Poisson operator from the centre value and the two neighbours per direction
@@ -620,7 +713,7 @@ struct SchurVariantApplyDot {
   }
 };
 
-// coupled operator, velocity block: y_v = A v + (dt/rho) G0 p ; also w = v + (dt/rho) G0 p
+// coupled operator, velocity block: y_v = A v + (dt/rho) G0 p ; also w = v + (dt/rho) G0 p (skipped when w is empty)
 template <int DIM>
 struct CoupledCells {
   Geom          g;
@@ -645,7 +738,7 @@ struct CoupledCells {
 #pragma unroll
     for (int c = 0; c < DIM; ++c) {
       fl_store(y.c[c] + nb.c, av[c] + sp.dtrho * gp[c]);
-      fl_store(w.c[c] + nb.c, x.c[c][nb.c] + sp.dtrho * gp[c]);
+      if (w.c[0]) fl_store(w.c[c] + nb.c, x.c[c][nb.c] + sp.dtrho * gp[c]);
     }
   }
 };

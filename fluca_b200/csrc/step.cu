@@ -98,6 +98,7 @@ void halo_cells(Solver &s, const V3 &v)
   const Geom &g = s.gh.g;
   if (g.dim != 3) return;
   double *f[3] = {v.c[0], v.c[1], v.c[2]};
+  KTimer  kt(s.ex, KT_HALO, s.comm->nranks > 1 || g.t[2].per);
   s.comm->halo(s.ex, f, 3, g.plane, g.nzl, g.t[2].per != 0);
 }
 void halo_scalar(Solver &s, double *p)
@@ -105,6 +106,7 @@ void halo_scalar(Solver &s, double *p)
   const Geom &g = s.gh.g;
   if (g.dim != 3) return;
   double *f[1] = {p};
+  KTimer  kt(s.ex, KT_HALO, s.comm->nranks > 1 || g.t[2].per);
   s.comm->halo(s.ex, f, 1, g.plane, g.nzl, g.t[2].per != 0);
 }
 void halo_faces(Solver &s, const V3 &U)
@@ -115,12 +117,16 @@ void halo_faces(Solver &s, const V3 &U)
   if (g.dim != 3) return;
   double *f[1] = {U.c[2]};
   // on the last wall rank plane nzl holds owned FRONT faces: a non-periodic exchange never writes it
+  KTimer kt(s.ex, KT_HALO, s.comm->nranks > 1 || g.t[2].per);
   s.comm->halo(s.ex, f, 1, g.plane, g.nzl, g.t[2].per != 0);
 }
 
 void reduce_finish(Solver &s, int n, double *out)
 {
-  s.comm->allsum(s.ex, s.ex.d_result, n);
+  {
+    KTimer kt(s.ex, KT_HALO, s.comm->nranks > 1); // communication class of the live timing: halos, allreduces, allgathers
+    s.comm->allsum(s.ex, s.ex.d_result, n);
+  }
   copy_d2h(s.ex, s.ex.h_result, s.ex.d_result, sizeof(double) * n);
   s.ex.sync();
   for (int i = 0; i < n; ++i) out[i] = s.ex.h_result[i];
@@ -433,16 +439,13 @@ static void abf_apply_t(Solver &s, const V3 &bm, const V3 &bi, const double *bcn
 {
   KScope ks(s.ex, KT_RHS_PROJECT);
   const Geom &g = s.gh.g;
-  // stage 1 (abfpc.c:72-77)
+  // stage 1 (abfpc.c:72-77): momentum solve, then U* = r_int + T v* and the Poisson right-hand side in ONE pass (FaceStarRhs)
   momentum_solve(s, bm, s.vstar, guess, in_scale);
   halo_cells(s, s.vstar);
-  FaceCombine<DIM> fc;
-  fc.g = g, fc.a = in_scale, fc.b = 1., fc.c = 0., fc.in = CV3(bi), fc.w = CV3(s.vstar), fc.p = nullptr, fc.out = s.Ustar;
-  for_box<2>(s.ex, cell_box(s), fc);
-  halo_faces(s, s.Ustar);
-  PoissonRhs<DIM> pr;
-  pr.g = g, pr.scale = s.sp.rho / s.sp.dt, pr.rcscale = in_scale, pr.U = CV3(s.Ustar), pr.rc = bcn, pr.out = s.srhs;
-  for_box_reduce<1>(s.ex, cell_box(s), pr);
+  halo_faces(s, bi); // the upper z face of the slab's last plane is formed from r_int's ghost face plane and v*'s ghost plane
+  FaceStarRhs<DIM> fs;
+  fs.g = g, fs.a = in_scale, fs.scale = s.sp.rho / s.sp.dt, fs.rcscale = in_scale, fs.in = CV3(bi), fs.w = CV3(s.vstar), fs.rc = bcn, fs.Us = s.Ustar, fs.out = s.srhs;
+  for_box_reduce<1>(s.ex, cell_box(s), fs);
   if (!s.has_outlet) {
     // constant null space (abfpc.c:173-177): make the right-hand side compatible
     double sum;
@@ -457,18 +460,17 @@ static void abf_apply_t(Solver &s, const V3 &bm, const V3 &bi, const double *bcn
   // stage 2 (abfpc.c:80-101); the T*G~p terms of V cancel: V = V* - G~st p
   halo_scalar(s, op);
   if (s.opt.upper_ainv == 0) {
-    ProjectCells<DIM> pc;
-    pc.g = g, pc.dtrho = s.sp.dtrho, pc.vs = CV3(s.vstar), pc.p = op, pc.v = ov;
-    for_box<2>(s.ex, cell_box(s), pc);
-    fc.a = 1., fc.b = 0., fc.c = -s.sp.dtrho, fc.in = CV3(s.Ustar), fc.w = CV3(), fc.p = op, fc.out = oU;
-    for_box<2>(s.ex, cell_box(s), fc);
+    ProjectAll<DIM> pa; // v = v* - G~ p and U = U* - G~st p in one pass
+    pa.g = g, pa.dtrho = s.sp.dtrho, pa.vs = CV3(s.vstar), pa.Us = CV3(s.Ustar), pa.p = op, pa.v = ov, pa.U = oU;
+    for_box<2>(s.ex, cell_box(s), pa);
   } else {
     // DIAG / ROWSUM (abfpc.c:81-99): v = v* - a1 G~ p,  V = V* - T (a1 G~ p) - (-R) p = V* - G~st p + T w,  w = (1 - a1) G~ p
     GradScaleCells<DIM> gs;
     gs.g = g, gs.scale = s.sp.dtrho, gs.ainv = CV3(s.ainv_u), gs.p = op, gs.vs = CV3(s.vstar), gs.v = ov, gs.w = s.tw;
     for_box(s.ex, cell_box(s), gs);
     halo_cells(s, s.tw);
-    fc.a = 1., fc.b = 1., fc.c = -s.sp.dtrho, fc.in = CV3(s.Ustar), fc.w = CV3(s.tw), fc.p = op, fc.out = oU;
+    FaceCombine<DIM> fc;
+    fc.g = g, fc.a = 1., fc.b = 1., fc.c = -s.sp.dtrho, fc.in = CV3(s.Ustar), fc.w = CV3(s.tw), fc.p = op, fc.out = oU;
     for_box<2>(s.ex, cell_box(s), fc);
   }
   s.stats.abf_applies++;
@@ -488,7 +490,7 @@ static void coupled_apply_t(Solver &s, const V3 &xv, const V3 &xU, double *xp, c
   bool tiled = false;
 #ifndef FLUCA_HOSTEMU
   if (DIM == 3 && tma_usable(s)) {
-    coupled_cells_tma(s, xv, xp, yv, s.tw);
+    coupled_cells_tma(s, xv, xp, yv, s.tw, true);
     tiled = true;
   }
 #endif
@@ -505,6 +507,37 @@ static void coupled_apply_t(Solver &s, const V3 &xv, const V3 &xU, double *xp, c
   DivCell<DIM> dc;
   dc.g = g, dc.U = CV3(xU), dc.out = yp;
   for_box<2>(s.ex, cell_box(s), dc);
+}
+
+// M z for z = ABF(b): only the momentum and continuity blocks need arithmetic -- y_v = A z_v + (dt/rho) G z_p, y_p = D z_U; the
+// interpolation block equals b's (see outer_gmres) and is not formed here.
+template <int DIM>
+static void coupled_apply_abf_output_t(Solver &s, const V3 &zv, const V3 &zU, double *zp, const V3 &yv, double *yp)
+{
+  const Geom &g = s.gh.g;
+  halo_cells(s, zv);
+  halo_scalar(s, zp);
+  bool tiled = false;
+#ifndef FLUCA_HOSTEMU
+  if (DIM == 3 && tma_usable(s)) {
+    coupled_cells_tma(s, zv, zp, yv, s.tw, false);
+    tiled = true;
+  }
+#endif
+  if (!tiled) {
+    CoupledCells<DIM> cc;
+    cc.g = g, cc.sp = s.sp, cc.bc = s.bc, cc.x = CV3(zv), cc.v0 = CV3(s.v0), cc.U0 = CV3(s.U0), cc.p = zp, cc.y = yv, cc.w = V3{{nullptr, nullptr, nullptr}};
+    for_box(s.ex, cell_box(s), cc);
+  }
+  halo_faces(s, zU);
+  DivCell<DIM> dc;
+  dc.g = g, dc.U = CV3(zU), dc.out = yp;
+  for_box<2>(s.ex, cell_box(s), dc);
+}
+
+static void coupled_apply_abf_output(Solver &s, const V3 &zv, const V3 &zU, double *zp, const V3 &yv, double *yp)
+{
+  DIM_DISPATCH(s, coupled_apply_abf_output_t<2>(s, zv, zU, zp, yv, yp), coupled_apply_abf_output_t<3>(s, zv, zU, zp, yv, yp));
 }
 
 void coupled_apply(Solver &s, const V3 &xv, const V3 &xU, double *xp, const V3 &yv, const V3 &yU, double *yp)
@@ -719,19 +752,27 @@ static double mv_lincomb(Solver &s, const std::vector<MV> &V, int nv, const doub
 }
 
 // fused classical Gram-Schmidt step against the UNNORMALISED basis V_j (norms vn_j): h_j = <V_j, w> / vn_j (j < nv),
-// ww = <w, w>; w -= sum_j (h_j / vn_j) V_j; nrm2 = |w|^2
-static void mv_project(Solver &s, const std::vector<MV> &V, const double *vn, int nv, const MV &w, double *h, double &ww, double &nrm2)
+// ww = <w, w>; out = w - sum_j (h_j / vn_j) V_j; nrm2 = |out|^2.  `w` is a read-only VIEW (its face block may alias the face
+// block of a basis vector, see outer_gmres); `out` is where the new basis vector is stored (out may be w itself).
+// dots_only: stop after the projections of the first block (nv <= MVB) -- the caller decides from h and ww whether the
+// vector is needed at all, and calls again with h_known to form it.
+static void mv_project(Solver &s, const std::vector<MV> &V, const double *vn, int nv, const MV &w, const MV &out, double *h, double &ww, double &nrm2, bool dots_only = false, bool h_known = false)
 {
-  ww = 0.;
+  if (!h_known) ww = 0.;
   for (int j0 = 0; j0 < nv; j0 += MVB) {
     const int nc = nv - j0 < MVB ? nv - j0 : MVB;
     double    red[MVB + 1], neg[MVB];
-#define CALL(N) mv_dots_t<N>(s, &V[j0], w, red)
-    MV_DISPATCH(nc, CALL)
+    const MV &win = j0 == 0 ? w : out;
+    if (!(h_known && j0 == 0)) {
+#define CALL(N) mv_dots_t<N>(s, &V[j0], win, red)
+      MV_DISPATCH(nc, CALL)
 #undef CALL
-    if (j0 == 0) ww = red[nc];
-    for (int j = 0; j < nc; ++j) h[j0 + j] = red[j] / vn[j0 + j], neg[j] = -h[j0 + j] / vn[j0 + j];
-#define CALL(N) nrm2 = mv_comb_t<N>(s, &V[j0], neg, 1., w, w)
+      if (j0 == 0) ww = red[nc];
+      for (int j = 0; j < nc; ++j) h[j0 + j] = red[j] / vn[j0 + j];
+    }
+    if (dots_only) return;
+    for (int j = 0; j < nc; ++j) neg[j] = -h[j0 + j] / vn[j0 + j];
+#define CALL(N) nrm2 = mv_comb_t<N>(s, &V[j0], neg, 1., win, out)
     MV_DISPATCH(nc, CALL)
 #undef CALL
   }
@@ -752,6 +793,7 @@ static int outer_gmres(Solver &s)
   for (auto &b : s.basis) V.push_back(make_mv(s, b));
   for (auto &b : s.zbasis) Zb.push_back(make_mv(s, b));
   std::vector<double> H((size_t)(m + 1) * m, 0.), cs(m), sn(m), gvec(m + 1), y(m), vn(m + 1, 1.);
+  const bool   no_lazy = getenv("FLUCA_B200_NO_LAZY_BASIS") != nullptr; // always form the last basis vector (A/B timing, tests)
   const double relax_c = getenv("FLUCA_B200_RELAX") ? atof(getenv("FLUCA_B200_RELAX")) : 0.05; // 0 switches the relaxation off; measured: 0.05 keeps the outer counts, 0.2 adds outer iterations
   int    its = 0;
   double rnorm0 = -1., rnorm = 0.;
@@ -784,7 +826,8 @@ static int outer_gmres(Solver &s)
     gvec[0] = rnorm;
     int k = 0;
     for (; k < m && its < s.opt.outer_maxit; ++k) {
-      // z_k = ABF(v_k), v_k = V_k / vn_k; w = M z_k
+      // Z_k = ABF(V_k) with V_k UNNORMALISED (norm vn_k): Z_k = vn_k z_k, W = M Z_k = vn_k w.  Only host scalars carry the
+      // factor: no pass over the fields scales anything.
       V3      kv, kU, zv, zU;
       double *kp = (k == 0 && alias_b) ? s.rc : s.basis[k][6], *zp = s.zbasis[k][6];
       for (int c = 0; c < 3; ++c) {
@@ -792,61 +835,89 @@ static int outer_gmres(Solver &s)
         kU.c[c] = (k == 0 && alias_b) ? s.ri.c[c] : s.basis[k][3 + c];
         zv.c[c] = s.zbasis[k][c], zU.c[c] = s.zbasis[k][3 + c];
       }
-      bool guess = false;
-      if (s.have_guess && its == 0) {
-        // the right-hand side of this application is b / |b|: scale the guess of A^-1 b_mom likewise
-        const double sc = 1. / rnorm;
-        const long   off = interior_off(s), len = interior_len(s);
-        double      *g0 = s.vstar.c[0] + off, *g1 = s.vstar.c[1] + off, *g2 = s.dim == 3 ? s.vstar.c[2] + off : nullptr;
-        for_range(s.ex, len, FL_LAMBDA(long i) {
-          g0[i] *= sc;
-          g1[i] *= sc;
-          if (g2) g2[i] *= sc;
-        });
-        guess = true;
-      }
+      // the first application of a step acts on b itself: the previous velocity (or the forced IBM predictor) is its guess
+      const bool guess = s.have_guess && its == 0;
       // Inexact flexible GMRES: the Arnoldi relation M Z = V H holds whatever the accuracy of z_k = ABF(v_k), so the
       // residual estimate stays the true residual; an inner error of eta_k only needs eta_k |r_k| below the target
       // (Simoncini & Szyld 2003): inner rtol = max(user's, c * outer_rtol * |r_0| / |r_k|), at most 0.1.  The first
       // application (|r_0| = |b|) keeps the user's tolerances.
       s.tol_floor = (relax_c > 0. && rnorm > 0. && rnorm < rnorm0) ? relax_c * s.opt.outer_rtol * rnorm0 / rnorm : 0.;
-      abf_apply(s, kv, kU, kp, zv, zU, zp, guess, 1. / vn[k]);
+      abf_apply(s, kv, kU, kp, zv, zU, zp, guess, 1.);
       s.tol_floor = 0.;
-      V3 nv, nU;
-      for (int c = 0; c < 3; ++c) nv.c[c] = s.basis[k + 1][c], nU.c[c] = s.basis[k + 1][3 + c];
-      coupled_apply(s, zv, zU, zp, nv, nU, s.basis[k + 1][6]);
+      // W = M Z_k.  Its interpolation block needs no arithmetic: the face update of the ABF application is the exact
+      // algebraic inverse of that block row (abfpc.c:73-74 against :96-101: -T v + U + (-R) p = U* - T v* = the input), for
+      // every A-inverse variant and whatever the accuracy of the two inner solves.  So W's face block IS V_k's face block:
+      // the Gram-Schmidt kernels read it in place and no field is written for it.
+      V3 nv;
+      for (int c = 0; c < 3; ++c) nv.c[c] = s.basis[k + 1][c];
+      coupled_apply_abf_output(s, zv, zU, zp, nv, s.basis[k + 1][6]);
       if (!s.has_outlet) remove_mean(s, s.basis[k + 1][6]); // null space of J (nsbasic.c:229-243)
+      const MV Win = make_mv(s, nv, kU, s.basis[k + 1][6]);
       // classical Gram-Schmidt, all projections in one pass (PETSc's GMRES default,
       // KSPGMRESClassicalGramSchmidtOrthogonalization; its default refinement type is "never").  w = M z_k is nearly
       // parallel to v_k (ABF is a good preconditioner), so the remainder is small; one more pass removes the cancellation
       // error, which only matters when the requested tolerance comes near it: remainder / |w| against 1e-12 / outer_rtol
-      std::vector<double> hcolv(m + 1, 0.);
+      std::vector<double> hcolv(m + 1, 0.), col(m + 1, 0.);
       double             *hcol = hcolv.data(), ww = 0., nrm2 = 0.;
-      mv_project(s, Vl, vn.data(), k + 1, V[k + 1], hcol, ww, nrm2);
-      for (int jx = 0; jx <= k; ++jx) H[(size_t)jx * m + k] = hcol[jx];
+      // column k of H and the residual it implies, for a given norm hn of the remainder (true scale: / vn_k)
+      auto residual_with = [&](double hn, bool commit) {
+        for (int jx = 0; jx <= k; ++jx) col[jx] = hcol[jx] / vn[k];
+        col[k + 1] = hn;
+        for (int jx = 0; jx < k; ++jx) {
+          const double a = col[jx], b = col[jx + 1];
+          col[jx]     = cs[jx] * a + sn[jx] * b;
+          col[jx + 1] = -sn[jx] * a + cs[jx] * b;
+        }
+        const double a = col[k], b = col[k + 1], r = std::hypot(a, b);
+        const double ck = r > 0. ? a / r : 1., sk = r > 0. ? b / r : 0., gk = gvec[k];
+        if (commit) {
+          for (int jx = 0; jx < k; ++jx) H[(size_t)jx * m + k] = col[jx];
+          H[(size_t)k * m + k]       = r;
+          H[(size_t)(k + 1) * m + k] = 0.;
+          cs[k] = ck, sn[k] = sk;
+          gvec[k + 1] = -sk * gvec[k];
+          gvec[k]     = ck * gvec[k];
+        }
+        return std::fabs(sk * gk); // the residual norm after this column
+      };
+      bool lazy_done = false;
+      if (k + 1 <= MVB) {
+        // The last iteration of a solve never needs its new basis vector.  One pass gives every projection and <w, w>; the
+        // remainder norm follows from Pythagoras (the basis is orthonormal to round-off).  If that estimate is safely clear of
+        // cancellation and already meets the tolerance with a margin, the vector is not formed (7 fields read + 7 written).
+        mv_project(s, Vl, vn.data(), k + 1, Win, V[k + 1], hcol, ww, nrm2, true);
+        double sum2 = 0.;
+        for (int jx = 0; jx <= k; ++jx) sum2 += hcol[jx] * hcol[jx];
+        const double est2 = ww - sum2;
+        if (no_lazy == false && est2 > 1e-8 * ww) {
+          const double rn_est = residual_with(std::sqrt(est2) / vn[k], false);
+          if (rn_est <= 0.9 * s.opt.outer_rtol * rnorm0) {
+            rnorm     = residual_with(std::sqrt(est2) / vn[k], true);
+            lazy_done = true;
+          }
+        }
+        if (!lazy_done) mv_project(s, Vl, vn.data(), k + 1, Win, V[k + 1], hcol, ww, nrm2, false, true);
+      } else {
+        mv_project(s, Vl, vn.data(), k + 1, Win, V[k + 1], hcol, ww, nrm2);
+      }
+      if (lazy_done) {
+        its++;
+        if (s.stats.nhist < 128) s.stats.hist[s.stats.nhist++] = rnorm;
+        ++k;
+        done              = true;
+        s.stats.converged = 1;
+        break;
+      }
       const double cancel = 1e-12 / s.opt.outer_rtol; // round-off left in the remainder, relative to the target
       if (nrm2 < 0.5 * ww && nrm2 < cancel * cancel * 1e4 * ww) {
-        double ww2;
-        mv_project(s, Vl, vn.data(), k + 1, V[k + 1], hcol, ww2, nrm2);
-        for (int jx = 0; jx <= k; ++jx) H[(size_t)jx * m + k] += hcol[jx];
+        std::vector<double> h2(m + 1, 0.);
+        double              ww2;
+        mv_project(s, Vl, vn.data(), k + 1, V[k + 1], V[k + 1], h2.data(), ww2, nrm2);
+        for (int jx = 0; jx <= k; ++jx) hcol[jx] += h2[jx];
       }
-      double hn = std::sqrt(nrm2);
-      H[(size_t)(k + 1) * m + k] = hn;
-      vn[k + 1]                  = hn > 0. ? hn : 1.;
-      for (int jx = 0; jx < k; ++jx) {
-        double a = H[(size_t)jx * m + k], b = H[(size_t)(jx + 1) * m + k];
-        H[(size_t)jx * m + k]       = cs[jx] * a + sn[jx] * b;
-        H[(size_t)(jx + 1) * m + k] = -sn[jx] * a + cs[jx] * b;
-      }
-      {
-        double a = H[(size_t)k * m + k], b = H[(size_t)(k + 1) * m + k], r = std::hypot(a, b);
-        cs[k] = r > 0. ? a / r : 1.;
-        sn[k] = r > 0. ? b / r : 0.;
-        H[(size_t)k * m + k]       = r;
-        H[(size_t)(k + 1) * m + k] = 0.;
-        gvec[k + 1]                = -sn[k] * gvec[k];
-        gvec[k]                    = cs[k] * gvec[k];
-      }
+      const double nrm = std::sqrt(nrm2), hn = nrm / vn[k];
+      vn[k + 1]        = nrm > 0. ? nrm : 1.;
+      (void)residual_with(hn, true);
       its++;
       rnorm = std::fabs(gvec[k + 1]);
       if (s.stats.nhist < 128) s.stats.hist[s.stats.nhist++] = rnorm;
@@ -863,6 +934,7 @@ static int outer_gmres(Solver &s)
       for (int l = jx + 1; l < k; ++l) sum -= H[(size_t)jx * m + l] * y[l];
       y[jx] = sum / H[(size_t)jx * m + jx];
     }
+    for (int jx = 0; jx < k; ++jx) y[jx] /= vn[jx]; // Z_j = vn_j z_j
     (void)mv_lincomb(s, Zb, k, y.data(), x_zero ? 0. : 1., X, X);
     x_zero = false;
     if (its >= s.opt.outer_maxit) done = true;

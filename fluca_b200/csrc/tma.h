@@ -47,6 +47,7 @@ struct TmaGrid {
   int nx, ny;     // cells
   int kbeg, kend; // local planes [kbeg, kend) computed by this launch
   int ntx, nty, nchunk;
+  int nside;      // CTAs [0, nside) of the launch run the operator's side work (Op::SIDE) instead of a tile column
 };
 
 // tensor map of one field array laid out (px, py, nplanes) doubles; cached per (pointer, extents)
@@ -107,6 +108,10 @@ struct TileOpDefaults {
   static const int  ZALIGN  = 1;     // chunk boundaries are multiples of ZALIGN planes
   static const int  SCRATCH = 0;     // bytes of CTA scratch in shared memory
   static const bool POST    = false; // post(...) is called after the plane barrier (sees what every thread wrote to scratch)
+  // SIDE: the launch carries extra CTAs (the first tg.nside block indices, so that they are scheduled first and overlap the
+  // tile stream) that run op.side(tg, b, acc) with direct loads -- the cells the tile path leaves out (wall columns / planes
+  // with one-sided rows).  int side_blocks(const TmaGrid &) says how many.
+  static const bool SIDE    = false;
 };
 
 __device__ __forceinline__ void mbar_wait_addr(uint32_t bar, unsigned parity)
@@ -147,8 +152,19 @@ __global__ void __launch_bounds__(TMX *TMY, Op::MINB) k_tma_march(const __grid_c
   double            *scratch = reinterpret_cast<double *>(tma_smem + (size_t)TMS * SLOT * sizeof(double) + TMS * sizeof(uint64_t));
   const uint32_t     ring_s = smem_u32(ring), full_s = smem_u32(full);
   const int tid = threadIdx.x, tx = tid & (TMX - 1), ty = tid / TMX;
+  if constexpr (Op::SIDE) {
+    if ((int)blockIdx.x < tg.nside) { // block-uniform branch: the whole CTA does side work
+      double sacc[Op::NR > 0 ? Op::NR : 1];
+#pragma unroll
+      for (int r = 0; r < (Op::NR > 0 ? Op::NR : 1); ++r) sacc[r] = 0.;
+      op.side(tg, (int)blockIdx.x, tx, ty, sacc);
+      if (Op::NR > 0) block_reduce_and_finish<(Op::NR > 0 ? Op::NR : 1)>(sacc, carry, partials, result, ticket, gridDim.x, blockIdx.x);
+      return;
+    }
+  }
   const int ntile = tg.ntx * tg.nty;
-  const int tile = blockIdx.x % ntile, bz = blockIdx.x / ntile;
+  const int mb = (int)blockIdx.x - tg.nside; // index among the tile CTAs
+  const int tile = mb % ntile, bz = mb / ntile;
   const int bx = tile % tg.ntx, by = tile / tg.ntx;
   const int i0 = min(bx * TMX, (tg.nx - TMX + 1) & ~1), j0 = min(by * TMY, tg.ny - TMY); // i0 even
   int       k0, k1;
@@ -244,7 +260,7 @@ inline int tma_pick_chunks(int ntile, int nplanes, int slots, long max_blocks)
 template <class Op>
 inline void tma_launch(Exec &ex, const Op &op, const double *const *fields, int px, int py, int nplanes_alloc, int nx, int ny, int kbeg, int kend, const double *carry)
 {
-  if (kend <= kbeg) {
+  if (kend <= kbeg && !Op::SIDE) {
     if (Op::NR > 0) {
       if (carry) copy_d2d(ex, ex.d_result, carry, sizeof(double) * Op::NR);
       else dev_zero(ex, ex.d_result, sizeof(double) * Op::NR);
@@ -258,8 +274,15 @@ inline void tma_launch(Exec &ex, const Op &op, const double *const *fields, int 
   tg.ntx = (nx + TMX - 1) / TMX, tg.nty = (ny + TMY - 1) / TMY;
   if ((kend - kbeg) % Op::ZALIGN) throw Error(FL_ERR_INTERNAL, "plane range of a tile launch is not a multiple of the operator's alignment");
   tg.nchunk = tma_pick_chunks(tg.ntx * tg.nty, (kend - kbeg) / Op::ZALIGN, Op::MINB * ex.sm_count, ex.max_blocks);
+  tg.nside  = 0;
+  if constexpr (Op::SIDE) tg.nside = op.side_blocks(tg);
+  if (kend <= kbeg) tg.nchunk = 0; // no plane for the tile path: only side CTAs run (they never touch the ring)
+  if (tg.ntx * tg.nty * tg.nchunk + tg.nside == 0) {
+    if (Op::NR > 0) dev_zero(ex, ex.d_result, sizeof(double) * Op::NR);
+    return;
+  }
   // one block partial per CTA: a reducing operator must not start more CTAs than ex.d_partials has room for
-  if (Op::NR > 0 && (long)tg.ntx * tg.nty * tg.nchunk > ex.max_blocks) throw Error(FL_ERR_INTERNAL, "tile launch of a reducing operator exceeds the partial buffer");
+  if (Op::NR > 0 && (long)tg.ntx * tg.nty * tg.nchunk + tg.nside > ex.max_blocks) throw Error(FL_ERR_INTERNAL, "tile launch of a reducing operator exceeds the partial buffer");
   const size_t smem = (size_t)Op::STAGES * Op::NIN * TILE_STRIDE * sizeof(double) + Op::STAGES * sizeof(uint64_t) + Op::SCRATCH;
   static bool  configured = false; // per template instantiation
   if (!configured) {
@@ -268,7 +291,7 @@ inline void tma_launch(Exec &ex, const Op &op, const double *const *fields, int 
   }
   ex.stats.launches++;
   KTimer kt(ex, ex.kt_current);
-  k_tma_march<Op><<<(unsigned)(tg.ntx * tg.nty * tg.nchunk), TMX * TMY, smem, ex.stream>>>(in, op, tg, carry, ex.d_partials, ex.d_result, ex.d_ticket);
+  k_tma_march<Op><<<(unsigned)(tg.ntx * tg.nty * tg.nchunk + tg.nside), TMX * TMY, smem, ex.stream>>>(in, op, tg, carry, ex.d_partials, ex.d_result, ex.d_ticket);
   FL_CUDA(cudaGetLastError());
 }
 

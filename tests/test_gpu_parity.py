@@ -182,13 +182,11 @@ def test_config2_cylinder2d_full_size_properties(lib):
 def test_config4_sphere512_full_size_properties(lib):
     """BASELINE config 4 at its full size (512^3, 100k markers) in fractional mode: one step; discrete continuity, finite
     fields, forcing acts against the free stream"""
-    import bench
-
     n = 512
-    c = bench.sphere_case(n, n)
+    c = cases.sphere_bench_case(n, n)
     ns = parity.make_ns(c, lib, "fractional", ns_abf_momentum_ksp_rtol=1e-8, ns_abf_schur_ksp_rtol=1e-8)
     s = fb.NSB200GetSolver(ns)
-    v, U, p = bench.uniform_inflow_state(c)
+    v, U, p = cases.uniform_inflow_state(c)
     s.set_state(v=v, U=U, p=p, phalf=p)
     del v, U, p
     mk = cases.sphere_markers((0.0, 0.0, 0.0), 1.0, 100000, 16.0 / n)
