@@ -28,6 +28,13 @@ import numpy as np  # noqa: E402
 
 
 print_json = print
+T0 = time.time()
+
+
+def note(msg):
+    """progress marker on stderr (rank-tagged, seconds since start): a stuck multi-GPU run shows where it stopped"""
+    sys.stderr.write(f"[bench r{os.environ.get('RANK', '0')} +{time.time() - T0:6.1f}s] {msg}\n")
+    sys.stderr.flush()
 
 
 def parse():
@@ -163,7 +170,9 @@ def cpu_sample(args, n, steps, warmup, mode):
     ILU(0), reference default tolerances) on an n^3 sample of the sphere / cavity workload, on all host threads.  The thread
     count is forced through OpenMP's API (a launcher such as torchrun pre-sets OMP_NUM_THREADS=1) and what a parallel
     region actually gets is what is reported."""
-    want = os.cpu_count() or 1
+    # all host cores, up to 32: beyond that the block-Jacobi ILU of a 64^3 sample has more blocks than it can use and the
+    # OpenMP barriers of its short loops cost more than they save (the count actually used is what the line reports)
+    want = min(os.cpu_count() or 1, 32)
     os.environ["OMP_NUM_THREADS"] = str(want)
     from oracle import oracle as O
     from tests import cases
@@ -293,12 +302,24 @@ class Ctx:
         return self.torch.empty(shape, dtype=self.torch.float64).pin_memory().numpy()
 
     def gather_z(self, arrs, axis):
-        """rank 0 gets the z-concatenation of every rank's slab (small arrays only)."""
+        """rank 0 gets the z-concatenation of every rank's slab (small arrays only).  One node: through files in a scratch
+        directory and a barrier, not through an object collective."""
         if self.world == 1:
             return arrs
-        out = [None] * self.world if self.rank == 0 else None
-        self.dist.gather_object(arrs, out, dst=0)
-        return np.concatenate(out, axis=axis) if self.rank == 0 else None
+        import tempfile
+
+        self._gather_id = getattr(self, "_gather_id", 0) + 1
+        d = os.path.join(tempfile.gettempdir(), f"fluca_b200_bench_{os.environ.get('MASTER_PORT', '0')}")
+        os.makedirs(d, exist_ok=True)
+        np.save(os.path.join(d, f"g{self._gather_id}_r{self.rank}.npy"), arrs)
+        self.barrier()
+        out = None
+        if self.rank == 0:
+            out = np.concatenate([np.load(os.path.join(d, f"g{self._gather_id}_r{r}.npy")) for r in range(self.world)], axis=axis)
+        self.barrier()
+        if os.path.exists(os.path.join(d, f"g{self._gather_id}_r{self.rank}.npy")):
+            os.remove(os.path.join(d, f"g{self._gather_id}_r{self.rank}.npy"))
+        return out
 
 
 def parity_selfcheck(ctx, lib):
@@ -320,6 +341,7 @@ def parity_selfcheck(ctx, lib):
     runs = (("ID/ID", "ID", "ID", 2), ("DIAG/ROWSUM", "DIAG", "ROWSUM", 1))
     got = {}
     for label, sa, ua, nsteps in runs:
+        note(f"parity case {label}: building the solver")
         ns = W.make_ns(case, lib, "coupled", comm=ctx.comm(), ns_pc_abf_schur_ainv_type=sa, ns_pc_abf_upper_ainv_type=ua, **tight)
         W.set_initial_slab(ns, state)
         fb.NSB200SetMarkers(ns, mk["X"], mk["Ud"], mk["dV"], 4)
@@ -331,12 +353,14 @@ def parity_selfcheck(ctx, lib):
         g = dict(v=ctx.gather_z(st["v"], 1), p=ctx.gather_z(st["p"], 0), U=[ctx.gather_z(u, 0) for u in st["U"]], outer=outer)
         fb.NSDestroy(ns)
         got[label] = g
+    note("parity case: GPU side done")
     if rank != 0:
         return None
     from oracle import oracle as O  # checker
     from tests import cases
 
-    O.set_threads(os.cpu_count() or 1)
+    # a 16 k-cell case at tight tolerances is ~1e5 short OpenMP regions: a handful of threads, not the 100+ of an 8-GPU host
+    O.set_threads(min(os.cpu_count() or 1, 8))
 
     def rel(a, b):
         return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300))
@@ -353,6 +377,7 @@ def parity_selfcheck(ctx, lib):
         e = dict(v=rel(g["v"], a["v"]), U=eU, p=rel(g["p"], a["p"]), steps=nsteps, outer_its_gpu=g["outer"], outer_its_oracle=oo)
         ok = ok and e["v"] <= tol and e["U"] <= tol and e["p"] <= 10 * tol
         res[label] = e
+    note("parity case: oracle side done")
     return {"ok": bool(ok), "ranks": world, "tolerance": "rel. L2 <= 1e-10 (v, U), 1e-9 (p) against the CPU oracle at tight tolerances", "case": f"sphere workload builder at {nx}x{ny}x{nz} (inflow/outlet/symmetry, 300 IBM markers), coupled mode, {world} z-slab(s) over {'NCCL' if world > 1 else 'one GPU'}; ABF factor variants schur/upper", "runs": res, "oracle": "parity unpinned: the oracle is this repo's restatement (DESIGN.md 2)"}
 
 
@@ -406,6 +431,7 @@ def measure(ctx, lib, args, scaling, with_e2e):
     big = (float(n) ** 2 * nzg / world) * (2 if args.workload == "channel" else 1) >= 100e6
     restart = args.restart or (3 if big else 10)
     case = make_case(args, n, nzg)
+    note(f"measure {scaling}: building {case.n}")
     opts = {"ns_ksp_gmres_restart": restart, "ns_pc_abf_schur_ainv_type": args.schur_ainv, "ns_pc_abf_upper_ainv_type": args.upper_ainv}
     ns = W.make_ns(case, lib, args.mode, comm=ctx.comm(), **opts)
     s = fb.NSB200GetSolver(ns)
@@ -419,9 +445,11 @@ def measure(ctx, lib, args, scaling, with_e2e):
         nmark = int(mk["dV"].shape[0])
 
     # ---- device-resident throughput ("value"): state lives in HBM, nothing crosses PCIe in the timed region
+    note(f"measure {scaling}: warm-up")
     for _ in range(args.warmup):
         fb.NSStep(ns)
     ctx.barrier()
+    note(f"measure {scaling}: timed region")
     sampler = ClockSampler(ctx.local)
     if rank == 0:
         sampler.start()
@@ -438,6 +466,7 @@ def measure(ctx, lib, args, scaling, with_e2e):
     ms = stop()
     ctx.barrier()
     ms = ctx.max_over_ranks(ms)
+    note(f"measure {scaling}: {ms / args.steps:.2f} ms per step")
     launches = s.launch_count() - l0
     ktimes = s.kernel_times(reset=True)
     s.kernel_timing(False)
@@ -609,6 +638,10 @@ def run_b200(args, ctx=None, lib=None):
 
 
 def main():
+    import faulthandler
+
+    faulthandler.enable()
+    faulthandler.dump_traceback_later(240, repeat=True, file=sys.stderr)  # a stuck run says where, every 4 minutes
     args = parse()
     # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL prints its version there)
     # are sent to stderr for the duration of the run

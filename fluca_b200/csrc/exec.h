@@ -332,8 +332,10 @@ FL_HD void z_chunk(int nz, int nchunks, int c, int &k0, int &k1)
   k1 = k0 + base + (c < rem ? 1 : 0);
 }
 
-template <int U, class F>
-__global__ void __launch_bounds__(BX *BY, 2) k_box(Box b, F f)
+// MINB: resident CTAs per SM the register allocation aims at (2 -> 128 registers, 3 -> 80, 4 -> 64).  The streaming functors
+// with light stencils are latency-bound at 2 CTAs per SM (one plane of loads in flight per thread): they ask for more.
+template <int U, int MINB, class F>
+__global__ void __launch_bounds__(BX *BY, MINB) k_box(Box b, F f)
 {
   const int i = blockIdx.x * BX + threadIdx.x;
   const int j = blockIdx.y * BY + threadIdx.y;
@@ -402,8 +404,8 @@ __device__ __forceinline__ void block_reduce_and_finish(double (&acc)[NR], const
   }
 }
 
-template <int NR, class F>
-__global__ void __launch_bounds__(BX *BY, 2) k_box_reduce(Box b, F f, const double *carry, double *partials, double *result, unsigned *ticket)
+template <int NR, int MINB, class F>
+__global__ void __launch_bounds__(BX *BY, MINB) k_box_reduce(Box b, F f, const double *carry, double *partials, double *result, unsigned *ticket)
 {
   const int i = blockIdx.x * BX + threadIdx.x;
   const int j = blockIdx.y * BY + threadIdx.y;
@@ -447,7 +449,7 @@ inline dim3 box_grid(const Exec &ex, Box b, long cap_blocks)
 #endif // !FLUCA_HOSTEMU
 
 // f(i, j, k) for every point of the box; U: planes per loop trip of a thread (loads of U planes in flight)
-template <int U = 1, class F>
+template <int U = 1, int MINB = 2, class F>
 inline void for_box(Exec &ex, Box b, F f)
 {
   if (b.nx <= 0 || b.ny <= 0 || b.nz <= 0) return;
@@ -455,7 +457,7 @@ inline void for_box(Exec &ex, Box b, F f)
 #ifndef FLUCA_HOSTEMU
   dim3   g = box_grid(ex, b, 0);
   KTimer kt(ex, ex.kt_current);
-  k_box<U><<<g, dim3(BX, BY, 1), 0, ex.stream>>>(b, f);
+  k_box<U, MINB><<<g, dim3(BX, BY, 1), 0, ex.stream>>>(b, f);
   FL_CUDA(cudaGetLastError());
 #else
   for (int k = 0; k < b.nz; ++k)
@@ -484,7 +486,7 @@ inline void for_range(Exec &ex, long n, F f)
 // f(i, j, k, acc[NR]) accumulates into acc; the NR sums land in ex.d_result (device)
 // carry / result (device pointers, CUDA build): chain the sums of several launches of one reduction;
 // the default writes ex.d_result
-template <int NR, class F>
+template <int NR, int MINB = 2, class F>
 inline void for_box_reduce(Exec &ex, Box b, F f, const double *carry = nullptr, double *result = nullptr)
 {
   static_assert(NR <= Exec::MAXR, "too many simultaneous reductions");
@@ -499,7 +501,7 @@ inline void for_box_reduce(Exec &ex, Box b, F f, const double *carry = nullptr, 
   dim3 g = box_grid(ex, b, ex.max_blocks);
   if ((long)g.x * g.y * g.z > ex.max_blocks) throw Error(FL_ERR_INTERNAL, "reduction grid exceeds partial buffer");
   KTimer kt(ex, ex.kt_current);
-  k_box_reduce<NR><<<g, dim3(BX, BY, 1), 0, ex.stream>>>(b, f, carry, ex.d_partials, result, ex.d_ticket);
+  k_box_reduce<NR, MINB><<<g, dim3(BX, BY, 1), 0, ex.stream>>>(b, f, carry, ex.d_partials, result, ex.d_ticket);
   FL_CUDA(cudaGetLastError());
 #else
   double acc[NR];

@@ -104,7 +104,7 @@ struct MGSmooth {
 // the same sweep from TMA-staged tiles (3-D levels of at least one tile per plane, see tma.h)
 template <int NRED>
 struct MGSmoothTile : TileOpDefaults {
-  static const int NIN = 1, NR = NRED, MINB = 4, STAGES = 8;
+  static const int NIN = 1, NR = NRED, MINB = 4, STAGES = 8, PLANES = FL_TILE_PLANES;
   MGLevel          L;
   double           omega;
   const double    *b;
@@ -112,7 +112,7 @@ struct MGSmoothTile : TileOpDefaults {
   struct Regs {
     double b;
   };
-  __device__ int flags(int i, int j) const { return (L.uni && i > 0 && i < L.n[0] - 1 && j > 0 && j < L.n[1] - 1) ? 1 : 0; }
+  __device__ int flags(int i, int j) const { return (L.uni && (L.per[0] || (i > 0 && i < L.n[0] - 1)) && j > 0 && j < L.n[1] - 1) ? 1 : 0; }
   __device__ void prefetch(Regs &rg, int off, int kl) const { rg.b = b[off]; }
   __device__ void cell(const TileView &tv, const Regs &rg, int fl, int i, int j, int kl, int off, double *acc) const
   {
@@ -147,13 +147,13 @@ __device__ __forceinline__ double mg_diag3(const MGLevel &L, int i, int j, int k
 // so the second one, x2 = x1 + omega (b - P x1) / diag, needs only b at the cell and its six neighbours.  The tile holds b
 // (ghost planes exchanged by the caller); x1 is never stored: 16 B/cell instead of 16 + 24.
 struct MGFirstTwoTile : TileOpDefaults {
-  static const int NIN = 1, NR = 0, MINB = 4, STAGES = 8;
+  static const int NIN = 1, NR = 0, MINB = 4, STAGES = 8, PLANES = FL_TILE_PLANES;
   MGLevel          L;
   double           omega, omega2; // weights of the first and the second sweep
   double          *xout;
   struct Regs {
   };
-  __device__ int  flags(int i, int j) const { return (L.uni && i >= 2 && i <= L.n[0] - 3 && j >= 2 && j <= L.n[1] - 3) ? 1 : 0; }
+  __device__ int  flags(int i, int j) const { return (L.uni && (L.per[0] || (i >= 2 && i <= L.n[0] - 3)) && j >= 2 && j <= L.n[1] - 3) ? 1 : 0; }
   __device__ void prefetch(Regs &, int, int) const { }
   __device__ double first(double bv, int i, int j, int kg) const
   {
@@ -176,8 +176,8 @@ struct MGFirstTwoTile : TileOpDefaults {
       // neighbours outside the domain count as zero (Neumann: zero conductance; outlet: Dirichlet ghost), as in mg_row
       const double x1c = first(bc, i, j, kg);
       double       xm[3], xp[3];
-      xm[0] = i > 0 ? first(bm[0], i - 1, j, kg) : 0.;
-      xp[0] = i < L.n[0] - 1 ? first(bp[0], i + 1, j, kg) : 0.;
+      xm[0] = i > 0 ? first(bm[0], i - 1, j, kg) : (L.per[0] ? first(bm[0], L.n[0] - 1, j, kg) : 0.);
+      xp[0] = i < L.n[0] - 1 ? first(bp[0], i + 1, j, kg) : (L.per[0] ? first(bp[0], 0, j, kg) : 0.);
       xm[1] = j > 0 ? first(bm[1], i, j - 1, kg) : 0.;
       xp[1] = j < L.n[1] - 1 ? first(bp[1], i, j + 1, kg) : 0.;
       xm[2] = kg > 0 ? first(bm[2], i, j, kg - 1) : (L.per[2] ? first(bm[2], i, j, n2 - 1) : 0.);
@@ -194,13 +194,15 @@ struct MGFirstTwoTile : TileOpDefaults {
 // fine cell; x-pairs are summed with a warp shuffle, y-pairs through CTA scratch after the plane barrier, z-pairs in a
 // register across two consecutive planes (chunks start at even planes: ZALIGN = 2).
 struct MGResidTile : TileOpDefaults {
-  static const int  NIN = 1, NR = 0, MINB = 4, STAGES = 8, ZALIGN = 2, SCRATCH = 2 * TMY * (TMX / 2) * (int)sizeof(double);
+  // scratch: one half-row buffer per plane of two consecutive trips (a trip holds up to two planes; the next trip must not
+  // overwrite what a slower thread still reads in post())
+  static const int  NIN = 1, NR = 0, MINB = 4, STAGES = 8, ZALIGN = 2, PLANES = FL_TILE_PLANES, SCRATCH = 4 * TMY * (TMX / 2) * (int)sizeof(double);
   static const bool POST = true;
   MGLevel           F, C;
   struct Regs {
     double b;
   };
-  __device__ int  flags(int i, int j) const { return (F.uni && i > 0 && i < F.n[0] - 1 && j > 0 && j < F.n[1] - 1) ? 1 : 0; }
+  __device__ int  flags(int i, int j) const { return (F.uni && (F.per[0] || (i > 0 && i < F.n[0] - 1)) && j > 0 && j < F.n[1] - 1) ? 1 : 0; }
   __device__ void prefetch(Regs &rg, int off, int) const { rg.b = F.b[off]; }
   __device__ void cell(const TileView &tv, const Regs &rg, int fl, int i, int j, int kl, int, double *) const
   {
@@ -213,13 +215,13 @@ struct MGResidTile : TileOpDefaults {
     else mg_row_core<3>(F, i, j, kl, xc, xm, xp, Ax, dg);
     double r = rg.b - Ax;
     r += __shfl_xor_sync(__activemask(), r, 1); // cells (2m, 2m+1) of a row are owned together (tile origins are even)
-    if (!(tx & 1)) tv.scratch[((kl & 1) * TMY + ty) * (TMX / 2) + (tx >> 1)] = r;
+    if (!(tx & 1)) tv.scratch[((kl & 3) * TMY + ty) * (TMX / 2) + (tx >> 1)] = r;
   }
   __device__ void post(const TileView &tv, int, bool owned, int i, int j, int kl, double &zsum) const
   {
     const int tx = threadIdx.x & (TMX - 1), ty = threadIdx.x / TMX;
     if (!owned || (tx & 1) || (ty & 1)) return;
-    const double *row = tv.scratch + ((kl & 1) * TMY + ty) * (TMX / 2) + (tx >> 1);
+    const double *row = tv.scratch + ((kl & 3) * TMY + ty) * (TMX / 2) + (tx >> 1);
     const double  s   = row[0] + row[TMX / 2];
     if (!(kl & 1)) zsum = s;
     else C.b[C.idx(i >> 1, j >> 1, kl >> 1)] = zsum + s;
@@ -404,11 +406,11 @@ void smooth(Solver &s, MGLevel &L, bool zero_guess, bool with_dot, double omega)
     if (with_dot) {
       MGSmoothTile<1> op;
       op.L = L, op.omega = omega, op.b = L.b, op.xout = L.t;
-      tma_launch(s.ex, op, fields, L.px, L.py, L.nzl + 2, L.n[0], L.n[1], 0, L.nzl, nullptr);
+      tma_launch(s.ex, op, fields, L.px, L.py, L.nzl + 2, L.n[0], L.n[1], 0, L.nzl, nullptr, L.per[0] != 0);
     } else {
       MGSmoothTile<0> op;
       op.L = L, op.omega = omega, op.b = L.b, op.xout = L.t;
-      tma_launch(s.ex, op, fields, L.px, L.py, L.nzl + 2, L.n[0], L.n[1], 0, L.nzl, nullptr);
+      tma_launch(s.ex, op, fields, L.px, L.py, L.nzl + 2, L.n[0], L.n[1], 0, L.nzl, nullptr, L.per[0] != 0);
     }
     double *tmp = L.x;
     L.x         = L.t;
@@ -465,7 +467,7 @@ void vcycle(Solver &s, std::vector<MGLevel> &levels, size_t l, bool want_dot)
     MGFirstTwoTile op;
     op.L = L, op.omega = sweep_weight(DIM, false, s.opt.mg_nu1, 0, false), op.omega2 = sweep_weight(DIM, false, s.opt.mg_nu1, 1, false), op.xout = L.x;
     const double *fields[1] = {L.b};
-    tma_launch(s.ex, op, fields, L.px, L.py, L.nzl + 2, L.n[0], L.n[1], 0, L.nzl, nullptr);
+    tma_launch(s.ex, op, fields, L.px, L.py, L.nzl + 2, L.n[0], L.n[1], 0, L.nzl, nullptr, L.per[0] != 0);
     done = 2;
   }
 #endif
@@ -481,7 +483,7 @@ void vcycle(Solver &s, std::vector<MGLevel> &levels, size_t l, bool want_dot)
       MGResidTile op;
       op.F = L, op.C = C;
       const double *fields[1] = {L.x};
-      tma_launch(s.ex, op, fields, L.px, L.py, L.nzl + 2, L.n[0], L.n[1], 0, L.nzl, nullptr);
+      tma_launch(s.ex, op, fields, L.px, L.py, L.nzl + 2, L.n[0], L.n[1], 0, L.nzl, nullptr, L.per[0] != 0);
       tiled = true;
     }
 #endif

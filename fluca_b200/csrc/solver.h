@@ -4,6 +4,7 @@
 #include "stencil.h"
 #include "ibm.h"
 #include <memory>
+#include <string>
 
 namespace fluca {
 
@@ -203,6 +204,7 @@ void set_ainv_types(Solver &s, int schur_type, int upper_type); // PCABFSetSchur
 // out = vol (rho/dt) S' p for the DIAG / ROWSUM Schur complement, returns <a, out> (uses s.tw)
 double schur_variant_apply_dot(Solver &s, double *pin, double *out, const double *a);
 int  do_step(Solver &s, double t, int step_index);
+double bench_kernel(Solver &s, const std::string &name); // one launch of a named kernel group (tools/kernel_bench.py)
 
 #ifndef FLUCA_HOSTEMU
 // TMA-staged versions of the hot 3-D operators (tiles.cu); tma_usable() says whether the mesh qualifies

@@ -181,10 +181,24 @@ void solver_setup(Solver &s, int dim, const int n[3], const double *const xf[3],
   s.rm = s.alloc_v3(), s.ri = s.alloc_v3(), s.rc = s.alloc_field();
   s.xv = s.alloc_v3(), s.xU = s.alloc_v3(), s.xp = s.alloc_field();
   s.vstar = s.alloc_v3(), s.Ustar = s.alloc_v3(), s.srhs = s.alloc_field();
-  s.kr = s.alloc_v3(), s.krh = s.alloc_v3(), s.kp = s.alloc_v3(), s.kv = s.alloc_v3(), s.ks = s.alloc_v3(), s.kt = s.alloc_v3();
-  s.pr = s.alloc_field(), s.pp = s.alloc_field(), s.pq = s.alloc_field();
-  if (s.has_outlet) s.ps = s.alloc_field(), s.pt = s.alloc_field(), s.prh = s.alloc_field();
-  s.tw = s.alloc_v3();
+  // Krylov work space.  BASELINE config 5 (2.2 GB per field and GPU) only fits the coupled mode if work vectors whose lives
+  // never overlap share storage:
+  //  * BiCGStab's s overwrites r in place (s = r - alpha v, then r = s - omega t): five vectors, not six;
+  //  * the pressure Krylov vectors and the cell scratch tw live only between two momentum solves, when the momentum
+  //    vectors r^, p, v, t are dead: they are views of those (all cell-located: their padding stays zero);
+  //  * the work vector of the restart residual is the last basis vector, which is free at a cycle start (below).
+  s.kr = s.alloc_v3(), s.krh = s.alloc_v3(), s.kp = s.alloc_v3(), s.kv = s.alloc_v3(), s.kt = s.alloc_v3();
+  s.ks = s.kr;
+  {
+    std::vector<double *> scratch;
+    for (const V3 *q : {&s.krh, &s.kp, &s.kv, &s.kt})
+      for (int c = 0; c < dim; ++c) scratch.push_back(q->c[c]);
+    size_t at = 0;
+    s.pr = scratch[at++], s.pp = scratch[at++], s.pq = scratch[at++];
+    s.ps = scratch[at++], s.pt = scratch[at++], s.prh = scratch[at++]; // BiCGStab forms (pressure outlet, DIAG / ROWSUM Schur complement)
+    s.tw = V3{{nullptr, nullptr, nullptr}};
+    for (int c = 0; c < dim; ++c) s.tw.c[c] = scratch[at++];
+  }
   if (opt.mode == 0) {
     s.basis_size = opt.outer_restart + 1;
     s.basis.resize(s.basis_size);
@@ -199,7 +213,9 @@ void solver_setup(Solver &s, int dim, const int n[3], const double *const xf[3],
       for (int f = 0; f < 7; ++f)
         if (dim == 3 || (f != 2 && f != 5)) vec[f] = s.alloc_field();
     }
-    s.wv = s.alloc_v3(), s.wU = s.alloc_v3(), s.wp = s.alloc_field();
+    // r = b - M x of a restart is formed in the last basis vector (free until the cycle reaches it)
+    for (int c = 0; c < 3; ++c) s.wv.c[c] = s.basis[opt.outer_restart][c], s.wU.c[c] = s.basis[opt.outer_restart][3 + c];
+    s.wp = s.basis[opt.outer_restart][6];
     for (int c = 0; c < 3; ++c) s.zv.c[c] = s.zbasis[0][c], s.zU.c[c] = s.zbasis[0][3 + c];
     s.zp = s.zbasis[0][6];
   }
@@ -247,6 +263,30 @@ static Box cell_box(const Solver &s)
   Box b = {s.gh.g.nx, s.gh.g.ny, s.gh.g.nzl};
   return b;
 }
+
+// Resident CTAs per SM the streaming box kernels of this file are compiled for (FLUCA_B200_BOX_MINB = 2, 3 or 4: 128 / 80 / 64
+// registers per thread).  These kernels keep one plane of loads in flight per thread, so their bandwidth follows occupancy.
+static int box_minb()
+{
+  static const int v = getenv("FLUCA_B200_BOX_MINB") ? atoi(getenv("FLUCA_B200_BOX_MINB")) : 3;
+  return v;
+}
+#define FOR_BOX_MINB(U, box, f) \
+  do { \
+    switch (box_minb()) { \
+    case 2: for_box<U, 2>(s.ex, box, f); break; \
+    case 4: for_box<U, 4>(s.ex, box, f); break; \
+    default: for_box<U, 3>(s.ex, box, f); break; \
+    } \
+  } while (0)
+#define FOR_BOX_REDUCE_MINB(NR, box, f) \
+  do { \
+    switch (box_minb()) { \
+    case 2: for_box_reduce<NR, 2>(s.ex, box, f); break; \
+    case 4: for_box_reduce<NR, 4>(s.ex, box, f); break; \
+    default: for_box_reduce<NR, 3>(s.ex, box, f); break; \
+    } \
+  } while (0)
 
 // f(i, j, kl) over the cells adjacent to boundary b held by this rank
 template <class F>
@@ -338,7 +378,6 @@ void set_ainv_types(Solver &s, int schur_type, int upper_type)
   s.opt.schur_ainv = schur_type, s.opt.upper_ainv = upper_type;
   if (schur_type != 0) {
     if (!s.ainv_store[0].c[0]) s.ainv_store[0] = s.alloc_v3();
-    if (!s.ps) s.ps = s.alloc_field(), s.pt = s.alloc_field(), s.prh = s.alloc_field(); // the Schur complement loses its symmetry: BiCGStab
   }
   if (upper_type != 0 && upper_type != schur_type && !s.ainv_store[1].c[0]) s.ainv_store[1] = s.alloc_v3();
   s.ainv_s = schur_type != 0 ? s.ainv_store[0] : V3{};
@@ -445,7 +484,7 @@ static void abf_apply_t(Solver &s, const V3 &bm, const V3 &bi, const double *bcn
   halo_faces(s, bi); // the upper z face of the slab's last plane is formed from r_int's ghost face plane and v*'s ghost plane
   FaceStarRhs<DIM> fs;
   fs.g = g, fs.a = in_scale, fs.scale = s.sp.rho / s.sp.dt, fs.rcscale = in_scale, fs.in = CV3(bi), fs.w = CV3(s.vstar), fs.rc = bcn, fs.Us = s.Ustar, fs.out = s.srhs;
-  for_box_reduce<1>(s.ex, cell_box(s), fs);
+  FOR_BOX_REDUCE_MINB(1, cell_box(s), fs);
   if (!s.has_outlet) {
     // constant null space (abfpc.c:173-177): make the right-hand side compatible
     double sum;
@@ -462,7 +501,7 @@ static void abf_apply_t(Solver &s, const V3 &bm, const V3 &bi, const double *bcn
   if (s.opt.upper_ainv == 0) {
     ProjectAll<DIM> pa; // v = v* - G~ p and U = U* - G~st p in one pass
     pa.g = g, pa.dtrho = s.sp.dtrho, pa.vs = CV3(s.vstar), pa.Us = CV3(s.Ustar), pa.p = op, pa.v = ov, pa.U = oU;
-    for_box<2>(s.ex, cell_box(s), pa);
+    FOR_BOX_MINB(2, cell_box(s), pa);
   } else {
     // DIAG / ROWSUM (abfpc.c:81-99): v = v* - a1 G~ p,  V = V* - T (a1 G~ p) - (-R) p = V* - G~st p + T w,  w = (1 - a1) G~ p
     GradScaleCells<DIM> gs;
@@ -506,7 +545,7 @@ static void coupled_apply_t(Solver &s, const V3 &xv, const V3 &xU, double *xp, c
   halo_faces(s, xU);
   DivCell<DIM> dc;
   dc.g = g, dc.U = CV3(xU), dc.out = yp;
-  for_box<2>(s.ex, cell_box(s), dc);
+  FOR_BOX_MINB(2, cell_box(s), dc);
 }
 
 // M z for z = ABF(b): only the momentum and continuity blocks need arithmetic -- y_v = A z_v + (dt/rho) G z_p, y_p = D z_U; the
@@ -532,7 +571,7 @@ static void coupled_apply_abf_output_t(Solver &s, const V3 &zv, const V3 &zU, do
   halo_faces(s, zU);
   DivCell<DIM> dc;
   dc.g = g, dc.U = CV3(zU), dc.out = yp;
-  for_box<2>(s.ex, cell_box(s), dc);
+  FOR_BOX_MINB(2, cell_box(s), dc);
 }
 
 static void coupled_apply_abf_output(Solver &s, const V3 &zv, const V3 &zU, double *zp, const V3 &yv, double *yp)
@@ -944,6 +983,51 @@ static int outer_gmres(Solver &s)
   s.stats.outer_rnorm0 = rnorm0;
   s.stats.outer_rnorm  = rnorm;
   return s.stats.converged ? 0 : 1;
+}
+
+// ------------------------------------------------------------------ single-kernel launches for tools/kernel_bench.py
+// (fluca_b200_time_kernel): one launch of the named kernel group on scratch fields of a prepared step; returns its algorithmic
+// bytes per cell (3-D)
+double bench_kernel(Solver &s, const std::string &n)
+{
+  const Geom &g = s.gh.g;
+  if (n == "face_star_rhs") {
+    if (s.dim == 3) {
+      FaceStarRhs<3> fs;
+      fs.g = g, fs.a = 1., fs.scale = s.sp.rho / s.sp.dt, fs.rcscale = 1., fs.in = CV3(s.ri), fs.w = CV3(s.vstar), fs.rc = s.rc, fs.Us = s.Ustar, fs.out = s.srhs;
+      FOR_BOX_REDUCE_MINB(1, cell_box(s), fs);
+    }
+    return 88.;
+  }
+  if (n == "project_all") {
+    if (s.dim == 3) {
+      ProjectAll<3> pa;
+      pa.g = g, pa.dtrho = s.sp.dtrho, pa.vs = CV3(s.vstar), pa.Us = CV3(s.Ustar), pa.p = s.xp, pa.v = s.xv, pa.U = s.xU;
+      FOR_BOX_MINB(2, cell_box(s), pa);
+    }
+    return 104.;
+  }
+  if (n == "div_cell") {
+    if (s.dim == 3) {
+      DivCell<3> dc;
+      dc.g = g, dc.U = CV3(s.xU), dc.out = s.srhs;
+      FOR_BOX_MINB(2, cell_box(s), dc);
+    }
+    return 32.;
+  }
+  if (n == "coupled_abf_output") {
+    coupled_apply_abf_output(s, s.xv, s.xU, s.xp, s.vstar, s.srhs);
+    return 96. + 8. + 32.; // y_v = A z_v + G~ z_p (x, v0, U0, p -> y) and y_p = D z_U, as SURVEY 8(d) would count them
+  }
+  if (n == "momentum_rhs") {
+    if (s.dim == 3) {
+      MomentumRhs<3> mr;
+      mr.g = g, mr.sp = s.sp, mr.bc = s.bc, mr.v0 = CV3(s.v0), mr.q = s.phalf, mr.r = s.rm;
+      for_box(s.ex, cell_box(s), mr);
+    }
+    return 56.;
+  }
+  throw Error(FL_ERR_ARG, "unknown kernel name");
 }
 
 // ------------------------------------------------------------------ the step

@@ -74,7 +74,8 @@ bool tma_usable(const Solver &s)
 {
   static const bool off = getenv("FLUCA_B200_NO_TMA") != nullptr;
   const Geom       &g   = s.gh.g;
-  return !off && s.dim == 3 && !g.t[0].per && !g.t[1].per && g.nx >= TMX && g.ny >= TMY;
+  // periodic x is served by the wrap fix-up of the first / last tile of a row (tma.h); periodic y is not
+  return !off && s.dim == 3 && !g.t[1].per && g.nx >= TMX && g.ny >= TMY;
 }
 
 // ------------------------------------------------------------------ momentum operator from shared-memory tiles
@@ -97,7 +98,7 @@ __device__ __forceinline__ void a_apply_tile(const Geom &g, const StepParams &sp
     const Tab    &T  = g.t[d];
     const int     ig = d == 0 ? i : (d == 1 ? j : g.k0 + kl);
     // planes that touch a z wall never reach this function (a_apply_dots sends them to the direct-load kernel)
-    const bool    lo = BND && d < 2 && ig == 0, hi = BND && d < 2 && ig == T.n - 1;
+    const bool    lo = BND && d < 2 && !T.per && ig == 0, hi = BND && d < 2 && !T.per && ig == T.n - 1;
     const double *nm = d == 2 ? tv.pm : tv.p0, *np = d == 2 ? tv.pp : tv.p0;
     const int     st = d == 0 ? 1 : (d == 1 ? TLX : 0);
     const int     om = lc - st, op = lc + st;
@@ -198,15 +199,7 @@ __device__ __forceinline__ void a_apply_tile_uniform(const UniCoef &u, const Ste
 
 template <int NRED>
 struct AApplyTile : TileOpDefaults {
-  static const int  NIN = 9, NR = NRED, MINB = 2, STAGES = 4;
-  static const bool SIDE = true;
-  // side work: the cells whose rows reach two cells inward (one-sided wall rows) and would drag a whole warp down the
-  // table-driven path -- the two x-wall columns of the tiled planes and the planes at a physical z wall.  They used to be
-  // four extra launches (17 % of the operator's time at 256^3 for < 1 % of the cells, profiles/r02n); now they are extra CTAs
-  // of the SAME launch, scheduled first, whose scattered loads run under the tile stream.
-  CV3              xg, v0g, U0g; // global pointers of the tile fields, for the side CTAs
-  const double    *pg = nullptr; // pressure of the coupled velocity block (the side cells form their own gradient)
-  int              zwall[2] = {-1, -1}; // local planes at a physical z wall (-1: none)
+  static const int NIN = 9, NR = NRED, MINB = 2, STAGES = 4;
   Geom             g;
   StepParams       sp;
   BcDev            bc;
@@ -221,59 +214,10 @@ struct AApplyTile : TileOpDefaults {
   };
   // bit 0: no wall in reach in x and y; bit 1: x-wall column, computed by the transposed wall launch instead (a single
   // wall lane would send its whole warp down the table-driven path: 12-25 % of the warps, profiles/r01p)
-  __device__ int flags(int i, int j) const { return ((i > 0 && i < g.nx - 1 && j > 0 && j < g.ny - 1) ? 1 : 0) | ((i == 0 || i == g.nx - 1) ? 2 : 0); }
-  __host__ int side_blocks(const TmaGrid &tg) const
+  __device__ int flags(int i, int j) const
   {
-    const int gy = (g.ny + 31) / 32, gk = tg.kend > tg.kbeg ? (tg.kend - tg.kbeg + 7) / 8 : 0;
-    const int gp = ((g.nx + 31) / 32) * ((g.ny + 7) / 8);
-    return 2 * gy * gk + ((zwall[0] >= 0) + (zwall[1] >= 0)) * gp;
-  }
-  __device__ void side_cell(int i, int j, int kl, double *acc) const
-  {
-    double r[3];
-    a_apply_cell<3>(g, sp, bc, xg, v0g, U0g, i, j, kl, r);
-    const int c = g.idx(i, j, kl);
-    if (NRED == 0 && wout[0]) {
-      Nbr<3> nb;
-      nbr<3>(g, i, j, kl, nb);
-      double gp[3];
-      grad_cell<3>(g, pg, nb, gp);
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        y[q][c] = r[q] + sp.dtrho * gp[q];
-        if (keep_w) wout[q][c] = xg.c[q][c] + sp.dtrho * gp[q];
-      }
-      return;
-    }
-    double d0 = 0., d1 = 0.;
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      y[q][c] = r[q];
-      if (NRED > 0) {
-        const double av = a[q] ? a[q][c] : xg.c[q][c];
-        d0 += av * r[q];
-        d1 += r[q] * r[q];
-      }
-    }
-    if (NRED > 0) acc[0] += d0, acc[1] += d1;
-  }
-  __device__ void side(const TmaGrid &tg, int b, int tx, int ty, double *acc) const
-  {
-    const int gy = (g.ny + 31) / 32, gk = tg.kend > tg.kbeg ? (tg.kend - tg.kbeg + 7) / 8 : 0;
-    const int nxw = 2 * gy * gk;
-    if (b < nxw) {
-      // an x-wall column: the CTA covers 32 rows j x 8 planes, so that a warp holds 32 wall cells
-      const int sd = b / (gy * gk), r = b % (gy * gk);
-      const int j = (r % gy) * 32 + tx, kl = tg.kbeg + (r / gy) * 8 + ty;
-      if (j < g.ny && kl < tg.kend) side_cell(sd ? g.nx - 1 : 0, j, kl, acc);
-      return;
-    }
-    b -= nxw;
-    const int gx = (g.nx + 31) / 32, gp = gx * ((g.ny + 7) / 8);
-    const int which = b / gp, r = b % gp;
-    const int kl = (which == 0 && zwall[0] >= 0) ? zwall[0] : zwall[1];
-    const int i = (r % gx) * 32 + tx, j = (r / gx) * 8 + ty;
-    if (i < g.nx && j < g.ny) side_cell(i, j, kl, acc);
+    const bool xin = g.t[0].per || (i > 0 && i < g.nx - 1);
+    return ((xin && j > 0 && j < g.ny - 1) ? 1 : 0) | ((!g.t[0].per && (i == 0 || i == g.nx - 1)) ? 2 : 0);
   }
   __device__ void prefetch(Regs &rg, int off, int kl) const
   {
@@ -316,51 +260,94 @@ struct AApplyTile : TileOpDefaults {
   }
 };
 
-static UniCoef uni_coef(const Geom &g)
-{
-  UniCoef uc;
-  uc.l4 = 0.;
-  for (int d = 0; d < 3; ++d) uc.q[d] = 0.25 / g.t[d].uh, uc.l[d] = 1. / (g.t[d].uh * g.t[d].uh), uc.l4 += 4. * uc.l[d];
-  return uc;
-}
+// shifts the plane index of a box functor (the z-wall planes are launched as 1-plane boxes)
+template <class F>
+struct PlaneAt {
+  F   f;
+  int kl;
+  FL_HD void operator()(int i, int j, int, double *acc) const { f(i, j, kl, acc); }
+};
 
-template <class Op>
-static void a_tile_common(Solver &s, Op &op, const V3 &x, int &kbeg, int &kend)
+// the two x-wall columns of planes [kbeg, kend): a block covers 32 rows j x 8 planes, so that a warp holds 32 wall cells
+// and all eight warps of a block work (box = {ny, planes, 1})
+template <class F>
+struct XWallAt {
+  F   f;
+  int i, kbeg;
+  FL_HD void operator()(int a, int b, int, double *acc) const { f(i, a, kbeg + b, acc); }
+};
+
+// y = A x ; out[0] = <a, y>, out[1] = <y, y> are left in ex.d_result (reduce_finish reads them)
+void a_apply_dots_tma(Solver &s, const V3 &x, const V3 &y, const V3 &a, bool with_dots)
 {
   const Geom &g  = s.gh.g;
   const bool  wl = g.t[2].wall_lo && !g.t[2].per, wh = g.t[2].wall_hi && !g.t[2].per;
-  static const bool no_uni = getenv("FLUCA_B200_NO_UNIFORM") != nullptr;
-  op.g = g, op.sp = s.sp, op.bc = s.bc, op.uc = uni_coef(g);
-  op.uniform = (!no_uni && g.t[0].uni && g.t[1].uni && g.t[2].uni) ? 1 : 0;
-  op.xg = CV3(x), op.v0g = CV3(s.v0), op.U0g = CV3(s.U0);
-  // planes that touch a physical z wall need the one-sided 4-point rows (cells k +- 2): side CTAs
-  kbeg = wl ? 1 : 0;
-  kend = wh ? g.nzl - 1 : g.nzl;
+  KGroup      grp(s.ex, KT_MOMENTUM_APPLY);
+  // 1. the (up to two) planes at physical z walls: direct-load kernel with the one-sided rows
+  const double *carry = nullptr;
+  int           ncar  = 0;
+  AApplyDots<3> f;
+  f.g = g, f.sp = s.sp, f.bc = s.bc, f.x = CV3(x), f.v0 = CV3(s.v0), f.U0 = CV3(s.U0), f.a = CV3(with_dots ? a : x), f.y = y;
+  const Box plane_box = {g.nx, g.ny, 1};
+  const int kbeg = wl ? 1 : 0;
+  int       kend = wh ? g.nzl - 1 : g.nzl;
   if (kend < kbeg) kend = kbeg;
-  op.zwall[0] = wl ? 0 : -1;
-  op.zwall[1] = (wh && g.nzl - 1 >= kbeg) ? g.nzl - 1 : -1;
-}
-
-// y = A x ; out[0] = <a, y>, out[1] = <y, y> are left in ex.d_result (reduce_finish reads them).  ONE launch: tile CTAs for
-// the planes and columns away from the walls, side CTAs for the rest.
-void a_apply_dots_tma(Solver &s, const V3 &x, const V3 &y, const V3 &a, bool with_dots)
-{
-  const Geom   &g = s.gh.g;
-  KGroup        grp(s.ex, KT_MOMENTUM_APPLY);
+  if (wl) {
+    PlaneAt<AApplyDots<3>> pf = {f, 0};
+    double                *res = s.ex.d_carry + Exec::MAXR * ncar;
+    for_box_reduce<2>(s.ex, plane_box, pf, carry, res);
+    carry = res, ++ncar;
+  }
+  if (wh && g.nzl - 1 >= kbeg) {
+    PlaneAt<AApplyDots<3>> pf = {f, g.nzl - 1};
+    double                *res = s.ex.d_carry + Exec::MAXR * ncar;
+    for_box_reduce<2>(s.ex, plane_box, pf, carry, res);
+    carry = res, ++ncar;
+  }
+  // 2. the x-wall columns of the remaining planes
+  if (kend > kbeg && !g.t[0].per) {
+    const Box wall_box = {g.ny, kend - kbeg, 1};
+    for (int side = 0; side < 2; ++side) {
+      XWallAt<AApplyDots<3>> xf = {f, side ? g.nx - 1 : 0, kbeg};
+      double                *res = s.ex.d_carry + Exec::MAXR * ncar;
+      for_box_reduce<2>(s.ex, wall_box, xf, carry, res);
+      carry = res, ++ncar;
+    }
+  }
+  // 3. everything else through the TMA pipeline
   const double *fields[9] = {x.c[0], x.c[1], x.c[2], s.v0.c[0], s.v0.c[1], s.v0.c[2], s.U0.c[0], s.U0.c[1], s.U0.c[2]};
-  int           kbeg, kend;
+  UniCoef       uc;
+  static const bool no_uni = getenv("FLUCA_B200_NO_UNIFORM") != nullptr;
+  const int     uniform = (!no_uni && g.t[0].uni && g.t[1].uni && g.t[2].uni) ? 1 : 0;
+  uc.l4 = 0.;
+  for (int d = 0; d < 3; ++d) uc.q[d] = 0.25 / g.t[d].uh, uc.l[d] = 1. / (g.t[d].uh * g.t[d].uh), uc.l4 += 4. * uc.l[d];
   if (with_dots) {
     AApplyTile<2> op;
-    a_tile_common(s, op, x, kbeg, kend);
+    op.g = g, op.sp = s.sp, op.bc = s.bc, op.uc = uc, op.uniform = uniform;
     for (int c = 0; c < 3; ++c) op.a[c] = (a.c[c] == x.c[c]) ? nullptr : a.c[c], op.y[c] = y.c[c], op.wout[c] = nullptr;
-    tma_launch(s.ex, op, fields, g.px, g.py, g.nzl + 2, g.nx, g.ny, kbeg, kend, nullptr);
+    tma_launch(s.ex, op, fields, g.px, g.py, g.nzl + 2, g.nx, g.ny, kbeg, kend, carry, g.t[0].per != 0);
   } else {
     AApplyTile<0> op;
-    a_tile_common(s, op, x, kbeg, kend);
+    op.g = g, op.sp = s.sp, op.bc = s.bc, op.uc = uc, op.uniform = uniform;
     for (int c = 0; c < 3; ++c) op.a[c] = nullptr, op.y[c] = y.c[c], op.wout[c] = nullptr;
-    tma_launch(s.ex, op, fields, g.px, g.py, g.nzl + 2, g.nx, g.ny, kbeg, kend, nullptr);
+    tma_launch(s.ex, op, fields, g.px, g.py, g.nzl + 2, g.nx, g.ny, kbeg, kend, nullptr, g.t[0].per != 0);
   }
+  (void)ncar;
 }
+
+// plain (no reduction) versions of the wall adapters
+template <class F>
+struct PlaneAtPlain {
+  F   f;
+  int kl;
+  FL_HD void operator()(int i, int j, int) const { f(i, j, kl); }
+};
+template <class F>
+struct XWallAtPlain {
+  F   f;
+  int i, kbeg;
+  FL_HD void operator()(int a, int b, int) const { f(i, a, kbeg + b); }
+};
 
 // velocity block of the coupled operator: y = A x + (dt/rho) G p, w = x + (dt/rho) G p
 void coupled_cells_tma(Solver &s, const V3 &x, const double *p, const V3 &y, const V3 &w, bool keep_w)
@@ -371,21 +358,47 @@ void coupled_cells_tma(Solver &s, const V3 &x, const double *p, const V3 &y, con
   gc.g = g, gc.dtrho = s.sp.dtrho, gc.p = p, gc.w = w;
   const Box all = {g.nx, g.ny, g.nzl};
   for_box<2>(s.ex, all, gc);
-  // 2. one launch: tiles + side CTAs (the side cells form the gradient themselves)
+  // 2. wall planes and wall columns with the direct-load functor (it forms the gradient itself)
+  const bool wl = g.t[2].wall_lo && !g.t[2].per, wh = g.t[2].wall_hi && !g.t[2].per;
+  CoupledCells<3> f;
+  f.g = g, f.sp = s.sp, f.bc = s.bc, f.x = CV3(x), f.v0 = CV3(s.v0), f.U0 = CV3(s.U0), f.p = p, f.y = y, f.w = keep_w ? w : V3{{nullptr, nullptr, nullptr}};
+  const Box plane_box = {g.nx, g.ny, 1};
+  const int kbeg = wl ? 1 : 0;
+  int       kend = wh ? g.nzl - 1 : g.nzl;
+  if (kend < kbeg) kend = kbeg;
+  if (wl) {
+    PlaneAtPlain<CoupledCells<3>> pf = {f, 0};
+    for_box(s.ex, plane_box, pf);
+  }
+  if (wh && g.nzl - 1 >= kbeg) {
+    PlaneAtPlain<CoupledCells<3>> pf = {f, g.nzl - 1};
+    for_box(s.ex, plane_box, pf);
+  }
+  if (kend > kbeg && !g.t[0].per) {
+    const Box wall_box = {g.ny, kend - kbeg, 1};
+    for (int side = 0; side < 2; ++side) {
+      XWallAtPlain<CoupledCells<3>> xf = {f, side ? g.nx - 1 : 0, kbeg};
+      for_box(s.ex, wall_box, xf);
+    }
+  }
+  // 3. everything else from TMA tiles
   const double *fields[9] = {x.c[0], x.c[1], x.c[2], s.v0.c[0], s.v0.c[1], s.v0.c[2], s.U0.c[0], s.U0.c[1], s.U0.c[2]};
+  UniCoef       uc;
+  static const bool no_uni = getenv("FLUCA_B200_NO_UNIFORM") != nullptr;
+  uc.l4 = 0.;
+  for (int d = 0; d < 3; ++d) uc.q[d] = 0.25 / g.t[d].uh, uc.l[d] = 1. / (g.t[d].uh * g.t[d].uh), uc.l4 += 4. * uc.l[d];
   AApplyTile<0> op;
-  int           kbeg, kend;
-  a_tile_common(s, op, x, kbeg, kend);
+  op.g = g, op.sp = s.sp, op.bc = s.bc, op.uc = uc, op.uniform = (!no_uni && g.t[0].uni && g.t[1].uni && g.t[2].uni) ? 1 : 0;
   for (int c = 0; c < 3; ++c) op.a[c] = nullptr, op.y[c] = y.c[c], op.wout[c] = w.c[c];
-  op.keep_w = keep_w ? 1 : 0, op.pg = p;
-  tma_launch(s.ex, op, fields, g.px, g.py, g.nzl + 2, g.nx, g.ny, kbeg, kend, nullptr);
+  op.keep_w = keep_w ? 1 : 0;
+  tma_launch(s.ex, op, fields, g.px, g.py, g.nzl + 2, g.nx, g.ny, kbeg, kend, nullptr, g.t[0].per != 0);
 }
 
 // ------------------------------------------------------------------ Poisson operator from shared-memory tiles
 // No plane needs special treatment: the wall rows of P use the cells (c, c+1) / (c-1, c) only.
 template <int NRED>
 struct PoissonTile : TileOpDefaults {
-  static const int NIN = 1, NR = NRED, MINB = 4, STAGES = 8;
+  static const int NIN = 1, NR = NRED, MINB = 4, STAGES = 8, PLANES = FL_TILE_PLANES;
   Geom             g;
   const double    *a; // dot partner; nullptr: p itself
   double          *out;
@@ -394,7 +407,7 @@ struct PoissonTile : TileOpDefaults {
   struct Regs {
     double a;
   };
-  __device__ int flags(int i, int j) const { return (uniform && i > 0 && i < g.nx - 1 && j > 0 && j < g.ny - 1) ? 1 : 0; }
+  __device__ int flags(int i, int j) const { return (uniform && (g.t[0].per || (i > 0 && i < g.nx - 1)) && j > 0 && j < g.ny - 1) ? 1 : 0; }
   __device__ void prefetch(Regs &rg, int off, int kl) const
   {
     if (NRED > 0 && a) rg.a = a[off];
@@ -426,7 +439,7 @@ void poisson_apply_dot_tma(Solver &s, const double *pin, double *out, const doub
     for (int d = 0; d < 3; ++d) op.cd[d] = (hu[0] * hu[1] * hu[2] / hu[d]) / hu[d];
   }
   const double *fields[1] = {pin};
-  tma_launch(s.ex, op, fields, g.px, g.py, g.nzl + 2, g.nx, g.ny, 0, g.nzl, nullptr);
+  tma_launch(s.ex, op, fields, g.px, g.py, g.nzl + 2, g.nx, g.ny, 0, g.nzl, nullptr, g.t[0].per != 0);
 }
 
 } // namespace fluca

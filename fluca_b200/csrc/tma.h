@@ -26,6 +26,9 @@
 namespace fluca {
 
 static const int TMX = 32, TMY = 8;             // cells per tile (one warp = one 32-cell row)
+#ifndef FL_TILE_PLANES
+#define FL_TILE_PLANES 2 // planes per CTA barrier of the 1-field tile operators (build with -DFL_TILE_PLANES=1 for A/B runs)
+#endif
 // box with halo.  The innermost start coordinate of a TMA box must be 16-byte aligned (measured on B200 with
 // tools/tma_probe.cu: an odd fp64 start coordinate raises "illegal instruction", even ones -- negative or
 // not -- are fine), so the x halo is two cells wide and tile origins are even.
@@ -39,7 +42,8 @@ static const int TILE_STRIDE = 368;             // doubles between consecutive f
 
 template <int NIN>
 struct alignas(64) TmaIn {
-  CUtensorMap m[NIN];
+  CUtensorMap   m[NIN];
+  const double *p[NIN]; // the same arrays as plain pointers (periodic-x wrap columns are patched in with ordinary loads)
 };
 
 struct TmaGrid {
@@ -47,7 +51,7 @@ struct TmaGrid {
   int nx, ny;     // cells
   int kbeg, kend; // local planes [kbeg, kend) computed by this launch
   int ntx, nty, nchunk;
-  int nside;      // CTAs [0, nside) of the launch run the operator's side work (Op::SIDE) instead of a tile column
+  int perx;       // x is periodic: the halo columns of the first / last tile of a row hold the wrapped cells
 };
 
 // tensor map of one field array laid out (px, py, nplanes) doubles; cached per (pointer, extents)
@@ -108,10 +112,7 @@ struct TileOpDefaults {
   static const int  ZALIGN  = 1;     // chunk boundaries are multiples of ZALIGN planes
   static const int  SCRATCH = 0;     // bytes of CTA scratch in shared memory
   static const bool POST    = false; // post(...) is called after the plane barrier (sees what every thread wrote to scratch)
-  // SIDE: the launch carries extra CTAs (the first tg.nside block indices, so that they are scheduled first and overlap the
-  // tile stream) that run op.side(tg, b, acc) with direct loads -- the cells the tile path leaves out (wall columns / planes
-  // with one-sided rows).  int side_blocks(const TmaGrid &) says how many.
-  static const bool SIDE    = false;
+  static const int  PLANES  = 1;     // planes computed per CTA barrier (needs STAGES >= PLANES + 3)
 };
 
 __device__ __forceinline__ void mbar_wait_addr(uint32_t bar, unsigned parity)
@@ -126,6 +127,24 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t bar, unsigned parity)
                  : "memory");
     if (!ok && ++spins > (1u << 22)) __trap(); // a protocol bug traps after ~seconds instead of hanging the GPU
   } while (!ok);
+}
+
+// Periodic x: the TMA unit zero-fills the halo columns left of column 0 and reads padding right of column nx - 1.  The CTAs
+// that own the first / last tile of a row overwrite those two halo columns of a freshly arrived plane with the cells from the
+// other end of the row (plain loads; 2 x TMY x NIN values), then the CTA synchronises.  Only 2 of the nx / 32 CTAs of a row
+// pay for it.  (A second TMA box cannot land inside the halo columns of the tile: a box is dense in shared memory.)
+template <int NIN>
+__device__ __forceinline__ void wrap_fix(double *slot, const TmaIn<NIN> &in, const TmaGrid &tg, int i0, int j0, int zplane, bool wl, bool wr)
+{
+  constexpr int PER = NIN * TMY * 2;
+  const int     n   = ((wl ? 1 : 0) + (wr ? 1 : 0)) * PER;
+  for (int e = threadIdx.x; e < n; e += TMX * TMY) {
+    const bool right = wl ? (e >= PER) : true;
+    const int  r = e % PER, f = r / (TMY * 2), row = (r % (TMY * 2)) >> 1, cc = r & 1;
+    const int  gcol = right ? cc : tg.nx - 2 + cc;
+    const int  lcol = right ? THX + tg.nx - i0 + cc : cc;
+    if (lcol < TLX) slot[f * TILE_STRIDE + (row + 1) * TLX + lcol] = in.p[f][(size_t)gcol + (size_t)tg.px * ((size_t)(j0 + row) + (size_t)tg.py * (size_t)zplane)];
+  }
 }
 
 // Op interface:
@@ -152,19 +171,8 @@ __global__ void __launch_bounds__(TMX *TMY, Op::MINB) k_tma_march(const __grid_c
   double            *scratch = reinterpret_cast<double *>(tma_smem + (size_t)TMS * SLOT * sizeof(double) + TMS * sizeof(uint64_t));
   const uint32_t     ring_s = smem_u32(ring), full_s = smem_u32(full);
   const int tid = threadIdx.x, tx = tid & (TMX - 1), ty = tid / TMX;
-  if constexpr (Op::SIDE) {
-    if ((int)blockIdx.x < tg.nside) { // block-uniform branch: the whole CTA does side work
-      double sacc[Op::NR > 0 ? Op::NR : 1];
-#pragma unroll
-      for (int r = 0; r < (Op::NR > 0 ? Op::NR : 1); ++r) sacc[r] = 0.;
-      op.side(tg, (int)blockIdx.x, tx, ty, sacc);
-      if (Op::NR > 0) block_reduce_and_finish<(Op::NR > 0 ? Op::NR : 1)>(sacc, carry, partials, result, ticket, gridDim.x, blockIdx.x);
-      return;
-    }
-  }
   const int ntile = tg.ntx * tg.nty;
-  const int mb = (int)blockIdx.x - tg.nside; // index among the tile CTAs
-  const int tile = mb % ntile, bz = mb / ntile;
+  const int tile = blockIdx.x % ntile, bz = blockIdx.x / ntile;
   const int bx = tile % tg.ntx, by = tile / tg.ntx;
   const int i0 = min(bx * TMX, (tg.nx - TMX + 1) & ~1), j0 = min(by * TMY, tg.ny - TMY); // i0 even
   int       k0, k1;
@@ -174,6 +182,7 @@ __global__ void __launch_bounds__(TMX *TMY, Op::MINB) k_tma_march(const __grid_c
   const bool owned = (i >= bx * TMX) && (i < tg.nx) && (j >= by * TMY);
   const int  nplanes = k1 - k0 + 2; // ring index r <-> local plane k0 - 1 + r
   const int  cx = i0 - THX, cy = j0 - 1;
+  const bool wrap_l = tg.perx && i0 == 0, wrap_r = tg.perx && bx == tg.ntx - 1; // block-uniform
 
   if (tid == 0) {
 #pragma unroll
@@ -200,6 +209,11 @@ __global__ void __launch_bounds__(TMX *TMY, Op::MINB) k_tma_march(const __grid_c
   if (k0 < k1) {
     mbar_wait_addr(full_s, 0);
     mbar_wait_addr(full_s + 8, 0);
+    if (wrap_l || wrap_r) { // planes k0 - 1 and k0 (array planes k0, k0 + 1)
+      wrap_fix<Op::NIN>(ring, in, tg, i0, j0, k0, wrap_l, wrap_r);
+      wrap_fix<Op::NIN>(ring + SLOT, in, tg, i0, j0, k0 + 1, wrap_l, wrap_r);
+      __syncthreads();
+    }
   }
   TileView tv;
   tv.lc      = (ty + 1) * TLX + tx + THX;
@@ -210,31 +224,55 @@ __global__ void __launch_bounds__(TMX *TMY, Op::MINB) k_tma_march(const __grid_c
   int      sc = 1;          // ring slot of plane k+1 (after the advance at the top of the loop)
   unsigned par = 0;        // phase parity of slot sc
   int      zload = k0 + TMS; // TMA z coordinate of the next plane to request
-  for (int k = k0; k < k1; ++k) {
-    cur = nxt;
-    // operands read straight from global memory (one value per cell, no reuse) are requested a whole plane ahead
-    if (owned && k + 1 < k1) op.prefetch(nxt, off + pstride, k + 1);
-    sc = sc + 1 == TMS ? 0 : sc + 1;
-    if (sc == 0) par ^= 1u;
-    mbar_wait_addr(full_s + 8u * sc, par);
-    tv.pm = tv.p0;
-    tv.p0 = tv.pp;
-    tv.pp = ring + sc * SLOT;
-    if (owned) op.cell(tv, cur, fl, i, j, k, off, acc);
-    off += pstride;
-    __syncthreads(); // every thread is done with plane k-1: its slot may be refilled
-    if constexpr (Op::POST) op.post(tv, fl, owned, i, j, k, pstate);
-    if (tid == 0 && zload < k0 + nplanes) {
-      // the slot of plane k-1 is two behind sc
-      const int      sr  = sc >= 2 ? sc - 2 : sc - 2 + TMS;
-      const uint32_t bar = full_s + 8u * sr, dst = ring_s + (uint32_t)(sr * SLOT * sizeof(double));
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(TX_BYTES) : "memory");
+  // PL planes per trip: one CTA barrier (and one refill round of the producer thread) per PL planes.  The 1-field operators
+  // do so little per plane that the barrier was their main stall (profiles/r02n: PoissonTile 42 % of DRAM peak, 3.8 barrier
+  // stall cycles per issue); the ring must hold the PL + 2 live planes plus what is in flight (STAGES >= PL + 3).
+  constexpr int PL = Op::PLANES;
+  static_assert(TMS >= PL + 3, "ring too small for the planes per trip");
+  for (int k = k0; k < k1; k += PL) {
+    const int np = (k1 - k) < PL ? (k1 - k) : PL;
 #pragma unroll
-      for (int f = 0; f < Op::NIN; ++f)
-        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst + (uint32_t)(f * TILE_STRIDE * sizeof(double))), "l"(&in.m[f]), "r"(cx), "r"(cy), "r"(zload), "r"(bar)
-                     : "memory");
+    for (int q = 0; q < PL; ++q) {
+      if (q < np) {
+        cur = nxt;
+        // operands read straight from global memory (one value per cell, no reuse) are requested a whole plane ahead
+        if (owned && k + q + 1 < k1) op.prefetch(nxt, off + pstride, k + q + 1);
+        sc = sc + 1 == TMS ? 0 : sc + 1;
+        if (sc == 0) par ^= 1u;
+        mbar_wait_addr(full_s + 8u * sc, par);
+        if (wrap_l || wrap_r) { // plane k + q + 1 = array plane k + q + 2 just arrived in slot sc
+          wrap_fix<Op::NIN>(ring + sc * SLOT, in, tg, i0, j0, k + q + 2, wrap_l, wrap_r);
+          __syncthreads();
+        }
+        tv.pm = tv.p0;
+        tv.p0 = tv.pp;
+        tv.pp = ring + sc * SLOT;
+        if (owned) op.cell(tv, cur, fl, i, j, k + q, off, acc);
+        off += pstride;
+      }
     }
-    ++zload;
+    __syncthreads(); // every thread is done with planes k-1 .. k+np-2: their slots may be refilled
+    if constexpr (Op::POST) {
+#pragma unroll
+      for (int q = 0; q < PL; ++q)
+        if (q < np) op.post(tv, fl, owned, i, j, k + q, pstate);
+    }
+    if (tid == 0) {
+      // the slot of plane k+np-1-m (m = 1 .. np) is m + 1 behind sc; refill the oldest first
+      for (int m = np; m >= 1; --m) {
+        if (zload < k0 + nplanes) {
+          int sr = sc - 1 - m;
+          if (sr < 0) sr += TMS;
+          const uint32_t bar = full_s + 8u * sr, dst = ring_s + (uint32_t)(sr * SLOT * sizeof(double));
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(TX_BYTES) : "memory");
+#pragma unroll
+          for (int f = 0; f < Op::NIN; ++f)
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst + (uint32_t)(f * TILE_STRIDE * sizeof(double))), "l"(&in.m[f]), "r"(cx), "r"(cy), "r"(zload), "r"(bar)
+                         : "memory");
+        }
+        ++zload;
+      }
+    }
   }
   if (Op::NR > 0) block_reduce_and_finish<(Op::NR > 0 ? Op::NR : 1)>(acc, carry, partials, result, ticket, gridDim.x, blockIdx.x);
 }
@@ -258,9 +296,9 @@ inline int tma_pick_chunks(int ntile, int nplanes, int slots, long max_blocks)
 
 // launches Op over local planes [kbeg, kend); `fields` are the NIN input arrays in the order the operator expects
 template <class Op>
-inline void tma_launch(Exec &ex, const Op &op, const double *const *fields, int px, int py, int nplanes_alloc, int nx, int ny, int kbeg, int kend, const double *carry)
+inline void tma_launch(Exec &ex, const Op &op, const double *const *fields, int px, int py, int nplanes_alloc, int nx, int ny, int kbeg, int kend, const double *carry, bool perx = false)
 {
-  if (kend <= kbeg && !Op::SIDE) {
+  if (kend <= kbeg) {
     if (Op::NR > 0) {
       if (carry) copy_d2d(ex, ex.d_result, carry, sizeof(double) * Op::NR);
       else dev_zero(ex, ex.d_result, sizeof(double) * Op::NR);
@@ -268,21 +306,15 @@ inline void tma_launch(Exec &ex, const Op &op, const double *const *fields, int 
     return;
   }
   TmaIn<Op::NIN> in;
-  for (int f = 0; f < Op::NIN; ++f) in.m[f] = tensor_map_for(fields[f], px, py, nplanes_alloc);
+  for (int f = 0; f < Op::NIN; ++f) in.m[f] = tensor_map_for(fields[f], px, py, nplanes_alloc), in.p[f] = fields[f];
   TmaGrid tg;
+  tg.perx = perx ? 1 : 0;
   tg.px = px, tg.py = py, tg.nx = nx, tg.ny = ny, tg.kbeg = kbeg, tg.kend = kend;
   tg.ntx = (nx + TMX - 1) / TMX, tg.nty = (ny + TMY - 1) / TMY;
   if ((kend - kbeg) % Op::ZALIGN) throw Error(FL_ERR_INTERNAL, "plane range of a tile launch is not a multiple of the operator's alignment");
   tg.nchunk = tma_pick_chunks(tg.ntx * tg.nty, (kend - kbeg) / Op::ZALIGN, Op::MINB * ex.sm_count, ex.max_blocks);
-  tg.nside  = 0;
-  if constexpr (Op::SIDE) tg.nside = op.side_blocks(tg);
-  if (kend <= kbeg) tg.nchunk = 0; // no plane for the tile path: only side CTAs run (they never touch the ring)
-  if (tg.ntx * tg.nty * tg.nchunk + tg.nside == 0) {
-    if (Op::NR > 0) dev_zero(ex, ex.d_result, sizeof(double) * Op::NR);
-    return;
-  }
   // one block partial per CTA: a reducing operator must not start more CTAs than ex.d_partials has room for
-  if (Op::NR > 0 && (long)tg.ntx * tg.nty * tg.nchunk + tg.nside > ex.max_blocks) throw Error(FL_ERR_INTERNAL, "tile launch of a reducing operator exceeds the partial buffer");
+  if (Op::NR > 0 && (long)tg.ntx * tg.nty * tg.nchunk > ex.max_blocks) throw Error(FL_ERR_INTERNAL, "tile launch of a reducing operator exceeds the partial buffer");
   const size_t smem = (size_t)Op::STAGES * Op::NIN * TILE_STRIDE * sizeof(double) + Op::STAGES * sizeof(uint64_t) + Op::SCRATCH;
   static bool  configured = false; // per template instantiation
   if (!configured) {
@@ -291,7 +323,7 @@ inline void tma_launch(Exec &ex, const Op &op, const double *const *fields, int 
   }
   ex.stats.launches++;
   KTimer kt(ex, ex.kt_current);
-  k_tma_march<Op><<<(unsigned)(tg.ntx * tg.nty * tg.nchunk + tg.nside), TMX * TMY, smem, ex.stream>>>(in, op, tg, carry, ex.d_partials, ex.d_result, ex.d_ticket);
+  k_tma_march<Op><<<(unsigned)(tg.ntx * tg.nty * tg.nchunk), TMX * TMY, smem, ex.stream>>>(in, op, tg, carry, ex.d_partials, ex.d_result, ex.d_ticket);
   FL_CUDA(cudaGetLastError());
 }
 

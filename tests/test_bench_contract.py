@@ -127,3 +127,38 @@ def test_resident_e2e_loop_reads_every_step_result():
     last = s.staged_state()  # the drained copy is the final state
     assert np.array_equal(last["v"], st["v"]) and np.array_equal(last["p"], st["p"])
     fb.NSDestroy(ns)
+
+
+def _run_bench_world(world, tmp_path, workload="sphere", n=16):
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / f"bench_{workload}_{world}.json")
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1", BENCH_WORKLOAD=workload, BENCH_N=str(n))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "bench_worker.py"), out], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    logs = []
+    for p in procs:
+        try:
+            o, _ = p.communicate(timeout=900)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        logs.append(o)
+    assert all(p.returncode == 0 for p in procs), "\n".join(lg[-3000:] for lg in logs)
+    return json.loads(open(out).read())
+
+
+def test_gpu_arm_logic_multi_rank_gloo(tmp_path):
+    """bench.py's whole N > 1 flow (N-rank parity case against the oracle, strong-scaling headline, weak run) with 2 and 4 ranks
+    on the test double: every rank must issue the same collectives; the line carries parity, strong value and the weak run."""
+    for world in (2, 4):
+        d = _run_bench_world(world, tmp_path)
+        assert d["n_gpus"] == world and d["scaling"] == "strong" and d["value"] > 0
+        assert d["parity"]["ok"] and d["parity"]["ranks"] == world, d["parity"]
+        assert d["weak"]["value"] > 0 and "WEAK" in d["weak"]["workload"] and "STRONG" in d["config"]["workload"]

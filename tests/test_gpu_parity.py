@@ -41,6 +41,13 @@ CASES = [
     ("tma_cavity_sym", lambda: cases.cavity3d(n=(48, 24, 10)), 23, 1),
     ("tma_channel_outlet", lambda: cases.channel3d(n=(40, 16, 10), pout=0.2, dt=0.05), 29, 1),
     ("tma_channel_periodic_z", lambda: cases.channel3d(n=(33, 9, 8), periodic_z=True, dt=0.05), 31, 1),
+    # periodic x on the tile path (BASELINE config 5's boundary set): wrap columns of the first / last tile of a row; one tile
+    # per row (both wraps in one CTA), two tiles, a shifted last tile (odd nx), and two tiled multigrid levels
+    ("direct_channel5_periodic_xz", lambda: cases.channel_bench_case((16, 12, 12), periodic_z=True), 33, 2),
+    ("tma_channel5_one_tile_per_row", lambda: cases.channel_bench_case((32, 16, 8), periodic_z=True), 35, 1),
+    ("tma_channel5_two_tiles_sym_z", lambda: cases.channel_bench_case((64, 16, 8), periodic_z=False), 37, 1),
+    ("tma_channel5_shifted_last_tile", lambda: cases.channel_bench_case((50, 9, 6), periodic_z=True), 39, 1),
+    ("tma_channel5_two_mg_levels", lambda: cases.channel_bench_case((64, 32, 8), periodic_z=True), 41, 1),
 ]
 
 

@@ -29,6 +29,9 @@ CASES = [
     ("channel2d_outlet", lambda: cases.channel2d(n=(16, 8), pout=0.3, time_dependent=True), 7),
     ("channel3d_outlet", lambda: cases.channel3d(n=(8, 6, 6), pout=0.2, dt=0.05), 11),
     ("channel3d_periodic_z", lambda: cases.channel3d(n=(8, 6, 6), periodic_z=True, dt=0.05), 13),
+    # BASELINE config 5's boundary set: periodic x, no-slip walls in y, periodic or symmetry z
+    ("channel5_periodic_xz", lambda: cases.channel_bench_case((8, 6, 6), periodic_z=True), 15),
+    ("channel5_periodic_x_sym_z", lambda: cases.channel_bench_case((8, 6, 6), periodic_z=False), 16),
 ]
 
 
