@@ -123,6 +123,7 @@ SYMBOLS = [
     "fluca_b200_fd_tvd_set_current_solution",
     "fluca_b200_fd_set_locations",
     "fluca_b200_step_model_bytes_split",
+    "fluca_b200_ibm_info",
     "fluca_b200_fd_set_boundary_condition",
     "fluca_b200_fd_setup",
     "fluca_b200_fd_get_stencil",
@@ -182,6 +183,7 @@ def _prototype(L):
     L.fluca_b200_time_kernel.argtypes = [_P, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.fluca_b200_set_markers.argtypes = [_P, C.c_long, _P, _P, _P, C.c_int]
     L.fluca_b200_get_marker_forces.argtypes = [_P, _P, _P]
+    L.fluca_b200_ibm_info.argtypes = [_P, C.POINTER(C.c_long)]
     L.fluca_b200_ibm_interpolate.argtypes = [_P, _P, _P]
     L.fluca_b200_ibm_spread.argtypes = [_P, _P, _P]
     L.fluca_b200_set_ibm_iterations.argtypes = [_P, C.c_int]

@@ -631,12 +631,12 @@ extern "C" int fluca_b200_get_marker_forces(fluca_b200_solver *h, double *F, dou
 {
   API_BEGIN
   Solver &s = h->s;
-  const Ibm &b = s.ibm;
-  for (int d = 0; d < s.dim && b.n > 0; ++d) {
-    if (F) copy_d2h(s.ex, F + (size_t)b.n * d, b.F[d], sizeof(double) * b.n);
-    if (Um) copy_d2h(s.ex, Um + (size_t)b.n * d, b.Um[d], sizeof(double) * b.n);
+  Ibm    &b = s.ibm;
+  if (b.n > 0) {
+    // collective with several ranks: every marker's value comes from the rank that reports it
+    if (F) ibm_gather_global(s, b.F, F);
+    if (Um) ibm_gather_global(s, b.Um, Um);
   }
-  s.ex.sync();
   API_END
 }
 
@@ -647,8 +647,15 @@ extern "C" int fluca_b200_ibm_interpolate(fluca_b200_solver *h, const double *v,
   if (s.ibm.n <= 0) throw Error(FL_ERR_ARG, "no markers set");
   put_cells(s, s.vstar, v);
   ibm_interpolate(s, s.vstar);
-  for (int d = 0; d < s.dim; ++d) copy_d2h(s.ex, Um + (size_t)s.ibm.n * d, s.ibm.Um[d], sizeof(double) * s.ibm.n);
-  s.ex.sync();
+  ibm_gather_global(s, s.ibm.Um, Um);
+  API_END
+}
+
+extern "C" int fluca_b200_ibm_info(fluca_b200_solver *h, long info[4])
+{
+  API_BEGIN
+  const Ibm &b = h->s.ibm;
+  info[0] = b.nl, info[1] = b.nsh[0], info[2] = b.nsh[1], info[3] = b.sparse ? 1 : 0;
   API_END
 }
 

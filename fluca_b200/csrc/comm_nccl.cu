@@ -50,6 +50,25 @@ struct NcclComm : public Comm {
     FL_NCCL(ncclGroupEnd());
     ex.stats.launches++;
   }
+  void sendrecv(Exec &ex, const double *send_down, double *recv_down, const double *send_up, double *recv_up, long count, bool periodic) override
+  {
+    if (count <= 0) return;
+    const int down = rank > 0 ? rank - 1 : (periodic ? nranks - 1 : -1);
+    const int up   = rank < nranks - 1 ? rank + 1 : (periodic ? 0 : -1);
+    if (nranks == 1) {
+      if (!periodic) return;
+      copy_d2d(ex, recv_down, send_up, sizeof(double) * count);
+      copy_d2d(ex, recv_up, send_down, sizeof(double) * count);
+      return;
+    }
+    FL_NCCL(ncclGroupStart()); // same post order as halo(): it matters when both neighbours are one rank
+    if (down >= 0) FL_NCCL(ncclSend(send_down, count, ncclDouble, down, comm, ex.stream));
+    if (up >= 0) FL_NCCL(ncclSend(send_up, count, ncclDouble, up, comm, ex.stream));
+    if (up >= 0) FL_NCCL(ncclRecv(recv_up, count, ncclDouble, up, comm, ex.stream));
+    if (down >= 0) FL_NCCL(ncclRecv(recv_down, count, ncclDouble, down, comm, ex.stream));
+    FL_NCCL(ncclGroupEnd());
+    ex.stats.launches++;
+  }
   void allsum(Exec &ex, double *dev, int n) override
   {
     if (nranks == 1) return;

@@ -89,7 +89,7 @@ IbmDev ibm_dev(const Solver &s)
     I.len[d] = d < s.dim ? s.gh.xf[d].back() - s.gh.xf[d].front() : 1.;
     I.X[d] = b.X[d], I.Ud[d] = b.Ud[d];
   }
-  I.dV = b.dV, I.perm = b.perm, I.seg = b.seg, I.nseg = b.nseg;
+  I.dV = b.dV, I.perm = b.perm, I.lq = b.lq, I.lseg = b.lseg, I.nl = b.nl, I.nlseg = b.nlseg;
   I.k0 = s.dim == 3 ? g.k0 : 0, I.nzl = g.nzl, I.px = g.px, I.py = g.py;
   return I;
 }
@@ -108,8 +108,9 @@ void ibm_free_markers(Ibm &b)
   for (void *p : b.owned) dev_free(p);
   b.owned.clear();
   for (int d = 0; d < 3; ++d) b.X[d] = b.Ud[d] = b.Um[d] = b.Dl[d] = b.F[d] = nullptr;
-  b.dV = b.Umbuf = nullptr, b.perm = b.seg = nullptr;
-  b.n = 0, b.nseg = 0, b.cap = 0;
+  b.dV = b.Umbuf = b.xbuf = b.gbuf = nullptr, b.perm = b.lq = b.lseg = b.own = nullptr;
+  b.sh[0] = b.sh[1] = nullptr;
+  b.n = 0, b.nl = 0, b.nlseg = 0, b.cap = 0, b.nsh[0] = b.nsh[1] = 0, b.shcap = 0, b.sparse = false;
 }
 } // namespace
 
@@ -127,7 +128,8 @@ void ibm_set_markers(Solver &s, long n, const double *X, const double *Ud, const
   if (npts != 0 && npts != 3 && npts != 4) throw Error(FL_ERR_ARG, "the discrete delta function has 3 or 4 points");
   if (n >= (1L << 31) / 4) throw Error(FL_ERR_ARG, "too many markers");
   s.ex.sync();
-  if (n != b.cap || n == 0) { // the arrays are laid out with stride n (Um is one contiguous block for the allreduce)
+  { // the arrays are laid out with stride n (Um is one contiguous block for the allreduce); the ownership lists depend on
+    // the positions, so everything is rebuilt on every call
     ibm_free_markers(b);
     if (n == 0) return;
     const int dim = s.dim;
@@ -136,7 +138,6 @@ void ibm_set_markers(Solver &s, long n, const double *X, const double *Ud, const
     b.Umbuf = b.Um[0];
     b.dV    = blk + (size_t)n * 5 * dim;
     b.perm  = ibm_alloc<int>(b, (size_t)n);
-    b.seg   = ibm_alloc<int>(b, (size_t)n + 1);
     b.cap   = n;
   }
   b.n = n, b.npts = npts == 3 ? 3 : 4;
@@ -171,7 +172,10 @@ void ibm_set_markers(Solver &s, long n, const double *X, const double *Ud, const
     keys[m] = ib_key(I, base);
     idx[m]  = (int)m;
   });
-  int *perm = b.perm, *seg = b.seg;
+  int *perm = b.perm;
+  // sorted order on the host: keys in sorted order + the permutation (set_markers is off the hot path; 12 bytes per marker)
+  std::vector<unsigned long long> hk((size_t)n);
+  std::vector<int>                hperm((size_t)n);
 #ifndef FLUCA_HOSTEMU
   {
     size_t tb = 0;
@@ -179,43 +183,109 @@ void ibm_set_markers(Solver &s, long n, const double *X, const double *Ud, const
     void *tmp = dev_alloc(tb);
     FL_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, keys, keys_sorted, idx, perm, (int)n, 0, 64, s.ex.stream));
     s.ex.stats.launches++;
-    // segment heads -> exclusive scan -> scatter of the head positions
-    for_range(s.ex, n, FL_LAMBDA(long q) { flag[q] = (q == 0 || keys_sorted[q] != keys_sorted[q - 1]) ? 1 : 0; });
-    int   *pos = idx; // idx is dead after the sort
-    size_t sb  = 0;
-    FL_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, sb, flag, pos, (int)n, s.ex.stream));
-    void *tmp2 = dev_alloc(sb);
-    FL_CUDA(cub::DeviceScan::ExclusiveSum(tmp2, sb, flag, pos, (int)n, s.ex.stream));
-    s.ex.stats.launches++;
-    for_range(s.ex, n, FL_LAMBDA(long q) {
-      if (flag[q]) seg[pos[q]] = (int)q;
-    });
-    int last[2];
-    copy_d2h(s.ex, &last[0], pos + (n - 1), sizeof(int));
-    copy_d2h(s.ex, &last[1], flag + (n - 1), sizeof(int));
+    copy_d2h(s.ex, hk.data(), keys_sorted, sizeof(unsigned long long) * n);
+    copy_d2h(s.ex, hperm.data(), perm, sizeof(int) * n);
     s.ex.sync();
-    b.nseg = last[0] + last[1];
-    const int nn = (int)n;
-    copy_h2d(s.ex, seg + b.nseg, &nn, sizeof(int));
-    s.ex.sync();
-    dev_free(tmp), dev_free(tmp2);
+    dev_free(tmp);
+    (void)flag;
   }
 #else
   {
     std::vector<int> order(n);
     for (long m = 0; m < n; ++m) order[m] = (int)m;
     std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return keys[a] < keys[c]; });
-    int ns = 0;
-    for (long q = 0; q < n; ++q) {
-      perm[q] = order[q];
-      if (q == 0 || keys[order[q]] != keys[order[q - 1]]) seg[ns++] = (int)q;
-    }
-    seg[ns] = (int)n;
-    b.nseg  = ns;
+    for (long q = 0; q < n; ++q) perm[q] = order[q], hperm[q] = order[q], hk[q] = keys[order[q]];
     (void)keys_sorted, (void)flag;
   }
 #endif
   dev_free(keys), dev_free(idx);
+
+  // ---- slab ownership.  The key is z-major: base plane of the support = key / ((nx + 8)(ny + 8)) - 4.  A marker is LOCAL when
+  // one of its npts support planes (wrapped in a periodic z) lies in [k0, k0 + nzl); its other planes belong to the lower or
+  // the upper neighbour slab (a support is thinner than a slab, checked below), which makes it SHARED with that neighbour.
+  const Geom &g = s.gh.g;
+  const int   nranks = s.comm->nranks, np = b.npts;
+  const bool  perz = s.dim == 3 && g.t[2].per;
+  const unsigned long long exy = ((unsigned long long)g.nx + 8) * ((unsigned long long)g.ny + 8);
+  std::vector<int> lq, lseg, shl[2], own((size_t)n, 0);
+  bool             try_sparse = nranks > 1 && s.dim == 3;
+  for (long q = 0; q < n; ++q) {
+    bool local = true, dn = false, up = false;
+    if (s.dim == 3 && nranks > 1) {
+      const int base = (int)(hk[q] / exy) - 4;
+      // the image of the support (shifted by a period if need be) that overlaps the slab
+      int shift = 0;
+      local = false;
+      for (int sgn = 0; sgn < (perz ? 3 : 1) && !local; ++sgn) {
+        shift = sgn == 0 ? 0 : (sgn == 1 ? g.nzg : -g.nzg);
+        for (int t = 0; t < np; ++t) {
+          const int k = base + t + shift;
+          if (!perz && (base + t < 0 || base + t >= g.nzg)) continue;
+          if (k >= g.k0 && k < g.k0 + g.nzl) local = true;
+        }
+      }
+      if (local)
+        for (int t = 0; t < np; ++t) {
+          if (!perz && (base + t < 0 || base + t >= g.nzg)) continue; // outside the domain: zero weight
+          const int k = base + t + shift;
+          if (k < g.k0) dn = true;
+          if (k >= g.k0 + g.nzl) up = true;
+        }
+    }
+    if (!local) continue;
+    if (lq.empty() || hk[q] != hk[lq.back()]) lseg.push_back((int)lq.size());
+    lq.push_back((int)q);
+    if (dn) shl[0].push_back(hperm[q]);
+    if (up) shl[1].push_back(hperm[q]);
+    if (!dn) own[hperm[q]] = 1; // of the two ranks that share a marker the lower one reports it
+  }
+  lseg.push_back((int)lq.size());
+  if (try_sparse) {
+    // every rank must be able to take part: slabs at least as thick as a support; the exchange count is the largest list
+    double *tmp = (double *)dev_alloc(sizeof(double) * 3 * (nranks + 1));
+    const double mine[3] = {g.nzl >= np ? 1. : 0., (double)shl[0].size(), (double)shl[1].size()};
+    copy_h2d(s.ex, tmp, mine, sizeof(mine));
+    s.comm->allgather(s.ex, tmp, tmp + 3, 3);
+    std::vector<double> all((size_t)3 * nranks);
+    copy_d2h(s.ex, all.data(), tmp + 3, sizeof(double) * 3 * nranks);
+    s.ex.sync();
+    dev_free(tmp);
+    long cap = 0;
+    for (int r = 0; r < nranks; ++r) {
+      if (all[3 * r] == 0.) try_sparse = false;
+      cap = std::max(cap, (long)std::max(all[3 * r + 1], all[3 * r + 2]));
+    }
+    b.shcap = cap;
+  }
+  b.sparse = try_sparse;
+  if (!b.sparse) {
+    // replicated sums: every rank walks every marker (partial sums over its own planes) and one allreduce completes them
+    lq.resize(n);
+    lseg.clear();
+    for (long q = 0; q < n; ++q) {
+      if (q == 0 || hk[q] != hk[q - 1]) lseg.push_back((int)q);
+      lq[q] = (int)q;
+    }
+    lseg.push_back((int)n);
+    shl[0].clear(), shl[1].clear();
+    std::fill(own.begin(), own.end(), 1);
+    b.shcap = 0;
+  }
+  b.nl = (long)lq.size(), b.nlseg = (int)lseg.size() - 1;
+  b.lq   = ibm_alloc<int>(b, lq.size());
+  b.lseg = ibm_alloc<int>(b, lseg.size());
+  b.own  = ibm_alloc<int>(b, (size_t)n);
+  b.gbuf = ibm_alloc<double>(b, (size_t)n * s.dim);
+  copy_h2d(s.ex, b.lq, lq.data(), sizeof(int) * lq.size());
+  copy_h2d(s.ex, b.lseg, lseg.data(), sizeof(int) * lseg.size());
+  copy_h2d(s.ex, b.own, own.data(), sizeof(int) * n);
+  for (int sd = 0; sd < 2; ++sd) {
+    b.nsh[sd] = (long)shl[sd].size();
+    b.sh[sd]  = ibm_alloc<int>(b, shl[sd].size());
+    copy_h2d(s.ex, b.sh[sd], shl[sd].data(), sizeof(int) * shl[sd].size());
+  }
+  b.xbuf = ibm_alloc<double>(b, (size_t)4 * b.shcap * s.dim);
+  s.ex.sync();
 }
 
 // ------------------------------------------------------------------ gather / scatter
@@ -266,8 +336,8 @@ __global__ void __launch_bounds__(256) k_ibm_interp(const IbmDev I, const CV3 v,
   const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long)gridDim.x * blockDim.x) >> 5;
   const int  npd = DIM == 3 ? I.npts * I.npts * I.npts : I.npts * I.npts;
   double    *um[3] = {um0, um1, um2};
-  for (long q = wid; q < I.n; q += nw) {
-    const int m = I.perm[q];
+  for (long t = wid; t < I.nl; t += nw) {
+    const int m = I.perm[I.lq[t]];
     int       base[3];
     double    wl;
     warp_marker<DIM>(I, m, lane, base, wl);
@@ -299,8 +369,8 @@ __global__ void __launch_bounds__(256) k_ibm_spread(const IbmDev I, const double
   const long    wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long)gridDim.x * blockDim.x) >> 5;
   const int     npd = DIM == 3 ? I.npts * I.npts * I.npts : I.npts * I.npts;
   const double *fm[3] = {f0, f1, f2};
-  for (long sg = wid; sg < I.nseg; sg += nw) {
-    const int q0 = I.seg[sg], q1 = I.seg[sg + 1];
+  for (long sg = wid; sg < I.nlseg; sg += nw) {
+    const int q0 = I.lseg[sg], q1 = I.lseg[sg + 1];
     double    acc[2][DIM];
     int       cells[2];
     double    ivol[2];
@@ -311,7 +381,7 @@ __global__ void __launch_bounds__(256) k_ibm_spread(const IbmDev I, const double
       for (int c = 0; c < DIM; ++c) acc[t][c] = 0.;
     }
     for (int q = q0; q < q1; ++q) {
-      const int m = I.perm[q];
+      const int m = I.perm[I.lq[q]];
       int       base[3];
       double    wl;
       warp_marker<DIM>(I, m, lane, base, wl);
@@ -356,8 +426,8 @@ template <int DIM>
 void host_transfer(const IbmDev &I, int mode, const CV3 &v, double *const um[3], double *const fm[3], const V3 &out, const V3 &out2)
 {
   const int np = I.npts;
-  for (long q = 0; q < I.n; ++q) {
-    const int m = I.perm[q];
+  for (long q = 0; q < I.nl; ++q) {
+    const int m = I.perm[I.lq[q]];
     int       base[3] = {0, 0, 0};
     double    w[3][4] = {{1., 0., 0., 0.}, {1., 0., 0., 0.}, {1., 0., 0., 0.}};
     for (int d = 0; d < DIM; ++d) {
@@ -407,8 +477,9 @@ void ibm_interpolate(Solver &s, const V3 &v)
 #ifndef FLUCA_HOSTEMU
   {
     KTimer kt(s.ex, s.ex.kt_current);
-    long   blocks = (b.n * 32 + 255) / 256, cap = (long)s.ex.sm_count * 16;
+    long   blocks = (b.nl * 32 + 255) / 256, cap = (long)s.ex.sm_count * 16;
     if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
     if (s.dim == 2) k_ibm_interp<2><<<(unsigned)blocks, 256, 0, s.ex.stream>>>(I, CV3(v), b.Um[0], b.Um[1], b.Um[2]);
     else k_ibm_interp<3><<<(unsigned)blocks, 256, 0, s.ex.stream>>>(I, CV3(v), b.Um[0], b.Um[1], b.Um[2]);
     FL_CUDA(cudaGetLastError());
@@ -421,8 +492,54 @@ void ibm_interpolate(Solver &s, const V3 &v)
     else host_transfer<3>(I, 0, CV3(v), b.Um, nullptr, none, none);
   }
 #endif
-  // every rank summed over its own planes only: the marker velocity is the sum over the ranks
-  s.comm->allsum(s.ex, b.Umbuf, (int)(b.n * s.dim));
+  // every rank summed over its own planes only
+  if (!b.sparse) {
+    s.comm->allsum(s.ex, b.Umbuf, (int)(b.n * s.dim)); // replicated sums: one allreduce over all markers
+    return;
+  }
+  if (b.shcap <= 0) return;
+  // ownership exchange: the partial sums of the markers whose support crosses a slab face go to that neighbour, its partial
+  // sums come back, and both hold the complete velocity (they both need it: each spreads the force into its own planes)
+  const int  dim = s.dim;
+  const long cap = b.shcap, n0 = b.nsh[0], n1 = b.nsh[1];
+  double    *sd = b.xbuf, *rd = b.xbuf + cap * dim, *su = b.xbuf + 2 * cap * dim, *ru = b.xbuf + 3 * cap * dim;
+  const int *l0 = b.sh[0], *l1 = b.sh[1];
+  double    *u0 = b.Um[0], *u1 = b.Um[1], *u2 = b.Um[2];
+  for_range(s.ex, cap * dim, FL_LAMBDA(long e) {
+    const long   k = e % cap;
+    const int    c = (int)(e / cap);
+    const double *u = c == 0 ? u0 : (c == 1 ? u1 : u2);
+    sd[e] = k < n0 ? u[l0[k]] : 0.;
+    su[e] = k < n1 ? u[l1[k]] : 0.;
+  });
+  s.comm->sendrecv(s.ex, sd, rd, su, ru, cap * dim, s.gh.g.t[2].per != 0);
+  for_range(s.ex, cap * dim, FL_LAMBDA(long e) {
+    const long k = e % cap;
+    const int  c = (int)(e / cap);
+    double    *u = c == 0 ? u0 : (c == 1 ? u1 : u2);
+    if (k < n0) u[l0[k]] += rd[e];
+    if (k < n1) u[l1[k]] += ru[e];
+  });
+}
+
+void ibm_gather_global(Solver &s, double *const src[3], double *host)
+{
+  Ibm &b = s.ibm;
+  if (b.n <= 0) return;
+  const long n = b.n;
+  if (b.sparse) {
+    const int *own = b.own;
+    for (int c = 0; c < s.dim; ++c) {
+      double       *gb = b.gbuf + (size_t)n * c;
+      const double *sc = src[c];
+      for_range(s.ex, n, FL_LAMBDA(long m) { gb[m] = own[m] ? sc[m] : 0.; });
+    }
+    s.comm->allsum(s.ex, b.gbuf, (int)(n * s.dim));
+    copy_d2h(s.ex, host, b.gbuf, sizeof(double) * n * s.dim);
+  } else {
+    for (int c = 0; c < s.dim; ++c) copy_d2h(s.ex, host + (size_t)n * c, src[c], sizeof(double) * n);
+  }
+  s.ex.sync();
 }
 
 void ibm_spread(Solver &s, double *const Fm[3], const V3 &f, const V3 *f2)
@@ -438,7 +555,7 @@ void ibm_spread(Solver &s, double *const Fm[3], const V3 &f, const V3 *f2)
 #ifndef FLUCA_HOSTEMU
   {
     KTimer kt(s.ex, s.ex.kt_current);
-    long   blocks = ((long)b.nseg * 32 + 255) / 256, cap = (long)s.ex.sm_count * 16;
+    long   blocks = ((long)b.nlseg * 32 + 255) / 256, cap = (long)s.ex.sm_count * 16;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     if (s.dim == 2) k_ibm_spread<2><<<(unsigned)blocks, 256, 0, s.ex.stream>>>(I, Fm[0], Fm[1], nullptr, f, o2);
@@ -464,7 +581,8 @@ void ibm_force_rhs(Solver &s)
   if (b.n <= 0) return;
   momentum_solve(s, s.rm, s.vstar, s.have_guess); // predictor v~ = A^-1 r_mom (guess: previous velocity, do_step)
   const int    dim = s.dim, passes = b.iters > 1 ? b.iters : 1;
-  const long   n = b.n;
+  const long   nl = b.nl;
+  const int   *perm = b.perm, *lq = b.lq;
   const double fscale = s.sp.rho / s.sp.dt;
   const double *dv = b.dV;
   const IbP3   UD = {{b.Ud[0], b.Ud[1], b.Ud[2]}}, UM = {{b.Um[0], b.Um[1], b.Um[2]}}, DL = {{b.Dl[0], b.Dl[1], b.Dl[2]}}, FF = {{b.F[0], b.F[1], b.F[2]}};
@@ -473,7 +591,8 @@ void ibm_force_rhs(Solver &s)
     ibm_interpolate(s, s.vstar);
     {
       KScope ks(s.ex, KT_IBM);
-      for_range(s.ex, n, FL_LAMBDA(long m) {
+      for_range(s.ex, nl, FL_LAMBDA(long t) {
+        const int m = perm[lq[t]];
         for (int c = 0; c < dim; ++c) {
           const double d = UD.c[c][m] - UM.c[c][m];
           DL.c[c][m]     = d;

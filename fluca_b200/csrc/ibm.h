@@ -8,9 +8,12 @@
 //   locate       per direction: cell that holds the marker, first support cell, 3 or 4 delta weights
 //   sort         markers ordered by the linear index of their first support cell (z-major): neighbours in
 //                the list touch the same cache lines; equal keys form SEGMENTS that share all support cells
+//   ownership    a rank works on the markers whose support touches its z-slab (a contiguous stretch of the sorted list plus
+//                the periodic wrap); the markers whose support crosses a slab face are SHARED with that neighbour
 //   interpolate  U_m = sum_cells w_m(cell) v(cell)         one warp per marker, lanes over the support,
-//                                                          warp-shuffle reduction, planes of this rank only,
-//                                                          then one allreduce over the ranks
+//                                                          warp-shuffle reduction, planes of this rank only; the partial sums
+//                                                          of the shared markers are exchanged with the two neighbour slabs
+//                                                          (one grouped send/recv of a few hundred doubles) and added
 //   spread       f(cell) += sum_m w_m(cell) F_m dV_m/vol   one warp per segment: lanes accumulate their support
 //                                                          cells over all markers of the segment in registers,
 //                                                          then ONE atomicAdd per support cell and segment
@@ -32,8 +35,10 @@ struct IbmDev { // by-value kernel argument
   double        x0[3], len[3];
   const double *X[3], *Ud[3], *dV;
   const int    *perm; // sorted position -> marker
-  const int    *seg;  // [nseg + 1] first sorted position of every segment
-  int           nseg;
+  const int    *lq;   // [nl] sorted positions of the markers this rank works on
+  const int    *lseg; // [nlseg + 1] first entry of lq of every segment
+  long          nl;
+  int           nlseg;
 };
 
 struct Ibm {
@@ -43,17 +48,29 @@ struct Ibm {
   double *coord[3][2] = {}; // device xf / xc per direction
   double *X[3] = {}, *Ud[3] = {}, *Um[3] = {}, *Dl[3] = {}, *F[3] = {}, *dV = nullptr;
   double *Umbuf = nullptr; // the three Um arrays are one allocation (one allreduce)
-  int    *perm = nullptr, *seg = nullptr;
-  int     nseg = 0;
+  int    *perm = nullptr;
   long    cap = 0;
+  // slab ownership
+  int    *lq = nullptr, *lseg = nullptr; // local list (sorted positions) and its segments
+  long    nl = 0;
+  int     nlseg = 0;
+  bool    sparse = false;          // neighbour exchange of the shared markers (else: every rank walks every marker + one allreduce)
+  int    *sh[2] = {nullptr, nullptr}; // marker ids shared with the lower / upper neighbour slab, in sorted order
+  long    nsh[2] = {0, 0}, shcap = 0; // shcap: exchange count (the largest shared list of any rank)
+  double *xbuf = nullptr;          // [4][shcap * dim]: send down, recv down, send up, recv up
+  int    *own = nullptr;           // [n] 1 where this rank reports the marker (assembly of global marker arrays)
+  double *gbuf = nullptr;          // [n * dim] scratch of that assembly
   std::vector<void *> owned;
 };
 
 void ibm_set_markers(Solver &s, long n, const double *X, const double *Ud, const double *dV, int npts);
 void ibm_destroy(Solver &s);
 IbmDev ibm_dev(const Solver &s);
-// Um = interpolation of the cell field v (summed over the ranks)
+// Um = interpolation of the cell field v, complete for every marker this rank works on
 void ibm_interpolate(Solver &s, const V3 &v);
+// host copy of a per-marker device array set (dim arrays of n doubles) with every marker's value taken from the rank that
+// reports it: what the C ABI returns for marker forces / velocities
+void ibm_gather_global(Solver &s, double *const src[3], double *host);
 // f += spreading of Fm (dim arrays of n doubles, device); f2 (optional) receives the same increment
 void ibm_spread(Solver &s, double *const Fm[3], const V3 &f, const V3 *f2 = nullptr);
 // steps 2-4 of the coupling: predictor solve, interpolation, forcing added to the momentum RHS

@@ -22,6 +22,9 @@ struct Comm {
   virtual void allsum(Exec &ex, double *dev, int n) = 0;
   // gathers `count` doubles from every rank (device), rank-major
   virtual void allgather(Exec &ex, const double *send, double *recv, long count) = 0;
+  // exchanges `count` doubles with both z neighbours (device buffers): send_down / recv_down with rank - 1, send_up / recv_up
+  // with rank + 1; the ends talk to each other when periodic, else their outer buffers are left alone
+  virtual void sendrecv(Exec &ex, const double *send_down, double *recv_down, const double *send_up, double *recv_up, long count, bool periodic) = 0;
   virtual void barrier(Exec &ex) { (void)ex; }
 };
 
@@ -29,6 +32,12 @@ struct LocalComm : public Comm {
   void halo(Exec &ex, double *const *fields, int nf, long plane, int nzl, bool periodic) override;
   void allsum(Exec &, double *, int) override { }
   void allgather(Exec &ex, const double *send, double *recv, long count) override { copy_d2d(ex, recv, send, sizeof(double) * count); }
+  void sendrecv(Exec &ex, const double *send_down, double *recv_down, const double *send_up, double *recv_up, long count, bool periodic) override
+  {
+    if (!periodic) return; // one rank: it is its own neighbour on both sides
+    copy_d2d(ex, recv_down, send_up, sizeof(double) * count);
+    copy_d2d(ex, recv_up, send_down, sizeof(double) * count);
+  }
 };
 
 // host-callback communicator: used by the CPU (gloo) tests of the multi-rank logic, and available
@@ -45,6 +54,7 @@ struct CallbackComm : public Comm {
   void halo(Exec &ex, double *const *fields, int nf, long plane, int nzl, bool periodic) override;
   void allsum(Exec &ex, double *dev, int n) override;
   void allgather(Exec &ex, const double *send, double *recv, long count) override;
+  void sendrecv(Exec &ex, const double *send_down, double *recv_down, const double *send_up, double *recv_up, long count, bool periodic) override;
 };
 
 #ifndef FLUCA_HOSTEMU

@@ -93,6 +93,27 @@ void CallbackComm::allgather(Exec &ex, const double *send, double *recv, long co
 #endif
 }
 
+void CallbackComm::sendrecv(Exec &ex, const double *send_down, double *recv_down, const double *send_up, double *recv_up, long count, bool periodic)
+{
+  if (count <= 0) return;
+  if (nranks == 1 && !periodic) return;
+#ifdef FLUCA_HOSTEMU
+  int rc = halo_cb(ctx, send_down, recv_down, send_up, recv_up, count, periodic ? 1 : 0);
+#else
+  hs0.resize(count), hs1.resize(count), hr0.resize(count), hr1.resize(count);
+  copy_d2h(ex, hs0.data(), send_down, sizeof(double) * count);
+  copy_d2h(ex, hs1.data(), send_up, sizeof(double) * count);
+  copy_d2h(ex, hr0.data(), recv_down, sizeof(double) * count);
+  copy_d2h(ex, hr1.data(), recv_up, sizeof(double) * count);
+  ex.sync();
+  int rc = halo_cb(ctx, hs0.data(), hr0.data(), hs1.data(), hr1.data(), count, periodic ? 1 : 0);
+  copy_h2d(ex, recv_down, hr0.data(), sizeof(double) * count);
+  copy_h2d(ex, recv_up, hr1.data(), sizeof(double) * count);
+  ex.sync();
+#endif
+  if (rc) throw Error(FL_ERR_INTERNAL, "halo callback failed");
+}
+
 void halo_cells(Solver &s, const V3 &v)
 {
   const Geom &g = s.gh.g;

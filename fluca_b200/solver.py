@@ -297,6 +297,12 @@ class Solver:
     def kernel_timing(self, enable: bool):
         _lib.check(self.L, self.L.fluca_b200_kernel_timing(self._h, 1 if enable else 0))
 
+    def ibm_info(self):
+        """(markers this rank works on, shared with the lower slab, shared with the upper slab, neighbour exchange in use)"""
+        info = (C.c_long * 4)()
+        _lib.check(self.L, self.L.fluca_b200_ibm_info(self._h, info))
+        return int(info[0]), int(info[1]), int(info[2]), bool(info[3])
+
     def model_bytes_split(self, stats):
         """SURVEY.md 8d model bytes of one step with these iteration counts, per kernel class name."""
         n = len(_lib.KT_NAMES)

@@ -596,6 +596,7 @@ PetscErrorCode NSB200SyncSolution(NS ns)
   PetscFunctionReturn(PETSC_SUCCESS);
 }
 
+/* collective on the NS communicator: every marker's entry comes from the rank whose slab reports it */
 PetscErrorCode NSB200GetMarkerForces(NS ns, PetscReal F[], PetscReal Um[])
 {
   NS_B200 *b = (NS_B200 *)ns->data;

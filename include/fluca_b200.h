@@ -135,8 +135,10 @@ int fluca_b200_set_boundary_pressure(fluca_b200_solver *s, int boundary, int slo
 
 /* ---- immersed boundary.  The reference advertises the method (README.md:14) but has no code
  * for it (THEORY_GUIDE.md:130-132 is a TODO), so these entry points replace no reference interface; they are what an
- * IBM-enabled NS type would add next to NSSetBoundaryCondition.  Markers are replicated: every rank passes the same
- * global list.  X, Ud, F, Um: dim consecutive blocks of n doubles; dV: n doubles (Lagrangian volume weights).
+ * IBM-enabled NS type would add next to NSSetBoundaryCondition.  Every rank passes the same global list; a rank then works
+ * only on the markers whose support touches its slab and exchanges the partial sums of the markers that straddle a slab face
+ * with that neighbour (the "marker ownership exchange").  With several ranks set_markers, get_marker_forces and
+ * ibm_interpolate are COLLECTIVE: every rank calls them, every rank gets the complete arrays.  X, Ud, F, Um: dim consecutive blocks of n doubles; dV: n doubles (Lagrangian volume weights).
  * delta_points: 4 (Peskin, default for 0) or 3 (Roma).  n = 0 removes the markers.
  * Coupling: direct forcing with an implicit predictor, added to the momentum right-hand side of the step. */
 int fluca_b200_set_markers(fluca_b200_solver *s, long n, const double *X, const double *Ud, const double *dV, int delta_points);
@@ -144,6 +146,9 @@ int fluca_b200_set_markers(fluca_b200_solver *s, long n, const double *X, const 
 int fluca_b200_set_ibm_iterations(fluca_b200_solver *s, int passes);
 /* force of every marker on the fluid, rho (Ud - Um) dV / dt, and the interpolated predictor velocity Um of the last step */
 int fluca_b200_get_marker_forces(fluca_b200_solver *s, double *F, double *Um);
+/* ownership of this rank: info = {markers it works on, shared with the lower slab, shared with the upper slab, 1 if the
+ * neighbour exchange is in use (0: every rank walks every marker and one allreduce completes the sums)} */
+int fluca_b200_ibm_info(fluca_b200_solver *s, long info[4]);
 /* operator-level (tests): Um = interpolation of the cell field v; f = spreading of Fm (f is overwritten) */
 int fluca_b200_ibm_interpolate(fluca_b200_solver *s, const double *v, double *Um);
 int fluca_b200_ibm_spread(fluca_b200_solver *s, const double *Fm, double *f);

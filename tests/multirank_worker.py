@@ -85,10 +85,13 @@ def main():
         "cavity32": lambda: cases.cavity3d_full(n=(32, 32, 32)),
         "sphere_ibm": lambda: cases.channel3d(n=(12, 8, 8), pout=0.1, dt=0.05),
         "sphere_ibm_tma": lambda: cases.channel3d(n=(40, 16, 16), pout=0.1, dt=0.02),
+        "sphere_ibm_periodic": lambda: cases.channel3d(n=(12, 8, 12), periodic_z=True, dt=0.05),
     }[case_name]()
     markers = None
     if case_name.startswith("sphere_ibm"):  # the body straddles the slab interface: gather and scatter both cross it
         markers = cases.sphere_markers((0.1, 0.0, 0.05), 1.2, 120, 4.0 / case.n[1])
+        if case_name == "sphere_ibm_periodic":  # near the periodic z boundary: the support wraps from the last slab into the first
+            markers = cases.sphere_markers((0.1, 0.0, 1.7), 1.0, 150, 4.0 / case.n[1])
     if backend == "nccl":
         comm = dict(rank=rank, nranks=world, make_comm=lambda L: fb.Comm.nccl(L, uid, rank, world))
     else:
@@ -110,6 +113,10 @@ def main():
         its.append((st.outer_its, st.mom_its, st.schur_its))
     loc = s.get_state()
     # gather slabs on rank 0
+    forces = fb.NSB200GetMarkerForces(ns) if markers is not None else None  # collective: every rank calls it
+    infos = [None] * world
+    if markers is not None:
+        dist.all_gather_object(infos, s.ibm_info())
     parts = [None] * world
     dist.all_gather_object(parts, dict(k0=k0, nzl=nzl, v=loc["v"], U=loc["U"], p=loc["p"], phalf=loc["phalf"]))
     if rank == 0:
@@ -120,8 +127,9 @@ def main():
         gU = [np.concatenate([d["U"][a] for d in parts], axis=0) for a in range(3)]
         extra = {}
         if markers is not None:
-            F, Um = fb.NSB200GetMarkerForces(ns)
+            F, Um = forces
             extra = dict(F=F, Um=Um)
+            extra["ibm_info"] = np.array([[a, b, c, int(d)] for a, b, c, d in infos])
         np.savez(out_path, v=gv, p=gp, phalf=gph, U0=gU[0], U1=gU[1], U2=gU[2], its=np.array(its), **extra)
     fb.NSDestroy(ns)
     dist.barrier()

@@ -32,7 +32,7 @@ def run_world(case_name, mode, world, tmp_path, backend="gloo", ainv=(0, 0)):
     logs = []
     for p in procs:
         try:
-            o, _ = p.communicate(timeout=600)
+            o, _ = p.communicate(timeout=240)
         except subprocess.TimeoutExpired:
             for q in procs:
                 q.kill()
@@ -51,6 +51,7 @@ CASEMAP = {
     "cavity32": lambda: cases.cavity3d_full(n=(32, 32, 32)),
     "sphere_ibm": lambda: cases.channel3d(n=(12, 8, 8), pout=0.1, dt=0.05),
     "sphere_ibm_tma": lambda: cases.channel3d(n=(40, 16, 16), pout=0.1, dt=0.02),
+    "sphere_ibm_periodic": lambda: cases.channel3d(n=(12, 8, 12), periodic_z=True, dt=0.05),
 }
 
 
@@ -60,6 +61,8 @@ def _oracle_reference(case_name, mode, ainv=(0, 0)):
     orc.set_state(*case.initial_state(seed=31))
     if case_name.startswith("sphere_ibm"):
         mk = cases.sphere_markers((0.1, 0.0, 0.05), 1.2, 120, 4.0 / case.n[1])
+        if case_name == "sphere_ibm_periodic":
+            mk = cases.sphere_markers((0.1, 0.0, 1.7), 1.0, 150, 4.0 / case.n[1])
         orc.set_markers(mk["X"], mk["Ud"], mk["dV"], 4, 2)
     infos = [orc.step(O.default_options(mode=0 if mode == "coupled" else 1, schur_ainv=ainv[0], upper_ainv=ainv[1], **parity.ORC_TIGHT)) for _ in range(2)]
     return orc, infos
@@ -67,7 +70,7 @@ def _oracle_reference(case_name, mode, ainv=(0, 0)):
 
 @pytest.mark.parametrize(
     "case_name,mode,world",
-    [("cavity3d", "coupled", 2), ("channel3d", "coupled", 2), ("periodic_z", "fractional", 2), ("uneven", "fractional", 2), ("three", "fractional", 3), ("sphere_ibm", "coupled", 2)],
+    [("cavity3d", "coupled", 2), ("channel3d", "coupled", 2), ("periodic_z", "fractional", 2), ("uneven", "fractional", 2), ("three", "fractional", 3), ("sphere_ibm", "coupled", 2), ("sphere_ibm_periodic", "fractional", 3)],
 )
 def test_slab_partition_matches_oracle(case_name, mode, world, tmp_path):
     parity.hostemu_library()
@@ -80,6 +83,15 @@ def test_slab_partition_matches_oracle(case_name, mode, world, tmp_path):
     if "F" in got.files:  # immersed boundary across the slab interface: marker velocities are summed over the ranks
         Fo, Uo = orc.marker_forces()
         assert parity.rel(got["Um"], Uo) < 1e-10 and parity.rel(got["F"], Fo) < 1e-8
+        # marker ownership: the neighbour exchange is in use, no rank works on every marker, and what one rank shares upwards
+        # is what the next one shares downwards (periodic: the last with the first)
+        info = got["ibm_info"]
+        n = got["Um"].shape[1]
+        assert all(info[:, 3] == 1) and all(info[:, 0] <= n) and info[:, 0].sum() >= n and (world < 3 or info[:, 0].min() < n)
+        for r in range(world - 1):
+            assert info[r, 2] == info[r + 1, 1] and info[r, 2] > 0 or case_name == "sphere_ibm_periodic"
+        if case_name == "sphere_ibm_periodic":
+            assert info[world - 1, 2] == info[0, 1] > 0  # the wrap
     if mode == "coupled":
         assert [int(a) for a in got["its"][:, 0]] == [i.outer_its for i in infos]
 
