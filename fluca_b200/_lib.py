@@ -124,6 +124,8 @@ SYMBOLS = [
     "fluca_b200_fd_set_locations",
     "fluca_b200_step_model_bytes_split",
     "fluca_b200_ibm_info",
+    "fluca_b200_host_alloc",
+    "fluca_b200_host_free",
     "fluca_b200_fd_set_boundary_condition",
     "fluca_b200_fd_setup",
     "fluca_b200_fd_get_stencil",
@@ -184,6 +186,8 @@ def _prototype(L):
     L.fluca_b200_set_markers.argtypes = [_P, C.c_long, _P, _P, _P, C.c_int]
     L.fluca_b200_get_marker_forces.argtypes = [_P, _P, _P]
     L.fluca_b200_ibm_info.argtypes = [_P, C.POINTER(C.c_long)]
+    L.fluca_b200_host_alloc.argtypes = [C.c_size_t, C.POINTER(_P)]
+    L.fluca_b200_host_free.argtypes = [_P]
     L.fluca_b200_ibm_interpolate.argtypes = [_P, _P, _P]
     L.fluca_b200_ibm_spread.argtypes = [_P, _P, _P]
     L.fluca_b200_set_ibm_iterations.argtypes = [_P, C.c_int]

@@ -253,6 +253,27 @@ void view_get(Solver &s, double *host, const double *dev, Ext e)
 }
 } // namespace
 
+extern "C" int fluca_b200_host_alloc(size_t bytes, void **ptr)
+{
+  API_BEGIN
+  if (!ptr) throw Error(FL_ERR_ARG, "null argument");
+  *ptr = pinned_alloc(bytes);
+  API_END
+}
+
+extern "C" int fluca_b200_host_free(void *ptr)
+{
+  API_BEGIN
+  if (ptr) {
+#ifndef FLUCA_HOSTEMU
+    FL_CUDA(cudaFreeHost(ptr));
+#else
+    free(ptr);
+#endif
+  }
+  API_END
+}
+
 extern "C" int fluca_b200_stage_state(fluca_b200_solver *h)
 {
   API_BEGIN

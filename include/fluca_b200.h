@@ -23,6 +23,7 @@
 #ifndef FLUCA_B200_H
 #define FLUCA_B200_H
 
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -116,6 +117,10 @@ int fluca_b200_set_abf_ainv_types(fluca_b200_solver *s, int schur_type, int uppe
 int fluca_b200_set_state(fluca_b200_solver *s, const double *v, const double *const U[3], const double *p, const double *phalf);
 int fluca_b200_get_state(fluca_b200_solver *s, double *v, double *const U[3], double *p, double *phalf);
 
+/* page-locked host memory for the caller's staging buffers (full-rate DMA for set_state / get_state / boundary planes) without
+ * the caller needing the CUDA headers: the PETSc glue allocates its upload buffers here */
+int fluca_b200_host_alloc(size_t bytes, void **ptr);
+int fluca_b200_host_free(void *ptr);
 /* ---- asynchronous solution views: what a monitor, NSViewSolution or the CGNS writer needs (NSViewSolution nssol.c:130-174,
  * VecView_Cart cartvec.c:4-25) without stalling the time loop.
  * stage_state  enqueues a copy of the current state into library-owned PINNED host buffers on a second CUDA stream, ordered

@@ -192,5 +192,16 @@ struct _p_NS {
   Vec                  sol, sol0;
   NSConvergedReason    reason;
   PetscBool            setupcalled;
+#ifdef FLUCA_NS_HAS_MATRIXFREE
+  PetscBool            matrixfree; /* glue/patches/0001-ns-matrix-free-type-hooks.patch */
+#endif
 };
+/* ---- additions for the hardened glue: option flags, formatted output, array comparison ---- */
+PetscErrorCode PetscOptionsBoolStub(PetscOptionItems, const char *, const char *, const char *, PetscBool, PetscBool *, PetscBool *);
+#define PetscOptionsBool(a, b, c, d, e, f) PetscOptionsBoolStub(PetscOptionsObject, a, b, c, d, e, f)
+PetscErrorCode PetscPrintf(MPI_Comm, const char[], ...);
+PetscErrorCode PetscArraycmpStub(const void *, const void *, size_t, PetscBool *);
+#define PetscArraycmp(a, b, n, e) PetscArraycmpStub((a), (b), (size_t)(n) * sizeof(*(a)), (e))
+PetscErrorCode PetscArraycpyStub(void *, const void *, size_t);
+#define PetscArraycpy(a, b, n) PetscArraycpyStub((a), (b), (size_t)(n) * sizeof(*(a)))
 #endif
