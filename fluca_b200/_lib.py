@@ -134,6 +134,7 @@ SYMBOLS = [
     "fluca_b200_fd_apply_device",
     "fluca_b200_fd_stream",
     "fluca_b200_fd_sync",
+    "fluca_b200_fd_get_operator",
     "fluca_b200_fd_destroy",
 ]
 FD_MAX_STENCIL = 32
@@ -213,6 +214,7 @@ def _prototype(L):
     L.fluca_b200_fd_apply_device.argtypes = [_P, C.c_int, C.POINTER(_P), _P]
     L.fluca_b200_fd_stream.argtypes = [_P, C.POINTER(_P)]
     L.fluca_b200_fd_sync.argtypes = [_P]
+    L.fluca_b200_fd_get_operator.argtypes = [_P, C.POINTER(C.c_long), C.POINTER(C.c_long), C.POINTER(C.c_long), C.POINTER(FDCol), C.POINTER(C.c_double)]
     L.fluca_b200_fd_destroy.argtypes = [_P]
     L.fluca_b200_stage_state.argtypes = [_P]
     L.fluca_b200_staged_state.argtypes = [_P, C.POINTER(_P), _PD3, C.POINTER(_P), C.POINTER(_P)]

@@ -623,6 +623,9 @@ struct fluca_b200_fd {
 };
 
 static thread_local std::string g_fd_err;
+// bumped whenever a field an operator depends on changes (vector of a scale, velocity / current solution of a TVD operator):
+// an assembled device plan of a field-dependent tree is rebuilt when it is older than this
+static long g_fd_field_generation = 0;
 extern "C" const char *fluca_b200_fd_last_error(void) { return g_fd_err.c_str(); }
 
 #define FD_BEGIN try {
@@ -772,6 +775,7 @@ extern "C" int fluca_b200_fd_tvd_set_velocity(fluca_b200_fd *h, const double *fa
   TVD *t = h ? dynamic_cast<TVD *>(h->op) : nullptr;
   if (!t || !face_velocity) throw Error(FL_ERR_ARG, "not a secondordertvd operator");
   t->vel.assign(*t->g, t->output_loc, face_velocity);
+  ++g_fd_field_generation;
   FD_END
 }
 extern "C" int fluca_b200_fd_tvd_set_current_solution(fluca_b200_fd *h, const double *phi)
@@ -780,6 +784,7 @@ extern "C" int fluca_b200_fd_tvd_set_current_solution(fluca_b200_fd *h, const do
   TVD *t = h ? dynamic_cast<TVD *>(h->op) : nullptr;
   if (!t || !phi) throw Error(FL_ERR_ARG, "not a secondordertvd operator");
   t->phi.assign(*t->g, LOC_ELEMENT, phi);
+  ++g_fd_field_generation;
   FD_END
 }
 extern "C" int fluca_b200_fd_set_locations(fluca_b200_fd *h, int input_loc, int input_c, int output_loc, int output_c)
@@ -995,23 +1000,117 @@ static void build_plan(Op &op, Plan &p)
 } // namespace fd
 } // namespace fluca
 
-extern "C" int fluca_b200_fd_apply_inputs(fluca_b200_fd *h, int *ninputs, int loc[4], int c[4])
-{
-  FD_BEGIN
-  if (!h || !h->op || !ninputs || !loc || !c) throw Error(FL_ERR_ARG, "null argument");
-  Plan p;
-  build_plan(*h->op, p);
-  *ninputs = p.nslots;
-  for (int s = 0; s < p.nslots; ++s) loc[s] = p.slot_loc[s], c[s] = p.slot_c[s];
-  FD_END
-}
-
 namespace fluca {
 namespace fd {
+// ---- v2: the ASSEMBLED apply, for everything the class-table kernel above rejects (vector scale, second-order TVD with its
+// limiters, non-uniform coordinates, periodic stencils wider than the ghost width).  The host evaluates FlucaFDGetStencil at
+// every output point -- exactly what FlucaFDApply does per point (fdapply.c:85-106) and what FlucaFDGetOperator assembles
+// into a Mat (fdapply.c:123-180) -- into an ELL table (column-major: entry t of every row is contiguous), boundary values and
+// constant terms folded into one number per row, and the kernel computes y = const + sum_t w_t x_slot(idx_t), one thread per
+// output point.  A tree with field-dependent nodes is re-assembled when one of its fields changed (TVD: every apply after
+// SetCurrentSolution, as in the reference, whose stencils are re-derived per point on every FlucaFDApply).
+struct Assembled {
+  long                  nrows = 0;
+  int                   width = 0; // entries per row (rows are padded with zero weights)
+  std::vector<double>   val;       // [width][nrows]
+  std::vector<unsigned> idx;       // [width][nrows]: (slot << 28) | linear index in the slot's compact array
+  std::vector<double>   cst;       // [nrows]
+  int                   nslots = 0, slot_loc[MAX_SLOTS], slot_c[MAX_SLOTS];
+  int                   E[3] = {1, 1, 1};
+};
+static const unsigned ELL_IDX_BITS = 28, ELL_IDX_MASK = (1u << ELL_IDX_BITS) - 1u;
+
+struct EllFunctor {
+  long            nrows;
+  int             width;
+  const double   *val;
+  const unsigned *idx;
+  const double   *cst;
+  const double   *in[MAX_SLOTS];
+  double         *out;
+  FL_HD void operator()(long r) const
+  {
+    double acc = cst[r];
+    for (int t = 0; t < width; ++t) {
+      const unsigned e = idx[(size_t)t * nrows + r];
+      acc += val[(size_t)t * nrows + r] * in[e >> ELL_IDX_BITS][e & ELL_IDX_MASK];
+    }
+    out[r] = acc;
+  }
+};
+
+static void assemble(Op &op, Assembled &a)
+{
+  const Grid &g = *op.g;
+  if (!op.setupcalled) throw Error(FL_ERR_ARG, "FlucaFD not setup");
+  field_extents(g, op.output_loc, a.E);
+  a.nrows = (long)a.E[0] * a.E[1] * a.E[2];
+  std::vector<Stencil> rows((size_t)a.nrows);
+  int                  in_ext[MAX_SLOTS][3];
+  a.nslots = 0, a.width = 1;
+  a.cst.assign((size_t)a.nrows, 0.);
+  // pass 1: stencils, slots, row width
+  for (int k = 0; k < a.E[2]; ++k)
+    for (int j = 0; j < a.E[1]; ++j)
+      for (int i = 0; i < a.E[0]; ++i) {
+        const long r = (long)i + (long)a.E[0] * ((long)j + (long)a.E[1] * (long)k);
+        Stencil   &st = rows[(size_t)r];
+        op.stencil(i, j, k, st);
+        int nint = 0;
+        for (int q = 0; q < st.n; ++q) {
+          const Col &c = st.col[q];
+          if (c.c == CONSTANT) a.cst[(size_t)r] += st.v[q];
+          else if (c.c < 0) a.cst[(size_t)r] += st.v[q] * op.bc_value[-c.c - 1]; // fdapply.c:99-104
+          else {
+            ++nint;
+            int slot = -1;
+            for (int s2 = 0; s2 < a.nslots; ++s2)
+              if (a.slot_loc[s2] == c.loc && a.slot_c[s2] == c.c) slot = s2;
+            if (slot < 0) {
+              if (a.nslots >= MAX_SLOTS) throw Error(FL_ERR_ARG, "too many distinct input fields");
+              slot = a.nslots++, a.slot_loc[slot] = c.loc, a.slot_c[slot] = c.c;
+              field_extents(g, c.loc, in_ext[slot]);
+              if ((long)in_ext[slot][0] * in_ext[slot][1] * in_ext[slot][2] > (long)ELL_IDX_MASK) throw Error(FL_ERR_ARG, "input field too large for the assembled apply (2^28 entries)");
+            }
+          }
+        }
+        a.width = std::max(a.width, nint);
+      }
+  // pass 2: the ELL table
+  a.val.assign((size_t)a.width * a.nrows, 0.);
+  a.idx.assign((size_t)a.width * a.nrows, 0u);
+  for (long r = 0; r < a.nrows; ++r) {
+    const Stencil &st = rows[(size_t)r];
+    int            t  = 0;
+    for (int q = 0; q < st.n; ++q) {
+      const Col &c = st.col[q];
+      if (c.c < 0) continue;
+      int slot = 0;
+      for (int s2 = 0; s2 < a.nslots; ++s2)
+        if (a.slot_loc[s2] == c.loc && a.slot_c[s2] == c.c) slot = s2;
+      int qi[3] = {c.i, c.j, c.k};
+      for (int d = 0; d < 3; ++d) {
+        const int n = in_ext[slot][d];
+        if (d < g.dim && g.per[d]) qi[d] = ((qi[d] % n) + n) % n; // ghost elements of a periodic direction (DMGlobalToLocal fills them)
+        if (qi[d] < 0 || qi[d] >= n) throw Error(FL_ERR_INTERNAL, "stencil point outside the input field after off-grid removal");
+      }
+      const unsigned lin = (unsigned)((long)qi[0] + (long)in_ext[slot][0] * ((long)qi[1] + (long)in_ext[slot][1] * (long)qi[2]));
+      a.val[(size_t)t * a.nrows + r] = st.v[q];
+      a.idx[(size_t)t * a.nrows + r] = ((unsigned)slot << ELL_IDX_BITS) | lin;
+      ++t;
+    }
+  }
+}
+
 struct DevicePlan {
   Exec                ex;
   Plan                p;
   ApplyFunctor        f; // table pointers filled in; in[] / out set per launch
+  bool                assembled = false; // v2 (ELL) instead of the class table
+  bool                field_dep = false; // the tree holds field-dependent nodes: rebuilt when a field changed
+  long                generation = 0;
+  Assembled           a;
+  EllFunctor          ef;
   std::vector<void *> owned;
 };
 void free_device_plan(DevicePlan *dp)
@@ -1025,8 +1124,22 @@ void free_device_plan(DevicePlan *dp)
   dp->ex.destroy();
   delete dp;
 }
+// can the class-table kernel (v1) serve this operator?  (build_plan throws FL_ERR_ARG with the reason otherwise)
+static bool class_table_applies(Op &op, Plan &p)
+{
+  if (getenv("FLUCA_B200_FD_ASSEMBLED")) return false; // tests: force the assembled path
+  try {
+    build_plan(op, p);
+    return true;
+  } catch (const Error &e) {
+    if (e.code != FL_ERR_ARG || !op.setupcalled) throw;
+    return false;
+  }
+}
+
 static DevicePlan *device_plan(fluca_b200_fd *h)
 {
+  if (h->plan && h->plan->field_dep && h->plan->generation != g_fd_field_generation) free_device_plan(h->plan), h->plan = nullptr;
   if (h->plan) return h->plan;
 #ifndef FLUCA_HOSTEMU
   {
@@ -1035,7 +1148,9 @@ static DevicePlan *device_plan(fluca_b200_fd *h)
   }
 #endif
   std::unique_ptr<DevicePlan> dp(new DevicePlan());
-  build_plan(*h->op, dp->p);
+  dp->assembled = !class_table_applies(*h->op, dp->p);
+  dp->field_dep = field_dependent(h->op), dp->generation = g_fd_field_generation;
+  if (dp->assembled) assemble(*h->op, dp->a);
   dp->ex.init();
   const Grid &g = *h->op->g;
   const Plan &p = dp->p;
@@ -1046,6 +1161,29 @@ static DevicePlan *device_plan(fluca_b200_fd *h)
     return d;
   };
   ApplyFunctor &f = dp->f;
+  if (dp->assembled) {
+    try {
+      const Assembled &a = dp->a;
+      EllFunctor      &e = dp->ef;
+      e.nrows = a.nrows, e.width = a.width;
+      e.val = (const double *)up(a.val.data(), sizeof(double) * a.val.size());
+      e.idx = (const unsigned *)up(a.idx.data(), sizeof(unsigned) * a.idx.size());
+      e.cst = (const double *)up(a.cst.data(), sizeof(double) * a.cst.size());
+      for (int s2 = 0; s2 < MAX_SLOTS; ++s2) e.in[s2] = nullptr;
+      e.out = nullptr;
+      // the v1 bookkeeping the entry points read: slots and extents
+      dp->p.nslots = a.nslots;
+      for (int s2 = 0; s2 < a.nslots; ++s2) dp->p.slot_loc[s2] = a.slot_loc[s2], dp->p.slot_c[s2] = a.slot_c[s2], field_extents(g, a.slot_loc[s2], f.in_ext[s2]);
+      for (int d = 0; d < 3; ++d) dp->p.E[d] = a.E[d];
+      dp->ex.sync();
+      std::vector<double>().swap(dp->a.val), std::vector<unsigned>().swap(dp->a.idx), std::vector<double>().swap(dp->a.cst); // the device holds them now
+    } catch (...) {
+      free_device_plan(dp.release());
+      throw;
+    }
+    h->plan = dp.release();
+    return h->plan;
+  }
   try {
     f.dim = g.dim, f.R = p.R;
     for (int d = 0; d < 3; ++d) f.E[d] = p.E[d], f.per[d] = d < g.dim ? g.per[d] : 0, f.ncls[d] = p.ncls[d];
@@ -1096,6 +1234,22 @@ static DevicePlan *device_plan(fluca_b200_fd *h)
 } // namespace fd
 } // namespace fluca
 
+extern "C" int fluca_b200_fd_apply_inputs(fluca_b200_fd *h, int *ninputs, int loc[4], int c[4])
+{
+  FD_BEGIN
+  if (!h || !h->op || !ninputs || !loc || !c) throw Error(FL_ERR_ARG, "null argument");
+  Plan p;
+  if (!class_table_applies(*h->op, p)) { // v2: the slots come from the assembled table (same discovery order as apply uses)
+    Assembled a;
+    assemble(*h->op, a);
+    p.nslots = a.nslots;
+    for (int s = 0; s < a.nslots; ++s) p.slot_loc[s] = a.slot_loc[s], p.slot_c[s] = a.slot_c[s];
+  }
+  *ninputs = p.nslots;
+  for (int s = 0; s < p.nslots; ++s) loc[s] = p.slot_loc[s], c[s] = p.slot_c[s];
+  FD_END
+}
+
 // device-resident form: inputs / output are device pointers (compact layout); the launch is asynchronous on the operator's
 // stream (fluca_b200_fd_stream), ordered with nothing else -- the caller synchronises (fluca_b200_fd_sync or its own events)
 extern "C" int fluca_b200_fd_apply_device(fluca_b200_fd *h, int ninputs, const double *const dev_inputs[], double *dev_output)
@@ -1104,14 +1258,20 @@ extern "C" int fluca_b200_fd_apply_device(fluca_b200_fd *h, int ninputs, const d
   if (!h || !h->op || !dev_inputs || !dev_output) throw Error(FL_ERR_ARG, "null argument");
   DevicePlan *dp = device_plan(h);
   if (ninputs != dp->p.nslots) throw Error(FL_ERR_ARG, "number of input fields does not match fluca_b200_fd_apply_inputs");
-  ApplyFunctor f = dp->f;
-  for (int s = 0; s < ninputs; ++s) {
+  for (int s = 0; s < ninputs; ++s)
     if (!dev_inputs[s]) throw Error(FL_ERR_ARG, "null input field");
-    f.in[s] = dev_inputs[s];
+  if (dp->assembled) {
+    EllFunctor e = dp->ef;
+    for (int s = 0; s < ninputs; ++s) e.in[s] = dev_inputs[s];
+    e.out = dev_output;
+    for_range(dp->ex, e.nrows, e);
+  } else {
+    ApplyFunctor f = dp->f;
+    for (int s = 0; s < ninputs; ++s) f.in[s] = dev_inputs[s];
+    f.out = dev_output;
+    Box b = {dp->p.E[0], dp->p.E[1], dp->p.E[2]};
+    for_box(dp->ex, b, f);
   }
-  f.out = dev_output;
-  Box b = {dp->p.E[0], dp->p.E[1], dp->p.E[2]};
-  for_box(dp->ex, b, f);
   FD_END
 }
 extern "C" int fluca_b200_fd_stream(fluca_b200_fd *h, void **stream)
@@ -1150,8 +1310,15 @@ extern "C" int fluca_b200_fd_apply(fluca_b200_fd *h, int ninputs, const double *
     const size_t nout = (size_t)p.E[0] * p.E[1] * p.E[2];
     f.out             = (double *)dev_alloc(sizeof(double) * nout);
     tmp.push_back(f.out);
-    Box b = {p.E[0], p.E[1], p.E[2]};
-    for_box(dp->ex, b, f);
+    if (dp->assembled) {
+      EllFunctor e = dp->ef;
+      for (int s = 0; s < p.nslots; ++s) e.in[s] = f.in[s];
+      e.out = f.out;
+      for_range(dp->ex, e.nrows, e);
+    } else {
+      Box b = {p.E[0], p.E[1], p.E[2]};
+      for_box(dp->ex, b, f);
+    }
     copy_d2h(dp->ex, output, f.out, sizeof(double) * nout);
     dp->ex.sync();
   } catch (...) {
@@ -1163,6 +1330,40 @@ extern "C" int fluca_b200_fd_apply(fluca_b200_fd *h, int ninputs, const double *
     throw;
   }
   for (void *d : tmp) dev_free(d);
+  FD_END
+}
+
+// FlucaFDGetOperator (fdapply.c:123-180): the matrix of the operator -- interior stencil points only, boundary and constant terms
+// left out, as the reference leaves them out of the Mat -- as host CSR.  Two calls: with rowptr == NULL it reports the sizes.
+extern "C" int fluca_b200_fd_get_operator(fluca_b200_fd *h, long *nrows, long *nnz, long *rowptr, fluca_b200_fd_col *cols, double *vals)
+{
+  FD_BEGIN
+  if (!h || !h->op || !nrows || !nnz) throw Error(FL_ERR_ARG, "null argument");
+  Op &op = *h->op;
+  if (!op.setupcalled) throw Error(FL_ERR_ARG, "FlucaFD not setup");
+  int E[3];
+  field_extents(*op.g, op.output_loc, E);
+  const long nr = (long)E[0] * E[1] * E[2];
+  long       at = 0;
+  Stencil    st;
+  for (int k = 0; k < E[2]; ++k)
+    for (int j = 0; j < E[1]; ++j)
+      for (int i = 0; i < E[0]; ++i) {
+        const long r = (long)i + (long)E[0] * ((long)j + (long)E[1] * (long)k);
+        if (rowptr) rowptr[r] = at;
+        op.stencil(i, j, k, st);
+        for (int q = 0; q < st.n; ++q) {
+          if (st.col[q].c < 0) continue;
+          if (rowptr) {
+            if (at >= *nnz) throw Error(FL_ERR_ARG, "the arrays are smaller than the operator (call with rowptr = NULL for the sizes)");
+            cols[at].i = st.col[q].i, cols[at].j = st.col[q].j, cols[at].k = st.col[q].k, cols[at].loc = st.col[q].loc, cols[at].c = st.col[q].c;
+            vals[at] = st.v[q];
+          }
+          ++at;
+        }
+      }
+  if (rowptr) rowptr[nr] = at;
+  *nrows = nr, *nnz = at;
   FD_END
 }
 

@@ -114,6 +114,17 @@ class FlucaFD:
         _check(self.L, self.L.fluca_b200_fd_apply(self._h, len(arrs), ptr, out.ctypes.data))
         return out
 
+    def GetOperator(self):
+        """FlucaFDGetOperator (fdapply.c:123-180) as scipy-style CSR pieces over the output points: (rowptr, cols, vals) with
+        cols = [(i, j, k, loc, c)] of the interior stencil points (boundary and constant terms are not part of the matrix)."""
+        nr, nz = C.c_long(), C.c_long()
+        _check(self.L, self.L.fluca_b200_fd_get_operator(self._h, C.byref(nr), C.byref(nz), None, None, None))
+        rowptr = (C.c_long * (nr.value + 1))()
+        cols = (_lib.FDCol * max(nz.value, 1))()
+        vals = (C.c_double * max(nz.value, 1))()
+        _check(self.L, self.L.fluca_b200_fd_get_operator(self._h, C.byref(nr), C.byref(nz), rowptr, cols, vals))
+        return np.array(rowptr[: nr.value + 1]), [(cols[q].i, cols[q].j, cols[q].k, cols[q].loc, cols[q].c) for q in range(nz.value)], np.array(vals[: nz.value])
+
     def ApplyDevice(self, dev_inputs: Sequence[int], dev_output: int):
         """device pointers (ints) in ApplyInputs() order; asynchronous on Stream(); Sync() waits"""
         ptr = (C.c_void_p * max(len(dev_inputs), 1))(*dev_inputs)

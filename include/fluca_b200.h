@@ -259,7 +259,9 @@ int fluca_b200_fd_setup(fluca_b200_fd *fd);
 int fluca_b200_fd_get_stencil(fluca_b200_fd *fd, int i, int j, int k, int *ncols, fluca_b200_fd_col col[FLUCA_B200_FD_MAX_STENCIL], double v[FLUCA_B200_FD_MAX_STENCIL]);
 /* FlucaFDApply (flucafd.h:75, fdapply.c:47-121) as a matrix-free device kernel generated from the stencil layer; v1 covers
  * derivative / sum / constant scale / composition on uniform product coordinates and rejects anything else with an error
- * (csrc/fd.cu).  apply_inputs reports which input fields (location, component) the composed operator reads, in the order
+ * (csrc/fd.cu) -- v2: those fall to the ASSEMBLED apply (every point's stencil evaluated on the host into an ELL table, one
+ * thread per output point on the device; re-assembled when a field the tree depends on changed), so vector scale, second-order
+ * TVD and non-uniform coordinates are applied too.  apply_inputs reports which input fields (location, component) the composed operator reads, in the order
  * apply expects them; inputs / output are host arrays in the compact layout above (copied to and from the device inside).
  * Needs a CUDA device (FLUCA_B200_ERR_NODEVICE otherwise). */
 int fluca_b200_fd_apply_inputs(fluca_b200_fd *fd, int *ninputs, int loc[4], int c[4]);
@@ -270,6 +272,10 @@ int fluca_b200_fd_apply(fluca_b200_fd *fd, int ninputs, const double *const inpu
 int fluca_b200_fd_apply_device(fluca_b200_fd *fd, int ninputs, const double *const dev_inputs[], double *dev_output);
 int fluca_b200_fd_stream(fluca_b200_fd *fd, void **stream);
 int fluca_b200_fd_sync(fluca_b200_fd *fd);
+/* FlucaFDGetOperator (flucafd.h, fdapply.c:123-180): the operator's matrix as host CSR over the output points (row = i + nx (j + ny k)
+ * of the output location), interior stencil points only -- boundary and constant terms are left out, as the reference leaves
+ * them out of the Mat.  Call with rowptr = NULL for the sizes, then with arrays of nrows + 1 / nnz / nnz entries. */
+int fluca_b200_fd_get_operator(fluca_b200_fd *fd, long *nrows, long *nnz, long *rowptr, fluca_b200_fd_col *cols, double *vals);
 int fluca_b200_fd_destroy(fluca_b200_fd *fd);
 
 #ifdef __cplusplus

@@ -1,10 +1,10 @@
-"""FlucaFDApply as a matrix-free kernel generated from the stencil layer (csrc/fd.cu, v1: derivative / sum / constant scale /
-composition on uniform coordinates) against the point-by-point definition of fdapply.c:85-106 evaluated with the
-golden-pinned stencil layer (tests/test_fd_stencils.py) at EVERY output point, boundary closures and corners included.
+"""FlucaFDApply on the device (csrc/fd.cu) against the point-by-point definition of fdapply.c:85-106 evaluated with the
+golden-pinned stencil layer (tests/test_fd_stencils.py) at EVERY output point, boundary closures and corners included:
+v1, the class-table kernel (derivative / sum / constant scale / composition on uniform coordinates), and v2, the assembled
+(ELL) apply that serves everything else -- vector scale, second-order TVD with its limiters (the operator of
+tutorials/fd/ex1.c), non-uniform coordinates, wide periodic stencils -- and FlucaFDGetOperator (fdapply.c:123-180).
 
-CPU: the host-emulation build of the same sources.  The GPU cases are skipped, not claimed: the kernel was written after this
-round's GPU budget was spent and has not run on a B200 yet; they are the first thing to enable next round.
-(The file sorts last on purpose.)"""
+CPU: the host-emulation build of the same sources; -m gpu: the CUDA library.  (The file sorts last on purpose.)"""
 import os
 
 import numpy as np
@@ -132,19 +132,115 @@ def test_device_resident_form_and_plan_rebuild_host_emulation():
     assert np.abs(out - want).max() < 1e-11 and np.abs(want - reference_apply(op, g, fields, out_loc, bc)).max() > 1e-3
 
 
-def test_what_v1_does_not_cover_is_rejected_not_approximated():
+# ---- v2: what the class-table kernel cannot serve goes through the assembled (ELL) apply: vector scale, second-order TVD with
+# its limiters, non-uniform coordinates, periodic stencils wider than the ghost width -- the operators of tutorials/fd/ex1-4.c
+def case_vector_scale_1d(lib):
+    g = FD.FDGrid.uniform([12], [0.0], [1.0], library=lib)
+    d = deriv(g, 0, 1, 2, E, E)
+    d.SetBoundaryCondition(0, FD.FLUCAFD_BC_DIRICHLET, 0.4)
+    sv = FD.FlucaFDScaleCreateVector(d.SetUp(), 1.0 + np.arange(12.0) ** 1.5, E)
+    sv.SetBoundaryCondition(0, FD.FLUCAFD_BC_DIRICHLET, 0.4)
+    return g, sv.SetUp(), E, [0.4, 0, 0, 0, 0, 0]
+
+
+def case_nonuniform_laplacian_2d(lib):
+    g = FD.FDGrid([10, 8], [np.linspace(0, 1, 11) ** 1.5, 2.0 * np.linspace(0, 1, 9) ** 0.8], library=lib)
+    ops = [deriv(g, d, 2, 2, E, E).SetUp() for d in range(2)]
+    s_ = FD.FlucaFDSumCreate(ops)
+    s_.SetBoundaryCondition(0, FD.FLUCAFD_BC_DIRICHLET, 0.3), s_.SetBoundaryCondition(3, FD.FLUCAFD_BC_NEUMANN, -0.7)
+    return g, s_.SetUp(), E, [0.3, 0, 0, -0.7, 0, 0]
+
+
+def case_wide_periodic_third_derivative(lib):
+    g = FD.FDGrid.uniform([12], [0.0], [1.0], periodic=[True], stencil_width=1, library=lib)
+    return g, deriv(g, 0, 3, 2, E, E).SetUp(), E, [0.0] * 6
+
+
+def tutorial_convection_diffusion(lib, limiter, n=24, rho=1.3, gamma=0.05):
+    """the operator of tutorials/fd/ex1.c:46-110: d/dx(rho u phi) by second-order TVD composed with a face-to-element derivative,
+    minus d/dx(gamma d/dx phi); Dirichlet phi(0) = 1, phi(1) = 0"""
+    g = FD.FDGrid.uniform([n], [0.0], [1.0], library=lib)
+
+    def bcs(op):
+        op.SetBoundaryCondition(0, FD.FLUCAFD_BC_DIRICHLET, 1.0), op.SetBoundaryCondition(1, FD.FLUCAFD_BC_DIRICHLET, 0.0)
+        return op
+
+    tvd = bcs(FD.FlucaFDSecondOrderTVDCreate(g, FD.FLUCAFD_X, 0, 0))
+    FD.FlucaFDSecondOrderTVDSetLimiter(tvd, limiter)
+    tvd.SetUp()
+    conv = bcs(FD.FlucaFDCompositionCreate(FD.FlucaFDScaleCreateConstant(tvd, rho).SetUp(), deriv(g, 0, 1, 2, L, E).SetUp())).SetUp()
+    inner = deriv(g, 0, 1, 2, E, L).SetUp()
+    diff = bcs(FD.FlucaFDCompositionCreate(FD.FlucaFDScaleCreateConstant(inner, gamma).SetUp(), deriv(g, 0, 1, 2, L, E).SetUp())).SetUp()
+    op = bcs(FD.FlucaFDSumCreate([conv, FD.FlucaFDScaleCreateConstant(diff, -1.0).SetUp()])).SetUp()
+    return g, op, tvd
+
+
+V2_CASES = [case_vector_scale_1d, case_nonuniform_laplacian_2d, case_wide_periodic_third_derivative]
+
+
+@pytest.mark.parametrize("make", V2_CASES, ids=[c.__name__[5:] for c in V2_CASES])
+def test_assembled_apply_host_emulation(make):
+    _check(parity.hostemu_library(), make)
+
+
+@pytest.mark.parametrize("make", CASES[:3], ids=[c.__name__[5:] for c in CASES[:3]])
+def test_assembled_apply_equals_the_class_table_kernel(make, monkeypatch):
+    """the operators v1 serves give the same result through the assembled path (FLUCA_B200_FD_ASSEMBLED forces it)"""
     lib = parity.hostemu_library()
-    g = FD.FDGrid.uniform([8], [0.0], [1.0], library=lib)
-    d = deriv(g, 0, 1, 2, E, E).SetUp()
-    sv = FD.FlucaFDScaleCreateVector(d, np.arange(8.0), E).SetUp()
-    with pytest.raises(FD.FlucaFDError, match="vector scale and TVD"):
-        sv.ApplyInputs()
-    gn = FD.FDGrid([8], [np.linspace(0, 1, 9) ** 1.5], library=lib)
-    with pytest.raises(FD.FlucaFDError, match="uniform product coordinates"):
-        deriv(gn, 0, 1, 2, E, E).SetUp().ApplyInputs()
-    gp = FD.FDGrid.uniform([8], [0.0], [1.0], periodic=[True], stencil_width=1, library=lib)
-    with pytest.raises(FD.FlucaFDError, match="wider than the DMStag stencil width"):
-        deriv(gp, 0, 3, 2, E, E).SetUp().ApplyInputs()
+    g, op, out_loc, bc = make(lib)
+    order = op.ApplyInputs()
+    fields = {key: field(g, key[0], 20 + n) for n, key in enumerate(order)}
+    a = op.Apply(fields, out_loc)
+    monkeypatch.setenv("FLUCA_B200_FD_ASSEMBLED", "1")
+    g2, op2, _, _ = make(lib)
+    assert op2.ApplyInputs() == order
+    b = op2.Apply(fields, out_loc)
+    assert np.abs(a - b).max() <= 1e-12 * max(1.0, np.abs(a).max())
+
+
+def _tvd_check(lib, limiter):
+    g, op, tvd = tutorial_convection_diffusion(lib, limiter)
+    n = g.n[0]
+    FD.FlucaFDSecondOrderTVDSetVelocity(tvd, 1.0 + 0.3 * np.cos(np.arange(n + 1.0)))
+    bc = [1.0, 0.0, 0, 0, 0, 0]
+    for seed in (0, 1):  # the stencil depends on the current solution: a second field re-assembles the table
+        phi = np.random.default_rng(seed).uniform(0.0, 1.0, n)
+        FD.FlucaFDSecondOrderTVDSetCurrentSolution(tvd, phi)
+        assert op.ApplyInputs() == [(E, 0)]
+        got = op.Apply({(E, 0): phi}, E)
+        want = reference_apply(op, g, {(E, 0): phi}, E, bc)
+        assert np.abs(got - want).max() <= 1e-11 * max(1.0, np.abs(want).max()), (limiter, seed)
+
+
+@pytest.mark.parametrize("limiter", ["minmod", "vanleer", "superbee", "mc", "vanalbada"])
+def test_tutorial_tvd_operator_host_emulation(limiter):
+    _tvd_check(parity.hostemu_library(), limiter)
+
+
+def test_get_operator_is_the_matrix_of_apply():
+    """FlucaFDGetOperator: CSR of the interior stencil points; apply(x) = A x + apply(0) (the boundary / constant part)"""
+    lib = parity.hostemu_library()
+    g, op, out_loc, bc = case_laplacian_3d_mixed(lib)
+    rowptr, cols, vals = op.GetOperator()
+    shape = g.field_shape(E)
+    nr = int(np.prod(shape))
+    assert len(rowptr) == nr + 1 and rowptr[-1] == len(cols) == len(vals)
+    x = field(g, E, 5)
+    y = np.zeros(nr)
+    n = list(g.n) + [1] * (3 - g.dim)
+    for r in range(nr):
+        for q in range(rowptr[r], rowptr[r + 1]):
+            ci, cj, ck, loc, c = cols[q]
+            assert loc == E and c == 0
+            y[r] += vals[q] * x[ck % n[2], cj, ci]  # z is periodic in this case: ghost columns wrap
+    zero = op.Apply({(E, 0): np.zeros(shape)}, E)
+    full = op.Apply({(E, 0): x}, E)
+    assert np.abs(full.ravel() - (y + zero.ravel())).max() <= 1e-10 * np.abs(full).max()
+    # the stencil at one interior point is that row
+    i, j, k = 4, 3, 2
+    r = i + shape[2] * (j + shape[1] * k)
+    st = [(cv, v) for cv, v in op.GetStencil(i, j, k) if cv[4] >= 0]
+    assert sorted((cols[q], vals[q]) for q in range(rowptr[r], rowptr[r + 1])) == sorted(st)
 
 
 def test_product_library_refuses_to_apply_without_a_device():
@@ -161,8 +257,16 @@ def test_product_library_refuses_to_apply_without_a_device():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("make", CASES, ids=[c.__name__[5:] for c in CASES])
+@pytest.mark.parametrize("make", CASES + V2_CASES, ids=[c.__name__[5:] for c in CASES + V2_CASES])
 def test_apply_cuda(make):
     L_ = fb._lib.load()
     assert L_.fluca_b200_is_host_emulation() == 0
     _check(L_, make)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("limiter", ["minmod", "superbee"])
+def test_tutorial_tvd_operator_cuda(limiter):
+    L_ = fb._lib.load()
+    assert L_.fluca_b200_is_host_emulation() == 0
+    _tvd_check(L_, limiter)

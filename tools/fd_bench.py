@@ -1,7 +1,6 @@
 """Times the generated FlucaFDApply kernel (csrc/fd.cu, v1) on device-resident fields: a 7-point Laplacian (sum of three
 second derivatives, Dirichlet / Neumann / periodic mix) on n^3 elements.  Algorithmic traffic: 8 B read + 8 B written per
-output point.  Not part of bench.py's contract; prints one JSON line.  NOT YET RUN (written after the GPU budget of round 1
-was spent) -- tools/next_round_gpu.sh runs it.
+output point.  Not part of bench.py's contract; prints one JSON line.  --assembled times the v2 ELL path.
 
     python tools/fd_bench.py --n 512 --reps 20
 """
@@ -18,7 +17,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=512)
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--assembled", action="store_true", help="time the v2 assembled (ELL) apply of the same operator instead of the class-table kernel")
     args = ap.parse_args()
+    if args.assembled:
+        os.environ["FLUCA_B200_FD_ASSEMBLED"] = "1"
     import torch
 
     import fluca_b200 as fb
@@ -58,7 +60,9 @@ def main():
     except Exception:
         pass
     ach = 16.0 * n**3 / (ms * 1e-3) / 1e9
-    print(json.dumps({"kernel": "fd_apply_laplacian", "n": n, "avg_ms": ms, "reps": args.reps, "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}, "interior_rel_err_vs_torch": err}))
+    if args.assembled:  # the table is the traffic: 7 entries x (8 B weight + 4 B index) + 8 B constant + 8 B result, + the gathered x
+        ach = (7 * 12.0 + 8.0 + 8.0 + 8.0) * n**3 / (ms * 1e-3) / 1e9
+    print(json.dumps({"kernel": "fd_apply_laplacian_assembled_ell" if args.assembled else "fd_apply_laplacian", "n": n, "avg_ms": ms, "reps": args.reps, "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}, "interior_rel_err_vs_torch": err}))
 
 
 if __name__ == "__main__":
