@@ -429,7 +429,8 @@ def measure(ctx, lib, args, scaling, with_e2e):
         nzg = n * world // 8 if scaling == "weak" else n  # config 5: 2048 x 1024 x 1024 on 8 GPUs = 128 z-planes per GPU
         nzg = max(nzg, 8 * world)
     big = (float(n) ** 2 * nzg / world) * (2 if args.workload == "channel" else 1) >= 100e6
-    restart = args.restart or (3 if big else 10)
+    # config 5 (2.2 GB per field and GPU): the coupled mode fits with restart 1 (73 fields)
+    restart = args.restart or ((1 if args.workload == "channel" else 3) if big else 10)
     case = make_case(args, n, nzg)
     note(f"measure {scaling}: building {case.n}")
     opts = {"ns_ksp_gmres_restart": restart, "ns_pc_abf_schur_ainv_type": args.schur_ainv, "ns_pc_abf_upper_ainv_type": args.upper_ainv}

@@ -233,7 +233,7 @@ struct AinvCells { // ainv = 1 / diag(A) (type 1) or 1 / rowsum(A) (type 2)
   }
 };
 
-// y = A x fused with acc[0] += <a, y>, acc[1] += <y, y>
+// y = A x fused with acc[0] += <a, y>, acc[1] += <y, y>, acc[2] += <x, y>, acc[3] += <a, x>
 template <int DIM>
 struct AApplyDots {
   Geom       g;
@@ -241,20 +241,24 @@ struct AApplyDots {
   BcDev      bc;
   CV3        x, v0, U0, a;
   V3         y;
-  FL_HD void operator()(int i, int j, int kl, double acc[2]) const
+  FL_HD void operator()(int i, int j, int kl, double acc[4]) const
   {
     double r[DIM];
     a_apply_cell<DIM>(g, sp, bc, x, v0, U0, i, j, kl, r);
     const long c = g.idx(i, j, kl);
-    double     d0 = 0., d1 = 0.;
+    double     d0 = 0., d1 = 0., d2 = 0., d3 = 0.;
 #pragma unroll
     for (int q = 0; q < DIM; ++q) {
       y.c[q][c] = r[q];
       d0 += a.c[q][c] * r[q];
       d1 += r[q] * r[q];
+      d2 += x.c[q][c] * r[q];
+      d3 += a.c[q][c] * x.c[q][c];
     }
     acc[0] += d0;
     acc[1] += d1;
+    acc[2] += d2;
+    acc[3] += d3;
   }
 };
 

@@ -349,7 +349,7 @@ static void build_rhs(Solver &s)
   halo_scalar(s, q);
   MomentumRhs<DIM> mr;
   mr.g = g, mr.sp = s.sp, mr.bc = s.bc, mr.v0 = CV3(s.v0), mr.q = q, mr.r = s.rm;
-  for_box(s.ex, cell_box(s), mr);
+  FOR_BOX_MINB(1, cell_box(s), mr);
 
   // r_int = bcT(t+dt) + (-T) dt/rho (bcG(tq) - bcG(th)) + dt/rho (bcGst(tq) - bcGst(th)),  :2998-3033
   for (int d = 0; d < DIM; ++d) dev_zero(s.ex, s.ri.c[d], sizeof(double) * (size_t)g.nalloc);
@@ -1044,7 +1044,7 @@ double bench_kernel(Solver &s, const std::string &n)
     if (s.dim == 3) {
       MomentumRhs<3> mr;
       mr.g = g, mr.sp = s.sp, mr.bc = s.bc, mr.v0 = CV3(s.v0), mr.q = s.phalf, mr.r = s.rm;
-      for_box(s.ex, cell_box(s), mr);
+      FOR_BOX_MINB(1, cell_box(s), mr);
     }
     return 56.;
   }

@@ -238,7 +238,7 @@ struct AApplyTile : TileOpDefaults {
       if (uniform) a_apply_tile_uniform(uc, sp, tv, r);
       else a_apply_tile<false>(g, sp, bc, tv, i, j, kl, r);
     } else a_apply_tile<true>(g, sp, bc, tv, i, j, kl, r);
-    double    d0 = 0., d1 = 0.;
+    double    d0 = 0., d1 = 0., d2 = 0., d3 = 0.;
     if (NRED == 0 && wout[0]) {
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
@@ -251,12 +251,14 @@ struct AApplyTile : TileOpDefaults {
     for (int q = 0; q < 3; ++q) {
       y[q][c] = r[q];
       if (NRED > 0) {
-        const double av = a[q] ? rg.a[q] : tv.p0[q * TILE_STRIDE + tv.lc];
+        const double xv = tv.p0[q * TILE_STRIDE + tv.lc], av = a[q] ? rg.a[q] : xv;
         d0 += av * r[q];
         d1 += r[q] * r[q];
+        d2 += xv * r[q];
+        d3 += av * xv;
       }
     }
-    if (NRED > 0) acc[0] += d0, acc[1] += d1;
+    if (NRED > 0) acc[0] += d0, acc[1] += d1, acc[2] += d2, acc[3] += d3;
   }
 };
 
@@ -277,7 +279,7 @@ struct XWallAt {
   FL_HD void operator()(int a, int b, int, double *acc) const { f(i, a, kbeg + b, acc); }
 };
 
-// y = A x ; out[0] = <a, y>, out[1] = <y, y> are left in ex.d_result (reduce_finish reads them)
+// y = A x ; out = {<a, y>, <y, y>, <x, y>, <a, x>} are left in ex.d_result (reduce_finish reads them)
 void a_apply_dots_tma(Solver &s, const V3 &x, const V3 &y, const V3 &a, bool with_dots)
 {
   const Geom &g  = s.gh.g;
@@ -295,13 +297,13 @@ void a_apply_dots_tma(Solver &s, const V3 &x, const V3 &y, const V3 &a, bool wit
   if (wl) {
     PlaneAt<AApplyDots<3>> pf = {f, 0};
     double                *res = s.ex.d_carry + Exec::MAXR * ncar;
-    for_box_reduce<2>(s.ex, plane_box, pf, carry, res);
+    for_box_reduce<4>(s.ex, plane_box, pf, carry, res);
     carry = res, ++ncar;
   }
   if (wh && g.nzl - 1 >= kbeg) {
     PlaneAt<AApplyDots<3>> pf = {f, g.nzl - 1};
     double                *res = s.ex.d_carry + Exec::MAXR * ncar;
-    for_box_reduce<2>(s.ex, plane_box, pf, carry, res);
+    for_box_reduce<4>(s.ex, plane_box, pf, carry, res);
     carry = res, ++ncar;
   }
   // 2. the x-wall columns of the remaining planes
@@ -310,7 +312,7 @@ void a_apply_dots_tma(Solver &s, const V3 &x, const V3 &y, const V3 &a, bool wit
     for (int side = 0; side < 2; ++side) {
       XWallAt<AApplyDots<3>> xf = {f, side ? g.nx - 1 : 0, kbeg};
       double                *res = s.ex.d_carry + Exec::MAXR * ncar;
-      for_box_reduce<2>(s.ex, wall_box, xf, carry, res);
+      for_box_reduce<4>(s.ex, wall_box, xf, carry, res);
       carry = res, ++ncar;
     }
   }
@@ -322,7 +324,7 @@ void a_apply_dots_tma(Solver &s, const V3 &x, const V3 &y, const V3 &a, bool wit
   uc.l4 = 0.;
   for (int d = 0; d < 3; ++d) uc.q[d] = 0.25 / g.t[d].uh, uc.l[d] = 1. / (g.t[d].uh * g.t[d].uh), uc.l4 += 4. * uc.l[d];
   if (with_dots) {
-    AApplyTile<2> op;
+    AApplyTile<4> op;
     op.g = g, op.sp = s.sp, op.bc = s.bc, op.uc = uc, op.uniform = uniform;
     for (int c = 0; c < 3; ++c) op.a[c] = (a.c[c] == x.c[c]) ? nullptr : a.c[c], op.y[c] = y.c[c], op.wout[c] = nullptr;
     tma_launch(s.ex, op, fields, g.px, g.py, g.nzl + 2, g.nx, g.ny, kbeg, kend, carry, g.t[0].per != 0);
@@ -357,7 +359,7 @@ void coupled_cells_tma(Solver &s, const V3 &x, const double *p, const V3 &y, con
   GradCells<3> gc;
   gc.g = g, gc.dtrho = s.sp.dtrho, gc.p = p, gc.w = w;
   const Box all = {g.nx, g.ny, g.nzl};
-  for_box<2>(s.ex, all, gc);
+  for_box<2, 3>(s.ex, all, gc); // 80 registers: three CTAs per SM (the streaming kernels follow occupancy, profiles/r04)
   // 2. wall planes and wall columns with the direct-load functor (it forms the gradient itself)
   const bool wl = g.t[2].wall_lo && !g.t[2].per, wh = g.t[2].wall_hi && !g.t[2].per;
   CoupledCells<3> f;

@@ -27,7 +27,7 @@ namespace fluca {
 
 static const int TMX = 32, TMY = 8;             // cells per tile (one warp = one 32-cell row)
 #ifndef FL_TILE_PLANES
-#define FL_TILE_PLANES 2 // planes per CTA barrier of the 1-field tile operators (build with -DFL_TILE_PLANES=1 for A/B runs)
+#define FL_TILE_PLANES 1 // planes per CTA barrier of the 1-field tile operators; 2 measured 4-6 % SLOWER (profiles/r04: the kernels are issue-bound, not barrier-bound)
 #endif
 // box with halo.  The innermost start coordinate of a TMA box must be 16-byte aligned (measured on B200 with
 // tools/tma_probe.cu: an odd fp64 start coordinate raises "illegal instruction", even ones -- negative or
