@@ -454,8 +454,9 @@ def measure(ctx, lib, args, scaling, with_e2e):
     sampler = ClockSampler(ctx.local)
     if rank == 0:
         sampler.start()
-    s.kernel_times(reset=True)
-    s.kernel_timing(True)
+    # (1) the headline: K steps with NO per-launch instrumentation (event pairs around ~700 launches per step cost time, and
+    #     the multigrid cycles replay as CUDA graphs only when nothing is recorded between their launches)
+    s.kernel_timing(False)
     l0 = s.launch_count()
     stats = []
     start, stop = ctx.stream_timer(s)
@@ -469,10 +470,23 @@ def measure(ctx, lib, args, scaling, with_e2e):
     ms = ctx.max_over_ranks(ms)
     note(f"measure {scaling}: {ms / args.steps:.2f} ms per step")
     launches = s.launch_count() - l0
-    ktimes = s.kernel_times(reset=True)
-    s.kernel_timing(False)
     clocks = sampler.stop() if rank == 0 else None
     value = cells_total * args.steps / (ms * 1e-3) / 1e6
+    # (2) the breakdown: a few more steps with a CUDA-event pair around every launch (class times, per-class rooflines)
+    nb = max(1, min(args.steps, 5))
+    s.kernel_times(reset=True)
+    s.kernel_timing(True)
+    bstats = []
+    start, stop = ctx.stream_timer(s)
+    ctx.barrier()
+    start()
+    for _ in range(nb):
+        fb.NSStep(ns)
+        bstats.append(fb.NSB200GetStats(ns))
+    bms = ctx.max_over_ranks(stop())
+    ctx.barrier()
+    ktimes = s.kernel_times(reset=True)
+    s.kernel_timing(False)
 
     # ---- rooflines (live CUDA-event pairs around every launch of the timed region; this rank's kernels)
     peak, peak_src = load_peaks()
@@ -489,21 +503,21 @@ def measure(ctx, lib, args, scaling, with_e2e):
         tr = traffic.get("momentum_apply", {})
         roof = {"kernel": "k_tma_march<AApplyTile> + wall launches (momentum operator y = A x fused with <a, y>, <y, y>)", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": (tr["bytes_per_cell"] * cells_rank / 1e9 if "bytes_per_cell" in tr else None), "traffic_unit": "GB per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum per cell of the committed capture x cells of this launch)", "traffic_source": tr.get("capture"),
-                "algorithmic_GB_per_launch": 96.0 * cells_rank / 1e9, "algorithmic_bytes_per_cell": 96.0, "launches": cnt_ma, "avg_ms": t_ma / cnt_ma, "share_of_step": t_ma / ms, "peak_source": peak_src,
+                "algorithmic_GB_per_launch": 96.0 * cells_rank / 1e9, "algorithmic_bytes_per_cell": 96.0, "launches": cnt_ma, "avg_ms": t_ma / cnt_ma, "share_of_step": t_ma / bms, "peak_source": peak_src,
                 "achieved_counting_the_dot_partner": 108.0 * cells_rank * cnt_ma / (t_ma * 1e-3) / 1e9, "note": "achieved = SURVEY 8(d)'s 96 B/cell x cells of one launch / mean CUDA-event duration of one operator application in the timed region; the second figure adds the dot partner r^ that every other application reads (108 B/cell mean)"}
     # per class: the step model (fluca_b200_step_model_bytes_split) over the event time of the class
     split = {}
-    for st in stats:
+    for st in bstats:
         for k, v in s.model_bytes_split(st).items():
             split[k] = split.get(k, 0.0) + v
     classes = {}
     for k, (t, cnt) in ktimes.items():
         if cnt and t > 0:
             by = split.get(k, 0.0)
-            classes[k] = {"ms_per_step": t / args.steps, "launch_groups": cnt, "share_of_step": round(t / ms, 4), "model_GB_per_step": by / args.steps / 1e9, "achieved": (by / (t * 1e-3) / 1e9) if by else None, "frac": (by / (t * 1e-3) / 1e9 / peak) if by else None}
+            classes[k] = {"ms_per_step": t / nb, "launch_groups_per_step": cnt / nb, "share_of_step": round(t / bms, 4), "model_GB_per_step": by / nb / 1e9, "achieved": (by / (t * 1e-3) / 1e9) if by else None, "frac": (by / (t * 1e-3) / 1e9 / peak) if by else None}
     t_solve = sum(ktimes[k][0] for k in ("poisson_apply", "poisson_vec", "mg_smooth", "mg_transfer"))
     b_solve = sum(split.get(k, 0.0) for k in ("poisson_apply", "poisson_vec", "mg_smooth", "mg_transfer"))
-    its_p = int(sum(st.schur_its for st in stats))
+    its_p = int(sum(st.schur_its for st in bstats))
     poisson = None
     if t_solve > 0 and its_p > 0:
         ach = b_solve / (t_solve * 1e-3) / 1e9
@@ -523,7 +537,8 @@ def measure(ctx, lib, args, scaling, with_e2e):
         "poisson_solve": poisson,
         "step_roofline": {"algorithmic_GB_per_step": model_bytes / args.steps / 1e9 * world, "achieved": step_ach * world, "peak": peak * world, "unit": "GB/s", "frac": step_ach / peak, "peak_source": peak_src, "note": "SURVEY 8(d) step model bytes (this rank's cells) / step time / peak"},
         "class_rooflines": classes,
-        "time_outside_kernels_frac": max(0.0, 1.0 - kernel_ms / ms),
+        "breakdown": {"steps": nb, "ms_per_step": bms / nb, "iterations_per_step": {"outer": [st.outer_its for st in bstats], "momentum": [st.mom_its for st in bstats], "schur": [st.schur_its for st in bstats]}, "note": "class_rooflines, roofline and poisson_solve come from these extra steps, run after the headline steps with a CUDA-event pair around every launch (eager multigrid cycles); the headline value is timed without any of that"},
+        "time_outside_kernels_frac": max(0.0, 1.0 - kernel_ms / bms),
         "gpu_launches": int(launches),
         "clocks": clocks,
         "l2": f"inputs larger than L2 (each field {8 * cells_rank / 1e6:.0f} MB per GPU vs 126 MB L2; >50 fields streamed per step), no flush",

@@ -18,6 +18,7 @@ namespace fluca {
 
 struct NcclComm : public Comm {
   ncclComm_t comm = nullptr;
+  bool       capturable() const override { return true; } // NCCL operations are stream-ordered enqueues
   ~NcclComm() override
   {
     if (comm) ncclCommDestroy(comm);

@@ -596,6 +596,11 @@ void mg_setup(Solver &s)
 
 void mg_destroy(Solver &s)
 {
+#ifndef FLUCA_HOSTEMU
+  for (Solver::VGraph &g : s.vgraphs)
+    if (g.exec) cudaGraphExecDestroy((cudaGraphExec_t)g.exec);
+#endif
+  s.vgraphs.clear();
   for (void *p : s.mg_owned) dev_free(p);
   s.mg_owned.clear();
   s.mg.clear();
@@ -604,7 +609,7 @@ void mg_destroy(Solver &s)
 
 // returns z = V-cycle(r) with zero initial guess; want_dot: the last sweep leaves <r, z> in ex.d_result.  r is a fine-level field (Geom layout); the result
 // lives in a level-0 buffer (same layout, ghost planes included) that stays valid until the next call.
-double *mg_vcycle(Solver &s, double *r, bool want_dot)
+static double *mg_vcycle_eager(Solver &s, double *r, bool want_dot)
 {
   MGLevel &L0 = s.mg[0];
   L0.b        = r;
@@ -612,6 +617,84 @@ double *mg_vcycle(Solver &s, double *r, bool want_dot)
   else vcycle<3>(s, s.mg, 0, want_dot);
   L0.b = nullptr;
   return L0.x;
+}
+
+#ifndef FLUCA_HOSTEMU
+// The V-cycle as a CUDA graph.  A cycle is ~100 launches -- most of them a few microseconds long on the coarse levels -- and, on
+// several ranks, ~16 grouped NCCL exchanges; enqueueing them costs the host more than the GPU needs to run them (8-GPU strong
+// scaling, profiles/r04: 200 communication calls per step at 43 us each, the stream running dry in between).  The cycle is a fixed
+// sequence for given buffer roles, so it is captured once per (input field, dot flag, roles of the Jacobi double buffers) and
+// replayed with ONE launch.  Not used while per-launch event timing is on (the events would be baked into the graph) or with a
+// host-callback communicator.
+static void mg_roles(Solver &s, std::vector<double *> &v)
+{
+  v.clear();
+  for (auto *lv : {&s.mg, &s.mg_agg})
+    for (MGLevel &L : *lv) v.push_back(L.x), v.push_back(L.t);
+}
+static void mg_set_roles(Solver &s, const std::vector<double *> &v)
+{
+  size_t at = 0;
+  for (auto *lv : {&s.mg, &s.mg_agg})
+    for (MGLevel &L : *lv) L.x = v[at++], L.t = v[at++];
+}
+
+static double *mg_vcycle_graph(Solver &s, double *r, bool want_dot)
+{
+  std::vector<double *> now;
+  mg_roles(s, now);
+  for (Solver::VGraph &g : s.vgraphs)
+    if (g.r == r && g.dot == want_dot && g.pre == now) {
+      FL_CUDA(cudaGraphLaunch((cudaGraphExec_t)g.exec, s.ex.stream));
+      mg_set_roles(s, g.post);
+      s.ex.stats.launches += g.launches;
+      return s.mg[0].x;
+    }
+  if (s.vgraphs.size() >= 32) return mg_vcycle_eager(s, r, want_dot); // roles never settle: stay eager
+  // capture: the eager code enqueues into the capturing stream; nothing runs until the launch below
+  const long  l0 = s.ex.stats.launches;
+  cudaGraph_t graph = nullptr;
+  bool        ok = cudaStreamBeginCapture(s.ex.stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+  if (ok) {
+    try {
+      (void)mg_vcycle_eager(s, r, want_dot);
+    } catch (...) {
+      ok = false;
+    }
+    if (cudaStreamEndCapture(s.ex.stream, &graph) != cudaSuccess || !graph) ok = false;
+  }
+  cudaGraphExec_t exec = nullptr;
+  if (ok && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) ok = false;
+  if (graph) cudaGraphDestroy(graph);
+  if (!ok) {
+    // not capturable here: undo the host-side role changes of the aborted pass and run the cycle the ordinary way from now on
+    (void)cudaGetLastError();
+    mg_set_roles(s, now);
+    s.ex.stats.launches = l0;
+    s.vgraph_state      = -1;
+    return mg_vcycle_eager(s, r, want_dot);
+  }
+  Solver::VGraph g;
+  g.pre = now, g.r = r, g.dot = want_dot, g.exec = (void *)exec, g.launches = s.ex.stats.launches - l0;
+  mg_roles(s, g.post);
+  s.vgraphs.push_back(g);
+  FL_CUDA(cudaGraphLaunch(exec, s.ex.stream));
+  return s.mg[0].x;
+}
+#endif
+
+double *mg_vcycle(Solver &s, double *r, bool want_dot)
+{
+#ifndef FLUCA_HOSTEMU
+  if (s.vgraph_state == 0) {
+    static const bool off = getenv("FLUCA_B200_NO_GRAPH") != nullptr;
+    s.vgraph_state = (!off && s.comm->capturable() && (!s.local_comm || s.local_comm->capturable())) ? 1 : -1;
+  }
+  // the first cycles run eagerly (one-time kernel attribute settings and tensor maps happen there)
+  // (tests toggle FLUCA_B200_NO_MG_FUSION between calls: a captured cycle would not see it)
+  if (s.vgraph_state == 1 && !s.ex.ktime_on && getenv("FLUCA_B200_NO_MG_FUSION") == nullptr && ++s.vcycles > 2) return mg_vcycle_graph(s, r, want_dot);
+#endif
+  return mg_vcycle_eager(s, r, want_dot);
 }
 
 } // namespace fluca

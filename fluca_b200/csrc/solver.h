@@ -26,11 +26,15 @@ struct Comm {
   // with rank + 1; the ends talk to each other when periodic, else their outer buffers are left alone
   virtual void sendrecv(Exec &ex, const double *send_down, double *recv_down, const double *send_up, double *recv_up, long count, bool periodic) = 0;
   virtual void barrier(Exec &ex) { (void)ex; }
+  // every operation of this communicator is an asynchronous enqueue on ex.stream (no host round trip): its calls may be
+  // captured into a CUDA graph
+  virtual bool capturable() const { return false; }
 };
 
 struct LocalComm : public Comm {
   void halo(Exec &ex, double *const *fields, int nf, long plane, int nzl, bool periodic) override;
   void allsum(Exec &, double *, int) override { }
+  bool capturable() const override { return true; }
   void allgather(Exec &ex, const double *send, double *recv, long count) override { copy_d2d(ex, recv, send, sizeof(double) * count); }
   void sendrecv(Exec &ex, const double *send_down, double *recv_down, const double *send_up, double *recv_up, long count, bool periodic) override
   {
@@ -160,6 +164,17 @@ struct Solver {
   std::vector<MGLevel> mg_agg; // agglomerated coarse levels: the global grid on every rank, solved redundantly
   std::unique_ptr<Comm> local_comm; // single-rank halo (periodic wrap) of the replicated levels
   std::vector<void *>  mg_owned;
+  // CUDA graphs of the V-cycle (mg.cu): one per (input field, dot flag, buffer roles of the Jacobi double buffers)
+  struct VGraph {
+    std::vector<double *> pre, post; // x / t of every level before and after the cycle
+    double               *r;
+    bool                  dot;
+    void                 *exec; // cudaGraphExec_t
+    long                  launches;
+  };
+  std::vector<VGraph> vgraphs;
+  int                 vgraph_state = 0; // 0 untried, 1 in use, -1 disabled (capture failed or not applicable)
+  long                vcycles = 0;
   // outer GMRES basis: (restart + 1) vectors of 7 fields, plus work vectors
   std::vector<std::vector<double *>> basis, zbasis; // zbasis[k] = ABF(basis[k]) (flexible GMRES: no final application)
   V3      wv, wU, zv, zU, tw;
