@@ -629,6 +629,7 @@ def run_b200(args, ctx=None, lib=None):
         "poisson_solve": head["poisson_solve"],
         "step_roofline": head["step_roofline"],
         "class_rooflines": head["class_rooflines"],
+        "breakdown": head["breakdown"],
         "time_outside_kernels_frac": head["time_outside_kernels_frac"],
         "gpu_launches": head["gpu_launches"],
         "clocks": head["clocks"],
@@ -639,7 +640,7 @@ def run_b200(args, ctx=None, lib=None):
             line[k] = head[k]
     if "weak" in runs and order[0] != "weak":
         w = runs["weak"]
-        line["weak"] = {k: w[k] for k in ("value", "ms_per_step", "cells", "workload", "iterations_per_step", "step_roofline", "time_outside_kernels_frac", "gpu_launches")}
+        line["weak"] = {k: w[k] for k in ("value", "ms_per_step", "cells", "workload", "iterations_per_step", "step_roofline", "class_rooflines", "time_outside_kernels_frac", "gpu_launches")}
         line["weak"]["unit"] = "Mcell-updates/s"
 
     # ---- CPU baseline on the box's host cores (rank 0, N=1 only), bounded sample
