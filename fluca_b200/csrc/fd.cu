@@ -871,13 +871,18 @@ struct ApplyFunctor {
   {
     const bool fast = fast_n > 0 && i >= fast_lo[0] && i < fast_hi[0] && j >= fast_lo[1] && j < fast_hi[1] && k >= fast_lo[2] && k < fast_hi[2];
     if (FL_WARP_ALL(fast)) {
+      // index of P in every slot's array once per point (registers; the slot of a tap selects one), then one add, one load and
+      // one fma per tap.  The arrays of this path hold fewer than 2^31 entries (checked when the plan is built).
+      int base[MAX_SLOTS];
+#pragma unroll
+      for (int s = 0; s < MAX_SLOTS; ++s) base[s] = i + in_ext[s][0] * (j + in_ext[s][1] * k);
       double acc = fast_const;
       for (int t = 0; t < fast_n; ++t) {
-        const int  s    = fast_slot[t];
-        const long base = (long)i + (long)in_ext[s][0] * ((long)j + (long)in_ext[s][1] * (long)k); // index of P in slot s
-        acc += fast_w[t] * in[s][base + fast_off[t]];
+        const int s = fast_slot[t];
+        const int b = s == 0 ? base[0] : (s == 1 ? base[1] : (s == 2 ? base[2] : base[3]));
+        acc += fast_w[t] * in[s][b + fast_off[t]];
       }
-      out[(long)i + (long)E[0] * ((long)j + (long)E[1] * (long)k)] = acc;
+      out[i + E[0] * (j + E[1] * k)] = acc;
       return;
     }
     const int    v  = (cls(2, k) * ncls[1] + cls(1, j)) * ncls[0] + cls(0, i);
@@ -1204,7 +1209,9 @@ static DevicePlan *device_plan(fluca_b200_fd *h)
       const int v = (cv[2] * p.ncls[1] + cv[1]) * p.ncls[0] + cv[0];
       const int t0 = p.tap_start[v], t1 = p.tap_start[v + 1];
       f.fast_n = 0;
-      if (t1 - t0 <= FLUCA_B200_FD_MAX_STENCIL) {
+      bool small = (long)p.E[0] * p.E[1] * p.E[2] < (1L << 31);
+      for (int s2 = 0; s2 < p.nslots; ++s2) small = small && (long)f.in_ext[s2][0] * f.in_ext[s2][1] * f.in_ext[s2][2] < (1L << 31);
+      if (small && t1 - t0 <= FLUCA_B200_FD_MAX_STENCIL) {
         f.fast_n     = t1 - t0;
         f.fast_const = p.var_const[v];
         int reach[3] = {0, 0, 0};

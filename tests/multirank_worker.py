@@ -86,6 +86,7 @@ def main():
         "sphere_ibm": lambda: cases.channel3d(n=(12, 8, 8), pout=0.1, dt=0.05),
         "sphere_ibm_tma": lambda: cases.channel3d(n=(40, 16, 16), pout=0.1, dt=0.02),
         "sphere_ibm_periodic": lambda: cases.channel3d(n=(12, 8, 12), periodic_z=True, dt=0.05),
+        "channel5": lambda: cases.channel_bench_case((8, 6, 8), periodic_z=True),  # BASELINE config 5's boundary set: periodic x and z, walls in y
     }[case_name]()
     markers = None
     if case_name.startswith("sphere_ibm"):  # the body straddles the slab interface: gather and scatter both cross it

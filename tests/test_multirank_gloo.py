@@ -52,6 +52,7 @@ CASEMAP = {
     "sphere_ibm": lambda: cases.channel3d(n=(12, 8, 8), pout=0.1, dt=0.05),
     "sphere_ibm_tma": lambda: cases.channel3d(n=(40, 16, 16), pout=0.1, dt=0.02),
     "sphere_ibm_periodic": lambda: cases.channel3d(n=(12, 8, 12), periodic_z=True, dt=0.05),
+    "channel5": lambda: cases.channel_bench_case((8, 6, 8), periodic_z=True),
 }
 
 
@@ -70,7 +71,7 @@ def _oracle_reference(case_name, mode, ainv=(0, 0)):
 
 @pytest.mark.parametrize(
     "case_name,mode,world",
-    [("cavity3d", "coupled", 2), ("channel3d", "coupled", 2), ("periodic_z", "fractional", 2), ("uneven", "fractional", 2), ("three", "fractional", 3), ("sphere_ibm", "coupled", 2), ("sphere_ibm_periodic", "fractional", 3)],
+    [("cavity3d", "coupled", 2), ("channel3d", "coupled", 2), ("periodic_z", "fractional", 2), ("uneven", "fractional", 2), ("three", "fractional", 3), ("sphere_ibm", "coupled", 2), ("sphere_ibm_periodic", "fractional", 3), ("channel5", "coupled", 2)],
 )
 def test_slab_partition_matches_oracle(case_name, mode, world, tmp_path):
     parity.hostemu_library()

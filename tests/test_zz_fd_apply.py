@@ -175,6 +175,41 @@ def tutorial_convection_diffusion(lib, limiter, n=24, rho=1.3, gamma=0.05):
     return g, op, tvd
 
 
+def tutorial_ex3_rhs_2d(lib, limiter, n=(14, 12), mu=0.01):
+    """the right-hand side operator of tutorials/fd/ex3.c:55-125: -(d/dx)(u phi) - (d/dy)(v phi) + (d/dx)(mu dphi/dx) + (d/dy)(mu dphi/dy) on
+    a doubly periodic square, the two convective fluxes by second-order TVD"""
+    g = FD.FDGrid.uniform(list(n), [0.0, 0.0], [1.0, 1.0], periodic=[True, True], library=lib)
+    tvds, terms = [], []
+    for d, face in ((0, L), (1, D)):
+        t = FD.FlucaFDSecondOrderTVDCreate(g, d, 0, 0)
+        FD.FlucaFDSecondOrderTVDSetLimiter(t, limiter)
+        tvds.append(t.SetUp())
+        conv = FD.FlucaFDCompositionCreate(t, deriv(g, d, 1, 2, face, E).SetUp()).SetUp()
+        terms.append(FD.FlucaFDScaleCreateConstant(conv, -1.0).SetUp())
+        inner = FD.FlucaFDScaleCreateConstant(deriv(g, d, 1, 2, E, face).SetUp(), mu).SetUp()
+        terms.append(FD.FlucaFDCompositionCreate(inner, deriv(g, d, 1, 2, face, E).SetUp()).SetUp())
+    return g, FD.FlucaFDSumCreate(terms).SetUp(), tvds
+
+
+def _ex3_check(lib, limiter):
+    g, op, tvds = tutorial_ex3_rhs_2d(lib, limiter)
+    rng = np.random.default_rng(7)
+    FD.FlucaFDSecondOrderTVDSetVelocity(tvds[0], 1.0 + 0.2 * rng.standard_normal(g.field_shape(L)))
+    FD.FlucaFDSecondOrderTVDSetVelocity(tvds[1], -0.7 + 0.2 * rng.standard_normal(g.field_shape(D)))
+    for seed in (0, 1):
+        phi = np.random.default_rng(seed).uniform(0.0, 1.0, g.field_shape(E))
+        for t in tvds:
+            FD.FlucaFDSecondOrderTVDSetCurrentSolution(t, phi)
+        got = op.Apply({(E, 0): phi}, E)
+        want = reference_apply(op, g, {(E, 0): phi}, E, [0.0] * 6)
+        assert np.abs(got - want).max() <= 1e-11 * max(1.0, np.abs(want).max()), (limiter, seed)
+
+
+@pytest.mark.parametrize("limiter", ["minmod", "vanleer", "mc"])
+def test_tutorial_ex3_2d_periodic_tvd_operator_host_emulation(limiter):
+    _ex3_check(parity.hostemu_library(), limiter)
+
+
 V2_CASES = [case_vector_scale_1d, case_nonuniform_laplacian_2d, case_wide_periodic_third_derivative]
 
 
@@ -270,3 +305,4 @@ def test_tutorial_tvd_operator_cuda(limiter):
     L_ = fb._lib.load()
     assert L_.fluca_b200_is_host_emulation() == 0
     _tvd_check(L_, limiter)
+    _ex3_check(L_, limiter)
