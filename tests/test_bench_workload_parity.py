@@ -59,3 +59,23 @@ def test_cavity_workload_default_tolerances_64cube(lib):
     case = cases.cavity_bench_case(64, 64)
     out = parity.default_tolerance_check(case, lib, case.initial_state(), nsteps=3, orc_steps=3)
     print("cavity 64^3 at default tolerances:", out)
+
+
+def channel_workload(n3, nspheres=2):
+    """bench.py's config-5 builder (periodic x and z, no-slip walls in y, several spheres) at n3 cells; one sphere sits across the
+    periodic x boundary so that marker supports wrap"""
+    case = cases.channel_bench_case(n3, periodic_z=True)
+    h = case.hi[0] / n3[0]
+    Lx, Ly, Lz = case.hi
+    centres = [(0.02 * Lx, 0.5 * Ly, 0.45 * Lz), (0.6 * Lx, 0.4 * Ly, 0.98 * Lz)][:nspheres]
+    D = 0.25 * Ly
+    mk = cases.multi_sphere_markers(centres, D, 150, h)
+    return case, mk
+
+
+@pytest.mark.parametrize("n3", [(64, 16, 8), (40, 12, 12)], ids=["tiled_64x16x8", "tiled_shifted_40x12x12"])
+def test_channel_workload_with_wrapping_markers_matches_oracle(lib, n3):
+    """BASELINE config 5's code path: periodic-x tile kernels + immersed-boundary supports that wrap in x and z, coupled mode"""
+    case, mk = channel_workload(n3)
+    out = parity.compare_steps(case, lib, mode="coupled", nsteps=2, tol=1e-10, markers=mk, state=cases.uniform_inflow_state(case), fast_oracle=True, ilu_blocks=os.cpu_count() or 1)
+    parity.assert_histories_track(out)
