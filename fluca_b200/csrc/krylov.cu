@@ -179,29 +179,23 @@ int momentum_solve(Solver &s, const V3 &b, const V3 &x, bool guess, double bscal
 
 // ------------------------------------------------------------------ Poisson
 template <int DIM>
-struct PoissonApplyDot { // out = P p ; acc += {<a, out>, <out, out>, <a2, out>, <a, a2>} (the last two with a second partner)
+struct PoissonApplyDot { // out = P p ; acc[0] += <a, out>
   Geom          g;
-  const double *p, *a, *a2;
+  const double *p, *a;
   double       *out;
-  FL_HD void operator()(int i, int j, int kl, double acc[4]) const
+  FL_HD void operator()(int i, int j, int kl, double acc[1]) const
   {
     Nbr<DIM> nb;
     nbr<DIM>(g, i, j, kl, nb);
-    const double v = poisson_apply_cell<DIM>(g, p, nb), av = a[nb.c];
+    const double v = poisson_apply_cell<DIM>(g, p, nb);
     out[nb.c]      = v;
-    acc[0] += av * v;
-    acc[1] += v * v;
-    if (a2) {
-      const double bv = a2[nb.c];
-      acc[2] += bv * v;
-      acc[3] += av * bv;
-    }
+    acc[0] += a[nb.c] * v;
   }
 };
 
 // DIAG / ROWSUM Schur complement (abfpc.c:155-170): out = P p + vol D T ((1 - a1) .* G0 p), two passes with the
 // cell field w = (1 - a1) .* G0 p in between (its halo plane is needed by T across a slab face); returns <a, out>
-double schur_variant_apply_dot(Solver &s, double *pin, double *out, const double *a, const double *a2, double *sums)
+double schur_variant_apply_dot(Solver &s, double *pin, double *out, const double *a)
 {
   if (!s.ainv_s.c[0] || !s.prepared) throw Error(FL_ERR_ARG, "the DIAG / ROWSUM Schur complement needs the momentum operator of a prepared step");
   halo_scalar(s, pin);
@@ -222,49 +216,44 @@ double schur_variant_apply_dot(Solver &s, double *pin, double *out, const double
     KScope kt(s.ex, KT_POISSON_APPLY);
     if (s.dim == 2) {
       SchurVariantApplyDot<2> f;
-      f.g = s.gh.g, f.p = pin, f.a = a, f.a2 = a2, f.w = CV3(s.tw), f.out = out;
-      for_box_reduce<4>(s.ex, cell_box(s), f);
+      f.g = s.gh.g, f.p = pin, f.a = a, f.w = CV3(s.tw), f.out = out;
+      for_box_reduce<1>(s.ex, cell_box(s), f);
     } else {
       SchurVariantApplyDot<3> f;
-      f.g = s.gh.g, f.p = pin, f.a = a, f.a2 = a2, f.w = CV3(s.tw), f.out = out;
-      for_box_reduce<4>(s.ex, cell_box(s), f);
+      f.g = s.gh.g, f.p = pin, f.a = a, f.w = CV3(s.tw), f.out = out;
+      for_box_reduce<1>(s.ex, cell_box(s), f);
     }
   }
-  double r[4];
-  reduce_finish(s, 4, r);
-  if (sums)
-    for (int q = 0; q < 4; ++q) sums[q] = r[q];
-  return r[0];
+  double r;
+  reduce_finish(s, 1, &r);
+  return r;
 }
 
-// out = P p (or the DIAG / ROWSUM Schur complement); returns <a, out>; sums (optional) = {<a, out>, <out, out>, <a2, out>, <a, a2>}
-static double poisson_apply_dot(Solver &s, double *pin, double *out, const double *a, const double *a2 = nullptr, double *sums = nullptr)
+static double poisson_apply_dot(Solver &s, double *pin, double *out, const double *a)
 {
-  if (s.opt.schur_ainv != 0) return schur_variant_apply_dot(s, pin, out, a, a2, sums);
+  if (s.opt.schur_ainv != 0) return schur_variant_apply_dot(s, pin, out, a);
   halo_scalar(s, pin);
 #ifndef FLUCA_HOSTEMU
   if (tma_usable(s)) {
     KScope kt(s.ex, KT_POISSON_APPLY);
-    poisson_apply_dot_tma(s, pin, out, a, a2);
+    poisson_apply_dot_tma(s, pin, out, a);
   } else
 #endif
   {
     KScope kt(s.ex, KT_POISSON_APPLY);
     if (s.dim == 2) {
       PoissonApplyDot<2> f;
-      f.g = s.gh.g, f.p = pin, f.a = a, f.a2 = a2, f.out = out;
-      for_box_reduce<4>(s.ex, cell_box(s), f);
+      f.g = s.gh.g, f.p = pin, f.a = a, f.out = out;
+      for_box_reduce<1>(s.ex, cell_box(s), f);
     } else {
       PoissonApplyDot<3> f;
-      f.g = s.gh.g, f.p = pin, f.a = a, f.a2 = a2, f.out = out;
-      for_box_reduce<4>(s.ex, cell_box(s), f);
+      f.g = s.gh.g, f.p = pin, f.a = a, f.out = out;
+      for_box_reduce<1>(s.ex, cell_box(s), f);
     }
   }
-  double r[4];
-  reduce_finish(s, 4, r);
-  if (sums)
-    for (int q = 0; q < 4; ++q) sums[q] = r[q];
-  return r[0];
+  double r;
+  reduce_finish(s, 1, &r);
+  return r;
 }
 
 void poisson_apply(Solver &s, double *pin, double *out)
@@ -367,27 +356,26 @@ static int poisson_bicgstab(Solver &s, double *b, double *x)
     if (std::sqrt(red[0]) <= tol) break;
     double       *zf = mg_vcycle(s, s.ps); // z = M^-1 s  (y is dead by now: x was updated above)
     const double *Z  = zf + off;
-    // t = P z with four fused sums: <r^, t>, <t, t>, <s, t>, <r^, s> -- as in the momentum solve, the next rho and beta are known
-    // before r is formed, so x, r and p are updated in ONE pass (x, z, s, t, p, v -> x, r, p) with one reduction
-    double sums[4];
-    (void)poisson_apply_dot(s, zf, s.pt, s.prh, s.ps, sums);
-    if (sums[1] == 0.) throw Error(FL_ERR_DIVERGED, "BiCGStab breakdown in the pressure solve (P z = 0)");
-    omega = sums[2] / sums[1];
-    const double rho_new = sums[3] - omega * sums[0];
-    if (rho_new == 0. || omega == 0. || !(rho_new == rho_new)) throw Error(FL_ERR_DIVERGED, "BiCGStab breakdown in the pressure solve (rho = 0)");
-    const double beta = (rho_new / rho) * (alpha / omega);
-    rho               = rho_new;
-    for_range_reduce<1>(s.ex, len, FL_LAMBDA(long i, double acc[1]) {
+    const double  ts = poisson_apply_dot(s, zf, s.pt, s.ps);
+    for_range_reduce<1>(s.ex, len, FL_LAMBDA(long i, double acc[1]) { acc[0] += T[i] * T[i]; });
+    reduce_finish(s, 1, red);
+    if (red[0] == 0.) throw Error(FL_ERR_DIVERGED, "BiCGStab breakdown in the pressure solve (P z = 0)");
+    omega = ts / red[0];
+    for_range_reduce<2>(s.ex, len, FL_LAMBDA(long i, double acc[2]) {
       X[i] += omega * Z[i];
       const double rv = S[i] - omega * T[i];
       R[i]            = rv;
-      PP[i]           = rv + beta * (PP[i] - omega * V[i]);
       acc[0] += rv * rv;
+      acc[1] += RH[i] * rv;
     });
-    reduce_finish(s, 1, red);
+    reduce_finish(s, 2, red);
     s.stats.schur_last_rel = std::sqrt(red[0]) / bnorm;
     if (std::sqrt(red[0]) <= tol) break;
     if (!(red[0] == red[0])) throw Error(FL_ERR_DIVERGED, "pressure residual is NaN");
+    if (red[1] == 0. || omega == 0.) throw Error(FL_ERR_DIVERGED, "BiCGStab breakdown in the pressure solve (rho = 0)");
+    const double beta = (red[1] / rho) * (alpha / omega);
+    rho               = red[1];
+    for_range(s.ex, len, FL_LAMBDA(long i) { PP[i] = R[i] + beta * (PP[i] - omega * V[i]); });
   }
   s.stats.schur_its += it;
   return (it >= s.opt.inner_maxit) ? 1 : 0;

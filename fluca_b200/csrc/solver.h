@@ -227,7 +227,7 @@ void coupled_apply(Solver &s, const V3 &xv, const V3 &xU, double *xp, const V3 &
 void schur_apply_reference_scaling(Solver &s, double *pin, double *out);
 void set_ainv_types(Solver &s, int schur_type, int upper_type); // PCABFSetSchurComplementAinvType / ...UpperTriangular...
 // out = vol (rho/dt) S' p for the DIAG / ROWSUM Schur complement, returns <a, out> (uses s.tw)
-double schur_variant_apply_dot(Solver &s, double *pin, double *out, const double *a, const double *a2 = nullptr, double *sums = nullptr);
+double schur_variant_apply_dot(Solver &s, double *pin, double *out, const double *a);
 int  do_step(Solver &s, double t, int step_index);
 double bench_kernel(Solver &s, const std::string &name); // one launch of a named kernel group (tools/kernel_bench.py)
 
@@ -236,7 +236,7 @@ double bench_kernel(Solver &s, const std::string &name); // one launch of a name
 bool tma_usable(const Solver &s);
 void tensor_map_forget(const double *field); // drops the cached tensor maps of a field that is about to be freed
 void a_apply_dots_tma(Solver &s, const V3 &x, const V3 &y, const V3 &a, bool with_dots);
-void poisson_apply_dot_tma(Solver &s, const double *pin, double *out, const double *a, const double *a2);
+void poisson_apply_dot_tma(Solver &s, const double *pin, double *out, const double *a);
 // w carries (dt/rho) G p into the tile kernel; keep_w: it leaves as x + (dt/rho) G p (the operand of the face block)
 void coupled_cells_tma(Solver &s, const V3 &x, const double *p, const V3 &y, const V3 &w, bool keep_w);
 #endif

@@ -685,14 +685,14 @@ struct GradScaleCells {
 
 // Schur complement of the DIAG / ROWSUM variants in the scaling of the pressure solve:
 //   out = vol * (rho/dt) S' p = P p + vol * D T w,   w = (1 - a1) .* G0 p   (abfpc.c:155-170; S' = D((-T) a1 G~ - (-R)))
-// fused with acc[0] += <a, out>, acc[1] += <out, out>, and -- with a second partner -- acc[2] += <a2, out>, acc[3] += <a, a2>
+// fused with acc[0] += <a, out>
 template <int DIM>
 struct SchurVariantApplyDot {
   Geom          g;
-  const double *p, *a, *a2;
+  const double *p, *a;
   CV3           w;
   double       *out;
-  FL_HD void operator()(int i, int j, int kl, double acc[4]) const
+  FL_HD void operator()(int i, int j, int kl, double acc[1]) const
   {
     Nbr<DIM> nb;
     nbr<DIM>(g, i, j, kl, nb);
@@ -713,14 +713,7 @@ struct SchurVariantApplyDot {
       s += area[d] * (up - lo);
     }
     out[nb.c] = s;
-    const double av = a[nb.c];
-    acc[0] += av * s;
-    acc[1] += s * s;
-    if (a2) {
-      const double bv = a2[nb.c];
-      acc[2] += bv * s;
-      acc[3] += av * bv;
-    }
+    acc[0] += a[nb.c] * s;
   }
 };
 

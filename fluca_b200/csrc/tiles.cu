@@ -402,19 +402,17 @@ template <int NRED>
 struct PoissonTile : TileOpDefaults {
   static const int NIN = 1, NR = NRED, MINB = 4, STAGES = 8, PLANES = FL_TILE_PLANES;
   Geom             g;
-  const double    *a;  // dot partner; nullptr: p itself
-  const double    *a2; // second partner (BiCGStab: the sums <a2, q> and <a, a2> come along); may be null
+  const double    *a; // dot partner; nullptr: p itself
   double          *out;
   int              uniform; // all directions uniform: interior warps use the constant row cd[d] (2 p - p- - p+)
   double           cd[3];
   struct Regs {
-    double a, a2;
+    double a;
   };
   __device__ int flags(int i, int j) const { return (uniform && (g.t[0].per || (i > 0 && i < g.nx - 1)) && j > 0 && j < g.ny - 1) ? 1 : 0; }
   __device__ void prefetch(Regs &rg, int off, int kl) const
   {
     if (NRED > 0 && a) rg.a = a[off];
-    if (NRED > 0 && a2) rg.a2 = a2[off];
   }
   __device__ void cell(const TileView &tv, const Regs &rg, int fl, int i, int j, int kl, int off, double *acc) const
   {
@@ -426,21 +424,16 @@ struct PoissonTile : TileOpDefaults {
     if (__all_sync(__activemask(), inter)) v = cd[0] * (2. * pc - pm[0] - pp[0]) + cd[1] * (2. * pc - pm[1] - pp[1]) + cd[2] * (2. * pc - pm[2] - pp[2]);
     else v = poisson_row<3>(g, ig, pc, pm, pp);
     out[off] = v;
-    if (NRED > 0) {
-      const double av = a ? rg.a : pc;
-      acc[0] += av * v;
-      acc[1] += v * v;
-      if (a2) acc[2] += rg.a2 * v, acc[3] += av * rg.a2;
-    }
+    if (NRED > 0) acc[0] += (a ? rg.a : pc) * v;
   }
 };
 
-// out = P p ; {<a, out>, <out, out>, <a2, out>, <a, a2>} are left in ex.d_result (the last two only with a second partner)
-void poisson_apply_dot_tma(Solver &s, const double *pin, double *out, const double *a, const double *a2)
+// out = P p ; <a, out> is left in ex.d_result
+void poisson_apply_dot_tma(Solver &s, const double *pin, double *out, const double *a)
 {
   const Geom    &g = s.gh.g;
-  PoissonTile<4> op;
-  op.g = g, op.a = (a == pin) ? nullptr : a, op.a2 = a2, op.out = out;
+  PoissonTile<1> op;
+  op.g = g, op.a = (a == pin) ? nullptr : a, op.out = out;
   static const bool no_uni = getenv("FLUCA_B200_NO_UNIFORM") != nullptr;
   op.uniform = (!no_uni && g.t[0].uni && g.t[1].uni && g.t[2].uni) ? 1 : 0;
   {
