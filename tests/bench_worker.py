@@ -2,7 +2,6 @@
 callback communicator of tests/multirank_worker.py.  Runs bench.run_b200 (parity self-check + strong + weak measurement) on a
 tiny grid so that mismatched collectives between ranks show up here and not on an 8-GPU box."""
 import argparse
-import json
 import os
 import sys
 import time
@@ -64,9 +63,6 @@ def main():
     lines = []
     bench.print_json = lines.append
     args = argparse.Namespace(gpus=ctx.world, steps=2, warmup=1, impl="b200", workload=os.environ.get("BENCH_WORKLOAD", "sphere"), n=int(os.environ.get("BENCH_N", "16")), markers=300, scaling="both", strong=False, mode="coupled", restart=0, schur_ainv="ID", upper_ainv="ID", cpu_n=8, no_cpu_baseline=True, no_e2e=False, no_parity=False)
-
-    class _NoDestroy:  # bench.run_b200 tears the process group down at the end
-        pass
 
     bench.run_b200(args, ctx=ctx, lib=lib)
     if ctx.rank == 0:

@@ -7,7 +7,6 @@ themselves -- sphere + pressure outlet + symmetry + immersed boundary, and the 3
 (reference: NSStep_CNLinear_Cart3d_Internal cnlinearcart3d.c:2807-2863, tolerances nssol.c:21-29)."""
 import os
 
-import numpy as np
 import pytest
 
 import fluca_b200 as fb

@@ -5,8 +5,6 @@ v1, the class-table kernel (derivative / sum / constant scale / composition on u
 tutorials/fd/ex1.c), non-uniform coordinates, wide periodic stencils -- and FlucaFDGetOperator (fdapply.c:123-180).
 
 CPU: the host-emulation build of the same sources; -m gpu: the CUDA library.  (The file sorts last on purpose.)"""
-import os
-
 import numpy as np
 import pytest
 
