@@ -210,3 +210,21 @@ def test_config4_sphere512_full_size_properties(lib):
     F, Um = fb.NSB200GetMarkerForces(ns)
     assert F[0].sum() < 0.0 and np.isfinite(st["p"]).all() and np.abs(Um[0]).max() <= 1.5
     fb.NSDestroy(ns)
+
+
+@pytest.mark.parametrize("restart", [1, 3])
+def test_restarted_outer_gmres_matches_oracle(lib, restart):
+    """short restarts (BASELINE config 5 runs GMRES(1) for memory): the restart residual is formed in the last basis vector"""
+    case = cases.cavity3d(n=(48, 24, 10))
+    state = case.initial_state(seed=23)
+    orc = cases.make_oracle(case)
+    orc.set_state(*state)
+    ns = parity.make_ns(case, lib, "coupled", **dict(parity.TIGHT, ns_ksp_gmres_restart=restart, ns_ksp_max_it=400))
+    parity.set_initial(ns, state)
+    orc.step(O.default_options(mode=0, **parity.ORC_TIGHT))
+    fb.NSStep(ns)
+    st = fb.NSB200GetStats(ns)
+    assert st.converged and st.outer_its > restart
+    a, b = orc.get_state(), fb.NSB200GetSolver(ns).get_state()
+    assert parity.rel(b["v"], a["v"]) < 1e-10 and parity.relU(b["U"], a["U"]) < 1e-10 and parity.rel(b["p"], a["p"]) < 1e-9
+    fb.NSDestroy(ns)

@@ -228,3 +228,24 @@ def _formfunction_between_steps(lib, case, seed):
 def test_formfunction_has_no_side_effect_on_the_state(lib):
     _formfunction_between_steps(lib, cases.cavity2d(n=16), 4)
     _formfunction_between_steps(lib, cases.channel3d(n=(8, 6, 6), pout=0.2, dt=0.05), 9)
+
+
+@pytest.mark.parametrize("restart", [1, 2, 5])
+def test_restarted_outer_gmres_matches_oracle(lib, restart):
+    """Short restarts (BASELINE config 5 runs GMRES(1) for memory): the residual of a new cycle is formed in the last basis vector
+    (aliased work space, solver_setup) and the cycles must still converge to the oracle's answer."""
+    case = cases.cavity3d(n=(8, 8, 4))
+    state = case.initial_state(seed=5)
+    orc = cases.make_oracle(case)
+    orc.set_state(*state)
+    opts = dict(parity.TIGHT, ns_ksp_gmres_restart=restart, ns_ksp_max_it=400)
+    ns = parity.make_ns(case, lib, "coupled", **opts)
+    parity.set_initial(ns, state)
+    for _ in range(2):
+        orc.step(O.default_options(mode=0, **parity.ORC_TIGHT))
+        fb.NSStep(ns)
+        st = fb.NSB200GetStats(ns)
+        assert st.converged and st.outer_its > restart  # more than one cycle ran
+    a, b = orc.get_state(), fb.NSB200GetSolver(ns).get_state()
+    assert parity.rel(b["v"], a["v"]) < 1e-10 and parity.relU(b["U"], a["U"]) < 1e-10 and parity.rel(b["p"], a["p"]) < 1e-9
+    fb.NSDestroy(ns)
