@@ -1,7 +1,8 @@
 /* tests/petsc_stub/petsc_fluca_stub.h -- TEST INFRASTRUCTURE ONLY.
- * Declaration-only stand-in for the subset of the PETSc (>= 3.23) and Fluca C APIs that glue/nsb200.c uses, so that
- * tests/test_glue_syntax.py can run `gcc -fsyntax-only` on the glue in an image without PETSc.  Nothing here has a
- * body; nothing links against it.  Signatures follow the PETSc manual pages and fluca/include/ *.h. */
+ * Stand-in for the subset of the PETSc (>= 3.23) and Fluca C APIs that glue/nsb200.c uses, in an image without PETSc:
+ * tests/test_glue_syntax.py runs `gcc -fsyntax-only` on the glue against these declarations, and tests/test_glue_mock.py
+ * links the glue with the single-rank functional model of them in petsc_fluca_mock.c and RUNS it.  Signatures follow the
+ * PETSc manual pages and fluca/include/ *.h. */
 #ifndef PETSC_FLUCA_STUB_H
 #define PETSC_FLUCA_STUB_H
 #include <stddef.h>
@@ -17,6 +18,15 @@ typedef enum { PETSC_FALSE, PETSC_TRUE } PetscBool;
 typedef int    MPI_Comm;
 typedef int    MPI_Datatype;
 typedef int    MPI_Op;
+/* the part of PETSc's object header the glue relies on (type name, state counter, communicator); first member of every mock object */
+struct _p_PetscObject {
+  const char      *class_name;
+  char             type_name[32];
+  char             name[64];
+  PetscObjectState state;
+  MPI_Comm         comm;
+  int              refct;
+};
 typedef struct _p_PetscObject *PetscObject;
 typedef struct _p_Vec *Vec;
 typedef struct _p_Mat *Mat;
@@ -67,9 +77,10 @@ PetscErrorCode PetscErrorStub(MPI_Comm, int, const char *, ...);
 #define PetscMax(a, b) ((a) > (b) ? (a) : (b))
 #define PetscRealPart(a) (a)
 PetscErrorCode PetscMallocStub(size_t, void *);
+PetscErrorCode PetscCallocStub(size_t, void *);
 #define PetscMalloc1(n, p) PetscMallocStub((size_t)(n) * sizeof(**(p)), (void *)(p))
-#define PetscCalloc1(n, p) PetscMallocStub((size_t)(n) * sizeof(**(p)), (void *)(p))
-#define PetscNew(p) PetscMallocStub(sizeof(**(p)), (void *)(p))
+#define PetscCalloc1(n, p) PetscCallocStub((size_t)(n) * sizeof(**(p)), (void *)(p))
+#define PetscNew(p) PetscCallocStub(sizeof(**(p)), (void *)(p))
 PetscErrorCode PetscFreeStub(void *);
 #define PetscFree(p) (PetscFreeStub((void *)(p)) || ((p) = NULL, 0))
 PetscErrorCode PetscMemzero(void *, size_t);
@@ -182,6 +193,7 @@ struct _NSOps {
 };
 /* the members of struct _p_NS that a type implementation touches (nsimpl.h:41-82) */
 struct _p_NS {
+  struct _p_PetscObject hdr;
   struct _NSOps        ops[1];
   PetscReal            rho, mu, dt, max_time;
   PetscInt             max_steps, step;
