@@ -158,14 +158,12 @@ Ext face_ext(const Geom &g, int d)
 void put(Solver &s, double *dev, const double *host, Ext e)
 {
   const Geom &g = s.gh.g;
-  for (int k = 0; k < e.planes; ++k)
-    copy2d_h2d(s.ex, dev + g.idx(0, 0, k), sizeof(double) * g.px, host + (size_t)k * e.w * e.hgt, sizeof(double) * e.w, sizeof(double) * e.w, e.hgt);
+  copy3d(s.ex, nullptr, 0, dev + g.idx(0, 0, 0), sizeof(double) * g.px, g.py, host, sizeof(double) * e.w, e.hgt, sizeof(double) * e.w, e.hgt, e.planes);
 }
 void get(Solver &s, double *host, const double *dev, Ext e)
 {
   const Geom &g = s.gh.g;
-  for (int k = 0; k < e.planes; ++k)
-    copy2d_d2h(s.ex, host + (size_t)k * e.w * e.hgt, sizeof(double) * e.w, dev + g.idx(0, 0, k), sizeof(double) * g.px, sizeof(double) * e.w, e.hgt);
+  copy3d(s.ex, nullptr, 1, host, sizeof(double) * e.w, e.hgt, dev + g.idx(0, 0, 0), sizeof(double) * g.px, g.py, sizeof(double) * e.w, e.hgt, e.planes);
 }
 size_t ext_count(Ext e) { return (size_t)e.w * e.hgt * e.planes; }
 
@@ -241,15 +239,12 @@ void *pinned_alloc(size_t bytes)
 void view_get(Solver &s, double *host, const double *dev, Ext e)
 {
   const Geom &g = s.gh.g;
-  for (int k = 0; k < e.planes; ++k) {
-    double       *dst = host + (size_t)k * e.w * e.hgt;
-    const double *src = dev + g.idx(0, 0, k);
 #ifndef FLUCA_HOSTEMU
-    FL_CUDA(cudaMemcpy2DAsync(dst, sizeof(double) * e.w, src, sizeof(double) * g.px, sizeof(double) * e.w, e.hgt, cudaMemcpyDeviceToHost, s.view.stream));
+  void *stream = (void *)s.view.stream;
 #else
-    for (int r = 0; r < e.hgt; ++r) memcpy(dst + (size_t)r * e.w, src + (size_t)r * g.px, sizeof(double) * e.w);
+  void *stream = nullptr;
 #endif
-  }
+  copy3d(s.ex, stream, 1, host, sizeof(double) * e.w, e.hgt, dev + g.idx(0, 0, 0), sizeof(double) * g.px, g.py, sizeof(double) * e.w, e.hgt, e.planes);
 }
 } // namespace
 

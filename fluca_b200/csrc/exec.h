@@ -106,7 +106,8 @@ struct Exec {
   double      *d_result   = nullptr; // [MAXR]
   double      *d_carry    = nullptr; // [4][MAXR] partial sums handed from one launch of a reduction to the next
   unsigned    *d_ticket   = nullptr;
-  double      *h_result   = nullptr; // pinned [MAXR]
+  double      *h_result   = nullptr; // pinned and mapped [MAXR]
+  double      *h_result_dev = nullptr; // the device-side address of h_result (reduce_finish publishes the sums through it)
   long         max_blocks = 0;
   int          sm_count   = 148;
   static const int MAXR = 16;
@@ -158,7 +159,7 @@ inline void copy_h2d(Exec &ex, void *dst, const void *src, size_t bytes)
   FL_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ex.stream));
 #else
   (void)ex;
-  memcpy(dst, src, bytes);
+  if (bytes) memcpy(dst, src, bytes); // an empty marker list hands a null pointer with zero bytes
 #endif
 }
 inline void copy_d2h(Exec &ex, void *dst, const void *src, size_t bytes)
@@ -167,7 +168,7 @@ inline void copy_d2h(Exec &ex, void *dst, const void *src, size_t bytes)
   FL_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ex.stream));
 #else
   (void)ex;
-  memcpy(dst, src, bytes);
+  if (bytes) memcpy(dst, src, bytes); // an empty marker list hands a null pointer with zero bytes
 #endif
 }
 inline void copy_d2d(Exec &ex, void *dst, const void *src, size_t bytes)
@@ -176,7 +177,7 @@ inline void copy_d2d(Exec &ex, void *dst, const void *src, size_t bytes)
   FL_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ex.stream));
 #else
   (void)ex;
-  memmove(dst, src, bytes);
+  if (bytes) memmove(dst, src, bytes);
 #endif
 }
 // strided 2-D copies (pitch in bytes), used to pad/unpad rows between the compact C-ABI layout
@@ -201,6 +202,33 @@ inline void copy2d_d2h(Exec &ex, void *dst, size_t dpitch, const void *src, size
   for (size_t r = 0; r < height; ++r) memcpy((char *)dst + r * dpitch, (const char *)src + r * spitch, width);
 #endif
 }
+// the same for a whole field in one call: `depth` planes of `height` rows; a plane is `dslice` / `sslice` rows apart in memory.
+// One enqueue per field instead of one per plane (512 per field at 512^3: the host needs 20-30 ms to enqueue the 3584 plane
+// copies of a solution view, during which it cannot enqueue the next step).  kind 0: host to device, 1: device to host.
+inline void copy3d(Exec &ex, void *stream, int kind, void *dst, size_t dpitch, size_t dslice, const void *src, size_t spitch, size_t sslice, size_t width, size_t height, size_t depth)
+{
+  if (!width || !height || !depth) return;
+#ifndef FLUCA_HOSTEMU
+  static const bool by_plane = getenv("FLUCA_B200_COPY_PLANES") != nullptr;
+  cudaStream_t      st = stream ? (cudaStream_t)stream : ex.stream;
+  if (by_plane) {
+    for (size_t k = 0; k < depth; ++k)
+      FL_CUDA(cudaMemcpy2DAsync((char *)dst + k * dslice * dpitch, dpitch, (const char *)src + k * sslice * spitch, spitch, width, height, kind ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice, st));
+    return;
+  }
+  cudaMemcpy3DParms p;
+  memset(&p, 0, sizeof(p));
+  p.srcPtr = make_cudaPitchedPtr(const_cast<void *>(src), spitch, width, sslice);
+  p.dstPtr = make_cudaPitchedPtr(dst, dpitch, width, dslice);
+  p.extent = make_cudaExtent(width, height, depth);
+  p.kind   = kind ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice;
+  FL_CUDA(cudaMemcpy3DAsync(&p, st));
+#else
+  (void)ex, (void)stream, (void)kind;
+  for (size_t k = 0; k < depth; ++k)
+    for (size_t r = 0; r < height; ++r) memcpy((char *)dst + (k * dslice + r) * dpitch, (const char *)src + (k * sslice + r) * spitch, width);
+#endif
+}
 
 inline void Exec::init()
 {
@@ -214,7 +242,8 @@ inline void Exec::init()
   d_result   = (double *)dev_alloc(sizeof(double) * MAXR);
   d_carry    = (double *)dev_alloc(sizeof(double) * MAXR * 4);
   d_ticket   = (unsigned *)dev_alloc(sizeof(unsigned));
-  FL_CUDA(cudaMallocHost((void **)&h_result, sizeof(double) * MAXR));
+  FL_CUDA(cudaHostAlloc((void **)&h_result, sizeof(double) * MAXR, cudaHostAllocMapped));
+  if (!getenv("FLUCA_B200_RESULT_MEMCPY")) FL_CUDA(cudaHostGetDevicePointer((void **)&h_result_dev, h_result, 0));
 #else
   h_result = (double *)calloc(MAXR, sizeof(double));
   d_result = (double *)calloc(MAXR, sizeof(double));
@@ -238,7 +267,7 @@ inline void Exec::destroy()
   free(d_result);
   free(d_carry);
 #endif
-  d_partials = d_result = h_result = d_carry = nullptr;
+  d_partials = d_result = h_result = d_carry = h_result_dev = nullptr;
   d_ticket   = nullptr;
   stream     = nullptr;
 }

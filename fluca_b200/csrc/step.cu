@@ -142,13 +142,30 @@ void halo_faces(Solver &s, const V3 &U)
   s.comm->halo(s.ex, f, 1, g.plane, g.nzl, g.t[2].per != 0);
 }
 
+#ifndef FLUCA_HOSTEMU
+__global__ void k_publish_sums(const double *__restrict__ src, double *__restrict__ dst, int n)
+{
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
+}
+#endif
+
 void reduce_finish(Solver &s, int n, double *out)
 {
   {
     KTimer kt(s.ex, KT_HALO, s.comm->nranks > 1); // communication class of the live timing: halos, allreduces, allgathers
     s.comm->allsum(s.ex, s.ex.d_result, n);
   }
-  copy_d2h(s.ex, s.ex.h_result, s.ex.d_result, sizeof(double) * n);
+  // The sums reach the host through a one-warp kernel that stores them into mapped pinned memory, not through a device-to-host
+  // memcpy: a memcpy queues on the copy engine behind whatever another stream has put there -- the 8.6 GB solution view of
+  // fluca_b200_stage_state at 512^3 (section 8c of DESIGN.md) -- and ~70 reductions per step would each wait for it.
+#ifndef FLUCA_HOSTEMU
+  if (s.ex.h_result_dev) {
+    k_publish_sums<<<1, 32, 0, s.ex.stream>>>(s.ex.d_result, s.ex.h_result_dev, n);
+    FL_CUDA(cudaGetLastError());
+    s.ex.stats.launches++;
+  } else
+#endif
+    copy_d2h(s.ex, s.ex.h_result, s.ex.d_result, sizeof(double) * n);
   s.ex.sync();
   for (int i = 0; i < n; ++i) out[i] = s.ex.h_result[i];
 }

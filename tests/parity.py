@@ -13,7 +13,8 @@ from oracle import oracle as O
 from tests import cases
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-HOSTEMU = os.path.join(ROOT, "tests", "hostemu", "_build", "libfluca_b200_hostemu.so")
+# FLUCA_B200_HOSTEMU_LIB: another build of the test double, e.g. the AddressSanitizer one of `make -C tests/hostemu asan`
+HOSTEMU = os.environ.get("FLUCA_B200_HOSTEMU_LIB") or os.path.join(ROOT, "tests", "hostemu", "_build", "libfluca_b200_hostemu.so")
 
 
 def hostemu_library():
