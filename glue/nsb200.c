@@ -437,7 +437,9 @@ static PetscErrorCode NSStep_B200(NS ns)
   PetscFunctionReturn(PETSC_SUCCESS);
 }
 
-/* right-hand side b = (r_mom, r_int, r_con) of the current step, for callers of NSFormFunction */
+/* right-hand side b = (r_mom, r_int, r_con) of the current step, for callers of NSFormFunction.  As in the reference, whose
+ * ops->formfunction fills f with b itself (cnlinearcart3d.c:2945-3043: the "b(x)" of SNESSetPicard, nsbasic.c:249; the residual
+ * A x - b is formed by SNES, not by the type) */
 static PetscErrorCode NSFormFunction_B200(NS ns, Vec x, Vec f)
 {
   NS_B200 *b = (NS_B200 *)ns->data;
@@ -447,7 +449,7 @@ static PetscErrorCode NSFormFunction_B200(NS ns, Vec x, Vec f)
   PetscInt d;
 
   PetscFunctionBegin;
-  (void)x; /* the system is linear and the guess is zero (nsbasic.c:146-151): F(0) = -b */
+  (void)x; /* the system is linear: b does not depend on x */
   {
     /* same coherence rule as NSStep_B200: a user edit of ns->sol since the last download goes up first */
     PetscObjectState st;
@@ -478,7 +480,6 @@ static PetscErrorCode NSFormFunction_B200(NS ns, Vec x, Vec f)
   for (d = 0; d < b->dim; ++d) PetscCall(B200Download_Private(vdm, fv, DMSTAG_ELEMENT, d, 0, 0, 0, b->hv + b->ncell * d));
   for (d = 0; d < b->dim; ++d) PetscCall(B200Download_Private(Sdm, fV, B200FaceLoc[d], 0, d == 0 && !b->per[0], d == 1 && !b->per[1], d == 2 && b->lastz, b->hU[d]));
   PetscCall(B200Download_Private(sdm, fp, DMSTAG_ELEMENT, 0, 0, 0, 0, b->hp));
-  PetscCall(VecScale(f, -1.)); /* FormFunction returns A x - b at x = 0 */
   PetscCall(VecRestoreSubVector(f, vis, &fv));
   PetscCall(VecRestoreSubVector(f, Vis, &fV));
   PetscCall(VecRestoreSubVector(f, pis, &fp));
