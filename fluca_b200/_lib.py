@@ -45,6 +45,7 @@ class Desc(C.Structure):
         ("mg_nu2", C.c_int),
         ("mg_coarse_sweeps", C.c_int),
         ("no_bcg_quirk", C.c_int),
+        ("no_t_outlet_quirk", C.c_int),
     ]
 
 

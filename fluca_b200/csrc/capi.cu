@@ -114,6 +114,7 @@ extern "C" int fluca_b200_create(const fluca_b200_desc *d, fluca_b200_comm *comm
   if (d->mg_nu2 > 0) o.mg_nu2 = d->mg_nu2;
   if (d->mg_coarse_sweeps > 0) o.mg_coarse_sweeps = d->mg_coarse_sweeps;
   o.quirk_bcg_scale = d->no_bcg_quirk ? 0 : 1;
+  o.quirk_t_outlet  = d->no_t_outlet_quirk ? 0 : 1;
   if (o.mode != FLUCA_B200_MODE_COUPLED && o.mode != FLUCA_B200_MODE_FRACTIONAL) throw Error(FL_ERR_ARG, "unknown solve mode");
   fluca_b200_solver *h = new fluca_b200_solver;
   Comm              *c = comm ? comm->c : nullptr;

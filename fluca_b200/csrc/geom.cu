@@ -53,7 +53,7 @@ void ext_hi(const Dir &D, double w[2])
   w[1] = -(h2 * h2) / den;
 }
 
-void build_dir(GeomHost &gh, Exec &ex, Tab &T, const Dir &D, int off, int nloc)
+void build_dir(GeomHost &gh, Exec &ex, Tab &T, const Dir &D, int off, int nloc, bool quirk_t_outlet)
 {
   const int n = D.n;
   memset(&T, 0, sizeof(Tab));
@@ -139,6 +139,13 @@ void build_dir(GeomHost &gh, Exec &ex, Tab &T, const Dir &D, int off, int nloc)
         }
       }
       for (int q = 0; q < 2; ++q) (side ? T.cv2_hi : T.cv2_lo)[q] = (bc == BC_PRESSURE_OUTLET) ? (side ? e_hi[q] : -e_lo[q]) : 0.;
+      // operator T at the wall face.  QUIRK of the reference's 3-D file (kept for parity, fluca_b200_desc.no_t_outlet_quirk): at an
+      // UPPER pressure outlet it extrapolates with the arguments (centre n-1, face n, slot of the partial element n) where the 2-D
+      // file and operator B pass (centre n-2, centre n-1, face n): cnlinearcart3d.c:1996,2055,2114 against cnlinearcart2d.c:1391.
+      // That slot holds x_max + h/2 on a mesh from MeshCartSetUniformCoordinates, so the cells (n-2, n-1) get (-1/3, 4/3) in
+      // cartdiscret.c:406-423 instead of (-1/8, 9/8).  Found by running the reference's compiled sources (oracle/ref_model).
+      for (int q = 0; q < 2; ++q) (side ? T.tn_hi : T.tn_lo)[q] = (side ? T.it_hi : T.it_lo)[1][q];
+      if (quirk_t_outlet && side && bc == BC_PRESSURE_OUTLET) T.tn_hi[0] = -1. / 3., T.tn_hi[1] = 4. / 3.;
       (side ? T.it_hi_bc : T.it_lo_bc) = (bc == BC_VELOCITY) ? 1. : 0.;
 
       // cell-centred pressure gradient of the wall cell, cnlinearcart2d.c:38-79
@@ -189,7 +196,7 @@ void build_dir(GeomHost &gh, Exec &ex, Tab &T, const Dir &D, int off, int nloc)
 
 } // namespace
 
-void geom_build(GeomHost &gh, Exec &ex, int dim, const int n[3], const double *const xf[3], const int bc[6], int rank, int nranks, int k0, int nzl)
+void geom_build(GeomHost &gh, Exec &ex, int dim, const int n[3], const double *const xf[3], const int bc[6], int rank, int nranks, int k0, int nzl, int quirk_t_outlet)
 {
   if (dim != 2 && dim != 3) throw Error(FL_ERR_ARG, "dim must be 2 or 3");
   Geom &g = gh.g;
@@ -221,7 +228,7 @@ void geom_build(GeomHost &gh, Exec &ex, int dim, const int n[3], const double *c
     if ((D.bc_hi == BC_PERIODIC) != (D.bc_lo == BC_PERIODIC)) throw Error(FL_ERR_ARG, "periodic boundary conditions must be set on both sides of a direction");
     D.xf = &gh.xf[d], D.xc = &gh.xc[d];
     D.len = gh.xf[d][n[d]] - gh.xf[d][0];
-    build_dir(gh, ex, g.t[d], D, d == 2 ? g.k0 : 0, d == 2 ? g.nzl : n[d]);
+    build_dir(gh, ex, g.t[d], D, d == 2 ? g.k0 : 0, d == 2 ? g.nzl : n[d], dim == 3 && quirk_t_outlet);
   }
   if (dim == 3 && nranks > 1 && (g.t[2].wall_lo || g.t[2].wall_hi) && g.nzl < 3) throw Error(FL_ERR_ARG, "a slab that touches a z wall needs at least 3 planes");
 }

@@ -47,6 +47,7 @@ struct Tab {
   double gr_bc_lo, gr_bc_hi;         // weight of the outlet pressure
   double it_lo[2][2], it_hi[2][2];   // wall-face value from cells (0,1) / (n-2,n-1)
   double it_lo_bc, it_hi_bc;         // 1 if the wall face takes the prescribed velocity
+  double tn_lo[2], tn_hi[2];         // the same for operator T (normal component): it_*[1] except at a 3-D upper outlet (geom.cu)
   double cv1_lo[2][2], cv1_hi[2][2]; // convection, advected-component interpolation at the wall face
   double cv2_lo[2], cv2_hi[2];       // convection, normal-component interpolation at the wall face
   double gst_lo[2], gst_hi[2];       // outlet face-normal derivative from cells (0,1) / (n-2,n-1)
@@ -86,6 +87,6 @@ struct GeomHost {
 
 // builds tables for a mesh of n[] cells with faces xf[d][0..n[d]], BC types bc[6] (LEFT, RIGHT,
 // DOWN, UP, BACK, FRONT), on slab [k0, k0 + nzl) of rank / nranks
-void geom_build(GeomHost &gh, Exec &ex, int dim, const int n[3], const double *const xf[3], const int bc[6], int rank, int nranks, int k0, int nzl);
+void geom_build(GeomHost &gh, Exec &ex, int dim, const int n[3], const double *const xf[3], const int bc[6], int rank, int nranks, int k0, int nzl, int quirk_t_outlet = 1);
 
 } // namespace fluca

@@ -95,6 +95,7 @@ struct Options {
   int    inner_maxit   = 500;
   int    mg_nu1 = 2, mg_nu2 = 2, mg_coarse_sweeps = 40;
   int    quirk_bcg_scale = 1;
+  int    quirk_t_outlet  = 1; // 3-D: operator T at an upper pressure outlet as cnlinearcart3d.c:1996 forms it (geom.cu)
   // approximation of A^-1 inside the ABF factors: 0 ID (default, abfpc.c:328-329), 1 DIAG, 2 ROWSUM (PCABFAinvType, flucans.h:99-103)
   int    schur_ainv = 0, upper_ainv = 0;
 };

@@ -352,7 +352,7 @@ FL_HD double t_face_lo(const Geom &g, int d, const double *__restrict__ f, const
 {
   const Tab &T  = g.t[d];
   const int  ig = nb.ig[d];
-  if (!T.per && ig == 0) return T.it_lo[1][0] * f[nb.c] + T.it_lo[1][1] * f[nb.p[d]];
+  if (!T.per && ig == 0) return T.tn_lo[0] * f[nb.c] + T.tn_lo[1] * f[nb.p[d]];
   return T.itw[2 * ig] * f[nb.m[d]] + T.itw[2 * ig + 1] * f[nb.c];
 }
 // value at the extra (upper wall) face of the last cell
@@ -360,7 +360,7 @@ template <int DIM>
 FL_HD double t_face_wall_hi(const Geom &g, int d, const double *__restrict__ f, const Nbr<DIM> &nb)
 {
   const Tab &T = g.t[d];
-  return T.it_hi[1][0] * f[nb.m[d]] + T.it_hi[1][1] * f[nb.c];
+  return T.tn_hi[0] * f[nb.m[d]] + T.tn_hi[1] * f[nb.c];
 }
 // unscaled face-normal pressure derivative (Gst0 p) at the lower face / extra upper wall face
 template <int DIM>

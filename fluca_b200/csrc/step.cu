@@ -188,7 +188,7 @@ void solver_setup(Solver &s, int dim, const int n[3], const double *const xf[3],
   s.comm.reset(comm ? comm : new LocalComm());
   int bc[6];
   for (int b = 0; b < 6; ++b) bc[b] = (b < 2 * dim) ? bcin[b] : BC_NONE;
-  geom_build(s.gh, s.ex, dim, n, xf, bc, s.comm->rank, s.comm->nranks, k0, nzl);
+  geom_build(s.gh, s.ex, dim, n, xf, bc, s.comm->rank, s.comm->nranks, k0, nzl, opt.quirk_t_outlet);
   const Geom &g = s.gh.g;
   s.has_outlet = false;
   for (int b = 0; b < 2 * dim; ++b)
@@ -397,11 +397,11 @@ static void build_rhs(Solver &s)
         const int    n  = TT.n;
         if (!side) {
           const double g0 = dtrho * TT.gr_bc_lo * dl; // the only non-zero entry of dt/rho (bcG_q - bcG_h), at cell 0
-          rid[nb.c] += -TT.it_lo[1][0] * g0 + dtrho * TT.gst_bc_lo * dl;
+          rid[nb.c] += -TT.tn_lo[0] * g0 + dtrho * TT.gst_bc_lo * dl;
           rid[nb.p[d]] += -TT.itw[2 * 1 + 0] * g0; // face 1 interpolates cells (0, 1)
         } else {
           const double g0 = dtrho * TT.gr_bc_hi * dl;
-          rid[nb.fu[d]] += -TT.it_hi[1][1] * g0 + dtrho * TT.gst_bc_hi * dl;
+          rid[nb.fu[d]] += -TT.tn_hi[1] * g0 + dtrho * TT.gst_bc_hi * dl;
           rid[nb.c] += -TT.itw[2 * (n - 1) + 1] * g0; // face n-1 interpolates cells (n-2, n-1)
         }
       });

@@ -68,6 +68,9 @@ typedef struct {
   int    mg_nu1, mg_nu2;  /* [2, 2]  Jacobi pre / post sweeps of the pressure V-cycle */
   int    mg_coarse_sweeps; /* [40] */
   int    no_bcg_quirk;    /* 0: 3-D scales the outlet-gradient BC vector by 1 as cnlinearcart3d.c:2977 does; 1: by dt/rho */
+  int    no_t_outlet_quirk; /* 0: 3-D forms operator T at an UPPER pressure outlet as cnlinearcart3d.c:1996,2055,2114 do (cell weights
+                               -1/3, 4/3: the wall coordinate is read from the slot of the partial element); 1: as cnlinearcart2d.c:1391
+                               and operator B do (-1/8, 9/8 on a uniform mesh) */
 } fluca_b200_desc;
 
 typedef struct {

@@ -72,6 +72,9 @@ void orc_default_options(OrcOptions *o);
 
 /* n[d] cells, periodic[d] flags, xf[d] = n[d]+1 face coordinates (centres are face midpoints,
  * cart.c:497).  bcs ordered LEFT,RIGHT,DOWN,UP,BACK,FRONT (cart.c:564-591). */
+/* 1 (default): objects created from now on form the 3-D upper-outlet rows of T as cnlinearcart3d.c:1996,2055,2114 do (weights
+   -1/3, 4/3); 0: as the 2-D file does (-1/8, 9/8 on a uniform mesh).  See interp_row in src/ns.c. */
+void orc_set_t_outlet_quirk(int on);
 Orc *orc_create(int dim, const int n[3], const int periodic[3], const double *const xf[3], double rho, double mu, double dt, const OrcBC bcs[6]);
 void orc_destroy(Orc *o);
 

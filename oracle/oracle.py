@@ -101,11 +101,17 @@ def lib():
         L.orc_ibm_interpolate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_ibm_spread.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_get_marker_forces.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_set_t_outlet_quirk.argtypes = [C.c_int]
         L.orc_set_threads.argtypes = [C.c_int]
         L.orc_set_threads.restype = C.c_int
         L.orc_get_threads.restype = C.c_int
         _lib = L
     return _lib
+
+
+def set_t_outlet_quirk(on: bool) -> None:
+    """Objects created from now on form the 3-D upper-outlet rows of T as cnlinearcart3d.c:1996 does (default) or as the 2-D file does."""
+    lib().orc_set_t_outlet_quirk(1 if on else 0)
 
 
 def set_threads(n: int) -> int:

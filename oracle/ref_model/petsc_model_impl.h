@@ -1,0 +1,82 @@
+/* oracle/ref_model/petsc_model_impl.h -- TEST INFRASTRUCTURE ONLY: the object layouts of the PETSc model (petsc_model.c) and the
+ * helpers ref_driver.c uses to reach into them.  The reference's sources never see this header (they include petsc_model.h only). */
+#ifndef PETSC_MODEL_IMPL_H
+#define PETSC_MODEL_IMPL_H
+#include <petsc_model.h>
+
+#define MODEL_GARBAGE (-777) /* what arguments documented as "ignored in lower dimensions" come back as */
+
+struct _p_ISLocalToGlobalMapping {
+  int  n;
+  int *idx; /* local entry -> global entry; -1 for entries that do not exist in a partial element */
+};
+struct _p_IS {
+  struct _p_PetscObject hdr;
+  int                   field; /* the field of the solution nest this index set selects */
+  PetscInt              n;     /* its number of entries */
+};
+struct _p_Vec {
+  struct _p_PetscObject hdr;
+  DM                    dm;
+  int                   local;
+  PetscInt              n;
+  double               *a;
+  int                   nsub;
+  Vec                   sub[3];
+  void                 *table[3];
+  int                   array_out;
+};
+struct _p_MatNullSpace {
+  int       refct;
+  PetscBool has_cnst;
+  Vec       vec;
+};
+struct _p_Mat {
+  struct _p_PetscObject  hdr;
+  PetscInt               m, n;
+  int                   *rn, *rcap, **rc;
+  double               **rv;
+  ISLocalToGlobalMapping rl2g, cl2g;
+  int                    nest, assembled;
+  Mat                    blk[3][3];
+  IS                     isr[3], isc[3];
+  MatNullSpace           nullspace;
+};
+struct _p_KSP {
+  struct _p_PetscObject hdr;
+  Mat                   A;
+  long                  nsolves;
+};
+struct _p_SNES {
+  struct _p_PetscObject hdr;
+  void                 *ctx;
+  PetscErrorCode (*solve)(SNES, Vec, Vec);
+};
+struct _p_PetscViewer {
+  struct _p_PetscObject hdr;
+  FILE                 *f;
+};
+#define MODEL_MAXLOC 8
+struct _p_DM {
+  struct _p_PetscObject            hdr;
+  int                              dim, N[3], per[3], dof[4], epe, gs[3], gn[3], on[3], nloc;
+  DMStagStencilLocation            loc[MODEL_MAXLOC];
+  int                              locmask[MODEL_MAXLOC], locoff[MODEL_MAXLOC], locdof[MODEL_MAXLOC];
+  int                              nglobal, nlocal;
+  struct _p_ISLocalToGlobalMapping l2g;
+  double                         **ctab; /* [dim]: pointer tables of the 1-D product coordinates (owned by the mesh) */
+};
+
+const char *ModelLastError(void);
+void        ModelHeaderInit(void *obj, PetscClassId, const char *cls, const char *type, PetscErrorCode (*destroy)(PetscObject));
+void        ModelHeaderFree(void *obj);
+Vec         ModelVecCreate(DM dm, int local, PetscInt n);
+Vec         ModelVecCreateNest(int nsub, Vec sub[]);
+void        ModelVecGather(Vec, double *);
+void        ModelVecScatter(Vec, const double *);
+Mat         ModelMatCreateAIJ(PetscInt m, PetscInt n);
+double     *ModelMatEntry(Mat, int i, int j, int create);
+double      ModelDenseSolve(int n, double *a, double *b);
+DM          ModelDMStagCreate(int dim, const int N[3], const int per[3], int d0, int d1, int d2, int d3, double **ctab);
+void        ModelDMDestroy(DM);
+#endif

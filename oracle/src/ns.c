@@ -336,6 +336,7 @@ struct Orc {
   double  rho, mu, dt;
   OrcBC   bcs[6];
   int     has_outlet; /* nsbasic.c:215-244: no null space if any boundary is an outlet */
+  int     quirk_t_outlet; /* interp_row: the 3-D upper-outlet rows of T as cnlinearcart3d.c:1996 forms them */
 
   /* state */
   double *v, *U, *p, *phalf;
@@ -721,7 +722,17 @@ static St interp_row(const Orc *g, int c, int d, int f, int full)
   } else if (f == n) {
     switch (g->bcs[2 * d + 1].type) {
     case ORC_BC_VELOCITY: return st_none();
-    case ORC_BC_PRESSURE_OUTLET: return lin_bwd_extrap(XC(g, d, f - 2), XC(g, d, f - 1), XF(g, d, f));
+    case ORC_BC_PRESSURE_OUTLET:
+      /* QUIRK of the reference's 3-D file, found by running its compiled sources (oracle/ref_model): operator T at an upper
+         pressure outlet passes (centre n-1, face n, "centre" of the partial element n) where the 2-D file and operator B pass
+         (centre n-2, centre n-1, face n) -- cnlinearcart3d.c:1996,2055,2114 against cnlinearcart2d.c:1391 and
+         cnlinearcart3d.c:1581.  The slot of the partial element holds x_max + h/2 on a mesh built by
+         MeshCartSetUniformCoordinates (DMStagSetUniformCoordinatesProduct fills every local element), so the weights of the
+         cells (n-2, n-1) come out as (-1/3, 4/3) instead of (-1/8, 9/8); the stencil columns are unchanged.  On loaded
+         non-uniform coordinates the reference reads a stale value there (cart.c:137-143); the mirror image of the last centre
+         is used, which reduces to the uniform case.  Kept for parity; orc_set_t_outlet_quirk(0) gives the 2-D form. */
+      if (!full && g->dim == 3 && g->quirk_t_outlet) return lin_bwd_extrap(XC(g, d, f - 1), XF(g, d, f), 2. * XF(g, d, f) - XC(g, d, f - 1));
+      return lin_bwd_extrap(XC(g, d, f - 2), XC(g, d, f - 1), XF(g, d, f));
     case ORC_BC_SYMMETRY:
       if (full && c != d) return lin_bwd_extrap(XC(g, d, f - 2), XC(g, d, f - 1), XF(g, d, f));
       return st_none();
@@ -899,10 +910,15 @@ void orc_default_options(OrcOptions *o)
   o->quirk_bcg_scale = 1;
 }
 
+/* process-wide default of the quirk for objects created afterwards (the constant operators are assembled in orc_create) */
+static int default_quirk_t_outlet = 1;
+void orc_set_t_outlet_quirk(int on) { default_quirk_t_outlet = on ? 1 : 0; }
+
 Orc *orc_create(int dim, const int n[3], const int periodic[3], const double *const xf[3], double rho, double mu, double dt, const OrcBC bcs[6])
 {
   Orc *g = (Orc *)calloc(1, sizeof(Orc));
   g->dim = dim;
+  g->quirk_t_outlet = default_quirk_t_outlet;
   g->rho = rho, g->mu = mu, g->dt = dt;
   for (int d = 0; d < 3; ++d) {
     g->n[d]   = d < dim ? n[d] : 1;

@@ -1,0 +1,201 @@
+"""The oracle -- and the product -- against the REFERENCE's own Navier-Stokes code.
+
+oracle/_ref/libfluca_ref_ns.so is thecasterian/fluca's cartdiscret.c, cnlinear.c, cnlinearcart2d.c, cnlinearcart3d.c and abfpc.c,
+compiled from /root/reference on a single-rank model of the PETSc API subset they use (oracle/ref_model/; `make -C oracle ref`).
+Its outputs on eleven small cases are committed as tests/golden/ns_reference.npz (tests/golden/make_ns_reference_golden.py).
+
+  everywhere      the oracle reproduces the reference's right-hand side, ABF application, state after two steps in both solve modes
+                  and the outer GMRES residual history; the product sources (host emulation) reproduce the states
+  -m gpu          the CUDA library reproduces the states
+  where the reference tree or the built library is present (this container; the .so also travels to the GPU box)
+                  live comparison: every assembled operator of the oracle equals the reference's entry for entry (explicit zeros
+                  included), on more cases and sizes than the fixtures hold
+
+What this pins and what it cannot: the discretisation (every stencil, boundary row and boundary vector), the Crank-Nicolson
+right-hand side, the ABF factors, the solution update and pressure extrapolation are the reference's compiled code.  PETSc's own
+arithmetic -- GMRES / ILU(0) iteration histories of the inner solves -- is not, because PETSc is absent: inner solves are exact."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+import fluca_b200 as fb
+from oracle import oracle as O
+from oracle import ref as R
+from tests import cases, parity
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = np.load(os.path.join(HERE, "golden", "ns_reference.npz"))
+_spec = importlib.util.spec_from_file_location("make_ns_reference_golden", os.path.join(HERE, "golden", "make_ns_reference_golden.py"))
+_gen = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(_gen)
+FIX = _gen.fixtures()
+NAMES = list(FIX)
+
+
+def _inputs(name, dim):
+    return G[f"{name}/in_v"], [G[f"{name}/in_U{d}"] for d in range(dim)], G[f"{name}/in_p"]
+
+
+def _assert_state(got, name, tag, dim, tol=1e-10):
+    k = f"{name}/{tag}"
+    err = dict(v=parity.rel(got["v"], G[f"{k}/v"]), U=parity.relU(got["U"], [G[f"{k}/U{d}"] for d in range(dim)]), p=parity.rel(got["p"], G[f"{k}/p"]), phalf=parity.rel(got["phalf"], G[f"{k}/phalf"]))
+    assert err["v"] <= tol and err["U"] <= tol and err["p"] <= 10 * tol and err["phalf"] <= 10 * tol, (name, tag, err)
+
+
+# ------------------------------------------------------------------ the oracle against the committed reference outputs
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_reproduces_the_reference(name):
+    case, seed, ainv = FIX[name]
+    state = case.initial_state(seed=seed)
+    assert np.array_equal(state[0], G[f"{name}/in_v"])
+    for mode, tag in ((0, "coupled"), (1, "fractional")):
+        orc = cases.make_oracle(case)
+        orc.set_state(*state)
+        opt = O.default_options(mode=mode, schur_ainv=ainv[0], upper_ainv=ainv[1], **parity.ORC_TIGHT)
+        if tag == "coupled":
+            rhs = orc.prepare_step(opt)  # NSFormFunction: b before the null space is removed ...
+            if not any(bc["type"] == cases.BC_PRESSURE_OUTLET for bc in case.bcs):
+                ref = G[f"{name}/rhs"].copy()  # ... the oracle hands it out with the mean of the continuity block removed
+                ref[-orc.ncell :] -= ref[-orc.ncell :].mean()
+            else:
+                ref = G[f"{name}/rhs"]
+            assert parity.rel(rhs, ref) <= 1e-12, name
+        infos = [orc.step(opt) for _ in range(2)]
+        _assert_state(orc.get_state(), name, tag, case.dim)
+    # one application of PCABF with the operators of step 0
+    orc = cases.make_oracle(case)
+    orc.set_state(*state)
+    opt = O.default_options(mode=0, schur_ainv=ainv[0], upper_ainv=ainv[1], **parity.ORC_TIGHT)
+    orc.prepare_step(opt)
+    x, _ = orc.abf_apply(G[f"{name}/abf_in"], opt)
+    assert parity.rel(x, G[f"{name}/abf_out"]) <= 1e-9, name
+    # the outer Krylov history: right-preconditioned GMRES + PCABF with converged inner solves depends on (J, PCABF, b) only
+    orc = cases.make_oracle(case)
+    orc.set_state(*state)
+    info = orc.step(O.default_options(mode=0, schur_ainv=ainv[0], upper_ainv=ainv[1], outer_rtol=1e-12, mom_rtol=1e-14, schur_rtol=1e-14))
+    hist_ref, hist = G[f"{name}/gmres_hist"], [info.hist[i] for i in range(info.nhist)]
+    assert abs(len(hist) - len(hist_ref)) <= 1, (len(hist), len(hist_ref))
+    for a, b in list(zip(hist, hist_ref))[: min(len(hist), len(hist_ref), 8)]:
+        assert a == pytest.approx(b, rel=1e-6, abs=1e-11 * hist_ref[0]), (name, hist[:8], hist_ref[:8])
+    del infos
+
+
+# ------------------------------------------------------------------ the product against the committed reference outputs
+def _product_matches(lib, name, mode):
+    case, seed, ainv = FIX[name]
+    ns = parity.make_ns(case, lib, mode, ns_pc_abf_schur_ainv_type=parity.AINV_OPTION[ainv[0]], ns_pc_abf_upper_ainv_type=parity.AINV_OPTION[ainv[1]], **parity.TIGHT)
+    parity.set_initial(ns, _inputs(name, case.dim))
+    for _ in range(2):
+        fb.NSStep(ns)
+    _assert_state(fb.NSB200GetSolver(ns).get_state(), name, mode, case.dim)
+    fb.NSDestroy(ns)
+
+
+@pytest.mark.parametrize("mode", ["coupled", "fractional"])
+@pytest.mark.parametrize("name", NAMES)
+def test_product_sources_reproduce_the_reference(name, mode):
+    _product_matches(parity.hostemu_library(), name, mode)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["coupled", "fractional"])
+@pytest.mark.parametrize("name", NAMES)
+def test_cuda_library_reproduces_the_reference(name, mode):
+    L = fb._lib.load()
+    assert L.fluca_b200_is_host_emulation() == 0
+    _product_matches(L, name, mode)
+
+
+# ------------------------------------------------------------------ live: the compiled reference next to the oracle
+def _have_reference():
+    try:
+        return R.available()
+    except Exception:
+        return False
+
+
+needs_reference = pytest.mark.skipif(not _have_reference(), reason="oracle/_ref/libfluca_ref_ns.so is not here (it is built from /root/reference)")
+
+
+def _live_cases():
+    big = cases.cavity2d(n=20)
+    big.stretch = 0.3
+    c3 = cases.channel3d(n=(10, 6, 6), pout=0.4)
+    c3.stretch = 0.1
+    full = cases.cavity3d_full(n=(6, 6, 6))
+    return {
+        "cavity2d_20_stretched": (big, 21),
+        "channel2d_16x10": (cases.channel2d(n=(16, 10), pout=0.1), 22),
+        "tgv_periodic_12": (cases.tgv(n=12, periodic=True), None),
+        "cavity3d_full_6": (full, 23),
+        "channel3d_10x6x6_stretched": (c3, 24),
+        "channel3d_periodic_z_10x6x4": (cases.channel3d(n=(10, 6, 4), periodic_z=True), 25),
+    }
+
+
+@needs_reference
+@pytest.mark.parametrize("name", list(_live_cases()))
+def test_every_operator_equals_the_references(name):
+    """G, L, -T, -R = (-T) G + Gst, D, Gst and A = I + dt C - (nu dt / 2) L of the oracle against the matrices the reference's
+    assembly loops produce (cnlinearcart2d.c / cnlinearcart3d.c), entry for entry, explicitly stored zeros included."""
+    case, seed = _live_cases()[name]
+    state = case.initial_state(seed=seed)
+    ref, orc = _gen.make_reference(case), cases.make_oracle(case)
+    ref.set_state(*state)
+    orc.set_state(*state)
+    ref.step(mode=R.ABF_ONCE)  # forms J of step 0 (the cheap solve)
+    orc.prepare_step()
+    for mat in ("G", "L", "negT", "negR", "D", "Gst", "A"):
+        a, b = ref.matrix(mat).tocsr(), orc.matrix(mat).tocsr()
+        a.sort_indices(), b.sort_indices()
+        assert a.shape == b.shape and a.nnz == b.nnz, (mat, a.shape, b.shape, a.nnz, b.nnz)
+        assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices), mat  # the same stored pattern
+        assert np.abs(a.data - b.data).max() <= 1e-13 * np.abs(b.data).max(), (mat, np.abs(a.data - b.data).max())
+    assert parity.rel(ref.last_rhs(), orc.prepare_step()) <= 1e-12
+    ident = ref.matrix("I").tocsr()
+    assert (ident != __import__("scipy.sparse", fromlist=["identity"]).identity(ident.shape[0], format="csr")).nnz == 0
+
+
+@needs_reference
+@pytest.mark.parametrize("name", list(_live_cases()))
+def test_steps_equal_the_references(name):
+    case, seed = _live_cases()[name]
+    state = case.initial_state(seed=seed)
+    for rmode, omode in ((R.ABF_ONCE, 1), (R.EXACT, 0)):
+        if rmode == R.EXACT and np.prod(case.n) > 300:
+            continue  # the dense coupled solve is for the small fixtures
+        ref, orc = _gen.make_reference(case), cases.make_oracle(case)
+        ref.set_state(*state)
+        orc.set_state(*state)
+        opt = O.default_options(mode=omode, **parity.ORC_TIGHT)
+        for _ in range(3):
+            ref.step(mode=rmode)
+            orc.step(opt)
+        a, b = orc.get_state(), ref.get_state()
+        assert parity.rel(a["v"], b["v"]) <= 1e-10 and parity.relU(a["U"], b["U"]) <= 1e-10 and parity.rel(a["p"], b["p"]) <= 1e-9 and parity.rel(a["phalf"], b["phalf"]) <= 1e-9, name
+
+
+@needs_reference
+def test_the_upper_outlet_quirk_of_the_3d_file_is_what_the_reference_does():
+    """cnlinearcart3d.c:1996,2055,2114: operator T at an upper pressure outlet reads the slot of the partial element.  With the quirk
+    the oracle's T equals the reference's; without it (the 2-D form) it does not -- and in 2-D there is no difference at all."""
+    case = cases.channel3d(n=(6, 5, 4), pout=0.2)
+    ref = _gen.make_reference(case)
+    ref.set_state(*case.initial_state(seed=1))
+    ref.step(mode=R.ABF_ONCE)
+    T_ref = ref.matrix("negT")
+    try:
+        O.set_t_outlet_quirk(False)
+        plain = cases.make_oracle(case).matrix("negT")
+    finally:
+        O.set_t_outlet_quirk(True)
+    quirk = cases.make_oracle(case).matrix("negT")
+    assert abs(T_ref - quirk).max() <= 1e-14 and abs(T_ref - plain).max() > 0.1
+    diff = (T_ref - plain).tocoo()
+    rows = np.unique(diff.row[np.abs(diff.data) > 1e-12])
+    nfx = ref.nface[0]
+    assert len(rows) == case.n[1] * case.n[2] and rows.max() < nfx  # exactly the faces of the RIGHT boundary
+    w = -T_ref.tocsr()[rows[0]].data
+    assert sorted(np.round(w, 12)) == sorted(np.round([-1.0 / 3.0, 4.0 / 3.0], 12))
