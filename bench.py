@@ -157,12 +157,15 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------- CPU arm
 def reference_build_probe():
-    """a PETSc build of the reference may be provided on the GPU box; it never was."""
+    """a PETSc build of the reference may be provided on the GPU box; it never was.  oracle/_ref holds the
+    reference's NS sources compiled on a PETSc MODEL with dense solves: the checker of the oracle, not a timing baseline."""
     petsc = os.environ.get("PETSC_DIR")
-    ref = os.path.isdir(os.path.join(ROOT, "baseline", "_ref")) or os.path.isdir(os.path.join(ROOT, "oracle", "_ref"))
+    ref = os.path.isdir(os.path.join(ROOT, "baseline", "_ref"))
+    model = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libfluca_ref_ns.so"))
+    note = "; oracle/_ref = the reference's NS sources on a PETSc model (parity checker with dense solves, not timed)" if model else ""
     if petsc or ref:
-        return f"present (PETSC_DIR={petsc!r}, _ref dir={ref}) but not used: no build recipe for the reference exists in this repo (it needs MPI, HDF5 and parallel CGNS as well)"
-    return "absent (no $PETSC_DIR, no baseline/_ref, no oracle/_ref): the reference needs PETSc >= 3.23 + MPI + HDF5 + CGNS; the CPU arm is the repo's C restatement (oracle/, kind 'port')"
+        return f"present (PETSC_DIR={petsc!r}, baseline/_ref={ref}) but not used: no build recipe for the reference exists in this repo (it needs MPI, HDF5 and parallel CGNS as well)" + note
+    return "absent (no $PETSC_DIR, no baseline/_ref): the reference needs PETSc >= 3.23 + MPI + HDF5 + CGNS; the CPU arm is the repo's C restatement (oracle/, kind 'port')" + note
 
 
 def cpu_sample(args, n, steps, warmup, mode):
@@ -378,7 +381,7 @@ def parity_selfcheck(ctx, lib):
         ok = ok and e["v"] <= tol and e["U"] <= tol and e["p"] <= 10 * tol
         res[label] = e
     note("parity case: oracle side done")
-    return {"ok": bool(ok), "ranks": world, "tolerance": "rel. L2 <= 1e-10 (v, U), 1e-9 (p) against the CPU oracle at tight tolerances", "case": f"sphere workload builder at {nx}x{ny}x{nz} (inflow/outlet/symmetry, 300 IBM markers), coupled mode, {world} z-slab(s) over {'NCCL' if world > 1 else 'one GPU'}; ABF factor variants schur/upper", "runs": res, "oracle": "parity unpinned: the oracle is this repo's restatement (DESIGN.md 2)"}
+    return {"ok": bool(ok), "ranks": world, "tolerance": "rel. L2 <= 1e-10 (v, U), 1e-9 (p) against the CPU oracle at tight tolerances", "case": f"sphere workload builder at {nx}x{ny}x{nz} (inflow/outlet/symmetry, 300 IBM markers), coupled mode, {world} z-slab(s) over {'NCCL' if world > 1 else 'one GPU'}; ABF factor variants schur/upper", "runs": res, "oracle": "this repo's restatement, pinned to the reference's own NS sources compiled on a PETSc model (operators, RHS, ABF, steps: tests/test_oracle_vs_reference.py); PETSc's solver arithmetic and the IBM section are unpinned (DESIGN.md 2)"}
 
 
 def e2e_resident_loop(ns, solver, ksteps, barrier, clock):

@@ -12,11 +12,17 @@
  * unpinned: fluca/CMakeLists.txt:9-11) -- MatMult, MatMatMult, GMRES(30), ILU(0)/block-Jacobi --
  * is restated in oracle/src/sparse.c from the published algorithms.
  *
- * PARITY STATUS: *parity unpinned* for the NS step itself.  The reference registers no NS test
- * and stores no NS golden output, and it cannot be built here (needs PETSc, MPI,
- * HDF5, CGNS).  What IS pinned: the stencil coefficients, against the reference's own fd golden
- * outputs (tests/golden/fd_coefficients.json, extracted from fluca/tests/fd/output/ *.out), and
- * the Taylor-Green analytic solution of fluca/tests/taylor_green_vortex.
+ * PARITY STATUS: PINNED to the reference's own code for everything the reference computes itself, UNPINNED for what it
+ * delegates to PETSc.  The reference registers no NS test and stores no NS golden output and cannot be built as a
+ * whole here (needs PETSc, MPI, HDF5, CGNS) -- but its NS sources (cartdiscret.c, cnlinear.c, cnlinearcart2d.c, cnlinearcart3d.c,
+ * abfpc.c) compile, from where they lie under /root/reference, against a single-rank model of the PETSc API subset they use
+ * (oracle/ref_model/, `make -C oracle ref` -> oracle/_ref/libfluca_ref_ns.so).  tests/test_oracle_vs_reference.py: every assembled
+ * operator of this oracle equals the reference's entry for entry (stored zeros included), and right-hand side, PCABF application
+ * (ID / DIAG / ROWSUM), the state after K steps in both solve modes and the outer GMRES residual history agree to round-off on 2-D
+ * and 3-D cases with every boundary type, uniform and stretched; the reference's outputs are committed as
+ * tests/golden/ns_reference.npz.  Also pinned: the stencil coefficients against the reference's fd golden outputs
+ * (tests/golden/fd_coefficients.json) and the Taylor-Green analytic solution.  NOT pinned: PETSc's own arithmetic (inner GMRES /
+ * ILU(0) iteration histories; the model's solves are exact) and the immersed-boundary section (the reference has no IBM code).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * use this library.  The product path (fluca_b200/) never links or loads it.

@@ -2,9 +2,9 @@
 
 TEST INFRASTRUCTURE, NOT PRODUCT CODE: only tests/, __graft_entry__.smoke() and the
 cpu_baseline / --impl reference legs of bench.py import this module.  The product package
-(fluca_b200/) never does.  Parity status of the oracle: *parity unpinned* for the NS step (the
-reference stores no NS golden output and cannot be built here); stencil coefficients are pinned
-against the reference's fd goldens (tests/golden/fd_coefficients.json).
+(fluca_b200/) never does.  Parity status of the oracle (oracle/fluca_oracle.h): PINNED to the reference's own NS sources compiled
+on a PETSc model (oracle/ref.py, tests/test_oracle_vs_reference.py) for the discretisation, right-hand side, ABF factors and the
+step; UNPINNED for PETSc's solver arithmetic (absent from the image) and for the immersed-boundary section (no reference code).
 """
 from __future__ import annotations
 

@@ -7,8 +7,9 @@
  * (impl/linearcn/cnlinearcart2d.c, cnlinearcart3d.c); here each operator is written once,
  * looped over the direction d and the (lower, upper) side, which is the same arithmetic.
  *
- * PARITY STATUS: parity unpinned for the NS step (no reference NS golden output exists; the
- * reference cannot be built here).  Coefficients are pinned by tests/golden/fd_coefficients.json.
+ * PARITY STATUS (details in ../fluca_oracle.h): pinned to the reference's own NS sources compiled on a PETSc model (oracle/ref_model,
+ * tests/test_oracle_vs_reference.py: operators entry for entry, RHS, ABF, K steps, outer histories); PETSc's solver arithmetic and
+ * the immersed-boundary section are unpinned.
  */
 #include "../fluca_oracle.h"
 #include "sparse.h"

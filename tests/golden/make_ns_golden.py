@@ -4,7 +4,8 @@ The reference stores no NS golden output and cannot be built in this image (SURV
 prescribes -- the oracle itself produces the fixtures: seeded inputs, exact (tight-tolerance, mode A = coupled solve and mode
 B = one ABF application) outputs after two steps, plus one operator-level tier (right-hand side of the first step).  They
 pin the oracle against accidental change and give the product tests a comparison that needs no oracle at run time.
-PARITY STATUS: unpinned with respect to the reference itself; see oracle/fluca_oracle.h.
+PARITY STATUS: these are the ORACLE's outputs (incl. the IBM case, which has no reference); the fixtures computed by the reference's
+own compiled sources are tests/golden/ns_reference.npz (make_ns_reference_golden.py).  See oracle/fluca_oracle.h.
 
     python tests/golden/make_ns_golden.py          # rewrites tests/golden/ns_steps.npz
 """

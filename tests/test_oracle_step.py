@@ -1,4 +1,5 @@
-"""Self-consistency of the oracle's NS step (the reference stores no NS golden: parity unpinned).
+"""Self-consistency of the oracle's NS step (the reference stores no NS golden; the pin against the reference's compiled sources is
+tests/test_oracle_vs_reference.py).
 
 What is checked instead:
   * the oracle's Krylov result equals a sparse-direct (SciPy SuperLU) solve of the very same
