@@ -181,6 +181,21 @@ PetscErrorCode PetscInfoModel(void *, const char *, ...);
 #define PetscLogEventEnd(e, a, b, c, d) PETSC_SUCCESS
 #define PetscArraycpy(a, b, n) (memcpy((a), (b), (size_t)(n) * sizeof(*(a))), PETSC_SUCCESS)
 
+PetscErrorCode PetscPrintf(MPI_Comm, const char[], ...);
+#define PetscArraycmp(a, b, n, e) (*(e) = memcmp((a), (b), (size_t)(n) * sizeof(*(a))) ? PETSC_FALSE : PETSC_TRUE, PETSC_SUCCESS)
+/* MPI: one rank */
+typedef int MPI_Datatype;
+typedef int MPI_Op;
+#define MPI_IN_PLACE ((void *)1)
+#define MPI_DOUBLE 1
+#define MPI_INT 2
+#define MPI_BYTE 3
+#define MPI_SUM 1
+int MPI_Comm_rank(MPI_Comm, int *);
+int MPI_Comm_size(MPI_Comm, int *);
+int MPI_Bcast(void *, int, MPI_Datatype, int, MPI_Comm);
+int MPI_Allreduce(const void *, void *, int, MPI_Datatype, MPI_Op, MPI_Comm);
+
 /* options: the type implementations only declare theirs; values are set through the API by ref_driver.c */
 #define PetscOptionsHeadBegin(obj, head) (void)(obj)
 #define PetscOptionsHeadEnd()

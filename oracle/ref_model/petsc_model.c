@@ -62,6 +62,24 @@ PetscErrorCode PetscStrallocpy(const char s[], char **t)
   return PETSC_SUCCESS;
 }
 PetscErrorCode PetscInfoModel(void *o, const char *fmt, ...) { return (void)o, (void)fmt, PETSC_SUCCESS; }
+PetscErrorCode PetscPrintf(MPI_Comm c, const char fmt[], ...)
+{
+  va_list ap;
+  (void)c;
+  va_start(ap, fmt);
+  vfprintf(stdout, fmt, ap);
+  va_end(ap);
+  return PETSC_SUCCESS;
+}
+int MPI_Comm_rank(MPI_Comm c, int *r) { return (void)c, *r = 0, 0; }
+int MPI_Comm_size(MPI_Comm c, int *s) { return (void)c, *s = 1, 0; }
+int MPI_Bcast(void *b, int n, MPI_Datatype t, int root, MPI_Comm c) { return (void)b, (void)n, (void)t, (void)root, (void)c, 0; }
+int MPI_Allreduce(const void *s, void *r, int n, MPI_Datatype t, MPI_Op op, MPI_Comm c)
+{
+  (void)op, (void)c;
+  if (s != MPI_IN_PLACE) memcpy(r, s, (size_t)n * (t == MPI_DOUBLE ? sizeof(double) : t == MPI_INT ? sizeof(int) : 1));
+  return 0;
+}
 
 /* ------------------------------------------------------------------ PetscObject */
 struct composed_object {

@@ -38,6 +38,21 @@ def test_matrix_free_patch_applies_to_the_reference(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
 
 
+def test_glue_compiles_against_the_references_own_headers():
+    """Where the reference tree is present: glue/nsb200.c against the reference's REAL Fluca headers (fluca/include: nsimpl.h with
+    struct _p_NS, flucans.h, flucameshcart.h, flucansbc.h, flucaviewer.h) -- only the PETSc headers underneath come from the model of
+    oracle/ref_model/.  Every Fluca function the glue calls is thereby checked against the declaration the reference itself compiles with."""
+    import pytest
+
+    ref = "/root/reference/fluca/include"
+    if not os.path.isdir(ref):
+        pytest.skip("the reference tree is not on this machine")
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    for extra in ([], ["-DFLUCA_NS_HAS_MATRIXFREE_CHECK_ONLY"]):
+        r = subprocess.run([cc, "-std=gnu11", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-Wno-unused-parameter", "-Wno-unused-variable", "-I", os.path.join(ROOT, "oracle", "ref_model", "include"), "-I", ref, "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "glue", "nsb200.c")] + extra, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
 def test_glue_fills_every_ns_op_and_registers_the_type():
     src = open(os.path.join(ROOT, "glue", "nsb200.c")).read()
     for op in ("setfromoptions", "setup", "step", "formjacobian", "formfunction", "destroy", "view", "viewsolution", "loadsolution"):  # nsimpl.h:21-31
