@@ -177,8 +177,9 @@ PetscErrorCode PetscStrcmp(const char[], const char[], PetscBool *);
 PetscErrorCode PetscStrallocpy(const char[], char **);
 PetscErrorCode PetscInfoModel(void *, const char *, ...);
 #define PetscInfo(obj, ...) PetscInfoModel((void *)(obj), __VA_ARGS__)
-#define PetscLogEventBegin(e, a, b, c, d) PETSC_SUCCESS
-#define PetscLogEventEnd(e, a, b, c, d) PETSC_SUCCESS
+static inline PetscErrorCode ModelLogNoop(void) { return PETSC_SUCCESS; }
+#define PetscLogEventBegin(e, a, b, c, d) ModelLogNoop()
+#define PetscLogEventEnd(e, a, b, c, d) ModelLogNoop()
 #define PetscArraycpy(a, b, n) (memcpy((a), (b), (size_t)(n) * sizeof(*(a))), PETSC_SUCCESS)
 
 PetscErrorCode PetscPrintf(MPI_Comm, const char[], ...);
@@ -196,13 +197,80 @@ int MPI_Comm_size(MPI_Comm, int *);
 int MPI_Bcast(void *, int, MPI_Datatype, int, MPI_Comm);
 int MPI_Allreduce(const void *, void *, int, MPI_Datatype, MPI_Op, MPI_Comm);
 
-/* options: the type implementations only declare theirs; values are set through the API by ref_driver.c */
+/* options database (filled from argv by PetscInitialize, or by ModelOptionsSetValue) */
+PetscErrorCode ModelOptionsSetValue(const char name[], const char value[]);
+PetscErrorCode ModelOptionsClear(void);
+PetscErrorCode ModelOptionsReal(const char name[], PetscReal *val, PetscBool *set);
+PetscErrorCode ModelOptionsInt(const char name[], PetscInt *val, PetscBool *set);
+PetscErrorCode ModelOptionsBool(const char name[], PetscBool *val, PetscBool *set);
+PetscErrorCode ModelOptionsString(const char name[], char *val, size_t len, PetscBool *set);
+PetscErrorCode ModelOptionsEnum(const char name[], const char *const *list, PetscEnum *val, PetscBool *set);
+void ModelOptionsPrefixPush(const char *prefix);
+void ModelOptionsPrefixPop(void);
+#define PetscObjectOptionsBegin(obj) \
+  { \
+    PetscOptionItems PetscOptionsObject = (PetscOptionItems)(obj); \
+    (void)PetscOptionsObject; \
+    ModelOptionsPrefixPush(((PetscObject)(obj))->prefix);
+#define PetscOptionsEnd() \
+  ModelOptionsPrefixPop(); \
+  }
 #define PetscOptionsHeadBegin(obj, head) (void)(obj)
 #define PetscOptionsHeadEnd()
-#define PetscOptionsEnum(name, text, man, list, cur, val, set) PETSC_SUCCESS
-#define PetscOptionsInt(name, text, man, cur, val, set) PETSC_SUCCESS
-#define PetscOptionsReal(name, text, man, cur, val, set) PETSC_SUCCESS
-#define PetscOptionsBool(name, text, man, cur, val, set) PETSC_SUCCESS
+#define PetscOptionsEnum(name, text, man, list, cur, val, set) ModelOptionsEnum(name, list, val, set)
+#define PetscOptionsInt(name, text, man, cur, val, set) ModelOptionsInt(name, val, set)
+#define PetscOptionsBoundedInt(name, text, man, cur, val, set, bound) ModelOptionsInt(name, val, set)
+#define PetscOptionsReal(name, text, man, cur, val, set) ModelOptionsReal(name, val, set)
+#define PetscOptionsBool(name, text, man, cur, val, set) ModelOptionsBool(name, val, set)
+#define PetscOptionsFList(name, text, man, list, def, val, len, set) ModelOptionsString(name, val, len, set)
+#define PetscOptionsGetReal(opts, pre, name, val, set) ModelOptionsReal(name, val, set)
+#define PetscOptionsGetInt(opts, pre, name, val, set) ModelOptionsInt(name, val, set)
+#define PetscOptionsGetBool(opts, pre, name, val, set) ModelOptionsBool(name, val, set)
+#define PetscOptionsGetString(opts, pre, name, val, len, set) ModelOptionsString(name, val, len, set)
+PetscErrorCode PetscStrInList(const char[], const char[], char, PetscBool *);
+#define PETSC_MAX_PATH_LEN 4096
+#define PETSC_MAX_OPTION_NAME 512
+#define PETSC_INT_MAX 2147483647
+#define PETSC_ERR_ARG_UNKNOWN_TYPE 86
+#define PETSC_ERR_NOT_CONVERGED 82
+#define PetscFunctionBeginUser
+#define PetscSinReal(a) sin(a)
+#define PetscCosReal(a) cos(a)
+#define PetscExpReal(a) exp(a)
+#include <math.h>
+
+/* ---- program, packages, classes, function lists ---- */
+PetscErrorCode PetscInitialize(int *, char ***, const char[], const char[]);
+PetscErrorCode PetscInitialized(PetscBool *);
+PetscErrorCode PetscFinalize(void);
+PetscErrorCode PetscFinalized(PetscBool *);
+PetscErrorCode PetscRegisterFinalize(PetscErrorCode (*)(void));
+PetscErrorCode PetscClassIdRegister(const char[], PetscClassId *);
+PetscErrorCode PetscLogEventRegister(const char[], PetscClassId, PetscLogEvent *);
+PetscErrorCode PetscInfoProcessClass(const char[], PetscInt, PetscClassId[]);
+PetscErrorCode PetscLogEventExcludeClass(PetscClassId);
+PetscErrorCode ModelFunctionListAdd(PetscFunctionList *, const char[], void (*)(void));
+PetscErrorCode ModelFunctionListFind(PetscFunctionList, const char[], void (**)(void));
+PetscErrorCode PetscFunctionListDestroy(PetscFunctionList *);
+#define PetscFunctionListAdd(list, name, f) ModelFunctionListAdd(list, name, (void (*)(void))(f))
+#define PetscFunctionListFind(list, name, f) ModelFunctionListFind(list, name, (void (**)(void))(f))
+PetscErrorCode ModelHeaderCreate(void *pobj, size_t size, PetscClassId, const char cls[], MPI_Comm);
+PetscErrorCode ModelHeaderDestroy(void *pobj);
+#define PetscHeaderCreate(h, classid, class_name, descr, mansec, comm, destroy, view) ModelHeaderCreate((void *)&(h), sizeof(*(h)), classid, class_name, comm)
+#define PetscHeaderDestroy(h) ModelHeaderDestroy((void *)(h))
+PetscErrorCode PetscObjectChangeTypeName(PetscObject, const char[]);
+PetscErrorCode PetscObjectGetName(PetscObject, const char *[]);
+PetscErrorCode PetscObjectPrintClassNamePrefixType(PetscObject, PetscViewer);
+PetscErrorCode PetscObjectDereference(PetscObject);
+#define PetscUseTypeMethod(obj, method, ...) \
+  do { \
+    PetscCheck((obj)->ops->method, 0, PETSC_ERR_SUP, "No method %s for %s of type %s", #method, ((PetscObject)(obj))->class_name, ((PetscObject)(obj))->type_name); \
+    PetscCall((*(obj)->ops->method)(obj __VA_OPT__(, ) __VA_ARGS__)); \
+  } while (0)
+#define PetscTryTypeMethod(obj, method, ...) \
+  do { \
+    if ((obj)->ops->method) PetscCall((*(obj)->ops->method)(obj __VA_OPT__(, ) __VA_ARGS__)); \
+  } while (0)
 
 /* ---- PetscObject ---- */
 MPI_Comm       PetscObjectComm(PetscObject);
@@ -238,7 +306,40 @@ PetscErrorCode PetscViewerASCIIPrintf(PetscViewer, const char[], ...);
 PetscErrorCode PetscViewerASCIIPushTab(PetscViewer);
 PetscErrorCode PetscViewerASCIIPopTab(PetscViewer);
 
+struct _p_PetscViewerAndFormat {
+  PetscViewer       viewer;
+  PetscViewerFormat format;
+  PetscInt          view_interval;
+  void             *data;
+};
+typedef struct {
+  int unused;
+} *PetscSegBuffer;
+typedef int PetscDataType;
+PetscErrorCode PetscViewerAndFormatCreate(PetscViewer, PetscViewerFormat, PetscViewerAndFormat **);
+PetscErrorCode PetscViewerAndFormatDestroy(PetscViewerAndFormat **);
+PetscErrorCode PetscViewerPushFormat(PetscViewer, PetscViewerFormat);
+PetscErrorCode PetscViewerPopFormat(PetscViewer);
+PetscErrorCode PetscViewerFlush(PetscViewer);
+PetscErrorCode PetscViewerDestroy(PetscViewer *);
+PetscErrorCode PetscViewerCheckReadable(PetscViewer);
+PetscErrorCode PetscViewerRegister(const char[], PetscErrorCode (*)(PetscViewer));
+PetscErrorCode PetscViewerASCIIGetStdout(MPI_Comm, PetscViewer *);
+PetscErrorCode PetscViewerASCIISynchronizedPrintf(PetscViewer, const char[], ...);
+PetscErrorCode PetscViewerASCIIAddTab(PetscViewer, PetscInt);
+PetscErrorCode PetscViewerASCIISubtractTab(PetscViewer, PetscInt);
+PetscErrorCode PetscViewerASCIIPushSynchronized(PetscViewer);
+PetscErrorCode PetscViewerASCIIPopSynchronized(PetscViewer);
+PetscErrorCode PetscMonitorCompare(PetscErrorCode (*)(void), void *, PetscErrorCode (*)(void **), PetscErrorCode (*)(void), void *, PetscErrorCode (*)(void **), PetscBool *);
+
 /* ---- Vec ---- */
+typedef enum { NORM_1, NORM_2, NORM_INFINITY } NormType;
+typedef enum { VECOP_VIEW = 33, VECOP_LOAD = 41 } VecOperation;
+PetscErrorCode VecNorm(Vec, NormType, PetscReal *);
+PetscErrorCode VecSetOperation(Vec, VecOperation, void (*)(void));
+PetscErrorCode VecCreateNest(MPI_Comm, PetscInt, IS[], Vec[], Vec *);
+PetscErrorCode VecGetDM(Vec, DM *);
+PetscErrorCode ISDestroy(IS *);
 PetscErrorCode VecDestroy(Vec *);
 PetscErrorCode VecDuplicate(Vec, Vec *);
 PetscErrorCode VecSet(Vec, PetscScalar);
@@ -304,8 +405,53 @@ PetscErrorCode KSPSetFromOptions(KSP);
 PetscErrorCode KSPSetOptionsPrefix(KSP, const char[]);
 PetscErrorCode KSPView(KSP, PetscViewer);
 PetscErrorCode SNESSolve(SNES, Vec b, Vec x);
+typedef enum { KSP_NORM_DEFAULT = -1, KSP_NORM_NONE, KSP_NORM_PRECONDITIONED, KSP_NORM_UNPRECONDITIONED, KSP_NORM_NATURAL } KSPNormType;
+typedef enum { SNES_CONVERGED_ITERATING = 0, SNES_CONVERGED_FNORM_RELATIVE = 3, SNES_DIVERGED_LINEAR_SOLVE = -3 } SNESConvergedReason;
+extern const char *const *SNESConvergedReasons;
+typedef const char       *PCType;
+PetscErrorCode KSPGetPC(KSP, PC *);
+PetscErrorCode KSPSetTolerances(KSP, PetscReal, PetscReal, PetscReal, PetscInt);
+PetscErrorCode KSPSetNormType(KSP, KSPNormType);
+PetscErrorCode PCSetType(PC, PCType);
+PetscErrorCode PCRegister(const char[], PetscErrorCode (*)(PC));
+PetscErrorCode SNESCreate(MPI_Comm, SNES *);
+PetscErrorCode SNESDestroy(SNES *);
+PetscErrorCode SNESGetKSP(SNES, KSP *);
+PetscErrorCode SNESSetTolerances(SNES, PetscReal, PetscReal, PetscReal, PetscInt, PetscInt);
+PetscErrorCode SNESSetOptionsPrefix(SNES, const char[]);
+PetscErrorCode SNESAppendOptionsPrefix(SNES, const char[]);
+PetscErrorCode SNESSetFromOptions(SNES);
+PetscErrorCode SNESSetPicard(SNES, Vec, PetscErrorCode (*)(SNES, Vec, Vec, void *), Mat, Mat, PetscErrorCode (*)(SNES, Vec, Mat, Mat, void *), void *);
+PetscErrorCode SNESSetFunction(SNES, Vec, PetscErrorCode (*)(SNES, Vec, Vec, void *), void *);
+PetscErrorCode SNESSetComputeInitialGuess(SNES, PetscErrorCode (*)(SNES, Vec, void *), void *);
+PetscErrorCode SNESPicardComputeFunction(SNES, Vec, Vec, void *);
+PetscErrorCode SNESMonitorCancel(SNES);
+PetscErrorCode SNESGetConvergedReason(SNES, SNESConvergedReason *);
 
 /* ---- DM / DMStag ---- */
+typedef enum { DMSTAG_STENCIL_NONE, DMSTAG_STENCIL_STAR, DMSTAG_STENCIL_BOX } DMStagStencilType;
+typedef const char *DMType;
+#define DMPRODUCT "product"
+#define DMSTAG "stag"
+PetscErrorCode DMStagCreate2d(MPI_Comm, DMBoundaryType, DMBoundaryType, PetscInt, PetscInt, PetscInt, PetscInt, PetscInt, PetscInt, PetscInt, DMStagStencilType, PetscInt, const PetscInt[], const PetscInt[], DM *);
+PetscErrorCode DMStagCreate3d(MPI_Comm, DMBoundaryType, DMBoundaryType, DMBoundaryType, PetscInt, PetscInt, PetscInt, PetscInt, PetscInt, PetscInt, PetscInt, PetscInt, PetscInt, PetscInt, DMStagStencilType, PetscInt, const PetscInt[], const PetscInt[], const PetscInt[], DM *);
+PetscErrorCode DMStagCreateCompatibleDMStag(DM, PetscInt, PetscInt, PetscInt, PetscInt, DM *);
+PetscErrorCode DMSetUp(DM);
+PetscErrorCode DMDestroy(DM *);
+PetscErrorCode DMSetMatrixPreallocateOnly(DM, PetscBool);
+PetscErrorCode DMStagSetRefinementFactor(DM, PetscInt, PetscInt, PetscInt);
+PetscErrorCode DMStagGetNumRanks(DM, PetscInt *, PetscInt *, PetscInt *);
+PetscErrorCode DMStagGetOwnershipRanges(DM, const PetscInt *[], const PetscInt *[], const PetscInt *[]);
+PetscErrorCode DMStagGetLocalSizes(DM, PetscInt *, PetscInt *, PetscInt *);
+PetscErrorCode DMStagSetUniformCoordinatesProduct(DM, PetscReal, PetscReal, PetscReal, PetscReal, PetscReal, PetscReal);
+PetscErrorCode DMStagGetProductCoordinateArrays(DM, void *, void *, void *);
+PetscErrorCode DMStagRestoreProductCoordinateArrays(DM, void *, void *, void *);
+PetscErrorCode DMStagSetCoordinateDMType(DM, DMType);
+PetscErrorCode DMGetCoordinateDM(DM, DM *);
+PetscErrorCode DMSetCoordinateDM(DM, DM);
+PetscErrorCode DMCompositeCreate(MPI_Comm, DM *);
+PetscErrorCode DMCompositeAddDM(DM, DM);
+PetscErrorCode DMCompositeGetGlobalISs(DM, IS *[]);
 PetscErrorCode DMGetDimension(DM, PetscInt *);
 PetscErrorCode DMGetLocalVector(DM, Vec *);
 PetscErrorCode DMRestoreLocalVector(DM, Vec *);

@@ -352,7 +352,7 @@ PetscErrorCode VecRestoreSubVector(Vec v, IS is, Vec *sub)
 }
 PetscErrorCode VecAssemblyBegin(Vec v) { return (void)v, PETSC_SUCCESS; }
 PetscErrorCode VecAssemblyEnd(Vec v) { return (void)v, PETSC_SUCCESS; }
-PetscErrorCode VecView(Vec v, PetscViewer w) { return (void)v, (void)w, PETSC_SUCCESS; }
+PetscErrorCode VecView(Vec v, PetscViewer w) { return v->view_op ? v->view_op(v, w) : PETSC_SUCCESS; }
 /* flat copies of a (possibly nested) vector, block after block */
 void ModelVecGather(Vec v, double *out)
 {
@@ -817,8 +817,8 @@ PetscErrorCode KSPSetOptionsPrefix(KSP k, const char p[])
 PetscErrorCode KSPView(KSP k, PetscViewer v) { return (void)k, (void)v, PETSC_SUCCESS; }
 PetscErrorCode SNESSolve(SNES s, Vec b, Vec x)
 {
-  PetscCheck(s && s->solve, 0, PETSC_ERR_ARG_WRONGSTATE, "SNESSolve: no solve routine attached");
-  return s->solve(s, b, x);
+  PetscCheck(s, 0, PETSC_ERR_ARG_WRONGSTATE, "SNESSolve: no SNES");
+  return s->solve ? s->solve(s, b, x) : ModelSNESSolvePicard(s, b, x);
 }
 
 /* ------------------------------------------------------------------ DMStag */
@@ -836,12 +836,35 @@ static int entry_exists(DM dm, int l, const int g[3])
   return 1;
 }
 /* dof0..dof3: vertices, edges, faces, elements (2-D: vertices, faces, elements); coordinates belong to the mesh */
-DM ModelDMStagCreate(int dim, const int N[3], const int per[3], int d0, int d1, int d2, int d3, double **ctab)
+struct model_coords *ModelCoordsCreate(int dim, const int N[3], const int per[3])
+{
+  struct model_coords *c = (struct model_coords *)zalloc(sizeof(*c));
+  int                  d, li;
+  c->refct = 1, c->dim = dim;
+  for (d = 0; d < dim; ++d) {
+    c->gs[d]    = per[d] ? -1 : 0;
+    c->gn[d]    = N[d] + (per[d] ? 2 : 1);
+    c->coord[d] = (double *)zalloc(sizeof(double) * (2 * (size_t)c->gn[d] + 1));
+    c->ctab[d]  = (double **)zalloc(sizeof(double *) * (size_t)c->gn[d]);
+    for (li = 0; li < c->gn[d]; ++li) c->ctab[d][li] = c->coord[d] + 2 * li;
+    for (li = 0; li <= 2 * c->gn[d]; ++li) c->coord[d][li] = NAN;
+  }
+  return c;
+}
+void ModelCoordsDestroy(struct model_coords *c)
+{
+  int d;
+  if (!c || --c->refct > 0) return;
+  for (d = 0; d < 3; ++d) free(c->coord[d]), free(c->ctab[d]);
+  free(c);
+}
+DM ModelDMStagCreate(int dim, const int N[3], const int per[3], int d0, int d1, int d2, int d3, struct model_coords *coords)
 {
   DM  dm = (DM)zalloc(sizeof(*dm));
   int d, l, li[3], g[3], w[3];
   ModelHeaderInit(dm, 15, "DM", "stag", NULL);
-  dm->dim = dim, dm->ctab = ctab;
+  dm->dim = dim, dm->coords = coords, dm->setup = 1;
+  if (coords) ++coords->refct;
   dm->dof[0] = d0, dm->dof[1] = d1, dm->dof[2] = d2, dm->dof[3] = d3;
   for (d = 0; d < 3; ++d) {
     dm->N[d]   = d < dim ? N[d] : 1;
@@ -890,6 +913,7 @@ void ModelDMDestroy(DM dm)
 {
   if (!dm) return;
   ModelHeaderFree(dm);
+  ModelCoordsDestroy(dm->coords);
   free(dm->l2g.idx), free(dm);
 }
 PetscErrorCode DMGetDimension(DM dm, PetscInt *dim) { return *dim = dm->dim, PETSC_SUCCESS; }
@@ -1074,9 +1098,10 @@ PetscErrorCode DMStagVecRestoreArray(DM dm, Vec v, void *a) { return stag_array_
 PetscErrorCode DMStagVecRestoreArrayRead(DM dm, Vec v, void *a) { return stag_array_restore(dm, v, a, 0); }
 PetscErrorCode DMStagGetProductCoordinateArraysRead(DM dm, void *ax, void *ay, void *az)
 {
-  if (ax) *(double ***)ax = (double **)dm->ctab[0] - dm->gs[0];
-  if (ay) *(double ***)ay = (double **)dm->ctab[1] - dm->gs[1];
-  if (az && dm->dim == 3) *(double ***)az = (double **)dm->ctab[2] - dm->gs[2];
+  PetscCheck(dm->coords, 0, PETSC_ERR_ARG_WRONGSTATE, "the DM has no coordinates");
+  if (ax) *(double ***)ax = dm->coords->ctab[0] - dm->gs[0];
+  if (ay) *(double ***)ay = dm->coords->ctab[1] - dm->gs[1];
+  if (az && dm->dim == 3) *(double ***)az = dm->coords->ctab[2] - dm->gs[2];
   return PETSC_SUCCESS;
 }
 PetscErrorCode DMStagRestoreProductCoordinateArraysRead(DM dm, void *ax, void *ay, void *az)

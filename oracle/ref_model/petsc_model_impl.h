@@ -15,8 +15,19 @@ struct _p_IS {
   int                   field; /* the field of the solution nest this index set selects */
   PetscInt              n;     /* its number of entries */
 };
+/* 1-D product coordinates shared by the DMs of a mesh: per direction [ghosted element][LEFT, ELEMENT]; RIGHT = next LEFT */
+struct model_coords {
+  int      refct, dim, gs[3], gn[3];
+  double  *coord[3];
+  double **ctab[3];
+};
+struct model_coords *ModelCoordsCreate(int dim, const int N[3], const int per[3]);
+void                 ModelCoordsDestroy(struct model_coords *);
+
 struct _p_Vec {
   struct _p_PetscObject hdr;
+  PetscErrorCode (*view_op)(Vec, PetscViewer);
+  PetscErrorCode (*load_op)(Vec, PetscViewer);
   DM                    dm;
   int                   local;
   PetscInt              n;
@@ -46,15 +57,37 @@ struct _p_KSP {
   struct _p_PetscObject hdr;
   Mat                   A;
   long                  nsolves;
+  PC                    pc; /* the KSP of a SNES owns a PC (SNESGetKSP / KSPGetPC) */
+  double                rtol;
 };
 struct _p_SNES {
   struct _p_PetscObject hdr;
   void                 *ctx;
-  PetscErrorCode (*solve)(SNES, Vec, Vec);
+  PetscErrorCode (*solve)(SNES, Vec, Vec); /* ref_driver.c attaches its own; NULL: the generic Picard solve of petsc_model_app.c */
+  KSP ksp;
+  Vec r;
+  Mat J, Jpre;
+  PetscErrorCode (*bfunc)(SNES, Vec, Vec, void *);
+  PetscErrorCode (*jfunc)(SNES, Vec, Mat, Mat, void *);
+  PetscErrorCode (*func)(SNES, Vec, Vec, void *);
+  PetscErrorCode (*guess)(SNES, Vec, void *);
+  void *pctx, *fctx, *gctx;
+  int   mode, its, nhist; /* 0 exact, 1 one PC application (-ns_ksp_type preonly), 2 right-preconditioned GMRES */
+  double hist[256];
+};
+struct stored_vec {
+  char              *name;
+  PetscInt           n;
+  double            *a;
+  struct stored_vec *next;
 };
 struct _p_PetscViewer {
   struct _p_PetscObject hdr;
   FILE                 *f;
+  char                 *path;  /* "flucacgns" model viewers dump named vectors (natural ordering of their DM) to this file */
+  struct stored_vec    *store;
+  PetscInt              step;
+  PetscReal             time;
 };
 #define MODEL_MAXLOC 8
 struct _p_DM {
@@ -64,9 +97,13 @@ struct _p_DM {
   int                              locmask[MODEL_MAXLOC], locoff[MODEL_MAXLOC], locdof[MODEL_MAXLOC];
   int                              nglobal, nlocal;
   struct _p_ISLocalToGlobalMapping l2g;
-  double                         **ctab; /* [dim]: pointer tables of the 1-D product coordinates (owned by the mesh) */
+  struct model_coords             *coords; /* shared by the DMs of a mesh */
+  int                              setup, ncomposite;
+  DM                               composite[4];
+  PetscInt                         ownership[3];
 };
 
+PetscErrorCode ModelSNESSolvePicard(SNES, Vec, Vec);
 const char *ModelLastError(void);
 void        ModelHeaderInit(void *obj, PetscClassId, const char *cls, const char *type, PetscErrorCode (*destroy)(PetscObject));
 void        ModelHeaderFree(void *obj);
@@ -77,6 +114,6 @@ void        ModelVecScatter(Vec, const double *);
 Mat         ModelMatCreateAIJ(PetscInt m, PetscInt n);
 double     *ModelMatEntry(Mat, int i, int j, int create);
 double      ModelDenseSolve(int n, double *a, double *b);
-DM          ModelDMStagCreate(int dim, const int N[3], const int per[3], int d0, int d1, int d2, int d3, double **ctab);
+DM          ModelDMStagCreate(int dim, const int N[3], const int per[3], int d0, int d1, int d2, int d3, struct model_coords *coords);
 void        ModelDMDestroy(DM);
 #endif

@@ -30,8 +30,7 @@ struct _p_Mesh {
   struct _p_PetscObject hdr;
   int                   dim, N[3], per[3];
   DM                    dm[4];
-  double               *coord[3];
-  double              **ctab[3];
+  struct model_coords  *coords;
 };
 PetscErrorCode MeshGetDimension(Mesh m, PetscInt *dim) { return *dim = m->dim, PETSC_SUCCESS; }
 PetscErrorCode MeshGetDM(Mesh m, MeshDMType t, DM *dm) { return *dm = m->dm[t], PETSC_SUCCESS; }
@@ -50,11 +49,10 @@ static Mesh mesh_create(int dim, const int N[3], const int per[3], const double 
   ModelHeaderInit(m, MESH_CLASSID, "Mesh", MESHCART, NULL);
   m->dim = dim;
   for (d = 0; d < 3; ++d) m->N[d] = d < dim ? N[d] : 1, m->per[d] = d < dim ? per[d] : 0;
+  m->coords = ModelCoordsCreate(dim, m->N, m->per);
   for (d = 0; d < dim; ++d) { /* 1-D product coordinates: [element][LEFT, ELEMENT], RIGHT = the next element's LEFT */
-    const int    gs = m->per[d] ? -1 : 0, gn = m->N[d] + (m->per[d] ? 2 : 1);
+    const int    gs = m->coords->gs[d], gn = m->coords->gn[d];
     const double L = xf[d][m->N[d]] - xf[d][0];
-    m->coord[d] = (double *)calloc(2 * (size_t)gn + 1, sizeof(double));
-    m->ctab[d]  = (double **)calloc((size_t)gn, sizeof(double *));
     for (li = 0; li < gn; ++li) {
       const int g = li + gs;
       double    left, right = NAN;
@@ -64,30 +62,28 @@ static Mesh mesh_create(int dim, const int N[3], const int per[3], const double 
         left = xf[d][m->N[d]];
         if (m->per[d]) right = xf[d][1] + L;
       }
-      m->coord[d][2 * li] = left, m->coord[d][2 * li + 1] = (left + right) / 2.;
+      m->coords->coord[d][2 * li] = left, m->coords->coord[d][2 * li + 1] = (left + right) / 2.;
       /* The partial element at the upper end of a non-periodic direction has no centre, but its slot exists and the reference READS
          it (cnlinearcart3d.c:1996,2055,2114: the face-normal interpolation at an upper pressure outlet passes arrc[N][ielem] as the
          wall coordinate).  PETSc's DMStagSetUniformCoordinatesProduct fills that slot like any other element, x_max + h/2 -- what a
          mesh built with MeshCartSetUniformCoordinates holds; on loaded non-uniform coordinates the reference leaves a stale value
          there (cart.c:137-143 sets centres for i < N only).  The model stores the mirror image of the last centre, which is
          x_max + h/2 on a uniform mesh. */
-      if (g == m->N[d] && !m->per[d]) m->coord[d][2 * li + 1] = 2. * xf[d][m->N[d]] - (xf[d][m->N[d] - 1] + xf[d][m->N[d]]) / 2.;
-      m->ctab[d][li] = m->coord[d] + 2 * li;
+      if (g == m->N[d] && !m->per[d]) m->coords->coord[d][2 * li + 1] = 2. * xf[d][m->N[d]] - (xf[d][m->N[d] - 1] + xf[d][m->N[d]]) / 2.;
     }
-    m->coord[d][2 * gn] = NAN;
   }
   /* cart.c:88-120: scalar, vector (dim dof per element), staggered scalar (1 dof per face), staggered vector (dim dof per face) */
-  m->dm[MESH_DM_SCALAR]      = dim == 2 ? ModelDMStagCreate(2, m->N, m->per, 0, 0, 1, 0, (double **)m->ctab) : ModelDMStagCreate(3, m->N, m->per, 0, 0, 0, 1, (double **)m->ctab);
-  m->dm[MESH_DM_VECTOR]      = dim == 2 ? ModelDMStagCreate(2, m->N, m->per, 0, 0, 2, 0, (double **)m->ctab) : ModelDMStagCreate(3, m->N, m->per, 0, 0, 0, 3, (double **)m->ctab);
-  m->dm[MESH_DM_STAG_SCALAR] = dim == 2 ? ModelDMStagCreate(2, m->N, m->per, 0, 1, 0, 0, (double **)m->ctab) : ModelDMStagCreate(3, m->N, m->per, 0, 0, 1, 0, (double **)m->ctab);
-  m->dm[MESH_DM_STAG_VECTOR] = dim == 2 ? ModelDMStagCreate(2, m->N, m->per, 0, 2, 0, 0, (double **)m->ctab) : ModelDMStagCreate(3, m->N, m->per, 0, 0, 3, 0, (double **)m->ctab);
+  m->dm[MESH_DM_SCALAR]      = dim == 2 ? ModelDMStagCreate(2, m->N, m->per, 0, 0, 1, 0, m->coords) : ModelDMStagCreate(3, m->N, m->per, 0, 0, 0, 1, m->coords);
+  m->dm[MESH_DM_VECTOR]      = dim == 2 ? ModelDMStagCreate(2, m->N, m->per, 0, 0, 2, 0, m->coords) : ModelDMStagCreate(3, m->N, m->per, 0, 0, 0, 3, m->coords);
+  m->dm[MESH_DM_STAG_SCALAR] = dim == 2 ? ModelDMStagCreate(2, m->N, m->per, 0, 1, 0, 0, m->coords) : ModelDMStagCreate(3, m->N, m->per, 0, 0, 1, 0, m->coords);
+  m->dm[MESH_DM_STAG_VECTOR] = dim == 2 ? ModelDMStagCreate(2, m->N, m->per, 0, 2, 0, 0, m->coords) : ModelDMStagCreate(3, m->N, m->per, 0, 0, 3, 0, m->coords);
   return m;
 }
 static void mesh_destroy(Mesh m)
 {
   int d;
   for (d = 0; d < 4; ++d) ModelDMDestroy(m->dm[d]);
-  for (d = 0; d < 3; ++d) free(m->coord[d]), free(m->ctab[d]);
+  ModelCoordsDestroy(m->coords);
   ModelHeaderFree(m);
   free(m);
 }
@@ -144,7 +140,6 @@ PetscErrorCode NSGetField(NS ns, const char name[], PetscInt *idx, MeshDMType *d
   return PETSC_SUCCESS;
 }
 PetscErrorCode NSCheckDiverged(NS ns) { return (void)ns, PETSC_SUCCESS; } /* nsbasic.c:425-436 reads the SNES reason: the exact solves do not diverge */
-PetscErrorCode FlucaVecLoad(Vec v, PetscViewer w) { return (void)v, (void)w, PETSC_ERR_SUP; }
 
 /* ------------------------------------------------------------------ canonical layout <-> DMStag global entries */
 static PetscErrorCode build_map(Ref *h, DM dm, DMStagStencilLocation loc, int comp, int facedir, int *map, long *count)

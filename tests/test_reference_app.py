@@ -1,0 +1,112 @@
+"""NS type "b200" INSIDE THE REFERENCE'S OWN PROGRAMS.
+
+oracle/_ref/ holds the reference as a program (`make -C oracle ref_app`, where /root/reference is present): its sys, mesh and NS
+libraries -- flucainit.c, meshbasic.c, cart.c, nsbasic.c, nsopts.c, nssol.c, nsreg.c, cnlinear*.c, abfpc.c, ... everything but the
+CGNS viewer and FlucaFD -- and its own NS test drivers cavity_flow_2d.c, cavity_flow_3d.c and taylor_green_vortex.c, all UNMODIFIED
+and compiled from where they lie, on the single-rank PETSc model of oracle/ref_model/.  glue/nsb200.c is built against the
+reference's own headers as the out-of-tree plugin of INTEGRATION.md 2(b) and loaded the way PETSc loads it:
+
+    cavity_flow_2d -dll_append libfluca_nsb200.so -ns_type b200 ...
+
+PetscInitialize opens the library and calls PetscDLLibraryRegister_fluca_nsb200 -> NSRegister("b200", NSCreate_B200)
+(nsreg.c:5-11); NSSetFromOptions (nsopts.c:179-181) switches the type the driver had hard-coded; NSSetUp / NSSolve / NSStep /
+NSMonitorSolution -> NSViewSolution of the reference's base class drive it.  The solution every step writes through the viewer
+(Velocity, FaceNormalVelocity, Pressure and the type's PressureHalfStep, in DMStag's own ordering) is compared with the same
+program run with the reference's own type cnlinear.  CPU: the plugin links the host-emulation build; -m gpu: the CUDA library.
+What is modelled is PETSc only (exact linear solves in place of GMRES + ILU); no reference source is changed or copied."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+TIGHT = ["-ns_b200_outer_rtol", "1e-13", "-ns_b200_momentum_rtol", "1e-13", "-ns_b200_schur_rtol", "1e-13"]
+
+
+def _ready(kind):
+    if os.path.isdir("/root/reference/fluca"):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "hostemu")], check=True, stdout=subprocess.DEVNULL)
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref_app"], check=True, stdout=subprocess.DEVNULL)
+    need = [os.path.join(REFDIR, p) for p in ("cavity_flow_2d", "cavity_flow_3d", "taylor_green_vortex", "libfluca_ref_full.so", os.path.join(kind, "libfluca_nsb200.so"))]
+    return all(os.path.exists(p) for p in need)
+
+
+def load_dump(path):
+    """name -> values, as VecView of the model's stand-in for the CGNS viewer writes them (petsc_model_app.c)"""
+    out, b, i = {}, open(path, "rb").read(), 0
+    while i < len(b):
+        j = b.index(b"\n", i)
+        k = b.index(b"\n", j + 1)
+        n = int(b[j + 1 : k])
+        out[b[i:j].decode()] = np.frombuffer(b[k + 1 : k + 1 + 8 * n], dtype=np.float64).copy()
+        i = k + 1 + 8 * n + 1
+    return out
+
+
+def run(prog, args, tmp_path, tag, plugin=None):
+    dump = str(tmp_path / f"{prog}_{tag}.bin")
+    cmd = [os.path.join(REFDIR, prog)] + list(args) + ["-ns_monitor", "-ns_monitor_solution", f"flucacgns:{dump}"]
+    if plugin:
+        cmd += ["-dll_append", os.path.join(REFDIR, plugin, "libfluca_nsb200.so"), "-ns_type", "b200"] + TIGHT
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "WARNING! There are options you set that were not used" not in r.stderr, r.stderr
+    return load_dump(dump), r.stdout
+
+
+def compare(prog, args, tmp_path, plugin, ref_extra=(), b200_extra=(), tol=1e-10):
+    a, out_a = run(prog, list(args) + list(ref_extra), tmp_path, "cnlinear")
+    b, out_b = run(prog, list(args) + list(b200_extra), tmp_path, "b200", plugin=plugin)
+    assert set(a) == set(b) == {"Velocity", "FaceNormalVelocity", "Pressure", "PressureHalfStep"}
+    for k in a:
+        scale = max(np.abs(a[k]).max(), 1e-300)
+        assert a[k].shape == b[k].shape and np.abs(a[k] - b[k]).max() <= (10 * tol if k.startswith("Pressure") else tol) * scale, (prog, k, np.abs(a[k] - b[k]).max() / scale)
+    mon = [ln for ln in out_a.splitlines() if " NS dt " in ln]
+    assert mon and mon == [ln for ln in out_b.splitlines() if " NS dt " in ln]  # NSMonitorDefault: same steps, same times
+    return out_a, out_b
+
+
+CASES = [
+    ("cavity_flow_2d", ["-cart_grid_x", "12", "-cart_grid_y", "12", "-ns_time_step_size", "0.04", "-ns_max_steps", "4"], (), ()),
+    ("cavity_flow_2d", ["-cart_grid_x", "10", "-cart_grid_y", "8", "-Re", "400", "-ns_time_step_size", "0.05", "-ns_max_steps", "3"], ("-ns_ksp_type", "preonly"), ("-ns_b200_mode", "1")),
+    ("cavity_flow_2d", ["-cart_grid_x", "8", "-cart_grid_y", "8", "-ns_time_step_size", "0.06", "-ns_max_steps", "3", "-ns_pc_abf_schur_ainv_type", "DIAG", "-ns_pc_abf_upper_ainv_type", "ROWSUM"], ("-ns_ksp_type", "preonly"), ("-ns_b200_mode", "1")),
+    ("cavity_flow_3d", ["-cart_grid_x", "6", "-cart_grid_y", "6", "-cart_grid_z", "4", "-ns_time_step_size", "0.08", "-ns_max_steps", "3"], (), ()),
+    ("taylor_green_vortex", ["-nsteps", "5", "-t_final", "0.25"], (), ()),
+    ("taylor_green_vortex", ["-nsteps", "4", "-t_final", "0.2", "-periodic", "-cart_grid_x", "12", "-cart_grid_y", "12"], (), ()),
+]
+IDS = ["cavity2d_12", "cavity2d_10x8_preonly_vs_fractional", "cavity2d_abf_diag_rowsum", "cavity3d_6x6x4", "tgv_dirichlet", "tgv_periodic_12"]
+
+
+@pytest.mark.skipif(not _ready("hostemu"), reason="oracle/_ref (the reference's programs on the PETSc model) is not built here")
+@pytest.mark.parametrize("prog,args,ref_extra,b200_extra", CASES, ids=IDS)
+def test_b200_inside_the_references_own_programs(tmp_path, prog, args, ref_extra, b200_extra):
+    out_a, out_b = compare(prog, args, tmp_path, "hostemu", ref_extra, b200_extra)
+    if prog == "taylor_green_vortex":  # the driver's own verdict: the error against the analytic solution, printed with %g
+        err_a = [float(ln.split(":")[1]) for ln in out_a.splitlines() if "error" in ln]
+        err_b = [float(ln.split(":")[1]) for ln in out_b.splitlines() if "error" in ln]
+        assert len(err_a) == 2 and err_a == pytest.approx(err_b, rel=1e-5)
+
+
+@pytest.mark.skipif(not _ready("hostemu"), reason="oracle/_ref is not built here")
+def test_the_type_is_unknown_without_the_plugin(tmp_path):
+    """-ns_type b200 without -dll_append: the reference's NSSetType does not know the type (nsbasic.c:55-79) -- nothing of it is linked
+    into the reference's programs."""
+    r = subprocess.run([os.path.join(REFDIR, "cavity_flow_2d"), "-ns_type", "b200", "-cart_grid_x", "8", "-cart_grid_y", "8", "-ns_max_steps", "1"], capture_output=True, text=True)
+    assert r.returncode != 0 and "b200" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not _ready("cuda"), reason="oracle/_ref is not built here")
+@pytest.mark.parametrize(
+    "prog,args,ref_extra,b200_extra",
+    [
+        # 32 x 8 cells per plane reach the TMA tile kernels; the model's inner solves are dense, hence few planes and one ABF application
+        ("cavity_flow_3d", ["-cart_grid_x", "32", "-cart_grid_y", "8", "-cart_grid_z", "3", "-ns_time_step_size", "0.02", "-ns_max_steps", "2"], ("-ns_ksp_type", "preonly"), ("-ns_b200_mode", "1")),
+        ("taylor_green_vortex", ["-nsteps", "3", "-t_final", "0.15", "-cart_grid_x", "16", "-cart_grid_y", "16"], (), ()),
+    ],
+    ids=["cavity3d_tiles_fractional", "tgv_16_coupled"],
+)
+def test_b200_cuda_inside_the_references_own_programs(tmp_path, prog, args, ref_extra, b200_extra):
+    compare(prog, args, tmp_path, "cuda", ref_extra, b200_extra)
