@@ -264,6 +264,7 @@ PetscErrorCode VecCopy(Vec x, Vec y)
 {
   int s;
   SAME_LAYOUT(x, y);
+  if (x->nsub && getenv("PETSC_MODEL_TRACE")) fprintf(stderr, "[PETSc model trace] VecCopy of a nest (%d entries)\n", (int)x->n);
   for (s = 0; s < x->nsub; ++s) PetscCall(VecCopy(x->sub[s], y->sub[s]));
   if (!x->nsub && x != y) memcpy(y->a, x->a, sizeof(double) * (size_t)x->n);
   ++y->hdr.state;
@@ -630,6 +631,7 @@ PetscErrorCode MatCreateNest(MPI_Comm c, PetscInt nr, const IS isr[], PetscInt n
 {
   int i;
   PetscCheck(nr == 3 && nc == 3 && !a, c, PETSC_ERR_SUP, "the model has 3 x 3 nests created empty");
+  if (getenv("PETSC_MODEL_TRACE")) fprintf(stderr, "[PETSc model trace] MatCreateNest\n");
   *J = (Mat)zalloc(sizeof(**J));
   ModelHeaderInit(*J, MAT_CLASSID, "Mat", MATNEST, mat_destroy_obj);
   (*J)->nest = 1;

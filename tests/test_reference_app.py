@@ -110,3 +110,44 @@ def test_the_type_is_unknown_without_the_plugin(tmp_path):
 )
 def test_b200_cuda_inside_the_references_own_programs(tmp_path, prog, args, ref_extra, b200_extra):
     compare(prog, args, tmp_path, "cuda", ref_extra, b200_extra)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/fluca"), reason="the reference tree is not on this machine")
+def test_matrix_free_patch_compiled_into_the_references_base_class(tmp_path):
+    """SURVEY 8f rank 2, as a running program: glue/patches/0001-ns-matrix-free-type-hooks.patch applied to a COPY of the reference's
+    sources (under the test's temporary directory), the patched reference built on the PETSc model, the glue built with
+    -DFLUCA_NS_HAS_MATRIXFREE.  The patched NSSetUp builds no Jacobian / null space / SNES for b200 and NSStep skips the host copy
+    sol -> sol0; the answer is the unpatched reference's cnlinear answer, and cnlinear itself is unchanged by the patch."""
+    import shutil
+
+    tree = tmp_path / "patched"
+    (tree / "fluca").mkdir(parents=True)
+    for sub in ("include", "src", "tests"):
+        shutil.copytree(os.path.join("/root/reference/fluca", sub), tree / "fluca" / sub)
+    r = subprocess.run(["patch", "-p1", "-i", os.path.join(ROOT, "glue", "patches", "0001-ns-matrix-free-type-hooks.patch")], cwd=tree, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = tmp_path / "out"
+    subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "hostemu")], check=True, stdout=subprocess.DEVNULL)
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref_app", f"REF={tree}/fluca", f"OUTDIR={out}", "PLUGINDEFS=-DFLUCA_NS_HAS_MATRIXFREE", f"PLUGINS={out}/hostemu/libfluca_nsb200.so"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    args = ["-cart_grid_x", "6", "-cart_grid_y", "6", "-cart_grid_z", "4", "-ns_time_step_size", "0.08", "-ns_max_steps", "3", "-ns_monitor"]
+
+    trace = {}
+
+    def go(exe_dir, extra, tag):
+        dump = str(tmp_path / f"{tag}.bin")
+        rr = subprocess.run([os.path.join(exe_dir, "cavity_flow_3d")] + args + ["-ns_monitor_solution", f"flucacgns:{dump}"] + extra, capture_output=True, text=True, timeout=600, env=dict(os.environ, PETSC_MODEL_TRACE="1"))
+        assert rr.returncode == 0, rr.stdout + rr.stderr
+        trace[tag] = rr.stderr
+        return load_dump(dump)
+
+    ref = go(REFDIR, [], "unpatched_cnlinear")
+    cn = go(str(out), [], "patched_cnlinear")
+    b2 = go(str(out), ["-dll_append", str(out / "hostemu" / "libfluca_nsb200.so"), "-ns_type", "b200"] + TIGHT, "patched_b200")
+    for k in ref:
+        assert np.array_equal(ref[k], cn[k]), k  # the patch does not touch a type that leaves the flag unset
+        scale = np.abs(ref[k]).max()
+        assert np.abs(ref[k] - b2[k]).max() <= (1e-9 if k.startswith("Pressure") else 1e-10) * scale, k
+    # what the patch is for: no MatNest Jacobian (nsbasic.c:203-208) and no host copy sol -> sol0 per step (nsbasic.c:281-282) for b200
+    assert trace["patched_cnlinear"].count("MatCreateNest") == 1 and trace["patched_cnlinear"].count("VecCopy of a nest") >= 3  # one per step (+ the model's solver)
+    assert "MatCreateNest" not in trace["patched_b200"] and "VecCopy of a nest" not in trace["patched_b200"]
