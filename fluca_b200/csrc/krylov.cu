@@ -279,8 +279,16 @@ static int poisson_pcg(Solver &s, double *b, double *x)
   if (bnorm == 0.) return 0;
   if (!(bnorm == bnorm)) throw Error(FL_ERR_DIVERGED, "Poisson right-hand side is NaN");
   const double tol = inner_rtol(s, s.opt.schur_rtol) * bnorm;
-  double       rz = 0.;
-  int          it = 0;
+  // The V-cycle is not a symmetric operator (summed-residual restriction against trilinear prolongation; measured: 8 % asymmetry on a
+  // 6^3 grid with a symmetry plane), so the Fletcher-Reeves beta of textbook PCG loses conjugacy in LONG solves: a rough right-hand
+  // side then needs 185 iterations for 1e-5 and stalls at 1e-5 for good, where the flexible (Polak-Ribiere) beta
+  //   beta = (<r_new, z_new> - <r_old, z_new>) / <r_old, z_old>,   <r_old, z_new> = <r_new, z_new> + alpha <q, z_new>
+  // takes 10 and converges to round-off (found by the randomised comparison with the compiled reference).  It costs one
+  // more reduction over (q, z) per iteration, so it is used from iteration `pr_from` of a solve on: the 4-6 iteration solves of the
+  // cavity configurations never pay for it.  FLUCA_B200_PCG_PR_FROM=n moves the switch (0: always flexible, -1: textbook always).
+  static const int pr_from = getenv("FLUCA_B200_PCG_PR_FROM") ? atoi(getenv("FLUCA_B200_PCG_PR_FROM")) : 4;
+  double            rz = 0., alpha = 0.;
+  int               it = 0;
   for (; it < s.opt.inner_maxit;) {
     // z = V-cycle(r); its last smoothing sweep also accumulates rz_new = <r, z>
     const double *Z = mg_vcycle(s, s.pr, s.opt.mg_nu2 > 0) + off;
@@ -290,7 +298,15 @@ static int poisson_pcg(Solver &s, double *b, double *x)
     if (it == 0) {
       for_range(s.ex, len, FL_LAMBDA(long i) { PP[i] = Z[i]; });
     } else {
-      const double beta = rz_new / rz;
+      double qz = 0.;
+      const bool flexible = pr_from >= 0 && it >= pr_from;
+      if (flexible) { // q still holds P p of the previous iteration
+        double r2[1];
+        for_range_reduce<1>(s.ex, len, FL_LAMBDA(long i, double acc[1]) { acc[0] += Q[i] * Z[i]; });
+        reduce_finish(s, 1, r2);
+        qz = r2[0];
+      }
+      const double beta = flexible ? -alpha * qz / rz : rz_new / rz;
       for_range(s.ex, len, FL_LAMBDA(long i) { PP[i] = Z[i] + beta * PP[i]; });
     }
     rz = rz_new;
@@ -299,7 +315,7 @@ static int poisson_pcg(Solver &s, double *b, double *x)
       if (pq == 0.) break;
       throw Error(FL_ERR_DIVERGED, "CG breakdown in the pressure solve (<p, P p> <= 0 or NaN)");
     }
-    const double alpha = rz / pq;
+    alpha = rz / pq;
     for_range_reduce<1>(s.ex, len, FL_LAMBDA(long i, double acc[1]) {
       X[i] += alpha * PP[i];
       const double rv = R[i] - alpha * Q[i];

@@ -264,3 +264,27 @@ def test_random_boundary_sets_equal_the_references(block):
             orc.step(opt)
         x, y = ref.get_state(), orc.get_state()
         assert parity.rel(x["v"], y["v"]) <= 1e-9 and parity.relU(x["U"], y["U"]) <= 1e-9 and parity.rel(x["p"], y["p"]) <= 1e-8, tag
+
+
+@needs_reference
+@pytest.mark.parametrize("block", range(4))
+def test_product_sources_equal_the_reference_on_random_boundary_sets(block):
+    """The product's host logic (host-emulation build) against the compiled reference directly, fractional mode, two steps, on
+    random cases.  This sweep is what exposed the stall of the pressure PCG on rough right-hand sides (the V-cycle is not a symmetric
+    operator; krylov.cu now switches to the flexible beta in long solves): 500 iterations at 1e-5 of the tolerance before, <= 30 now."""
+    lib = parity.hostemu_library()
+    for seed in range(10 * block, 10 * block + 10):
+        case = _random_case(seed)
+        state = case.initial_state(seed=seed + 100)
+        ref = _gen.make_reference(case)
+        ref.set_state(*state)
+        ns = parity.make_ns(case, lib, "fractional", **parity.TIGHT)
+        parity.set_initial(ns, state)
+        for _ in range(2):
+            ref.step(mode=R.ABF_ONCE)
+            fb.NSStep(ns)
+            assert fb.NSB200GetStats(ns).schur_its < 120, (seed, fb.NSB200GetStats(ns).schur_its)
+        x, y = ref.get_state(), fb.NSB200GetSolver(ns).get_state()
+        fb.NSDestroy(ns)
+        tag = (seed, case.n, [b["type"] for b in case.bcs], case.stretch)
+        assert parity.rel(y["v"], x["v"]) <= 1e-9 and parity.relU(y["U"], x["U"]) <= 1e-9 and parity.rel(y["p"], x["p"]) <= 1e-8, tag
