@@ -456,7 +456,7 @@ static PetscErrorCode NSFormFunction_B200(NS ns, Vec x, Vec f)
     PetscCall(PetscObjectStateGet((PetscObject)ns->sol, &st));
     if (!b->device_current || st != b->solstate) {
       PetscCall(B200HostToDevice_Private(ns));
-      b->solstate = st;
+      PetscCall(PetscObjectStateGet((PetscObject)ns->sol, &b->solstate)); /* after the upload: restoring the sub-vectors of a VecNest bumps its state */
     }
   }
   PetscCall(B200UploadBoundaryData_Private(ns));
