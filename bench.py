@@ -384,6 +384,46 @@ def parity_selfcheck(ctx, lib):
     return {"ok": bool(ok), "ranks": world, "tolerance": "rel. L2 <= 1e-10 (v, U), 1e-9 (p) against the CPU oracle at tight tolerances", "case": f"sphere workload builder at {nx}x{ny}x{nz} (inflow/outlet/symmetry, 300 IBM markers), coupled mode, {world} z-slab(s) over {'NCCL' if world > 1 else 'one GPU'}; ABF factor variants schur/upper", "runs": res, "oracle": "this repo's restatement, pinned to the reference's own NS sources compiled on a PETSc model (operators, RHS, ABF, steps: tests/test_oracle_vs_reference.py); PETSc's solver arithmetic and the IBM section are unpinned (DESIGN.md 2)"}
 
 
+def reference_selfcheck(lib):
+    """Rank 0 only, untimed, no collective: the library about to be timed against the REFERENCE'S OWN compiled NS sources
+    (oracle/_ref/libfluca_ref_ns.so: cartdiscret.c, cnlinear*.c, abfpc.c of thecasterian/fluca on a single-rank PETSc model, built in the
+    container where /root/reference lives and shipped with the repo).  The sphere workload's box and boundary set
+    (inflow / pressure outlet / symmetry) without markers -- the reference has no IBM -- at 8 x 5 x 5, two steps: one ABF application per
+    step against -ns_ksp_type preonly, and the coupled solve against the exact solution of the reference's J x = b."""
+    import fluca_b200 as fb
+    from fluca_b200 import workloads as W
+
+    from oracle import ref as R  # checker
+
+    if not os.path.exists(R.LIB):
+        return {"available": False, "note": "oracle/_ref/libfluca_ref_ns.so is not on this machine (it is built from /root/reference)"}
+    from oracle import oracle as O  # its BC container only
+
+    case = W.sphere_bench_case(5, 5)
+    case.n, case.dt, case.hi = (8, 5, 5), 0.5 * 16.0 / 8, (12.0, 8.0, 8.0)
+    state = W.uniform_inflow_state(case)
+    tight = {"ns_ksp_rtol": 1e-13, "ns_abf_momentum_ksp_rtol": 1e-13, "ns_abf_schur_ksp_rtol": 1e-13, "ns_ksp_max_it": 60}
+
+    def rel(a, b):
+        return float(np.linalg.norm((np.asarray(a) - np.asarray(b)).ravel()) / max(np.linalg.norm(np.asarray(b).ravel()), 1e-300))
+
+    res, ok = {}, True
+    for mode, rmode in (("fractional", R.ABF_ONCE), ("coupled", R.EXACT)):
+        ref = R.Reference(case.n, case.faces(), case.rho, case.mu, case.dt, [O.BC(b["type"], velocity=b["velocity"], pressure=b["pressure"]) for b in case.bcs])
+        ref.set_state(*state)
+        ns = W.make_ns(case, lib, mode, **tight)
+        W.set_initial(ns, state)
+        for _ in range(2):
+            ref.step(mode=rmode)
+            fb.NSStep(ns)
+        a, g = ref.get_state(), fb.NSB200GetSolver(ns).get_state()
+        fb.NSDestroy(ns)
+        eU = float(np.sqrt(sum(np.sum((x - y) ** 2) for x, y in zip(g["U"], a["U"]))) / np.sqrt(sum(np.sum(y**2) for y in a["U"])))
+        res[mode] = dict(v=rel(g["v"], a["v"]), U=eU, p=rel(g["p"], a["p"]), phalf=rel(g["phalf"], a["phalf"]))
+        ok = ok and res[mode]["v"] <= 1e-10 and eU <= 1e-10 and res[mode]["p"] <= 1e-9
+    return {"available": True, "ok": bool(ok), "against": "the reference's own NS sources (cartdiscret.c, cnlinear*.c, abfpc.c) compiled on a single-rank PETSc model with exact linear solves", "case": "sphere workload box and boundary set without markers, 8x5x5, 2 steps, rank 0's device", "runs": res}
+
+
 def e2e_resident_loop(ns, solver, ksteps, barrier, clock):
     """The time loop the PETSc glue runs with an output every step (glue/nsb200.c, -ns_b200_sync_interval 1), with the
     download taken off the critical path: the state stays on the device, each step's result is staged into pinned host
@@ -602,6 +642,11 @@ def run_b200(args, ctx=None, lib=None):
             parity = parity_selfcheck(ctx, lib)
         except Exception as exc:  # reported, never fatal for the timing that follows; every rank leaves the same way
             parity = {"ok": False, "error": repr(exc)[:300]}
+        if rank == 0 and isinstance(parity, dict):
+            try:
+                parity["reference_sources"] = reference_selfcheck(lib)
+            except Exception as exc:  # an extra: never fatal, never a collective
+                parity["reference_sources"] = {"available": True, "ok": False, "error": repr(exc)[:300]}
     ctx.barrier()
     if args.workload == "channel":
         order = ["weak"]  # config 5 is sized per GPU (268 M cells each); the full grid only exists at 8 GPUs

@@ -95,6 +95,8 @@ def test_gpu_arm_logic_on_the_test_double():
         assert key in d, key
     assert d["parity"]["ok"], d["parity"]
     assert set(d["parity"]["runs"]) == {"ID/ID", "DIAG/ROWSUM"}
+    rs = d["parity"]["reference_sources"]  # the same library against the reference's own compiled NS sources (where oracle/_ref exists)
+    assert rs["available"] is False or (rs["ok"] and set(rs["runs"]) == {"fractional", "coupled"}), rs
     assert d["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["value"] > 0 and d["gpu_launches"] > 0
     assert d["cpu_baseline"]["cores"] >= 1 and "absent" in d["cpu_baseline"]["reference_build"]
     assert d["config"]["workload"].startswith("BASELINE config 4")
