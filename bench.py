@@ -388,7 +388,7 @@ def reference_selfcheck(lib):
     """Rank 0 only, untimed, no collective: the library about to be timed against the REFERENCE'S OWN compiled NS sources
     (oracle/_ref/libfluca_ref_ns.so: cartdiscret.c, cnlinear*.c, abfpc.c of thecasterian/fluca on a single-rank PETSc model, built in the
     container where /root/reference lives and shipped with the repo).  The sphere workload's box and boundary set
-    (inflow / pressure outlet / symmetry) without markers -- the reference has no IBM -- at 8 x 5 x 5, two steps: one ABF application per
+    (inflow / pressure outlet / symmetry) without markers -- the reference has no IBM -- at 8 x 5 x 5, seeded smooth initial state, two steps: one ABF application per
     step against -ns_ksp_type preonly, and the coupled solve against the exact solution of the reference's J x = b."""
     import fluca_b200 as fb
     from fluca_b200 import workloads as W
@@ -401,7 +401,7 @@ def reference_selfcheck(lib):
 
     case = W.sphere_bench_case(5, 5)
     case.n, case.dt, case.hi = (8, 5, 5), 0.5 * 16.0 / 8, (12.0, 8.0, 8.0)
-    state = W.uniform_inflow_state(case)
+    state = case.initial_state(seed=5)  # a seeded smooth field: the uniform stream is an exact solution of the empty box (p = 0)
     tight = {"ns_ksp_rtol": 1e-13, "ns_abf_momentum_ksp_rtol": 1e-13, "ns_abf_schur_ksp_rtol": 1e-13, "ns_ksp_max_it": 60}
 
     def rel(a, b):
