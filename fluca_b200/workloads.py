@@ -209,6 +209,24 @@ def channel3d(n=(12, 8, 8), Re=300.0, dt=None, pout=0.0, periodic_z=False):
     return Case("channel3d", n, (-2, -2, -2), (4, 2, 2), 1.0, 1.0 / Re, dt, [inl, out, sym, sym, z, z])
 
 
+def channel3d_z(n=(6, 6, 8), Re=300.0, dt=None, pout=0.0):
+    """The same boundary set turned into z: inflow BACK, pressure outlet FRONT, symmetry elsewhere.  The outlet then sits on the last
+    z-slab of a multi-rank run, and on the upper boundary where the reference's 3-D file forms operator T in its own way
+    (cnlinearcart3d.c:2114)."""
+
+    def inflow(dim, t, x):
+        return (0.0, 0.0, 1.0 + 0.2 * math.cos(2 * math.pi * x[0] / 4.0))
+
+    def pressure(dim, t, x):
+        return pout * (1.0 + 0.1 * x[1])
+
+    inl = dict(type=BC_VELOCITY, velocity=inflow, pressure=None)
+    out = dict(type=BC_PRESSURE_OUTLET, velocity=None, pressure=pressure)
+    sym = dict(type=BC_SYMMETRY, velocity=None, pressure=None)
+    dt = dt if dt is not None else 0.5 * 6.0 / n[2]
+    return Case("channel3d_z", n, (-2, -2, -2), (2, 2, 4), 1.0, 1.0 / Re, dt, [sym, sym, sym, sym, inl, out])
+
+
 # ------------------------------------------------------------------ immersed-boundary marker sets
 def cylinder_markers(centre, D, n, h, Ud=(0.0, 0.0), npts=4):
     """n markers equally spaced in angle on a circle (BASELINE config 2: theta_k = 2 pi k / n, SURVEY.md 8d);

@@ -78,6 +78,8 @@ def main():
         lib = lib or fb._lib.load(parity.HOSTEMU)
     case = {
         "channel3d": lambda: cases.channel3d(n=(8, 6, 8), pout=0.2, dt=0.05),
+        "z_outlet": lambda: cases.channel3d_z(n=(6, 6, 8), pout=0.2, dt=0.05),
+        "z_outlet9": lambda: cases.channel3d_z(n=(6, 5, 9), pout=0.2, dt=0.05),
         "cavity3d": lambda: cases.cavity3d_full(n=(8, 8, 8)),
         "periodic_z": lambda: cases.channel3d(n=(8, 6, 8), periodic_z=True, dt=0.05),
         "uneven": lambda: cases.cavity3d_full(n=(8, 6, 7)),

@@ -44,6 +44,8 @@ def run_world(case_name, mode, world, tmp_path, backend="gloo", ainv=(0, 0)):
 
 CASEMAP = {
     "channel3d": lambda: cases.channel3d(n=(8, 6, 8), pout=0.2, dt=0.05),
+    "z_outlet": lambda: cases.channel3d_z(n=(6, 6, 8), pout=0.2, dt=0.05),
+    "z_outlet9": lambda: cases.channel3d_z(n=(6, 5, 9), pout=0.2, dt=0.05),
     "cavity3d": lambda: cases.cavity3d_full(n=(8, 8, 8)),
     "periodic_z": lambda: cases.channel3d(n=(8, 6, 8), periodic_z=True, dt=0.05),
     "uneven": lambda: cases.cavity3d_full(n=(8, 6, 7)),
@@ -71,7 +73,7 @@ def _oracle_reference(case_name, mode, ainv=(0, 0)):
 
 @pytest.mark.parametrize(
     "case_name,mode,world",
-    [("cavity3d", "coupled", 2), ("channel3d", "coupled", 2), ("periodic_z", "fractional", 2), ("uneven", "fractional", 2), ("three", "fractional", 3), ("sphere_ibm", "coupled", 2), ("sphere_ibm_periodic", "fractional", 3), ("channel5", "coupled", 2)],
+    [("cavity3d", "coupled", 2), ("channel3d", "coupled", 2), ("z_outlet", "coupled", 2), ("z_outlet9", "fractional", 3), ("periodic_z", "fractional", 2), ("uneven", "fractional", 2), ("three", "fractional", 3), ("sphere_ibm", "coupled", 2), ("sphere_ibm_periodic", "fractional", 3), ("channel5", "coupled", 2)],
 )
 def test_slab_partition_matches_oracle(case_name, mode, world, tmp_path):
     parity.hostemu_library()
@@ -112,7 +114,7 @@ def test_slab_partition_abf_variants_match_oracle(case_name, mode, world, ainv, 
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case_name,mode", [("cavity3d", "coupled"), ("channel3d", "coupled"), ("periodic_z", "fractional"), ("sphere_ibm", "coupled"), ("sphere_ibm_tma", "fractional")])
+@pytest.mark.parametrize("case_name,mode", [("cavity3d", "coupled"), ("channel3d", "coupled"), ("z_outlet", "coupled"), ("periodic_z", "fractional"), ("sphere_ibm", "coupled"), ("sphere_ibm_tma", "fractional")])
 def test_nccl_two_gpus_match_oracle(case_name, mode, tmp_path):
     """The same comparison with the CUDA library on 2 GPUs: NCCL halo exchange + allreduce."""
     import torch

@@ -132,6 +132,7 @@ def _live_cases():
         "cavity3d_full_6": (full, 23),
         "channel3d_10x6x6_stretched": (c3, 24),
         "channel3d_periodic_z_10x6x4": (cases.channel3d(n=(10, 6, 4), periodic_z=True), 25),
+        "channel3d_outlet_in_z_6x5x8": (cases.channel3d_z(n=(6, 5, 8), pout=0.3), 26),
     }
 
 
