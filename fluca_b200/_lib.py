@@ -63,6 +63,7 @@ class Stats(C.Structure):
         ("launches", C.c_long),
         ("mom_last_rel", C.c_double),
         ("schur_last_rel", C.c_double),
+        ("inner_unconverged", C.c_int),
     ]
 
 

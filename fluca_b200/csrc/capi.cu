@@ -189,6 +189,7 @@ void fill_stats(const Solver &s, fluca_b200_stats *st)
   for (int i = 0; i < s.stats.nhist && i < 128; ++i) st->hist[i] = s.stats.hist[i];
   st->launches     = s.stats.launches;
   st->mom_last_rel = s.stats.mom_last_rel, st->schur_last_rel = s.stats.schur_last_rel;
+  st->inner_unconverged = s.stats.inner_unconverged;
 }
 } // namespace
 

@@ -107,6 +107,7 @@ struct Stats {
   double hist[128];
   long   launches = 0;
   double mom_last_rel = 0., schur_last_rel = 0.;
+  int    inner_unconverged = 0;
 };
 
 struct Field {

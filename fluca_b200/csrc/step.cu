@@ -517,7 +517,7 @@ static void abf_apply_t(Solver &s, const V3 &bm, const V3 &bi, const double *bcn
   KScope ks(s.ex, KT_RHS_PROJECT);
   const Geom &g = s.gh.g;
   // stage 1 (abfpc.c:72-77): momentum solve, then U* = r_int + T v* and the Poisson right-hand side in ONE pass (FaceStarRhs)
-  momentum_solve(s, bm, s.vstar, guess, in_scale);
+  if (momentum_solve(s, bm, s.vstar, guess, in_scale)) ++s.stats.inner_unconverged;
   halo_cells(s, s.vstar);
   halo_faces(s, bi); // the upper z face of the slab's last plane is formed from r_int's ghost face plane and v*'s ghost plane
   FaceStarRhs<DIM> fs;
@@ -532,7 +532,7 @@ static void abf_apply_t(Solver &s, const V3 &bm, const V3 &bi, const double *bcn
     const Geom   gg   = g;
     for_box(s.ex, cell_box(s), FL_LAMBDA(int i, int j, int kl) { sr[gg.idx(i, j, kl)] -= mean; });
   }
-  poisson_solve(s, s.srhs, op);
+  if (poisson_solve(s, s.srhs, op)) ++s.stats.inner_unconverged;
   if (!s.has_outlet) remove_mean(s, op);
   // stage 2 (abfpc.c:80-101); the T*G~p terms of V cancel: V = V* - G~st p
   halo_scalar(s, op);

@@ -422,6 +422,7 @@ static PetscErrorCode NSStep_B200(NS ns)
   }
   PetscCheck(rc == FLUCA_B200_OK, PetscObjectComm((PetscObject)ns), PETSC_ERR_LIB, "fluca_b200: %s", fluca_b200_last_error());
   PetscCall(PetscInfo(ns, "b200 step %" PetscInt_FMT ": outer its %d, momentum its %d, Schur its %d, ABF applications %d, |r|/|r0| %g\n", ns->step, b->stats.outer_its, b->stats.mom_its, b->stats.schur_its, b->stats.abf_applies, b->stats.outer_rnorm0 > 0 ? b->stats.outer_rnorm / b->stats.outer_rnorm0 : 0.));
+  if (b->stats.inner_unconverged) PetscCall(PetscInfo(ns, "b200 step %" PetscInt_FMT ": %d inner solve(s) ran into their iteration limit (last |r|/|b|: momentum %g, Schur %g)\n", ns->step, b->stats.inner_unconverged, b->stats.mom_last_rel, b->stats.schur_last_rel));
 
   if (b->ksp_monitor) {
     /* PETSc's KSPMonitorResidual format, one block per step; the inner solves report counts and final relative residuals

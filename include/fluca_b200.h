@@ -84,6 +84,8 @@ typedef struct {
   double hist[128];    /* outer true-residual history, the analogue of -ns_ksp_monitor */
   long   launches;     /* kernels + device copies launched by this step */
   double mom_last_rel, schur_last_rel;
+  int    inner_unconverged; /* inner solves of this step that ran into inner_maxit (PETSc's KSP inside PCApply_ABF would return
+                               KSP_DIVERGED_ITS without an error too; the count makes a stalled inner solve visible) */
 } fluca_b200_stats;
 
 const char *fluca_b200_last_error(void);

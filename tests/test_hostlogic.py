@@ -249,3 +249,20 @@ def test_restarted_outer_gmres_matches_oracle(lib, restart):
     a, b = orc.get_state(), fb.NSB200GetSolver(ns).get_state()
     assert parity.rel(b["v"], a["v"]) < 1e-10 and parity.relU(b["U"], a["U"]) < 1e-10 and parity.rel(b["p"], a["p"]) < 1e-9
     fb.NSDestroy(ns)
+
+
+def test_a_stalled_inner_solve_is_reported(lib, monkeypatch):
+    """fluca_b200_stats.inner_unconverged counts the inner solves that ran into their iteration limit (PETSc's KSP inside
+    PCApply_ABF returns KSP_DIVERGED_ITS without an error as well; before, nothing told the caller)."""
+    case = cases.cavity3d_full(n=(8, 8, 8))
+    ns = parity.make_ns(case, lib, "fractional", ns_abf_ksp_max_it=2, **{k: v for k, v in parity.TIGHT.items()})
+    parity.set_initial(ns, case.initial_state(seed=3))
+    fb.NSStep(ns)
+    st = fb.NSB200GetStats(ns)
+    assert st.inner_unconverged == 2 and st.mom_its == 2 and st.schur_its == 2  # both solves of the one ABF application
+    fb.NSDestroy(ns)
+    ns = parity.make_ns(case, lib, "fractional", **parity.TIGHT)
+    parity.set_initial(ns, case.initial_state(seed=3))
+    fb.NSStep(ns)
+    assert fb.NSB200GetStats(ns).inner_unconverged == 0
+    fb.NSDestroy(ns)
