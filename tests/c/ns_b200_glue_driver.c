@@ -10,8 +10,10 @@
  *   usage: ns_b200_glue_driver case=<name> out=<file> [n=a,b[,c]] [steps=K] [steps2=K] [scenario=<s>] [stretch=x] [pout=x] [init=zero|smooth]
  *                              [-petsc_option[=value]] ...
  *   cases (fluca_b200/workloads.py): cavity2d cavity3d cavity3d_full tgv tgv_periodic channel2d channel2d_t channel3d channel3d_pz
- *   scenarios: plain | formfunction | edit | restart | stage
+ *   scenarios: plain | formfunction | edit | restart | stage;  markers=N: an immersed sphere of N Fibonacci-lattice markers (D = 1.2 at
+ *   (0.1, 0, 0.05), 4-point delta) through NSB200SetMarkers, marker forces through NSB200GetMarkerForces
  *   out: float64 [dim n0 n1 n2 nstate nf] + v (component-major, then z, y, x) U_x U_y [U_z] p phalf [+ the same blocks of f]
+ *        [+ with markers: F (dim x N) and U_m (dim x N)]
  */
 #include <math.h>
 #include <stdio.h>
@@ -259,7 +261,7 @@ static NS new_ns(const Case *c, Mesh mesh)
 int main(int argc, char **argv)
 {
   const char *casename = "cavity2d", *outname = NULL, *scenario = "plain", *init = "zero";
-  int         n_arg[3] = {0, 0, 0}, n_given = 0, steps = 2, steps2 = 1, a, d, k;
+  int         n_arg[3] = {0, 0, 0}, n_given = 0, steps = 2, steps2 = 1, a, d, k, nmark = 0;
   double      stretch = 0.;
   Case        c;
   Mesh        mesh;
@@ -278,6 +280,7 @@ int main(int argc, char **argv)
     else if (!strncmp(argv[a], "init=", 5)) init = argv[a] + 5;
     else if (!strncmp(argv[a], "steps=", 6)) steps = atoi(argv[a] + 6);
     else if (!strncmp(argv[a], "steps2=", 7)) steps2 = atoi(argv[a] + 7);
+    else if (!strncmp(argv[a], "markers=", 8)) nmark = atoi(argv[a] + 8);
     else if (!strncmp(argv[a], "stretch=", 8)) stretch = atof(argv[a] + 8);
     else if (!strncmp(argv[a], "pout=", 5)) pout = atof(argv[a] + 5);
     else if (!strncmp(argv[a], "nestbump=", 9)) MockSetNestRestoreBumpsState(atoi(argv[a] + 9));
@@ -326,7 +329,23 @@ int main(int argc, char **argv)
   }
 
   size_t  nstate = 0, nf = 0;
-  double *state = NULL, *fbuf = NULL;
+  double *state = NULL, *fbuf = NULL, *mark = NULL;
+  if (nmark > 0) { /* fluca_b200/workloads.py sphere_markers: Fibonacci lattice, volume weight = area / N x h; arrays are [component][marker] */
+    const double D = 1.2, ctr[3] = {0.1, 0., 0.05}, h = 4.0 / c.n[1];
+    double      *X = malloc(sizeof(double) * 3 * (size_t)nmark), *Ud = calloc(3 * (size_t)nmark, sizeof(double)), *dV = malloc(sizeof(double) * (size_t)nmark);
+    if (c.dim != 3) {
+      fprintf(stderr, "markers= needs a 3-D case\n");
+      return 2;
+    }
+    for (k = 0; k < nmark; ++k) {
+      const double kk = k + 0.5, z = 1. - 2. * kk / nmark, r = sqrt(fmax(0., 1. - z * z)), ph = M_PI * (1. + sqrt(5.)) * kk;
+      X[k] = ctr[0] + 0.5 * D * r * cos(ph), X[nmark + k] = ctr[1] + 0.5 * D * r * sin(ph), X[2 * nmark + k] = ctr[2] + 0.5 * D * z;
+      dV[k] = M_PI * D * D / nmark * h;
+    }
+    CHK(NSB200SetMarkers(ns, nmark, X, Ud, dV, 4));
+    free(X), free(Ud), free(dV);
+    mark = malloc(sizeof(double) * 6 * (size_t)nmark);
+  }
   /* sizes: count once with a scratch buffer large enough for any field set */
   {
     size_t cells = (size_t)(c.n[0] + 1) * (c.n[1] + 1) * (c.dim == 3 ? c.n[2] + 1 : 1);
@@ -385,6 +404,10 @@ int main(int argc, char **argv)
     fwrite(hdr, sizeof(double), 6, f);
     fwrite(state, sizeof(double), nstate, f);
     fwrite(fbuf, sizeof(double), nf, f);
+    if (nmark > 0) {
+      CHK(NSB200GetMarkerForces(ns, mark, mark + 3 * (size_t)nmark));
+      fwrite(mark, sizeof(double), 6 * (size_t)nmark, f);
+    }
     fclose(f);
   }
   printf("STEP %d TIME %.17g\n", (int)ns->step, ns->t);
@@ -393,7 +416,7 @@ int main(int argc, char **argv)
   CHK(PetscViewerDestroy(&ascii));
   CHK(NSDestroy(&ns));
   CHK(MeshDestroy(&mesh));
-  free(state), free(fbuf);
+  free(state), free(fbuf), free(mark);
   printf("LIVE %ld\n", MockLiveAllocations());
   return 0;
 }

@@ -74,6 +74,8 @@ def run(exe, name, tmp_path, n=None, stretch=0.0, pout=0.0, steps=2, steps2=1, s
     assert r.returncode == 0, r.stdout + r.stderr
     raw = np.fromfile(out)
     dim, nstate, nf = int(raw[0]), int(raw[4]), int(raw[5])
+    marks = raw[6 + nstate + nf :]
+    raw = raw[: 6 + nstate + nf]
     case = make_case(name, n, stretch, pout)
     cell, face = case.shapes()
     assert dim == case.dim and tuple(int(x) for x in raw[1 : 1 + dim]) == case.n
@@ -99,7 +101,7 @@ def run(exe, name, tmp_path, n=None, stretch=0.0, pout=0.0, steps=2, steps2=1, s
     lines = r.stdout.splitlines()
     info = {ln.split()[0]: ln.split()[1:] for ln in lines if ln.split() and ln.split()[0] in ("STEP", "BCCALLS", "G2L", "LIVE")}
     assert info["LIVE"] == ["0"], "the glue leaked PETSc objects or memory: " + r.stdout  # NSDestroy_B200 frees everything it made
-    return dict(case=case, state=split(raw[6 : 6 + nstate], True), f=split(raw[6 + nstate : 6 + nstate + nf], False) if nf else None, stdout=r.stdout, info=info)
+    return dict(case=case, state=split(raw[6 : 6 + nstate], True), f=split(raw[6 + nstate : 6 + nstate + nf], False) if nf else None, stdout=r.stdout, info=info, marks=marks)
 
 
 def smooth_state(case):
@@ -246,6 +248,25 @@ def test_base_class_with_the_matrix_free_hooks(exe_matrixfree, tmp_path):
     res = run(exe_matrixfree, "channel3d_pz", tmp_path, steps=2, init="smooth", opts=TIGHT)
     orc, _, _ = oracle_steps(res["case"], 2, state=smooth_state(res["case"]))
     assert_state(res["state"], orc.get_state())
+
+
+def test_immersed_boundary_through_the_glue(exe, tmp_path):
+    """NSB200SetMarkers / NSB200GetMarkerForces (the b200 type's own entry points: the reference has no IBM): a sphere of markers in
+    the inflow / outlet channel, two coupled steps; fields and marker forces against the oracle's definition of the coupling."""
+    nm = 150
+    res = run(exe, "channel3d", tmp_path, n=(12, 8, 8), pout=0.1, steps=2, init="smooth", opts=TIGHT, extra=[f"markers={nm}"])
+    case = res["case"]
+    mk = cases.sphere_markers((0.1, 0.0, 0.05), 1.2, nm, 4.0 / case.n[1])
+    orc = cases.make_oracle(case)
+    orc.set_state(*smooth_state(case))
+    orc.set_markers(mk["X"], mk["Ud"], mk["dV"], 4)
+    opt = O.default_options(mode=0, **parity.ORC_TIGHT)
+    for _ in range(2):
+        orc.step(opt)
+    assert_state(res["state"], orc.get_state())
+    F, Um = res["marks"][: 3 * nm].reshape(3, nm), res["marks"][3 * nm :].reshape(3, nm)
+    Fo, Uo = orc.marker_forces()
+    assert parity.rel(Um, Uo) <= 1e-10 and parity.rel(F, Fo) <= 1e-8
 
 
 def test_unknown_option_value_is_an_error(exe, tmp_path):

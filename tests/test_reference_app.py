@@ -151,3 +151,21 @@ def test_matrix_free_patch_compiled_into_the_references_base_class(tmp_path):
     # what the patch is for: no MatNest Jacobian (nsbasic.c:203-208) and no host copy sol -> sol0 per step (nsbasic.c:281-282) for b200
     assert trace["patched_cnlinear"].count("MatCreateNest") == 1 and trace["patched_cnlinear"].count("VecCopy of a nest") >= 3  # one per step (+ the model's solver)
     assert "MatCreateNest" not in trace["patched_b200"] and "VecCopy of a nest" not in trace["patched_b200"]
+
+
+@pytest.mark.skipif(not _ready("hostemu"), reason="oracle/_ref is not built here")
+def test_b200_at_its_default_tolerances_lands_on_the_references_converged_answer(tmp_path):
+    """cavity_flow_3d as a user would run it: -ns_type b200 with NO tolerance options (the reference's defaults, 1e-5, with the inner
+    solves relaxed by the inexact-Krylov rule) against the reference's cnlinear with every linear solve taken to convergence."""
+    args = ["-cart_grid_x", "8", "-cart_grid_y", "8", "-cart_grid_z", "5", "-ns_time_step_size", "0.06", "-ns_max_steps", "4", "-ns_monitor"]
+    dumps = {}
+    for tag, extra in (("cnlinear", []), ("b200", ["-dll_append", os.path.join(REFDIR, "hostemu", "libfluca_nsb200.so"), "-ns_type", "b200"])):
+        dump = str(tmp_path / f"{tag}.bin")
+        r = subprocess.run([os.path.join(REFDIR, "cavity_flow_3d")] + args + ["-ns_monitor_solution", f"flucacgns:{dump}"] + extra, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        dumps[tag] = load_dump(dump)
+    for k in ("Velocity", "FaceNormalVelocity"):
+        a, b = dumps["cnlinear"][k], dumps["b200"][k]
+        assert np.linalg.norm(a - b) <= 1e-4 * np.linalg.norm(a), (k, np.linalg.norm(a - b) / np.linalg.norm(a))
+    a, b = dumps["cnlinear"]["Pressure"], dumps["b200"]["Pressure"]
+    assert np.linalg.norm(a - b) <= 2e-3 * np.linalg.norm(a), np.linalg.norm(a - b) / np.linalg.norm(a)
