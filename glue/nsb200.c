@@ -45,6 +45,8 @@ typedef struct {
   double   *bccache[6][2];
   PetscBool bcvalid[6][2], bc_time_independent;
   PetscBool ksp_monitor;           /* -ns_ksp_monitor: print the outer residual history of every step in PETSc's format */
+  PetscBool no_bcg_quirk, no_t_outlet_quirk; /* the two places where the reference's 3-D file differs from its 2-D file (include/fluca_b200.h):
+                                                default PETSC_FALSE = do what cnlinearcart3d.c does */
   /* coherence between ns->sol (host) and the device state */
   PetscObjectState solstate;
   PetscBool        device_current, host_current;
@@ -272,6 +274,8 @@ static PetscErrorCode NSSetFromOptions_B200(NS ns, PetscOptionItems PetscOptions
    * applies that PC, so it reads the same two names and hands the choice to the device-side ABF factors */
   PetscCall(PetscOptionsEnum("-ns_pc_abf_schur_ainv_type", "Type of approximation used in Schur complement", "PCABFSetSchurComplementAinvType", PCABFAinvTypes, (PetscEnum)b->schur_ainv, (PetscEnum *)&b->schur_ainv, NULL));
   PetscCall(PetscOptionsEnum("-ns_pc_abf_upper_ainv_type", "Type of approximation used in upper triangular matrix", "PCABFSetUpperTriangularAinvType", PCABFAinvTypes, (PetscEnum)b->upper_ainv, (PetscEnum *)&b->upper_ainv, NULL));
+  PetscCall(PetscOptionsBool("-ns_b200_no_bcg_quirk", "3-D: scale the outlet-gradient BC vector by dt/rho as the 2-D file does (cnlinearcart3d.c:2977 uses 1)", "", b->no_bcg_quirk, &b->no_bcg_quirk, NULL));
+  PetscCall(PetscOptionsBool("-ns_b200_no_t_outlet_quirk", "3-D: form operator T at an upper pressure outlet as the 2-D file does (cnlinearcart3d.c:1996,2055,2114 read the partial element's slot)", "", b->no_t_outlet_quirk, &b->no_t_outlet_quirk, NULL));
   PetscCall(PetscOptionsBool("-ns_b200_bc_time_independent", "the boundary callbacks do not depend on time: evaluate them once", "", b->bc_time_independent, &b->bc_time_independent, NULL));
   /* the reference prints residual histories through the KSP of its SNES (-ns_ksp_monitor); this type owns its
    * outer Krylov solver, reads the same option name and prints the same lines */
@@ -369,6 +373,8 @@ static PetscErrorCode NSSetup_B200(NS ns)
   desc.outer_restart = (int)b->restart;
   desc.mom_rtol      = b->mom_rtol;
   desc.schur_rtol    = b->schur_rtol;
+  desc.no_bcg_quirk      = b->no_bcg_quirk ? 1 : 0;
+  desc.no_t_outlet_quirk = b->no_t_outlet_quirk ? 1 : 0;
 
   if (size > 1) { /* NCCL over the GPUs of the box: rank 0 makes the id, MPI ships it */
     char id[256];

@@ -269,6 +269,25 @@ def test_immersed_boundary_through_the_glue(exe, tmp_path):
     assert parity.rel(Um, Uo) <= 1e-10 and parity.rel(F, Fo) <= 1e-8
 
 
+def test_the_3d_quirks_of_the_reference_are_options(exe, tmp_path):
+    """-ns_b200_no_t_outlet_quirk / -ns_b200_no_bcg_quirk select the 2-D file's form of the two places where cnlinearcart3d.c differs
+    (operator T at an upper outlet, scaling of the outlet-gradient BC vector); the default is what the reference's 3-D file does."""
+    res = run(exe, "channel3d", tmp_path, n=(8, 6, 5), pout=0.3, steps=2, init="smooth", opts=TIGHT + ["-ns_b200_no_t_outlet_quirk", "-ns_b200_no_bcg_quirk"])
+    case = res["case"]
+    try:
+        O.set_t_outlet_quirk(False)
+        orc = cases.make_oracle(case)
+    finally:
+        O.set_t_outlet_quirk(True)
+    orc.set_state(*smooth_state(case))
+    opt = O.default_options(mode=0, quirk_bcg_scale=0, **parity.ORC_TIGHT)
+    for _ in range(2):
+        orc.step(opt)
+    assert_state(res["state"], orc.get_state())
+    dflt = run(exe, "channel3d", tmp_path, n=(8, 6, 5), pout=0.3, steps=2, init="smooth", opts=TIGHT)
+    assert parity.rel(dflt["state"]["v"], res["state"]["v"]) > 1e-4  # the quirks do change the answer
+
+
 def test_unknown_option_value_is_an_error(exe, tmp_path):
     r = subprocess.run([exe, "case=cavity2d", f"out={tmp_path / 'x.bin'}", "-ns_pc_abf_schur_ainv_type=nonsense"], capture_output=True, text=True)
     assert r.returncode != 0 and "unknown value" in r.stderr
