@@ -21,8 +21,7 @@
 #include <flucaviewer.h>
 #include <petscdmstag.h>
 #include <fluca_b200.h>
-
-#define NSB200 "b200"
+#include "flucansb200.h"
 
 typedef struct {
   fluca_b200_solver *solver;

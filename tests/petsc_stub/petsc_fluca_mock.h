@@ -39,13 +39,9 @@ PetscErrorCode NSViewSolution(NS ns, PetscViewer viewer);
 PetscErrorCode NSLoadSolution(NS ns, PetscViewer viewer);
 PetscErrorCode NSDestroy(NS *ns);
 
-/* the entry points of glue/nsb200.c that are not NSOps */
-PetscErrorCode NSCreate_B200(NS ns);
+/* the entry points of glue/nsb200.c that are not NSOps: the type's public header, and the plugin hook PETSc looks up by name */
+#include "../../glue/flucansb200.h"
 PetscErrorCode PetscDLLibraryRegister_fluca_nsb200(void);
-PetscErrorCode NSB200SetMarkers(NS ns, PetscInt n, const PetscReal X[], const PetscReal Ud[], const PetscReal dV[], PetscInt delta_points);
-PetscErrorCode NSB200StageSolution(NS ns);
-PetscErrorCode NSB200SyncSolution(NS ns);
-PetscErrorCode NSB200GetMarkerForces(NS ns, PetscReal F[], PetscReal Um[]);
 
 /* Vec helpers a driver uses */
 PetscErrorCode VecSet(Vec v, PetscScalar a);
