@@ -93,7 +93,8 @@ struct _p_PetscObject {
   int                       tablevel;
   struct composed_object   *olist;
   struct composed_function *flist;
-  PetscErrorCode (*destroy_model)(struct _p_PetscObject *); /* how PetscObjectDereference frees a composed object */
+  PetscErrorCode (*destroy_model)(struct _p_PetscObject *);  /* how PetscObjectDereference frees a composed object of the model ... */
+  PetscErrorCode (*destroy_public)(struct _p_PetscObject **); /* ... and one made by PetscHeaderCreate (its XxxDestroy(Xxx *)) */
 };
 typedef struct _p_PetscObject *PetscObject;
 #define PETSCHEADER(ObjectOps) \
@@ -254,9 +255,9 @@ PetscErrorCode ModelFunctionListFind(PetscFunctionList, const char[], void (**)(
 PetscErrorCode PetscFunctionListDestroy(PetscFunctionList *);
 #define PetscFunctionListAdd(list, name, f) ModelFunctionListAdd(list, name, (void (*)(void))(f))
 #define PetscFunctionListFind(list, name, f) ModelFunctionListFind(list, name, (void (**)(void))(f))
-PetscErrorCode ModelHeaderCreate(void *pobj, size_t size, PetscClassId, const char cls[], MPI_Comm);
+PetscErrorCode ModelHeaderCreate(void *pobj, size_t size, PetscClassId, const char cls[], MPI_Comm, PetscErrorCode (*destroy)(struct _p_PetscObject **));
 PetscErrorCode ModelHeaderDestroy(void *pobj);
-#define PetscHeaderCreate(h, classid, class_name, descr, mansec, comm, destroy, view) ModelHeaderCreate((void *)&(h), sizeof(*(h)), classid, class_name, comm)
+#define PetscHeaderCreate(h, classid, class_name, descr, mansec, comm, destroy, view) ModelHeaderCreate((void *)&(h), sizeof(*(h)), classid, class_name, comm, (PetscErrorCode(*)(struct _p_PetscObject **))(destroy))
 #define PetscHeaderDestroy(h) ModelHeaderDestroy((void *)(h))
 PetscErrorCode PetscObjectChangeTypeName(PetscObject, const char[]);
 PetscErrorCode PetscObjectGetName(PetscObject, const char *[]);

@@ -103,7 +103,7 @@ void ModelHeaderFree(void *o)
   while (h->olist) {
     struct composed_object *c = h->olist;
     h->olist                  = c->next;
-    if (c->obj && c->obj->destroy_model) c->obj->destroy_model(c->obj);
+    if (c->obj) PetscObjectDereference(c->obj);
     free(c->name), free(c);
   }
   while (h->flist) {
@@ -136,7 +136,7 @@ PetscErrorCode PetscObjectCompose(PetscObject o, const char name[], PetscObject 
     if (!strcmp((*pc)->name, name)) break;
   if (*pc) {
     c = *pc;
-    if (c->obj && c->obj->destroy_model) c->obj->destroy_model(c->obj);
+    if (c->obj) PetscObjectDereference(c->obj);
     if (!x) {
       *pc = c->next;
       free(c->name), free(c);

@@ -209,12 +209,12 @@ PetscErrorCode PetscFunctionListDestroy(PetscFunctionList *list)
   }
   return PETSC_SUCCESS;
 }
-PetscErrorCode ModelHeaderCreate(void *pobj, size_t size, PetscClassId classid, const char cls[], MPI_Comm comm)
+PetscErrorCode ModelHeaderCreate(void *pobj, size_t size, PetscClassId classid, const char cls[], MPI_Comm comm, PetscErrorCode (*destroy)(struct _p_PetscObject **))
 {
   void *o = calloc(1, size);
   PetscCheck(o, 0, 55, "out of memory");
   ModelHeaderInit(o, classid, cls, NULL, NULL);
-  ((PetscObject)o)->comm = comm;
+  ((PetscObject)o)->comm = comm, ((PetscObject)o)->destroy_public = destroy;
   *(void **)pobj         = o;
   return PETSC_SUCCESS;
 }
@@ -236,6 +236,7 @@ PetscErrorCode PetscObjectPrintClassNamePrefixType(PetscObject o, PetscViewer v)
 PetscErrorCode PetscObjectDereference(PetscObject o)
 {
   if (o && o->destroy_model) return o->destroy_model(o);
+  if (o && o->destroy_public) return o->destroy_public(&o);
   return PETSC_SUCCESS;
 }
 
