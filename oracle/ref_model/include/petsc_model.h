@@ -116,7 +116,7 @@ typedef struct _n_PetscFunctionList      *PetscFunctionList;
 typedef struct _p_PetscViewerAndFormat    PetscViewerAndFormat;
 typedef struct _n_PetscOptions           *PetscOptions;
 typedef int                               PetscViewerFormat;
-typedef int                               PetscFileMode;
+typedef enum { FILE_MODE_UNDEFINED = -1, FILE_MODE_READ = 0, FILE_MODE_WRITE, FILE_MODE_APPEND, FILE_MODE_UPDATE, FILE_MODE_APPEND_UPDATE } PetscFileMode;
 
 /* petsc/private/pcimpl.h: what a PC implementation touches */
 struct _PCOps {

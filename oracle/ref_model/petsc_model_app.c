@@ -337,10 +337,53 @@ PetscErrorCode PetscMonitorCompare(PetscErrorCode (*nmon)(void), void *nmctx, Pe
    vector's DM, and keeps a copy in memory so that a later load finds it (restart) */
 PetscErrorCode MeshView_Cart_CGNS(void *mesh, PetscViewer v) { return (void)mesh, (void)v, PETSC_SUCCESS; }
 PetscErrorCode MeshLoad_Cart_CGNS(void *mesh, PetscViewer v) { return (void)mesh, (void)v, PETSC_ERR_SUP; }
+/* the reference's public constructor of its CGNS viewer (flucaviewer.h): here the stand-in; FILE_MODE_READ loads the dump */
+PetscErrorCode MeshSetOutputSequenceNumber(void *mesh, PetscInt num, PetscReal val); /* meshbasic.c:198-212 */
+PetscErrorCode MeshGetOutputSequenceNumber(void *mesh, PetscInt *num, PetscReal *val);
+PetscErrorCode PetscViewerFlucaCGNSOpen(MPI_Comm comm, const char path[], PetscFileMode mode, PetscViewer *viewer)
+{
+  (void)comm;
+  *viewer = (PetscViewer)calloc(1, sizeof(**viewer));
+  ModelHeaderInit(*viewer, 31, "PetscViewer", "flucacgns", NULL);
+  (*viewer)->path = strdup(path);
+  (*viewer)->step = -1;
+  if (mode == FILE_MODE_READ) {
+    FILE *f = fopen(path, "rb");
+    char  name[256];
+    int   n;
+    PetscCheck(f, 0, PETSC_ERR_LIB, "cannot read %s", path);
+    free((*viewer)->path), (*viewer)->path = NULL; /* a reader never rewrites its file */
+    while (fgets(name, sizeof(name), f)) {
+      struct stored_vec *s = (struct stored_vec *)calloc(1, sizeof(*s));
+      name[strcspn(name, "\n")] = 0;
+      if (!strcmp(name, "@sequence")) { /* the output sequence number the writer's mesh carried (cartcgns.c:331, :714-724) */
+        double t;
+        free(s);
+        char line[256];
+        PetscCheck(fgets(line, sizeof(line), f) && sscanf(line, "%d %lf", &n, &t) == 2, 0, PETSC_ERR_LIB, "bad sequence record in %s", path);
+        (*viewer)->step = n, (*viewer)->time = t;
+        continue;
+      }
+      {
+        char line[256]; /* not fscanf("%d\n"): its trailing white space would eat payload bytes that happen to be blanks */
+        PetscCheck(fgets(line, sizeof(line), f) && sscanf(line, "%d", &n) == 1, 0, PETSC_ERR_LIB, "bad record in %s", path);
+      }
+      s->name = strdup(name), s->n = n, s->a = (double *)calloc((size_t)n, sizeof(double));
+      PetscCheck(fread(s->a, sizeof(double), (size_t)n, f) == (size_t)n, 0, PETSC_ERR_LIB, "short record in %s", path);
+      (void)fgetc(f);
+      s->next = (*viewer)->store, (*viewer)->store = s;
+    }
+    fclose(f);
+  }
+  return PETSC_SUCCESS;
+}
 PetscErrorCode VecView_Cart_Local_CGNS(Vec v, PetscViewer w)
 {
   struct stored_vec *s;
   const char        *name = v->hdr.name ? v->hdr.name : "";
+  PetscObject        mesh = NULL;
+  PetscCall(PetscObjectQuery((PetscObject)v, "Fluca_Mesh", &mesh)); /* cart.c:225: every mesh vector knows its mesh */
+  if (mesh) PetscCall(MeshGetOutputSequenceNumber(mesh, &w->step, &w->time));
   for (s = w->store; s; s = s->next)
     if (!strcmp(s->name, name)) break;
   if (!s) {
@@ -353,6 +396,7 @@ PetscErrorCode VecView_Cart_Local_CGNS(Vec v, PetscViewer w)
   if (w->path) { /* rewrite the whole file: the latest copy of every vector */
     FILE *f = fopen(w->path, "wb");
     PetscCheck(f, 0, PETSC_ERR_LIB, "cannot write %s", w->path);
+    fprintf(f, "@sequence\n%d %.17g\n", (int)w->step, w->time);
     for (s = w->store; s; s = s->next) {
       fprintf(f, "%s\n%d\n", s->name, (int)s->n);
       fwrite(s->a, sizeof(double), (size_t)s->n, f);
@@ -370,6 +414,16 @@ PetscErrorCode VecLoad_Cart_CGNS(Vec v, PetscViewer w)
   PetscCheck(s && s->n == v->n, 0, PETSC_ERR_ARG_WRONG, "no stored vector named %s", v->hdr.name ? v->hdr.name : "(unnamed)");
   memcpy(v->a, s->a, sizeof(double) * (size_t)v->n);
   ++v->hdr.state;
+  { /* cartcgns.c:714-724: the first vector loaded sets the mesh's output sequence number from the file */
+    PetscObject mesh = NULL;
+    PetscInt    step;
+    PetscReal   time;
+    PetscCall(PetscObjectQuery((PetscObject)v, "Fluca_Mesh", &mesh));
+    if (mesh) {
+      PetscCall(MeshGetOutputSequenceNumber(mesh, &step, &time));
+      if (step == -1 && time == 0.) PetscCall(MeshSetOutputSequenceNumber(mesh, w->step, w->time));
+    }
+  }
   return PETSC_SUCCESS;
 }
 PetscErrorCode FlucaVecLoad(Vec v, PetscViewer w) { return v->load_op ? v->load_op(v, w) : VecLoad_Cart_CGNS(v, w); }

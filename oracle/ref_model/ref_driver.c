@@ -42,6 +42,8 @@ PetscErrorCode MeshCreateMatrix(Mesh m, MeshDMType rt, MeshDMType ct, Mat *A)
   return PETSC_SUCCESS;
 }
 PetscErrorCode MeshGetNumberBoundaries(Mesh m, PetscInt *nb) { return *nb = 2 * m->dim, PETSC_SUCCESS; }
+PetscErrorCode MeshSetOutputSequenceNumber(Mesh m, PetscInt num, PetscReal val) { return (void)m, (void)num, (void)val, PETSC_SUCCESS; } /* no viewers here */
+PetscErrorCode MeshGetOutputSequenceNumber(Mesh m, PetscInt *num, PetscReal *val) { return (void)m, *num = -1, *val = 0., PETSC_SUCCESS; }
 static Mesh mesh_create(int dim, const int N[3], const int per[3], const double *const xf[3])
 {
   Mesh m = (Mesh)calloc(1, sizeof(*m));

@@ -39,6 +39,9 @@ def load_dump(path):
     while i < len(b):
         j = b.index(b"\n", i)
         k = b.index(b"\n", j + 1)
+        if b[i:j] == b"@sequence":  # step and time of the mesh when the file was written
+            i = k + 1
+            continue
         n = int(b[j + 1 : k])
         out[b[i:j].decode()] = np.frombuffer(b[k + 1 : k + 1 + 8 * n], dtype=np.float64).copy()
         i = k + 1 + 8 * n + 1
@@ -169,3 +172,29 @@ def test_b200_at_its_default_tolerances_lands_on_the_references_converged_answer
         assert np.linalg.norm(a - b) <= 1e-4 * np.linalg.norm(a), (k, np.linalg.norm(a - b) / np.linalg.norm(a))
     a, b = dumps["cnlinear"]["Pressure"], dumps["b200"]["Pressure"]
     assert np.linalg.norm(a - b) <= 2e-3 * np.linalg.norm(a), np.linalg.norm(a - b) / np.linalg.norm(a)
+
+
+@pytest.mark.skipif(not (_ready("hostemu") and os.path.exists(os.path.join(REFDIR, "ref_restart_app"))), reason="oracle/_ref is not built here")
+@pytest.mark.parametrize("writer,reader", [("cnlinear", "b200"), ("b200", "cnlinear"), ("b200", "b200")])
+def test_restart_files_are_interchangeable_between_cnlinear_and_b200(tmp_path, writer, reader):
+    """tests/c/ref_restart_app.c (written against the reference's public API, linked with the reference's own libraries): two steps
+    with one NS type, NSViewSolution; a second process with the other type, NSLoadSolution, two more steps.  The reference's
+    NSLoadSolution restores step and time from the file and the type's extra state travels as "PressureHalfStep"
+    (cnlinear.c:54,146-162; NSViewSolution_B200 / NSLoadSolution_B200), so the continued run equals four uninterrupted cnlinear steps."""
+    exe = os.path.join(REFDIR, "ref_restart_app")
+    plug = ["-dll_append", os.path.join(REFDIR, "hostemu", "libfluca_nsb200.so"), "-ns_type", "b200"] + TIGHT
+    common = ["-ns_time_step_size", "0.06"]
+
+    def go(mode, path, steps, kind):
+        r = subprocess.run([exe, mode, path] + common + ["-ns_max_steps", str(steps)] + (plug if kind == "b200" else []), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        return r.stdout
+
+    full, half = str(tmp_path / "full.bin"), str(tmp_path / "half.bin")
+    go("write", full, 4, "cnlinear")
+    go("write", half, 2, writer)
+    out = go("read", half, 4, reader)
+    assert "finished at step 4 time 0.24" in out  # step and time came back from the file (nssol.c:200-202)
+    a, b = load_dump(full), load_dump(half + ".out")
+    for k in ("Velocity", "FaceNormalVelocity", "Pressure", "PressureHalfStep"):
+        assert np.abs(a[k] - b[k]).max() <= (1e-9 if k.startswith("Pressure") else 1e-10) * np.abs(a[k]).max(), (k, writer, reader)
