@@ -9,11 +9,14 @@
  *
  *   ref_restart_app write <file> [options]   zero state, NSSolve to -ns_max_steps, NSViewSolution into <file>
  *   ref_restart_app read  <file> [options]   NSLoadSolution from <file>, NSSolve on to -ns_max_steps, NSViewSolution into <file>.out
+ *   -stretch s : a non-uniform mesh through the reference's public coordinate API (MeshCartGetCoordinateArrays / Restore, cart.c:467-502):
+ *                face k/n moves to k/n + s sin(2 pi k/n) / (2 pi) in every direction
  */
 #include <flucameshcart.h>
 #include <flucans.h>
 #include <flucasys.h>
 #include <flucaviewer.h>
+#include <math.h>
 #include <string.h>
 
 static PetscErrorCode wall_velocity(PetscInt dim, PetscReal t, const PetscReal x[], PetscScalar val[], void *ctx)
@@ -44,6 +47,24 @@ int main(int argc, char **argv)
   PetscCall(MeshSetFromOptions(mesh));
   PetscCall(MeshSetUp(mesh));
   PetscCall(MeshCartSetUniformCoordinates(mesh, 0., 1., 0., 1., 0., 0.5));
+  {
+    PetscReal     stretch = 0.;
+    PetscScalar **a[3];
+    PetscInt      N[3], iprev, d, i;
+    PetscCall(PetscOptionsGetReal(NULL, NULL, "-stretch", &stretch, NULL));
+    if (stretch != 0.) {
+      const double len[3] = {1., 1., 0.5};
+      PetscCall(MeshCartGetGlobalSizes(mesh, &N[0], &N[1], &N[2]));
+      PetscCall(MeshCartGetCoordinateLocationSlot(mesh, MESHCART_PREV, &iprev));
+      PetscCall(MeshCartGetCoordinateArrays(mesh, &a[0], &a[1], &a[2]));
+      for (d = 0; d < 3; ++d)
+        for (i = 0; i <= N[d]; ++i) {
+          const double s = (double)i / N[d];
+          a[d][i][iprev] = len[d] * (s + stretch * sin(2. * M_PI * s) / (2. * M_PI));
+        }
+      PetscCall(MeshCartRestoreCoordinateArrays(mesh, &a[0], &a[1], &a[2])); /* recomputes the centres */
+    }
+  }
   PetscCall(NSCreate(PETSC_COMM_WORLD, &ns));
   PetscCall(NSSetType(ns, NSCNLINEAR));
   PetscCall(NSSetMesh(ns, mesh));

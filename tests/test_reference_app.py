@@ -198,3 +198,22 @@ def test_restart_files_are_interchangeable_between_cnlinear_and_b200(tmp_path, w
     a, b = load_dump(full), load_dump(half + ".out")
     for k in ("Velocity", "FaceNormalVelocity", "Pressure", "PressureHalfStep"):
         assert np.abs(a[k] - b[k]).max() <= (1e-9 if k.startswith("Pressure") else 1e-10) * np.abs(a[k]).max(), (k, writer, reader)
+
+
+@pytest.mark.skipif(not (_ready("hostemu") and os.path.exists(os.path.join(REFDIR, "ref_restart_app"))), reason="oracle/_ref is not built here")
+def test_non_uniform_mesh_through_the_references_coordinate_api(tmp_path):
+    """A stretched mesh set through MeshCartGetCoordinateArrays / MeshCartRestoreCoordinateArrays (cart.c:467-502) of the reference's
+    own Mesh implementation: the glue reads the face coordinates back through MeshCartGetCoordinateArraysRead and b200 reproduces
+    cnlinear on it."""
+    exe = os.path.join(REFDIR, "ref_restart_app")
+    plug = ["-dll_append", os.path.join(REFDIR, "hostemu", "libfluca_nsb200.so"), "-ns_type", "b200"] + TIGHT
+    dumps = {}
+    for tag, extra in (("cnlinear", ["-stretch", "0.3"]), ("b200", ["-stretch", "0.3"] + plug), ("uniform", [])):
+        path = str(tmp_path / f"{tag}.bin")
+        r = subprocess.run([exe, "write", path, "-ns_time_step_size", "0.06", "-ns_max_steps", "3"] + extra, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        dumps[tag] = load_dump(path)
+    for k in dumps["cnlinear"]:
+        a, b = dumps["cnlinear"][k], dumps["b200"][k]
+        assert np.abs(a - b).max() <= (1e-9 if k.startswith("Pressure") else 1e-10) * np.abs(a).max(), k
+    assert np.abs(dumps["cnlinear"]["Velocity"] - dumps["uniform"]["Velocity"]).max() > 1e-2  # the stretching did reach the solver
