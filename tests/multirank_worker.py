@@ -60,6 +60,39 @@ def make_comm_factory(rank, nranks):
     return factory
 
 
+def random_case3d(seed):
+    """A random 3-D mesh / boundary set with at least 3 planes per slab for up to 3 ranks (tests/test_multirank_gloo.py)."""
+    import math
+
+    from fluca_b200.workloads import BC_PERIODIC, BC_PRESSURE_OUTLET, BC_SYMMETRY, BC_VELOCITY, Case
+
+    rng = np.random.default_rng(seed)
+    n = (int(rng.integers(4, 9)), int(rng.integers(4, 8)), int(rng.integers(9, 13)))
+    lo = tuple(float(rng.uniform(-2, 0)) for _ in range(3))
+    hi = tuple(x + float(rng.uniform(1, 4)) for x in lo)
+    a = [float(rng.uniform(-1, 1)) for _ in range(8)]
+    plan = []
+    for _ in range(3):
+        kind = rng.choice(["per", "walls", "mixed"], p=[0.25, 0.25, 0.5])
+        plan.append([BC_PERIODIC] * 2 if kind == "per" else [int(rng.choice([BC_VELOCITY, BC_PRESSURE_OUTLET, BC_SYMMETRY], p=[0.5, 0.25, 0.25])) if kind == "mixed" else BC_VELOCITY for _ in range(2)])
+    free = any(t == BC_PRESSURE_OUTLET for p in plan for t in p)
+
+    def make_vel(dn):
+        def vel(dim, t, x):
+            return tuple(((a[c] + a[c + 3] * math.sin(1.3 * t + 0.7 * x[(c + 1) % dim])) if (free or c != dn) else 0.0) for c in range(dim))
+
+        return vel
+
+    def prs(dim, t, x):
+        return a[6] * (1 + 0.3 * math.cos(2 * t)) * (1 + 0.2 * x[0] - 0.1 * x[2])
+
+    bcs = [dict(type=plan[d][s], velocity=make_vel(d) if plan[d][s] == BC_VELOCITY else None, pressure=prs if plan[d][s] == BC_PRESSURE_OUTLET else None) for d in range(3) for s in range(2)]
+    h = min((hi[d] - lo[d]) / n[d] for d in range(3))
+    case = Case("random3d", n, lo, hi, float(rng.uniform(0.5, 2)), float(rng.uniform(0.01, 0.2)), float(rng.uniform(0.1, 0.3)) * h, bcs)
+    case.stretch = float(rng.choice([0.0, 0.2]))
+    return case
+
+
 def main():
     case_name, mode, out_path = sys.argv[1], sys.argv[2], sys.argv[3]
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -89,7 +122,7 @@ def main():
         "sphere_ibm_tma": lambda: cases.channel3d(n=(40, 16, 16), pout=0.1, dt=0.02),
         "sphere_ibm_periodic": lambda: cases.channel3d(n=(12, 8, 12), periodic_z=True, dt=0.05),
         "channel5": lambda: cases.channel_bench_case((8, 6, 8), periodic_z=True),  # BASELINE config 5's boundary set: periodic x and z, walls in y
-    }[case_name]()
+    }.get(case_name, lambda: random_case3d(int(case_name.split(":")[1])))()
     markers = None
     if case_name.startswith("sphere_ibm"):  # the body straddles the slab interface: gather and scatter both cross it
         markers = cases.sphere_markers((0.1, 0.0, 0.05), 1.2, 120, 4.0 / case.n[1])
