@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--upper-ainv", default="ID", choices=["ID", "DIAG", "ROWSUM"], help="-ns_pc_abf_upper_ainv_type (abfpc.c:247)")
     ap.add_argument("--cpu-n", type=int, default=64, help="cells per direction of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-sources", action="store_true", help="skip the timed sample of the reference's own sources (oracle/_ref) inside the CPU legs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed N-rank parity case against the oracle")
     a = ap.parse_args()
@@ -158,11 +159,12 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------- CPU arm
 def reference_build_probe():
     """a PETSc build of the reference may be provided on the GPU box; it never was.  oracle/_ref holds the
-    reference's NS sources compiled on a PETSc MODEL with dense solves: the checker of the oracle, not a timing baseline."""
+    reference's NS sources compiled on a single-rank PETSc MODEL: the checker of the oracle, and (cpu_baseline.reference_sources) a
+    one-core timing of the reference's own assembly + PCABF with the model's GMRES(30) + ILU(0) -- not a PETSc build."""
     petsc = os.environ.get("PETSC_DIR")
     ref = os.path.isdir(os.path.join(ROOT, "baseline", "_ref"))
     model = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libfluca_ref_ns.so"))
-    note = "; oracle/_ref = the reference's NS sources on a PETSc model (parity checker with dense solves, not timed)" if model else ""
+    note = "; oracle/_ref = the reference's NS sources on a single-rank PETSc model (parity checker; timed on one core as cpu_baseline.reference_sources)" if model else ""
     if petsc or ref:
         return f"present (PETSC_DIR={petsc!r}, baseline/_ref={ref}) but not used: no build recipe for the reference exists in this repo (it needs MPI, HDF5 and parallel CGNS as well)" + note
     return "absent (no $PETSC_DIR, no baseline/_ref): the reference needs PETSc >= 3.23 + MPI + HDF5 + CGNS; the CPU arm is the repo's C restatement (oracle/, kind 'port')" + note
@@ -204,7 +206,56 @@ def cpu_sample(args, n, steps, warmup, mode):
         infos.append(orc.step(opt))
     dt = time.perf_counter() - t0
     cells = float(n) ** 3
-    return dict(value=cells * steps / dt / 1e6, seconds=dt, steps=steps, warmup=warmup, n=n, threads=threads, markers=nm, outer=[i.outer_its for i in infos], mom=[i.mom_its for i in infos], schur=[i.schur_its for i in infos])
+    res = dict(value=cells * steps / dt / 1e6, seconds=dt, steps=steps, warmup=warmup, n=n, threads=threads, markers=nm, outer=[i.outer_its for i in infos], mom=[i.mom_its for i in infos], schur=[i.schur_its for i in infos])
+    res["reference_sources"] = reference_sources_sample(case, orc.get_state(), mode, args)
+    return res
+
+
+def reference_sources_sample(case, state, mode, args, budget_s=20.0):
+    """The REFERENCE'S OWN NS sources timed on the same sample: oracle/_ref/libfluca_ref_ns.so (cartdiscret.c, cnlinear*.c, abfpc.c
+    of thecasterian/fluca compiled on the single-rank PETSc model of oracle/ref_model/, built where /root/reference is and shipped
+    with the repo) with the solver stack a serial PETSc run has by default -- outer right-preconditioned GMRES(30) on the true
+    residual + PCABF with GMRES(30) + ILU(0) inside, rtol 1e-5 everywhere (ref_model/petsc_model_ksp.c) -- on ONE core.  It starts
+    from the flow field the port has just produced (for the sphere: the developing flow around the immersed body); the reference
+    has no immersed boundary, so its steps run without the forcing.  What is timed is the reference's assembly
+    (MatSetValuesStencil per entry, every step), its PCSetUp_ABF (three sparse products per step) and its solves on a MODEL of PETSc:
+    the reference's algorithm and code, not PETSc's performance.  Bounded: one warm-up step, then steps until 2 are done or
+    budget_s is spent.  Reported beside the port, never instead of it."""
+    try:
+        from oracle import ref as R
+
+        if getattr(args, "no_reference_sources", False):
+            return {"available": False, "note": "--no-reference-sources"}
+        if not os.path.exists(R.LIB):
+            return {"available": False, "note": "oracle/_ref/libfluca_ref_ns.so is not on this machine (it is built from /root/reference)"}
+        from oracle import oracle as O  # its BC container only
+
+        R.set_inner_solvers(True)
+        try:
+            ref = R.Reference(case.n, case.faces(), case.rho, case.mu, case.dt, [O.BC(b["type"], velocity=b["velocity"], pressure=b["pressure"]) for b in case.bcs])
+            ref.set_state(state["v"], state["U"], state["p"], state["phalf"])
+            rmode = R.GMRES_ABF if mode == "coupled" else R.ABF_ONCE
+            ref.step(mode=rmode, rtol=1e-5, maxit=200)  # warm-up
+            m0, s0 = ref.inner_iterations()
+            outer, t0 = [], time.perf_counter()
+            while len(outer) < 2 and (not outer or time.perf_counter() - t0 < budget_s / 2):
+                outer.append(int(ref.step(mode=rmode, rtol=1e-5, maxit=200)[0]))
+            dt = time.perf_counter() - t0
+            m1, s1 = ref.inner_iterations()
+            del ref
+        finally:
+            R.set_inner_solvers(False)
+        cells = float(np.prod(case.n))
+        return {
+            "available": True,
+            "value": cells * len(outer) / dt / 1e6,
+            "unit": "Mcell-updates/s",
+            "cores": 1,
+            "kind": "reference sources on a PETSc model",
+            "sample": f"{'x'.join(str(k) for k in case.n)} sample from the port's final state, no immersed boundary (the reference has none), 1 warm-up + {len(outer)} timed step(s) in {dt:.1f} s, outer its {outer}, momentum its {m1 - m0}, Schur its {s1 - s0} (GMRES(30) + ILU(0), rtol 1e-5)",
+        }
+    except Exception as e:  # the checker's library is optional equipment: never lose the line over it
+        return {"available": False, "error": f"{type(e).__name__}: {e}"}
 
 
 def run_reference(args):
@@ -231,7 +282,7 @@ def run_reference(args):
         "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": workload_text(args, case, "strong", 1, args.restart or 3, args.markers) + f"; CPU arm: bounded sample {n}^3 of the same case ({r['markers']} markers: scaled with the surface cell count)", "mode": args.mode},
-        "cpu_baseline": {"value": r["value"], "unit": "Mcell-updates/s", "cores": r["threads"], "kind": "port", "sample": f"{n}^3 sample of the workload, {r['warmup']} warm-up + {r['steps']} timed steps on {r['threads']} OpenMP threads (of {os.cpu_count()} host CPUs), outer its {r['outer']}, momentum its {r['mom']}, Schur its {r['schur']}", "reference_build": reference_build_probe()},
+        "cpu_baseline": {"value": r["value"], "unit": "Mcell-updates/s", "cores": r["threads"], "kind": "port", "sample": f"{n}^3 sample of the workload, {r['warmup']} warm-up + {r['steps']} timed steps on {r['threads']} OpenMP threads (of {os.cpu_count()} host CPUs), outer its {r['outer']}, momentum its {r['mom']}, Schur its {r['schur']}", "reference_build": reference_build_probe(), "reference_sources": r["reference_sources"]},
         "e2e": {"value": r["value"], "unit": "Mcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -694,7 +745,7 @@ def run_b200(args, ctx=None, lib=None):
     # ---- CPU baseline on the box's host cores (rank 0, N=1 only), bounded sample
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_sample(args, args.cpu_n, 3, 1, args.mode)
-        line["cpu_baseline"] = {"value": r["value"], "unit": "Mcell-updates/s", "cores": r["threads"], "kind": "port", "sample": f"{args.cpu_n}^3 sample of the workload (same BCs, dt=0.5h, mode={args.mode}, tolerances 1e-5), 1 warm-up + 3 timed steps in {r['seconds']:.1f} s on {r['threads']} OpenMP threads", "reference_build": reference_build_probe()}
+        line["cpu_baseline"] = {"value": r["value"], "unit": "Mcell-updates/s", "cores": r["threads"], "kind": "port", "sample": f"{args.cpu_n}^3 sample of the workload (same BCs, dt=0.5h, mode={args.mode}, tolerances 1e-5), 1 warm-up + 3 timed steps in {r['seconds']:.1f} s on {r['threads']} OpenMP threads", "reference_build": reference_build_probe(), "reference_sources": r["reference_sources"]}
     if rank == 0:
         print_json(json.dumps(line))
     if world > 1:

@@ -47,9 +47,17 @@ def lib():
         L.ref_matrix.restype = C.c_long
         L.ref_matrix.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_destroy.argtypes = [C.c_void_p]
+        L.ref_set_inner_solvers.argtypes = [C.c_int, C.c_double]
+        L.ref_inner_iterations.argtypes = [C.c_void_p, C.POINTER(C.c_long), C.POINTER(C.c_long)]
         L.ref_last_error.restype = C.c_char_p
         _lib = L
     return _lib
+
+
+def set_inner_solvers(iterative: bool, rtol: float = 1e-5) -> None:
+    """The KSPs inside the reference's PCABF: False = the model's exact solves (default, what the parity checks use), True =
+    GMRES(30) + ILU(0) at rtol 1e-5, serial PETSc's defaults (ref_model/petsc_model_ksp.c).  Process-wide."""
+    lib().ref_set_inner_solvers(1 if iterative else 0, float(rtol))
 
 
 class Reference:
@@ -143,6 +151,12 @@ class Reference:
         hist = np.zeros(256)
         self._check(lib().ref_step(self._h, int(mode), int(schur_ainv), int(upper_ainv), float(rtol), int(maxit), C.byref(its), C.byref(nh), hist.ctypes.data))
         return its.value, hist[: nh.value].copy()
+
+    def inner_iterations(self):
+        """(momentum, Schur) Krylov iterations of the iterative inner KSPs since creation"""
+        a, b = C.c_long(0), C.c_long(0)
+        self._check(lib().ref_inner_iterations(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def last_rhs(self):
         b = np.empty(self.nsol)

@@ -208,6 +208,7 @@ PetscErrorCode ModelOptionsString(const char name[], char *val, size_t len, Pets
 PetscErrorCode ModelOptionsEnum(const char name[], const char *const *list, PetscEnum *val, PetscBool *set);
 void ModelOptionsPrefixPush(const char *prefix);
 void ModelOptionsPrefixPop(void);
+const char *ModelOptionsPrefixGet(void);
 #define PetscObjectOptionsBegin(obj) \
   { \
     PetscOptionItems PetscOptionsObject = (PetscOptionItems)(obj); \

@@ -4,8 +4,26 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
+#include <time.h>
 
 PetscClassId PC_CLASSID = 11, VEC_CLASSID = 12, MAT_CLASSID = 13;
+
+static int    mt_on = -1;
+static double mt_sum[MT_NSLOTS];
+static long   mt_calls[MT_NSLOTS];
+double ModelWallTime(void)
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+void ModelTimingAdd(int slot, double seconds) { mt_sum[slot] += seconds, ++mt_calls[slot]; }
+void ModelTimingReport(FILE *f)
+{
+  static const char *const names[MT_NSLOTS] = {"KSPSolve", "MatMatMult", "MatSetValues", "MatAXPY", "MatMult", "MatDuplicate"};
+  int i;
+  for (i = 0; i < MT_NSLOTS; ++i) fprintf(f, "[PETSc model timing] %-14s %10ld calls %10.3f s\n", names[i], mt_calls[i], mt_sum[i]);
+}
 
 /* ------------------------------------------------------------------ errors, memory, strings */
 static char last_error[1024];
@@ -426,7 +444,7 @@ PetscErrorCode MatSetType(Mat A, MatType t)
 PetscErrorCode MatSetUp(Mat A) { return (void)A, PETSC_SUCCESS; }
 PetscErrorCode MatSetLocalToGlobalMapping(Mat A, ISLocalToGlobalMapping r, ISLocalToGlobalMapping c) { return A->rl2g = r, A->cl2g = c, PETSC_SUCCESS; }
 PetscErrorCode MatSetOption(Mat A, MatOption o, PetscBool b) { return (void)A, (void)o, (void)b, PETSC_SUCCESS; }
-PetscErrorCode MatSetValuesLocal(Mat A, PetscInt nr, const PetscInt ir[], PetscInt nc, const PetscInt ic[], const PetscScalar v[], InsertMode mode)
+static PetscErrorCode MatSetValuesLocal_impl(Mat A, PetscInt nr, const PetscInt ir[], PetscInt nc, const PetscInt ic[], const PetscScalar v[], InsertMode mode)
 {
   int r, c;
   PetscCheck(A->rl2g && A->cl2g, 0, PETSC_ERR_ARG_WRONGSTATE, "MatSetValuesLocal: no local-to-global mapping");
@@ -453,6 +471,17 @@ PetscErrorCode MatSetValuesLocal(Mat A, PetscInt nr, const PetscInt ir[], PetscI
   }
   ++A->hdr.state;
   return PETSC_SUCCESS;
+}
+PetscErrorCode MatSetValuesLocal(Mat A, PetscInt nr, const PetscInt ir[], PetscInt nc, const PetscInt ic[], const PetscScalar v[], InsertMode mode)
+{
+  if (mt_on < 0) mt_on = getenv("PETSC_MODEL_TIMING") ? 1 : 0;
+  if (!mt_on) return MatSetValuesLocal_impl(A, nr, ir, nc, ic, v, mode);
+  {
+    const double         t0 = ModelWallTime();
+    const PetscErrorCode e  = MatSetValuesLocal_impl(A, nr, ir, nc, ic, v, mode);
+    ModelTimingAdd(MT_MATSETVALUES, ModelWallTime() - t0);
+    return e;
+  }
 }
 PetscErrorCode MatAssemblyBegin(Mat A, MatAssemblyType t) { return (void)A, (void)t, PETSC_SUCCESS; }
 PetscErrorCode MatAssemblyEnd(Mat A, MatAssemblyType t) { return (void)t, A->assembled = 1, PETSC_SUCCESS; }
@@ -495,7 +524,7 @@ PetscErrorCode MatShift(Mat A, PetscScalar a)
   for (i = 0; i < A->m && i < A->n; ++i) *ModelMatEntry(A, i, i, 1) += a;
   return PETSC_SUCCESS;
 }
-PetscErrorCode MatAXPY(Mat Y, PetscScalar a, Mat X, MatStructure s)
+static PetscErrorCode MatAXPY_impl(Mat Y, PetscScalar a, Mat X, MatStructure s)
 {
   int i, k;
   (void)s;
@@ -505,6 +534,17 @@ PetscErrorCode MatAXPY(Mat Y, PetscScalar a, Mat X, MatStructure s)
   for (i = 0; i < X->m; ++i)
     for (k = 0; k < X->rn[i]; ++k) *ModelMatEntry(Y, i, X->rc[i][k], 1) += a * X->rv[i][k];
   return PETSC_SUCCESS;
+}
+PetscErrorCode MatAXPY(Mat Y, PetscScalar a, Mat X, MatStructure s)
+{
+  if (mt_on < 0) mt_on = getenv("PETSC_MODEL_TIMING") ? 1 : 0;
+  if (!mt_on) return MatAXPY_impl(Y, a, X, s);
+  {
+    const double         t0 = ModelWallTime();
+    const PetscErrorCode e  = MatAXPY_impl(Y, a, X, s);
+    ModelTimingAdd(MT_MATAXPY, ModelWallTime() - t0);
+    return e;
+  }
 }
 static PetscErrorCode mult_plain(Mat A, const double *x, double *y, int add)
 {
@@ -516,7 +556,7 @@ static PetscErrorCode mult_plain(Mat A, const double *x, double *y, int add)
   }
   return PETSC_SUCCESS;
 }
-PetscErrorCode MatMult(Mat A, Vec x, Vec y)
+static PetscErrorCode MatMult_impl(Mat A, Vec x, Vec y)
 {
   if (A->nest) {
     int i, j;
@@ -535,6 +575,17 @@ PetscErrorCode MatMult(Mat A, Vec x, Vec y)
   ++y->hdr.state;
   return mult_plain(A, x->a, y->a, 0);
 }
+PetscErrorCode MatMult(Mat A, Vec x, Vec y)
+{
+  if (mt_on < 0) mt_on = getenv("PETSC_MODEL_TIMING") ? 1 : 0;
+  if (!mt_on) return MatMult_impl(A, x, y);
+  {
+    const double         t0 = ModelWallTime();
+    const PetscErrorCode e  = MatMult_impl(A, x, y);
+    ModelTimingAdd(MT_MATMULT, ModelWallTime() - t0);
+    return e;
+  }
+}
 PetscErrorCode MatMultAdd(Mat A, Vec x, Vec y, Vec z)
 {
   PLAIN(A);
@@ -543,7 +594,7 @@ PetscErrorCode MatMultAdd(Mat A, Vec x, Vec y, Vec z)
   ++z->hdr.state;
   return mult_plain(A, x->a, z->a, 1);
 }
-PetscErrorCode MatMatMult(Mat A, Mat B, MatReuse r, PetscReal fill, Mat *C)
+static PetscErrorCode MatMatMult_impl(Mat A, Mat B, MatReuse r, PetscReal fill, Mat *C)
 {
   int i, k, l;
   (void)fill;
@@ -560,7 +611,18 @@ PetscErrorCode MatMatMult(Mat A, Mat B, MatReuse r, PetscReal fill, Mat *C)
   (*C)->assembled = 1;
   return PETSC_SUCCESS;
 }
-PetscErrorCode MatDuplicate(Mat A, MatDuplicateOption o, Mat *B)
+PetscErrorCode MatMatMult(Mat A, Mat B, MatReuse r, PetscReal fill, Mat *C)
+{
+  if (mt_on < 0) mt_on = getenv("PETSC_MODEL_TIMING") ? 1 : 0;
+  if (!mt_on) return MatMatMult_impl(A, B, r, fill, C);
+  {
+    const double         t0 = ModelWallTime();
+    const PetscErrorCode e  = MatMatMult_impl(A, B, r, fill, C);
+    ModelTimingAdd(MT_MATMATMULT, ModelWallTime() - t0);
+    return e;
+  }
+}
+static PetscErrorCode MatDuplicate_impl(Mat A, MatDuplicateOption o, Mat *B)
 {
   int i, k;
   PLAIN(A);
@@ -569,6 +631,17 @@ PetscErrorCode MatDuplicate(Mat A, MatDuplicateOption o, Mat *B)
     for (k = 0; k < A->rn[i]; ++k) *ModelMatEntry(*B, i, A->rc[i][k], 1) = o == MAT_COPY_VALUES ? A->rv[i][k] : 0.;
   (*B)->rl2g = A->rl2g, (*B)->cl2g = A->cl2g, (*B)->assembled = 1;
   return PETSC_SUCCESS;
+}
+PetscErrorCode MatDuplicate(Mat A, MatDuplicateOption o, Mat *B)
+{
+  if (mt_on < 0) mt_on = getenv("PETSC_MODEL_TIMING") ? 1 : 0;
+  if (!mt_on) return MatDuplicate_impl(A, o, B);
+  {
+    const double         t0 = ModelWallTime();
+    const PetscErrorCode e  = MatDuplicate_impl(A, o, B);
+    ModelTimingAdd(MT_MATDUP, ModelWallTime() - t0);
+    return e;
+  }
 }
 PetscErrorCode MatDiagonalScale(Mat A, Vec l, Vec r)
 {
@@ -758,11 +831,16 @@ double ModelDenseSolve(int n, double *a, double *b)
   }
   return pmin / pmax;
 }
+static int    ksp_default_iterative = 0;
+static double ksp_default_rtol      = 1e-5;
+void          ModelKSPSetDefaults(int iterative) { ksp_default_iterative = iterative; }
+void          ModelKSPSetDefaultRtol(double rtol) { ksp_default_rtol = rtol > 0. ? rtol : 1e-5; }
+int        ModelKSPGetDefaultIterative(void) { return ksp_default_iterative; }
 PetscErrorCode KSPCreate(MPI_Comm c, KSP *k)
 {
   *k = (KSP)zalloc(sizeof(**k));
   ModelHeaderInit(*k, 14, "KSP", "exact", NULL);
-  (*k)->hdr.comm = c;
+  (*k)->hdr.comm = c, (*k)->iterative = -1; /* -1: the default at the time of the solve */
   return PETSC_SUCCESS;
 }
 PetscErrorCode KSPSetOperators(KSP k, Mat A, Mat P)
@@ -773,13 +851,21 @@ PetscErrorCode KSPSetOperators(KSP k, Mat A, Mat P)
   k->A = A;
   return PETSC_SUCCESS;
 }
-PetscErrorCode KSPSolve(KSP k, Vec b, Vec x)
+static PetscErrorCode KSPSolve_impl(KSP k, Vec b, Vec x)
 {
   Mat       A = k->A;
   const int n = A ? A->m : 0, bordered = A && A->nullspace ? 1 : 0, N = n + bordered;
   double   *a, *r, piv;
   int       i, q;
   PetscCheck(A && !A->nest && A->m == A->n && b->n == n && x->n == n, 0, PETSC_ERR_ARG_WRONG, "KSPSolve: needs a square AIJ operator and matching vectors");
+  if (k->iterative > 0 || (k->iterative < 0 && ksp_default_iterative)) { /* an unconverged solve is not an error (KSP_DIVERGED_ITS) */
+    const int rc = ModelKSPSolveIterative(A, b->a, x->a, k->rtol > 0. ? k->rtol : ksp_default_rtol, k->maxit > 0 ? k->maxit : 10000, &k->last_its, &k->last_rel);
+    PetscCheck(rc != 2, 0, PETSC_ERR_ARG_WRONGSTATE, "KSPSolve (ILU): the operator has a row without a diagonal entry");
+    k->last_reason = rc ? -3 : 2, k->total_its += k->last_its;
+    ++x->hdr.state, ++k->nsolves;
+    if (getenv("PETSC_MODEL_KSP_MONITOR")) fprintf(stderr, "[PETSc model] KSP %s n=%d: %d iterations, relative preconditioned residual %.3e%s\n", k->hdr.prefix ? k->hdr.prefix : "", n, k->last_its, k->last_rel, rc ? " (iteration limit)" : "");
+    return PETSC_SUCCESS;
+  }
   PetscCheck(!bordered || (A->nullspace->has_cnst && !A->nullspace->vec), 0, PETSC_ERR_SUP, "KSPSolve: only the constant null space");
   a = (double *)zalloc(sizeof(double) * (size_t)N * N), r = (double *)zalloc(sizeof(double) * (size_t)N);
   for (i = 0; i < n; ++i) {
@@ -798,6 +884,17 @@ PetscErrorCode KSPSolve(KSP k, Vec b, Vec x)
   ++x->hdr.state, ++k->nsolves;
   return PETSC_SUCCESS;
 }
+PetscErrorCode KSPSolve(KSP k, Vec b, Vec x)
+{
+  if (mt_on < 0) mt_on = getenv("PETSC_MODEL_TIMING") ? 1 : 0;
+  if (!mt_on) return KSPSolve_impl(k, b, x);
+  {
+    const double         t0 = ModelWallTime();
+    const PetscErrorCode e  = KSPSolve_impl(k, b, x);
+    ModelTimingAdd(MT_KSPSOLVE, ModelWallTime() - t0);
+    return e;
+  }
+}
 PetscErrorCode KSPDestroy(KSP *pk)
 {
   KSP k = *pk;
@@ -809,7 +906,26 @@ PetscErrorCode KSPDestroy(KSP *pk)
   free(k);
   return PETSC_SUCCESS;
 }
-PetscErrorCode KSPSetFromOptions(KSP k) { return (void)k, PETSC_SUCCESS; }
+/* -<prefix>ksp_type exact | gmres (GMRES(30) + ILU(0)), -<prefix>ksp_rtol, -<prefix>ksp_max_it; the prefix is the KSP's own, whatever
+   object's options are being processed around the call (PCSetFromOptions_ABF calls this for its sub-KSPs, abfpc.c:248-249) */
+PetscErrorCode KSPSetFromOptions(KSP k)
+{
+  const char *outer = ModelOptionsPrefixGet();
+  char        type[64] = "";
+  PetscBool   set = PETSC_FALSE;
+  PetscInt    maxit = k->maxit;
+  ModelOptionsPrefixPush(k->hdr.prefix);
+  PetscCall(ModelOptionsString("-ksp_type", type, sizeof(type), &set));
+  if (set) {
+    PetscCheck(!strcmp(type, "exact") || !strcmp(type, "gmres"), 0, PETSC_ERR_SUP, "the model's KSP types are exact and gmres, not %s", type);
+    k->iterative = !strcmp(type, "gmres");
+  }
+  PetscCall(ModelOptionsReal("-ksp_rtol", &k->rtol, NULL));
+  PetscCall(ModelOptionsInt("-ksp_max_it", &maxit, NULL));
+  k->maxit = (int)maxit;
+  ModelOptionsPrefixPush(outer);
+  return PETSC_SUCCESS;
+}
 PetscErrorCode KSPSetOptionsPrefix(KSP k, const char p[])
 {
   free(k->hdr.prefix);

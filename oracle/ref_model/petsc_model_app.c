@@ -41,6 +41,7 @@ PetscErrorCode ModelOptionsClear(void)
 static const char *current_prefix = NULL;
 void ModelOptionsPrefixPush(const char *prefix) { current_prefix = prefix; }
 void ModelOptionsPrefixPop(void) { current_prefix = NULL; }
+const char *ModelOptionsPrefixGet(void) { return current_prefix; }
 static const char *opt_find(const char *name)
 {
   char full[600];
@@ -131,6 +132,13 @@ PetscErrorCode PetscInitialize(int *argc, char ***argv, const char file[], const
     else PetscCall(ModelOptionsSetValue(arg, ""));
   }
   initialized = 1, finalized = 0;
+  { /* -model_solvers iterative: every KSP nobody configures runs GMRES(30) (+ ILU(0) for the assembled inner ones), as serial PETSc does */
+    const char *ms = opt_find("-model_solvers");
+    if (ms) {
+      PetscCheck(!strcmp(ms, "iterative") || !strcmp(ms, "exact"), 0, PETSC_ERR_SUP, "-model_solvers exact | iterative, not %s", ms);
+      ModelKSPSetDefaults(!strcmp(ms, "iterative"));
+    }
+  }
   /* -dll_append <library>: PETSc opens the shared library and calls PetscDLLibraryRegister_<name>, <name> = the file name without
      directory, "lib" and suffix.  That is how a type implemented outside the reference (glue/nsb200.c) registers itself. */
   {
@@ -169,6 +177,7 @@ PetscErrorCode PetscFinalize(void)
   for (i = 0; i < nopts; ++i)
     if (!opts[i].used && strcmp(opts[i].name, "-dll_append")) fprintf(stderr, "WARNING! There are options you set that were not used! Option left: name:%s value: %s\n", opts[i].name, opts[i].value);
   ModelOptionsClear();
+  if (getenv("PETSC_MODEL_TIMING")) ModelTimingReport(stderr);
   initialized = 0, finalized = 1;
   return PETSC_SUCCESS;
 }
@@ -673,6 +682,7 @@ PetscErrorCode SNESSetFromOptions(SNES s)
   KSP       k;
   PC        pc;
   PetscCall(SNESGetKSP(s, &k));
+  if (ModelKSPGetDefaultIterative()) strcpy(type, "gmres");
   snprintf(name, sizeof(name), "-%sksp_type", s->hdr.prefix ? s->hdr.prefix : "");
   PetscCall(ModelOptionsString(name, type, sizeof(type), &set));
   s->mode = !strcmp(type, "preonly") ? 1 : (!strcmp(type, "gmres") || !strcmp(type, "fgmres") ? 2 : 0);

@@ -2,6 +2,7 @@
  * helpers ref_driver.c uses to reach into them.  The reference's sources never see this header (they include petsc_model.h only). */
 #ifndef PETSC_MODEL_IMPL_H
 #define PETSC_MODEL_IMPL_H
+#include <stdio.h>
 #include <petsc_model.h>
 
 #define MODEL_GARBAGE (-777) /* what arguments documented as "ignored in lower dimensions" come back as */
@@ -59,7 +60,22 @@ struct _p_KSP {
   long                  nsolves;
   PC                    pc; /* the KSP of a SNES owns a PC (SNESGetKSP / KSPGetPC) */
   double                rtol;
+  int                   iterative, maxit; /* 0: dense LU ("exact"); 1: GMRES(30) + ILU(0) of petsc_model_ksp.c */
+  int                   last_its, last_reason;
+  long                  total_its;
+  double                last_rel;
 };
+/* PETSC_MODEL_TIMING=1: cumulative wall time of the model's expensive entry points, printed by PetscFinalize / ModelTimingReport
+   (a stand-in for -log_view: where a run of the reference on the model spends its time) */
+enum { MT_KSPSOLVE, MT_MATMATMULT, MT_MATSETVALUES, MT_MATAXPY, MT_MATMULT, MT_MATDUP, MT_NSLOTS };
+double ModelWallTime(void);
+void   ModelTimingAdd(int slot, double seconds);
+void   ModelTimingReport(FILE *f);
+/* defaults of KSPs nobody configured: ModelKSPSetDefaults(1, ...) / -model_solvers iterative = what serial PETSc would run */
+void ModelKSPSetDefaults(int iterative);
+void ModelKSPSetDefaultRtol(double rtol); /* of iterative KSPs whose rtol nobody set (PETSc: 1e-5) */
+int  ModelKSPGetDefaultIterative(void);
+int  ModelKSPSolveIterative(Mat A, const double *b, double *x, double rtol, int maxit, int *its, double *rel);
 struct _p_SNES {
   struct _p_PetscObject hdr;
   void                 *ctx;

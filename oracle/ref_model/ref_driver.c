@@ -453,6 +453,17 @@ int ref_step(void *vh, int mode, int schur_ainv, int upper_ainv, double rtol, in
     for (i = 0; i < h->nhist; ++i) hist[i] = h->hist[i];
   return 0;
 }
+/* inner KSPs of PCABF: 0 = the model's exact solves (the checker's default), 1 = GMRES(30) + ILU(0), rtol 1e-5: what serial PETSc
+   runs when nobody configures them (petsc_model_ksp.c); rtol <= 0: that default.  Process-wide; counts = Krylov iterations since creation. */
+void ref_set_inner_solvers(int iterative, double rtol) { ModelKSPSetDefaults(iterative), ModelKSPSetDefaultRtol(rtol); }
+int  ref_inner_iterations(void *vh, long *mom, long *schur)
+{
+  Ref *h = (Ref *)vh;
+  KSP  ka = NULL, ks = NULL;
+  if (PCABFGetSubKSPs(h->pc, &ka, &ks) || !ka || !ks) return 1;
+  *mom = ka->total_its, *schur = ks->total_its;
+  return 0;
+}
 /* the right-hand side of the solve inside the last ref_step (null space removed, as SNES sees it) */
 int ref_last_rhs(void *vh, double *b)
 {

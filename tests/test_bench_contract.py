@@ -20,6 +20,10 @@ def test_reference_arm_prints_one_json_line():
         assert key in d, key
     assert d["impl"] == "reference" and d["dtype"] == "f64" and d["unit"] == "Mcell-updates/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    rs = d["cpu_baseline"]["reference_sources"]  # the reference's own sources timed beside the port, where oracle/_ref exists
+    assert "error" not in rs, rs
+    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libfluca_ref_ns.so")):
+        assert rs["available"] and rs["value"] > 0 and rs["cores"] == 1 and "GMRES(30) + ILU(0)" in rs["sample"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
 
 
@@ -97,6 +101,8 @@ def test_gpu_arm_logic_on_the_test_double():
     assert set(d["parity"]["runs"]) == {"ID/ID", "DIAG/ROWSUM"}
     rs = d["parity"]["reference_sources"]  # the same library against the reference's own compiled NS sources (where oracle/_ref exists)
     assert rs["available"] is False or (rs["ok"] and set(rs["runs"]) == {"fractional", "coupled"}), rs
+    rs = d["cpu_baseline"]["reference_sources"]
+    assert "error" not in rs and (rs["available"] is False or (rs["value"] > 0 and rs["cores"] == 1)), rs
     assert d["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["value"] > 0 and d["gpu_launches"] > 0
     assert d["cpu_baseline"]["cores"] >= 1 and "absent" in d["cpu_baseline"]["reference_build"]
     assert d["config"]["workload"].startswith("BASELINE config 4")

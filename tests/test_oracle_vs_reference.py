@@ -289,3 +289,40 @@ def test_product_sources_equal_the_reference_on_random_boundary_sets(block):
         fb.NSDestroy(ns)
         tag = (seed, case.n, [b["type"] for b in case.bcs], case.stretch)
         assert parity.rel(y["v"], x["v"]) <= 1e-9 and parity.relU(y["U"], x["U"]) <= 1e-9 and parity.rel(y["p"], x["p"]) <= 1e-8, tag
+
+
+@needs_reference
+@pytest.mark.parametrize("name", ["channel3d_24x14x12_stretched", "cavity2d_48_stretched"])
+def test_steps_equal_the_references_beyond_the_reach_of_dense_solves(name):
+    """The same comparison on grids the model's dense LU cannot take (4 000 cells in 3-D, 12 000 velocity unknowns): the reference's
+    sources with the model's iterative KSPs (GMRES(30) + ILU(0), oracle/ref_model/petsc_model_ksp.c) taken to 1e-13, outer GMRES +
+    the reference's PCABF to 1e-12, against the oracle's own solvers taken to convergence."""
+    if name.startswith("channel3d"):
+        case = cases.channel3d(n=(24, 14, 12), pout=0.2)
+        case.stretch = 0.15
+    else:
+        case = cases.cavity2d(n=48)
+        case.stretch = 0.3
+    state = case.initial_state(seed=31)
+    lib = parity.hostemu_library()
+    ns = parity.make_ns(case, lib, "coupled", **parity.TIGHT)  # the product's sources (host build) on the same grid
+    parity.set_initial(ns, state)
+    R.set_inner_solvers(True, 1e-13)
+    try:
+        ref, orc = _gen.make_reference(case), cases.make_oracle(case)
+        ref.set_state(*state)
+        orc.set_state(*state)
+        opt = O.default_options(mode=0, **parity.ORC_TIGHT)
+        for _ in range(2):
+            its, hist = ref.step(mode=R.GMRES_ABF, rtol=1e-12, maxit=200)
+            assert hist[-1] <= 1e-12 * hist[0]
+            orc.step(opt)
+            fb.NSStep(ns)
+        mom, schur = ref.inner_iterations()
+        assert mom > 0 and schur > 0  # the iterative KSPs did the work
+    finally:
+        R.set_inner_solvers(False)
+    a, b, c = orc.get_state(), ref.get_state(), fb.NSB200GetSolver(ns).get_state()
+    fb.NSDestroy(ns)
+    assert parity.rel(a["v"], b["v"]) <= 1e-9 and parity.relU(a["U"], b["U"]) <= 1e-9 and parity.rel(a["p"], b["p"]) <= 1e-8 and parity.rel(a["phalf"], b["phalf"]) <= 1e-8
+    assert parity.rel(c["v"], b["v"]) <= 1e-9 and parity.relU(c["U"], b["U"]) <= 1e-9 and parity.rel(c["p"], b["p"]) <= 1e-8 and parity.rel(c["phalf"], b["phalf"]) <= 1e-8

@@ -217,3 +217,42 @@ def test_non_uniform_mesh_through_the_references_coordinate_api(tmp_path):
         a, b = dumps["cnlinear"][k], dumps["b200"][k]
         assert np.abs(a - b).max() <= (1e-9 if k.startswith("Pressure") else 1e-10) * np.abs(a).max(), k
     assert np.abs(dumps["cnlinear"]["Velocity"] - dumps["uniform"]["Velocity"]).max() > 1e-2  # the stretching did reach the solver
+
+
+ITER_CASES = [
+    ("cavity_flow_3d", ["-cart_grid_x", "10", "-cart_grid_y", "9", "-cart_grid_z", "6", "-ns_time_step_size", "0.05", "-ns_max_steps", "3"]),
+    ("cavity_flow_2d", ["-cart_grid_x", "16", "-cart_grid_y", "14", "-ns_time_step_size", "0.03", "-ns_max_steps", "3"]),
+    ("taylor_green_vortex", ["-nsteps", "3", "-t_final", "0.15", "-periodic", "-cart_grid_x", "12", "-cart_grid_y", "12"]),
+]
+
+
+@pytest.mark.skipif(not _ready("hostemu"), reason="oracle/_ref is not built here")
+@pytest.mark.parametrize("prog,args", ITER_CASES, ids=[c[0] for c in ITER_CASES])
+def test_the_models_iterative_solvers_converge_to_its_exact_solves(tmp_path, prog, args):
+    """`-model_solvers iterative` (oracle/ref_model/petsc_model_ksp.c: outer right-preconditioned GMRES(30) + the reference's PCABF
+    with GMRES(30) + ILU(0) inside, what a serial PETSc run does by default) is the configuration bench.py times as the CPU figure
+    of the reference's own sources.  Taken to convergence it must land on the exact solves the parity checks use; at PETSc's default
+    tolerances (1e-5 everywhere, nssol.c:22-24) it stays within the accuracy those tolerances buy."""
+    exact, _ = run(prog, args, tmp_path, "exact")
+    tight, _ = run(prog, args + ["-model_solvers", "iterative", "-ns_ksp_rtol", "1e-12", "-ns_abf_momentum_ksp_rtol", "1e-13", "-ns_abf_schur_ksp_rtol", "1e-13"], tmp_path, "tight")
+    loose, _ = run(prog, args + ["-model_solvers", "iterative"], tmp_path, "loose")
+    for k in ("Velocity", "FaceNormalVelocity", "Pressure"):
+        n = np.linalg.norm(exact[k])
+        assert np.linalg.norm(tight[k] - exact[k]) <= 1e-8 * n, (k, np.linalg.norm(tight[k] - exact[k]) / n)
+        assert np.linalg.norm(loose[k] - exact[k]) <= (5e-2 if k == "Pressure" else 2e-3) * n, (k, np.linalg.norm(loose[k] - exact[k]) / n)
+
+
+@pytest.mark.skipif(not _ready("hostemu"), reason="oracle/_ref is not built here")
+def test_b200_and_the_reference_both_at_default_tolerances(tmp_path):
+    """What a user sees when switching types with no other option: the reference's cnlinear with iterative solvers at PETSc's
+    defaults against -ns_type b200 at its defaults, in the reference's own cavity_flow_3d.  Neither is converged; they differ by what
+    1e-5 tolerances leave open, not by more."""
+    args = ["-cart_grid_x", "12", "-cart_grid_y", "12", "-cart_grid_z", "6", "-ns_time_step_size", "0.04", "-ns_max_steps", "4"]
+    ref, _ = run("cavity_flow_3d", args + ["-model_solvers", "iterative"], tmp_path, "ref_defaults")
+    dump = str(tmp_path / "b200_defaults.bin")
+    r = subprocess.run([os.path.join(REFDIR, "cavity_flow_3d")] + args + ["-ns_monitor_solution", f"flucacgns:{dump}", "-dll_append", os.path.join(REFDIR, "hostemu", "libfluca_nsb200.so"), "-ns_type", "b200"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    b200 = load_dump(dump)
+    for k, tol in (("Velocity", 2e-3), ("FaceNormalVelocity", 2e-3), ("Pressure", 5e-2)):
+        n = np.linalg.norm(ref[k])
+        assert np.linalg.norm(ref[k] - b200[k]) <= tol * n, (k, np.linalg.norm(ref[k] - b200[k]) / n)
