@@ -139,7 +139,7 @@ def test_nccl_two_gpus_match_oracle(case_name, mode, tmp_path):
         assert [int(a) for a in got["its"][:, 0]] == [i.outer_its for i in infos]
 
 
-@pytest.mark.parametrize("seed,mode,world", [(2, "coupled", 2), (5, "fractional", 3), (9, "coupled", 2)])
+@pytest.mark.parametrize("seed,mode,world", [(5, "fractional", 3), (9, "coupled", 2)])
 def test_slab_partition_on_random_boundary_sets(seed, mode, world, tmp_path):
     """Random 3-D meshes and boundary sets (any mix of velocity / outlet / symmetry / periodic, also on the slab direction z,
     uniform or stretched; tests/multirank_worker.py random_case3d) over 2 and 3 slabs against the single-domain oracle.  (Twelve

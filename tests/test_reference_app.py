@@ -220,7 +220,7 @@ def test_non_uniform_mesh_through_the_references_coordinate_api(tmp_path):
 
 
 ITER_CASES = [
-    ("cavity_flow_3d", ["-cart_grid_x", "10", "-cart_grid_y", "9", "-cart_grid_z", "6", "-ns_time_step_size", "0.05", "-ns_max_steps", "3"]),
+    ("cavity_flow_3d", ["-cart_grid_x", "8", "-cart_grid_y", "7", "-cart_grid_z", "5", "-ns_time_step_size", "0.06", "-ns_max_steps", "2"]),
     ("cavity_flow_2d", ["-cart_grid_x", "16", "-cart_grid_y", "14", "-ns_time_step_size", "0.03", "-ns_max_steps", "3"]),
     ("taylor_green_vortex", ["-nsteps", "3", "-t_final", "0.15", "-periodic", "-cart_grid_x", "12", "-cart_grid_y", "12"]),
 ]
