@@ -264,6 +264,21 @@ static PetscErrorCode NSSetFromOptions_B200(NS ns, PetscOptionItems PetscOptions
   PetscFunctionBegin;
   PetscOptionsHeadBegin(PetscOptionsObject, "NSB200 Options"); /* pattern: cnlinear.c:5-12 */
   PetscCall(PetscOptionsInt("-ns_b200_mode", "0: coupled solve, PC = ABF (reference default); 1: one ABF application (classical fractional step)", "", b->mode, &b->mode, NULL));
+  /* the reference's OWN names for the solver knobs first, so that a command line written for cnlinear keeps its meaning when only
+   * -ns_type changes: the KSP of the SNES lives under "ns_" (nssol.c:13-25), the two KSPs of PCABF under "ns_abf_momentum_" and
+   * "ns_abf_schur_" (abfpc.c:33-46).  PETSc hands the same values to those objects of the base class, which this type never solves
+   * with.  The -ns_b200_* spellings below are read afterwards and win. */
+  PetscCall(PetscOptionsReal("-ns_ksp_rtol", "outer relative tolerance", "KSPSetTolerances", b->outer_rtol, &b->outer_rtol, NULL));
+  PetscCall(PetscOptionsInt("-ns_ksp_max_it", "outer iteration limit", "KSPSetTolerances", b->outer_maxit, &b->outer_maxit, NULL));
+  PetscCall(PetscOptionsInt("-ns_ksp_gmres_restart", "restart of the outer GMRES", "KSPGMRESSetRestart", b->restart, &b->restart, NULL));
+  PetscCall(PetscOptionsReal("-ns_abf_momentum_ksp_rtol", "momentum solve relative tolerance", "KSPSetTolerances", b->mom_rtol, &b->mom_rtol, NULL));
+  PetscCall(PetscOptionsReal("-ns_abf_schur_ksp_rtol", "pressure solve relative tolerance", "KSPSetTolerances", b->schur_rtol, &b->schur_rtol, NULL));
+  {
+    PetscInt ma = 0, ms = 0; /* one limit for both inner solves in the library: the larger of the two asked for */
+    PetscCall(PetscOptionsInt("-ns_abf_momentum_ksp_max_it", "momentum solve iteration limit", "KSPSetTolerances", ma, &ma, NULL));
+    PetscCall(PetscOptionsInt("-ns_abf_schur_ksp_max_it", "pressure solve iteration limit", "KSPSetTolerances", ms, &ms, NULL));
+    if (PetscMax(ma, ms) > 0) b->inner_maxit = PetscMax(ma, ms);
+  }
   PetscCall(PetscOptionsInt("-ns_b200_gmres_restart", "restart of the outer GMRES ((restart + 1) x 7 fields of device memory)", "", b->restart, &b->restart, NULL));
   PetscCall(PetscOptionsReal("-ns_b200_outer_rtol", "outer relative tolerance (nssol.c:24 sets 1e-5)", "", b->outer_rtol, &b->outer_rtol, NULL));
   PetscCall(PetscOptionsReal("-ns_b200_momentum_rtol", "momentum solve relative tolerance", "", b->mom_rtol, &b->mom_rtol, NULL));
@@ -370,6 +385,8 @@ static PetscErrorCode NSSetup_B200(NS ns)
   desc.mode          = (int)b->mode;
   desc.outer_rtol    = b->outer_rtol;
   desc.outer_restart = (int)b->restart;
+  desc.outer_maxit   = (int)b->outer_maxit; /* 0: the library's defaults (100 outer, 500 inner) */
+  desc.inner_maxit   = (int)b->inner_maxit;
   desc.mom_rtol      = b->mom_rtol;
   desc.schur_rtol    = b->schur_rtol;
   desc.no_bcg_quirk      = b->no_bcg_quirk ? 1 : 0;

@@ -256,3 +256,45 @@ def test_b200_and_the_reference_both_at_default_tolerances(tmp_path):
     for k, tol in (("Velocity", 2e-3), ("FaceNormalVelocity", 2e-3), ("Pressure", 5e-2)):
         n = np.linalg.norm(ref[k])
         assert np.linalg.norm(ref[k] - b200[k]) <= tol * n, (k, np.linalg.norm(ref[k] - b200[k]) / n)
+
+
+def _program(prog, args, tmp_path, tag, b200):
+    dump = str(tmp_path / f"{prog}_{tag}.bin")
+    cmd = [os.path.join(REFDIR, prog)] + list(args) + ["-ns_monitor", "-ns_monitor_solution", f"flucacgns:{dump}"]
+    if b200:
+        cmd += ["-dll_append", os.path.join(REFDIR, "hostemu", "libfluca_nsb200.so"), "-ns_type", "b200"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    return r, (load_dump(dump) if os.path.exists(dump) else None)
+
+
+@pytest.mark.skipif(not _ready("hostemu"), reason="oracle/_ref is not built here")
+def test_one_command_line_for_both_types(tmp_path):
+    """A command line written for the reference's type keeps its meaning when only the type changes: the tolerances go in under the
+    reference's own option names (-ns_ksp_rtol for the KSP of the SNES, nssol.c:13-25; -ns_abf_momentum_ksp_rtol and
+    -ns_abf_schur_ksp_rtol for the KSPs of PCABF, abfpc.c:33-46), b200 reads them (glue/nsb200.c NSSetFromOptions_B200), nothing is
+    left unused, and both runs land on the same answer."""
+    args = ["-cart_grid_x", "12", "-cart_grid_y", "10", "-cart_grid_z", "6", "-ns_time_step_size", "0.05", "-ns_max_steps", "3", "-model_solvers", "iterative",
+            "-ns_ksp_rtol", "1e-12", "-ns_abf_momentum_ksp_rtol", "1e-13", "-ns_abf_schur_ksp_rtol", "1e-13"]
+    out = {}
+    for tag, b200 in (("cnlinear", False), ("b200", True)):
+        r, out[tag] = _program("cavity_flow_3d", args, tmp_path, tag, b200)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "options you set that were not used" not in r.stderr, r.stderr
+    for k in ("Velocity", "FaceNormalVelocity", "Pressure", "PressureHalfStep"):
+        a, b = out["cnlinear"][k], out["b200"][k]
+        assert np.linalg.norm(a - b) <= 1e-8 * np.linalg.norm(a), (k, np.linalg.norm(a - b) / np.linalg.norm(a))
+
+
+@pytest.mark.skipif(not _ready("hostemu"), reason="oracle/_ref is not built here")
+def test_a_step_that_does_not_converge_meets_the_references_failure_policy(tmp_path):
+    """-ns_ksp_max_it 1 with a tolerance one iteration cannot reach: the library reports DIVERGED, the glue sets ns->reason =
+    NS_DIVERGED_NONLINEAR_SOLVE as NSCheckDiverged does (nsbasic.c:425-436) and the reference's NSStep applies its policy
+    (nsbasic.c:288-297): by default the program stops with PETSC_ERR_NOT_CONVERGED; with -ns_error_if_step_failed 0 NSSolve ends
+    quietly with the step counter and the time where they were."""
+    args = ["-cart_grid_x", "10", "-cart_grid_y", "10", "-ns_time_step_size", "0.05", "-ns_max_steps", "3", "-ns_ksp_rtol", "1e-12", "-ns_ksp_max_it", "1"]
+    r, _ = _program("cavity_flow_2d", args, tmp_path, "stop", True)
+    assert r.returncode != 0 and "NSStep has failed due to" in r.stderr and "DIVERGED_NONLINEAR_SOLVE" in r.stderr, r.stdout + r.stderr
+    r, _ = _program("cavity_flow_2d", args + ["-ns_error_if_step_failed", "0"], tmp_path, "quiet", True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    mon = [ln for ln in r.stdout.splitlines() if " NS dt " in ln]
+    assert mon and all(ln.startswith("0 NS dt 0.05 time 0") for ln in mon), mon  # NSSolve's monitors before and after: the failed step did not advance
