@@ -445,6 +445,9 @@ def _b200_setup(ns: NS):
     for key, name in (("ns_ksp_max_it", "outer_maxit"), ("ns_ksp_gmres_restart", "outer_restart"), ("ns_abf_ksp_max_it", "inner_maxit"), ("ns_b200_mg_nu1", "mg_nu1"), ("ns_b200_mg_nu2", "mg_nu2"), ("ns_b200_mg_coarse_sweeps", "mg_coarse_sweeps"), ("ns_b200_no_bcg_quirk", "no_bcg_quirk"), ("ns_b200_no_t_outlet_quirk", "no_t_outlet_quirk")):
         if key in o:
             kw[name] = int(o[key])
+    inner = [int(o[k]) for k in ("ns_abf_momentum_ksp_max_it", "ns_abf_schur_ksp_max_it") if k in o]  # PCABF's two KSPs (abfpc.c:33-46): one limit here
+    if inner:
+        kw["inner_maxit"] = max(inner)
     rank, nranks, comm = 0, 1, None
     if ns.comm:
         rank, nranks = ns.comm["rank"], ns.comm["nranks"]
