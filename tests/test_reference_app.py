@@ -298,3 +298,29 @@ def test_a_step_that_does_not_converge_meets_the_references_failure_policy(tmp_p
     assert r.returncode == 0, r.stdout + r.stderr
     mon = [ln for ln in r.stdout.splitlines() if " NS dt " in ln]
     assert mon and all(ln.startswith("0 NS dt 0.05 time 0") for ln in mon), mon  # NSSolve's monitors before and after: the failed step did not advance
+
+
+@pytest.mark.skipif(not (_ready("hostemu") and os.path.exists(os.path.join(REFDIR, "fluca_app"))), reason="oracle/_ref is not built here")
+@pytest.mark.parametrize("first,second", [("b200", "cnlinear"), ("cnlinear", "b200")])
+def test_the_references_application_restarts_across_types(tmp_path, first, second):
+    """The reference's APPLICATION (fluca/app/main.c, unmodified: lid-driven cavity, -ns_load_solution_from_file) on the PETSc model:
+    four steps with cnlinear in one run against two steps with one type, the solution file NSMonitorSolution wrote, and a second
+    run of the application that loads it (-ns_load_solution_from_file -> NSLoadSolution, nssol.c:176-204: step, time, PressureHalfStep)
+    and continues to step 4 with the OTHER type."""
+    app = os.path.join(REFDIR, "fluca_app")
+    grid = ["-cart_grid_x", "12", "-cart_grid_y", "10", "-ns_monitor"]
+    plug = ["-dll_append", os.path.join(REFDIR, "hostemu", "libfluca_nsb200.so"), "-ns_type", "b200"] + TIGHT
+
+    def go(args, kind):
+        r = subprocess.run([app] + grid + args + (plug if kind == "b200" else []), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "options you set that were not used" not in r.stderr, r.stdout + r.stderr
+        return [ln for ln in r.stdout.splitlines() if " NS dt " in ln]
+
+    full, half, cont = (str(tmp_path / f"{n}.bin") for n in ("full", "half", "cont"))
+    go(["-ns_max_steps", "4", "-ns_monitor_solution", f"flucacgns:{full}"], "cnlinear")
+    go(["-ns_max_steps", "2", "-ns_monitor_solution", f"flucacgns:{half}"], first)
+    mon = go(["-ns_max_steps", "4", "-ns_load_solution_from_file", half, "-ns_monitor_solution", f"flucacgns:{cont}"], second)
+    assert mon[0].startswith("2 NS dt 0.002 time 0.004") and mon[-1].startswith("4 NS"), mon  # picked up at step 2
+    a, b = load_dump(full), load_dump(cont)
+    for k in ("Velocity", "FaceNormalVelocity", "Pressure", "PressureHalfStep"):
+        assert np.abs(a[k] - b[k]).max() <= 1e-10 * np.abs(a[k]).max(), (k, np.abs(a[k] - b[k]).max() / np.abs(a[k]).max())
