@@ -49,6 +49,9 @@ class Desc(C.Structure):
     ]
 
 
+INNER_MONITOR_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_double)  # fluca_b200_inner_monitor_fn
+
+
 class Stats(C.Structure):
     _fields_ = [
         ("outer_its", C.c_int),
@@ -108,6 +111,7 @@ SYMBOLS = [
     "fluca_b200_ibm_spread",
     "fluca_b200_set_ibm_iterations",
     "fluca_b200_set_abf_ainv_types",
+    "fluca_b200_set_inner_monitor",
     "fluca_b200_stage_state",
     "fluca_b200_staged_state",
     # FlucaFD stencil layer (host-side; csrc/fd.cu)
@@ -195,6 +199,7 @@ def _prototype(L):
     L.fluca_b200_ibm_spread.argtypes = [_P, _P, _P]
     L.fluca_b200_set_ibm_iterations.argtypes = [_P, C.c_int]
     L.fluca_b200_set_abf_ainv_types.argtypes = [_P, C.c_int, C.c_int]
+    L.fluca_b200_set_inner_monitor.argtypes = [_P, INNER_MONITOR_FN, C.c_void_p]
     L.fluca_b200_fd_last_error.restype = C.c_char_p
     L.fluca_b200_fd_grid_create.argtypes = [C.c_int, C.POINTER(C.c_int), _PD3, _PD3, C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]
     L.fluca_b200_fd_grid_destroy.argtypes = [_P]

@@ -701,6 +701,14 @@ extern "C" int fluca_b200_set_abf_ainv_types(fluca_b200_solver *h, int schur_typ
   API_END
 }
 
+extern "C" int fluca_b200_set_inner_monitor(fluca_b200_solver *h, fluca_b200_inner_monitor_fn fn, void *ctx)
+{
+  API_BEGIN
+  if (!h) throw Error(FL_ERR_ARG, "null solver");
+  h->s.inner_monitor = fn, h->s.inner_monitor_ctx = ctx;
+  API_END
+}
+
 extern "C" int fluca_b200_set_ibm_iterations(fluca_b200_solver *h, int passes)
 {
   API_BEGIN

@@ -116,6 +116,7 @@ int momentum_solve(Solver &s, const V3 &b, const V3 &x, bool guess, double bscal
   const double tol = inner_rtol(s, s.opt.mom_rtol) * bnorm;
   double       rho = red[0], alpha = 1., omega = 1.;
   s.stats.mom_last_rel = std::sqrt(red[0]) / bnorm;
+  s.monitor(0, 0, std::sqrt(red[0]));
   if (std::sqrt(red[0]) <= tol) return 0; // the guess already meets the tolerance
   int          it = 0;
   for (; it < s.opt.inner_maxit;) {
@@ -141,6 +142,7 @@ int momentum_solve(Solver &s, const V3 &b, const V3 &x, bool guess, double bscal
         _Pragma("unroll") for (int q = 0; q < 3; ++q) if (q < nc) X.c[q][i] += alpha * PV.c[q][i];
       });
       s.stats.mom_last_rel = std::sqrt(red[0]) / bnorm;
+      s.monitor(0, it, std::sqrt(red[0]));
       break;
     }
     // t = A s with four fused sums: <r^, t>, <t, t>, <s, t>, <r^, s>
@@ -170,6 +172,7 @@ int momentum_solve(Solver &s, const V3 &b, const V3 &x, bool guess, double bscal
     });
     reduce_finish(s, 1, red);
     s.stats.mom_last_rel = std::sqrt(red[0]) / bnorm;
+    s.monitor(0, it, std::sqrt(red[0]));
     if (std::sqrt(red[0]) <= tol) break;
     if (!(red[0] == red[0])) throw Error(FL_ERR_DIVERGED, "momentum residual is NaN");
   }
@@ -279,6 +282,7 @@ static int poisson_pcg(Solver &s, double *b, double *x)
   if (bnorm == 0.) return 0;
   if (!(bnorm == bnorm)) throw Error(FL_ERR_DIVERGED, "Poisson right-hand side is NaN");
   const double tol = inner_rtol(s, s.opt.schur_rtol) * bnorm;
+  s.monitor(1, 0, bnorm);
   // The V-cycle is not a symmetric operator (summed-residual restriction against trilinear prolongation; measured: 8 % asymmetry on a
   // 6^3 grid with a symmetry plane), so the Fletcher-Reeves beta of textbook PCG loses conjugacy in LONG solves: a rough right-hand
   // side then needs 185 iterations for 1e-5 and stalls at 1e-5 for good, where the flexible (Polak-Ribiere) beta
@@ -325,6 +329,7 @@ static int poisson_pcg(Solver &s, double *b, double *x)
     reduce_finish(s, 1, red);
     ++it;
     s.stats.schur_last_rel = std::sqrt(red[0]) / bnorm;
+    s.monitor(1, it, std::sqrt(red[0]));
     if (std::sqrt(red[0]) <= tol) break;
   }
   s.stats.schur_its += it;
@@ -354,6 +359,7 @@ static int poisson_bicgstab(Solver &s, double *b, double *x)
   const double tol = inner_rtol(s, s.opt.schur_rtol) * bnorm;
   double       rho = red[0], alpha = 1., omega = 1.;
   int          it = 0;
+  s.monitor(1, 0, bnorm);
   for (; it < s.opt.inner_maxit;) {
     double       *yf = mg_vcycle(s, s.pp); // y = M^-1 p
     const double *Y  = yf + off;
@@ -369,7 +375,10 @@ static int poisson_bicgstab(Solver &s, double *b, double *x)
     reduce_finish(s, 1, red);
     ++it;
     s.stats.schur_last_rel = std::sqrt(red[0]) / bnorm;
-    if (std::sqrt(red[0]) <= tol) break;
+    if (std::sqrt(red[0]) <= tol) {
+      s.monitor(1, it, std::sqrt(red[0]));
+      break;
+    }
     double       *zf = mg_vcycle(s, s.ps); // z = M^-1 s  (y is dead by now: x was updated above)
     const double *Z  = zf + off;
     const double  ts = poisson_apply_dot(s, zf, s.pt, s.ps);
@@ -386,6 +395,7 @@ static int poisson_bicgstab(Solver &s, double *b, double *x)
     });
     reduce_finish(s, 2, red);
     s.stats.schur_last_rel = std::sqrt(red[0]) / bnorm;
+    s.monitor(1, it, std::sqrt(red[0]));
     if (std::sqrt(red[0]) <= tol) break;
     if (!(red[0] == red[0])) throw Error(FL_ERR_DIVERGED, "pressure residual is NaN");
     if (red[1] == 0. || omega == 0.) throw Error(FL_ERR_DIVERGED, "BiCGStab breakdown in the pressure solve (rho = 0)");

@@ -137,6 +137,9 @@ struct Solver {
   Options   opt;
   StepParams sp;
   std::unique_ptr<Comm> comm;
+  void (*inner_monitor)(void *, int, int, double) = nullptr; // fluca_b200_set_inner_monitor: host callback per inner residual norm
+  void *inner_monitor_ctx = nullptr;
+  void  monitor(int which, int it, double rnorm) const { if (inner_monitor) inner_monitor(inner_monitor_ctx, which, it, rnorm); }
   bool      has_outlet = false;
   int       dim = 3;
   // boundary values (device) + descriptor

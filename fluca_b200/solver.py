@@ -249,6 +249,12 @@ class Solver:
         _lib.check(self.L, self.L.fluca_b200_set_abf_ainv_types(self._h, int(schur_type), int(upper_type)))
         self.ainv_types = (int(schur_type), int(upper_type))
 
+    def set_inner_monitor(self, fn=None):
+        """fn(which, it, rnorm) per inner residual norm (which: 0 momentum, 1 Schur; it = 0: initial residual of a solve) -- the
+        analogue of -ns_abf_momentum_ksp_monitor / -ns_abf_schur_ksp_monitor; None switches it off."""
+        self._monitor_cb = _lib.INNER_MONITOR_FN(lambda ctx, which, it, rnorm: fn(which, it, rnorm)) if fn else _lib.INNER_MONITOR_FN()
+        _lib.check(self.L, self.L.fluca_b200_set_inner_monitor(self._h, self._monitor_cb, None))
+
     # ------------------------------------------------------------------ immersed boundary
     def set_markers(self, X, Ud, dV, delta_points: int = 4, iterations: int = 1):
         """X, Ud: (dim, n) marker positions / prescribed velocities; dV: (n,) volume weights (replicated on every rank)."""

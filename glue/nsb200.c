@@ -44,6 +44,8 @@ typedef struct {
   double   *bccache[6][2];
   PetscBool bcvalid[6][2], bc_time_independent;
   PetscBool ksp_monitor;           /* -ns_ksp_monitor: print the outer residual history of every step in PETSc's format */
+  PetscBool inner_monitor[2];      /* -ns_abf_momentum_ksp_monitor / -ns_abf_schur_ksp_monitor: every inner residual norm, as it is computed */
+  MPI_Comm  comm;                  /* for the monitor callback */
   PetscBool no_bcg_quirk, no_t_outlet_quirk; /* the two places where the reference's 3-D file differs from its 2-D file (include/fluca_b200.h):
                                                 default PETSC_FALSE = do what cnlinearcart3d.c does */
   /* coherence between ns->sol (host) and the device state */
@@ -294,8 +296,22 @@ static PetscErrorCode NSSetFromOptions_B200(NS ns, PetscOptionItems PetscOptions
   /* the reference prints residual histories through the KSP of its SNES (-ns_ksp_monitor); this type owns its
    * outer Krylov solver, reads the same option name and prints the same lines */
   PetscCall(PetscOptionsBool("-ns_ksp_monitor", "print the outer (coupled) residual history of every step", "KSPMonitorSet", b->ksp_monitor, &b->ksp_monitor, NULL));
+  /* ... and the KSPs of its PCABF under -ns_abf_momentum_ksp_monitor / -ns_abf_schur_ksp_monitor (abfpc.c:33-46): same names, same
+   * line format, printed as the inner solvers of the library go (fluca_b200_set_inner_monitor) */
+  PetscCall(PetscOptionsBool("-ns_abf_momentum_ksp_monitor", "print the residual norms of every momentum solve", "KSPMonitorSet", b->inner_monitor[0], &b->inner_monitor[0], NULL));
+  PetscCall(PetscOptionsBool("-ns_abf_schur_ksp_monitor", "print the residual norms of every pressure (Schur complement) solve", "KSPMonitorSet", b->inner_monitor[1], &b->inner_monitor[1], NULL));
   PetscOptionsHeadEnd();
   PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+/* fluca_b200_inner_monitor_fn: KSPMonitorResidual's lines at the tab level of a KSP inside a PC inside the KSP of the SNES.  Every
+ * rank gets the same calls with the same values; PetscPrintf prints on the first rank of the communicator. */
+static void B200InnerMonitor_Private(void *ctx, int which, int it, double rnorm)
+{
+  NS_B200 *b = (NS_B200 *)ctx;
+  if (!b->inner_monitor[which]) return;
+  if (it == 0) (void)PetscPrintf(b->comm, "    Residual norms for ns_abf_%s_ solve.\n", which ? "schur" : "momentum");
+  (void)PetscPrintf(b->comm, "    %3d KSP Residual norm %14.12e\n", it, rnorm);
 }
 
 /* NSSetUp builds a MatNest J and calls formjacobian(INIT) before ops->setup, then MatCreateVecs(J) (nsbasic.c:203-208).
@@ -402,6 +418,8 @@ static PetscErrorCode NSSetup_B200(NS ns)
   }
   B200Call(ns, fluca_b200_create(&desc, gcomm, &b->solver));
   if (b->schur_ainv != PC_ABF_AINV_ID || b->upper_ainv != PC_ABF_AINV_ID) B200Call(ns, fluca_b200_set_abf_ainv_types(b->solver, (int)b->schur_ainv, (int)b->upper_ainv)); /* same numeric values */
+  b->comm = comm;
+  if (b->inner_monitor[0] || b->inner_monitor[1]) B200Call(ns, fluca_b200_set_inner_monitor(b->solver, B200InnerMonitor_Private, b));
   for (d = 0; d < 3; ++d) PetscCall(PetscFree(xf[d]));
 
   b->ncell    = (size_t)m * n * b->nzl;

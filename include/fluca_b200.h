@@ -117,6 +117,14 @@ int fluca_b200_destroy(fluca_b200_solver *s);
 #define FLUCA_B200_AINV_ROWSUM 2 /* PC_ABF_AINV_ROWSUM */
 int fluca_b200_set_abf_ainv_types(fluca_b200_solver *s, int schur_type, int upper_type);
 
+/* ---- inner residual histories: the analogue of -ns_abf_momentum_ksp_monitor / -ns_abf_schur_ksp_monitor on the two KSPs of PCABF
+ * (abfpc.c:33-46,72,77).  fn is called on the host, from the thread that calls fluca_b200_step, once per residual norm the inner
+ * solvers evaluate anyway (no extra reduction, no extra synchronisation): which = 0 momentum, 1 Schur complement; it = 0 for the
+ * initial residual of a solve, then the iteration number; rnorm = 2-norm of the residual (all ranks see the same values).
+ * fn = NULL switches it off.  The callback must not call into the library. */
+typedef void (*fluca_b200_inner_monitor_fn)(void *ctx, int which, int it, double rnorm);
+int fluca_b200_set_inner_monitor(fluca_b200_solver *s, fluca_b200_inner_monitor_fn fn, void *ctx);
+
 /* ---- state: ns->sol sub-vectors Velocity / FaceNormalVelocity / Pressure + "PressureHalfStep" (cnlinear.c:54) ---- */
 /* host pointers; any argument may be NULL to skip that field */
 int fluca_b200_set_state(fluca_b200_solver *s, const double *v, const double *const U[3], const double *p, const double *phalf);

@@ -266,3 +266,37 @@ def test_a_stalled_inner_solve_is_reported(lib, monkeypatch):
     fb.NSStep(ns)
     assert fb.NSB200GetStats(ns).inner_unconverged == 0
     fb.NSDestroy(ns)
+
+
+def test_inner_monitor_reports_every_inner_residual(lib):
+    """fluca_b200_set_inner_monitor: the analogue of -ns_abf_momentum_ksp_monitor / -ns_abf_schur_ksp_monitor (abfpc.c:33-46).  Every
+    solve starts with it = 0, the iteration numbers of a solve run 1, 2, ... without gaps, the number of monitored iterations equals
+    the counts in the step statistics, the last norm of every solve is the one the statistics call mom/schur_last_rel times |b|, and
+    switching the monitor off stops the calls.  Closed (PCG) and open (BiCGStab) pressure systems."""
+    for case in (cases.cavity3d(n=(8, 8, 6)), cases.channel3d(n=(10, 6, 6), pout=0.2)):
+        ns = parity.make_ns(case, lib, "coupled")
+        parity.set_initial(ns, case.initial_state(seed=4))
+        seen = []
+        solver = fb.NSB200GetSolver(ns)
+        solver.set_inner_monitor(lambda which, it, rnorm: seen.append((which, it, rnorm)))
+        fb.NSStep(ns)
+        st = fb.NSB200GetStats(ns)
+        for which, total in ((0, st.mom_its), (1, st.schur_its)):
+            mine = [(it, r) for w, it, r in seen if w == which]
+            assert mine and mine[0][0] == 0
+            solves, cur = [], None
+            for it, r in mine:
+                if it == 0:
+                    cur = [r]
+                    solves.append(cur)
+                else:
+                    assert it == len(cur), (which, it, len(cur))  # consecutive within a solve
+                    cur.append(r)
+            assert sum(len(s) - 1 for s in solves) == total, (which, [len(s) - 1 for s in solves], total)
+            assert all(np.isfinite(r) and r >= 0 for s in solves for r in s)
+            assert all(s[-1] < s[0] for s in solves if len(s) > 1)
+        n = len(seen)
+        solver.set_inner_monitor(None)
+        fb.NSStep(ns)
+        assert len(seen) == n
+        fb.NSDestroy(ns)

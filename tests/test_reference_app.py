@@ -324,3 +324,34 @@ def test_the_references_application_restarts_across_types(tmp_path, first, secon
     a, b = load_dump(full), load_dump(cont)
     for k in ("Velocity", "FaceNormalVelocity", "Pressure", "PressureHalfStep"):
         assert np.abs(a[k] - b[k]).max() <= 1e-10 * np.abs(a[k]).max(), (k, np.abs(a[k] - b[k]).max() / np.abs(a[k]).max())
+
+
+@pytest.mark.skipif(not _ready("hostemu"), reason="oracle/_ref is not built here")
+def test_inner_ksp_monitors_under_the_references_option_names(tmp_path):
+    """-ns_abf_momentum_ksp_monitor / -ns_abf_schur_ksp_monitor (the KSPs of PCABF, abfpc.c:33-46) and -ns_ksp_monitor on a b200 run
+    inside the reference's program: KSPMonitorResidual's lines, one block per inner solve, as many iterations as the statistics count."""
+    args = ["-cart_grid_x", "8", "-cart_grid_y", "8", "-ns_time_step_size", "0.05", "-ns_max_steps", "2", "-ns_ksp_monitor", "-ns_abf_momentum_ksp_monitor", "-ns_abf_schur_ksp_monitor"]
+    r, _ = _program("cavity_flow_2d", args, tmp_path, "mon", True)
+    assert r.returncode == 0 and "options you set that were not used" not in r.stderr, r.stdout + r.stderr
+    out = r.stdout.splitlines()
+    blocks = {"momentum": 0, "schur": 0}
+    its = {"momentum": 0, "schur": 0}
+    cur = None
+    for ln in out:
+        if ln.startswith("    Residual norms for ns_abf_"):
+            cur = "momentum" if "momentum" in ln else "schur"
+            blocks[cur] += 1
+        elif ln.startswith("    ") and " KSP Residual norm " in ln and cur:
+            k = int(ln.split()[0])
+            its[cur] += k > 0
+        elif ln.startswith("  Residual norms for ns_ solve."):
+            cur = None
+    assert blocks["momentum"] >= 2 and blocks["schur"] >= 2
+    summary = [ln for ln in out if "ns_abf_momentum_ solves:" in ln]  # the per-step totals the outer monitor prints
+    assert len(summary) == 2
+    tot_m = sum(int(ln.split("ns_abf_momentum_ solves:")[1].split()[0]) for ln in summary)
+    tot_s = sum(int(ln.split("ns_abf_schur_ solves:")[1].split()[0]) for ln in summary)
+    assert (its["momentum"], its["schur"]) == (tot_m, tot_s), (its, tot_m, tot_s)
+    # without the options: silent
+    r, _ = _program("cavity_flow_2d", args[:8], tmp_path, "quiet", True)
+    assert "KSP Residual norm" not in r.stdout
