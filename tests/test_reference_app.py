@@ -125,7 +125,7 @@ def test_matrix_free_patch_compiled_into_the_references_base_class(tmp_path):
 
     tree = tmp_path / "patched"
     (tree / "fluca").mkdir(parents=True)
-    for sub in ("include", "src", "tests"):
+    for sub in ("include", "src", "tests", "app"):
         shutil.copytree(os.path.join("/root/reference/fluca", sub), tree / "fluca" / sub)
     r = subprocess.run(["patch", "-p1", "-i", os.path.join(ROOT, "glue", "patches", "0001-ns-matrix-free-type-hooks.patch")], cwd=tree, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
