@@ -55,6 +55,22 @@ typedef struct {
   fluca_b200_stats stats;
 } NS_B200;
 
+/* PETSc log events of the type (-log_view): the base class brackets the whole step with its own NSStep event (nsbasic.c:284-286);
+ * these split what this type adds around the device work -- the DMStag <-> compact-layout conversions with their host <-> device
+ * copies, and the evaluation + upload of the boundary callbacks. */
+static PetscLogEvent NSB200_HostToDevice = 0, NSB200_DeviceToHost = 0, NSB200_BoundaryData = 0, NSB200_DeviceStep = 0;
+static PetscErrorCode B200RegisterEvents_Private(void)
+{
+  PetscFunctionBegin;
+  if (!NSB200_DeviceStep) {
+    PetscCall(PetscLogEventRegister("NSB200HostToDevice", NS_CLASSID, &NSB200_HostToDevice));
+    PetscCall(PetscLogEventRegister("NSB200DeviceToHost", NS_CLASSID, &NSB200_DeviceToHost));
+    PetscCall(PetscLogEventRegister("NSB200BoundaryData", NS_CLASSID, &NSB200_BoundaryData));
+    PetscCall(PetscLogEventRegister("NSB200DeviceStep", NS_CLASSID, &NSB200_DeviceStep));
+  }
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
 #define B200Call(ns, call) \
   do { \
     int rc_ = (call); \
@@ -135,6 +151,7 @@ static PetscErrorCode B200HostToDevice_Private(NS ns)
   PetscInt d;
 
   PetscFunctionBegin;
+  PetscCall(PetscLogEventBegin(NSB200_HostToDevice, (PetscObject)ns, 0, 0, 0));
   PetscCall(MeshGetDM(ns->mesh, MESH_DM_SCALAR, &sdm));
   PetscCall(MeshGetDM(ns->mesh, MESH_DM_VECTOR, &vdm));
   PetscCall(MeshGetDM(ns->mesh, MESH_DM_STAG_SCALAR, &Sdm));
@@ -153,6 +170,7 @@ static PetscErrorCode B200HostToDevice_Private(NS ns)
     B200Call(ns, fluca_b200_set_state(b->solver, b->hv, U, b->hp, b->hph));
   }
   b->device_current = PETSC_TRUE;
+  PetscCall(PetscLogEventEnd(NSB200_HostToDevice, (PetscObject)ns, 0, 0, 0));
   PetscFunctionReturn(PETSC_SUCCESS);
 }
 
@@ -166,6 +184,7 @@ static PetscErrorCode B200DeviceToHost_Private(NS ns)
   const double *hv, *hU[3], *hp, *hph;
 
   PetscFunctionBegin;
+  PetscCall(PetscLogEventBegin(NSB200_DeviceToHost, (PetscObject)ns, 0, 0, 0));
   /* the library's own pinned buffers (fluca_b200_stage_state): full-rate DMA and no second host copy.  If the user staged
      the state earlier (NSB200StageSolution) the copy has been running behind the steps issued since. */
   if (!b->staged) B200Call(ns, fluca_b200_stage_state(b->solver));
@@ -190,6 +209,7 @@ static PetscErrorCode B200DeviceToHost_Private(NS ns)
   PetscCall(NSRestoreSolutionSubVector(ns, NS_FIELD_PRESSURE, &p));
   PetscCall(PetscObjectStateGet((PetscObject)ns->sol, &b->solstate));
   b->host_current = PETSC_TRUE;
+  PetscCall(PetscLogEventEnd(NSB200_DeviceToHost, (PetscObject)ns, 0, 0, 0));
   PetscFunctionReturn(PETSC_SUCCESS);
 }
 
@@ -205,6 +225,7 @@ static PetscErrorCode B200UploadBoundaryData_Private(NS ns)
   const PetscReal     tq = ns->step == 0 ? ns->t : ns->t - 0.5 * ns->dt;
 
   PetscFunctionBegin;
+  PetscCall(PetscLogEventBegin(NSB200_BoundaryData, (PetscObject)ns, 0, 0, 0));
   PetscCall(MeshGetDM(ns->mesh, MESH_DM_SCALAR, &sdm));
   PetscCall(DMStagGetCorners(sdm, &x, &y, &z, &m, &n, &p, NULL, NULL, NULL));
   PetscCall(DMStagGetProductCoordinateArraysRead(sdm, &ax, &ay, &az));
@@ -255,6 +276,7 @@ static PetscErrorCode B200UploadBoundaryData_Private(NS ns)
     }
   }
   PetscCall(DMStagRestoreProductCoordinateArraysRead(sdm, &ax, &ay, &az));
+  PetscCall(PetscLogEventEnd(NSB200_BoundaryData, (PetscObject)ns, 0, 0, 0));
   PetscFunctionReturn(PETSC_SUCCESS);
 }
 
@@ -455,7 +477,9 @@ static PetscErrorCode NSStep_B200(NS ns)
   if (!b->device_current || st != b->solstate) PetscCall(B200HostToDevice_Private(ns));
   PetscCall(B200UploadBoundaryData_Private(ns));
 
+  PetscCall(PetscLogEventBegin(NSB200_DeviceStep, (PetscObject)ns, 0, 0, 0));
   rc = fluca_b200_step(b->solver, (double)ns->t, (int)ns->step, &b->stats);
+  PetscCall(PetscLogEventEnd(NSB200_DeviceStep, (PetscObject)ns, 0, 0, 0));
   if (rc == FLUCA_B200_ERR_DIVERGED) {
     ns->reason = NS_DIVERGED_NONLINEAR_SOLVE; /* NSCheckDiverged (nsbasic.c:425-436); NSStep applies the failure policy (:293-297) */
     PetscFunctionReturn(PETSC_SUCCESS);
@@ -592,6 +616,7 @@ PetscErrorCode NSCreate_B200(NS ns)
   NS_B200 *b;
 
   PetscFunctionBegin;
+  PetscCall(B200RegisterEvents_Private());
   PetscCall(PetscNew(&b));
   ns->data = (void *)b;
   b->mode          = FLUCA_B200_MODE_COUPLED;

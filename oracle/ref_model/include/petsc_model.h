@@ -178,9 +178,11 @@ PetscErrorCode PetscStrcmp(const char[], const char[], PetscBool *);
 PetscErrorCode PetscStrallocpy(const char[], char **);
 PetscErrorCode PetscInfoModel(void *, const char *, ...);
 #define PetscInfo(obj, ...) PetscInfoModel((void *)(obj), __VA_ARGS__)
-static inline PetscErrorCode ModelLogNoop(void) { return PETSC_SUCCESS; }
-#define PetscLogEventBegin(e, a, b, c, d) ModelLogNoop()
-#define PetscLogEventEnd(e, a, b, c, d) ModelLogNoop()
+/* log events: timed (wall clock, inclusive) when PETSC_MODEL_TIMING is set and listed by PetscFinalize, otherwise free */
+PetscErrorCode ModelLogEventBegin(PetscLogEvent e);
+PetscErrorCode ModelLogEventEnd(PetscLogEvent e);
+#define PetscLogEventBegin(e, a, b, c, d) ModelLogEventBegin(e)
+#define PetscLogEventEnd(e, a, b, c, d) ModelLogEventEnd(e)
 #define PetscArraycpy(a, b, n) (memcpy((a), (b), (size_t)(n) * sizeof(*(a))), PETSC_SUCCESS)
 
 PetscErrorCode PetscPrintf(MPI_Comm, const char[], ...);

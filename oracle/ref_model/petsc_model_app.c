@@ -170,6 +170,7 @@ PetscErrorCode PetscRegisterFinalize(PetscErrorCode (*f)(void))
   finalizers[nfinalizers++] = f;
   return PETSC_SUCCESS;
 }
+static void events_report(FILE *f);
 PetscErrorCode PetscFinalize(void)
 {
   int i;
@@ -177,13 +178,54 @@ PetscErrorCode PetscFinalize(void)
   for (i = 0; i < nopts; ++i)
     if (!opts[i].used && strcmp(opts[i].name, "-dll_append")) fprintf(stderr, "WARNING! There are options you set that were not used! Option left: name:%s value: %s\n", opts[i].name, opts[i].value);
   ModelOptionsClear();
-  if (getenv("PETSC_MODEL_TIMING")) ModelTimingReport(stderr);
+  if (getenv("PETSC_MODEL_TIMING")) ModelTimingReport(stderr), events_report(stderr);
   initialized = 0, finalized = 1;
   return PETSC_SUCCESS;
 }
 static PetscClassId next_classid = 1000;
 PetscErrorCode PetscClassIdRegister(const char name[], PetscClassId *id) { return (void)name, *id = next_classid++, PETSC_SUCCESS; }
-PetscErrorCode PetscLogEventRegister(const char name[], PetscClassId c, PetscLogEvent *e) { return (void)name, (void)c, *e = next_classid++, PETSC_SUCCESS; }
+enum { MAX_EVENTS = 64 };
+static struct {
+  int    id;
+  char   name[48];
+  double t0, sum;
+  long   calls;
+} events[MAX_EVENTS];
+static int nevents = 0, events_on = -1;
+PetscErrorCode PetscLogEventRegister(const char name[], PetscClassId c, PetscLogEvent *e)
+{
+  (void)c;
+  *e = next_classid++;
+  if (nevents < MAX_EVENTS) events[nevents].id = *e, snprintf(events[nevents].name, sizeof(events[nevents].name), "%s", name), ++nevents;
+  return PETSC_SUCCESS;
+}
+static int event_slot(PetscLogEvent e)
+{
+  int i;
+  if (events_on < 0) events_on = getenv("PETSC_MODEL_TIMING") ? 1 : 0;
+  if (!events_on) return -1;
+  for (i = 0; i < nevents; ++i)
+    if (events[i].id == e) return i;
+  return -1;
+}
+PetscErrorCode ModelLogEventBegin(PetscLogEvent e)
+{
+  const int i = event_slot(e);
+  if (i >= 0) events[i].t0 = ModelWallTime();
+  return PETSC_SUCCESS;
+}
+PetscErrorCode ModelLogEventEnd(PetscLogEvent e)
+{
+  const int i = event_slot(e);
+  if (i >= 0) events[i].sum += ModelWallTime() - events[i].t0, ++events[i].calls;
+  return PETSC_SUCCESS;
+}
+static void events_report(FILE *f)
+{
+  int i;
+  for (i = 0; i < nevents; ++i)
+    if (events[i].calls) fprintf(f, "[PETSc model timing] event %-22s %8ld calls %10.3f s\n", events[i].name, events[i].calls, events[i].sum);
+}
 PetscErrorCode PetscInfoProcessClass(const char n[], PetscInt k, PetscClassId ids[]) { return (void)n, (void)k, (void)ids, PETSC_SUCCESS; }
 PetscErrorCode PetscLogEventExcludeClass(PetscClassId c) { return (void)c, PETSC_SUCCESS; }
 

@@ -42,6 +42,9 @@ typedef struct _n_PetscFunctionList *PetscFunctionList;
 typedef struct _p_PetscViewerAndFormat PetscViewerAndFormat;
 typedef int PetscClassId;
 typedef int PetscLogEvent;
+#define PetscLogEventRegister(name, classid, e) (*(e) = 1, PETSC_SUCCESS) /* -log_view is PETSc's; the mock has no profiler */
+#define PetscLogEventBegin(e, a, b, c, d) PETSC_SUCCESS
+#define PetscLogEventEnd(e, a, b, c, d) PETSC_SUCCESS
 typedef enum { INSERT_VALUES = 1, ADD_VALUES = 2 } InsertMode;
 typedef enum { MAT_FLUSH_ASSEMBLY = 1, MAT_FINAL_ASSEMBLY = 0 } MatAssemblyType;
 typedef enum { DMSTAG_NULL_LOCATION, DMSTAG_BACK_DOWN_LEFT, DMSTAG_BACK_DOWN, DMSTAG_BACK_DOWN_RIGHT, DMSTAG_BACK_LEFT, DMSTAG_BACK, DMSTAG_BACK_RIGHT, DMSTAG_BACK_UP_LEFT, DMSTAG_BACK_UP, DMSTAG_BACK_UP_RIGHT, DMSTAG_DOWN_LEFT, DMSTAG_DOWN, DMSTAG_DOWN_RIGHT, DMSTAG_LEFT, DMSTAG_ELEMENT, DMSTAG_RIGHT } DMStagStencilLocation;

@@ -355,3 +355,22 @@ def test_inner_ksp_monitors_under_the_references_option_names(tmp_path):
     # without the options: silent
     r, _ = _program("cavity_flow_2d", args[:8], tmp_path, "quiet", True)
     assert "KSP Residual norm" not in r.stdout
+
+
+@pytest.mark.skipif(not _ready("hostemu"), reason="oracle/_ref is not built here")
+def test_log_events_of_the_type_show_next_to_the_references(tmp_path):
+    """The glue registers PETSc log events for what it adds around the device work (NSB200HostToDevice / DeviceToHost / BoundaryData /
+    DeviceStep); with the model's stand-in for -log_view (PETSC_MODEL_TIMING) they are listed next to the reference's own NSSetUp /
+    NSStep events: one upload of the initial state, one download per step at the default sync interval, none with
+    -ns_b200_sync_interval 0 until a viewer asks."""
+    def events(extra):
+        cmd = [os.path.join(REFDIR, "cavity_flow_2d"), "-cart_grid_x", "12", "-cart_grid_y", "12", "-ns_time_step_size", "0.04", "-ns_max_steps", "4",
+               "-dll_append", os.path.join(REFDIR, "hostemu", "libfluca_nsb200.so"), "-ns_type", "b200"] + extra
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, PETSC_MODEL_TIMING="1"))
+        assert r.returncode == 0, r.stdout + r.stderr
+        return {ln.split()[4]: int(ln.split()[5]) for ln in r.stderr.splitlines() if ln.startswith("[PETSc model timing] event")}
+
+    ev = events([])
+    assert ev["NSStep"] == 4 and ev["NSB200DeviceStep"] == 4 and ev["NSB200HostToDevice"] == 1 and ev["NSB200DeviceToHost"] == 4 and ev["NSB200BoundaryData"] == 4, ev
+    ev = events(["-ns_b200_sync_interval", "0"])
+    assert ev["NSB200DeviceStep"] == 4 and "NSB200DeviceToHost" not in ev, ev  # nothing observes ns->sol: it stays on the device
