@@ -80,63 +80,90 @@ static PetscErrorCode B200RegisterEvents_Private(void)
 /* ------------------------------------------------------------------ DMStag <-> C-ABI layout
  * Per-element entry order and the extra faces of the last rank are DMStag's business: everything goes through
  * DMStagVecGetArray + DMStagGetLocationSlot (SURVEY.md 8b "do not assume raw DMStag global ordering"). */
-static PetscErrorCode B200Upload_Private(DM dm, Vec g, DMStagStencilLocation loc, PetscInt c, PetscInt ex, PetscInt ey, PetscInt ez, double *host)
+typedef struct {
+  DMStagStencilLocation loc;        /* where the entry lives in its element */
+  PetscInt              c;          /* component at that location */
+  PetscInt              ex, ey, ez; /* one more entry in x / y / z than there are cells (the face layer of the last rank) */
+  double               *host;       /* compact array of the C ABI (x fastest) */
+} B200Slot;
+
+/* One DMGlobalToLocal and one array access per DM and Vec, however many slots are read from it (velocity: dim components, face-normal
+ * velocity: dim face locations): at 512^3 each pass over a local vector is gigabytes of host traffic. */
+static PetscErrorCode B200Upload_Private(DM dm, Vec g, PetscInt nslots, const B200Slot sl[])
 {
-  PetscInt x, y, z, m, n, p, dim, slot, i, j, k;
+  PetscInt x, y, z, m, n, p, dim, slot, i, j, k, q;
   Vec      l;
 
   PetscFunctionBegin;
   PetscCall(DMGetDimension(dm, &dim));
   PetscCall(DMStagGetCorners(dm, &x, &y, &z, &m, &n, &p, NULL, NULL, NULL));
-  PetscCall(DMStagGetLocationSlot(dm, loc, c, &slot));
   PetscCall(DMGetLocalVector(dm, &l));
   PetscCall(DMGlobalToLocal(dm, g, INSERT_VALUES, l));
   if (dim == 2) {
     const PetscScalar ***a;
     PetscCall(DMStagVecGetArrayRead(dm, l, &a));
-    for (j = 0; j < n + ey; ++j)
-      for (i = 0; i < m + ex; ++i) host[i + (size_t)(m + ex) * j] = PetscRealPart(a[y + j][x + i][slot]);
+    for (q = 0; q < nslots; ++q) {
+      const PetscInt mm = m + sl[q].ex, nn = n + sl[q].ey;
+      double        *host = sl[q].host;
+      PetscCall(DMStagGetLocationSlot(dm, sl[q].loc, sl[q].c, &slot));
+      for (j = 0; j < nn; ++j)
+        for (i = 0; i < mm; ++i) host[i + (size_t)mm * j] = PetscRealPart(a[y + j][x + i][slot]);
+    }
     PetscCall(DMStagVecRestoreArrayRead(dm, l, &a));
   } else {
     const PetscScalar ****a;
     PetscCall(DMStagVecGetArrayRead(dm, l, &a));
-    for (k = 0; k < p + ez; ++k)
-      for (j = 0; j < n + ey; ++j)
-        for (i = 0; i < m + ex; ++i) host[i + (size_t)(m + ex) * (j + (size_t)(n + ey) * k)] = PetscRealPart(a[z + k][y + j][x + i][slot]);
+    for (q = 0; q < nslots; ++q) {
+      const PetscInt mm = m + sl[q].ex, nn = n + sl[q].ey, pp = p + sl[q].ez;
+      double        *host = sl[q].host;
+      PetscCall(DMStagGetLocationSlot(dm, sl[q].loc, sl[q].c, &slot));
+      for (k = 0; k < pp; ++k)
+        for (j = 0; j < nn; ++j)
+          for (i = 0; i < mm; ++i) host[i + (size_t)mm * (j + (size_t)nn * k)] = PetscRealPart(a[z + k][y + j][x + i][slot]);
+    }
     PetscCall(DMStagVecRestoreArrayRead(dm, l, &a));
   }
   PetscCall(DMRestoreLocalVector(dm, &l));
   PetscFunctionReturn(PETSC_SUCCESS);
 }
 
-/* One local round trip per slot: this runs only when a host observer needs ns->sol, so clarity wins.  The slots of
- * one Vec are accumulated with ADD_VALUES (every entry is owned by exactly one rank): the caller zeroes the Vec first. */
-static PetscErrorCode B200Download_Private(DM dm, Vec g, DMStagStencilLocation loc, PetscInt c, PetscInt ex, PetscInt ey, PetscInt ez, const double *host)
+/* The reverse: all slots of one Vec are written into ONE local vector, and one DMLocalToGlobal with INSERT_VALUES moves the owned
+ * entries (every entry of these DMs is one of the slots, and is owned by exactly one rank: nothing of g keeps an old value). */
+static PetscErrorCode B200Download_Private(DM dm, Vec g, PetscInt nslots, const B200Slot sl[])
 {
-  PetscInt x, y, z, m, n, p, dim, slot, i, j, k;
+  PetscInt x, y, z, m, n, p, dim, slot, i, j, k, q;
   Vec      l;
 
   PetscFunctionBegin;
   PetscCall(DMGetDimension(dm, &dim));
   PetscCall(DMStagGetCorners(dm, &x, &y, &z, &m, &n, &p, NULL, NULL, NULL));
-  PetscCall(DMStagGetLocationSlot(dm, loc, c, &slot));
   PetscCall(DMGetLocalVector(dm, &l));
-  PetscCall(VecZeroEntries(l));
+  PetscCall(VecZeroEntries(l)); /* ghost entries and the entries a partial element does not have */
   if (dim == 2) {
     PetscScalar ***a;
     PetscCall(DMStagVecGetArray(dm, l, &a));
-    for (j = 0; j < n + ey; ++j)
-      for (i = 0; i < m + ex; ++i) a[y + j][x + i][slot] = host[i + (size_t)(m + ex) * j];
+    for (q = 0; q < nslots; ++q) {
+      const PetscInt mm = m + sl[q].ex, nn = n + sl[q].ey;
+      const double  *host = sl[q].host;
+      PetscCall(DMStagGetLocationSlot(dm, sl[q].loc, sl[q].c, &slot));
+      for (j = 0; j < nn; ++j)
+        for (i = 0; i < mm; ++i) a[y + j][x + i][slot] = host[i + (size_t)mm * j];
+    }
     PetscCall(DMStagVecRestoreArray(dm, l, &a));
   } else {
     PetscScalar ****a;
     PetscCall(DMStagVecGetArray(dm, l, &a));
-    for (k = 0; k < p + ez; ++k)
-      for (j = 0; j < n + ey; ++j)
-        for (i = 0; i < m + ex; ++i) a[z + k][y + j][x + i][slot] = host[i + (size_t)(m + ex) * (j + (size_t)(n + ey) * k)];
+    for (q = 0; q < nslots; ++q) {
+      const PetscInt mm = m + sl[q].ex, nn = n + sl[q].ey, pp = p + sl[q].ez;
+      const double  *host = sl[q].host;
+      PetscCall(DMStagGetLocationSlot(dm, sl[q].loc, sl[q].c, &slot));
+      for (k = 0; k < pp; ++k)
+        for (j = 0; j < nn; ++j)
+          for (i = 0; i < mm; ++i) a[z + k][y + j][x + i][slot] = host[i + (size_t)mm * (j + (size_t)nn * k)];
+    }
     PetscCall(DMStagVecRestoreArray(dm, l, &a));
   }
-  PetscCall(DMLocalToGlobal(dm, l, ADD_VALUES, g));
+  PetscCall(DMLocalToGlobal(dm, l, INSERT_VALUES, g));
   PetscCall(DMRestoreLocalVector(dm, &l));
   PetscFunctionReturn(PETSC_SUCCESS);
 }
@@ -158,10 +185,18 @@ static PetscErrorCode B200HostToDevice_Private(NS ns)
   PetscCall(NSGetSolutionSubVector(ns, NS_FIELD_VELOCITY, &v));
   PetscCall(NSGetSolutionSubVector(ns, NS_FIELD_FACE_NORMAL_VELOCITY, &V));
   PetscCall(NSGetSolutionSubVector(ns, NS_FIELD_PRESSURE, &p));
-  for (d = 0; d < b->dim; ++d) PetscCall(B200Upload_Private(vdm, v, DMSTAG_ELEMENT, d, 0, 0, 0, b->hv + b->ncell * d));
-  for (d = 0; d < b->dim; ++d) PetscCall(B200Upload_Private(Sdm, V, B200FaceLoc[d], 0, d == 0 && !b->per[0], d == 1 && !b->per[1], d == 2 && b->lastz, b->hU[d]));
-  PetscCall(B200Upload_Private(sdm, p, DMSTAG_ELEMENT, 0, 0, 0, 0, b->hp));
-  PetscCall(B200Upload_Private(sdm, b->phalf, DMSTAG_ELEMENT, 0, 0, 0, 0, b->hph));
+  {
+    B200Slot sv[3], sU[3], sp = {DMSTAG_ELEMENT, 0, 0, 0, 0, b->hp}, sph = {DMSTAG_ELEMENT, 0, 0, 0, 0, b->hph};
+    for (d = 0; d < b->dim; ++d) {
+      const B200Slot cv = {DMSTAG_ELEMENT, d, 0, 0, 0, b->hv + b->ncell * d};
+      const B200Slot cU = {B200FaceLoc[d], 0, d == 0 && !b->per[0], d == 1 && !b->per[1], d == 2 && b->lastz, b->hU[d]};
+      sv[d] = cv, sU[d] = cU;
+    }
+    PetscCall(B200Upload_Private(vdm, v, b->dim, sv));
+    PetscCall(B200Upload_Private(Sdm, V, b->dim, sU));
+    PetscCall(B200Upload_Private(sdm, p, 1, &sp));
+    PetscCall(B200Upload_Private(sdm, b->phalf, 1, &sph));
+  }
   PetscCall(NSRestoreSolutionSubVector(ns, NS_FIELD_VELOCITY, &v));
   PetscCall(NSRestoreSolutionSubVector(ns, NS_FIELD_FACE_NORMAL_VELOCITY, &V));
   PetscCall(NSRestoreSolutionSubVector(ns, NS_FIELD_PRESSURE, &p));
@@ -196,14 +231,18 @@ static PetscErrorCode B200DeviceToHost_Private(NS ns)
   PetscCall(NSGetSolutionSubVector(ns, NS_FIELD_VELOCITY, &v));
   PetscCall(NSGetSolutionSubVector(ns, NS_FIELD_FACE_NORMAL_VELOCITY, &V));
   PetscCall(NSGetSolutionSubVector(ns, NS_FIELD_PRESSURE, &p));
-  PetscCall(VecZeroEntries(v));
-  PetscCall(VecZeroEntries(V));
-  PetscCall(VecZeroEntries(p));
-  PetscCall(VecZeroEntries(b->phalf));
-  for (d = 0; d < b->dim; ++d) PetscCall(B200Download_Private(vdm, v, DMSTAG_ELEMENT, d, 0, 0, 0, hv + b->ncell * d));
-  for (d = 0; d < b->dim; ++d) PetscCall(B200Download_Private(Sdm, V, B200FaceLoc[d], 0, d == 0 && !b->per[0], d == 1 && !b->per[1], d == 2 && b->lastz, hU[d]));
-  PetscCall(B200Download_Private(sdm, p, DMSTAG_ELEMENT, 0, 0, 0, 0, hp));
-  PetscCall(B200Download_Private(sdm, b->phalf, DMSTAG_ELEMENT, 0, 0, 0, 0, hph));
+  {
+    B200Slot sv[3], sU[3], sp = {DMSTAG_ELEMENT, 0, 0, 0, 0, (double *)hp}, sph = {DMSTAG_ELEMENT, 0, 0, 0, 0, (double *)hph}; /* read only */
+    for (d = 0; d < b->dim; ++d) {
+      const B200Slot cv = {DMSTAG_ELEMENT, d, 0, 0, 0, (double *)hv + b->ncell * d};
+      const B200Slot cU = {B200FaceLoc[d], 0, d == 0 && !b->per[0], d == 1 && !b->per[1], d == 2 && b->lastz, (double *)hU[d]};
+      sv[d] = cv, sU[d] = cU;
+    }
+    PetscCall(B200Download_Private(vdm, v, b->dim, sv));
+    PetscCall(B200Download_Private(Sdm, V, b->dim, sU));
+    PetscCall(B200Download_Private(sdm, p, 1, &sp));
+    PetscCall(B200Download_Private(sdm, b->phalf, 1, &sph));
+  }
   PetscCall(NSRestoreSolutionSubVector(ns, NS_FIELD_VELOCITY, &v));
   PetscCall(NSRestoreSolutionSubVector(ns, NS_FIELD_FACE_NORMAL_VELOCITY, &V));
   PetscCall(NSRestoreSolutionSubVector(ns, NS_FIELD_PRESSURE, &p));
@@ -539,12 +578,17 @@ static PetscErrorCode NSFormFunction_B200(NS ns, Vec x, Vec f)
   PetscCall(VecGetSubVector(f, vis, &fv));
   PetscCall(VecGetSubVector(f, Vis, &fV));
   PetscCall(VecGetSubVector(f, pis, &fp));
-  PetscCall(VecZeroEntries(fv));
-  PetscCall(VecZeroEntries(fV));
-  PetscCall(VecZeroEntries(fp));
-  for (d = 0; d < b->dim; ++d) PetscCall(B200Download_Private(vdm, fv, DMSTAG_ELEMENT, d, 0, 0, 0, b->hv + b->ncell * d));
-  for (d = 0; d < b->dim; ++d) PetscCall(B200Download_Private(Sdm, fV, B200FaceLoc[d], 0, d == 0 && !b->per[0], d == 1 && !b->per[1], d == 2 && b->lastz, b->hU[d]));
-  PetscCall(B200Download_Private(sdm, fp, DMSTAG_ELEMENT, 0, 0, 0, 0, b->hp));
+  {
+    B200Slot sv[3], sU[3], sp = {DMSTAG_ELEMENT, 0, 0, 0, 0, b->hp};
+    for (d = 0; d < b->dim; ++d) {
+      const B200Slot cv = {DMSTAG_ELEMENT, d, 0, 0, 0, b->hv + b->ncell * d};
+      const B200Slot cU = {B200FaceLoc[d], 0, d == 0 && !b->per[0], d == 1 && !b->per[1], d == 2 && b->lastz, b->hU[d]};
+      sv[d] = cv, sU[d] = cU;
+    }
+    PetscCall(B200Download_Private(vdm, fv, b->dim, sv));
+    PetscCall(B200Download_Private(Sdm, fV, b->dim, sU));
+    PetscCall(B200Download_Private(sdm, fp, 1, &sp));
+  }
   PetscCall(VecRestoreSubVector(f, vis, &fv));
   PetscCall(VecRestoreSubVector(f, Vis, &fV));
   PetscCall(VecRestoreSubVector(f, pis, &fp));
