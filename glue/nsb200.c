@@ -91,12 +91,18 @@ typedef struct {
  * velocity: dim face locations): at 512^3 each pass over a local vector is gigabytes of host traffic. */
 static PetscErrorCode B200Upload_Private(DM dm, Vec g, PetscInt nslots, const B200Slot sl[])
 {
-  PetscInt x, y, z, m, n, p, dim, slot, i, j, k, q;
-  Vec      l;
+  PetscInt  x, y, z, m, n, p, dim, slot, i, j, k, q, slots[3];
+  PetscBool same = PETSC_TRUE; /* all slots cover the same index range */
+  Vec       l;
 
   PetscFunctionBegin;
   PetscCall(DMGetDimension(dm, &dim));
   PetscCall(DMStagGetCorners(dm, &x, &y, &z, &m, &n, &p, NULL, NULL, NULL));
+  PetscCheck(nslots >= 1 && nslots <= 3, PetscObjectComm((PetscObject)dm), PETSC_ERR_ARG_WRONG, "1 to 3 slots");
+  for (q = 0; q < nslots; ++q) {
+    PetscCall(DMStagGetLocationSlot(dm, sl[q].loc, sl[q].c, &slots[q]));
+    if (sl[q].ex != sl[0].ex || sl[q].ey != sl[0].ey || sl[q].ez != sl[0].ez) same = PETSC_FALSE;
+  }
   PetscCall(DMGetLocalVector(dm, &l));
   PetscCall(DMGlobalToLocal(dm, g, INSERT_VALUES, l));
   if (dim == 2) {
@@ -105,7 +111,7 @@ static PetscErrorCode B200Upload_Private(DM dm, Vec g, PetscInt nslots, const B2
     for (q = 0; q < nslots; ++q) {
       const PetscInt mm = m + sl[q].ex, nn = n + sl[q].ey;
       double        *host = sl[q].host;
-      PetscCall(DMStagGetLocationSlot(dm, sl[q].loc, sl[q].c, &slot));
+      slot = slots[q];
       for (j = 0; j < nn; ++j)
         for (i = 0; i < mm; ++i) host[i + (size_t)mm * j] = PetscRealPart(a[y + j][x + i][slot]);
     }
@@ -113,14 +119,23 @@ static PetscErrorCode B200Upload_Private(DM dm, Vec g, PetscInt nslots, const B2
   } else {
     const PetscScalar ****a;
     PetscCall(DMStagVecGetArrayRead(dm, l, &a));
-    for (q = 0; q < nslots; ++q) {
-      const PetscInt mm = m + sl[q].ex, nn = n + sl[q].ey, pp = p + sl[q].ez;
-      double        *host = sl[q].host;
-      PetscCall(DMStagGetLocationSlot(dm, sl[q].loc, sl[q].c, &slot));
-      for (k = 0; k < pp; ++k)
-        for (j = 0; j < nn; ++j)
-          for (i = 0; i < mm; ++i) host[i + (size_t)mm * (j + (size_t)nn * k)] = PetscRealPart(a[z + k][y + j][x + i][slot]);
-    }
+    if (same) { /* the components of one element are neighbours in memory: one pass over the local array for all of them */
+      for (k = 0; k < p + sl[0].ez; ++k)
+        for (j = 0; j < n + sl[0].ey; ++j)
+          for (i = 0; i < m + sl[0].ex; ++i) {
+            const PetscScalar *e = a[z + k][y + j][x + i];
+            const size_t       o = i + (size_t)(m + sl[0].ex) * (j + (size_t)(n + sl[0].ey) * k);
+            for (q = 0; q < nslots; ++q) sl[q].host[o] = PetscRealPart(e[slots[q]]);
+          }
+    } else
+      for (q = 0; q < nslots; ++q) {
+        const PetscInt mm = m + sl[q].ex, nn = n + sl[q].ey, pp = p + sl[q].ez;
+        double        *host = sl[q].host;
+        slot = slots[q];
+        for (k = 0; k < pp; ++k)
+          for (j = 0; j < nn; ++j)
+            for (i = 0; i < mm; ++i) host[i + (size_t)mm * (j + (size_t)nn * k)] = PetscRealPart(a[z + k][y + j][x + i][slot]);
+      }
     PetscCall(DMStagVecRestoreArrayRead(dm, l, &a));
   }
   PetscCall(DMRestoreLocalVector(dm, &l));
@@ -131,12 +146,18 @@ static PetscErrorCode B200Upload_Private(DM dm, Vec g, PetscInt nslots, const B2
  * entries (every entry of these DMs is one of the slots, and is owned by exactly one rank: nothing of g keeps an old value). */
 static PetscErrorCode B200Download_Private(DM dm, Vec g, PetscInt nslots, const B200Slot sl[])
 {
-  PetscInt x, y, z, m, n, p, dim, slot, i, j, k, q;
-  Vec      l;
+  PetscInt  x, y, z, m, n, p, dim, slot, i, j, k, q, slots[3];
+  PetscBool same = PETSC_TRUE; /* all slots cover the same index range */
+  Vec       l;
 
   PetscFunctionBegin;
   PetscCall(DMGetDimension(dm, &dim));
   PetscCall(DMStagGetCorners(dm, &x, &y, &z, &m, &n, &p, NULL, NULL, NULL));
+  PetscCheck(nslots >= 1 && nslots <= 3, PetscObjectComm((PetscObject)dm), PETSC_ERR_ARG_WRONG, "1 to 3 slots");
+  for (q = 0; q < nslots; ++q) {
+    PetscCall(DMStagGetLocationSlot(dm, sl[q].loc, sl[q].c, &slots[q]));
+    if (sl[q].ex != sl[0].ex || sl[q].ey != sl[0].ey || sl[q].ez != sl[0].ez) same = PETSC_FALSE;
+  }
   PetscCall(DMGetLocalVector(dm, &l));
   PetscCall(VecZeroEntries(l)); /* ghost entries and the entries a partial element does not have */
   if (dim == 2) {
@@ -145,7 +166,7 @@ static PetscErrorCode B200Download_Private(DM dm, Vec g, PetscInt nslots, const 
     for (q = 0; q < nslots; ++q) {
       const PetscInt mm = m + sl[q].ex, nn = n + sl[q].ey;
       const double  *host = sl[q].host;
-      PetscCall(DMStagGetLocationSlot(dm, sl[q].loc, sl[q].c, &slot));
+      slot = slots[q];
       for (j = 0; j < nn; ++j)
         for (i = 0; i < mm; ++i) a[y + j][x + i][slot] = host[i + (size_t)mm * j];
     }
@@ -153,14 +174,23 @@ static PetscErrorCode B200Download_Private(DM dm, Vec g, PetscInt nslots, const 
   } else {
     PetscScalar ****a;
     PetscCall(DMStagVecGetArray(dm, l, &a));
-    for (q = 0; q < nslots; ++q) {
-      const PetscInt mm = m + sl[q].ex, nn = n + sl[q].ey, pp = p + sl[q].ez;
-      const double  *host = sl[q].host;
-      PetscCall(DMStagGetLocationSlot(dm, sl[q].loc, sl[q].c, &slot));
-      for (k = 0; k < pp; ++k)
-        for (j = 0; j < nn; ++j)
-          for (i = 0; i < mm; ++i) a[z + k][y + j][x + i][slot] = host[i + (size_t)mm * (j + (size_t)nn * k)];
-    }
+    if (same) {
+      for (k = 0; k < p + sl[0].ez; ++k)
+        for (j = 0; j < n + sl[0].ey; ++j)
+          for (i = 0; i < m + sl[0].ex; ++i) {
+            PetscScalar *e = a[z + k][y + j][x + i];
+            const size_t o = i + (size_t)(m + sl[0].ex) * (j + (size_t)(n + sl[0].ey) * k);
+            for (q = 0; q < nslots; ++q) e[slots[q]] = sl[q].host[o];
+          }
+    } else
+      for (q = 0; q < nslots; ++q) {
+        const PetscInt mm = m + sl[q].ex, nn = n + sl[q].ey, pp = p + sl[q].ez;
+        const double  *host = sl[q].host;
+        slot = slots[q];
+        for (k = 0; k < pp; ++k)
+          for (j = 0; j < nn; ++j)
+            for (i = 0; i < mm; ++i) a[z + k][y + j][x + i][slot] = host[i + (size_t)mm * (j + (size_t)nn * k)];
+      }
     PetscCall(DMStagVecRestoreArray(dm, l, &a));
   }
   PetscCall(DMLocalToGlobal(dm, l, INSERT_VALUES, g));
