@@ -19,6 +19,7 @@ options, the time loop (nsbasic.c:325-351), monitors (nsmon.c), failure policy
 from __future__ import annotations
 
 import math
+import sys
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional, Sequence
 
@@ -472,6 +473,18 @@ def _b200_setup(ns: NS):
         ainv.append(_lib.AINV_NAMES[name])
     if any(ainv):
         dat.solver.set_abf_ainv_types(*ainv)
+    # -ns_abf_momentum_ksp_monitor / -ns_abf_schur_ksp_monitor (the KSPs of PCABF, abfpc.c:33-46): KSPMonitorResidual's lines on rank 0
+    want = (bool(o.get("ns_abf_momentum_ksp_monitor")), bool(o.get("ns_abf_schur_ksp_monitor")))
+    if any(want) and rank == 0:
+        out = o.get("ns_monitor_file", sys.stdout)
+
+        def _inner(which, it, rnorm):
+            if want[which]:
+                if it == 0:
+                    print(f"    Residual norms for ns_abf_{'schur' if which else 'momentum'}_ solve.", file=out)
+                print(f"    {it:3d} KSP Residual norm {rnorm:14.12e}", file=out)
+
+        dat.solver.set_inner_monitor(_inner)
     dat.pts = [_boundary_points(mesh, dat.solver, b) for b in range(2 * mesh.dim)]
     dat.bc_cache = {}
     dat.history = []

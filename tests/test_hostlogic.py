@@ -300,3 +300,19 @@ def test_inner_monitor_reports_every_inner_residual(lib):
         fb.NSStep(ns)
         assert len(seen) == n
         fb.NSDestroy(ns)
+
+
+def test_inner_ksp_monitor_options_of_the_ns_mirror(lib):
+    """-ns_abf_schur_ksp_monitor through the NS mirror: the same lines the C glue prints (KSPMonitorResidual's format)."""
+    import io
+
+    case = cases.cavity2d(n=12)
+    buf = io.StringIO()
+    ns = parity.make_ns(case, lib, "fractional", ns_abf_schur_ksp_monitor=True, ns_monitor_file=buf)
+    parity.set_initial(ns, case.initial_state(seed=2))
+    fb.NSStep(ns)
+    st = fb.NSB200GetStats(ns)
+    fb.NSDestroy(ns)
+    lines = buf.getvalue().splitlines()
+    assert lines[0] == "    Residual norms for ns_abf_schur_ solve." and not any("momentum" in ln for ln in lines)
+    assert sum(1 for ln in lines if " KSP Residual norm " in ln and int(ln.split()[0]) > 0) == st.schur_its
